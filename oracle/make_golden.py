@@ -1,0 +1,170 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (under oracle/ref_shim.py)
+on seeded synthetic inputs.  Run in the authoring container only:
+
+    python -m oracle.make_golden
+
+TEST INFRASTRUCTURE ONLY.  The golden files are what the GPU box (no /root/reference) checks
+the oracle restatement and the CUDA path against.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim, state_spec  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+SPARSE_FRAMES = [0, 1, 2, 3, 100, 200, 397, 398, 399, 400]
+
+
+def ref_lfcc(wave):
+    fe = ref_shim.load("feature_extraction")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mod = fe.LFCC(320, 160, 512, 16000, 20, with_energy=False)
+        return mod(wave.clone()), mod      # the reference mutates its input in place
+
+
+def golden_lfcc():
+    out = {}
+    # config[0]: 32 seeded 4 s waves + 3 edge rows
+    w = state_spec.seeded_waves(32, 64000, seed=0, edge_rows=True)
+    y, mod = ref_lfcc(w)
+    y = y.numpy()
+    out["full_rows"] = np.array([0, 1, 2, 31, 32, 33, 34])
+    out["full"] = y[out["full_rows"]]
+    out["sparse_frames"] = np.array(SPARSE_FRAMES)
+    out["sparse"] = y[:, SPARSE_FRAMES, :]
+    out["colsum"] = y.astype(np.float64).sum(axis=1)           # (35,60) checksum over frames
+    out["lfcc_fb"] = mod.lfcc_fb.detach().numpy()
+    out["dct_weight"] = mod.l_dct.weight.detach().numpy()
+    # ragged lengths: T = 1 + L//160
+    for L in (3200, 12345, 160 * 37, 160 * 37 + 159, 321, 800):
+        wl = state_spec.seeded_waves(2, L, seed=L)
+        out["ragged_%d" % L] = ref_lfcc(wl)[0].numpy()
+    # the silence vector of dataset.py:13-16
+    out["silence"] = ref_lfcc(torch.zeros(1, 3200))[0][:, 0, :].numpy()
+    np.savez_compressed(os.path.join(GOLD, "lfcc_golden.npz"), **out)
+    print("lfcc_golden.npz", {k: v.shape for k, v in out.items()})
+
+
+def golden_padcrop():
+    """Run the reference's own pad helpers (dataset.py:513-528) on index-valued tensors."""
+    import importlib.util
+    # dataset.py imports librosa + builds an LFCC at import: fine under the shim
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ds = ref_shim.load("dataset")
+    out = {}
+    for T in (1, 21, 401, 749):
+        spec = torch.arange(T, dtype=torch.float32).reshape(1, T, 1).repeat(1, 1, 60)
+        out["repeat_%d" % T] = ds.repeat_padding_Tensor(spec, 750)[0, :, 0].numpy().astype(np.int64)
+        z = ds.padding_Tensor(spec + 1, 750)[0, :, 0].numpy().astype(np.int64) - 1   # -1 where zero
+        out["zero_%d" % T] = z
+        s = ds.silence_padding_Tensor(spec + 1000, 750)[0, :, 0].numpy()
+        out["silence_%d" % T] = s       # silence rows carry c0 of the silence vector (< 0)
+    out["silence_pad_value"] = ds.silence_pad_value.numpy()
+    np.savez_compressed(os.path.join(GOLD, "padcrop_golden.npz"), **out)
+    print("padcrop_golden.npz", list(out))
+
+
+def _features(batch, seed):
+    w = state_spec.seeded_waves(batch, 64000, seed=seed)
+    y, _ = ref_lfcc(w)
+    T = y.shape[1]
+    idx = torch.arange(750) % T                                   # repeat padding (dataset.py:519-522)
+    return y[:, idx, :]                                           # (B,750,60)
+
+
+def _grad_summary(named_params):
+    keys, norms, sums, heads = [], [], [], []
+    for k, p in named_params:
+        if p.grad is None:
+            continue
+        g = p.grad.detach().double().reshape(-1)
+        keys.append(k)
+        norms.append(float(g.norm()))
+        sums.append(float(g.sum()))
+        h = np.zeros(8)
+        h[:min(8, g.numel())] = g[:8].numpy()
+        heads.append(h)
+    return np.array(keys), np.array(norms), np.array(sums), np.stack(heads)
+
+
+def golden_nets(batch=4, seed=3):
+    rn = ref_shim.load("resnet")
+    ec = ref_shim.load("ecapa_tdnn")
+    ls = ref_shim.load("loss")
+    feats = _features(batch, seed)
+    labels = state_spec.seeded_labels(batch, seed)
+    out = {"labels": labels.numpy(), "batch": batch, "seed": seed}
+
+    real_randn = torch.randn
+    for arch in ("resnet", "ecapa"):
+        if arch == "resnet":
+            model = rn.ResNet(3, 256, "18", nclasses=2)
+            spec = state_spec.resnet_spec()
+            x = feats.unsqueeze(1).transpose(2, 3).contiguous()          # main_train.py:338
+        else:
+            model = ec.Res2Net2(ec.Bottle2neck, C=512, model_scale=8, nOut=2, n_mels=60)
+            spec = state_spec.ecapa_spec()
+            x = feats.transpose(1, 2).contiguous()                       # main_train.py:338,347-348
+        ref_keys = list(model.state_dict().keys())
+        assert ref_keys == [k for k, _, _ in spec], "state spec mismatch for " + arch
+        model.load_state_dict(state_spec.seeded_state(spec, seed=11))
+        loss_mod = ls.AngularIsoLoss(256, r_real=0.9, r_fake=0.2, alpha=20.0)
+        with torch.no_grad():
+            loss_mod.center.copy_(state_spec.seeded_center(256, seed=11))
+        model.train()
+        torch.randn = lambda *a, **k: torch.zeros(*a, **k)                # SelfAttention noise -> 0
+        try:
+            feat, logits = model(x)
+        finally:
+            torch.randn = real_randn
+        loss, score = loss_mod(feat, labels)
+        ce = torch.nn.functional.cross_entropy(logits, labels)
+        loss.backward()
+        keys, norms, sums, heads = _grad_summary(list(model.named_parameters()))
+        out[arch + "_feat"] = feat.detach().numpy()
+        out[arch + "_logits"] = logits.detach().numpy()
+        out[arch + "_loss"] = float(loss)
+        out[arch + "_ce"] = float(ce)
+        out[arch + "_score"] = score.detach().numpy()
+        out[arch + "_grad_keys"] = keys
+        out[arch + "_grad_norm"] = norms
+        out[arch + "_grad_sum"] = sums
+        out[arch + "_grad_head"] = heads
+        out[arch + "_center_grad"] = loss_mod.center.grad.numpy()
+        # running stats after the one train-mode forward
+        sd = model.state_dict()
+        rk = [k for k in sd if k.endswith("running_mean") or k.endswith("running_var")]
+        out[arch + "_running_keys"] = np.array(rk)
+        out[arch + "_running_sum"] = np.array([float(sd[k].double().sum()) for k in rk])
+        # eval-mode forward with the updated running stats (the scoring path)
+        model.eval()
+        torch.randn = lambda *a, **k: torch.zeros(*a, **k)
+        try:
+            with torch.no_grad():
+                feat_e, logits_e = model(x)
+                _, score_e = loss_mod(feat_e, torch.zeros(batch))
+        finally:
+            torch.randn = real_randn
+        out[arch + "_eval_feat"] = feat_e.numpy()
+        out[arch + "_eval_logits"] = logits_e.numpy()
+        out[arch + "_eval_score"] = (-score_e).numpy()       # generate_score.py:117 writes -score
+        print(arch, "loss", float(loss), "ce", float(ce), "ngrads", len(keys))
+    np.savez_compressed(os.path.join(GOLD, "nets_golden.npz"), **out)
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(8)
+    golden_lfcc()
+    golden_padcrop()
+    golden_nets()

@@ -1,0 +1,179 @@
+"""CPU oracle (torch fp32, functional) for ResNet-18-OC, ECAPA-TDNN (Res2Net2), OC-Softmax,
+the logged CE loss, and the Adam(L2)/SGD optimiser step.
+
+TEST INFRASTRUCTURE ONLY -- see oracle/lfcc_oracle.py header.  These are floating-point
+kernels, so the oracle is a plain torch fp32 restatement (autograd provides the backward the
+reference gets from PyTorch).  State is a plain dict with the REFERENCE state_dict key names
+(SURVEY.md section 8b), so weights copied from the reference modules drive both.
+
+Parity status: pinned against the reference's own modules run under oracle/ref_shim.py
+(tests/test_oracle_pinned.py in the authoring container; tests/golden/*.npz elsewhere).
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+# ------------------------------------------------------------------------------------
+# BatchNorm helper: train mode uses batch stats (biased var) and updates running stats with
+# unbiased var, momentum 0.1, eps 1e-5 (nn.BatchNorm defaults used at resnet.py:54-56,132).
+# ------------------------------------------------------------------------------------
+def _bn(sd, prefix, x, training, update_running=False):
+    rm, rv = sd[prefix + ".running_mean"], sd[prefix + ".running_var"]
+    if training and not update_running:
+        rm, rv = rm.clone(), rv.clone()
+    return F.batch_norm(x, rm, rv, sd[prefix + ".weight"], sd[prefix + ".bias"],
+                        training=training, momentum=0.1, eps=1e-5)
+
+
+# ------------------------------------------------------------------------------------
+# ResNet-18 (pre-activation) + SelfAttention pooling            resnet.py:23-46,49-69,122-191
+# ------------------------------------------------------------------------------------
+def self_attention_pool(x, att_weights, noise=None):
+    """x (B,T,C) -> (B,2C).  resnet.py:23-46.
+
+    weights = x . a ; attentions = softmax_T(tanh(weights)); weighted = x * attentions
+    avg = sum_T weighted ; std = unbiased std_T(weighted + noise); noise = 1e-5*randn in the
+    reference (drawn every forward, train and eval) -- passed in explicitly here."""
+    w = torch.matmul(x, att_weights.reshape(-1))            # (B,T)   :26
+    a = F.softmax(torch.tanh(w), dim=1)                     # :29-33
+    weighted = x * a.unsqueeze(2)
+    avg = weighted.sum(1)                                   # :41
+    if noise is None:
+        noise = torch.zeros_like(weighted)
+    std = (weighted + noise).std(1)                         # unbiased (N-1)  :41
+    return torch.cat((avg, std), 1)
+
+
+def _preact_block(sd, p, x, stride, training, upd):
+    """resnet.py:63-69."""
+    out = F.relu(_bn(sd, p + ".bn1", x, training, upd))
+    if (p + ".shortcut.0.weight") in sd:
+        sc = F.conv2d(out, sd[p + ".shortcut.0.weight"], stride=stride)
+    else:
+        sc = x
+    out = F.conv2d(out, sd[p + ".conv1.weight"], stride=stride, padding=1)
+    out = F.conv2d(F.relu(_bn(sd, p + ".bn2", out, training, upd)), sd[p + ".conv2.weight"],
+                   stride=1, padding=1)
+    return out + sc
+
+
+def resnet_forward(sd, x, training=True, noise=None, update_running=False):
+    """x (B,1,60,T) -> (feat (B,enc_dim), mu (B,nclasses)).  resnet.py:174-191."""
+    upd = update_running
+    x = F.conv2d(x, sd["conv1.weight"], stride=(3, 1), padding=(1, 1))       # :131,176
+    x = F.relu(_bn(sd, "bn1", x, training, upd))
+    for li, stride in ((1, 1), (2, 2), (3, 2), (4, 2)):                      # :135-138
+        x = _preact_block(sd, "layer%d.0" % li, x, stride, training, upd)
+        x = _preact_block(sd, "layer%d.1" % li, x, 1, training, upd)
+    x = F.conv2d(x, sd["conv5.weight"], stride=1, padding=(0, 1))            # :140
+    x = F.relu(_bn(sd, "bn5", x, training, upd)).squeeze(2)                  # (B,256,T')
+    stats = self_attention_pool(x.permute(0, 2, 1), sd["attention.att_weights"], noise)
+    feat = F.linear(stats, sd["fc.weight"], sd["fc.bias"])
+    mu = F.linear(feat, sd["fc_mu.weight"], sd["fc_mu.bias"])
+    return feat, mu
+
+
+# ------------------------------------------------------------------------------------
+# ECAPA-TDNN (Res2Net2 / Bottle2neck / SEModule)                 ecapa_tdnn.py:15-198
+# NB the order in this file is conv -> ReLU -> BN everywhere.
+# ------------------------------------------------------------------------------------
+def _conv1d(sd, p, x, **kw):
+    return F.conv1d(x, sd[p + ".weight"], sd[p + ".bias"], **kw)
+
+
+def _se(sd, p, x, training, upd):
+    """ecapa_tdnn.py:15-29: mean_T -> conv 512->128 -> ReLU -> BN -> conv 128->512 -> sigmoid."""
+    s = x.mean(dim=2, keepdim=True)
+    s = F.relu(_conv1d(sd, p + ".se.1", s))
+    s = _bn(sd, p + ".se.3", s, training, upd)
+    s = torch.sigmoid(_conv1d(sd, p + ".se.4", s))
+    return x * s
+
+
+def _bottle2neck(sd, p, x, dilation, scale, training, upd):
+    """ecapa_tdnn.py:64-95."""
+    out = _bn(sd, p + ".bn1", F.relu(_conv1d(sd, p + ".conv1", x)), training, upd)
+    width = out.shape[1] // scale
+    spx = torch.split(out, width, 1)
+    outs = []
+    sp = None
+    for i in range(scale - 1):
+        sp = spx[i] if i == 0 else sp + spx[i]
+        sp = _conv1d(sd, p + ".convs.%d" % i, sp, dilation=dilation, padding=dilation)
+        sp = _bn(sd, p + ".bns.%d" % i, F.relu(sp), training, upd)
+        outs.append(sp)
+    outs.append(spx[scale - 1])
+    out = torch.cat(outs, 1)
+    out = _bn(sd, p + ".bn3", F.relu(_conv1d(sd, p + ".conv3", out)), training, upd)
+    out = _se(sd, p + ".se", out, training, upd)
+    return out + x
+
+
+def ecapa_forward(sd, x, training=True, update_running=False, scale=8):
+    """x (B,n_mels,T) -> (feat (B,256), logits (B,nOut)).  ecapa_tdnn.py:152-198
+    (encoder_type='ECA', context=True, summed=False, out_bn=True: the main_train.py:167 config)."""
+    upd = update_running
+    x = _bn(sd, "bn1", F.relu(_conv1d(sd, "conv1", x, padding=2)), training, upd)
+    x1 = _bottle2neck(sd, "layer1", x, 2, scale, training, upd)
+    x2 = _bottle2neck(sd, "layer2", x1, 3, scale, training, upd)
+    x3 = _bottle2neck(sd, "layer3", x2, 4, scale, training, upd)
+    x = F.relu(_conv1d(sd, "layer4", torch.cat((x1, x2, x3), dim=1)))
+    t = x.shape[-1]
+    gx = torch.cat((x, x.mean(dim=2, keepdim=True).repeat(1, 1, t),
+                    torch.sqrt(x.var(dim=2, keepdim=True).clamp(min=1e-4)).repeat(1, 1, t)), dim=1)
+    w = F.relu(_conv1d(sd, "attention.0", gx))
+    w = _bn(sd, "attention.2", w, training, upd)
+    w = F.softmax(_conv1d(sd, "attention.3", w), dim=2)
+    mu = torch.sum(x * w, dim=2)
+    sg = torch.sqrt((torch.sum((x ** 2) * w, dim=2) - mu ** 2).clamp(min=1e-4))
+    x = torch.cat((mu, sg), 1)
+    x = _bn(sd, "bn5", x, training, upd)
+    feat = F.linear(x, sd["fc6.weight"], sd["fc6.bias"])
+    x = F.linear(feat, sd["fc7.weight"], sd["fc7.bias"])
+    x = _bn(sd, "bn7", x, training, upd)
+    return feat, x
+
+
+# ------------------------------------------------------------------------------------
+# OC-Softmax == AngularIsoLoss                                   loss.py:187-206 == :73-97
+# ------------------------------------------------------------------------------------
+def ocsoftmax(center, x, labels, r_real=0.9, r_fake=0.5, alpha=20.0):
+    """-> (loss, -cos).  softplus has beta=1, threshold=20 (nn.Softplus defaults, loss.py:185)."""
+    w = F.normalize(center, p=2, dim=1)
+    xn = F.normalize(x, p=2, dim=1)
+    s = xn @ w.t()                                           # (B,1)
+    out_scores = s.clone()
+    m = torch.where((labels == 0).unsqueeze(1), r_real - s, s)
+    m = torch.where((labels == 1).unsqueeze(1), s - r_fake, m)
+    loss = F.softplus(alpha * m).mean()
+    return loss, -out_scores.squeeze(1)
+
+
+def cross_entropy(logits, labels):
+    """nn.CrossEntropyLoss (logged only when --add_loss is set; main_train.py:250-251,355-357)."""
+    return F.cross_entropy(logits, labels)
+
+
+# ------------------------------------------------------------------------------------
+# optimiser steps                                                main_train.py:175,272,404-409
+# ------------------------------------------------------------------------------------
+def adam_l2_step(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=5e-4):
+    """torch.optim.Adam semantics with coupled L2 weight decay; in place; `step` is 1-based."""
+    g = g + weight_decay * p
+    m.mul_(beta1).add_(g, alpha=1 - beta1)
+    v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+    bc1 = 1 - beta1 ** step
+    bc2 = 1 - beta2 ** step
+    denom = (v.sqrt() / math.sqrt(bc2)).add_(eps)
+    p.addcdiv_(m, denom, value=-lr / bc1)
+
+
+def sgd_step(p, g, lr):
+    p.add_(g, alpha=-lr)
+
+
+def lr_at_epoch(lr, epoch, lr_decay=0.5, interval=30):
+    """main_train.py:144-147."""
+    return lr * (lr_decay ** (epoch // interval))
