@@ -1,0 +1,62 @@
+"""ctypes binding of libair_b200.so (the C ABI declared in include/air_b200.h).
+
+There is deliberately NO fallback: if the library is missing or a symbol cannot be resolved the
+import fails loudly, and every wrapper raises on a non-zero status.
+"""
+import ctypes
+import os
+import re
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libair_b200.so")
+HEADER = os.path.join(os.path.dirname(HERE), "include", "air_b200.h")
+
+_lib = None
+
+
+class AirError(RuntimeError):
+    pass
+
+
+def declared_symbols(header=HEADER):
+    """Names of every `int air_*(...)` entry point declared in the public header."""
+    with open(header) as f:
+        text = f.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return re.findall(r"\bint\s+(air_\w+)\s*\(", text)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise AirError("libair_b200.so is not built (%s); run `python -m asvspoof2021_air_b200.build`. "
+                           "There is no CPU or PyTorch fallback for this path." % LIB_PATH)
+        _lib = ctypes.CDLL(LIB_PATH)
+        for name in declared_symbols():
+            getattr(_lib, name).restype = ctypes.c_int
+    return _lib
+
+
+def check(status, what):
+    if status != 0:
+        kind = "argument error" if status < 0 else "CUDA error"
+        raise AirError("%s failed: %s %d" % (what, kind, status))
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None) as c_void_p."""
+    if t is None:
+        return ctypes.c_void_p(0)
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+I = ctypes.c_int
+LL = ctypes.c_longlong
+F = ctypes.c_float
+D = ctypes.c_double

@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload W] [--impl reference]
+
+Workloads
+  resnet_train  (default when the train engine is built) wave -> LFCC -> ResNet-18-OC fwd/bwd ->
+                OC-Softmax -> Adam/SGD, B=256/GPU, bf16, synthetic 4 s @ 16 kHz waves
+  ecapa_train   same with ECAPA-TDNN-512
+  ecapa_score   generate_score.py inference, B=1024
+  lfcc          the fused LFCC kernel alone, B=256 (HBM roofline of the LFCC kernel)
+
+One JSON line is printed by rank 0 (contract in the task statement): value = whole-job
+utterances/s with inputs resident in HBM; e2e = same metric through the public Python API with
+pinned-host inputs, H2D/D2H inside the timed region; roofline = dominant kernel vs the measured
+peak in MEASURED_PEAKS.json; cpu_baseline = the oracle port of the reference's CPU path timed on
+this box's host cores over a bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WAVE_LEN = 64000
+LFCC_BYTES_PER_UTT = 4 * WAVE_LEN + 4 * 401 * 60      # 352 240 B
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    return rank, world, local
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(ms, world):
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    return ms
+
+
+def timed(step_fn, steps, warmup, world):
+    for i in range(warmup):
+        step_fn(i)
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step_fn(warmup + i)
+    e1.record()
+    barrier(world)
+    return max_over_ranks(e0.elapsed_time(e1), world)
+
+
+# ----------------------------------------------------------------------------------------------
+def cpu_lfcc_baseline(seconds=10.0, batch=32):
+    """Oracle port of the reference LFCC (torch fp32, all host threads) on a bounded sample."""
+    from oracle import lfcc_torch, state_spec as ss
+    n = os.cpu_count() or 1
+    torch.set_num_threads(n)
+    m = lfcc_torch.TorchLFCC()
+    w = ss.seeded_waves(batch, WAVE_LEN, seed=0)
+    m(w)
+    t0, it = time.perf_counter(), 0
+    while time.perf_counter() - t0 < seconds and it < 200:
+        m(w)
+        it += 1
+    dt = time.perf_counter() - t0
+    return {"value": batch * it / dt, "unit": "utterances/s", "cores": n, "kind": "port",
+            "sample": "%d x LFCC of %d synthetic 4 s waves (torch fp32 restatement of feature_extraction.py:93-138)" % (it, batch)}
+
+
+def run_lfcc(args, rank, world):
+    from asvspoof2021_air_b200.feature_extraction import LFCC
+    from oracle import state_spec as ss
+    B = args.batch or 256
+    mod = LFCC(320, 160, 512, 16000, 20).cuda()
+    nbuf = 4                                   # 4 x (65.5 MB in + 24.6 MB out) = 360 MB > 126 MB L2
+    waves = [ss.seeded_waves(B, WAVE_LEN, seed=rank * 16 + i).cuda() for i in range(nbuf)]
+    outs = [torch.empty(B, 401, 60, device="cuda") for _ in range(nbuf)]
+    launches = [0]
+
+    def step(i):
+        mod.extract(waves[i % nbuf], feat_len=0, layout="btd", dtype=torch.float32, out=outs[i % nbuf], fseg=args.fseg)
+        launches[0] += 1
+
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.start()
+    ms = timed(step, args.steps, args.warmup, world)
+    clocks = sampler.stop()
+    n_timed_launches = args.steps
+    # kernel time = step time here (one kernel per step, back to back on one stream)
+    per_launch_s = ms / 1e3 / args.steps
+    peaks = measured_peaks()
+    achieved = B * LFCC_BYTES_PER_UTT / per_launch_s / 1e9
+
+    # e2e: pinned host waves -> H2D -> kernel -> D2H of the features' checksum row
+    host = [w.cpu().pin_memory() for w in waves[:2]]
+    dev_in = torch.empty(B, WAVE_LEN, device="cuda")
+    res_host = torch.empty(B, 60, pin_memory=True)
+
+    def step_e2e(i):
+        dev_in.copy_(host[i % 2], non_blocking=True)
+        y = mod.extract(dev_in, feat_len=0, layout="btd", dtype=torch.float32, out=outs[i % nbuf], fseg=args.fseg)
+        res_host.copy_(y[:, 200, :], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    ms_e2e = timed(step_e2e, args.steps, args.warmup, world)
+    line = {
+        "metric": "LFCC utterances/sec (4 s@16 kHz)", "value": world * B * args.steps / (ms / 1e3),
+        "unit": "utterances/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "lfcc: fused wave->LFCC kernel, B=%d/GPU, 4 s @ 16 kHz, fp32 out (B,401,60)" % B,
+                   "batch_per_gpu": B, "l2": "inputs rotate over %d buffers (360 MB > L2)" % nbuf},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_src": peaks["src"],
+                     "kernel": "air_lfcc::lfcc_kernel", "bytes_per_launch": B * LFCC_BYTES_PER_UTT},
+        "e2e": {"value": world * B * args.steps / (ms_e2e / 1e3), "unit": "utterances/s",
+                "h2d_bytes_per_step": B * WAVE_LEN * 4, "d2h_bytes_per_step": B * 60 * 4},
+        "gpu_launches": n_timed_launches, "clocks": clocks,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_lfcc_baseline()
+    return line
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path (oracle port; /root/reference is not on
+    the GPU box), all host threads, bounded sample per step."""
+    if rank != 0:
+        return None
+    if args.workload == "lfcc":
+        from oracle import lfcc_torch, state_spec as ss
+        n = os.cpu_count() or 1
+        torch.set_num_threads(n)
+        B = 32
+        m = lfcc_torch.TorchLFCC()
+        w = ss.seeded_waves(B, WAVE_LEN, seed=0)
+        for _ in range(args.warmup):
+            m(w)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            m(w)
+        dt = time.perf_counter() - t0
+        v = B * args.steps / dt
+        return {"impl": "reference", "metric": "LFCC utterances/sec (4 s@16 kHz)", "value": v, "unit": "utterances/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "lfcc: reference CPU path (torch fp32 port), %d waves per step" % B},
+                "cpu_baseline": {"value": v, "unit": "utterances/s", "cores": n, "kind": "port",
+                                 "sample": "%d waves x %d steps" % (B, args.steps)},
+                "e2e": {"value": v, "unit": "utterances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    from asvspoof2021_air_b200 import bench_train
+    return bench_train.run_reference(args, rank, world)
+
+
+def default_workload():
+    try:
+        from asvspoof2021_air_b200 import bench_train  # noqa: F401
+        return "resnet_train"
+    except ImportError:
+        return "lfcc"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default=None, choices=[None, "lfcc", "resnet_train", "ecapa_train", "ecapa_score"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--fseg", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.workload is None:
+        args.workload = default_workload()
+
+    if args.impl == "reference":
+        rank = int(os.environ.get("RANK", "0"))
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        line = run_reference(args, rank, world)
+        if line is not None:
+            print(json.dumps(line), flush=True)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    rank, world, _ = dist_setup(args.gpus)
+    if args.workload == "lfcc":
+        line = run_lfcc(args, rank, world)
+    else:
+        from asvspoof2021_air_b200 import bench_train
+        line = bench_train.run(args, rank, world, helpers=sys.modules[__name__])
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,98 @@
+"""float64 numpy emulation of the lane/register algorithm of csrc/lfcc.cu (index math only).
+
+Host-side check that the 16x16 Cooley-Tukey split, the twiddle table layout, the mirror-lane
+real-FFT split and the sparse filterbank tables are right before any GPU time is spent."""
+import numpy as np
+
+from asvspoof2021_air_b200 import lfcc_tables as lt
+
+
+def fft16(v):
+    """v (..., 16) complex, natural order -> natural order; same radix-4x4 split as the kernel."""
+    W16 = np.exp(-2j * np.pi * np.arange(16) / 16)
+    T = np.zeros(v.shape[:-1] + (4, 4), dtype=complex)
+    for n1 in range(4):
+        x = [v[..., n1 + 4 * n2] for n2 in range(4)]
+        t0, t1, t2, t3 = x[0] + x[2], x[0] - x[2], x[1] + x[3], x[1] - x[3]
+        T[..., n1, 0] = t0 + t2
+        T[..., n1, 2] = t0 - t2
+        T[..., n1, 1] = t1 + (-1j) * t3
+        T[..., n1, 3] = t1 - (-1j) * t3
+    for n1 in range(4):
+        for k2 in range(4):
+            T[..., n1, k2] *= W16[(n1 * k2) % 16]
+    out = np.zeros_like(v)
+    for k2 in range(4):
+        x = [T[..., n1, k2] for n1 in range(4)]
+        t0, t1, t2, t3 = x[0] + x[2], x[0] - x[2], x[1] + x[3], x[1] - x[3]
+        out[..., k2] = t0 + t2
+        out[..., 8 + k2] = t0 - t2
+        out[..., 4 + k2] = t1 + (-1j) * t3
+        out[..., 12 + k2] = t1 - (-1j) * t3
+    return out
+
+
+def frame_cepstrum(y_frame, tbl):
+    """y_frame: 320 pre-emphasised samples (zeros outside the utterance) -> 20 cepstra."""
+    tbl = np.asarray(tbl, dtype=np.float32)
+    win = tbl[lt.OFF_WIN:lt.OFF_WIN + 320].astype(np.float64)
+    tw1 = tbl[lt.OFF_TW1:lt.OFF_TW1 + 512].astype(np.float64).reshape(16, 16, 2)
+    tw2 = tbl[lt.OFF_TW2:lt.OFF_TW2 + 512].astype(np.float64).reshape(256, 2)
+    yw = y_frame * win
+    z = np.zeros(256, dtype=complex)
+    z[:160] = yw[0::2] + 1j * yw[1::2]
+    v = np.zeros((16, 16), dtype=complex)          # [lane l][reg j] = z[l + 16 j]
+    for l in range(16):
+        for j in range(16):
+            v[l, j] = z[l + 16 * j]
+    v = fft16(v)                                    # [l][kj]
+    for l in range(16):
+        for kj in range(16):
+            v[l, kj] *= tw1[kj, l, 0] + 1j * tw1[kj, l, 1]
+    v = v.T.copy()                                  # smem transpose: lane q=kj holds [i=l]
+    v = fft16(v)                                    # v[q][r] = Z[q + 16 r]
+    P = np.zeros(256)
+    for q in range(16):
+        pl = (16 - q) & 15
+        for r in range(16):
+            m = v[q, (16 - r) & 15] if q == 0 else v[pl, 15 - r]
+            A = v[q, r]
+            sx, sy = A.real + m.real, A.imag - m.imag
+            dx, dy = A.real - m.real, A.imag + m.imag
+            c, s = tw2[q + 16 * r]
+            re = sx - s * dx + c * dy
+            im = sy - s * dy - c * dx
+            P[q + 16 * r] = 0.25 * (re * re + im * im)
+    starts = tbl[lt.OFF_FBS:lt.OFF_FBS + lt.NF].view(np.int32)
+    counts = tbl[lt.OFF_FBC:lt.OFF_FBC + lt.NF].view(np.int32)
+    fbe = np.zeros(lt.NF)
+    for f in range(lt.NF):
+        wts = tbl[lt.OFF_FBW + f * 33:lt.OFF_FBW + f * 33 + counts[f]].astype(np.float64)
+        fbe[f] = np.log10(np.dot(P[starts[f]:starts[f] + counts[f]], wts) + 1.1920928955078125e-07)
+    dct = np.stack([tbl[lt.OFF_DCT + k * 21:lt.OFF_DCT + k * 21 + lt.NF] for k in range(lt.NF)]).astype(np.float64)
+    return dct @ fbe, P
+
+
+def lfcc_emulated(wave, tbl):
+    """wave (L,) -> (T, 60) following the kernel's framing / delta rules."""
+    x = np.asarray(wave, dtype=np.float64)
+    L = len(x)
+    y = x.copy()
+    y[1:] = x[1:] - 0.97 * x[:-1]
+    T = 1 + L // 160
+    c = np.zeros((T, 20))
+    for t in range(T):
+        fr = np.zeros(320)
+        s0 = 160 * (t - 1)
+        lo, hi = max(s0, 0), min(s0 + 320, L)
+        if hi > lo:
+            fr[lo - s0:hi - s0] = y[lo:hi]
+        c[t], _ = frame_cepstrum(fr, tbl)
+    cl = lambda u: min(max(u, 0), T - 1)
+    out = np.zeros((T, 60))
+    for t in range(T):
+        tp, tm = cl(t + 1), cl(t - 1)
+        out[t, :20] = c[t]
+        out[t, 20:40] = c[tp] - c[tm]
+        out[t, 40:] = (c[cl(tp + 1)] - c[cl(tp - 1)]) - (c[cl(tm + 1)] - c[cl(tm - 1)])
+    return out

@@ -1,0 +1,160 @@
+"""CPU tests: the oracle restatements against the golden vectors generated from the reference,
+and (when /root/reference is mounted) against the reference modules themselves."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import lfcc_oracle as lo
+from oracle import nets_oracle as no
+from oracle import ref_shim, state_spec as ss
+from tolerances import lfcc_close, lfcc_worst
+
+
+@pytest.fixture(scope="module")
+def gl(golden_dir):
+    return np.load(os.path.join(golden_dir, "lfcc_golden.npz"))
+
+
+def test_constants_bit_identical(gl):
+    assert np.array_equal(lo.linear_filterbank(), gl["lfcc_fb"])
+    assert np.abs(lo.dct_matrix() - gl["dct_weight"]).max() < 1e-7
+    # bins 0 and 256 carry no weight; every bin feeds at most two filters
+    fb = gl["lfcc_fb"]
+    assert fb[0].sum() == 0 and fb[256].sum() == 0
+    assert ((fb > 0).sum(axis=1) <= 2).all()
+
+
+def test_lfcc_oracle_vs_reference_golden(gl):
+    w = ss.seeded_waves(32, 64000, seed=0, edge_rows=True).numpy()
+    rows = gl["full_rows"]
+    y = lo.lfcc(w[rows])
+    assert y.shape == (len(rows), 401, 60)
+    assert lfcc_close(y, gl["full"]).all(), lfcc_worst(y, gl["full"])
+    yall = lo.lfcc(w)
+    assert lfcc_close(yall[:, gl["sparse_frames"]], gl["sparse"]).all()
+    # checksum over frames: 401 terms, each within the per-element tolerance
+    assert (np.abs(yall.sum(axis=1) - gl["colsum"]) <= 1e-4 * (np.abs(gl["colsum"]) + 401.0)).all()
+
+
+@pytest.mark.parametrize("L", [3200, 12345, 5920, 6079, 321, 800])
+def test_lfcc_oracle_ragged_lengths(gl, L):
+    w = ss.seeded_waves(2, L, seed=L).numpy()
+    y = lo.lfcc(w)
+    ref = gl["ragged_%d" % L]
+    assert y.shape == ref.shape == (2, 1 + L // 160, 60)      # frame count is exact
+    assert lfcc_close(y, ref).all(), lfcc_worst(y, ref)
+
+
+def test_silence_vector(gl):
+    s = lo.silence_vector()
+    assert lfcc_close(s, gl["silence"][0]).all()
+    assert abs(s[0] + 30.96) < 0.01          # c0 of log10(eps) frames
+
+
+def test_pad_crop_index_maps_bit_exact(golden_dir):
+    g = np.load(os.path.join(golden_dir, "padcrop_golden.npz"))
+    sil_c0 = float(g["silence_pad_value"][0, 0, 0])
+    for T in (1, 21, 401, 749):
+        assert np.array_equal(lo.frame_index_map(T, 750, "repeat"), g["repeat_%d" % T])
+        assert np.array_equal(lo.frame_index_map(T, 750, "zero"), g["zero_%d" % T])
+        m = lo.frame_index_map(T, 750, "silence")
+        ref = g["silence_%d" % T]
+        ours = np.where(m == lo.SRC_SILENCE, sil_c0, m + 1000.0)
+        assert np.array_equal(ours.astype(np.float32), ref)
+    m = lo.frame_index_map(1000, 750, "repeat", startp=17)
+    assert m[0] == 17 and m[-1] == 17 + 749
+    assert np.array_equal(lo.frame_index_map(750, 750, "zero"), np.arange(750))
+
+
+def test_kernel_algorithm_emulation_matches_oracle():
+    """The lane/register algorithm of csrc/lfcc.cu, emulated in float64, against the oracle."""
+    from asvspoof2021_air_b200 import lfcc_tables as lt
+    import lfcc_emulation as em
+    tbl = lt.pack_table(lt.linear_filterbank(512, 16000, 20), lt.dct_ortho_matrix(20)).numpy()
+    for L in (800, 2000):
+        w = ss.seeded_waves(1, L, seed=L).numpy()
+        assert np.abs(em.lfcc_emulated(w[0], tbl) - lo.lfcc(w)[0]).max() < 2e-6
+
+
+def _nets_inputs(batch, seed):
+    feats = lo.apply_frame_map(lo.lfcc(ss.seeded_waves(batch, 64000, seed=seed).numpy()),
+                               lo.frame_index_map(401, 750, "repeat"))
+    return torch.from_numpy(feats).float(), ss.seeded_labels(batch, seed)
+
+
+@pytest.mark.parametrize("arch", ["resnet", "ecapa"])
+def test_nets_oracle_vs_reference_golden(golden_dir, arch):
+    g = np.load(os.path.join(golden_dir, "nets_golden.npz"))
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    feats, labels = _nets_inputs(int(g["batch"]), int(g["seed"]))
+    assert np.array_equal(labels.numpy(), g["labels"])
+    spec = ss.resnet_spec() if arch == "resnet" else ss.ecapa_spec()
+    sd = ss.seeded_state(spec, 11)
+    for k in ss.trainable_keys(spec):
+        sd[k].requires_grad_(True)
+    center = ss.seeded_center(256, 11).requires_grad_(True)
+    if arch == "resnet":
+        feat, logits = no.resnet_forward(sd, feats.unsqueeze(1).transpose(2, 3).contiguous(), True,
+                                         update_running=True)
+    else:
+        feat, logits = no.ecapa_forward(sd, feats.transpose(1, 2).contiguous(), True, update_running=True)
+    loss, score = no.ocsoftmax(center, feat, labels, 0.9, 0.2, 20.0)
+    loss.backward()
+    assert abs(float(loss) - float(g[arch + "_loss"])) <= 1e-3 * abs(float(g[arch + "_loss"]))
+    assert abs(float(no.cross_entropy(logits, labels)) - float(g[arch + "_ce"])) <= 1e-3
+    assert np.allclose(feat.detach().numpy(), g[arch + "_feat"], rtol=1e-3, atol=1e-3)
+    assert np.allclose(logits.detach().numpy(), g[arch + "_logits"], rtol=1e-3, atol=1e-3)
+    assert np.allclose(score.detach().numpy(), g[arch + "_score"], rtol=1e-3, atol=1e-4)
+    assert np.allclose(center.grad.numpy(), g[arch + "_center_grad"], rtol=1e-3, atol=1e-5)
+    gmax = float(g[arch + "_grad_norm"].max())
+    for k, n, h in zip(g[arch + "_grad_keys"], g[arch + "_grad_norm"], g[arch + "_grad_head"]):
+        gr = sd[str(k)].grad
+        assert gr is not None, k
+        # deep gradients are ill-conditioned (1e-6 input noise -> ~1% on single elements), so a
+        # different host CPU's conv kernels may move them: norms to 2%, leading elements loosely
+        assert abs(float(gr.double().norm()) - n) <= 2e-2 * n + 1e-5 * gmax, k
+        hh = gr.reshape(-1)[:8].double().numpy()
+        assert np.allclose(hh, h[:len(hh)], rtol=5e-2, atol=2e-2 * n + 1e-5 * gmax), k
+    # parameters the reference leaves without gradient under --add_loss ang_iso
+    nograd = [k for k in ss.trainable_keys(spec) if sd[k].grad is None]
+    expect = {"fc_mu.weight", "fc_mu.bias"} if arch == "resnet" else {"fc7.weight", "fc7.bias", "bn7.weight", "bn7.bias"}
+    assert set(nograd) == expect
+    rs = {str(k): v for k, v in zip(g[arch + "_running_keys"], g[arch + "_running_sum"])}
+    for k, v in rs.items():
+        assert abs(float(sd[k].double().sum()) - v) <= 1e-3 * abs(v) + 1e-3, k
+    # eval-mode (scoring) path with the updated running statistics
+    with torch.no_grad():
+        if arch == "resnet":
+            fe, le = no.resnet_forward(sd, feats.unsqueeze(1).transpose(2, 3).contiguous(), False)
+        else:
+            fe, le = no.ecapa_forward(sd, feats.transpose(1, 2).contiguous(), False)
+        _, sc = no.ocsoftmax(center, fe, torch.zeros(len(labels)), 0.9, 0.2, 20.0)
+    assert np.allclose(fe.numpy(), g[arch + "_eval_feat"], rtol=1e-3, atol=1e-3)
+    assert np.allclose((-sc).numpy(), g[arch + "_eval_score"], rtol=1e-3, atol=1e-4)
+
+
+def test_optimizer_restatement_matches_torch():
+    torch.manual_seed(0)
+    p = torch.randn(1000)
+    ref = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=5e-4)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 4):
+        g = torch.randn(1000)
+        ref.grad = g.clone()
+        opt.step()
+        no.adam_l2_step(p, g, m, v, step, 5e-4)
+        assert torch.allclose(p, ref.detach(), rtol=1e-6, atol=1e-7)
+    assert no.lr_at_epoch(5e-4, 61) == 5e-4 * 0.25
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="/root/reference not mounted")
+def test_state_specs_match_reference_modules():
+    rn, ec = ref_shim.load("resnet"), ref_shim.load("ecapa_tdnn")
+    m = rn.ResNet(3, 256, "18", nclasses=2)
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == [(k, s) for k, s, _ in ss.resnet_spec()]
+    e = ec.Res2Net2(ec.Bottle2neck, C=512, model_scale=8, nOut=2, n_mels=60)
+    assert [(k, tuple(v.shape)) for k, v in e.state_dict().items()] == [(k, s) for k, s, _ in ss.ecapa_spec()]
+    assert len(ss.resnet_spec()) == 117 and len(ss.ecapa_spec()) == 248
