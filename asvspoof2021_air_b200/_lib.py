@@ -23,7 +23,7 @@ def declared_symbols(header=HEADER):
     with open(header) as f:
         text = f.read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return re.findall(r"\bint\s+(air_\w+)\s*\(", text)
+    return re.findall(r"\b(?:int|long long)\s+(air_\w+)\s*\(", text)
 
 
 def lib():

@@ -1,0 +1,217 @@
+// Weight-gradient of the implicit-GEMM convolution on tcgen05 tensor cores.
+//
+//   dW[n, kx] += sum_{pixels m} dy[m, n] * im2col(x)[m, kx]        n = co, kx = (tap, ci)
+//
+// The reduction runs over pixels, so both operands are "MN-major" for the tensor core: rows of the
+// shared-memory image are pixels (the GEMM K dimension), 16-byte chunks are 8 channels.  That is the
+// same "column of rows" image the forward gather builds (tc05.cuh), so the same zero-filling
+// cp.async gather feeds it.  Tile: 256 (kx) x block_n (co) accumulated in TMEM as two M = 128
+// halves; the pixel range is split across CTAs (split-K) and reduced with fp32 red.global.add into
+// the caller-zeroed gradient buffer (GEMM layout [Cout][taps*Cin], fp32).
+#include <algorithm>
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace air_wgrad {
+using namespace tc05;
+
+constexpr int TILE_M = 256;              // kx per work item (two UMMA M=128 halves)
+constexpr int PIX = 64;                  // pixels per pipeline stage (GEMM K block)
+constexpr int A_HALF_BYTES = 16 * PIX * 16;      // 16 chunks x 64 rows x 16 B = 16 KB
+constexpr int CHUNK_STRIDE = PIX * 16;           // 1024 B between 8-channel chunks
+constexpr int THREADS = 256;             // 4 gather warps, 1 MMA warp, (1 idle), ... see roles below
+
+struct WgradParams {
+  const __nv_bfloat16* x; long long x_ld; int H, W, C;       // forward input (gather source)
+  const __nv_bfloat16* dy; long long dy_ld; int Ho, Wo, N;   // output gradient, N = Cout
+  int kh, kw, sh, sw, ph, pw, dh, dw;
+  int Kx;                                 // taps * C
+  float* dw_out;                          // [N][Kx] fp32, accumulated atomically
+  long long M;                            // pixels = B*Ho*Wo
+  int m_tiles, n_tiles, splits, kb_total, kb_per_split, block_n;
+  int stages, flags;
+};
+
+struct ChunkInfo { int hoff, woff, ci, ok; };
+
+__global__ void __launch_bounds__(THREADS, 1) conv_wgrad_kernel(const WgradParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.stages;
+  const uint32_t b_bytes = static_cast<uint32_t>(p.block_n / 8) * CHUNK_STRIDE;
+  const uint32_t stage_bytes = 2 * A_HALF_BYTES + b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * stage_bytes);
+  uint64_t* full = bars;            // [S] 128 gather arrivals
+  uint64_t* empty = bars + S;       // [S] tcgen05.commit
+  uint64_t* tfull = bars + 2 * S;   // [1] accumulators ready
+  uint64_t* tempty = bars + 2 * S + 1;   // [1] accumulators drained (128 epilogue threads)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 2);
+  ChunkInfo* cinfo = reinterpret_cast<ChunkInfo*>(bars + 2 * S + 4);   // [32] per work item
+
+  uint32_t ncols = 32;
+  while (ncols < 2u * p.block_n) ncols <<= 1;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
+    mbar_init(tfull, 1); mbar_init(tempty, 128);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, ncols);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const int total_items = p.m_tiles * p.n_tiles * p.splits;
+
+  // Roles: warps 0-3 gather (and, after the main loop of an item, act as the epilogue: they own
+  // TMEM lane quadrants 0-3), warp 4 issues the MMAs.  Warps 5-7 idle (kept so that blockDim is
+  // a multiple of 128 for the quadrant mapping).
+  uint32_t stage = 0, phase = 0;
+  int it = 0;
+  for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+    const int split = item % p.splits;
+    const int nt = (item / p.splits) % p.n_tiles;
+    const int mt = item / (p.splits * p.n_tiles);
+    const int kb0 = split * p.kb_per_split;
+    const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+    const int m0 = mt * TILE_M, n0 = nt * p.block_n;
+    const int halves = (p.Kx - m0 > 128) ? 2 : 1;
+
+    if (threadIdx.x < 32) {             // per-item chunk table: kx = m0 + 8c -> (tap offsets, ci)
+      const int kx = m0 + 8 * threadIdx.x;
+      ChunkInfo ci; ci.ok = kx < p.Kx;
+      const int tp = ci.ok ? kx / p.C : 0;
+      ci.ci = ci.ok ? kx - tp * p.C : 0;
+      const int khi = tp / p.kw, kwi = tp - khi * p.kw;
+      ci.hoff = khi * p.dh - p.ph; ci.woff = kwi * p.dw - p.pw;
+      cinfo[threadIdx.x] = ci;
+    }
+    __syncthreads();
+
+    if (warp < 4) {
+      const int row = threadIdx.x & 63, half = threadIdx.x >> 6;
+      const int nbc = p.block_n / 8;
+      const int bc0 = half * (nbc / 2), bc1 = (half == 0) ? nbc / 2 : nbc;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        const long long m = static_cast<long long>(kb) * PIX + row;
+        const bool row_ok = m < p.M;
+        int wo = 0, ho = 0, bb = 0;
+        if (row_ok) { wo = static_cast<int>(m % p.Wo); const long long t = m / p.Wo; ho = static_cast<int>(t % p.Ho); bb = static_cast<int>(t / p.Ho); }
+        const int hs = ho * p.sh, ws = wo * p.sw;
+        const __nv_bfloat16* img = p.x + static_cast<long long>(bb) * p.H * p.W * p.x_ld;
+        const uint32_t sbase = smem_u32(smem) + stage * stage_bytes + row * 16;
+        // x chunks: this thread fills chunks [16*half .. 16*half+16) of the 32-chunk (256 kx) A image
+        if (half < halves) {
+#pragma unroll 4
+          for (int c = 0; c < 16; ++c) {
+            const ChunkInfo ci = cinfo[half * 16 + c];
+            const int hi = hs + ci.hoff, wi = ws + ci.woff;
+            const bool ok = row_ok && ci.ok && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W;
+            const __nv_bfloat16* src = ok ? img + (static_cast<long long>(hi) * p.W + wi) * p.x_ld + ci.ci : p.x;
+            cp_async16(sbase + half * A_HALF_BYTES + c * CHUNK_STRIDE, src, ok ? 16u : 0u);
+          }
+        }
+        // dy chunks
+        const __nv_bfloat16* dsrc = p.dy + m * p.dy_ld + n0;
+        for (int c = bc0; c < bc1; ++c)
+          cp_async16(sbase + 2 * A_HALF_BYTES + c * CHUNK_STRIDE, row_ok ? dsrc + c * 8 : p.dy, row_ok ? 16u : 0u);
+        cp_async_arrive_noinc(&full[stage]);
+        if (++stage == static_cast<uint32_t>(S)) { stage = 0; phase ^= 1; }
+      }
+      // ---------------- epilogue (same warps): TMEM -> red.global.add ----------------
+      mbar_wait(tfull, it & 1);
+      fence_after_sync();
+      const int q = warp & 3;
+      for (int h = 0; h < halves; ++h) {
+        const int kx = m0 + h * 128 + q * 32 + lane;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + h * p.block_n;
+        for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+          float v[16];
+          tmem_ld16(taddr + c0, v);
+          if (kx < p.Kx) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              atomicAdd(p.dw_out + static_cast<long long>(n0 + c0 + i) * p.Kx + kx, v[i]);
+          }
+        }
+      }
+      fence_before_sync();
+      mbar_arrive(tempty);
+    } else if (warp == 4) {
+      if (lane == 0) {
+        const uint32_t idesc = instr_desc_bf16(128, p.block_n, 1, 1);
+        uint32_t lbo = 128, sbo = CHUNK_STRIDE;
+        if (p.flags & 1) { lbo = CHUNK_STRIDE; sbo = 128; }
+        mbar_wait(tempty, (it & 1) ^ 1);
+        fence_after_sync();
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          fence_after_sync();
+          const uint32_t s0 = smem_u32(smem) + stage * stage_bytes;
+#pragma unroll
+          for (int kk = 0; kk < PIX / 16; ++kk) {
+            const uint64_t bd = smem_desc(s0 + 2 * A_HALF_BYTES + kk * 256, lbo, sbo);
+            for (int h = 0; h < halves; ++h) {
+              const uint64_t ad = smem_desc(s0 + h * A_HALF_BYTES + kk * 256, lbo, sbo);
+              mma_bf16(tmem_base + h * p.block_n, ad, bd, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+            }
+          }
+          mma_commit(&empty[stage]);
+          if (kb == kb1 - 1) mma_commit(tfull);
+          if (++stage == static_cast<uint32_t>(S)) { stage = 0; phase ^= 1; }
+        }
+      }
+      __syncwarp();
+    }
+    __syncthreads();      // cinfo reuse + keeps the item sequence aligned across roles
+  }
+
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 4) { fence_after_sync(); tmem_dealloc(tmem_base, ncols); }
+}
+
+}  // namespace air_wgrad
+
+using namespace air_wgrad;
+
+extern "C" int air_conv_wgrad_bf16(const void* x, long long x_ld, int B, int H, int W, int C,
+                                   const void* dy, long long dy_ld, int Ho, int Wo, int N,
+                                   int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw,
+                                   float* dw_out, int num_sms, int flags, cudaStream_t stream) {
+  if (!x || !dy || !dw_out || B <= 0) return AIR_ERR_ARG;
+  if (C % 8 != 0 || x_ld % 8 != 0 || dy_ld % 8 != 0 || N % 16 != 0) return AIR_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) return AIR_ERR_UNSUPPORTED;
+  int bn = N <= 256 ? N : (N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 0)));
+  if (bn == 0) return AIR_ERR_UNSUPPORTED;
+  WgradParams p;
+  p.x = reinterpret_cast<const __nv_bfloat16*>(x); p.x_ld = x_ld; p.H = H; p.W = W; p.C = C;
+  p.dy = reinterpret_cast<const __nv_bfloat16*>(dy); p.dy_ld = dy_ld; p.Ho = Ho; p.Wo = Wo; p.N = N;
+  p.kh = kh; p.kw = kw; p.sh = sh; p.sw = sw; p.ph = ph; p.pw = pw; p.dh = dh; p.dw = dw;
+  p.Kx = kh * kw * C; p.dw_out = dw_out; p.M = static_cast<long long>(B) * Ho * Wo;
+  p.block_n = bn; p.n_tiles = N / bn; p.m_tiles = (p.Kx + TILE_M - 1) / TILE_M;
+  p.kb_total = static_cast<int>((p.M + PIX - 1) / PIX);
+  if (num_sms <= 0) num_sms = 148;
+  const int base_items = p.m_tiles * p.n_tiles;
+  int splits = (2 * num_sms + base_items - 1) / base_items;          // ~2 work items per SM
+  splits = std::max(1, std::min(splits, (p.kb_total + 7) / 8));      // at least 8 K blocks per split
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  p.flags = flags;
+  const int stage_bytes = 2 * A_HALF_BYTES + (bn / 8) * CHUNK_STRIDE;
+  int stages = (196 * 1024) / stage_bytes;
+  if (stages > 6) stages = 6;
+  if (stages < 2) return AIR_ERR_UNSUPPORTED;
+  p.stages = stages;
+  const size_t smem = static_cast<size_t>(stages) * stage_bytes + (2 * stages + 4) * 8 + 32 * sizeof(ChunkInfo) + 16;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_done = true;
+  }
+  const int total_items = base_items * p.splits;
+  const int grid = std::min(total_items, num_sms);
+  conv_wgrad_kernel<<<grid, THREADS, smem, stream>>>(p);
+  return air_launch_status();
+}

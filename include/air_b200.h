@@ -53,6 +53,42 @@ int air_lfcc_fwd(const float* wave, long long ldw, const int* lengths, int B, in
                  int out_bf16, int Tout, int feat_len, int pad_mode, const int* start,
                  const float* silence, float preemph, int fseg, air_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution on tcgen05 tensor cores (bf16 in, fp32 accumulate in TMEM).
+ * Replaces nn.Conv2d / nn.Conv1d forward and data-gradient (cuDNN in the reference:
+ * resnet.py:56-60,131,140; ecapa_tdnn.py:19-23,39,50,56,111-118,139-145).  Activations are
+ * channels-last bf16; weights are fp32 in GEMM layout [Cout][kh][kw][Cin] and are packed to bf16
+ * UMMA tiles by air_conv_pack_weights (mode 0: fprop operand, N=Cout, K=taps*Cin;
+ * mode 1: dgrad operand, N=Cin, K=taps*Cout).
+ *
+ * air_conv_gemm_bf16: out[m, n] = sum_k gather(a)[m, k] * W[n, k] (+bias[n]) (+res[m, n]) (ReLU)
+ *   mode 0 (fprop): m enumerates (b, ho, wo) of the OUTPUT grid (Ho, Wo); the gather reads pixel
+ *                   (ho*sh - ph + i*dh, wo*sw - pw + j*dw) of the (H, W, C) source, zero outside.
+ *   mode 1 (dgrad): m enumerates (b, h, w) of the INPUT grid passed as (Ho, Wo); the gather reads
+ *                   dy at ((h + ph - i*dh)/sh, (w + pw - j*dw)/sw) of the (H, W, C) = dy grid
+ *                   when divisible and in range.
+ *   a_ld / out_ld / res_ld: elements between consecutive pixels (channel slices are allowed).
+ *   Constraints: C, a_ld, out_ld, res_ld multiples of 8; N multiple of 16; 16-byte aligned bases.
+ * --------------------------------------------------------------------------------------------- */
+int air_conv_block_n(int N);
+long long air_conv_packed_elems(int N, int K);
+int air_conv_pack_weights(const float* w, void* dst, int N, int K, int mode, int Cin, int Cout, int taps,
+                          air_stream_t stream);
+int air_conv_gemm_bf16(const void* a, long long a_ld, int B, int H, int W, int C, int Ho, int Wo,
+                       int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw, int mode,
+                       const void* wpk, int N, int K, void* out, long long out_ld,
+                       const float* bias, const void* res, long long res_ld, int relu,
+                       int num_sms, int flags, air_stream_t stream);
+
+/* Weight gradient (cuDNN wgrad in the reference's autograd): dW[n][kx] += sum_m dy[m][n] *
+ * im2col(x)[m][kx], kx = (tap, ci), accumulated with fp32 atomics into the caller-zeroed
+ * `dw_out` ([Cout][kh*kw*Cin] fp32, GEMM layout).  x: forward input (B,H,W,C) channels-last bf16,
+ * dy: (B,Ho,Wo,N) channels-last bf16; pixel strides x_ld / dy_ld in elements. */
+int air_conv_wgrad_bf16(const void* x, long long x_ld, int B, int H, int W, int C,
+                        const void* dy, long long dy_ld, int Ho, int Wo, int N,
+                        int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw,
+                        float* dw_out, int num_sms, int flags, air_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
