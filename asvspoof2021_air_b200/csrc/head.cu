@@ -1,0 +1,308 @@
+// Pooling / embedding head / loss kernels (fp32 math on small tensors; HBM- or latency-bound).
+//
+//   air_selfattn_pool_{fwd,bwd} : SelfAttention.forward, resnet.py:23-46 (+ autograd backward)
+//   air_linear_{fwd,bwd}        : nn.Linear fc / fc_mu / fc6 / fc7 (resnet.py:142-143,187-189;
+//                                 ecapa_tdnn.py:148-149,190-192)
+//   air_ocsoftmax_fwd_bwd       : OCSoftmax / AngularIsoLoss forward + analytic backward
+//                                 (loss.py:187-206 == :73-97) and the logged CE (main_train.py:355-357)
+#include "common.cuh"
+
+namespace air_head {
+
+// Counter-based Gaussian noise standing in for `1e-5*torch.randn(...)` (resnet.py:38): the same
+// value is regenerated in the backward from (seed, element index), so nothing is stored.
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16; return x;
+}
+__device__ __forceinline__ float gauss_noise(long long seed, long long idx) {
+  if (seed < 0) return 0.f;
+  const uint32_t lo = static_cast<uint32_t>(idx), hi = static_cast<uint32_t>(idx >> 32);
+  const uint32_t s0 = static_cast<uint32_t>(seed), s1 = static_cast<uint32_t>(seed >> 32);
+  const uint32_t a = mix32(lo ^ mix32(hi + 0x9e3779b9U) ^ s0);
+  const uint32_t b = mix32(a + 0x85ebca6bU + s1);
+  const float u1 = (static_cast<float>(a >> 8) + 1.0f) * (1.0f / 16777217.0f);   // (0, 1)
+  const float u2 = static_cast<float>(b >> 8) * (1.0f / 16777216.0f);
+  return 1e-5f * sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
+}
+
+// ------------------------------------------------------------------------------------------
+// SelfAttention pooling.  One CTA per utterance, blockDim.x == C (<= 1024, multiple of 32).
+//   x (B,T,C) bf16;  att (C);  stats (B,2C) = [sum_t x*p | unbiased std_t(x*p + noise)]
+//   saved: p (B,T) softmax weights, th (B,T) tanh(x . att)
+// ------------------------------------------------------------------------------------------
+__global__ void selfattn_pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ att,
+                                         float* __restrict__ stats, float* __restrict__ p_out, float* __restrict__ th_out,
+                                         int T, int C, long long seed) {
+  extern __shared__ float sh[];           // sw[T], red[32]
+  float* sw = sh;
+  float* red = sh + T;
+  const int b = blockIdx.x, c = threadIdx.x, warp = c >> 5, lane = c & 31, nw = C >> 5;
+  const __nv_bfloat16* xb = x + static_cast<long long>(b) * T * C;
+  for (int t = warp; t < T; t += nw) {
+    float acc = 0.f;
+    for (int k = lane; k < C; k += 32) acc = fmaf(bf2f(xb[t * C + k]), att[k], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) sw[t] = tanhf(acc);
+  }
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int t = c; t < T; t += C) mx = fmaxf(mx, sw[t]);
+  mx = block_max(mx, red);
+  float se = 0.f;
+  for (int t = c; t < T; t += C) se += expf(sw[t] - mx);
+  se = block_sum(se, red);
+  __syncthreads();
+  for (int t = c; t < T; t += C) {
+    const float th = sw[t];
+    const float pv = expf(th - mx) / se;
+    th_out[b * T + t] = th;
+    p_out[b * T + t] = pv;
+    sw[t] = pv;
+  }
+  __syncthreads();
+  float sum = 0.f, sumn = 0.f;
+  for (int t = 0; t < T; ++t) {
+    const float v = bf2f(xb[t * C + c]) * sw[t];
+    sum += v;
+    sumn += v + gauss_noise(seed, (static_cast<long long>(b) * T + t) * C + c);
+  }
+  const float mean = sumn / T;
+  float ss = 0.f;
+  for (int t = 0; t < T; ++t) {
+    const float v = bf2f(xb[t * C + c]) * sw[t] + gauss_noise(seed, (static_cast<long long>(b) * T + t) * C + c) - mean;
+    ss = fmaf(v, v, ss);
+  }
+  stats[static_cast<long long>(b) * 2 * C + c] = sum;
+  stats[static_cast<long long>(b) * 2 * C + C + c] = sqrtf(ss / (T - 1));
+}
+
+__global__ void selfattn_pool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ att,
+                                         const float* __restrict__ p_in, const float* __restrict__ th_in,
+                                         const float* __restrict__ stats, const float* __restrict__ dstats,
+                                         __nv_bfloat16* __restrict__ dx, float* __restrict__ datt,
+                                         int T, int C, long long seed) {
+  extern __shared__ float sh[];           // sp[T], sdp[T], sdw[T], dav[C], kk[C], mn[C], red[32]
+  float* sp = sh; float* sdp = sh + T; float* sdw = sh + 2 * T;
+  float* dav = sh + 3 * T; float* kk = dav + C; float* mn = kk + C; float* red = mn + C;
+  const int b = blockIdx.x, c = threadIdx.x, warp = c >> 5, lane = c & 31, nw = C >> 5;
+  const __nv_bfloat16* xb = x + static_cast<long long>(b) * T * C;
+  for (int t = c; t < T; t += C) sp[t] = p_in[b * T + t];
+  __syncthreads();
+  {
+    float sumn = 0.f;
+    for (int t = 0; t < T; ++t)
+      sumn += bf2f(xb[t * C + c]) * sp[t] + gauss_noise(seed, (static_cast<long long>(b) * T + t) * C + c);
+    const float sd = stats[static_cast<long long>(b) * 2 * C + C + c];
+    dav[c] = dstats[static_cast<long long>(b) * 2 * C + c];
+    // d std / d v_t = (v_t - mean) / ((T-1) std); a dead channel (std == 0) gets zero gradient
+    kk[c] = sd > 0.f ? dstats[static_cast<long long>(b) * 2 * C + C + c] / ((T - 1) * sd) : 0.f;
+    mn[c] = sumn / T;
+  }
+  __syncthreads();
+  for (int t = warp; t < T; t += nw) {            // dp[t] = sum_c dweighted[t][c] * x[t][c]
+    float acc = 0.f;
+    for (int k = lane; k < C; k += 32) {
+      const float xv = bf2f(xb[t * C + k]);
+      const float v = xv * sp[t] + gauss_noise(seed, (static_cast<long long>(b) * T + t) * C + k);
+      acc = fmaf(dav[k] + kk[k] * (v - mn[k]), xv, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) sdp[t] = acc;
+  }
+  __syncthreads();
+  float dot = 0.f;
+  for (int t = c; t < T; t += C) dot = fmaf(sp[t], sdp[t], dot);
+  dot = block_sum(dot, red);
+  __syncthreads();
+  for (int t = c; t < T; t += C) {
+    const float th = th_in[b * T + t];
+    sdw[t] = sp[t] * (sdp[t] - dot) * (1.f - th * th);     // softmax bwd then tanh bwd
+  }
+  __syncthreads();
+  const float a = att[c];
+  float da = 0.f;
+  for (int t = 0; t < T; ++t) {
+    const float xv = bf2f(xb[t * C + c]);
+    const float v = xv * sp[t] + gauss_noise(seed, (static_cast<long long>(b) * T + t) * C + c);
+    const float dwgt = dav[c] + kk[c] * (v - mn[c]);
+    dx[(static_cast<long long>(b) * T + t) * C + c] = f2bf(dwgt * sp[t] + sdw[t] * a);
+    da = fmaf(sdw[t], xv, da);
+  }
+  atomicAdd(&datt[c], da);
+}
+
+// ------------------------------------------------------------------------------------------
+// fp32 linear layer  y = x W^T + b   (x (M,K), W (N,K))
+// ------------------------------------------------------------------------------------------
+__global__ void linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
+                                  float* __restrict__ y, int M, int N, int K) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long o = warp; o < static_cast<long long>(M) * N; o += nwarps) {
+    const int m = static_cast<int>(o / N), n = static_cast<int>(o - static_cast<long long>(m) * N);
+    float acc = 0.f;
+    for (int k = lane; k < K; k += 32) acc = fmaf(x[static_cast<long long>(m) * K + k], W[static_cast<long long>(n) * K + k], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) y[o] = acc + (bias ? bias[n] : 0.f);
+  }
+}
+// dx[m][k] = sum_n dy[m][n] W[n][k]
+__global__ void linear_dx_kernel(const float* __restrict__ dy, const float* __restrict__ W, float* __restrict__ dx,
+                                 int M, int N, int K) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < static_cast<long long>(M) * K;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int m = static_cast<int>(i / K), k = static_cast<int>(i - static_cast<long long>(m) * K);
+    float acc = 0.f;
+    for (int n = 0; n < N; ++n) acc = fmaf(dy[static_cast<long long>(m) * N + n], W[static_cast<long long>(n) * K + k], acc);
+    dx[i] = acc;
+  }
+}
+// dW[n][k] += sum_m dy[m][n] x[m][k];  db[n] += sum_m dy[m][n]
+__global__ void linear_dw_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dW,
+                                 float* __restrict__ db, int M, int N, int K) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < static_cast<long long>(N) * K;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(i / K), k = static_cast<int>(i - static_cast<long long>(n) * K);
+    float acc = 0.f;
+    for (int m = 0; m < M; ++m) acc = fmaf(dy[static_cast<long long>(m) * N + n], x[static_cast<long long>(m) * K + k], acc);
+    dW[i] += acc;
+    if (k == 0 && db) {
+      float s = 0.f;
+      for (int m = 0; m < M; ++m) s += dy[static_cast<long long>(m) * N + n];
+      db[n] += s;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// OC-Softmax forward + backward (single CTA, 256 threads).
+//   loss = mean_i softplus(alpha * m_i),  m_i = r_real - s_i (label 0) | s_i - r_fake (label 1) | s_i
+//   s_i = <x_i/|x_i|, w/|w|>, score_i = -s_i.   softplus: beta 1, threshold 20.
+//   dfeat = grad_scale * dloss/dx, dcenter += grad_scale * dloss/dcenter.
+// Optional CE over `logits` (B, ncls) for logging only.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ocsoftmax_kernel(const float* __restrict__ x, const long long* __restrict__ labels,
+                                                         const float* __restrict__ center, int B, int D,
+                                                         float r_real, float r_fake, float alpha, float grad_scale,
+                                                         float* __restrict__ loss_out, float* __restrict__ score,
+                                                         float* __restrict__ dfeat, float* __restrict__ dcenter,
+                                                         const float* __restrict__ logits, int ncls, float* __restrict__ ce_out) {
+  extern __shared__ float sh[];           // wn[D], s[B], coef[B], rinv[B], red[32]
+  float* wn = sh; float* ss = sh + D; float* coef = ss + B; float* rinv = coef + B; float* red = rinv + B;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+  float wsq = 0.f;
+  for (int d = tid; d < D; d += blockDim.x) wsq = fmaf(center[d], center[d], wsq);
+  wsq = block_sum(wsq, red);
+  const float wnorm = fmaxf(sqrtf(wsq), 1e-12f);
+  for (int d = tid; d < D; d += blockDim.x) wn[d] = center[d] / wnorm;
+  __syncthreads();
+  float lsum = 0.f;
+  for (int i = warp; i < B; i += nw) {
+    float xx = 0.f, xw = 0.f;
+    for (int d = lane; d < D; d += 32) { const float v = x[static_cast<long long>(i) * D + d]; xx = fmaf(v, v, xx); xw = fmaf(v, wn[d], xw); }
+    xx = warp_sum(xx); xw = warp_sum(xw);
+    if (lane == 0) {
+      const float xn = fmaxf(sqrtf(xx), 1e-12f);
+      const float s = xw / xn;
+      const long long lab = labels ? labels[i] : 0;
+      float m = s, sign = 1.f;
+      if (lab == 0) { m = r_real - s; sign = -1.f; } else if (lab == 1) { m = s - r_fake; }
+      const float z = alpha * m;
+      const float sp = z > 20.f ? z : log1pf(expf(z));
+      const float dsp = z > 20.f ? 1.f : 1.f / (1.f + expf(-z));
+      lsum += sp;
+      ss[i] = s; rinv[i] = 1.f / xn;
+      coef[i] = grad_scale * sign * alpha * dsp / B;          // dloss/ds_i
+      if (score) score[i] = -s;
+    }
+  }
+  lsum = block_sum(lsum, red);
+  if (tid == 0 && loss_out) loss_out[0] = lsum / B;
+  __syncthreads();
+  if (dfeat) {
+    for (long long j = tid; j < static_cast<long long>(B) * D; j += blockDim.x) {
+      const int i = static_cast<int>(j / D), d = static_cast<int>(j - static_cast<long long>(i) * D);
+      const float xh = x[j] * rinv[i];
+      dfeat[j] = coef[i] * (wn[d] - ss[i] * xh) * rinv[i];
+    }
+  }
+  if (dcenter) {
+    for (int d = tid; d < D; d += blockDim.x) {
+      float acc = 0.f;
+      for (int i = 0; i < B; ++i) acc = fmaf(coef[i], x[static_cast<long long>(i) * D + d] * rinv[i] - ss[i] * wn[d], acc);
+      dcenter[d] += acc / wnorm;
+    }
+  }
+  if (logits && ce_out) {
+    float cs = 0.f;
+    for (int i = tid; i < B; i += blockDim.x) {
+      float mx = -INFINITY;
+      for (int k = 0; k < ncls; ++k) mx = fmaxf(mx, logits[i * ncls + k]);
+      float se = 0.f;
+      for (int k = 0; k < ncls; ++k) se += expf(logits[i * ncls + k] - mx);
+      const long long lab = labels ? labels[i] : 0;
+      cs += (mx + logf(se)) - logits[i * ncls + (lab >= 0 && lab < ncls ? lab : 0)];
+    }
+    cs = block_sum(cs, red);
+    if (tid == 0) ce_out[0] = cs / B;
+  }
+}
+
+}  // namespace air_head
+
+using namespace air_head;
+
+extern "C" int air_selfattn_pool_fwd(const void* x, const float* att, float* stats, float* p_out, float* th_out,
+                                     int B, int T, int C, long long noise_seed, cudaStream_t stream) {
+  if (!x || !att || !stats || !p_out || !th_out || B <= 0 || T < 2 || C % 32 != 0 || C > 1024) return AIR_ERR_ARG;
+  selfattn_pool_fwd_kernel<<<B, C, (T + 32) * sizeof(float), stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), att, stats, p_out, th_out, T, C, noise_seed);
+  return air_launch_status();
+}
+
+extern "C" int air_selfattn_pool_bwd(const void* x, const float* att, const float* p_in, const float* th_in,
+                                     const float* stats, const float* dstats, void* dx, float* datt,
+                                     int B, int T, int C, long long noise_seed, cudaStream_t stream) {
+  if (!x || !att || !p_in || !th_in || !stats || !dstats || !dx || !datt || B <= 0 || T < 2 || C % 32 != 0 || C > 1024)
+    return AIR_ERR_ARG;
+  selfattn_pool_bwd_kernel<<<B, C, (3 * T + 3 * C + 32) * sizeof(float), stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), att, p_in, th_in, stats, dstats,
+      reinterpret_cast<__nv_bfloat16*>(dx), datt, T, C, noise_seed);
+  return air_launch_status();
+}
+
+extern "C" int air_linear_fwd(const float* x, const float* W, const float* bias, float* y, int M, int N, int K,
+                              cudaStream_t stream) {
+  if (!x || !W || !y || M <= 0 || N <= 0 || K <= 0) return AIR_ERR_ARG;
+  const long long warps = static_cast<long long>(M) * N;
+  const int blocks = static_cast<int>(std::min<long long>((warps + 7) / 8, 148 * 16));
+  linear_fwd_kernel<<<blocks, 256, 0, stream>>>(x, W, bias, y, M, N, K);
+  return air_launch_status();
+}
+
+extern "C" int air_linear_bwd(const float* x, const float* W, const float* dy, float* dx, float* dW, float* db,
+                              int M, int N, int K, cudaStream_t stream) {
+  if (!x || !W || !dy || M <= 0 || N <= 0 || K <= 0) return AIR_ERR_ARG;
+  if (dx) {
+    const int blocks = static_cast<int>(std::min<long long>((static_cast<long long>(M) * K + 255) / 256, 148 * 16));
+    linear_dx_kernel<<<blocks, 256, 0, stream>>>(dy, W, dx, M, N, K);
+  }
+  if (dW) {
+    const int blocks = static_cast<int>(std::min<long long>((static_cast<long long>(N) * K + 255) / 256, 148 * 16));
+    linear_dw_kernel<<<blocks, 256, 0, stream>>>(dy, x, dW, db, M, N, K);
+  }
+  return air_launch_status();
+}
+
+extern "C" int air_ocsoftmax_fwd_bwd(const float* x, const long long* labels, const float* center, int B, int D,
+                                     float r_real, float r_fake, float alpha, float grad_scale,
+                                     float* loss, float* score, float* dfeat, float* dcenter,
+                                     const float* logits, int ncls, float* ce, cudaStream_t stream) {
+  if (!x || !center || B <= 0 || D <= 0) return AIR_ERR_ARG;
+  const size_t smem = (static_cast<size_t>(D) + 3 * static_cast<size_t>(B) + 32) * sizeof(float);
+  if (smem > 48 * 1024) return AIR_ERR_UNSUPPORTED;
+  ocsoftmax_kernel<<<1, 256, smem, stream>>>(x, labels, center, B, D, r_real, r_fake, alpha, grad_scale,
+                                              loss, score, dfeat, dcenter, logits, ncls, ce);
+  return air_launch_status();
+}
