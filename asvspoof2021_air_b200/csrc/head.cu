@@ -5,6 +5,7 @@
 //                                 ecapa_tdnn.py:148-149,190-192)
 //   air_ocsoftmax_fwd_bwd       : OCSoftmax / AngularIsoLoss forward + analytic backward
 //                                 (loss.py:187-206 == :73-97) and the logged CE (main_train.py:355-357)
+#include <algorithm>
 #include "common.cuh"
 
 namespace air_head {

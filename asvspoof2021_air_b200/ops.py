@@ -58,3 +58,76 @@ def conv_wgrad(x, x_ld, B, H, W, C, dy, dy_ld, Ho, Wo, N, kh, kw, sh, sw, ph, pw
 
 def conv_out_size(n, k, s, p, d):
     return (n + 2 * p - d * (k - 1) - 1) // s + 1
+
+
+# ------------------------------------------------------------------------------------------
+# BatchNorm / stem / head / loss / optimiser wrappers
+# ------------------------------------------------------------------------------------------
+def bn_stats(x, x_ld, M, C, sums):
+    _lib.check(_lib.lib().air_bn_stats(_lib.ptr(x), _lib.LL(x_ld), _lib.LL(M), C, _lib.ptr(sums), num_sms(),
+                                       _lib.stream_ptr()), "air_bn_stats")
+
+
+def bn_apply(x, x_ld, y, y_ld, M, C, sums, gamma, beta, relu, training, save_mean, save_invstd,
+             running_mean, running_var, eps=1e-5, momentum=0.1):
+    _lib.check(_lib.lib().air_bn_apply(
+        _lib.ptr(x), _lib.LL(x_ld), _lib.ptr(y), _lib.LL(y_ld), _lib.LL(M), C, _lib.ptr(sums), _lib.ptr(gamma),
+        _lib.ptr(beta), _lib.F(eps), int(relu), int(training), _lib.ptr(save_mean), _lib.ptr(save_invstd),
+        _lib.ptr(running_mean), _lib.ptr(running_var), _lib.F(momentum), num_sms(), _lib.stream_ptr()), "air_bn_apply")
+
+
+def bn_bwd(dy, dy_ld, x, x_ld, add, add_ld, dx, dx_ld, M, C, order, mean, invstd, gamma, beta, rsum, dgamma, dbeta):
+    _lib.check(_lib.lib().air_bn_bwd(
+        _lib.ptr(dy), _lib.LL(dy_ld), _lib.ptr(x), _lib.LL(x_ld), _lib.ptr(add), _lib.LL(add_ld), _lib.ptr(dx),
+        _lib.LL(dx_ld), _lib.LL(M), C, order, _lib.ptr(mean), _lib.ptr(invstd), _lib.ptr(gamma), _lib.ptr(beta),
+        _lib.ptr(rsum), _lib.ptr(dgamma), _lib.ptr(dbeta), num_sms(), _lib.stream_ptr()), "air_bn_bwd")
+
+
+def stem_fwd(x, B, H, W, kh, kw, sh, sw, ph, pw, w, cout, y):
+    _lib.check(_lib.lib().air_stem_conv_fwd(_lib.ptr(x), B, H, W, kh, kw, sh, sw, ph, pw, _lib.ptr(w), cout,
+                                            _lib.ptr(y), _lib.stream_ptr()), "air_stem_conv_fwd")
+
+
+def stem_wgrad(x, B, H, W, kh, kw, sh, sw, ph, pw, dy, cout, dw):
+    _lib.check(_lib.lib().air_stem_conv_wgrad(_lib.ptr(x), B, H, W, kh, kw, sh, sw, ph, pw, _lib.ptr(dy), cout,
+                                              _lib.ptr(dw), _lib.stream_ptr()), "air_stem_conv_wgrad")
+
+
+def selfattn_pool_fwd(x, att, stats, p, th, B, T, C, seed=-1):
+    _lib.check(_lib.lib().air_selfattn_pool_fwd(_lib.ptr(x), _lib.ptr(att), _lib.ptr(stats), _lib.ptr(p), _lib.ptr(th),
+                                                B, T, C, _lib.LL(seed), _lib.stream_ptr()), "air_selfattn_pool_fwd")
+
+
+def selfattn_pool_bwd(x, att, p, th, stats, dstats, dx, datt, B, T, C, seed=-1):
+    _lib.check(_lib.lib().air_selfattn_pool_bwd(_lib.ptr(x), _lib.ptr(att), _lib.ptr(p), _lib.ptr(th), _lib.ptr(stats),
+                                                _lib.ptr(dstats), _lib.ptr(dx), _lib.ptr(datt), B, T, C, _lib.LL(seed),
+                                                _lib.stream_ptr()), "air_selfattn_pool_bwd")
+
+
+def linear_fwd(x, W, bias, y, M, N, K):
+    _lib.check(_lib.lib().air_linear_fwd(_lib.ptr(x), _lib.ptr(W), _lib.ptr(bias), _lib.ptr(y), M, N, K,
+                                         _lib.stream_ptr()), "air_linear_fwd")
+
+
+def linear_bwd(x, W, dy, dx, dW, db, M, N, K):
+    _lib.check(_lib.lib().air_linear_bwd(_lib.ptr(x), _lib.ptr(W), _lib.ptr(dy), _lib.ptr(dx), _lib.ptr(dW), _lib.ptr(db),
+                                         M, N, K, _lib.stream_ptr()), "air_linear_bwd")
+
+
+def ocsoftmax(x, labels, center, B, D, r_real, r_fake, alpha, grad_scale, loss, score, dfeat, dcenter,
+              logits=None, ncls=0, ce=None):
+    _lib.check(_lib.lib().air_ocsoftmax_fwd_bwd(
+        _lib.ptr(x), _lib.ptr(labels), _lib.ptr(center), B, D, _lib.F(r_real), _lib.F(r_fake), _lib.F(alpha),
+        _lib.F(grad_scale), _lib.ptr(loss), _lib.ptr(score), _lib.ptr(dfeat), _lib.ptr(dcenter), _lib.ptr(logits),
+        ncls, _lib.ptr(ce), _lib.stream_ptr()), "air_ocsoftmax_fwd_bwd")
+
+
+def adam_l2_step(p, g, m, v, n, lr, beta1, beta2, eps, wd, step, grad_scale=1.0):
+    _lib.check(_lib.lib().air_adam_l2_step(_lib.ptr(p), _lib.ptr(g), _lib.ptr(m), _lib.ptr(v), _lib.LL(n), _lib.F(lr),
+                                           _lib.F(beta1), _lib.F(beta2), _lib.F(eps), _lib.F(wd), int(step),
+                                           _lib.F(grad_scale), _lib.stream_ptr()), "air_adam_l2_step")
+
+
+def sgd_step(p, g, n, lr, grad_scale=1.0):
+    _lib.check(_lib.lib().air_sgd_step(_lib.ptr(p), _lib.ptr(g), _lib.LL(n), _lib.F(lr), _lib.F(grad_scale),
+                                       _lib.stream_ptr()), "air_sgd_step")

@@ -1,0 +1,100 @@
+"""The fused train / score step: raw waves in, optimiser step (or scores) out, all on device.
+
+Mirrors the step body of main_train.py:310-418 for `--add_loss ang_iso` (OC-Softmax) --
+LFCC (fused, replaces preprocess.py + dataset.py crop/pad) -> model -> CE (logged) -> OC-Softmax ->
+backward -> Adam(L2) on the model + SGD on the centre -- with no host synchronisation inside the
+step and, under data parallelism, one NCCL all-reduce of the flat gradient buffer.
+"""
+import torch
+
+from . import ops
+from .feature_extraction import LFCC
+
+BF16 = torch.bfloat16
+
+
+class Trainer:
+    def __init__(self, arch="resnet", enc_dim=256, feat_len=750, padding="repeat", lr=5e-4, beta_1=0.9,
+                 beta_2=0.999, eps=1e-8, weight_decay=5e-4, r_real=0.9, r_fake=0.2, alpha=20.0,
+                 weight_loss=1.0, device="cuda", process_group=None, seed=None):
+        self.arch, self.feat_len, self.padding = arch, feat_len, padding
+        self.lr, self.betas, self.eps, self.wd = lr, (beta_1, beta_2), eps, weight_decay
+        self.r_real, self.r_fake, self.alpha, self.weight_loss = r_real, r_fake, alpha, weight_loss
+        self.device = torch.device(device)
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None:
+            import torch.distributed as dist
+            self.world = dist.get_world_size(process_group)
+        self.lfcc = LFCC(320, 160, 512, 16000, 20).to(self.device)
+        if arch == "resnet":
+            from .engine import ResNetEngine
+            self.engine = ResNetEngine(enc_dim=enc_dim, nclasses=2, device=self.device)
+            self.layout = "resnet"
+        elif arch == "ecapa":
+            from .engine_ecapa import EcapaEngine
+            self.engine = EcapaEngine(device=self.device)
+            self.layout = "ecapa"
+        else:
+            raise ValueError(arch)
+        if seed is not None:
+            self.engine.init_parameters(seed)
+        g = torch.Generator().manual_seed(0 if seed is None else seed)
+        c = torch.randn(1, enc_dim, generator=g)
+        torch.nn.init.kaiming_uniform_(c, 0.25, generator=g)          # loss.py:183-184
+        self.center = c.to(self.device)
+        self.center_grad = torch.zeros_like(self.center)
+        self.loss = torch.zeros(1, device=self.device)
+        self.ce = torch.zeros(1, device=self.device)
+        self.x0 = None
+        self.dfeat = None
+        self.score = None
+        self.launches = 0
+
+    # ------------------------------------------------------------------------------------
+    def features(self, waves, lengths=None, start=None):
+        B = waves.shape[0]
+        shape = (B, 1, 60, self.feat_len) if self.layout == "resnet" else (B, self.feat_len, 64)
+        if self.x0 is None or tuple(self.x0.shape) != shape:
+            self.x0 = torch.zeros(shape, device=self.device, dtype=BF16)
+        self.lfcc.extract(waves, lengths=lengths, feat_len=self.feat_len, padding=self.padding, start=start,
+                          layout=self.layout, dtype=BF16, out=self.x0)
+        return self.x0[:, 0] if self.layout == "resnet" else self.x0
+
+    def train_step(self, waves, labels, lengths=None, start=None, lr=None):
+        """One optimiser step on a (B, L) fp32 wave batch; returns the device loss tensor (no sync)."""
+        eng = self.engine
+        B = waves.shape[0]
+        x0 = self.features(waves, lengths, start)
+        feat, logits = eng.forward(x0, training=True)
+        if self.dfeat is None or self.dfeat.shape[0] != B:
+            self.dfeat = torch.empty(B, feat.shape[1], device=self.device)
+            self.score = torch.empty(B, device=self.device)
+        eng.zero_grad()
+        self.center_grad.zero_()
+        ops.ocsoftmax(feat, labels, self.center, B, feat.shape[1], self.r_real, self.r_fake, self.alpha,
+                      self.weight_loss, self.loss, self.score, self.dfeat, self.center_grad, logits, logits.shape[1], self.ce)
+        eng.backward(self.dfeat)
+        scale = 1.0
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(eng.store.grads[:eng.store.n_train], group=self.pg)
+            dist.all_reduce(self.center_grad, group=self.pg)
+            scale = 1.0 / self.world
+        lr = self.lr if lr is None else lr
+        eng.store.adam_step(lr, self.betas[0], self.betas[1], self.eps, self.wd, grad_scale=scale)
+        ops.sgd_step(self.center, self.center_grad, self.center.numel(), lr, scale)
+        return self.loss
+
+    @torch.no_grad()
+    def score_step(self, waves, lengths=None, start=None):
+        """generate_score.py:84-119: eval-mode forward, returns +cos(feat, centre) per utterance."""
+        eng = self.engine
+        B = waves.shape[0]
+        x0 = self.features(waves, lengths, start)
+        feat, logits = eng.forward(x0, training=False)
+        if self.score is None or self.score.shape[0] != B:
+            self.score = torch.empty(B, device=self.device)
+        ops.ocsoftmax(feat, None, self.center, B, feat.shape[1], self.r_real, self.r_fake, self.alpha, 1.0,
+                      None, self.score, None, None)
+        return -self.score

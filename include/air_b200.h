@@ -89,6 +89,64 @@ int air_conv_wgrad_bf16(const void* x, long long x_ld, int B, int H, int W, int 
                         int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw,
                         float* dw_out, int num_sms, int flags, air_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * BatchNorm (+ReLU) on channels-last bf16 (nn.BatchNorm2d/1d + F.relu: resnet.py:54-69,132,141;
+ * ecapa_tdnn.py:40,51,57,113 and their autograd backward).  eps / momentum as nn.BatchNorm.
+ *   air_bn_stats : sums[0..C) += sum_m x, sums[C..2C) += sum_m x^2 (fp64, caller-zeroed)
+ *   air_bn_apply : y = [relu](gamma*(x-mean)*invstd+beta); training != 0 uses `sums` (biased var),
+ *                  saves mean/invstd and updates running stats (unbiased var); else running stats
+ *   air_bn_bwd   : order 0 (y = relu(bn(x))): dx from dy = dL/dy;  order 1 (y = bn(x), x = relu(.)):
+ *                  dx additionally masked by x > 0.  `add` (optional) is added to dx.  dgamma/dbeta are
+ *                  accumulated (+=).  rsum: 2C fp64 workspace, caller-zeroed.
+ * --------------------------------------------------------------------------------------------- */
+int air_bn_stats(const void* x, long long x_ld, long long M, int C, double* sums, int num_sms, air_stream_t stream);
+int air_bn_apply(const void* x, long long x_ld, void* y, long long y_ld, long long M, int C,
+                 const double* sums, const float* gamma, const float* beta, float eps, int relu,
+                 int training, float* save_mean, float* save_invstd, float* running_mean,
+                 float* running_var, float momentum, int num_sms, air_stream_t stream);
+int air_bn_bwd(const void* dy, long long dy_ld, const void* x, long long x_ld, const void* add, long long add_ld,
+               void* dx, long long dx_ld, long long M, int C, int order,
+               const float* mean, const float* invstd, const float* gamma, const float* beta,
+               double* rsum, float* dgamma, float* dbeta, int num_sms, air_stream_t stream);
+
+/* ResNet stem conv (Cin = 1, Cout = 16; resnet.py:131,176): direct CUDA-core forward / wgrad. */
+int air_stem_conv_fwd(const void* x, int B, int H, int W, int kh, int kw, int sh, int sw, int ph, int pw,
+                      const float* w, int Cout, void* y, air_stream_t stream);
+int air_stem_conv_wgrad(const void* x, int B, int H, int W, int kh, int kw, int sh, int sw, int ph, int pw,
+                        const void* dy, int Cout, float* dw, air_stream_t stream);
+
+/* SelfAttention pooling (resnet.py:23-46): x (B,T,C) bf16 -> stats (B,2C) fp32 = [avg | std];
+ * saves softmax weights p (B,T) and tanh scores th (B,T).  noise_seed >= 0 adds the reference's
+ * 1e-5*N(0,1) noise (counter-based, regenerated in the backward); < 0 disables it.
+ * Backward: dx (B,T,C) bf16, datt (C) accumulated. */
+int air_selfattn_pool_fwd(const void* x, const float* att, float* stats, float* p_out, float* th_out,
+                          int B, int T, int C, long long noise_seed, air_stream_t stream);
+int air_selfattn_pool_bwd(const void* x, const float* att, const float* p_in, const float* th_in,
+                          const float* stats, const float* dstats, void* dx, float* datt,
+                          int B, int T, int C, long long noise_seed, air_stream_t stream);
+
+/* fp32 nn.Linear: y = x W^T + b;  backward: dx (optional), dW += , db += (optional). */
+int air_linear_fwd(const float* x, const float* W, const float* bias, float* y, int M, int N, int K,
+                   air_stream_t stream);
+int air_linear_bwd(const float* x, const float* W, const float* dy, float* dx, float* dW, float* db,
+                   int M, int N, int K, air_stream_t stream);
+
+/* OCSoftmax / AngularIsoLoss forward + analytic backward (loss.py:187-206 == :73-97) and the logged
+ * CrossEntropy (main_train.py:355-357).  labels int64 (NULL: all 0).  Outputs (each optional):
+ * loss (1), score (B) = -cos, dfeat (B,D) = grad_scale*dloss/dx, dcenter (D) += grad_scale*dloss/dc,
+ * ce (1) from logits (B,ncls). */
+int air_ocsoftmax_fwd_bwd(const float* x, const long long* labels, const float* center, int B, int D,
+                          float r_real, float r_fake, float alpha, float grad_scale,
+                          float* loss, float* score, float* dfeat, float* dcenter,
+                          const float* logits, int ncls, float* ce, air_stream_t stream);
+
+/* Optimiser steps on flat fp32 buffers: Adam with coupled L2 (main_train.py:175,408; `step` 1-based)
+ * and SGD (main_train.py:272,409).  grad_scale multiplies the gradient (1/world_size under DP). */
+int air_adam_l2_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, int step, float grad_scale,
+                     air_stream_t stream);
+int air_sgd_step(float* p, const float* g, long long n, float lr, float grad_scale, air_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

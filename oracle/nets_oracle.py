@@ -46,29 +46,43 @@ def self_attention_pool(x, att_weights, noise=None):
     return torch.cat((avg, std), 1)
 
 
-def _preact_block(sd, p, x, stride, training, upd):
-    """resnet.py:63-69."""
-    out = F.relu(_bn(sd, p + ".bn1", x, training, upd))
+def _q_none(t):
+    return t
+
+
+def _q_bf16(t):
+    """Round to bf16 and back (differentiable: gradient passes straight through)."""
+    return t.to(torch.bfloat16).float()
+
+
+def _preact_block(sd, p, x, stride, training, upd, q=_q_none):
+    """resnet.py:63-69.  q marks the points where the bf16 tensor-core path stores bf16."""
+    out = q(F.relu(_bn(sd, p + ".bn1", x, training, upd)))
     if (p + ".shortcut.0.weight") in sd:
-        sc = F.conv2d(out, sd[p + ".shortcut.0.weight"], stride=stride)
+        sc = q(F.conv2d(out, q(sd[p + ".shortcut.0.weight"]), stride=stride))
     else:
         sc = x
-    out = F.conv2d(out, sd[p + ".conv1.weight"], stride=stride, padding=1)
-    out = F.conv2d(F.relu(_bn(sd, p + ".bn2", out, training, upd)), sd[p + ".conv2.weight"],
+    out = q(F.conv2d(out, q(sd[p + ".conv1.weight"]), stride=stride, padding=1))
+    out = F.conv2d(q(F.relu(_bn(sd, p + ".bn2", out, training, upd))), q(sd[p + ".conv2.weight"]),
                    stride=1, padding=1)
-    return out + sc
+    return q(out + sc)
 
 
-def resnet_forward(sd, x, training=True, noise=None, update_running=False):
-    """x (B,1,60,T) -> (feat (B,enc_dim), mu (B,nclasses)).  resnet.py:174-191."""
+def resnet_forward(sd, x, training=True, noise=None, update_running=False, bf16_points=False):
+    """x (B,1,60,T) -> (feat (B,enc_dim), mu (B,nclasses)).  resnet.py:174-191.
+
+    bf16_points=True rounds activations / conv weights to bf16 at exactly the points where the
+    sm_100a path stores bf16 (everything else stays fp32): the oracle for kernel-level parity of
+    the bf16 tensor-core path; bf16_points=False is the reference's fp32 arithmetic."""
     upd = update_running
-    x = F.conv2d(x, sd["conv1.weight"], stride=(3, 1), padding=(1, 1))       # :131,176
-    x = F.relu(_bn(sd, "bn1", x, training, upd))
+    q = _q_bf16 if bf16_points else _q_none
+    x = q(F.conv2d(q(x), sd["conv1.weight"], stride=(3, 1), padding=(1, 1)))  # :131,176
+    x = q(F.relu(_bn(sd, "bn1", x, training, upd)))
     for li, stride in ((1, 1), (2, 2), (3, 2), (4, 2)):                      # :135-138
-        x = _preact_block(sd, "layer%d.0" % li, x, stride, training, upd)
-        x = _preact_block(sd, "layer%d.1" % li, x, 1, training, upd)
-    x = F.conv2d(x, sd["conv5.weight"], stride=1, padding=(0, 1))            # :140
-    x = F.relu(_bn(sd, "bn5", x, training, upd)).squeeze(2)                  # (B,256,T')
+        x = _preact_block(sd, "layer%d.0" % li, x, stride, training, upd, q)
+        x = _preact_block(sd, "layer%d.1" % li, x, 1, training, upd, q)
+    x = q(F.conv2d(x, q(sd["conv5.weight"]), stride=1, padding=(0, 1)))       # :140
+    x = q(F.relu(_bn(sd, "bn5", x, training, upd))).squeeze(2)               # (B,256,T')
     stats = self_attention_pool(x.permute(0, 2, 1), sd["attention.att_weights"], noise)
     feat = F.linear(stats, sd["fc.weight"], sd["fc.bias"])
     mu = F.linear(feat, sd["fc_mu.weight"], sd["fc_mu.bias"])
