@@ -38,7 +38,11 @@ def lib():
     return _lib
 
 
-def check(status, what):
+LAUNCHES = [0]        # kernels launched through the C ABI by this process (bench.py reports it)
+
+
+def check(status, what, n=1):
+    LAUNCHES[0] += n
     if status != 0:
         kind = "argument error" if status < 0 else "CUDA error"
         raise AirError("%s failed: %s %d" % (what, kind, status))

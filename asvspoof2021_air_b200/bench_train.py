@@ -1,0 +1,233 @@
+"""Train-step / scoring workloads of bench.py (resnet_train, ecapa_train, ecapa_score).
+
+A "step" is one pass of the hot path over one batch of synthetic 4 s @ 16 kHz waves:
+wave -> fused LFCC -> net forward -> OC-Softmax -> backward -> [NCCL all-reduce] -> Adam/SGD
+(SURVEY.md section 8d).  `value` has the waves resident in HBM; `e2e` goes through the public
+Trainer API from pinned host memory (H2D of every step's waves and D2H of its loss inside the
+timed region, double-buffered on a copy stream).  The roofline pass re-runs a few steps with CUDA
+events around every C-ABI launch (ops.Profile) and reports the conv stack against the measured
+bf16 peak; the unprofiled timed region is what `value` comes from.
+"""
+import os
+import time
+
+import torch
+
+WAVE_LEN = 64000
+# algorithmic conv/linear FLOPs per utterance of one train step
+TRAIN_FLOPS_PER_UTT = {"resnet": 47.12e9, "ecapa": 22.86e9}
+FWD_FLOPS_PER_UTT = {"resnet": 15.709e9, "ecapa": 7.698e9}
+
+
+def _labels(B, seed):
+    g = torch.Generator().manual_seed(seed + 7)
+    lab = torch.randint(0, 2, (B,), generator=g)
+    lab[0], lab[1] = 0, 1                   # both classes present
+    return lab
+
+
+def _waves(B, seed):
+    g = torch.Generator().manual_seed(seed)
+    return 0.1 * torch.randn(B, WAVE_LEN, generator=g)
+
+
+def run(args, rank, world, helpers):
+    from . import _lib, ops
+    from .trainer import Trainer
+    arch = "resnet" if args.workload.startswith("resnet") else "ecapa"
+    scoring = args.workload.endswith("_score")
+    B = args.batch or (1024 if scoring else 256)
+    pg = None
+    if world > 1:
+        import torch.distributed as dist
+        pg = dist.group.WORLD
+    tr = Trainer(arch=arch, device="cuda", process_group=pg, seed=688)
+    nbuf = 2
+    waves = [_waves(B, rank * 16 + i).cuda() for i in range(nbuf)]
+    labels = _labels(B, rank).cuda()
+
+    def step(i):
+        if scoring:
+            tr.score_step(waves[i % nbuf])
+        else:
+            tr.train_step(waves[i % nbuf], labels)
+
+    step(0)                                   # allocate activations / pack weights outside the timing
+    torch.cuda.synchronize()
+    sampler = helpers.ClockSampler(torch.cuda.current_device())
+    sampler.start()
+    l0 = _lib.LAUNCHES[0]
+    ms = helpers.timed(step, args.steps, args.warmup, world)
+    launches = (_lib.LAUNCHES[0] - l0) * args.steps // (args.steps + args.warmup)
+    clocks = sampler.stop()
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- e2e: pinned host waves -> H2D (copy stream, double-buffered) -> step -> D2H loss ----
+    host = [w.cpu().pin_memory() for w in waves]
+    dev = [torch.empty_like(waves[0]) for _ in range(2)]
+    res_host = torch.empty(B if scoring else 1, pin_memory=True)
+    copy_stream = torch.cuda.Stream()
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    main = torch.cuda.current_stream()
+
+    def issue_copy(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[i % 2])
+            dev[i % 2].copy_(host[i % nbuf], non_blocking=True)
+            ready[i % 2].record(copy_stream)
+
+    for e in consumed:
+        e.record(main)
+    state = {"next": 0}
+
+    def step_e2e(i):
+        while state["next"] <= i + 1:          # this step's waves + prefetch of the next step's
+            issue_copy(state["next"])
+            state["next"] += 1
+        main.wait_event(ready[i % 2])
+        out = tr.score_step(dev[i % 2]) if scoring else tr.train_step(dev[i % 2], labels)
+        consumed[i % 2].record(main)
+        res_host.copy_(out.reshape(-1), non_blocking=True)
+        main.synchronize()                     # the user reads the loss / scores every step
+
+    ms_e2e = helpers.timed(step_e2e, args.steps, args.warmup, world)
+    e2e = world * B * args.steps / (ms_e2e / 1e3)
+
+    # ---- roofline pass: per-family device time over a few profiled steps ----
+    peaks = helpers.measured_peaks()
+    nprof = 3
+    with ops.Profile() as prof:
+        for i in range(nprof):
+            step(i)
+    fam = prof.summary()
+    conv = {k: v for k, v in fam.items() if k.startswith("conv_")}
+    conv_ms = sum(v["ms"] for v in conv.values())
+    conv_flops = sum(v["flops"] for v in conv.values())
+    total_ms = sum(v["ms"] for v in fam.values())
+    achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+    peak = peaks["bf16_tflops_sustained"]
+    breakdown = {k: {"ms_per_step": round(v["ms"] / nprof, 4), "launches_per_step": v["launches"] // nprof,
+                     **({"tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1)} if v["flops"] else {})}
+                 for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
+    flops_per_utt = (FWD_FLOPS_PER_UTT if scoring else TRAIN_FLOPS_PER_UTT)[arch]
+    name = {"resnet": "ResNet-18-OC", "ecapa": "ECAPA-TDNN-512"}[arch]
+    line = {
+        "metric": "utterances/sec (4 s@16 kHz) %s" % ("scoring" if scoring else "train-step"),
+        "value": value, "unit": "utterances/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "%s: wave->LFCC->%s %s + OC-Softmax%s, B=%d/GPU, 4 s @ 16 kHz, feat_len 750 (repeat pad)"
+                   % (args.workload, name, "eval forward" if scoring else "fwd/bwd",
+                      "" if scoring else " + Adam(L2)/SGD", B),
+                   "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
+                   "l2": "per-step activations (> 4 GB) exceed the 126 MB L2; waves rotate over %d buffers" % nbuf},
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                     "frac": achieved / peak if peak else None, "traffic": None, "peak_src": peaks["src"] + " (sustained)",
+                     "kernel": "conv stack: air_gemm::conv_gemm_kernel (fprop+dgrad) + air_wgrad::conv_wgrad_kernel",
+                     "flops_per_step": conv_flops / nprof, "conv_ms_per_step": conv_ms / nprof,
+                     "conv_share_of_step": conv_ms / total_ms if total_ms else None,
+                     "whole_step_tflops": B * flops_per_utt / (ms / args.steps / 1e3) / 1e12},
+        "kernels": breakdown,
+        "e2e": {"value": e2e, "unit": "utterances/s", "h2d_bytes_per_step": B * WAVE_LEN * 4,
+                "d2h_bytes_per_step": int(res_host.numel()) * 4, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches, "clocks": clocks,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(arch, scoring, seconds=15.0)
+    return line
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path (torch-CPU LFCC feature_extraction.py:93-138 ->
+# pad dataset.py:519-522 -> reference net + OC-Softmax + Adam/SGD, fp32), all host threads.
+# ----------------------------------------------------------------------------------------------
+class _CpuStep:
+    def __init__(self, arch, scoring, B):
+        from oracle import lfcc_torch, nets_oracle as no, state_spec as ss
+        self.no, self.arch, self.scoring, self.B = no, arch, scoring, B
+        self.lfcc = lfcc_torch.TorchLFCC()
+        self.spec = ss.resnet_spec() if arch == "resnet" else ss.ecapa_spec()
+        self.sd = ss.seeded_state(self.spec, 11)
+        skip = ("fc_mu.",) if arch == "resnet" else ("fc7.", "bn7.")
+        self.keys = [k for k in ss.trainable_keys(self.spec) if not k.startswith(skip)]
+        for k in self.keys:
+            self.sd[k].requires_grad_(not scoring)
+        self.center = ss.seeded_center(256, 11).requires_grad_(not scoring)
+        self.m = {k: torch.zeros_like(self.sd[k]) for k in self.keys}
+        self.v = {k: torch.zeros_like(self.sd[k]) for k in self.keys}
+        self.waves = ss.seeded_waves(B, WAVE_LEN, seed=0)
+        self.labels = ss.seeded_labels(B, 0)
+        self.step = 0
+
+    def __call__(self):
+        no = self.no
+        y = self.lfcc(self.waves)                                         # (B,401,60)
+        idx = torch.arange(750) % y.shape[1]                              # repeat pad, dataset.py:519-522
+        y = y[:, idx]
+        if self.arch == "resnet":
+            x = y.unsqueeze(1).transpose(2, 3)
+            fwd = lambda: no.resnet_forward(self.sd, x, not self.scoring, update_running=not self.scoring)
+        else:
+            x = y.transpose(1, 2)
+            fwd = lambda: no.ecapa_forward(self.sd, x, not self.scoring, update_running=not self.scoring)
+        if self.scoring:
+            with torch.no_grad():
+                feat, _ = fwd()
+                return no.ocsoftmax(self.center, feat, torch.zeros(self.B, dtype=torch.long))[1]
+        feat, logits = fwd()
+        loss, _ = no.ocsoftmax(self.center, feat, self.labels, 0.9, 0.2, 20.0)
+        no.cross_entropy(logits.detach(), self.labels)
+        for k in self.keys:
+            self.sd[k].grad = None
+        self.center.grad = None
+        loss.backward()
+        self.step += 1
+        with torch.no_grad():
+            for k in self.keys:
+                if self.sd[k].grad is not None:
+                    no.adam_l2_step(self.sd[k], self.sd[k].grad, self.m[k], self.v[k], self.step, 5e-4)
+            no.sgd_step(self.center, self.center.grad, 5e-4)
+        return loss.detach()
+
+
+def cpu_baseline(arch, scoring, seconds=15.0, B=8):
+    n = os.cpu_count() or 1
+    torch.set_num_threads(n)
+    st = _CpuStep(arch, scoring, B)
+    st()
+    t0, it = time.perf_counter(), 0
+    while it < 2 or (time.perf_counter() - t0 < seconds and it < 50):
+        st()
+        it += 1
+    dt = time.perf_counter() - t0
+    return {"value": B * it / dt, "unit": "utterances/s", "cores": n, "kind": "port",
+            "sample": "%d %s steps of B=%d synthetic 4 s waves (torch-CPU fp32 port of the reference: LFCC -> %s -> "
+                      "OC-Softmax%s)" % (it, "scoring" if scoring else "train", B, arch, "" if scoring else " -> Adam/SGD")}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return None
+    arch = "resnet" if args.workload.startswith("resnet") else "ecapa"
+    scoring = args.workload.endswith("_score")
+    n = os.cpu_count() or 1
+    torch.set_num_threads(n)
+    B = 8
+    st = _CpuStep(arch, scoring, B)
+    for _ in range(min(args.warmup, 2)):
+        st()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        st()
+    dt = time.perf_counter() - t0
+    v = B * args.steps / dt
+    return {"impl": "reference", "metric": "utterances/sec (4 s@16 kHz) %s" % ("scoring" if scoring else "train-step"),
+            "value": v, "unit": "utterances/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%s: reference CPU path (torch fp32 port), bounded sample of B=%d per step"
+                       % (args.workload, B)},
+            "cpu_baseline": {"value": v, "unit": "utterances/s", "cores": n, "kind": "port",
+                             "sample": "%d steps x B=%d" % (args.steps, B)},
+            "e2e": {"value": v, "unit": "utterances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

@@ -351,6 +351,30 @@ class ResNetEngine:
     def mark_dirty(self):
         self._packed_version = -1
 
+    def load_state(self, sd):
+        """Copy a reference-layout state dict (resnet.py key names) into the flat engine buffers."""
+        bufs = self.buffers.named_f32()
+        with torch.no_grad():
+            for k, t in sd.items():
+                t = t.detach()
+                if k in self.store.offsets:
+                    self.store.pt_view(k).copy_(t.to(self.device))
+                elif k in bufs:
+                    bufs[k].copy_(t.to(self.device))
+                elif k.endswith("num_batches_tracked"):
+                    dict(self.bns())[k[:-len(".num_batches_tracked")]].num_batches_tracked.fill_(int(t))
+                else:
+                    raise KeyError(k)
+        self.mark_dirty()
+
+    def state(self):
+        """Reference-layout state dict (detached copies on the engine's device)."""
+        out = {k: self.store.pt_view(k).detach().clone().contiguous() for k in self.store.names()}
+        out.update({k: v.clone() for k, v in self.buffers.named_f32().items()})
+        for name, bn in self.bns():
+            out[name + ".num_batches_tracked"] = bn.num_batches_tracked.clone()
+        return out
+
     def convs(self):
         out = []
         for blk in self.blocks:

@@ -80,7 +80,7 @@ def bn_bwd(dy, dy_ld, x, x_ld, add, add_ld, dx, dx_ld, M, C, order, mean, invstd
     _lib.check(_lib.lib().air_bn_bwd(
         _lib.ptr(dy), _lib.LL(dy_ld), _lib.ptr(x), _lib.LL(x_ld), _lib.ptr(add), _lib.LL(add_ld), _lib.ptr(dx),
         _lib.LL(dx_ld), _lib.LL(M), C, order, _lib.ptr(mean), _lib.ptr(invstd), _lib.ptr(gamma), _lib.ptr(beta),
-        _lib.ptr(rsum), _lib.ptr(dgamma), _lib.ptr(dbeta), num_sms(), _lib.stream_ptr()), "air_bn_bwd")
+        _lib.ptr(rsum), _lib.ptr(dgamma), _lib.ptr(dbeta), num_sms(), _lib.stream_ptr()), "air_bn_bwd", 2)
 
 
 def stem_fwd(x, B, H, W, kh, kw, sh, sw, ph, pw, w, cout, y):
@@ -111,7 +111,7 @@ def linear_fwd(x, W, bias, y, M, N, K):
 
 def linear_bwd(x, W, dy, dx, dW, db, M, N, K):
     _lib.check(_lib.lib().air_linear_bwd(_lib.ptr(x), _lib.ptr(W), _lib.ptr(dy), _lib.ptr(dx), _lib.ptr(dW), _lib.ptr(db),
-                                         M, N, K, _lib.stream_ptr()), "air_linear_bwd")
+                                         M, N, K, _lib.stream_ptr()), "air_linear_bwd", 2)
 
 
 def ocsoftmax(x, labels, center, B, D, r_real, r_fake, alpha, grad_scale, loss, score, dfeat, dcenter,
@@ -131,3 +131,84 @@ def adam_l2_step(p, g, m, v, n, lr, beta1, beta2, eps, wd, step, grad_scale=1.0)
 def sgd_step(p, g, n, lr, grad_scale=1.0):
     _lib.check(_lib.lib().air_sgd_step(_lib.ptr(p), _lib.ptr(g), _lib.LL(n), _lib.F(lr), _lib.F(grad_scale),
                                        _lib.stream_ptr()), "air_sgd_step")
+
+
+# ------------------------------------------------------------------------------------------
+# Optional per-kernel-family device timing (bench.py roofline pass): CUDA events recorded on the
+# launching stream around every C-ABI call while a Profile is active.  Off by default (no cost).
+# ------------------------------------------------------------------------------------------
+class Profile:
+    def __init__(self):
+        self.records = []          # (family, start_event, end_event, flops, bytes)
+
+    def __enter__(self):
+        global _ACTIVE
+        _ACTIVE = self
+        return self
+
+    def __exit__(self, *exc):
+        global _ACTIVE
+        _ACTIVE = None
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for fam, e0, e1, fl, by in self.records:
+            d = out.setdefault(fam, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += fl
+            d["bytes"] += by
+            d["launches"] += 1
+        return out
+
+
+_ACTIVE = None
+
+
+def _conv_work(args):
+    # conv_gemm(a, a_ld, B, H, W, C, Ho, Wo, kh, kw, ..., mode, wpk, N, K, ...)
+    # algorithmic FLOPs: a strided dgrad enumerates the input grid, of which 1/(sh*sw) of the
+    # gathered taps are structurally non-zero
+    B, Ho, Wo, N, K = args[2], args[6], args[7], args[18], args[19]
+    f = 2.0 * B * Ho * Wo * N * K
+    return f / (args[10] * args[11]) if args[16] == 1 else f
+
+
+def _wgrad_work(args):
+    # conv_wgrad(x, x_ld, B, H, W, C, dy, dy_ld, Ho, Wo, N, kh, kw, ...)
+    B, C, Ho, Wo, N, kh, kw = args[2], args[5], args[8], args[9], args[10], args[11], args[12]
+    return 2.0 * B * Ho * Wo * N * C * kh * kw
+
+
+def _timed(fn, family, work=None):
+    def wrapper(*args, **kw):
+        prof = _ACTIVE
+        if prof is None:
+            return fn(*args, **kw)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn(*args, **kw)
+        e1.record()
+        fam = family(args) if callable(family) else family
+        prof.records.append((fam, e0, e1, work(args) if work else 0.0, 0.0))
+        return r
+    wrapper.__name__ = fn.__name__
+    wrapper.__doc__ = fn.__doc__
+    return wrapper
+
+
+conv_gemm = _timed(conv_gemm, lambda a: "conv_dgrad" if a[16] == 1 else "conv_fprop", _conv_work)
+conv_wgrad = _timed(conv_wgrad, "conv_wgrad", _wgrad_work)
+bn_stats = _timed(bn_stats, "bn_stats")
+bn_apply = _timed(bn_apply, "bn_apply")
+bn_bwd = _timed(bn_bwd, "bn_bwd")
+stem_fwd = _timed(stem_fwd, "stem_fwd")
+stem_wgrad = _timed(stem_wgrad, "stem_wgrad")
+selfattn_pool_fwd = _timed(selfattn_pool_fwd, "pool_fwd")
+selfattn_pool_bwd = _timed(selfattn_pool_bwd, "pool_bwd")
+linear_fwd = _timed(linear_fwd, "linear")
+linear_bwd = _timed(linear_bwd, "linear")
+ocsoftmax = _timed(ocsoftmax, "ocsoftmax")
+adam_l2_step = _timed(adam_l2_step, "optim")
+sgd_step = _timed(sgd_step, "optim")
+pack_weights = _timed(pack_weights, "pack_weights")

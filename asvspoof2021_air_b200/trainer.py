@@ -51,6 +51,12 @@ class Trainer:
         self.score = None
         self.launches = 0
 
+    def load_state(self, model_sd, center=None):
+        """Load reference-layout model weights (and the OC-Softmax centre)."""
+        self.engine.load_state(model_sd)
+        if center is not None:
+            self.center.copy_(center.to(self.device))
+
     # ------------------------------------------------------------------------------------
     def features(self, waves, lengths=None, start=None):
         B = waves.shape[0]

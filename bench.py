@@ -152,11 +152,11 @@ def cpu_lfcc_baseline(seconds=10.0, batch=32):
 
 def run_lfcc(args, rank, world):
     from asvspoof2021_air_b200.feature_extraction import LFCC
-    from oracle import state_spec as ss
+    from asvspoof2021_air_b200.bench_train import _waves
     B = args.batch or 256
     mod = LFCC(320, 160, 512, 16000, 20).cuda()
     nbuf = 4                                   # 4 x (65.5 MB in + 24.6 MB out) = 360 MB > 126 MB L2
-    waves = [ss.seeded_waves(B, WAVE_LEN, seed=rank * 16 + i).cuda() for i in range(nbuf)]
+    waves = [_waves(B, rank * 16 + i).cuda() for i in range(nbuf)]
     outs = [torch.empty(B, 401, 60, device="cuda") for _ in range(nbuf)]
     launches = [0]
 

@@ -1,0 +1,129 @@
+"""GPU parity of the tcgen05 implicit-GEMM convolution kernels (fprop / dgrad / wgrad, through the
+C ABI) against a plain PyTorch fp32 convolution of the same bf16-rounded operands.
+
+Shapes are the ResNet-18 / ECAPA layer geometries of SURVEY.md section 8(a) at small batch.
+Tolerance: operands are exactly representable in bf16, products accumulate in fp32 in TMEM, the
+output is rounded once to bf16 -> |err| <= 2^-8 * |ref| + small fp32 accumulation slack."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    # name: B, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, dh, dw
+    "gemm_1x1_64_64": (1, 1, 256, 64, 64, 1, 1, 1, 1, 0, 0, 1, 1),
+    "gemm_1x1_128_256": (2, 1, 300, 128, 256, 1, 1, 1, 1, 0, 0, 1, 1),
+    "res_l1_3x3_64_64": (2, 18, 75, 64, 64, 3, 3, 1, 1, 1, 1, 1, 1),
+    "res_l1_3x3_16_64": (2, 18, 75, 16, 64, 3, 3, 1, 1, 1, 1, 1, 1),
+    "res_l1_sc_16_64": (2, 18, 75, 16, 64, 1, 1, 1, 1, 0, 0, 1, 1),
+    "res_l2_3x3_s2_64_128": (2, 18, 75, 64, 128, 3, 3, 2, 2, 1, 1, 1, 1),
+    "res_l2_sc_s2_64_128": (2, 18, 75, 64, 128, 1, 1, 2, 2, 0, 0, 1, 1),
+    "res_l3_3x3_s2_128_256": (2, 9, 38, 128, 256, 3, 3, 2, 2, 1, 1, 1, 1),
+    "res_l4_3x3_512_512": (2, 3, 94, 512, 512, 3, 3, 1, 1, 1, 1, 1, 1),
+    "res_conv5_512_256": (2, 3, 94, 512, 256, 3, 3, 1, 1, 0, 1, 1, 1),
+    "ecapa_k3_dil2_64_64": (3, 1, 750, 64, 64, 1, 3, 1, 1, 0, 2, 1, 2),
+    "ecapa_k3_dil4_64_64": (3, 1, 750, 64, 64, 1, 3, 1, 1, 0, 4, 1, 4),
+    "ecapa_k5_64_512": (2, 1, 750, 64, 512, 1, 5, 1, 1, 0, 2, 1, 1),
+    "ecapa_k1_1536_1536": (1, 1, 750, 1536, 1536, 1, 1, 1, 1, 0, 0, 1, 1),
+    "ecapa_k1_512_128": (2, 1, 750, 512, 128, 1, 1, 1, 1, 0, 0, 1, 1),
+}
+
+
+def _setup(name):
+    from asvspoof2021_air_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    B, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, dh, dw = CASES[name]
+    g = torch.Generator(device="cpu").manual_seed(1)
+    x = torch.randn(B, Cin, H, W, generator=g).cuda().to(torch.bfloat16)
+    w = (torch.randn(Cout, Cin, kh, kw, generator=g) / (Cin * kh * kw) ** 0.5).cuda()
+    Ho, Wo = ops.conv_out_size(H, kh, sh, ph, dh), ops.conv_out_size(W, kw, sw, pw, dw)
+    dy = torch.randn(B, Cout, Ho, Wo, generator=g).cuda().to(torch.bfloat16)
+    return ops, x, w, dy, Ho, Wo
+
+
+def _check(got, ref, what):
+    assert not torch.isnan(got).any(), what
+    err = (got - ref).abs()
+    tol = 2.0 ** -7 * ref.abs() + 2e-3 * ref.abs().max()
+    bad = err > tol
+    assert not bad.any(), "%s: %d bad, max err %g (ref max %g)" % (what, int(bad.sum()), float(err.max()), float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_fprop(name):
+    ops, x, w, dy, Ho, Wo = _setup(name)
+    B, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, dh, dw = CASES[name]
+    wq = w.to(torch.bfloat16).float()
+    ref = F.conv2d(x.float(), wq, stride=(sh, sw), padding=(ph, pw), dilation=(dh, dw))
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    wpk = ops.pack_weights(w.permute(0, 2, 3, 1).contiguous(), 0, Cin, Cout, kh * kw)
+    out = torch.full((B, Ho, Wo, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.conv_gemm(xn, Cin, B, H, W, Cin, Ho, Wo, kh, kw, sh, sw, ph, pw, dh, dw, 0, wpk, Cout, kh * kw * Cin, out, Cout)
+    torch.cuda.synchronize()
+    _check(out.float().permute(0, 3, 1, 2), ref, name + " fprop")
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_dgrad(name):
+    ops, x, w, dy, Ho, Wo = _setup(name)
+    B, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, dh, dw = CASES[name]
+    wq = w.to(torch.bfloat16).float()
+    ref = torch.nn.grad.conv2d_input((B, Cin, H, W), wq, dy.float(), stride=(sh, sw), padding=(ph, pw), dilation=(dh, dw))
+    dyn = dy.permute(0, 2, 3, 1).contiguous()
+    wpk = ops.pack_weights(w.permute(0, 2, 3, 1).contiguous(), 1, Cin, Cout, kh * kw)
+    out = torch.full((B, H, W, Cin), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.conv_gemm(dyn, Cout, B, Ho, Wo, Cout, H, W, kh, kw, sh, sw, ph, pw, dh, dw, 1, wpk, Cin, kh * kw * Cout, out, Cin)
+    torch.cuda.synchronize()
+    _check(out.float().permute(0, 3, 1, 2), ref, name + " dgrad")
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_wgrad(name):
+    ops, x, w, dy, Ho, Wo = _setup(name)
+    B, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, dh, dw = CASES[name]
+    ref = torch.nn.grad.conv2d_weight(x.float(), (Cout, Cin, kh, kw), dy.float(), stride=(sh, sw), padding=(ph, pw),
+                                      dilation=(dh, dw))
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    dyn = dy.permute(0, 2, 3, 1).contiguous()
+    dwb = torch.zeros(Cout, kh * kw * Cin, device="cuda")
+    ops.conv_wgrad(xn, Cin, B, H, W, Cin, dyn, Cout, Ho, Wo, Cout, kh, kw, sh, sw, ph, pw, dh, dw, dwb)
+    torch.cuda.synchronize()
+    got = dwb.view(Cout, kh, kw, Cin).permute(0, 3, 1, 2)
+    err = (got - ref).abs()
+    assert float(err.max()) <= 1e-3 * float(ref.abs().max()) + 1e-3, (name, float(err.max()), float(ref.abs().max()))
+
+
+def test_fused_epilogue_bias_residual_relu():
+    ops, x, w, dy, Ho, Wo = _setup("res_l1_3x3_64_64")
+    B, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, dh, dw = CASES["res_l1_3x3_64_64"]
+    g = torch.Generator(device="cpu").manual_seed(2)
+    bias = torch.randn(Cout, generator=g).cuda()
+    res = torch.randn(B, Ho, Wo, Cout, generator=g).cuda().to(torch.bfloat16)
+    wq = w.to(torch.bfloat16).float()
+    ref = F.relu(F.conv2d(x.float(), wq, bias, stride=1, padding=1) + res.float().permute(0, 3, 1, 2))
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    wpk = ops.pack_weights(w.permute(0, 2, 3, 1).contiguous(), 0, Cin, Cout, 9)
+    out = torch.empty(B, Ho, Wo, Cout, device="cuda", dtype=torch.bfloat16)
+    ops.conv_gemm(xn, Cin, B, H, W, Cin, Ho, Wo, 3, 3, 1, 1, 1, 1, 1, 1, 0, wpk, Cout, 9 * Cin, out, Cout,
+                  bias=bias, res=res, res_ld=Cout, relu=True)
+    torch.cuda.synchronize()
+    _check(out.float().permute(0, 3, 1, 2), ref, "fused epilogue")
+
+
+def test_channel_slices_with_leading_dimension():
+    """ECAPA Res2 branches read / write 64-channel slices of 512-channel rows (ld = 512)."""
+    from asvspoof2021_air_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(3)
+    B, T, C, width = 2, 750, 512, 64
+    big = torch.randn(B, T, C, generator=g).cuda().to(torch.bfloat16)
+    w = (torch.randn(width, width, 1, 3, generator=g) / (3 * width) ** 0.5).cuda()
+    out = torch.zeros(B, T, C, device="cuda", dtype=torch.bfloat16)
+    wpk = ops.pack_weights(w.permute(0, 2, 3, 1).contiguous(), 0, width, width, 3)
+    src = big[:, :, 128:192]
+    ops.conv_gemm(src, C, B, 1, T, width, 1, T, 1, 3, 1, 1, 0, 3, 1, 3, 0, wpk, width, 3 * width, out[:, :, 64:128], C)
+    torch.cuda.synchronize()
+    ref = F.conv1d(src.float().permute(0, 2, 1), w.to(torch.bfloat16).float()[:, :, 0], padding=3, dilation=3)
+    _check(out[:, :, 64:128].float().permute(0, 2, 1), ref, "slice conv")
+    assert (out[:, :, :64] == 0).all() and (out[:, :, 128:] == 0).all()
