@@ -8,6 +8,7 @@
 //   order 0 ("pre-activation", ResNet):  y = relu(bn(x))
 //   order 1 (ECAPA: conv -> ReLU -> BN): y = bn(x) with x = relu(conv) already applied upstream;
 //            the backward additionally masks the result with (x > 0).
+#include <algorithm>
 #include "common.cuh"
 
 namespace air_bn {
@@ -59,6 +60,7 @@ struct ApplyParams {
   const __nv_bfloat16* x; long long x_ld; __nv_bfloat16* y; long long y_ld; long long M; int C;
   const double* sums; const float* gamma; const float* beta; float eps; int relu; int training;
   float* save_mean; float* save_invstd; float* running_mean; float* running_var; float momentum;
+  const __nv_bfloat16* add; long long add_ld; __nv_bfloat16* y2; long long y2_ld;   // optional: y2 = y + add
 };
 
 __global__ void __launch_bounds__(THREADS) bn_apply_kernel(const ApplyParams p) {
@@ -103,7 +105,16 @@ __global__ void __launch_bounds__(THREADS) bn_apply_kernel(const ApplyParams p) 
       f[k] = fmaf(f[k], scale[c0 + k], shift[c0 + k]);
       if (p.relu) f[k] = fmaxf(f[k], 0.f);
     }
-    *reinterpret_cast<bf16x8*>(p.y + m * p.y_ld + c0) = pack8(f);
+    const bf16x8 yv = pack8(f);
+    *reinterpret_cast<bf16x8*>(p.y + m * p.y_ld + c0) = yv;
+    if (p.y2) {                                   // Res2 branch input: sp_{i} + spx[i+1] (ecapa_tdnn.py:77-80)
+      float a[8];
+      unpack8(yv, f);                             // the consumer adds the ROUNDED branch output
+      unpack8(*reinterpret_cast<const bf16x8*>(p.add + m * p.add_ld + c0), a);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] += a[k];
+      *reinterpret_cast<bf16x8*>(p.y2 + m * p.y2_ld + c0) = pack8(f);
+    }
   }
 }
 
@@ -117,6 +128,7 @@ struct BwdParams {
   __nv_bfloat16* dx; long long dx_ld; long long M; int C; int order;
   const float* mean; const float* invstd; const float* gamma; const float* beta;
   double* rsum; float* dgamma; float* dbeta;
+  float* dbias;                                        // optional: dbias[c] += sum_m dx[m][c] (bias of the producing conv)
 };
 
 __global__ void __launch_bounds__(THREADS) bn_bwd_reduce_kernel(const BwdParams p) {
@@ -182,10 +194,15 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_apply_kernel(const BwdParams p
   __syncthreads();
   const int cpr = p.C >> 3;
   const long long total = p.M * cpr;
+  float bs[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) bs[k] = 0.f;
+  int my_c0 = -1;
   for (long long i = static_cast<long long>(blockIdx.x) * THREADS + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * THREADS) {
     const long long m = i / cpr;
     const int c0 = static_cast<int>(i - m * cpr) * 8;
+    my_c0 = c0;                       // constant per thread when (gridDim.x * THREADS) % cpr == 0 (launcher guarantees it with dbias)
     float g[8], xv[8], ad[8];
     unpack8(*reinterpret_cast<const bf16x8*>(p.dy + m * p.dy_ld + c0), g);
     unpack8(*reinterpret_cast<const bf16x8*>(p.x + m * p.x_ld + c0), xv);
@@ -200,8 +217,26 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_apply_kernel(const BwdParams p
       if (p.order == 1 && !(xv[k] > 0.f)) d = 0.f;
       if (p.add) d += ad[k];
       g[k] = d;
+      bs[k] += d;
     }
     *reinterpret_cast<bf16x8*>(p.dx + m * p.dx_ld + c0) = pack8(g);
+  }
+  if (p.dbias) {
+    // block-level reduction first (one atomic per channel per CTA): thread t owns chunk
+    // ((blockIdx.x * THREADS + t) % cpr) for the whole loop (launcher guarantees (gridDim.x * THREADS) % cpr == 0)
+    float* red = sh + 7 * p.C;                  // [THREADS][8]
+    (void)my_c0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[threadIdx.x * 8 + k] = bs[k];
+    __syncthreads();
+    const int first = static_cast<int>((static_cast<long long>(blockIdx.x) * THREADS) % cpr);
+    for (int c = threadIdx.x; c < p.C; c += THREADS) {
+      const int chunk = c >> 3, e = c & 7;
+      int t0 = chunk - first; if (t0 < 0) t0 += cpr;
+      float a = 0.f;
+      for (int t = t0; t < THREADS; t += cpr) a += red[t * 8 + e];
+      atomicAdd(&p.dbias[c], a);
+    }
   }
 }
 
@@ -229,31 +264,62 @@ extern "C" int air_bn_stats(const void* x, long long x_ld, long long M, int C, d
   return air_launch_status();
 }
 
-extern "C" int air_bn_apply(const void* x, long long x_ld, void* y, long long y_ld, long long M, int C,
-                            const double* sums, const float* gamma, const float* beta, float eps, int relu,
-                            int training, float* save_mean, float* save_invstd, float* running_mean,
-                            float* running_var, float momentum, int num_sms, cudaStream_t stream) {
+extern "C" int air_bn_apply_add(const void* x, long long x_ld, void* y, long long y_ld, long long M, int C,
+                                const double* sums, const float* gamma, const float* beta, float eps, int relu,
+                                int training, float* save_mean, float* save_invstd, float* running_mean,
+                                float* running_var, float momentum, const void* add, long long add_ld, void* y2,
+                                long long y2_ld, int num_sms, cudaStream_t stream) {
   if (!x || !y || !bn_args_ok(M, C, x_ld) || y_ld % 8 != 0) return AIR_ERR_ARG;
   if (training ? !sums : (!running_mean || !running_var)) return AIR_ERR_ARG;
+  if (y2 && (!add || add_ld % 8 != 0 || y2_ld % 8 != 0)) return AIR_ERR_ARG;
   ApplyParams p{reinterpret_cast<const __nv_bfloat16*>(x), x_ld, reinterpret_cast<__nv_bfloat16*>(y), y_ld, M, C,
-                sums, gamma, beta, eps, relu, training, save_mean, save_invstd, running_mean, running_var, momentum};
+                sums, gamma, beta, eps, relu, training, save_mean, save_invstd, running_mean, running_var, momentum,
+                reinterpret_cast<const __nv_bfloat16*>(add), add_ld, reinterpret_cast<__nv_bfloat16*>(y2), y2_ld};
   const int grid = grid_for(M * (C / 8), THREADS * 8, num_sms);
   bn_apply_kernel<<<grid, THREADS, 2 * C * sizeof(float), stream>>>(p);
   return air_launch_status();
 }
 
+extern "C" int air_bn_apply(const void* x, long long x_ld, void* y, long long y_ld, long long M, int C,
+                            const double* sums, const float* gamma, const float* beta, float eps, int relu,
+                            int training, float* save_mean, float* save_invstd, float* running_mean,
+                            float* running_var, float momentum, int num_sms, cudaStream_t stream) {
+  return air_bn_apply_add(x, x_ld, y, y_ld, M, C, sums, gamma, beta, eps, relu, training, save_mean, save_invstd,
+                          running_mean, running_var, momentum, nullptr, 0, nullptr, 0, num_sms, stream);
+}
+
+extern "C" int air_bn_bwd_bias(const void* dy, long long dy_ld, const void* x, long long x_ld, const void* add, long long add_ld,
+                               void* dx, long long dx_ld, long long M, int C, int order,
+                               const float* mean, const float* invstd, const float* gamma, const float* beta,
+                               double* rsum, float* dgamma, float* dbeta, float* dbias, int num_sms, cudaStream_t stream);
+
 extern "C" int air_bn_bwd(const void* dy, long long dy_ld, const void* x, long long x_ld, const void* add, long long add_ld,
                           void* dx, long long dx_ld, long long M, int C, int order,
                           const float* mean, const float* invstd, const float* gamma, const float* beta,
                           double* rsum, float* dgamma, float* dbeta, int num_sms, cudaStream_t stream) {
+  return air_bn_bwd_bias(dy, dy_ld, x, x_ld, add, add_ld, dx, dx_ld, M, C, order, mean, invstd, gamma, beta, rsum, dgamma,
+                         dbeta, nullptr, num_sms, stream);
+}
+
+extern "C" int air_bn_bwd_bias(const void* dy, long long dy_ld, const void* x, long long x_ld, const void* add, long long add_ld,
+                               void* dx, long long dx_ld, long long M, int C, int order,
+                               const float* mean, const float* invstd, const float* gamma, const float* beta,
+                               double* rsum, float* dgamma, float* dbeta, float* dbias, int num_sms, cudaStream_t stream) {
   if (!dy || !x || !dx || !mean || !invstd || !rsum || !bn_args_ok(M, C, x_ld)) return AIR_ERR_ARG;
   if (dy_ld % 8 != 0 || dx_ld % 8 != 0 || (add && add_ld % 8 != 0)) return AIR_ERR_ARG;
   BwdParams p{reinterpret_cast<const __nv_bfloat16*>(dy), dy_ld, reinterpret_cast<const __nv_bfloat16*>(x), x_ld,
               reinterpret_cast<const __nv_bfloat16*>(add), add_ld, reinterpret_cast<__nv_bfloat16*>(dx), dx_ld, M, C, order,
-              mean, invstd, gamma, beta, rsum, dgamma, dbeta};
+              mean, invstd, gamma, beta, rsum, dgamma, dbeta, dbias};
   const int rows_per_it = THREADS / (C / 8);
   if (rows_per_it < 1) return AIR_ERR_UNSUPPORTED;
   bn_bwd_reduce_kernel<<<grid_for(M, rows_per_it * 16, num_sms), THREADS, 2 * THREADS * 8 * sizeof(float), stream>>>(p);
-  bn_bwd_apply_kernel<<<grid_for(M * (C / 8), THREADS * 8, num_sms), THREADS, 7 * C * sizeof(float), stream>>>(p);
+  int agrid = grid_for(M * (C / 8), THREADS * 8, num_sms);
+  if (dbias) {                         // every thread must stay on one 8-channel chunk: (grid * THREADS) % (C/8) == 0
+    const int cpr = C / 8;
+    int q = cpr;                       // smallest multiple of cpr / gcd(cpr, THREADS)
+    { int a = cpr, b = THREADS; while (b) { int t = a % b; a = b; b = t; } q = cpr / a; }
+    agrid = std::max(q, agrid / q * q);
+  }
+  bn_bwd_apply_kernel<<<agrid, THREADS, (7 * C + (dbias ? THREADS * 8 : 0)) * sizeof(float), stream>>>(p);
   return air_launch_status();
 }

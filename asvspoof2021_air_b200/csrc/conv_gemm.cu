@@ -40,6 +40,8 @@ struct ConvParams {
   long long M; int m_tiles;
   __nv_bfloat16* out; long long out_ld;
   const float* bias; const __nv_bfloat16* res; long long res_ld; int relu;
+  int bias_rows;                            // 0: bias[n]; > 0: bias[(m / bias_rows) * N + n] (per-utterance bias)
+  __nv_bfloat16* out2; long long out2_ld;   // optional second output: the accumulator (+bias) WITHOUT the residual
   int stages; int flags;
 };
 
@@ -198,8 +200,14 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const ConvParams 
         if (m < p.M) {
           const int n0 = n_tile * p.block_n + c0;
           if (p.bias) {
+            const float* bp = p.bias + n0 + (p.bias_rows > 0 ? (m / p.bias_rows) * p.N : 0);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + n0 + i);
+            for (int i = 0; i < 16; ++i) v[i] += __ldg(bp + i);
+          }
+          if (p.out2) {
+            bf16x8* o2 = reinterpret_cast<bf16x8*>(p.out2 + m * p.out2_ld + n0);
+            o2[0] = pack8(v);
+            o2[1] = pack8(v + 8);
           }
           if (p.res) {
             const bf16x8* rp = reinterpret_cast<const bf16x8*>(p.res + m * p.res_ld + n0);
@@ -235,6 +243,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const ConvParams 
 // ------------------------------------------------------------------------------------------
 __global__ void pack_weights_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                     int N, int K, int KB, int block_n, long long sn, int inner, long long so, long long si) {
+  // (for a column slice of a wider matrix, e.g. attention.0's W_x = W[:, :1536], sn is the full row stride)
   const long long total = static_cast<long long>(N) * KB * BLOCK_K;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -273,17 +282,26 @@ extern "C" long long air_conv_packed_elems(int N, int K) {
   return static_cast<long long>(N) * KB * BLOCK_K;
 }
 
+extern "C" int air_conv_pack_weights_ld(const float* w, long long w_ld, void* dst, int N, int K, int mode, int Cin, int Cout,
+                                        int taps, cudaStream_t stream);
+
 extern "C" int air_conv_pack_weights(const float* w, void* dst, int N, int K, int mode, int Cin, int Cout, int taps,
                                      cudaStream_t stream) {
+  return air_conv_pack_weights_ld(w, static_cast<long long>(taps) * Cin, dst, N, K, mode, Cin, Cout, taps, stream);
+}
+
+// w_ld: elements between consecutive output-channel rows of w (== taps*Cin for a dense tensor)
+extern "C" int air_conv_pack_weights_ld(const float* w, long long w_ld, void* dst, int N, int K, int mode, int Cin, int Cout,
+                                        int taps, cudaStream_t stream) {
   // mode 0: fprop pack of w[Cout][taps][Cin] (N = Cout, K = taps*Cin)
   // mode 1: dgrad pack of the same tensor      (N = Cin,  K = taps*Cout)
-  if (!w || !dst) return AIR_ERR_ARG;
+  if (!w || !dst || w_ld < static_cast<long long>(taps) * Cin) return AIR_ERR_ARG;
   const int bn = air_conv_block_n(N);
   if (bn == 0) return AIR_ERR_UNSUPPORTED;
   const int KB = (K + BLOCK_K - 1) / BLOCK_K;
   long long sn, so, si; int inner;
-  if (mode == 0) { if (N != Cout || K != taps * Cin) return AIR_ERR_ARG; sn = K; inner = K; so = 0; si = 1; }
-  else if (mode == 1) { if (N != Cin || K != taps * Cout) return AIR_ERR_ARG; sn = 1; inner = Cout; so = Cin; si = static_cast<long long>(taps) * Cin; }
+  if (mode == 0) { if (N != Cout || K != taps * Cin) return AIR_ERR_ARG; sn = w_ld; inner = K; so = 0; si = 1; }
+  else if (mode == 1) { if (N != Cin || K != taps * Cout) return AIR_ERR_ARG; sn = 1; inner = Cout; so = Cin; si = w_ld; }
   else return AIR_ERR_ARG;
   const long long total = static_cast<long long>(N) * KB * BLOCK_K;
   const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 2048));
@@ -291,14 +309,30 @@ extern "C" int air_conv_pack_weights(const float* w, void* dst, int N, int K, in
   return air_launch_status();
 }
 
+extern "C" int air_conv_gemm_bf16_ex(const void* a, long long a_ld, int B, int H, int W, int C, int Ho, int Wo,
+                                     int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw, int mode,
+                                     const void* wpk, int N, int K, void* out, long long out_ld,
+                                     const float* bias, int bias_rows, const void* res, long long res_ld, int relu,
+                                     void* out2, long long out2_ld, int num_sms, int flags, cudaStream_t stream);
+
 // Generic implicit-GEMM launch (fprop when mode == 0, dgrad when mode == 1).
 extern "C" int air_conv_gemm_bf16(const void* a, long long a_ld, int B, int H, int W, int C, int Ho, int Wo,
                                   int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw, int mode,
                                   const void* wpk, int N, int K, void* out, long long out_ld,
                                   const float* bias, const void* res, long long res_ld, int relu,
                                   int num_sms, int flags, cudaStream_t stream) {
+  return air_conv_gemm_bf16_ex(a, a_ld, B, H, W, C, Ho, Wo, kh, kw, sh, sw, ph, pw, dh, dw, mode, wpk, N, K, out, out_ld,
+                               bias, 0, res, res_ld, relu, nullptr, 0, num_sms, flags, stream);
+}
+
+extern "C" int air_conv_gemm_bf16_ex(const void* a, long long a_ld, int B, int H, int W, int C, int Ho, int Wo,
+                                     int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw, int mode,
+                                     const void* wpk, int N, int K, void* out, long long out_ld,
+                                     const float* bias, int bias_rows, const void* res, long long res_ld, int relu,
+                                     void* out2, long long out2_ld, int num_sms, int flags, cudaStream_t stream) {
   if (!a || !wpk || !out || B <= 0) return AIR_ERR_ARG;
-  if (C % 8 != 0 || a_ld % 8 != 0 || out_ld % 8 != 0 || (res && res_ld % 8 != 0)) return AIR_ERR_UNSUPPORTED;
+  if (C % 8 != 0 || a_ld % 8 != 0 || out_ld % 8 != 0 || (res && res_ld % 8 != 0) || (out2 && out2_ld % 8 != 0)) return AIR_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(out2) & 15) || bias_rows < 0) return AIR_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(wpk) |
        reinterpret_cast<uintptr_t>(res)) & 15) return AIR_ERR_UNSUPPORTED;
   const int bn = air_conv_block_n(N);
@@ -311,6 +345,7 @@ extern "C" int air_conv_gemm_bf16(const void* a, long long a_ld, int B, int H, i
   p.M = static_cast<long long>(B) * Ho * Wo; p.m_tiles = static_cast<int>((p.M + BLOCK_M - 1) / BLOCK_M);
   p.out = reinterpret_cast<__nv_bfloat16*>(out); p.out_ld = out_ld; p.bias = bias;
   p.res = reinterpret_cast<const __nv_bfloat16*>(res); p.res_ld = res_ld; p.relu = relu; p.flags = flags;
+  p.bias_rows = bias_rows; p.out2 = reinterpret_cast<__nv_bfloat16*>(out2); p.out2_ld = out2_ld;
   const int stage_bytes = A_STAGE_BYTES + bn * BLOCK_K * 2;
   int stages = (200 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;

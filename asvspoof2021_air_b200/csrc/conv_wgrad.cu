@@ -26,7 +26,7 @@ struct WgradParams {
   const __nv_bfloat16* dy; long long dy_ld; int Ho, Wo, N;   // output gradient, N = Cout
   int kh, kw, sh, sw, ph, pw, dh, dw;
   int Kx;                                 // taps * C
-  float* dw_out;                          // [N][Kx] fp32, accumulated atomically
+  float* dw_out; long long dw_ld;         // [N][dw_ld >= Kx] fp32, accumulated atomically
   long long M;                            // pixels = B*Ho*Wo
   int m_tiles, n_tiles, splits, kb_total, kb_per_split, block_n;
   int stages, flags;
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_wgrad_kernel(const WgradParam
           if (kx < p.Kx) {
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-              atomicAdd(p.dw_out + static_cast<long long>(n0 + c0 + i) * p.Kx + kx, v[i]);
+              atomicAdd(p.dw_out + static_cast<long long>(n0 + c0 + i) * p.dw_ld + kx, v[i]);
           }
         }
       }
@@ -175,10 +175,24 @@ __global__ void __launch_bounds__(THREADS, 1) conv_wgrad_kernel(const WgradParam
 
 using namespace air_wgrad;
 
+extern "C" int air_conv_wgrad_bf16_ld(const void* x, long long x_ld, int B, int H, int W, int C,
+                                      const void* dy, long long dy_ld, int Ho, int Wo, int N,
+                                      int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw,
+                                      float* dw_out, long long dw_ld, int num_sms, int flags, cudaStream_t stream);
+
 extern "C" int air_conv_wgrad_bf16(const void* x, long long x_ld, int B, int H, int W, int C,
                                    const void* dy, long long dy_ld, int Ho, int Wo, int N,
                                    int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw,
                                    float* dw_out, int num_sms, int flags, cudaStream_t stream) {
+  return air_conv_wgrad_bf16_ld(x, x_ld, B, H, W, C, dy, dy_ld, Ho, Wo, N, kh, kw, sh, sw, ph, pw, dh, dw, dw_out,
+                                static_cast<long long>(kh) * kw * C, num_sms, flags, stream);
+}
+
+// dw_ld: elements between consecutive output-channel rows of dw_out (a column slice of a wider gradient)
+extern "C" int air_conv_wgrad_bf16_ld(const void* x, long long x_ld, int B, int H, int W, int C,
+                                      const void* dy, long long dy_ld, int Ho, int Wo, int N,
+                                      int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw,
+                                      float* dw_out, long long dw_ld, int num_sms, int flags, cudaStream_t stream) {
   if (!x || !dy || !dw_out || B <= 0) return AIR_ERR_ARG;
   if (C % 8 != 0 || x_ld % 8 != 0 || dy_ld % 8 != 0 || N % 16 != 0) return AIR_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) return AIR_ERR_UNSUPPORTED;
@@ -188,7 +202,8 @@ extern "C" int air_conv_wgrad_bf16(const void* x, long long x_ld, int B, int H, 
   p.x = reinterpret_cast<const __nv_bfloat16*>(x); p.x_ld = x_ld; p.H = H; p.W = W; p.C = C;
   p.dy = reinterpret_cast<const __nv_bfloat16*>(dy); p.dy_ld = dy_ld; p.Ho = Ho; p.Wo = Wo; p.N = N;
   p.kh = kh; p.kw = kw; p.sh = sh; p.sw = sw; p.ph = ph; p.pw = pw; p.dh = dh; p.dw = dw;
-  p.Kx = kh * kw * C; p.dw_out = dw_out; p.M = static_cast<long long>(B) * Ho * Wo;
+  p.Kx = kh * kw * C; p.dw_out = dw_out; p.dw_ld = dw_ld;
+  if (dw_ld < p.Kx) return AIR_ERR_ARG; p.M = static_cast<long long>(B) * Ho * Wo;
   p.block_n = bn; p.n_tiles = N / bn; p.m_tiles = (p.Kx + TILE_M - 1) / TILE_M;
   p.kb_total = static_cast<int>((p.M + PIX - 1) / PIX);
   if (num_sms <= 0) num_sms = 148;

@@ -136,38 +136,38 @@ __global__ void selfattn_pool_bwd_kernel(const __nv_bfloat16* __restrict__ x, co
 // fp32 linear layer  y = x W^T + b   (x (M,K), W (N,K))
 // ------------------------------------------------------------------------------------------
 __global__ void linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
-                                  float* __restrict__ y, int M, int N, int K) {
+                                  float* __restrict__ y, int M, int N, int K, long long ldx, long long ldw, int accumulate) {
   const int lane = threadIdx.x & 31;
   const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   for (long long o = warp; o < static_cast<long long>(M) * N; o += nwarps) {
     const int m = static_cast<int>(o / N), n = static_cast<int>(o - static_cast<long long>(m) * N);
     float acc = 0.f;
-    for (int k = lane; k < K; k += 32) acc = fmaf(x[static_cast<long long>(m) * K + k], W[static_cast<long long>(n) * K + k], acc);
+    for (int k = lane; k < K; k += 32) acc = fmaf(x[static_cast<long long>(m) * ldx + k], W[static_cast<long long>(n) * ldw + k], acc);
     acc = warp_sum(acc);
-    if (lane == 0) y[o] = acc + (bias ? bias[n] : 0.f);
+    if (lane == 0) y[o] = acc + (bias ? bias[n] : 0.f) + (accumulate ? y[o] : 0.f);
   }
 }
 // dx[m][k] = sum_n dy[m][n] W[n][k]
 __global__ void linear_dx_kernel(const float* __restrict__ dy, const float* __restrict__ W, float* __restrict__ dx,
-                                 int M, int N, int K) {
+                                 int M, int N, int K, long long ldw) {
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < static_cast<long long>(M) * K;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int m = static_cast<int>(i / K), k = static_cast<int>(i - static_cast<long long>(m) * K);
     float acc = 0.f;
-    for (int n = 0; n < N; ++n) acc = fmaf(dy[static_cast<long long>(m) * N + n], W[static_cast<long long>(n) * K + k], acc);
+    for (int n = 0; n < N; ++n) acc = fmaf(dy[static_cast<long long>(m) * N + n], W[static_cast<long long>(n) * ldw + k], acc);
     dx[i] = acc;
   }
 }
 // dW[n][k] += sum_m dy[m][n] x[m][k];  db[n] += sum_m dy[m][n]
 __global__ void linear_dw_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dW,
-                                 float* __restrict__ db, int M, int N, int K) {
+                                 float* __restrict__ db, int M, int N, int K, long long ldw) {
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < static_cast<long long>(N) * K;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int n = static_cast<int>(i / K), k = static_cast<int>(i - static_cast<long long>(n) * K);
     float acc = 0.f;
     for (int m = 0; m < M; ++m) acc = fmaf(dy[static_cast<long long>(m) * N + n], x[static_cast<long long>(m) * K + k], acc);
-    dW[i] += acc;
+    dW[static_cast<long long>(n) * ldw + k] += acc;
     if (k == 0 && db) {
       float s = 0.f;
       for (int m = 0; m < M; ++m) s += dy[static_cast<long long>(m) * N + n];
@@ -278,22 +278,38 @@ extern "C" int air_linear_fwd(const float* x, const float* W, const float* bias,
   if (!x || !W || !y || M <= 0 || N <= 0 || K <= 0) return AIR_ERR_ARG;
   const long long warps = static_cast<long long>(M) * N;
   const int blocks = static_cast<int>(std::min<long long>((warps + 7) / 8, 148 * 16));
-  linear_fwd_kernel<<<blocks, 256, 0, stream>>>(x, W, bias, y, M, N, K);
+  linear_fwd_kernel<<<blocks, 256, 0, stream>>>(x, W, bias, y, M, N, K, K, K, 0);
+  return air_launch_status();
+}
+
+// y (+)= x W[:, slice]^T + b with a row stride on W (column slice of a wider weight, e.g. the
+// mean / std blocks of ECAPA's attention.0.weight (128, 4608), ecapa_tdnn.py:139,173-175)
+extern "C" int air_linear_fwd_ld(const float* x, const float* W, long long ldw, const float* bias, float* y, int M, int N, int K,
+                                 int accumulate, cudaStream_t stream) {
+  if (!x || !W || !y || M <= 0 || N <= 0 || K <= 0 || ldw < K) return AIR_ERR_ARG;
+  const long long warps = static_cast<long long>(M) * N;
+  const int blocks = static_cast<int>(std::min<long long>((warps + 7) / 8, 148 * 16));
+  linear_fwd_kernel<<<blocks, 256, 0, stream>>>(x, W, bias, y, M, N, K, K, ldw, accumulate);
+  return air_launch_status();
+}
+
+extern "C" int air_linear_bwd_ld(const float* x, const float* W, long long ldw, const float* dy, float* dx, float* dW, float* db,
+                                 int M, int N, int K, cudaStream_t stream) {
+  if (!x || !W || !dy || M <= 0 || N <= 0 || K <= 0 || ldw < K) return AIR_ERR_ARG;
+  if (dx) {
+    const int blocks = static_cast<int>(std::min<long long>((static_cast<long long>(M) * K + 255) / 256, 148 * 16));
+    linear_dx_kernel<<<blocks, 256, 0, stream>>>(dy, W, dx, M, N, K, ldw);
+  }
+  if (dW) {
+    const int blocks = static_cast<int>(std::min<long long>((static_cast<long long>(N) * K + 255) / 256, 148 * 16));
+    linear_dw_kernel<<<blocks, 256, 0, stream>>>(dy, x, dW, db, M, N, K, ldw);
+  }
   return air_launch_status();
 }
 
 extern "C" int air_linear_bwd(const float* x, const float* W, const float* dy, float* dx, float* dW, float* db,
                               int M, int N, int K, cudaStream_t stream) {
-  if (!x || !W || !dy || M <= 0 || N <= 0 || K <= 0) return AIR_ERR_ARG;
-  if (dx) {
-    const int blocks = static_cast<int>(std::min<long long>((static_cast<long long>(M) * K + 255) / 256, 148 * 16));
-    linear_dx_kernel<<<blocks, 256, 0, stream>>>(dy, W, dx, M, N, K);
-  }
-  if (dW) {
-    const int blocks = static_cast<int>(std::min<long long>((static_cast<long long>(N) * K + 255) / 256, 148 * 16));
-    linear_dw_kernel<<<blocks, 256, 0, stream>>>(dy, x, dW, db, M, N, K);
-  }
-  return air_launch_status();
+  return air_linear_bwd_ld(x, W, K, dy, dx, dW, db, M, N, K, stream);
 }
 
 extern "C" int air_ocsoftmax_fwd_bwd(const float* x, const long long* labels, const float* center, int B, int D,

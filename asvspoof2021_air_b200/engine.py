@@ -118,12 +118,15 @@ class ConvLayer:
                       self.dh, self.dw, 0, self.wpk, self.cout, self.K, out, out_ld, bias, res, res_ld, relu)
         return Ho, Wo
 
-    def dgrad(self, dy, dy_ld, B, H, W, dx, dx_ld, accumulate=False):
-        """dy on the (Ho,Wo) grid -> dx on the (H,W) input grid; accumulate adds into dx."""
+    def dgrad(self, dy, dy_ld, B, H, W, dx, dx_ld, accumulate=False, res=None, res_ld=0, out2=None, out2_ld=0):
+        """dy on the (Ho,Wo) grid -> dx on the (H,W) input grid.  accumulate adds into dx; `res` adds
+        another tensor instead; out2 (optional) receives the gradient without the residual."""
         Ho, Wo = self.out_hw(H, W)
-        ops.conv_gemm(dy, dy_ld, B, Ho, Wo, self.cout, H, W, self.kh, self.kw, self.sh, self.sw, self.ph, self.pw,
-                      self.dh, self.dw, 1, self.wpk_d, self.cin_g, self.taps * self.cout, dx, dx_ld, None,
-                      dx if accumulate else None, dx_ld, False)
+        if accumulate:
+            res, res_ld = dx, dx_ld
+        ops.conv_gemm_ex(dy, dy_ld, B, Ho, Wo, self.cout, H, W, self.kh, self.kw, self.sh, self.sw, self.ph, self.pw,
+                         self.dh, self.dw, 1, self.wpk_d, self.cin_g, self.taps * self.cout, dx, dx_ld, None,
+                         res, res_ld, False, 0, 0, out2, out2_ld)
 
     def wgrad(self, x, x_ld, B, H, W, dy, dy_ld):
         Ho, Wo = self.out_hw(H, W)

@@ -1,0 +1,384 @@
+"""Hand-scheduled forward / backward of the reference's ECAPA-TDNN (`Res2Net2(Bottle2neck, C=512,
+model_scale=8, nOut=2, n_mels=60)`, ecapa_tdnn.py:97-198; encoder_type='ECA', context=True,
+summed=False, out_bn=True -- the main_train.py:167-168 configuration) on channels-last bf16
+activations (B, T, C).
+
+Every arithmetic step is a hand-written sm_100a kernel behind the C ABI: the 37 Conv1d layers run as
+tcgen05 implicit-GEMM kernels (k = 1 / 3 dilated / 5; bias + ReLU fused in the epilogue, the order in this
+file is conv -> ReLU -> BN, ecapa_tdnn.py:68-91), BatchNorm / SE / statistics pooling as HBM-bound
+kernels (csrc/bn.cu, csrc/ecapa.cu).  The 3072 time-constant input columns of attention.0
+(mean / std broadcast over time, :169-175) are folded into a per-utterance bias instead of
+materialising the (B, 4608, T) `global_x`.
+"""
+import math
+
+import torch
+
+from . import ops
+from .engine import BF16, BNLayer, BufferStore, ConvLayer, ParamStore, _conv1d_pt, _ident, _resolve_lazies
+
+CLAMP = 1e-4
+
+
+class _Blk:
+    pass
+
+
+class _BN1d:
+    """fp32 BatchNorm1d over (batch, C) rows (SE bottleneck BN, bn5, bn7)."""
+
+    def __init__(self, store, buffers, name, C):
+        self.store, self.name, self.C = store, name, C
+        self.running_mean = buffers.add(name + ".running_mean", C, 0.0)
+        self.running_var = buffers.add(name + ".running_var", C, 1.0)
+        self.num_batches_tracked = torch.zeros((), dtype=torch.long, device=store.device)
+        self.save_mean = torch.empty(C, device=store.device)
+        self.save_invstd = torch.empty(C, device=store.device)
+
+    def forward(self, x, y, M, relu_in, training):
+        if training:
+            self.num_batches_tracked += 1
+        ops.bn1d_fwd(x, y, M, self.C, relu_in, self.store.view(self.name + ".weight"), self.store.view(self.name + ".bias"),
+                     training, self.save_mean, self.save_invstd, self.running_mean, self.running_var)
+
+    def backward(self, dy, x, dx, M, relu_in, frozen=False):
+        ops.bn1d_bwd(dy, x, dx, M, self.C, relu_in, self.store.view(self.name + ".weight"), self.save_mean, self.save_invstd,
+                     None if frozen else self.store.grad(self.name + ".weight"),
+                     None if frozen else self.store.grad(self.name + ".bias"))
+
+
+class EcapaEngine:
+    def __init__(self, C=512, scale=8, n_out=2, n_mels=60, bottleneck=128, enc_dim=256, device="cuda", train_head=False):
+        assert C % scale == 0 and (C // scale) % 16 == 0
+        self.C, self.scale, self.width, self.n_out, self.n_mels = C, scale, C // scale, n_out, n_mels
+        self.bott, self.enc_dim = bottleneck, enc_dim
+        self.mels_g = (n_mels + 7) // 8 * 8
+        self.C3 = 3 * C
+        dev = torch.device(device)
+        self.device = dev
+        self.B = self.T = None
+        W = self.width
+
+        def conv(prefix, co, ci, k):
+            return [(prefix + ".weight", (co, k, ci), _conv1d_pt), (prefix + ".bias", (co,), _ident)]
+
+        def bn(prefix, c):
+            return [(prefix + ".weight", (c,), _ident), (prefix + ".bias", (c,), _ident)]
+        ent = conv("conv1", C, n_mels, 5) + bn("bn1", C)
+        for li in (1, 2, 3):
+            p = "layer%d" % li
+            ent += conv(p + ".conv1", C, C, 1) + bn(p + ".bn1", C)
+            for i in range(scale - 1):
+                ent += conv(p + ".convs.%d" % i, W, W, 3)
+            for i in range(scale - 1):
+                ent += bn(p + ".bns.%d" % i, W)
+            ent += conv(p + ".conv3", C, C, 1) + bn(p + ".bn3", C)
+            ent += conv(p + ".se.se.1", bottleneck, C, 1) + bn(p + ".se.se.3", bottleneck) + conv(p + ".se.se.4", C, bottleneck, 1)
+        ent += conv("layer4", self.C3, self.C3, 1)
+        ent += conv("attention.0", 128, 3 * self.C3, 1) + bn("attention.2", 128) + conv("attention.3", self.C3, 128, 1)
+        ent += bn("bn5", 2 * self.C3)
+        ent += [("fc6.weight", (enc_dim, 2 * self.C3), _ident), ("fc6.bias", (enc_dim,), _ident),
+                ("fc7.weight", (n_out, enc_dim), _ident), ("fc7.bias", (n_out,), _ident)] + bn("bn7", n_out)
+        frozen = () if train_head else ("fc7.weight", "fc7.bias", "bn7.weight", "bn7.bias")
+        self.train_head = train_head
+        self.store = ParamStore(ent, dev, frozen=frozen)
+        self.buffers = BufferStore(dev)
+        st, bufs = self.store, self.buffers
+
+        self.conv1 = ConvLayer(st, "conv1", n_mels, C, 1, 5, pw=2, bias=True, need_dgrad=False, cin_pad=self.mels_g)
+        self.bn1 = BNLayer(st, bufs, "bn1", C)
+        self.blocks = []
+        for li, dil in ((1, 2), (2, 3), (3, 4)):
+            p = "layer%d" % li
+            blk = _Blk()
+            blk.name, blk.dil = p, dil
+            blk.conv1 = ConvLayer(st, p + ".conv1", C, C, 1, 1, bias=True)
+            blk.bn1 = BNLayer(st, bufs, p + ".bn1", C)
+            blk.convs = [ConvLayer(st, p + ".convs.%d" % i, W, W, 1, 3, pw=dil, dw=dil, bias=True) for i in range(scale - 1)]
+            blk.bns = [BNLayer(st, bufs, p + ".bns.%d" % i, W) for i in range(scale - 1)]
+            blk.conv3 = ConvLayer(st, p + ".conv3", C, C, 1, 1, bias=True)
+            blk.bn3 = BNLayer(st, bufs, p + ".bn3", C)
+            blk.se_bn = _BN1d(st, bufs, p + ".se.se.3", bottleneck)
+            self.blocks.append(blk)
+        self.layer4 = ConvLayer(st, "layer4", self.C3, self.C3, 1, 1, bias=True)
+        # attention.0: only the x-block of the (128, 4608) weight goes through the GEMM
+        self.att0_wpk = torch.empty(ops.packed_elems(128, self.C3), device=dev, dtype=BF16)
+        self.att0_wpk_d = torch.empty(ops.packed_elems(self.C3, 128), device=dev, dtype=BF16)
+        self.att_bn = BNLayer(st, bufs, "attention.2", 128)
+        self.att3 = ConvLayer(st, "attention.3", 128, self.C3, 1, 1, bias=True)
+        self.bn5 = _BN1d(st, bufs, "bn5", 2 * self.C3)
+        self.bn7 = _BN1d(st, bufs, "bn7", n_out)
+        bufs.finalize()
+        for obj in self.bn_layers():
+            _resolve_lazies(obj)
+        self._packed_version = -1
+        self.init_parameters()
+
+    # ---- inventories ------------------------------------------------------------------------
+    def bn_layers(self):
+        out = [self.bn1]
+        for blk in self.blocks:
+            out += [blk.bn1] + blk.bns + [blk.bn3, blk.se_bn]
+        return out + [self.att_bn, self.bn5, self.bn7]
+
+    def bns(self):
+        return [(b.name, b) for b in self.bn_layers()]
+
+    def convs(self):
+        out = [self.conv1]
+        for blk in self.blocks:
+            out += [blk.conv1] + blk.convs + [blk.conv3]
+        return out + [self.layer4, self.att3]
+
+    # ---- parameters -------------------------------------------------------------------------
+    def init_parameters(self, seed=None):
+        """PyTorch defaults of nn.Conv1d / nn.Linear (kaiming_uniform(a=sqrt(5)) == U(+-1/sqrt(fan_in)) for
+        weight and bias) and nn.BatchNorm1d (1 / 0); the reference does no custom init (ecapa_tdnn.py:97-150)."""
+        g = torch.Generator(device="cpu")
+        g.manual_seed(seed if seed is not None else torch.initial_seed() % (2 ** 31))
+        for name, (off, n, shape) in self.store.offsets.items():
+            v = self.store.view(name)
+            is_bn = ".bn" in name or name.startswith("bn") or ".se.se.3." in name or name.startswith("attention.2")
+            if is_bn:
+                v.fill_(1.0) if name.endswith(".weight") else v.zero_()
+                continue
+            wname = name[:-5] + ".weight" if name.endswith(".bias") else name
+            wshape = self.store.offsets[wname][2]
+            fan_in = int(math.prod(wshape[1:]))
+            bound = 1.0 / math.sqrt(fan_in)
+            v.copy_((torch.rand(shape, generator=g) * 2 - 1) * bound)
+        self.mark_dirty()
+
+    def mark_dirty(self):
+        self._packed_version = -1
+
+    def load_state(self, sd):
+        bufs = self.buffers.named_f32()
+        named_bn = dict(self.bns())
+        with torch.no_grad():
+            for k, t in sd.items():
+                t = t.detach()
+                if k in self.store.offsets:
+                    self.store.pt_view(k).copy_(t.to(self.device))
+                elif k in bufs:
+                    bufs[k].copy_(t.to(self.device))
+                elif k.endswith("num_batches_tracked"):
+                    named_bn[k[:-len(".num_batches_tracked")]].num_batches_tracked.fill_(int(t))
+                else:
+                    raise KeyError(k)
+        self.mark_dirty()
+
+    def state(self):
+        out = {k: self.store.pt_view(k).detach().clone().contiguous() for k in self.store.names()}
+        out.update({k: v.clone() for k, v in self.buffers.named_f32().items()})
+        for name, bn in self.bns():
+            out[name + ".num_batches_tracked"] = bn.num_batches_tracked.clone()
+        return out
+
+    def pack_weights(self):
+        for c in self.convs():
+            c.pack()
+        w = self.store.view("attention.0.weight")                       # [128][1][4608]
+        ops.pack_weights_ld(w, 3 * self.C3, 0, self.C3, 128, 1, self.att0_wpk)
+        ops.pack_weights_ld(w, 3 * self.C3, 1, self.C3, 128, 1, self.att0_wpk_d)
+        self._packed_version = self.store.step
+
+    # ---- buffers ----------------------------------------------------------------------------
+    def bind(self, B, T, training=True):
+        if self.B == B and self.T == T:
+            return
+        self.B, self.T = B, T
+        dev, C, W, C3 = self.device, self.C, self.width, self.C3
+
+        def act(*shape):
+            return torch.empty(shape, device=dev, dtype=BF16)
+
+        def f32(*shape):
+            return torch.empty(shape, device=dev, dtype=torch.float32)
+        self.c1, self.xb1 = act(B, T, C), act(B, T, C)
+        self.xcat = act(B, T, C3)
+        self.g_xcat = act(B, T, C3)
+        self.g_xb1, self.g_c1 = act(B, T, C), act(B, T, C)
+        for blk in self.blocks:
+            blk.t1, blk.o1, blk.cat, blk.t3, blk.o3 = (act(B, T, C) for _ in range(5))
+            blk.spin = [None] + [act(B, T, W) for _ in range(self.scale - 2)]
+            blk.tb = [act(B, T, W) for _ in range(self.scale - 1)]
+            blk.s, blk.z2, blk.g = f32(B, C), f32(B, C), f32(B, C)
+            blk.z1, blk.h1 = f32(B, self.bott), f32(B, self.bott)
+            # gradients
+            blk.g_o3, blk.g_t3, blk.g_cat, blk.g_o1, blk.g_t1 = (act(B, T, C) for _ in range(5))
+            blk.g_sp, blk.g_tb = act(B, T, W), act(B, T, W)
+            blk.dgate, blk.dz2, blk.ds = f32(B, C), f32(B, C), f32(B, C)
+            blk.dh1, blk.dz1 = f32(B, self.bott), f32(B, self.bott)
+        self.ones_gate = torch.ones(B, C, device=dev)
+        self.x4, self.g_x4 = act(B, T, C3), act(B, T, C3)
+        self.cmean, self.cstd, self.dcmean, self.dcstd = (f32(B, C3) for _ in range(4))
+        self.zeros_c3 = torch.zeros(B, C3, device=dev)
+        self.u, self.gu = f32(B, 128), f32(B, 128)
+        self.a1, self.a2, self.g_a1, self.g_a2 = (act(B, T, 128) for _ in range(4))
+        self.e, self.g_e = act(B, T, C3), act(B, T, C3)
+        self.pooled, self.p5, self.g_pooled, self.g_p5 = (f32(B, 2 * C3) for _ in range(4))
+        self.smax, self.ssum, self.sq = f32(B, C3), f32(B, C3), f32(B, C3)
+        self.feat, self.g_feat7 = f32(B, self.enc_dim), f32(B, self.enc_dim)
+        self.l7, self.logits, self.g_l7 = f32(B, self.n_out), f32(B, self.n_out), f32(B, self.n_out)
+        self._w1tmp = None
+
+    # ---- BN helpers (conv -> ReLU -> BN order: y = bn(x), x already relu'd) --------------------
+    def _bn_fwd(self, bn, x, x_ld, y, y_ld, M, training, add=None, add_ld=0, y2=None, y2_ld=0):
+        g, b = self.store.view(bn.name + ".weight"), self.store.view(bn.name + ".bias")
+        if training:
+            ops.bn_stats(x, x_ld, M, bn.C, bn.sums)
+            bn.num_batches_tracked += 1
+        ops.bn_apply_add(x, x_ld, y, y_ld, M, bn.C, bn.sums, g, b, False, training, bn.save_mean, bn.save_invstd,
+                         bn.running_mean, bn.running_var, add, add_ld, y2, y2_ld)
+
+    def _bn_bwd(self, bn, dy, dy_ld, x, x_ld, dx, dx_ld, M, dbias):
+        g, b = self.store.view(bn.name + ".weight"), self.store.view(bn.name + ".bias")
+        ops.bn_bwd_bias(dy, dy_ld, x, x_ld, None, 0, dx, dx_ld, M, bn.C, 1, bn.save_mean, bn.save_invstd, g, b, bn.rsum,
+                        self.store.grad(bn.name + ".weight"), self.store.grad(bn.name + ".bias"), dbias)
+
+    # ---- forward ----------------------------------------------------------------------------
+    def forward(self, x0, training=True):
+        """x0: (B, T, mels_g) bf16 channels-last LFCC (channels >= n_mels zero).  Returns (feat, logits) fp32."""
+        assert x0.dtype == BF16 and x0.dim() == 3 and x0.shape[2] == self.mels_g and x0.is_contiguous()
+        B, T = x0.shape[0], x0.shape[1]
+        self.bind(B, T)
+        if self._packed_version != self.store.step:
+            self.pack_weights()
+        if training:
+            self.buffers.f64.zero_()
+        st, C, W, C3, M = self.store, self.C, self.width, self.C3, B * T
+        self.x0 = x0
+        self.conv1.fprop(x0, self.mels_g, B, 1, T, self.c1, C, relu=True)                      # :156-158
+        self._bn_fwd(self.bn1, self.c1, C, self.xb1, C, M, training)
+        xin, xin_ld = self.xb1, C
+        for li, blk in enumerate(self.blocks):
+            blk.xin, blk.xin_ld = xin, xin_ld
+            out = self.xcat[:, :, li * C:(li + 1) * C]
+            blk.conv1.fprop(xin, xin_ld, B, 1, T, blk.t1, C, relu=True)                        # :67-69
+            self._bn_fwd(blk.bn1, blk.t1, C, blk.o1, C, M, training)
+            for i in range(self.scale - 1):                                                    # :73-83
+                src = blk.o1[:, :, 0:W] if i == 0 else blk.spin[i]
+                src_ld = C if i == 0 else W
+                blk.convs[i].fprop(src, src_ld, B, 1, T, blk.tb[i], W, relu=True)
+                dst = blk.cat[:, :, i * W:(i + 1) * W]
+                if i + 1 < self.scale - 1:       # next branch input = this output + spx[i+1]
+                    self._bn_fwd(blk.bns[i], blk.tb[i], W, dst, C, M, training,
+                                 add=blk.o1[:, :, (i + 1) * W:(i + 2) * W], add_ld=C, y2=blk.spin[i + 1], y2_ld=W)
+                else:
+                    self._bn_fwd(blk.bns[i], blk.tb[i], W, dst, C, M, training)
+            ops.copy_channels(blk.o1[:, :, C - W:], C, blk.cat[:, :, C - W:], C, M, W)         # :85
+            blk.conv3.fprop(blk.cat, C, B, 1, T, blk.t3, C, relu=True)                         # :87-89
+            self._bn_fwd(blk.bn3, blk.t3, C, blk.o3, C, M, training)
+            # SE (:15-29): squeeze -> 512->128 -> ReLU -> BN -> 128->512 -> sigmoid -> scale; + residual (:93)
+            p = blk.name + ".se.se."
+            ops.time_stats(blk.o3, C, B, T, C, blk.s)
+            ops.linear_fwd(blk.s, st.view(p + "1.weight"), st.view(p + "1.bias"), blk.z1, B, self.bott, C)
+            blk.se_bn.forward(blk.z1, blk.h1, B, True, training)
+            ops.linear_fwd(blk.h1, st.view(p + "4.weight"), st.view(p + "4.bias"), blk.z2, B, C, self.bott)
+            ops.sigmoid_fwd(blk.z2, blk.g, B * C)
+            ops.scale_residual(blk.o3, C, blk.g, xin, xin_ld, out, C3, B, T, C)
+            xin, xin_ld = out, C3
+        self.layer4.fprop(self.xcat, C3, B, 1, T, self.x4, C3, relu=True)                       # :165-166
+        ops.time_stats(self.x4, C3, B, T, C3, self.cmean, self.cstd, CLAMP)                     # :169-172
+        w0 = st.view("attention.0.weight").view(128, 3 * C3)
+        ops.linear_fwd_ld(self.cmean, w0[:, C3:], 3 * C3, st.view("attention.0.bias"), self.u, B, 128, C3)
+        ops.linear_fwd_ld(self.cstd, w0[:, 2 * C3:], 3 * C3, None, self.u, B, 128, C3, accumulate=True)
+        ops.conv_gemm_ex(self.x4, C3, B, 1, T, C3, 1, T, 1, 1, 1, 1, 0, 0, 1, 1, 0, self.att0_wpk, 128, C3,
+                         self.a1, 128, self.u, None, 0, True, 0, T)                             # :139-140 (+ReLU)
+        self._bn_fwd(self.att_bn, self.a1, 128, self.a2, 128, M, training)
+        self.att3.fprop(self.a2, 128, B, 1, T, self.e, C3)                                      # :143
+        ops.asp_fwd(self.e, C3, self.x4, C3, B, T, C3, self.pooled, self.smax, self.ssum, self.sq)   # :144,182-186
+        self.bn5.forward(self.pooled, self.p5, B, False, training)                              # :188
+        ops.linear_fwd(self.p5, st.view("fc6.weight"), st.view("fc6.bias"), self.feat, B, self.enc_dim, 2 * C3)
+        ops.linear_fwd(self.feat, st.view("fc7.weight"), st.view("fc7.bias"), self.l7, B, self.n_out, self.enc_dim)
+        self.bn7.forward(self.l7, self.logits, B, False, training)                              # :192-195
+        return self.feat, self.logits
+
+    # ---- backward ---------------------------------------------------------------------------
+    def zero_grad(self):
+        self.store.grads.zero_()
+
+    def backward(self, dfeat, dlogits=None):
+        """Accumulates parameter gradients into store.grads (call zero_grad() first)."""
+        B, T, st, C, W, C3 = self.B, self.T, self.store, self.C, self.width, self.C3
+        M = B * T
+        if dlogits is not None:
+            assert self.train_head, "fc7 / bn7 are frozen in this engine (OC-Softmax training)"
+            self.bn7.backward(dlogits.contiguous(), self.l7, self.g_l7, B, False)
+            ops.linear_bwd(self.feat, st.view("fc7.weight"), self.g_l7, self.g_feat7, st.grad("fc7.weight"),
+                           st.grad("fc7.bias"), B, self.n_out, self.enc_dim)
+            dfeat = self.g_feat7 if dfeat is None else dfeat + self.g_feat7
+        dfeat = dfeat.contiguous()
+        ops.linear_bwd(self.p5, st.view("fc6.weight"), dfeat, self.g_p5, st.grad("fc6.weight"), st.grad("fc6.bias"),
+                       B, self.enc_dim, 2 * C3)
+        self.bn5.backward(self.g_p5, self.pooled, self.g_pooled, B, False)
+        # pooling: de and the direct dx (context part is added after the attention branch is differentiated)
+        ops.asp_bwd(self.e, C3, self.x4, C3, B, T, C3, self.pooled, self.g_pooled, self.smax, self.ssum, self.sq,
+                    self.cmean, self.cstd, self.zeros_c3, self.zeros_c3, CLAMP, self.g_e, C3, self.g_x4, C3)
+        # attention.3 (128 -> 1536)
+        self.att3.wgrad(self.a2, 128, B, 1, T, self.g_e, C3)
+        ops.colsum(self.g_e, C3, M, C3, st.grad("attention.3.bias"))
+        self.att3.dgrad(self.g_e, C3, B, 1, T, self.g_a2, 128)
+        # attention.2 BN (+ the ReLU before it) ; dbias = bias gradient of attention.0
+        self._bn_bwd(self.att_bn, self.g_a2, 128, self.a1, 128, self.g_a1, 128, M, st.grad("attention.0.bias"))
+        # attention.0: x-block through the GEMMs, mean / std blocks through the per-utterance bias
+        gw0 = st.grad("attention.0.weight").view(128, 3 * C3)
+        w0 = st.view("attention.0.weight").view(128, 3 * C3)
+        ops.conv_wgrad_ld(self.x4, C3, B, 1, T, C3, self.g_a1, 128, 1, T, 128, 1, 1, 1, 1, 0, 0, 1, 1, gw0, 3 * C3)
+        ops.time_stats(self.g_a1, 128, B, T, 128, self.gu, None, -1.0)                          # sum over time
+        ops.linear_bwd_ld(self.cmean, w0[:, C3:], 3 * C3, self.gu, self.dcmean, gw0[:, C3:], None, B, 128, C3)
+        ops.linear_bwd_ld(self.cstd, w0[:, 2 * C3:], 3 * C3, self.gu, self.dcstd, gw0[:, 2 * C3:], None, B, 128, C3)
+        ops.conv_gemm_ex(self.g_a1, 128, B, 1, T, 128, 1, T, 1, 1, 1, 1, 0, 0, 1, 1, 1, self.att0_wpk_d, C3, 128,
+                         self.g_x4, C3, None, self.g_x4, C3, False)
+        ops.ctx_bwd_mask(self.x4, C3, B, T, C3, self.cmean, self.cstd, self.dcmean, self.dcstd, CLAMP, self.g_x4, C3)
+        # layer4 (1536 -> 1536)
+        self.layer4.wgrad(self.xcat, C3, B, 1, T, self.g_x4, C3)
+        ops.colsum(self.g_x4, C3, M, C3, st.grad("layer4.bias"))
+        self.layer4.dgrad(self.g_x4, C3, B, 1, T, self.g_xcat, C3)
+        for li in range(len(self.blocks) - 1, -1, -1):
+            blk = self.blocks[li]
+            dout = self.g_xcat[:, :, li * C:(li + 1) * C]
+            p = blk.name + ".se.se."
+            if li > 0:      # residual path: d xin += dout (the conv1 dgrad below accumulates on top)
+                prev = self.g_xcat[:, :, (li - 1) * C:li * C]
+                ops.scale_residual(dout, C3, self.ones_gate, prev, C3, prev, C3, B, T, C)
+            # SE backward
+            ops.se_dgate(dout, C3, blk.o3, C, B, T, C, blk.dgate)
+            ops.sigmoid_bwd(blk.dgate, blk.g, blk.dz2, B * C)
+            ops.linear_bwd(blk.h1, st.view(p + "4.weight"), blk.dz2, blk.dh1, st.grad(p + "4.weight"), st.grad(p + "4.bias"),
+                           B, C, self.bott)
+            blk.se_bn.backward(blk.dh1, blk.z1, blk.dz1, B, True)
+            ops.linear_bwd(blk.s, st.view(p + "1.weight"), blk.dz1, blk.ds, st.grad(p + "1.weight"), st.grad(p + "1.bias"),
+                           B, self.bott, C)
+            ops.se_apply_bwd(dout, C3, blk.g, blk.ds, blk.g_o3, C, B, T, C)
+            # bn3 / conv3
+            self._bn_bwd(blk.bn3, blk.g_o3, C, blk.t3, C, blk.g_t3, C, M, st.grad(blk.name + ".conv3.bias"))
+            blk.conv3.wgrad(blk.cat, C, B, 1, T, blk.g_t3, C)
+            blk.conv3.dgrad(blk.g_t3, C, B, 1, T, blk.g_cat, C)
+            # Res2 branches, last to first
+            for i in range(self.scale - 2, -1, -1):
+                if i == self.scale - 2:
+                    dy, dy_ld = blk.g_cat[:, :, i * W:(i + 1) * W], C
+                else:
+                    dy, dy_ld = blk.g_sp, W                     # d cat slice i + d sp_in_{i+1}
+                self._bn_bwd(blk.bns[i], dy, dy_ld, blk.tb[i], W, blk.g_tb, W, M, st.grad(blk.name + ".convs.%d.bias" % i))
+                src = blk.o1[:, :, 0:W] if i == 0 else blk.spin[i]
+                blk.convs[i].wgrad(src, C if i == 0 else W, B, 1, T, blk.g_tb, W)
+                if i > 0:
+                    blk.convs[i].dgrad(blk.g_tb, W, B, 1, T, blk.g_sp, W, res=blk.g_cat[:, :, (i - 1) * W:i * W], res_ld=C,
+                                       out2=blk.g_o1[:, :, i * W:(i + 1) * W], out2_ld=C)
+                else:
+                    blk.convs[i].dgrad(blk.g_tb, W, B, 1, T, blk.g_o1[:, :, 0:W], C)
+            ops.copy_channels(blk.g_cat[:, :, C - W:], C, blk.g_o1[:, :, C - W:], C, M, W)
+            # bn1 / conv1
+            self._bn_bwd(blk.bn1, blk.g_o1, C, blk.t1, C, blk.g_t1, C, M, st.grad(blk.name + ".conv1.bias"))
+            blk.conv1.wgrad(blk.xin, blk.xin_ld, B, 1, T, blk.g_t1, C)
+            if li > 0:
+                prev = self.g_xcat[:, :, (li - 1) * C:li * C]
+                blk.conv1.dgrad(blk.g_t1, C, B, 1, T, prev, C3, accumulate=True)
+            else:
+                blk.conv1.dgrad(blk.g_t1, C, B, 1, T, self.g_xb1, C, res=dout, res_ld=C3)
+        # stem: bn1 / conv1 (no data gradient: the LFCC input needs none)
+        self._bn_bwd(self.bn1, self.g_xb1, C, self.c1, C, self.g_c1, C, M, st.grad("conv1.bias"))
+        self.conv1.wgrad(self.x0, self.mels_g, B, 1, T, self.g_c1, C)

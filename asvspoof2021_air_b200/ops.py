@@ -134,12 +134,145 @@ def sgd_step(p, g, n, lr, grad_scale=1.0):
 
 
 # ------------------------------------------------------------------------------------------
+# ECAPA-TDNN wrappers (csrc/ecapa.cu and the *_ex / *_ld entry points)
+# ------------------------------------------------------------------------------------------
+def pack_weights_ld(w, w_ld, mode, cin, cout, taps, out):
+    """w: fp32 view whose output-channel rows are w_ld elements apart (column slice of a wider weight)."""
+    n, k = (cout, taps * cin) if mode == 0 else (cin, taps * cout)
+    st = _lib.lib().air_conv_pack_weights_ld(_lib.ptr(w), _lib.LL(w_ld), _lib.ptr(out), n, k, mode, cin, cout, taps,
+                                             _lib.stream_ptr())
+    _lib.check(st, "air_conv_pack_weights_ld")
+    return out
+
+
+def conv_gemm_ex(a, a_ld, B, H, W, C, Ho, Wo, kh, kw, sh, sw, ph, pw, dh, dw, mode, wpk, N, K,
+                 out, out_ld, bias=None, res=None, res_ld=0, relu=False, flags=0, bias_rows=0, out2=None, out2_ld=0):
+    st = _lib.lib().air_conv_gemm_bf16_ex(
+        _lib.ptr(a), _lib.LL(a_ld), B, H, W, C, Ho, Wo, kh, kw, sh, sw, ph, pw, dh, dw, mode,
+        _lib.ptr(wpk), N, K, _lib.ptr(out), _lib.LL(out_ld), _lib.ptr(bias), int(bias_rows), _lib.ptr(res), _lib.LL(res_ld),
+        int(relu), _lib.ptr(out2), _lib.LL(out2_ld), num_sms(), flags, _lib.stream_ptr())
+    _lib.check(st, "air_conv_gemm_bf16_ex")
+    return out
+
+
+def conv_wgrad_ld(x, x_ld, B, H, W, C, dy, dy_ld, Ho, Wo, N, kh, kw, sh, sw, ph, pw, dh, dw, dw_out, dw_ld, flags=0):
+    st = _lib.lib().air_conv_wgrad_bf16_ld(
+        _lib.ptr(x), _lib.LL(x_ld), B, H, W, C, _lib.ptr(dy), _lib.LL(dy_ld), Ho, Wo, N,
+        kh, kw, sh, sw, ph, pw, dh, dw, _lib.ptr(dw_out), _lib.LL(dw_ld), num_sms(), flags, _lib.stream_ptr())
+    _lib.check(st, "air_conv_wgrad_bf16_ld")
+    return dw_out
+
+
+def bn_apply_add(x, x_ld, y, y_ld, M, C, sums, gamma, beta, relu, training, save_mean, save_invstd,
+                 running_mean, running_var, add, add_ld, y2, y2_ld, eps=1e-5, momentum=0.1):
+    _lib.check(_lib.lib().air_bn_apply_add(
+        _lib.ptr(x), _lib.LL(x_ld), _lib.ptr(y), _lib.LL(y_ld), _lib.LL(M), C, _lib.ptr(sums), _lib.ptr(gamma),
+        _lib.ptr(beta), _lib.F(eps), int(relu), int(training), _lib.ptr(save_mean), _lib.ptr(save_invstd),
+        _lib.ptr(running_mean), _lib.ptr(running_var), _lib.F(momentum), _lib.ptr(add), _lib.LL(add_ld), _lib.ptr(y2),
+        _lib.LL(y2_ld), num_sms(), _lib.stream_ptr()), "air_bn_apply_add")
+
+
+def bn_bwd_bias(dy, dy_ld, x, x_ld, add, add_ld, dx, dx_ld, M, C, order, mean, invstd, gamma, beta, rsum, dgamma, dbeta,
+                dbias):
+    _lib.check(_lib.lib().air_bn_bwd_bias(
+        _lib.ptr(dy), _lib.LL(dy_ld), _lib.ptr(x), _lib.LL(x_ld), _lib.ptr(add), _lib.LL(add_ld), _lib.ptr(dx),
+        _lib.LL(dx_ld), _lib.LL(M), C, order, _lib.ptr(mean), _lib.ptr(invstd), _lib.ptr(gamma), _lib.ptr(beta),
+        _lib.ptr(rsum), _lib.ptr(dgamma), _lib.ptr(dbeta), _lib.ptr(dbias), num_sms(), _lib.stream_ptr()), "air_bn_bwd_bias", 2)
+
+
+def linear_fwd_ld(x, W, ldw, bias, y, M, N, K, accumulate=False):
+    _lib.check(_lib.lib().air_linear_fwd_ld(_lib.ptr(x), _lib.ptr(W), _lib.LL(ldw), _lib.ptr(bias), _lib.ptr(y), M, N, K,
+                                            int(accumulate), _lib.stream_ptr()), "air_linear_fwd_ld")
+
+
+def linear_bwd_ld(x, W, ldw, dy, dx, dW, db, M, N, K):
+    _lib.check(_lib.lib().air_linear_bwd_ld(_lib.ptr(x), _lib.ptr(W), _lib.LL(ldw), _lib.ptr(dy), _lib.ptr(dx), _lib.ptr(dW),
+                                            _lib.ptr(db), M, N, K, _lib.stream_ptr()), "air_linear_bwd_ld", 2)
+
+
+def time_stats(x, x_ld, B, T, C, mean_out, std_out=None, clampv=0.0):
+    _lib.check(_lib.lib().air_time_stats_fwd(_lib.ptr(x), _lib.LL(x_ld), B, T, C, _lib.ptr(mean_out), _lib.ptr(std_out),
+                                             _lib.F(clampv), _lib.stream_ptr()), "air_time_stats_fwd")
+
+
+def asp_fwd(e, e_ld, x, x_ld, B, T, C, out, smax, ssum, sq):
+    _lib.check(_lib.lib().air_ecapa_asp_fwd(_lib.ptr(e), _lib.LL(e_ld), _lib.ptr(x), _lib.LL(x_ld), B, T, C, _lib.ptr(out),
+                                            _lib.ptr(smax), _lib.ptr(ssum), _lib.ptr(sq), _lib.stream_ptr()), "air_ecapa_asp_fwd")
+
+
+def asp_bwd(e, e_ld, x, x_ld, B, T, C, out, dout, smax, ssum, sq, cmean, cstd, dcmean, dcstd, clampv, de, de_ld, dx, dx_ld):
+    _lib.check(_lib.lib().air_ecapa_asp_bwd(
+        _lib.ptr(e), _lib.LL(e_ld), _lib.ptr(x), _lib.LL(x_ld), B, T, C, _lib.ptr(out), _lib.ptr(dout), _lib.ptr(smax),
+        _lib.ptr(ssum), _lib.ptr(sq), _lib.ptr(cmean), _lib.ptr(cstd), _lib.ptr(dcmean), _lib.ptr(dcstd), _lib.F(clampv),
+        _lib.ptr(de), _lib.LL(de_ld), _lib.ptr(dx), _lib.LL(dx_ld), _lib.stream_ptr()), "air_ecapa_asp_bwd")
+
+
+def ctx_bwd_mask(x, x_ld, B, T, C, cmean, cstd, dcmean, dcstd, clampv, dx, dx_ld):
+    _lib.check(_lib.lib().air_ctx_stats_bwd_mask(_lib.ptr(x), _lib.LL(x_ld), B, T, C, _lib.ptr(cmean), _lib.ptr(cstd),
+                                                 _lib.ptr(dcmean), _lib.ptr(dcstd), _lib.F(clampv), _lib.ptr(dx), _lib.LL(dx_ld),
+                                                 _lib.stream_ptr()), "air_ctx_stats_bwd_mask")
+
+
+def scale_residual(x, x_ld, gate, res, res_ld, out, out_ld, B, T, C):
+    _lib.check(_lib.lib().air_scale_residual_fwd(_lib.ptr(x), _lib.LL(x_ld), _lib.ptr(gate), _lib.ptr(res), _lib.LL(res_ld),
+                                                 _lib.ptr(out), _lib.LL(out_ld), B, T, C, _lib.stream_ptr()),
+               "air_scale_residual_fwd")
+
+
+def se_dgate(dout, d_ld, x, x_ld, B, T, C, dgate):
+    _lib.check(_lib.lib().air_se_dgate(_lib.ptr(dout), _lib.LL(d_ld), _lib.ptr(x), _lib.LL(x_ld), B, T, C, _lib.ptr(dgate),
+                                       _lib.stream_ptr()), "air_se_dgate")
+
+
+def se_apply_bwd(dout, d_ld, gate, dmean, dx, dx_ld, B, T, C):
+    _lib.check(_lib.lib().air_se_apply_bwd(_lib.ptr(dout), _lib.LL(d_ld), _lib.ptr(gate), _lib.ptr(dmean), _lib.ptr(dx),
+                                           _lib.LL(dx_ld), B, T, C, _lib.stream_ptr()), "air_se_apply_bwd")
+
+
+def bn1d_fwd(x, y, M, C, relu_in, gamma, beta, training, save_mean, save_invstd, running_mean, running_var,
+             eps=1e-5, momentum=0.1):
+    _lib.check(_lib.lib().air_bn1d_f32_fwd(_lib.ptr(x), _lib.ptr(y), M, C, int(relu_in), _lib.ptr(gamma), _lib.ptr(beta),
+                                           _lib.F(eps), int(training), _lib.ptr(save_mean), _lib.ptr(save_invstd),
+                                           _lib.ptr(running_mean), _lib.ptr(running_var), _lib.F(momentum),
+                                           _lib.stream_ptr()), "air_bn1d_f32_fwd")
+
+
+def bn1d_bwd(dy, x, dx, M, C, relu_in, gamma, mean, invstd, dgamma, dbeta):
+    _lib.check(_lib.lib().air_bn1d_f32_bwd(_lib.ptr(dy), _lib.ptr(x), _lib.ptr(dx), M, C, int(relu_in), _lib.ptr(gamma),
+                                           _lib.ptr(mean), _lib.ptr(invstd), _lib.ptr(dgamma), _lib.ptr(dbeta),
+                                           _lib.stream_ptr()), "air_bn1d_f32_bwd")
+
+
+def sigmoid_fwd(x, y, n):
+    _lib.check(_lib.lib().air_sigmoid_fwd(_lib.ptr(x), _lib.ptr(y), _lib.LL(n), _lib.stream_ptr()), "air_sigmoid_fwd")
+
+
+def sigmoid_bwd(dy, y, dx, n):
+    _lib.check(_lib.lib().air_sigmoid_bwd(_lib.ptr(dy), _lib.ptr(y), _lib.ptr(dx), _lib.LL(n), _lib.stream_ptr()), "air_sigmoid_bwd")
+
+
+def copy_channels(src, s_ld, dst, d_ld, M, C, mask=None, m_ld=0):
+    _lib.check(_lib.lib().air_copy_channels(_lib.ptr(src), _lib.LL(s_ld), _lib.ptr(mask), _lib.LL(m_ld), _lib.ptr(dst),
+                                            _lib.LL(d_ld), _lib.LL(M), C, _lib.stream_ptr()), "air_copy_channels")
+
+
+def colsum(x, ld, M, C, out):
+    _lib.check(_lib.lib().air_colsum_bf16(_lib.ptr(x), _lib.LL(ld), _lib.LL(M), C, _lib.ptr(out), _lib.stream_ptr()),
+               "air_colsum_bf16")
+
+
+# ------------------------------------------------------------------------------------------
 # Optional per-kernel-family device timing (bench.py roofline pass): CUDA events recorded on the
 # launching stream around every C-ABI call while a Profile is active.  Off by default (no cost).
 # ------------------------------------------------------------------------------------------
 class Profile:
     def __init__(self):
         self.records = []          # (family, start_event, end_event, flops, bytes)
+        self.details = []          # scalar arguments of each recorded call
+
+    def per_call(self):
+        torch.cuda.synchronize()
+        return [(r[0], r[1].elapsed_time(r[2]), r[3], d) for r, d in zip(self.records, self.details)]
 
     def __enter__(self):
         global _ACTIVE
@@ -191,6 +324,7 @@ def _timed(fn, family, work=None):
         e1.record()
         fam = family(args) if callable(family) else family
         prof.records.append((fam, e0, e1, work(args) if work else 0.0, 0.0))
+        prof.details.append(tuple(a for a in args if isinstance(a, (int, float, bool))))
         return r
     wrapper.__name__ = fn.__name__
     wrapper.__doc__ = fn.__doc__
@@ -212,3 +346,23 @@ ocsoftmax = _timed(ocsoftmax, "ocsoftmax")
 adam_l2_step = _timed(adam_l2_step, "optim")
 sgd_step = _timed(sgd_step, "optim")
 pack_weights = _timed(pack_weights, "pack_weights")
+conv_gemm_ex = _timed(conv_gemm_ex, lambda a: "conv_dgrad" if a[16] == 1 else "conv_fprop", _conv_work)
+conv_wgrad_ld = _timed(conv_wgrad_ld, "conv_wgrad", _wgrad_work)
+pack_weights_ld = _timed(pack_weights_ld, "pack_weights")
+bn_apply_add = _timed(bn_apply_add, "bn_apply")
+bn_bwd_bias = _timed(bn_bwd_bias, "bn_bwd")
+linear_fwd_ld = _timed(linear_fwd_ld, "linear")
+linear_bwd_ld = _timed(linear_bwd_ld, "linear")
+time_stats = _timed(time_stats, "time_stats")
+asp_fwd = _timed(asp_fwd, "asp_pool")
+asp_bwd = _timed(asp_bwd, "asp_pool")
+scale_residual = _timed(scale_residual, "se")
+se_dgate = _timed(se_dgate, "se")
+se_apply_bwd = _timed(se_apply_bwd, "se")
+bn1d_fwd = _timed(bn1d_fwd, "bn1d")
+bn1d_bwd = _timed(bn1d_bwd, "bn1d")
+sigmoid_fwd = _timed(sigmoid_fwd, "se")
+sigmoid_bwd = _timed(sigmoid_bwd, "se")
+copy_channels = _timed(copy_channels, "copy")
+colsum = _timed(colsum, "colsum")
+ctx_bwd_mask = _timed(ctx_bwd_mask, "asp_pool")

@@ -80,6 +80,20 @@ int air_conv_gemm_bf16(const void* a, long long a_ld, int B, int H, int W, int C
                        const float* bias, const void* res, long long res_ld, int relu,
                        int num_sms, int flags, air_stream_t stream);
 
+/* Extended forms used by the ECAPA path:
+ *   air_conv_pack_weights_ld : `w` rows are `w_ld` elements apart (a column slice of a wider weight, e.g. the
+ *                              x-block of attention.0.weight (128, 4608), ecapa_tdnn.py:139,173-175)
+ *   air_conv_gemm_bf16_ex    : bias_rows > 0 selects a per-utterance bias bias[(m / bias_rows) * N + n]
+ *                              (the folded mean/std columns of attention.0); out2 (optional) receives the
+ *                              accumulator (+bias) WITHOUT the residual (Res2 branch gradients, :77-80). */
+int air_conv_pack_weights_ld(const float* w, long long w_ld, void* dst, int N, int K, int mode, int Cin, int Cout,
+                             int taps, air_stream_t stream);
+int air_conv_gemm_bf16_ex(const void* a, long long a_ld, int B, int H, int W, int C, int Ho, int Wo,
+                          int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw, int mode,
+                          const void* wpk, int N, int K, void* out, long long out_ld,
+                          const float* bias, int bias_rows, const void* res, long long res_ld, int relu,
+                          void* out2, long long out2_ld, int num_sms, int flags, air_stream_t stream);
+
 /* Weight gradient (cuDNN wgrad in the reference's autograd): dW[n][kx] += sum_m dy[m][n] *
  * im2col(x)[m][kx], kx = (tap, ci), accumulated with fp32 atomics into the caller-zeroed
  * `dw_out` ([Cout][kh*kw*Cin] fp32, GEMM layout).  x: forward input (B,H,W,C) channels-last bf16,
@@ -88,6 +102,12 @@ int air_conv_wgrad_bf16(const void* x, long long x_ld, int B, int H, int W, int 
                         const void* dy, long long dy_ld, int Ho, int Wo, int N,
                         int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw,
                         float* dw_out, int num_sms, int flags, air_stream_t stream);
+
+/* as above with dw_out rows `dw_ld` elements apart (gradient of a column slice of a wider weight) */
+int air_conv_wgrad_bf16_ld(const void* x, long long x_ld, int B, int H, int W, int C,
+                           const void* dy, long long dy_ld, int Ho, int Wo, int N,
+                           int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw,
+                           float* dw_out, long long dw_ld, int num_sms, int flags, air_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * BatchNorm (+ReLU) on channels-last bf16 (nn.BatchNorm2d/1d + F.relu: resnet.py:54-69,132,141;
@@ -108,6 +128,19 @@ int air_bn_bwd(const void* dy, long long dy_ld, const void* x, long long x_ld, c
                void* dx, long long dx_ld, long long M, int C, int order,
                const float* mean, const float* invstd, const float* gamma, const float* beta,
                double* rsum, float* dgamma, float* dbeta, int num_sms, air_stream_t stream);
+
+/* air_bn_apply_add: air_bn_apply that also writes y2 = y + add (the Res2 branch input sp + spx[i+1],
+ * ecapa_tdnn.py:77-80).  air_bn_bwd_bias: air_bn_bwd that also accumulates dbias[c] += sum_m dx[m][c], the
+ * bias gradient of the convolution that produced x (Conv1d has bias=True throughout ecapa_tdnn.py). */
+int air_bn_apply_add(const void* x, long long x_ld, void* y, long long y_ld, long long M, int C,
+                     const double* sums, const float* gamma, const float* beta, float eps, int relu,
+                     int training, float* save_mean, float* save_invstd, float* running_mean,
+                     float* running_var, float momentum, const void* add, long long add_ld, void* y2,
+                     long long y2_ld, int num_sms, air_stream_t stream);
+int air_bn_bwd_bias(const void* dy, long long dy_ld, const void* x, long long x_ld, const void* add, long long add_ld,
+                    void* dx, long long dx_ld, long long M, int C, int order,
+                    const float* mean, const float* invstd, const float* gamma, const float* beta,
+                    double* rsum, float* dgamma, float* dbeta, float* dbias, int num_sms, air_stream_t stream);
 
 /* ResNet stem conv (Cin = 1, Cout = 16; resnet.py:131,176): direct CUDA-core forward / wgrad. */
 int air_stem_conv_fwd(const void* x, int B, int H, int W, int kh, int kw, int sh, int sw, int ph, int pw,
@@ -130,6 +163,60 @@ int air_linear_fwd(const float* x, const float* W, const float* bias, float* y, 
                    air_stream_t stream);
 int air_linear_bwd(const float* x, const float* W, const float* dy, float* dx, float* dW, float* db,
                    int M, int N, int K, air_stream_t stream);
+
+/* as above with W rows `ldw` elements apart; accumulate != 0 adds into y */
+int air_linear_fwd_ld(const float* x, const float* W, long long ldw, const float* bias, float* y, int M, int N, int K,
+                      int accumulate, air_stream_t stream);
+int air_linear_bwd_ld(const float* x, const float* W, long long ldw, const float* dy, float* dx, float* dW, float* db,
+                      int M, int N, int K, air_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * ECAPA-TDNN (Res2Net2) non-GEMM stages on channels-last bf16 (B, T, C) activations
+ * (ecapa_tdnn.py:15-29 SEModule, :64-95 Bottle2neck, :152-198 Res2Net2.forward) + autograd backward.
+ *   air_time_stats_fwd     : mean_t (and sqrt(clamp(unbiased var_t, clampv)) if std_out) -> (B, C) fp32
+ *                            (SE squeeze :25; context statistics :169-172)
+ *   air_ecapa_asp_fwd      : w = softmax_t(e); out (B,2C) = [sum_t x w | sqrt(clamp(sum_t x^2 w - mu^2, 1e-4))]
+ *                            (:176-186); saves max_t e, sum_t exp(e - max), q = sum_t x^2 w per (b, c)
+ *   air_ecapa_asp_bwd      : de (softmax backward) and dx = attentive-statistics direct path + context-statistics path
+ *   air_scale_residual_fwd : out = x * gate[b, c] + res                      (:27-28, :93)
+ *   air_se_dgate           : dgate[b, c] = sum_t dout * x
+ *   air_se_apply_bwd       : dx = dout * gate[b, c] + dmean[b, c] / T
+ *   air_bn1d_f32_fwd/bwd   : fp32 BatchNorm1d over (M = batch, C) rows; relu_in applies ReLU to the input first
+ *   air_sigmoid_fwd/bwd    : SE gate
+ *   air_copy_channels      : dst = src [* (mask > 0)] on channel slices
+ *   air_colsum_bf16        : out[c] += sum_m x[m][c] (conv bias gradients)
+ * --------------------------------------------------------------------------------------------- */
+int air_time_stats_fwd(const void* x, long long x_ld, int B, int T, int C, float* mean_out, float* std_out,
+                       float clampv, air_stream_t stream);
+int air_ecapa_asp_fwd(const void* e, long long e_ld, const void* x, long long x_ld, int B, int T, int C,
+                      float* out, float* save_max, float* save_sum, float* save_q, air_stream_t stream);
+int air_ecapa_asp_bwd(const void* e, long long e_ld, const void* x, long long x_ld, int B, int T, int C,
+                      const float* out, const float* dout, const float* save_max, const float* save_sum,
+                      const float* save_q, const float* ctx_mean, const float* ctx_std, const float* dctx_mean,
+                      const float* dctx_std, float clampv, void* de, long long de_ld, void* dx, long long dx_ld,
+                      air_stream_t stream);
+/* dx = (dx + dctx_mean/T + dctx_std (x - mean)/((T-1) std) [var > clampv]) * (x > 0): context-statistics backward
+ * (ecapa_tdnn.py:169-172) fused with the ReLU mask of layer4 (:166).  air_time_stats_fwd with clampv < 0 and
+ * std_out == NULL writes the plain sum over time instead of the mean. */
+int air_ctx_stats_bwd_mask(const void* x, long long x_ld, int B, int T, int C, const float* ctx_mean,
+                           const float* ctx_std, const float* dctx_mean, const float* dctx_std, float clampv,
+                           void* dx, long long dx_ld, air_stream_t stream);
+int air_scale_residual_fwd(const void* x, long long x_ld, const float* gate, const void* res, long long res_ld,
+                           void* out, long long out_ld, int B, int T, int C, air_stream_t stream);
+int air_se_dgate(const void* dout, long long d_ld, const void* x, long long x_ld, int B, int T, int C, float* dgate,
+                 air_stream_t stream);
+int air_se_apply_bwd(const void* dout, long long d_ld, const float* gate, const float* dmean, void* dx, long long dx_ld,
+                     int B, int T, int C, air_stream_t stream);
+int air_bn1d_f32_fwd(const float* x, float* y, int M, int C, int relu_in, const float* gamma, const float* beta,
+                     float eps, int training, float* save_mean, float* save_invstd, float* running_mean,
+                     float* running_var, float momentum, air_stream_t stream);
+int air_bn1d_f32_bwd(const float* dy, const float* x, float* dx, int M, int C, int relu_in, const float* gamma,
+                     const float* mean, const float* invstd, float* dgamma, float* dbeta, air_stream_t stream);
+int air_sigmoid_fwd(const float* x, float* y, long long n, air_stream_t stream);
+int air_sigmoid_bwd(const float* dy, const float* y, float* dx, long long n, air_stream_t stream);
+int air_copy_channels(const void* src, long long s_ld, const void* mask, long long m_ld, void* dst, long long d_ld,
+                      long long M, int C, air_stream_t stream);
+int air_colsum_bf16(const void* x, long long ld, long long M, int C, float* out, air_stream_t stream);
 
 /* OCSoftmax / AngularIsoLoss forward + analytic backward (loss.py:187-206 == :73-97) and the logged
  * CrossEntropy (main_train.py:355-357).  labels int64 (NULL: all 0).  Outputs (each optional):

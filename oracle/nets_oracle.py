@@ -93,12 +93,12 @@ def resnet_forward(sd, x, training=True, noise=None, update_running=False, bf16_
 # ECAPA-TDNN (Res2Net2 / Bottle2neck / SEModule)                 ecapa_tdnn.py:15-198
 # NB the order in this file is conv -> ReLU -> BN everywhere.
 # ------------------------------------------------------------------------------------
-def _conv1d(sd, p, x, **kw):
-    return F.conv1d(x, sd[p + ".weight"], sd[p + ".bias"], **kw)
+def _conv1d(sd, p, x, q=_q_none, **kw):
+    return F.conv1d(x, q(sd[p + ".weight"]), sd[p + ".bias"], **kw)
 
 
 def _se(sd, p, x, training, upd):
-    """ecapa_tdnn.py:15-29: mean_T -> conv 512->128 -> ReLU -> BN -> conv 128->512 -> sigmoid."""
+    """ecapa_tdnn.py:15-29: mean_T -> conv 512->128 -> ReLU -> BN -> conv 128->512 -> sigmoid (fp32 throughout)."""
     s = x.mean(dim=2, keepdim=True)
     s = F.relu(_conv1d(sd, p + ".se.1", s))
     s = _bn(sd, p + ".se.3", s, training, upd)
@@ -106,40 +106,52 @@ def _se(sd, p, x, training, upd):
     return x * s
 
 
-def _bottle2neck(sd, p, x, dilation, scale, training, upd):
-    """ecapa_tdnn.py:64-95."""
-    out = _bn(sd, p + ".bn1", F.relu(_conv1d(sd, p + ".conv1", x)), training, upd)
+def _bottle2neck(sd, p, x, dilation, scale, training, upd, q=_q_none):
+    """ecapa_tdnn.py:64-95.  q marks the points where the bf16 tensor-core path stores bf16."""
+    out = q(_bn(sd, p + ".bn1", q(F.relu(_conv1d(sd, p + ".conv1", x, q))), training, upd))
     width = out.shape[1] // scale
     spx = torch.split(out, width, 1)
     outs = []
     sp = None
     for i in range(scale - 1):
-        sp = spx[i] if i == 0 else sp + spx[i]
-        sp = _conv1d(sd, p + ".convs.%d" % i, sp, dilation=dilation, padding=dilation)
-        sp = _bn(sd, p + ".bns.%d" % i, F.relu(sp), training, upd)
+        sp = spx[i] if i == 0 else q(sp + spx[i])
+        sp = q(F.relu(_conv1d(sd, p + ".convs.%d" % i, sp, q, dilation=dilation, padding=dilation)))
+        sp = q(_bn(sd, p + ".bns.%d" % i, sp, training, upd))
         outs.append(sp)
     outs.append(spx[scale - 1])
     out = torch.cat(outs, 1)
-    out = _bn(sd, p + ".bn3", F.relu(_conv1d(sd, p + ".conv3", out)), training, upd)
+    out = q(_bn(sd, p + ".bn3", q(F.relu(_conv1d(sd, p + ".conv3", out, q))), training, upd))
     out = _se(sd, p + ".se", out, training, upd)
-    return out + x
+    return q(out + x)
 
 
-def ecapa_forward(sd, x, training=True, update_running=False, scale=8):
+def ecapa_forward(sd, x, training=True, update_running=False, scale=8, bf16_points=False):
     """x (B,n_mels,T) -> (feat (B,256), logits (B,nOut)).  ecapa_tdnn.py:152-198
-    (encoder_type='ECA', context=True, summed=False, out_bn=True: the main_train.py:167 config)."""
+    (encoder_type='ECA', context=True, summed=False, out_bn=True: the main_train.py:167 config).
+    bf16_points: as in resnet_forward (rounding where the sm_100a path stores bf16)."""
     upd = update_running
-    x = _bn(sd, "bn1", F.relu(_conv1d(sd, "conv1", x, padding=2)), training, upd)
-    x1 = _bottle2neck(sd, "layer1", x, 2, scale, training, upd)
-    x2 = _bottle2neck(sd, "layer2", x1, 3, scale, training, upd)
-    x3 = _bottle2neck(sd, "layer3", x2, 4, scale, training, upd)
-    x = F.relu(_conv1d(sd, "layer4", torch.cat((x1, x2, x3), dim=1)))
+    q = _q_bf16 if bf16_points else _q_none
+    x = q(_bn(sd, "bn1", q(F.relu(_conv1d(sd, "conv1", q(x), q, padding=2))), training, upd))
+    x1 = _bottle2neck(sd, "layer1", x, 2, scale, training, upd, q)
+    x2 = _bottle2neck(sd, "layer2", x1, 3, scale, training, upd, q)
+    x3 = _bottle2neck(sd, "layer3", x2, 4, scale, training, upd, q)
+    x = q(F.relu(_conv1d(sd, "layer4", torch.cat((x1, x2, x3), dim=1), q)))
     t = x.shape[-1]
-    gx = torch.cat((x, x.mean(dim=2, keepdim=True).repeat(1, 1, t),
-                    torch.sqrt(x.var(dim=2, keepdim=True).clamp(min=1e-4)).repeat(1, 1, t)), dim=1)
-    w = F.relu(_conv1d(sd, "attention.0", gx))
-    w = _bn(sd, "attention.2", w, training, upd)
-    w = F.softmax(_conv1d(sd, "attention.3", w), dim=2)
+    if bf16_points:
+        # the x-block of attention.0 runs on the tensor cores (bf16 weights); the time-constant mean / std
+        # blocks are folded into an fp32 per-utterance bias
+        c3 = x.shape[1]
+        w0, b0 = sd["attention.0.weight"], sd["attention.0.bias"]
+        mean = x.mean(dim=2)
+        std = torch.sqrt(x.var(dim=2).clamp(min=1e-4))
+        u = b0 + mean @ w0[:, c3:2 * c3, 0].t() + std @ w0[:, 2 * c3:, 0].t()
+        w = q(F.relu(F.conv1d(x, q(w0[:, :c3])) + u.unsqueeze(2)))
+    else:
+        gx = torch.cat((x, x.mean(dim=2, keepdim=True).repeat(1, 1, t),
+                        torch.sqrt(x.var(dim=2, keepdim=True).clamp(min=1e-4)).repeat(1, 1, t)), dim=1)
+        w = F.relu(_conv1d(sd, "attention.0", gx))
+    w = q(_bn(sd, "attention.2", w, training, upd))
+    w = F.softmax(q(_conv1d(sd, "attention.3", w, q)), dim=2)
     mu = torch.sum(x * w, dim=2)
     sg = torch.sqrt((torch.sum((x ** 2) * w, dim=2) - mu ** 2).clamp(min=1e-4))
     x = torch.cat((mu, sg), 1)
