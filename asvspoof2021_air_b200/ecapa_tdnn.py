@@ -58,9 +58,17 @@ class _EcapaFn(torch.autograd.Function):
         return (None, None, *grads)
 
 
+def _rebuild_ecapa(args, sd, training):
+    C, scale, n_out, n_mels = args
+    m = Res2Net2(Bottle2neck, C=C, model_scale=scale, nOut=n_out, n_mels=n_mels)
+    m.load_state_dict(sd)
+    m.train(training)
+    return m
+
+
 class Res2Net2(nn.Module):
     def __init__(self, block, C, model_scale, nOut, n_mels, encoder_type='ECA', context=True, summed=False, out_bn=True,
-                 device=None, **kwargs):
+                 device=None, engine=None, **kwargs):
         super().__init__()
         if encoder_type != 'ECA' or not context or summed or not out_bn:
             raise NotImplementedError("only encoder_type='ECA', context=True, summed=False, out_bn=True "
@@ -71,8 +79,14 @@ class Res2Net2(nn.Module):
             device = "cuda" if torch.cuda.is_available() else "cpu"
         self.context, self.summed, self.n_mfcc, self.encoder_type, self.out_bn = context, summed, n_mels, encoder_type, out_bn
         self.scale, self.C, self.nOut = model_scale, C, nOut
-        self.engine = EcapaEngine(C=C, scale=model_scale, n_out=nOut, n_mels=n_mels, device=device, train_head=True)
+        self.engine = engine if engine is not None else EcapaEngine(C=C, scale=model_scale, n_out=nOut, n_mels=n_mels,
+                                                                    device=device, train_head=True)
         self._bind()
+
+    def __reduce__(self):
+        """Whole-module pickles (main_train.py:674-706): constructor arguments + CPU state_dict."""
+        sd = {k: v.detach().cpu().clone() for k, v in self.state_dict().items()}
+        return (_rebuild_ecapa, ((self.C, self.scale, self.nOut, self.n_mfcc), sd, self.training))
 
     def _ordered_keys(self):
         def conv(p):

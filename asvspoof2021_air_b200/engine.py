@@ -436,6 +436,12 @@ class ResNetEngine:
     def zero_grad(self):
         self.store.grads.zero_()
 
+    grad_hook = None        # optional callable(offset): every gradient at flat index >= offset is final
+
+    def _ready(self, name):
+        if self.grad_hook is not None:
+            self.grad_hook(self.store.offsets[name][0])
+
     def backward(self, dfeat, dmu=None):
         """Accumulates parameter gradients into store.grads (call zero_grad() first).
         dfeat (B, enc_dim) fp32 [, dmu (B, nclasses) fp32]."""
@@ -454,6 +460,7 @@ class ResNetEngine:
         self.bn5.backward(self.g_z5, 256, self.c5, 256, self.g_c5, 256, M5, 0)
         last = self.blocks[-1]
         self.conv5.wgrad(last.y, 512, B, last.Ho, last.Wo, self.g_c5, 256)
+        self._ready("conv5.weight")
         self.conv5.dgrad(self.g_c5, 256, B, last.Ho, last.Wo, last.g_y, 512)
         for i in range(len(self.blocks) - 1, -1, -1):
             blk = self.blocks[i]
@@ -470,6 +477,7 @@ class ResNetEngine:
                 blk.bn1.backward(blk.g_a1, blk.cin, blk.x, blk.cin, g_x, blk.cin, Min, 0)
             else:
                 blk.bn1.backward(blk.g_a1, blk.cin, blk.x, blk.cin, g_x, blk.cin, Min, 0, add=blk.g_y, add_ld=blk.planes)
+            self._ready(blk.name + ".bn1.weight")
         M1 = B * self.H1 * self.W1
         self.bn1.backward(self.g_z1, 16, self.c1, 16, self.g_c1, 16, M1, 0)
         ops.stem_wgrad(self.x0, B, self.H0, self.W0, 9, 3, 3, 1, 1, 1, self.g_c1, 16, st.grad("conv1.weight"))

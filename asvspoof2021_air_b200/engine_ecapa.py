@@ -299,6 +299,12 @@ class EcapaEngine:
     def zero_grad(self):
         self.store.grads.zero_()
 
+    grad_hook = None        # optional callable(offset): every gradient at flat index >= offset is final
+
+    def _ready(self, name):
+        if self.grad_hook is not None:
+            self.grad_hook(self.store.offsets[name][0])
+
     def backward(self, dfeat, dlogits=None):
         """Accumulates parameter gradients into store.grads (call zero_grad() first)."""
         B, T, st, C, W, C3 = self.B, self.T, self.store, self.C, self.width, self.C3
@@ -336,6 +342,7 @@ class EcapaEngine:
         self.layer4.wgrad(self.xcat, C3, B, 1, T, self.g_x4, C3)
         ops.colsum(self.g_x4, C3, M, C3, st.grad("layer4.bias"))
         self.layer4.dgrad(self.g_x4, C3, B, 1, T, self.g_xcat, C3)
+        self._ready("layer4.weight")
         for li in range(len(self.blocks) - 1, -1, -1):
             blk = self.blocks[li]
             dout = self.g_xcat[:, :, li * C:(li + 1) * C]
@@ -379,6 +386,7 @@ class EcapaEngine:
                 blk.conv1.dgrad(blk.g_t1, C, B, 1, T, prev, C3, accumulate=True)
             else:
                 blk.conv1.dgrad(blk.g_t1, C, B, 1, T, self.g_xb1, C, res=dout, res_ld=C3)
+            self._ready(blk.name + ".conv1.weight")
         # stem: bn1 / conv1 (no data gradient: the LFCC input needs none)
         self._bn_bwd(self.bn1, self.g_xb1, C, self.c1, C, self.g_c1, C, M, st.grad("conv1.bias"))
         self.conv1.wgrad(self.x0, self.mels_g, B, 1, T, self.g_c1, C)

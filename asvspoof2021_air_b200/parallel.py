@@ -1,0 +1,117 @@
+"""Data parallelism: one process per GPU (torchrun), NCCL over NVLink/NVSwitch for the single exchange
+step of the path -- the sum all-reduce of the flat gradient buffer.
+
+The reference is single-GPU (a commented-out nn.DataParallel at main_train.py:174); utterances are
+independent through LFCC / crop-pad / conv stacks / pooling, BatchNorm statistics stay per replica (the
+reference has no SyncBN, so a per-GPU batch of B reproduces its batch-B semantics on every replica) and
+the loss is a per-replica mean.  The 1/world average is folded into the optimiser kernels (grad_scale).
+
+`GradReducer` launches the all-reduce in buckets on a side stream as the backward pass finishes the
+layers that own them (the flat buffer is in forward order, the backward pass walks it from the end), so
+the exchange overlaps the remaining dgrad/wgrad work; the optimiser waits for the last bucket.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def env_world():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def init_from_env(backend=None):
+    """Initialise torch.distributed from the torchrun environment.  Returns (rank, world, local_rank)."""
+    rank, world, local = env_world()
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend)
+    elif torch.cuda.is_available():
+        torch.cuda.set_device(local if world > 1 else torch.cuda.current_device())
+    return rank, world, local
+
+
+def shard_range(n, rank, world):
+    """Contiguous [lo, hi) slice of n utterances for this rank (sizes differ by at most one)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def bucket_bounds(n, bucket_elems):
+    """Bucket boundaries of a flat buffer of n elements, walked from the END (backward order):
+    [(lo, hi), ...] with hi descending."""
+    out, hi = [], n
+    while hi > 0:
+        lo = max(0, hi - bucket_elems)
+        out.append((lo, hi))
+        hi = lo
+    return out
+
+
+class GradReducer:
+    """Bucketed sum all-reduce of a flat gradient buffer, overlapped with the backward pass."""
+
+    def __init__(self, flat, n, group=None, bucket_elems=4 << 20, overlap=True):
+        self.flat, self.n, self.group = flat, n, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.buckets = bucket_bounds(n, bucket_elems)
+        self.overlap = overlap and flat.is_cuda
+        self.stream = torch.cuda.Stream() if self.overlap else None
+        self.next = 0
+        self.extra = []
+
+    def begin(self):
+        self.next = 0
+
+    def ready(self, offset):
+        """Every gradient at flat index >= offset is final: launch the buckets that lie above it."""
+        if self.world == 1:
+            return
+        while self.next < len(self.buckets) and self.buckets[self.next][0] >= offset:
+            self._launch(self.buckets[self.next])
+            self.next += 1
+
+    def _launch(self, rng):
+        lo, hi = rng
+        view = self.flat[lo:hi]
+        if self.overlap:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            with torch.cuda.stream(self.stream):
+                self.stream.wait_event(ev)
+                dist.all_reduce(view, group=self.group)
+        else:
+            dist.all_reduce(view, group=self.group)
+
+    def finish(self, *extra):
+        """Launch whatever is left (and the small extra tensors, e.g. the OC-Softmax centre gradient), then make
+        the compute stream wait for the exchange.  Returns the factor the optimiser applies (1/world)."""
+        if self.world == 1:
+            return 1.0
+        self.ready(0)
+        for t in extra:
+            if self.overlap:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream())
+                with torch.cuda.stream(self.stream):
+                    self.stream.wait_event(ev)
+                    dist.all_reduce(t, group=self.group)
+            else:
+                dist.all_reduce(t, group=self.group)
+        if self.overlap:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        return 1.0 / self.world
+
+
+def broadcast_state(tensors, src=0, group=None):
+    """Make every replica start from rank `src`'s parameters / buffers."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        for t in tensors:
+            dist.broadcast(t, src=src, group=group)

@@ -40,17 +40,31 @@ class _ResNetFn(torch.autograd.Function):
         return (None, None, *grads)
 
 
+def _rebuild_resnet(args, sd, training):
+    m = ResNet(*args)
+    m.load_state_dict(sd)
+    m.train(training)
+    return m
+
+
 class ResNet(nn.Module):
-    def __init__(self, num_nodes, enc_dim, resnet_type='18', nclasses=2, device=None):
+    def __init__(self, num_nodes, enc_dim, resnet_type='18', nclasses=2, device=None, engine=None):
         super().__init__()
         if str(resnet_type) != '18':
             raise NotImplementedError("only the ResNet-18 configuration used by main_train.py:162-163 is implemented")
         if device is None:
             device = "cuda" if torch.cuda.is_available() else "cpu"
         self.num_nodes, self.enc_dim, self.nclasses = num_nodes, enc_dim, nclasses
-        self.engine = ResNetEngine(enc_dim=enc_dim, nclasses=nclasses if nclasses >= 2 else 1, device=device,
-                                   train_head_mu=True, num_nodes=num_nodes)
+        self.engine = engine if engine is not None else ResNetEngine(
+            enc_dim=enc_dim, nclasses=nclasses if nclasses >= 2 else 1, device=device, train_head_mu=True,
+            num_nodes=num_nodes)
         self._bind()
+
+    def __reduce__(self):
+        """Whole-module pickles (torch.save(feat_model, ...), main_train.py:674-706) carry the constructor
+        arguments and a CPU state_dict; unpickling rebuilds the engine on the current default device."""
+        sd = {k: v.detach().cpu().clone() for k, v in self.state_dict().items()}
+        return (_rebuild_resnet, ((self.num_nodes, self.enc_dim, '18', self.nclasses), sd, self.training))
 
     # ---- state binding ------------------------------------------------------------------
     def _ordered_keys(self):

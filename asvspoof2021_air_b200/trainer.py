@@ -7,7 +7,7 @@ step and, under data parallelism, one NCCL all-reduce of the flat gradient buffe
 """
 import torch
 
-from . import ops
+from . import ops, parallel
 from .feature_extraction import LFCC
 
 BF16 = torch.bfloat16
@@ -50,6 +50,13 @@ class Trainer:
         self.dfeat = None
         self.score = None
         self.launches = 0
+        self.reducer = None
+        if self.world > 1:
+            st = self.engine.store
+            parallel.broadcast_state([st.params, self.center] + list(self.engine.buffers.named_f32().values()), 0, self.pg)
+            self.engine.mark_dirty()
+            self.reducer = parallel.GradReducer(st.grads, st.n_train, self.pg)
+            self.engine.grad_hook = self.reducer.ready
 
     def load_state(self, model_sd, center=None):
         """Load reference-layout model weights (and the OC-Softmax centre)."""
@@ -80,17 +87,47 @@ class Trainer:
         self.center_grad.zero_()
         ops.ocsoftmax(feat, labels, self.center, B, feat.shape[1], self.r_real, self.r_fake, self.alpha,
                       self.weight_loss, self.loss, self.score, self.dfeat, self.center_grad, logits, logits.shape[1], self.ce)
+        if self.reducer is not None:
+            self.reducer.begin()
         eng.backward(self.dfeat)
-        scale = 1.0
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(eng.store.grads[:eng.store.n_train], group=self.pg)
-            dist.all_reduce(self.center_grad, group=self.pg)
-            scale = 1.0 / self.world
+        scale = self.reducer.finish(self.center_grad) if self.reducer is not None else 1.0
         lr = self.lr if lr is None else lr
         eng.store.adam_step(lr, self.betas[0], self.betas[1], self.eps, self.wd, grad_scale=scale)
         ops.sgd_step(self.center, self.center_grad, self.center.numel(), lr, scale)
         return self.loss
+
+    @torch.no_grad()
+    def eval_loss(self, waves, labels, lengths=None, start=None):
+        """Validation pass (main_train.py:489-577): eval-mode forward, OC-Softmax loss and scores, no update."""
+        eng = self.engine
+        B = waves.shape[0]
+        feat, logits = eng.forward(self.features(waves, lengths, start), training=False)
+        loss = torch.empty(1, device=self.device)
+        score = torch.empty(B, device=self.device)
+        ops.ocsoftmax(feat, labels, self.center, B, feat.shape[1], self.r_real, self.r_fake, self.alpha, 1.0,
+                      loss, score, None, None)
+        return loss, score
+
+    # ---- checkpoints (main_train.py:674-706 saves whole-module pickles) -------------------------
+    def modules(self):
+        """(feat_model, loss_model): the drop-in nn.Modules bound to this trainer's parameters."""
+        from .loss import AngularIsoLoss
+        if self.arch == "resnet":
+            from .resnet import ResNet
+            model = ResNet(3, self.engine.enc_dim, '18', nclasses=2, engine=self.engine)
+        else:
+            from .ecapa_tdnn import Res2Net2, Bottle2neck
+            model = Res2Net2(Bottle2neck, C=self.engine.C, model_scale=self.engine.scale, nOut=self.engine.n_out,
+                             n_mels=self.engine.n_mels, engine=self.engine)
+        loss_model = AngularIsoLoss(self.center.shape[1], r_real=self.r_real, r_fake=self.r_fake, alpha=self.alpha)
+        loss_model.center.data = self.center
+        return model, loss_model
+
+    def load_modules(self, model, loss_model=None):
+        """Adopt the weights of (unpickled) drop-in modules, e.g. for --continue_training / scoring."""
+        self.engine.load_state({k: v for k, v in model.state_dict().items()})
+        if loss_model is not None:
+            self.center.copy_(loss_model.center.detach().to(self.device))
 
     @torch.no_grad()
     def score_step(self, waves, lengths=None, start=None):

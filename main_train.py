@@ -1,0 +1,220 @@
+#!/usr/bin/env python
+"""Training driver with the argparse surface of the reference's main_train.py:23-95 (every flag, same
+names and defaults), running the fused B200 path: raw waves -> on-device LFCC / crop / pad -> ResNet-18 or
+ECAPA-TDNN -> OC-Softmax (`--add_loss ang_iso`) -> backward -> Adam(L2) + SGD(centre), one process per GPU
+under torchrun with an NCCL gradient all-reduce.
+
+Kept from the reference: args.json, train_loss.log (`epoch\\tstep\\tloss`), dev_loss.log, per-epoch whole-module
+checkpoints `checkpoint/anti-spoofing_{feat,loss}_model_%d.pt`, best-dev copies `anti-spoofing_{feat,loss}_model.pt`,
+lr * lr_decay^(epoch // interval), --continue_training (model + loss module only, main_train.py:172-173).
+New flags: --synthetic N (seeded synthetic utterances per epoch), --wave_dir / --protocol (+ --dev_*) for raw
+audio, --steps_per_epoch, --log_every.  Out of the hot-path scope and rejected at run time with a clear
+message: models other than resnet / ecapa, --add_loss other than ang_iso, --ADV_AUG, --visualize
+(SURVEY.md section 2.1).
+"""
+import argparse
+import json
+import os
+import shutil
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from asvspoof2021_air_b200.utils import setup_seed, str2bool  # noqa: E402
+
+# (flags, kwargs) -- names / defaults / choices as in main_train.py:26-93
+_REFERENCE_FLAGS = [
+    (("--seed",), dict(type=int, default=688)),
+    (("-a", "--access_type"), dict(type=str, default="LA")),
+    (("-d", "--path_to_database"), dict(type=str, default="/data/neil/DS_10283_3336/")),
+    (("-f", "--path_to_features"), dict(type=str, default="/data2/neil/ASVspoof2019LA/")),
+    (("-o", "--out_fold"), dict(type=str, required=True, default="./models/try/")),
+    (("--ratio",), dict(type=float, default=0.5)),
+    (("--feat",), dict(type=str, default="LFCC", choices=["CQCC", "LFCC"])),
+    (("--feat_len",), dict(type=int, default=750)),
+    (("--pad_chop",), dict(type=str2bool, nargs="?", const=True, default=True)),
+    (("--padding",), dict(type=str, default="repeat", choices=["zero", "repeat", "silence"])),
+    (("--enc_dim",), dict(type=int, default=256)),
+    (("-m", "--model"), dict(default="lcnn", choices=["cnn", "resnet", "lcnn", "res2net", "ecapa"])),
+    (("--num_epochs",), dict(type=int, default=200)),
+    (("--batch_size",), dict(type=int, default=64)),
+    (("--lr",), dict(type=float, default=0.0005)),
+    (("--lr_decay",), dict(type=float, default=0.5)),
+    (("--interval",), dict(type=int, default=30)),
+    (("--beta_1",), dict(type=float, default=0.9)),
+    (("--beta_2",), dict(type=float, default=0.999)),
+    (("--eps",), dict(type=float, default=1e-8)),
+    (("--gpu",), dict(type=str, default="1")),
+    (("--num_workers",), dict(type=int, default=0)),
+    (("--base_loss",), dict(type=str, default="ce", choices=["ce", "bce"])),
+    (("--add_loss",), dict(type=str, default=None, choices=[None, "isolate", "ang_iso", "p2sgrad"])),
+    (("--weight_loss",), dict(type=float, default=1)),
+    (("--r_real",), dict(type=float, default=0.9)),
+    (("--r_fake",), dict(type=float, default=0.2)),
+    (("--alpha",), dict(type=float, default=20)),
+    (("--num_centers",), dict(type=int, default=3)),
+    (("--visualize",), dict(action="store_true")),
+    (("--test_only",), dict(action="store_true")),
+    (("--continue_training",), dict(action="store_true")),
+    (("--ADV_AUG",), dict(type=str2bool, nargs="?", const=True, default=False)),
+    (("--LA_aug",), dict(type=str2bool, nargs="?", const=True, default=False)),
+    (("--DF_aug",), dict(type=str2bool, nargs="?", const=True, default=False)),
+    (("--LAPA_aug",), dict(type=str2bool, nargs="?", const=True, default=False)),
+    (("--DFPA_aug",), dict(type=str2bool, nargs="?", const=True, default=False)),
+    (("--lambda_",), dict(type=float, default=0.05)),
+    (("--lr_d",), dict(type=float, default=0.0001)),
+    (("--pre_train",), dict(action="store_true")),
+    (("--test_on_eval",), dict(action="store_true")),
+]
+
+
+def build_parser():
+    parser = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    for flags, kw in _REFERENCE_FLAGS:
+        parser.add_argument(*flags, **kw)
+    new = parser.add_argument_group("fused raw-wave path (not in the reference)")
+    new.add_argument("--synthetic", type=int, default=0, help="train on N seeded synthetic 4 s utterances per epoch")
+    new.add_argument("--dev_synthetic", type=int, default=0, help="validate on N synthetic utterances")
+    new.add_argument("--wave_dir", type=str, default=None, help="folder of .wav / .npy training waves")
+    new.add_argument("--protocol", type=str, default=None, help="protocol file for --wave_dir")
+    new.add_argument("--dev_wave_dir", type=str, default=None)
+    new.add_argument("--dev_protocol", type=str, default=None)
+    new.add_argument("--steps_per_epoch", type=int, default=0, help="0: one pass over the source")
+    new.add_argument("--log_every", type=int, default=50, help="steps between host reads of the device losses")
+    return parser
+
+
+def init_params(argv=None):
+    args = build_parser().parse_args(argv)
+    assert 0 < args.ratio <= 1                                           # main_train.py:98
+    rank = int(os.environ.get("RANK", "0"))
+    if "LOCAL_RANK" not in os.environ:
+        os.environ["CUDA_VISIBLE_DEVICES"] = args.gpu                     # main_train.py:101 (single-process launch)
+    setup_seed(args.seed)
+    if not (args.test_only or args.continue_training) and rank == 0:
+        if os.path.exists(args.out_fold):
+            shutil.rmtree(args.out_fold)
+        os.makedirs(os.path.join(args.out_fold, "checkpoint"))
+        with open(os.path.join(args.out_fold, "args.json"), "w") as f:
+            f.write(json.dumps(vars(args), sort_keys=True, separators=("\n", ":")))
+        for name, what in (("train_loss.log", "training"), ("dev_loss.log", "validation"), ("test_loss.log", "test")):
+            with open(os.path.join(args.out_fold, name), "w") as f:
+                f.write("Start recording %s loss ...\n" % what)
+    args.cuda = torch.cuda.is_available()
+    args.device = torch.device("cuda" if args.cuda else "cpu")
+    return args
+
+
+def adjust_learning_rate(args, lr, epoch_num):
+    """main_train.py:144-147."""
+    return lr * (args.lr_decay ** (epoch_num // args.interval))
+
+
+def _reject_out_of_scope(args):
+    if args.model not in ("resnet", "ecapa"):
+        raise SystemExit("--model %s is outside the B200 hot path (resnet / ecapa only, SURVEY.md section 2.1)" % args.model)
+    if args.add_loss != "ang_iso":
+        raise SystemExit("only --add_loss ang_iso (OC-Softmax) is implemented on the fused path")
+    if args.ADV_AUG or args.visualize:
+        raise SystemExit("--ADV_AUG / --visualize are outside the B200 hot path")
+    if args.feat != "LFCC":
+        raise SystemExit("only --feat LFCC is implemented (computed on device from raw waves)")
+
+
+def _source(args, dev=False):
+    from asvspoof2021_air_b200 import data
+    n = args.dev_synthetic if dev else args.synthetic
+    folder = args.dev_wave_dir if dev else args.wave_dir
+    if folder:
+        return data.WaveFolder(folder, args.dev_protocol if dev else args.protocol, args.feat_len, args.seed + (1 if dev else 0))
+    if n > 0:
+        return data.SyntheticWaves(n, seed=args.seed + (7 if dev else 0), feat_len=args.feat_len)
+    if dev:
+        return None
+    raise SystemExit("no training data: the reference's pre-extracted .pt feature folders (--path_to_features) are replaced "
+                     "by on-device LFCC; pass --wave_dir/--protocol or --synthetic N")
+
+
+def train(args):
+    from asvspoof2021_air_b200 import parallel
+    from asvspoof2021_air_b200.trainer import Trainer
+    _reject_out_of_scope(args)
+    if not torch.cuda.is_available():
+        raise SystemExit("main_train.py needs a CUDA device: the fused path has no CPU fallback")
+    rank, world, _ = parallel.init_from_env()
+    pg = torch.distributed.group.WORLD if world > 1 else None
+    tr = Trainer(arch=args.model, enc_dim=args.enc_dim, feat_len=args.feat_len, padding=args.padding, lr=args.lr,
+                 beta_1=args.beta_1, beta_2=args.beta_2, eps=args.eps, weight_decay=0.0005, r_real=args.r_real,
+                 r_fake=args.r_fake, alpha=args.alpha, weight_loss=args.weight_loss, device="cuda", process_group=pg,
+                 seed=args.seed)
+    if args.continue_training:                                            # main_train.py:172-173
+        model = torch.load(os.path.join(args.out_fold, "anti-spoofing_feat_model.pt"), weights_only=False)
+        lp = os.path.join(args.out_fold, "anti-spoofing_loss_model.pt")
+        tr.load_modules(model, torch.load(lp, weights_only=False) if os.path.exists(lp) else None)
+    src, dev_src = _source(args), _source(args, dev=True)
+    per_rank = args.batch_size
+    order_rng = np.random.RandomState(args.seed)
+    steps = args.steps_per_epoch or max(1, len(src) // (per_rank * world))
+    prev_loss, early_stop_cnt = 1e8, 0
+    feat_model = loss_model = None
+    for epoch in range(args.num_epochs):
+        lr = adjust_learning_rate(args, args.lr, epoch)
+        perm = order_rng.permutation(len(src))                            # SubsetRandomSampler, main_train.py:226-242
+        pending = []
+        for step in range(steps):
+            base = (step * world + rank) * per_rank
+            idx = [perm[(base + j) % len(src)] for j in range(per_rank)]
+            waves, lengths, labels, _, start = src.batch(idx)
+            loss = tr.train_step(waves.cuda(non_blocking=True), labels.cuda(non_blocking=True),
+                                 lengths=None if int(lengths.min()) == waves.shape[1] else lengths, start=start, lr=lr)
+            pending.append((step, loss.clone()))
+            if len(pending) >= args.log_every or step == steps - 1:
+                if rank == 0:                                             # main_train.py:479-481, batched host reads
+                    with open(os.path.join(args.out_fold, "train_loss.log"), "a") as log:
+                        for s, l in pending:
+                            log.write("%d\t%d\t%s\n" % (epoch, s, float(l)))
+                pending = []
+        val = float("nan")
+        if dev_src is not None:
+            tot, cnt = 0.0, 0
+            for lo in range(rank * per_rank, len(dev_src), per_rank * world):
+                idx = list(range(lo, min(lo + per_rank, len(dev_src))))
+                waves, lengths, labels, _, start = dev_src.batch(idx)
+                l, _ = tr.eval_loss(waves.cuda(), labels.cuda(), None if int(lengths.min()) == waves.shape[1] else lengths, start)
+                tot, cnt = tot + float(l) * len(idx), cnt + len(idx)
+            t = torch.tensor([tot, cnt], device="cuda", dtype=torch.float64)
+            if world > 1:
+                torch.distributed.all_reduce(t)
+            val = float(t[0] / t[1].clamp(min=1))
+            if rank == 0:
+                with open(os.path.join(args.out_fold, "dev_loss.log"), "a") as log:
+                    log.write("%d\t%s\n" % (epoch, val))
+        if rank == 0:                                                     # main_train.py:674-706
+            feat_model, loss_model = tr.modules()
+            ck = os.path.join(args.out_fold, "checkpoint")
+            torch.save(feat_model, os.path.join(ck, "anti-spoofing_feat_model_%d.pt" % (epoch + 1)))
+            torch.save(loss_model, os.path.join(ck, "anti-spoofing_loss_model_%d.pt" % (epoch + 1)))
+            if not (val >= prev_loss):                                    # also when there is no dev set (nan)
+                torch.save(feat_model, os.path.join(args.out_fold, "anti-spoofing_feat_model.pt"))
+                torch.save(loss_model, os.path.join(args.out_fold, "anti-spoofing_loss_model.pt"))
+        if val < prev_loss:
+            prev_loss, early_stop_cnt = val, 0
+        elif val == val:
+            early_stop_cnt += 1
+        if early_stop_cnt == 500:                                         # main_train.py:711-714
+            if rank == 0:
+                with open(os.path.join(args.out_fold, "args.json"), "a") as f:
+                    f.write("\nTrained Epochs: %d\n" % (epoch - 499))
+            break
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return feat_model, loss_model
+
+
+if __name__ == "__main__":
+    train(init_params())

@@ -1,0 +1,181 @@
+"""CPU tests of the host-side logic: drop-in module surfaces (constructor signatures, state_dict keys,
+whole-module pickles), the CLI argparse surfaces against the reference's, data sources, score-file
+formatting, LR schedule, and the data-parallel helpers under gloo with world_size 2."""
+import io
+import os
+import re
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_shim, state_spec as ss
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_resnet_module_surface_and_pickle():
+    from asvspoof2021_air_b200.resnet import ResNet
+    m = ResNet(3, 256, resnet_type='18', nclasses=2, device="cpu")
+    spec = ss.resnet_spec()
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == [(k, tuple(s)) for k, s, _ in spec]
+    sd = ss.seeded_state(spec, 3)
+    m.load_state_dict(sd)
+    buf = io.BytesIO()
+    torch.save(m, buf)                                        # main_train.py:674 saves whole modules
+    buf.seek(0)
+    m2 = torch.load(buf, weights_only=False)
+    assert type(m2).__name__ == "ResNet"
+    for k, v in m2.state_dict().items():
+        assert torch.equal(v.cpu().float(), sd[k].float()), k
+    with pytest.raises(Exception):
+        m(torch.zeros(1, 1, 60, 750))                         # no CPU path: fails loudly
+
+
+def test_ecapa_module_surface_and_pickle():
+    from asvspoof2021_air_b200.ecapa_tdnn import Res2Net2, Bottle2neck
+    m = Res2Net2(Bottle2neck, C=512, model_scale=8, nOut=2, n_mels=60, device="cpu")
+    spec = ss.ecapa_spec()
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == [(k, tuple(s)) for k, s, _ in spec]
+    assert sum(p.numel() for p in m.parameters()) == 6337734
+    sd = ss.seeded_state(spec, 4)
+    m.load_state_dict(sd)
+    buf = io.BytesIO()
+    torch.save(m, buf)
+    buf.seek(0)
+    m2 = torch.load(buf, weights_only=False)
+    for k, v in m2.state_dict().items():
+        assert torch.equal(v.cpu().float(), sd[k].float()), k
+    with pytest.raises(Exception):
+        m(torch.zeros(1, 60, 750))
+
+
+def test_loss_and_lfcc_module_surfaces():
+    from asvspoof2021_air_b200.loss import OCSoftmax, AngularIsoLoss
+    from asvspoof2021_air_b200.feature_extraction import LFCC
+    l = AngularIsoLoss(256, r_real=0.9, r_fake=0.2, alpha=20.0)
+    assert list(l.state_dict().keys()) == ["center"] and tuple(l.center.shape) == (1, 256)
+    assert OCSoftmax().r_fake == 0.5                               # class default, loss.py:177
+    f = LFCC(320, 160, 512, 16000, 20)
+    assert sorted(f.state_dict().keys()) == ["l_dct.weight", "lfcc_fb"]
+    assert tuple(f.lfcc_fb.shape) == (257, 20) and tuple(f.l_dct.weight.shape) == (20, 20)
+    with pytest.raises(Exception):
+        f(torch.zeros(1, 1000))
+
+
+def _flag_table(parser):
+    out = {}
+    for a in parser._actions:
+        for s in a.option_strings:
+            if s not in ("-h", "--help"):
+                out[s] = (a.default, tuple(a.choices) if a.choices else None)
+    return out
+
+
+def test_cli_surfaces_cover_the_reference_flags():
+    sys.path.insert(0, ROOT)
+    import main_train
+    import generate_score
+    ours = _flag_table(main_train.build_parser())
+    want = {"--seed": 688, "--feat_len": 750, "--padding": "repeat", "--enc_dim": 256, "--model": "lcnn", "--batch_size": 64,
+            "--lr": 0.0005, "--lr_decay": 0.5, "--interval": 30, "--beta_1": 0.9, "--beta_2": 0.999, "--eps": 1e-8,
+            "--add_loss": None, "--weight_loss": 1, "--r_real": 0.9, "--r_fake": 0.2, "--alpha": 20, "--num_epochs": 200,
+            "--ratio": 0.5, "--gpu": "1", "--lambda_": 0.05, "--lr_d": 0.0001, "--ADV_AUG": False}
+    for k, v in want.items():
+        assert ours[k][0] == v, k
+    gs = _flag_table(generate_score.build_parser())
+    assert gs["--task"][1] == tuple(generate_score.TASKS) and gs["--loss"][1] == (None, "ocsoftmax", "amsoftmax", "p2sgrad")
+    if ref_shim.reference_available():
+        for fname, table in (("main_train.py", ours), ("generate_score.py", gs)):
+            src = open(os.path.join(ref_shim.REFERENCE_ROOT, fname)).read()
+            flags = set(re.findall(r"add_argument\((?:['\"](-\w)['\"],\s*)?['\"](--\w+)['\"]", src))
+            for short, long in flags:
+                assert long in table, (fname, long)
+                if short:
+                    assert short in table, (fname, short)
+    args = main_train.build_parser().parse_args(["-o", "/tmp/x", "--add_loss", "ang_iso", "-m", "resnet", "--pad_chop", "False"])
+    assert args.pad_chop is False and args.model == "resnet"
+    assert main_train.adjust_learning_rate(args, 5e-4, 61) == 5e-4 * 0.25          # main_train.py:144-147
+
+
+def test_score_line_format_and_paths(tmp_path):
+    sys.path.insert(0, ROOT)
+    import generate_score as gs
+    assert gs.format_line("LA", "LA_E_1", 0.5, 0) == "LA_E_1 0.5\n"
+    assert gs.format_line("19eval", "LA_E_1", -0.25, 1) == "LA_E_1 -0.25 spoof\n"
+    assert gs.score_file_path(str(tmp_path), "m", "19dev").endswith("m_19dev_score.txt")
+    assert gs.score_file_path(str(tmp_path), "m", "DF").endswith(os.path.join("m_DF", "score.txt"))
+
+
+def test_data_sources(tmp_path):
+    from asvspoof2021_air_b200 import data
+    s = data.SyntheticWaves(10, length=3200, seed=1)
+    w, lens, lab, names, start = s.batch([0, 1, 5])
+    w2 = s.batch([5])[0]
+    assert w.shape == (3, 3200) and torch.equal(w[2], w2[0]) and lab.tolist() == [0, 1, 1] and start is None
+    import wave
+    a = (np.sin(np.arange(200000) * 0.01) * 1000).astype(np.int16)
+    with wave.open(str(tmp_path / "u1.wav"), "wb") as f:
+        f.setnchannels(1); f.setsampwidth(2); f.setframerate(16000); f.writeframes(a.tobytes())
+    np.save(tmp_path / "u2.npy", np.zeros(1000, dtype=np.float32))
+    (tmp_path / "proto.txt").write_text("LA_0001 u1 - A07 spoof\nu2 bonafide\n")
+    d = data.WaveFolder(str(tmp_path), str(tmp_path / "proto.txt"), feat_len=750, seed=0)
+    w, lens, lab, names, start = d.batch([0, 1])
+    assert w.shape == (2, 200000) and lens.tolist() == [200000, 1000] and lab.tolist() == [1, 0] and names == ["u1", "u2"]
+    assert abs(float(w[0, 157]) - a[157] / 32768.0) < 1e-7 and (w[1] == 0).all()
+    assert 0 <= int(start[0]) < (1 + 200000 // 160) - 750 and int(start[1]) == 0      # dataset.py:66-69
+
+
+def test_parallel_helpers_single_process():
+    from asvspoof2021_air_b200 import parallel
+    assert [parallel.shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    b = parallel.bucket_bounds(10, 4)
+    assert b == [(6, 10), (2, 6), (0, 2)]
+    r = parallel.GradReducer(torch.zeros(10), 10, bucket_elems=4)
+    r.begin(); r.ready(3)
+    assert r.finish() == 1.0
+
+
+_WORKER = textwrap.dedent('''
+    import os, sys, torch
+    sys.path.insert(0, %r)
+    import torch.distributed as dist
+    from asvspoof2021_air_b200 import parallel
+    rank, world, _ = parallel.init_from_env("gloo")
+    assert world == 2 and dist.get_backend() == "gloo"
+    n = 1000
+    flat = torch.arange(n, dtype=torch.float32) * (rank + 1)
+    extra = torch.full((4,), float(rank + 1))
+    red = parallel.GradReducer(flat, n - 100, bucket_elems=256, overlap=False)     # the tail is not reduced (frozen params)
+    red.begin()
+    launched = []
+    for off in (900, 700, 300):          # backward order: the layers owning the highest offsets finish first
+        red.ready(off)
+        launched.append(red.next)
+    scale = red.finish(extra)
+    assert launched == [0, 0, 2] and red.next == 4, (launched, red.next)
+    want = torch.arange(n, dtype=torch.float32) * 3
+    assert torch.equal(flat[:900], want[:900]) and torch.equal(flat[900:], torch.arange(900, n, dtype=torch.float32) * (rank + 1))
+    assert torch.equal(extra, torch.full((4,), 3.0)) and scale == 0.5
+    p = torch.full((5,), float(rank))
+    parallel.broadcast_state([p], 0)
+    assert torch.equal(p, torch.zeros(5))
+    lo, hi = parallel.shard_range(7, rank, world)
+    t = torch.tensor([hi - lo], dtype=torch.float32); dist.all_reduce(t); assert int(t) == 7
+    dist.destroy_process_group()
+    print("rank", rank, "ok")
+''')
+
+
+def test_gradient_reducer_gloo_world_size_2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER % ROOT)
+    port = 29500 + os.getpid() % 1000
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
