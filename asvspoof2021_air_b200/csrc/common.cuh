@@ -50,15 +50,26 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 __device__ __forceinline__ float bf2f(__nv_bfloat16 v) { return __bfloat162float(v); }
 __device__ __forceinline__ __nv_bfloat16 f2bf(float v) { return __float2bfloat16_rn(v); }
 
-// 8 bf16 <-> 8 floats through one 16-byte vector
-struct __align__(16) bf16x8 { __nv_bfloat162 v[4]; };
+// 8 bf16 <-> 8 floats through ONE 16-byte vector access.  The payload is a uint4 so that loads / stores of a
+// bf16x8 compile to LDG.128 / STG.128 (a struct of four __nv_bfloat162 is split into 32-bit accesses).
+struct __align__(16) bf16x8 { uint4 u; };
+__device__ __forceinline__ float2 bf2x_to_f2(uint32_t w) {
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t f2_to_bf2x(float lo, float hi) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
 __device__ __forceinline__ void unpack8(const bf16x8& p, float* f) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(p.v[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+  float2 t;
+  t = bf2x_to_f2(p.u.x); f[0] = t.x; f[1] = t.y;
+  t = bf2x_to_f2(p.u.y); f[2] = t.x; f[3] = t.y;
+  t = bf2x_to_f2(p.u.z); f[4] = t.x; f[5] = t.y;
+  t = bf2x_to_f2(p.u.w); f[6] = t.x; f[7] = t.y;
 }
 __device__ __forceinline__ bf16x8 pack8(const float* f) {
   bf16x8 p;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  p.u.x = f2_to_bf2x(f[0], f[1]); p.u.y = f2_to_bf2x(f[2], f[3]);
+  p.u.z = f2_to_bf2x(f[4], f[5]); p.u.w = f2_to_bf2x(f[6], f[7]);
   return p;
 }

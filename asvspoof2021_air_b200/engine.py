@@ -93,6 +93,19 @@ class ConvLayer:
         self.wpk = torch.empty(ops.packed_elems(cout, self.K), device=dev, dtype=BF16)
         self.wpk_d = torch.empty(ops.packed_elems(self.cin_g, self.taps * cout), device=dev, dtype=BF16) if need_dgrad else None
         self._wtmp = torch.zeros(cout, self.taps, self.cin_g, device=dev) if self.cin_g != cin else None
+        # 3x3 / stride 1 / pad 1 layers may run on the patch-resident kernel (chosen per call from the image size)
+        self.patch_ok = ((kh, kw, sh, sw, ph, pw, dh, dw) == (3, 3, 1, 1, 1, 1, 1, 1) and not bias and self._wtmp is None
+                         and ops.patch_supported(cin, cout, 1, 1) and ops.patch_supported(cout, cin, 1, 1)
+                         and cin <= 128 and cout <= 128)
+        self.wpk3 = torch.empty(9 * cin * cout, device=dev, dtype=BF16) if self.patch_ok else None
+        self.wpk3_d = torch.empty(9 * cin * cout, device=dev, dtype=BF16) if (self.patch_ok and need_dgrad) else None
+
+    @staticmethod
+    def _patch_efficiency(H, W):
+        return (W / (-(-W // 128) * 128)) * (H / (-(-H // 2) * 2))
+
+    def use_patch(self, H, W):
+        return self.patch_ok and self._patch_efficiency(H, W) >= 0.8
 
     def out_hw(self, H, W):
         return (ops.conv_out_size(H, self.kh, self.sh, self.ph, self.dh),
@@ -110,9 +123,16 @@ class ConvLayer:
         ops.pack_weights(w, 0, self.cin_g, self.cout, self.taps, self.wpk)
         if self.need_dgrad:
             ops.pack_weights(w, 1, self.cin_g, self.cout, self.taps, self.wpk_d)
+        if self.patch_ok:
+            ops.pack3x3(w, self.cin, self.cout, 0, self.wpk3)
+            if self.need_dgrad:
+                ops.pack3x3(w, self.cout, self.cin, 1, self.wpk3_d)
 
     def fprop(self, x, x_ld, B, H, W, out, out_ld, res=None, res_ld=0, relu=False):
         Ho, Wo = self.out_hw(H, W)
+        if self.use_patch(H, W):
+            ops.conv3x3_patch(x, x_ld, B, H, W, self.cin, self.wpk3, self.cout, out, out_ld, res, res_ld, relu, 0)
+            return Ho, Wo
         bias = self.store.view(self.name + ".bias") if self.bias else None
         ops.conv_gemm(x, x_ld, B, H, W, self.cin_g, Ho, Wo, self.kh, self.kw, self.sh, self.sw, self.ph, self.pw,
                       self.dh, self.dw, 0, self.wpk, self.cout, self.K, out, out_ld, bias, res, res_ld, relu)
@@ -124,6 +144,9 @@ class ConvLayer:
         Ho, Wo = self.out_hw(H, W)
         if accumulate:
             res, res_ld = dx, dx_ld
+        if out2 is None and self.use_patch(H, W):
+            ops.conv3x3_patch(dy, dy_ld, B, H, W, self.cout, self.wpk3_d, self.cin, dx, dx_ld, res, res_ld, False, 1)
+            return
         ops.conv_gemm_ex(dy, dy_ld, B, Ho, Wo, self.cout, H, W, self.kh, self.kw, self.sh, self.sw, self.ph, self.pw,
                          self.dh, self.dw, 1, self.wpk_d, self.cin_g, self.taps * self.cout, dx, dx_ld, None,
                          res, res_ld, False, 0, 0, out2, out2_ld)

@@ -56,6 +56,25 @@ def conv_wgrad(x, x_ld, B, H, W, C, dy, dy_ld, Ho, Wo, N, kh, kw, sh, sw, ph, pw
     return dw_out
 
 
+def patch_supported(C, N, H, W):
+    return bool(_lib.lib().air_conv3x3_patch_supported(int(C), int(N), int(H), int(W)))
+
+
+def pack3x3(w, C, N, mode, out):
+    """w: fp32 [Cout][3][3][Cin] (GEMM layout); mode 0: (C, N) = (Cin, Cout); mode 1 (dgrad): (C, N) = (Cout, Cin)."""
+    _lib.check(_lib.lib().air_conv3x3_pack_weights(_lib.ptr(w), _lib.ptr(out), C, N, mode, _lib.stream_ptr()),
+               "air_conv3x3_pack_weights")
+    return out
+
+
+def conv3x3_patch(a, a_ld, B, H, W, C, wpk, N, out, out_ld, res=None, res_ld=0, relu=False, mode=0):
+    """mode is only a label for the profiler (0 fprop, 1 dgrad): the arithmetic is identical."""
+    _lib.check(_lib.lib().air_conv3x3_patch_bf16(_lib.ptr(a), _lib.LL(a_ld), B, H, W, C, _lib.ptr(wpk), N, _lib.ptr(out),
+                                                 _lib.LL(out_ld), _lib.ptr(res), _lib.LL(res_ld), int(relu), num_sms(),
+                                                 _lib.stream_ptr()), "air_conv3x3_patch_bf16")
+    return out
+
+
 def conv_out_size(n, k, s, p, d):
     return (n + 2 * p - d * (k - 1) - 1) // s + 1
 
@@ -366,3 +385,6 @@ sigmoid_bwd = _timed(sigmoid_bwd, "se")
 copy_channels = _timed(copy_channels, "copy")
 colsum = _timed(colsum, "colsum")
 ctx_bwd_mask = _timed(ctx_bwd_mask, "asp_pool")
+pack3x3 = _timed(pack3x3, "pack_weights")
+conv3x3_patch = _timed(conv3x3_patch, lambda a: "conv_dgrad" if (len(a) > 13 and a[13] == 1) else "conv_fprop",
+                       lambda a: 2.0 * a[2] * a[3] * a[4] * a[5] * a[7] * 9)

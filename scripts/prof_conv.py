@@ -1,0 +1,37 @@
+"""Run a single conv layer shape a few times (for ncu captures).  usage: prof_conv.py kind B H W C N"""
+import os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from asvspoof2021_air_b200 import ops
+
+kind = sys.argv[1]
+B, H, W, C, N = (int(v) for v in sys.argv[2:7])
+x = torch.randn(B, H, W, C, device="cuda").to(torch.bfloat16)
+w = torch.randn(N, 3, 3, C, device="cuda") / (9 * C) ** 0.5
+out = torch.empty(B, H, W, N, device="cuda", dtype=torch.bfloat16)
+dy = torch.randn(B, H, W, N, device="cuda").to(torch.bfloat16)
+if kind == "patch":
+    wpk = torch.empty(9 * C * N, device="cuda", dtype=torch.bfloat16)
+    ops.pack3x3(w, C, N, 0, wpk)
+    f = lambda: ops.conv3x3_patch(x, C, B, H, W, C, wpk, N, out, N)
+elif kind == "gemm":
+    wpk = ops.pack_weights(w.reshape(N, 9, C).contiguous(), 0, C, N, 9)
+    f = lambda: ops.conv_gemm(x, C, B, H, W, C, H, W, 3, 3, 1, 1, 1, 1, 1, 1, 0, wpk, N, 9 * C, out, N)
+elif kind == "wgrad":
+    dw = torch.zeros(N, 9 * C, device="cuda")
+    f = lambda: ops.conv_wgrad(x, C, B, H, W, C, dy, N, H, W, N, 3, 3, 1, 1, 1, 1, 1, 1, dw)
+elif kind == "wgrad_patch":
+    dw = torch.zeros(N, 9 * C, device="cuda")
+    f = lambda: ops.conv3x3_wgrad_patch(x, C, B, H, W, C, dy, N, N, dw)
+for _ in range(3):
+    f()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(5):
+    f()
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 5
+print("%s B=%d H=%d W=%d C=%d N=%d: %.3f ms  %.1f TFLOP/s" % (kind, B, H, W, C, N, ms, 2.0 * B * H * W * C * N * 9 / ms / 1e9))

@@ -127,3 +127,44 @@ def test_channel_slices_with_leading_dimension():
     ref = F.conv1d(src.float().permute(0, 2, 1), w.to(torch.bfloat16).float()[:, :, 0], padding=3, dilation=3)
     _check(out[:, :, 64:128].float().permute(0, 2, 1), ref, "slice conv")
     assert (out[:, :, :64] == 0).all() and (out[:, :, 128:] == 0).all()
+
+
+PATCH_CASES = {
+    # name: B, H, W, Cin, Cout
+    "l1_64_64": (2, 18, 750, 64, 64),
+    "l1_16_64": (2, 18, 750, 16, 64),
+    "l2_128_128": (2, 9, 375, 128, 128),
+    "odd_rows_ragged_width": (3, 5, 131, 64, 128),
+    "single_row_narrow": (2, 1, 40, 32, 16),
+    "wide_n256": (1, 4, 260, 64, 256),
+}
+
+
+@pytest.mark.parametrize("name", list(PATCH_CASES))
+def test_patch_conv3x3_fprop_and_dgrad(name):
+    """csrc/conv_patch.cu (shared-memory resident patch, shifted descriptor windows) vs torch fp32 conv."""
+    from asvspoof2021_air_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    B, H, W, Cin, Cout = PATCH_CASES[name]
+    g = torch.Generator(device="cpu").manual_seed(11)
+    x = torch.randn(B, Cin, H, W, generator=g).cuda().to(torch.bfloat16)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5).cuda()
+    dy = torch.randn(B, Cout, H, W, generator=g).cuda().to(torch.bfloat16)
+    res = torch.randn(B, H, W, Cout, generator=g).cuda().to(torch.bfloat16)
+    wq = w.to(torch.bfloat16).float()
+    wg = w.permute(0, 2, 3, 1).contiguous()
+    assert ops.patch_supported(Cin, Cout, H, W) and ops.patch_supported(Cout, Cin, H, W)
+    wpk = torch.empty(9 * Cin * Cout, device="cuda", dtype=torch.bfloat16)
+    ops.pack3x3(wg, Cin, Cout, 0, wpk)
+    out = torch.full((B, H, W, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.conv3x3_patch(x.permute(0, 2, 3, 1).contiguous(), Cin, B, H, W, Cin, wpk, Cout, out, Cout, res, Cout, True)
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv2d(x.float(), wq, padding=1) + res.float().permute(0, 3, 1, 2))
+    _check(out.float().permute(0, 3, 1, 2), ref, name + " patch fprop")
+    wpk_d = torch.empty(9 * Cin * Cout, device="cuda", dtype=torch.bfloat16)
+    ops.pack3x3(wg, Cout, Cin, 1, wpk_d)
+    dx = torch.full((B, H, W, Cin), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.conv3x3_patch(dy.permute(0, 2, 3, 1).contiguous(), Cout, B, H, W, Cout, wpk_d, Cin, dx, Cin, None, 0, False, 1)
+    torch.cuda.synchronize()
+    refd = torch.nn.grad.conv2d_input((B, Cin, H, W), wq, dy.float(), padding=1)
+    _check(dx.float().permute(0, 3, 1, 2), refd, name + " patch dgrad")
