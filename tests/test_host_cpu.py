@@ -166,7 +166,7 @@ _WORKER = textwrap.dedent('''
     lo, hi = parallel.shard_range(7, rank, world)
     t = torch.tensor([hi - lo], dtype=torch.float32); dist.all_reduce(t); assert int(t) == 7
     dist.destroy_process_group()
-    print("rank", rank, "ok")
+    sys.stdout.write("rank %%d ok\\n" %% rank); sys.stdout.flush()
 ''')
 
 
@@ -178,4 +178,4 @@ def test_gradient_reducer_gloo_world_size_2(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
+    assert r.stdout.count(" ok") == 2 and "rank 0" in r.stdout and "rank 1" in r.stdout, r.stdout
