@@ -20,6 +20,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// one lane of the (converged) warp; the others get false
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -63,6 +70,16 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// Tiled TMA load of a 4-D box (SASS UTMALDG): out-of-bounds elements (negative coordinates included) are zero
+// filled, which is exactly the zero padding of the convolution.  `tmap` lives in kernel parameter space.
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -115,6 +132,27 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= static_cast<uint64_t>(1) << 46;
   return d;
+}
+// Swizzled shared-memory matrix descriptor (layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B).
+// The operand image is "rows of row_bytes" (row_bytes = the swizzle span, 128 / 64 / 32 B) exactly as a TMA box with
+// the matching swizzle writes it; the XOR pattern is a function of the absolute shared-memory address, so a window
+// that starts r rows further down the image is simply start address + r * row_bytes.
+//   K-major : rows = M/N index, a row holds the K elements; sbo = 8 * row_bytes (next 8-row group); lbo unused
+//   MN-major: rows = K index, a row holds 64/32/16 M/N elements; sbo = 8 * row_bytes (next 8 K rows),
+//             lbo = byte distance to the next group of M/N elements (ANY multiple of 16 B: a second image, or the
+//             same image shifted by some rows)
+__device__ __forceinline__ uint64_t smem_desc_sw(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(layout & 7) << 61;
+  return d;
+}
+// byte offset -> swizzled byte offset inside an image whose base is 1024-byte aligned (mask 7 / 3 / 1 for 128 / 64 / 32 B)
+__host__ __device__ __forceinline__ uint32_t swizzle_offset(uint32_t off, uint32_t mask) {
+  return off ^ (((off >> 7) & mask) << 4);
 }
 // kind::f16 instruction descriptor: bf16 A/B, fp32 accumulate, M x N tile, K = 16 per instruction
 __host__ __device__ __forceinline__ uint32_t instr_desc_bf16(int M, int N, int a_mn_major, int b_mn_major) {

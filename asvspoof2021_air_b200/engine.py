@@ -96,7 +96,9 @@ class ConvLayer:
         # 3x3 / stride 1 / pad 1 layers may run on the patch-resident kernel (chosen per call from the image size)
         self.patch_ok = ((kh, kw, sh, sw, ph, pw, dh, dw) == (3, 3, 1, 1, 1, 1, 1, 1) and not bias and self._wtmp is None
                          and ops.patch_supported(cin, cout, 1, 1) and ops.patch_supported(cout, cin, 1, 1)
-                         and cin <= 128 and cout <= 128)
+                         and cin <= 256 and cout <= 256)
+        self.wpatch_ok = ((kh, kw, sh, sw, ph, pw, dh, dw) == (3, 3, 1, 1, 1, 1, 1, 1) and self._wtmp is None
+                          and ops.wgrad_patch_supported(cin, cout))
         self.wpk3 = torch.empty(9 * cin * cout, device=dev, dtype=BF16) if self.patch_ok else None
         self.wpk3_d = torch.empty(9 * cin * cout, device=dev, dtype=BF16) if (self.patch_ok and need_dgrad) else None
 
@@ -105,7 +107,7 @@ class ConvLayer:
         return (W / (-(-W // 128) * 128)) * (H / (-(-H // 2) * 2))
 
     def use_patch(self, H, W):
-        return self.patch_ok and self._patch_efficiency(H, W) >= 0.8
+        return self.patch_ok and self._patch_efficiency(H, W) >= 0.6
 
     def out_hw(self, H, W):
         return (ops.conv_out_size(H, self.kh, self.sh, self.ph, self.dh),
@@ -153,6 +155,9 @@ class ConvLayer:
 
     def wgrad(self, x, x_ld, B, H, W, dy, dy_ld):
         Ho, Wo = self.out_hw(H, W)
+        if self.wpatch_ok and self._patch_efficiency(H, W) >= 0.5:
+            ops.conv3x3_wgrad_patch(x, x_ld, B, H, W, self.cin, dy, dy_ld, self.cout, self.store.grad(self.name + ".weight"))
+            return
         if self._wtmp is not None:
             g = self._gtmp if hasattr(self, "_gtmp") else None
             if g is None:

@@ -75,6 +75,18 @@ def conv3x3_patch(a, a_ld, B, H, W, C, wpk, N, out, out_ld, res=None, res_ld=0, 
     return out
 
 
+def wgrad_patch_supported(C, N):
+    return bool(_lib.lib().air_conv3x3_wgrad_patch_supported(int(C), int(N)))
+
+
+def conv3x3_wgrad_patch(x, x_ld, B, H, W, C, dy, dy_ld, N, dw_out, dw_ld=None):
+    """dw_out: fp32 [N][9*C] (GEMM layout [Cout][tap][Cin]) accumulated in place (caller zeroes)."""
+    _lib.check(_lib.lib().air_conv3x3_wgrad_patch_bf16(
+        _lib.ptr(x), _lib.LL(x_ld), B, H, W, C, _lib.ptr(dy), _lib.LL(dy_ld), N, _lib.ptr(dw_out),
+        _lib.LL(9 * C if dw_ld is None else dw_ld), num_sms(), _lib.stream_ptr()), "air_conv3x3_wgrad_patch_bf16")
+    return dw_out
+
+
 def conv_out_size(n, k, s, p, d):
     return (n + 2 * p - d * (k - 1) - 1) // s + 1
 
@@ -388,3 +400,4 @@ ctx_bwd_mask = _timed(ctx_bwd_mask, "asp_pool")
 pack3x3 = _timed(pack3x3, "pack_weights")
 conv3x3_patch = _timed(conv3x3_patch, lambda a: "conv_dgrad" if (len(a) > 13 and a[13] == 1) else "conv_fprop",
                        lambda a: 2.0 * a[2] * a[3] * a[4] * a[5] * a[7] * 9)
+conv3x3_wgrad_patch = _timed(conv3x3_wgrad_patch, "conv_wgrad", lambda a: 2.0 * a[2] * a[3] * a[4] * a[5] * a[8] * 9)

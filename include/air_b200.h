@@ -94,11 +94,12 @@ int air_conv_gemm_bf16_ex(const void* a, long long a_ld, int B, int H, int W, in
                           const float* bias, int bias_rows, const void* res, long long res_ld, int relu,
                           void* out2, long long out2_ld, int num_sms, int flags, air_stream_t stream);
 
-/* 3x3 / stride 1 / pad 1 convolution with a shared-memory resident input patch (csrc/conv_patch.cu): the nine taps
- * are shifted descriptor windows of one (2+2) x (128+2) pixel patch, so every activation crosses L2 -> SM about
- * twice instead of nine times.  Used for the wide-image layers of the ResNet (resnet.py:56-60, layer1 / layer2),
- * forward (mode-0 weights) and data gradient (mode-1 weights: flipped taps, swapped channels).
- *   a (B,H,W,C) channels-last bf16, out / res (B,H,W,N); C % 16 == 0 (C <= 64 or C % 64 == 0); N % 16 == 0, N <= 256.
+/* 3x3 / stride 1 / pad 1 convolution with a shared-memory resident input patch (csrc/conv_patch.cu): one TMA box
+ * load brings a (2+2) x (128+2) pixel patch (zero padding = TMA out-of-bounds fill) and the nine taps are shifted
+ * UMMA descriptor windows of it, so every activation crosses L2 -> SM about twice instead of nine times.  Used for
+ * the ResNet 3x3 layers (resnet.py:56-60), forward (mode-0 weights) and data gradient (mode-1 weights: flipped
+ * taps, swapped channels).
+ *   a (B,H,W,C) channels-last bf16, out / res (B,H,W,N); C in {16, 32} or C % 64 == 0; N % 16 == 0, N <= 256.
  *   w for air_conv3x3_pack_weights: fp32 GEMM layout [Cout][3][3][Cin]; mode 0: (C, N) = (Cin, Cout),
  *   mode 1: (C, N) = (Cout, Cin); dst holds 9*C*N bf16. */
 int air_conv3x3_patch_supported(int C, int N, int H, int W);
@@ -106,6 +107,14 @@ int air_conv3x3_pack_weights(const float* w, void* dst, int C, int N, int mode, 
 int air_conv3x3_patch_bf16(const void* a, long long a_ld, int B, int H, int W, int C,
                            const void* wpk, int N, void* out, long long out_ld,
                            const void* res, long long res_ld, int relu, int num_sms, air_stream_t stream);
+
+/* Weight gradient of the same 3x3 / stride 1 / pad 1 layers from shared-memory resident patches
+ * (csrc/conv_wgrad_patch.cu): dW[co][i][j][ci] += sum_{b,h,w} x[b,h+i-1,w+j-1,ci] * dy[b,h,w,co], accumulated with fp32
+ * atomics into the caller-zeroed dw_out ([Cout][dw_ld >= 9*Cin] fp32, GEMM layout).  C % 64 == 0, N % 64 == 0. */
+int air_conv3x3_wgrad_patch_supported(int C, int N);
+int air_conv3x3_wgrad_patch_bf16(const void* x, long long x_ld, int B, int H, int W, int C,
+                                 const void* dy, long long dy_ld, int N,
+                                 float* dw_out, long long dw_ld, int num_sms, air_stream_t stream);
 
 /* Weight gradient (cuDNN wgrad in the reference's autograd): dW[n][kx] += sum_m dy[m][n] *
  * im2col(x)[m][kx], kx = (tap, ci), accumulated with fp32 atomics into the caller-zeroed

@@ -24,14 +24,19 @@ elif kind == "wgrad":
 elif kind == "wgrad_patch":
     dw = torch.zeros(N, 9 * C, device="cuda")
     f = lambda: ops.conv3x3_wgrad_patch(x, C, B, H, W, C, dy, N, N, dw)
+import time
 for _ in range(3):
     f()
 torch.cuda.synchronize()
+NIT = 20
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+torch.cuda._sleep(20_000_000)          # ~10 ms of GPU busy time: lets the host run ahead so that launches are back to back
+t0 = time.perf_counter()
 e0.record()
-for _ in range(5):
+for _ in range(NIT):
     f()
 e1.record()
+host_us = (time.perf_counter() - t0) / NIT * 1e6
 torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / 5
-print("%s B=%d H=%d W=%d C=%d N=%d: %.3f ms  %.1f TFLOP/s" % (kind, B, H, W, C, N, ms, 2.0 * B * H * W * C * N * 9 / ms / 1e9))
+ms = e0.elapsed_time(e1) / NIT
+print("%s B=%d H=%d W=%d C=%d N=%d: %.3f ms  %.1f TFLOP/s  (host %.0f us/launch)" % (kind, B, H, W, C, N, ms, 2.0 * B * H * W * C * N * 9 / ms / 1e9, host_us))

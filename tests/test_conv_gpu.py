@@ -168,3 +168,35 @@ def test_patch_conv3x3_fprop_and_dgrad(name):
     torch.cuda.synchronize()
     refd = torch.nn.grad.conv2d_input((B, Cin, H, W), wq, dy.float(), padding=1)
     _check(dx.float().permute(0, 3, 1, 2), refd, name + " patch dgrad")
+
+
+WPATCH_CASES = {
+    # name: B, H, W, Cin, Cout
+    "l1_64_64": (2, 18, 750, 64, 64),
+    "l2_128_128": (2, 9, 375, 128, 128),
+    "odd_rows_ragged_width": (3, 5, 131, 64, 128),
+    "single_row_narrow": (2, 1, 40, 128, 64),
+    "l3_256_256": (1, 5, 188, 256, 256),
+}
+
+
+@pytest.mark.parametrize("name", list(WPATCH_CASES))
+def test_patch_conv3x3_wgrad(name):
+    """csrc/conv_wgrad_patch.cu (TMA patches, MN-major shifted windows, tap pairs through LBO) vs torch fp32 wgrad."""
+    from asvspoof2021_air_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    B, H, W, Cin, Cout = WPATCH_CASES[name]
+    g = torch.Generator(device="cpu").manual_seed(13)
+    x = torch.randn(B, Cin, H, W, generator=g).cuda().to(torch.bfloat16)
+    dy = torch.randn(B, Cout, H, W, generator=g).cuda().to(torch.bfloat16)
+    assert ops.wgrad_patch_supported(Cin, Cout)
+    dw = torch.zeros(Cout, 9 * Cin, device="cuda")
+    xc, dyc = x.permute(0, 2, 3, 1).contiguous(), dy.permute(0, 2, 3, 1).contiguous()
+    ops.conv3x3_wgrad_patch(xc, Cin, B, H, W, Cin, dyc, Cout, Cout, dw)
+    ops.conv3x3_wgrad_patch(xc, Cin, B, H, W, Cin, dyc, Cout, Cout, dw)          # accumulates
+    torch.cuda.synchronize()
+    ref = 2 * torch.nn.grad.conv2d_weight(x.float(), (Cout, Cin, 3, 3), dy.float(), padding=1)
+    got = dw.view(Cout, 3, 3, Cin).permute(0, 3, 1, 2)
+    err = (got - ref).norm() / ref.norm()
+    worst = (got - ref).abs().max() / ref.abs().max()
+    assert err < 1e-3 and worst < 2e-3, "%s: normwise %.3g, worst %.3g" % (name, float(err), float(worst))
