@@ -1,23 +1,27 @@
-// 3x3 / stride-1 / pad-1 convolution with a shared-memory resident input patch (TMA + tcgen05 + TMEM).
+// Shifted-window convolution from a shared-memory resident input patch (TMA + tcgen05 + TMEM).
 //
-// The generic implicit-GEMM kernel (conv_gemm.cu) gathers every activation once per tap (9x) through the
-// LSU, which makes the N = 64 / 128 layers of the ResNet (resnet.py:56-60, layer1 / layer2) gather bound.
-// Here a work item is R = 2 output rows x 128 pixels of one image; its (R+2) x 130 pixel input patch
-// (one block of <= 64 channels at a time) is brought into shared memory ONCE by a single TMA box load
-// (out-of-bounds rows / columns are zero filled by the TMA unit = the padding of the convolution) and
-// the nine taps are nine shifted windows of it: the patch image is "one swizzled row per pixel", so moving
-// the UMMA operand by one pixel is +row_bytes on the descriptor start address, by one image row +130 rows.
+// The generic implicit-GEMM kernel (conv_gemm.cu) gathers every activation once per tap (9x for a 3x3) through
+// the LSU.  Here a work item is R = 2 rows x 128 columns of an output pixel grid of one image; the
+// (R+2) x 130 pixel input patch it needs (one block of <= 64 channels at a time) is brought into shared memory
+// ONCE by a single TMA box load (out-of-bounds rows / columns are zero filled by the TMA unit = the zero padding of
+// the convolution) and every tap is a shifted window of it: the patch image is "one swizzled row per pixel", so
+// moving the UMMA A operand by one pixel is +row_bytes on the descriptor start address, by one patch row +130 rows.
 //
-//   out[b, h, w, n] = sum_{i,j,c} a[b, h+i-1, w+j-1, c] * Wp[n][i][j][c]   (+ res) (ReLU)
+//   out[b, oh(g), ow(g'), n] = sum_{t < ntaps} sum_c a[b, g + org_h + dr[t], g' + org_w + dc[t], c] * Wp[slice[t]][n][c]
+//                              (+ res) (ReLU),          oh(g) = g * osh + oph,  ow(g') = g' * osw + opw
 //
-// Forward uses Wp = W; the data gradient of the same layer is the same kernel on dy with the taps
-// flipped and (ci, co) swapped, which is done once in the weight packing (mode 1).
+// With the tap table of a 3x3 / stride 1 / pad 1 layer (org = -1, dr/dc = 0..2, os = 1) this is the forward
+// convolution of resnet.py:56-60 (mode-0 weights) or its data gradient (mode-1 weights: flipped taps, swapped
+// channels).  The data gradient of a STRIDE-2 3x3 layer is four such launches, one per output parity class
+// (oph, opw): each class only sees the 1 / 2 / 2 / 4 taps that are structurally non-zero for it, so no
+// zero-stuffed gather is ever made; a 1x1 layer is the single-tap case.
+//
 // Roles (256 threads): warp 0 issues the patch TMA loads, warp 1 streams pre-swizzled weight slices (one
 // bulk copy per (channel block, tap); all slices stay resident when they fit), warp 2 issues tcgen05.mma
-// (M = 128 pixels, N = Cout, K = 16 per instruction), warps 4-7 drain the double-buffered TMEM accumulators.
-// Persistent grid.
+// (M = 128 pixels, N = output channels, K = 16 per instruction; the whole warp runs the warp-uniform loop so
+// descriptors live in uniform registers, one elected lane issues), warps 4-7 drain the double-buffered TMEM
+// accumulators.  Persistent grid.
 #include <algorithm>
-#include <cstdlib>
 #include "common.cuh"
 #include "tc05.cuh"
 #include "tmap.cuh"
@@ -25,29 +29,64 @@
 namespace air_patch {
 using namespace tc05;
 
-constexpr int TW = 128;                 // output pixels per row segment (UMMA M)
+constexpr int TW = 128;                 // output columns per row segment (UMMA M)
 constexpr int PW = TW + 2;              // patch width
 constexpr int R = 2;                    // output rows per work item
 constexpr int PR = R + 2;               // patch rows
 constexpr int PPIX = PR * PW;           // 520 patch pixels
 constexpr int THREADS = 256;
 constexpr int PSTAGES = 2;
+constexpr int MAX_TAPS = 9;
 
 struct PatchParams {
-  int B, H, W, C;
-  const __nv_bfloat16* wpk; int N;
+  int B, GH, GW;                        // images, output pixel grid enumerated by the items
+  int OH, OW, osh, osw, oph, opw;       // output tensor geometry: grid (g, g') -> pixel (g*osh + oph, g'*osw + opw)
+  int org_h, org_w;                     // patch origin relative to (first grid row, first grid column) of the item
+  int C, N;
+  const __nv_bfloat16* wpk; int wtaps;  // packed weights: [C/CB][wtaps] slices of [N][CB]
   __nv_bfloat16* out; long long out_ld;
   const __nv_bfloat16* res; long long res_ld; int relu;
-  int CB, NCB, WT, HP;                  // channels per block (16 / 32 / 64), #blocks, W tiles, row pairs
+  int CB, NCB, WT, HP;                  // channels per block (16 / 32 / 64), #blocks, column tiles, row pairs
   int row_bytes, layout;                // CB * 2; UMMA layout type (6 / 4 / 2)
   uint32_t pstage_bytes, bslot_bytes, bslot_stride;
   int nb_slots, resident;               // weight ring
   int acc_stages;                       // 1 or 2
-  int dbg;                              // AIR_PATCH_DBG: 1 no stores, 2 no MMAs, 4 no patch loads (timing experiments only)
-  long long items;
+  int ntaps; int tap_off[MAX_TAPS]; int tap_slice[MAX_TAPS];     // window offset in patch pixels, weight slice
+  uint32_t items;
 };
 
-__global__ void __launch_bounds__(THREADS, 1) conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap, const PatchParams p) {
+template <int NC>
+__device__ __forceinline__ void epilogue_chunk(const PatchParams& p, uint32_t taddr, long long pixel, int c0, bool valid) {
+  // NC = 32 or 16 columns: residual loads are issued BEFORE the TMEM load so that their latency overlaps it
+  bf16x8 rv[NC / 8];
+  if (p.res != nullptr && valid) {
+    const bf16x8* rp = reinterpret_cast<const bf16x8*>(p.res + pixel * p.res_ld + c0);
+#pragma unroll
+    for (int i = 0; i < NC / 8; ++i) rv[i] = rp[i];
+  }
+  float v[NC];
+  if (NC == 32) tmem_ld32(taddr + c0, v); else tmem_ld16(taddr + c0, v);
+  if (valid) {
+    if (p.res != nullptr) {
+#pragma unroll
+      for (int i = 0; i < NC / 8; ++i) {
+        float rf[8];
+        unpack8(rv[i], rf);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[i * 8 + e] += rf[e];
+      }
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int i = 0; i < NC; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    bf16x8* op = reinterpret_cast<bf16x8*>(p.out + pixel * p.out_ld + c0);
+#pragma unroll
+    for (int i = 0; i < NC / 8; ++i) op[i] = pack8(v + i * 8);
+  }
+}
+
+__global__ void __launch_bounds__(THREADS, 1) conv_patch_kernel(const __grid_constant__ CUtensorMap tmap, const PatchParams p) {
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;      // swizzle patterns are anchored at 1024 B
@@ -78,19 +117,19 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_patch_kernel(const __grid_
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const int nslices = p.NCB * 9;
+  const int nslices = p.NCB * p.ntaps;
+  const uint32_t WT = p.WT, HP = p.HP;
 
   if (warp == 0) {
     // ===================== patch loads: one TMA box per (item, channel block) =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      const uint32_t items32 = static_cast<uint32_t>(p.items), WT = p.WT, HP = p.HP;
-      for (uint32_t item = blockIdx.x; item < items32; item += gridDim.x) {
+      for (uint32_t item = blockIdx.x; item < p.items; item += gridDim.x) {
         const uint32_t wt = item % WT, r1 = item / WT;            // coordinates are ready BEFORE the slot frees up
-        const int c1 = static_cast<int>(wt) * TW - 1, c2 = static_cast<int>(r1 % HP) * R - 1, c3 = static_cast<int>(r1 / HP);
+        const int c1 = static_cast<int>(wt) * TW + p.org_w, c2 = static_cast<int>(r1 % HP) * R + p.org_h;
+        const int c3 = static_cast<int>(r1 / HP);
         for (int cb = 0; cb < p.NCB; ++cb) {
           mbar_wait(&empty_p[stage], phase ^ 1);
-          if (p.dbg & 4) { mbar_arrive(&full_p[stage]); if (++stage == PSTAGES) { stage = 0; phase ^= 1; } continue; }
           mbar_arrive_expect_tx(&full_p[stage], static_cast<uint32_t>(PPIX) * p.row_bytes);
           tma_load_4d(sP + stage * p.pstage_bytes, &tmap, cb * p.CB, c1, c2, c3, &full_p[stage]);
           if (++stage == PSTAGES) { stage = 0; phase ^= 1; }
@@ -103,36 +142,36 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_patch_kernel(const __grid_
       const long long slice_elems = static_cast<long long>(p.N) * p.CB;
       if (p.resident) {
         for (int s = 0; s < nslices; ++s) {
+          const int cb = s / p.ntaps, t = s - cb * p.ntaps;
           mbar_arrive_expect_tx(&full_b[s], p.bslot_bytes);
-          bulk_g2s(sB + s * p.bslot_stride, p.wpk + s * slice_elems, p.bslot_bytes, &full_b[s]);
+          bulk_g2s(sB + s * p.bslot_stride, p.wpk + (cb * p.wtaps + p.tap_slice[t]) * slice_elems, p.bslot_bytes, &full_b[s]);
         }
       } else {
         uint32_t slot = 0, phase = 0;
-        for (uint32_t item = blockIdx.x; item < static_cast<uint32_t>(p.items); item += gridDim.x) {
+        for (uint32_t item = blockIdx.x; item < p.items; item += gridDim.x) {
           for (int s = 0; s < nslices; ++s) {
+            const int cb = s / p.ntaps, t = s - cb * p.ntaps;
             mbar_wait(&empty_b[slot], phase ^ 1);
             mbar_arrive_expect_tx(&full_b[slot], p.bslot_bytes);
-            bulk_g2s(sB + slot * p.bslot_stride, p.wpk + s * slice_elems, p.bslot_bytes, &full_b[slot]);
+            bulk_g2s(sB + slot * p.bslot_stride, p.wpk + (cb * p.wtaps + p.tap_slice[t]) * slice_elems, p.bslot_bytes, &full_b[slot]);
             if (++slot == static_cast<uint32_t>(p.nb_slots)) { slot = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 2) {
-    // ===================== MMA issuer =====================
-    // The WHOLE warp runs the (warp-uniform) loop so that descriptors live in uniform registers; one elected
-    // lane issues tcgen05.mma / tcgen05.commit.
+    // ===================== MMA issuer (warp-uniform loop, elected lane issues) =====================
     const bool leader = elect_one();
     const uint32_t idesc = instr_desc_bf16(TW, p.N, 0, 0);
     const uint32_t rb16 = static_cast<uint32_t>(p.row_bytes) >> 4;                  // row stride in 16-byte units
+    // descriptor high word: SBO = 8 rows, version 1, swizzle mode
     const uint32_t desc_hi = ((8u * p.row_bytes) >> 4) | (1u << 14) | (static_cast<uint32_t>(p.layout) << 29);
     const int KK = p.CB >> 4;
-    const uint32_t items32 = static_cast<uint32_t>(p.items);
     uint32_t pstage = 0, pphase = 0, slot = 0, bphase = 0;
     uint32_t it = 0;
-    for (uint32_t item = blockIdx.x; item < items32; item += gridDim.x, ++it) {
-      const uint32_t hp = (item / p.WT) % p.HP;
-      const int rows = min(R, p.H - static_cast<int>(hp) * R);
+    for (uint32_t item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      const uint32_t hp = (item / WT) % HP;
+      const int rows = min(R, p.GH - static_cast<int>(hp) * R);
       const uint32_t acc = p.acc_stages == 2 ? (it & 1) : 0;
       const uint32_t acc_phase = p.acc_stages == 2 ? ((it >> 1) & 1) : (it & 1);
       mbar_wait(&tempty[acc], acc_phase ^ 1);
@@ -142,12 +181,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_patch_kernel(const __grid_
         mbar_wait(&full_p[pstage], pphase);
         fence_after_sync();
         const uint32_t a_lo = (((sP + pstage * p.pstage_bytes) >> 4) & 0x3FFF) | (1u << 16);
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          const int ti = tap / 3, tj = tap - ti * 3;
+        for (int t = 0; t < p.ntaps; ++t) {
           uint32_t b0;
           if (p.resident) {
-            const int s = cb * 9 + tap;
+            const int s = cb * p.ntaps + t;
             if (it == 0) { mbar_wait(&full_b[s], 0); fence_after_sync(); }
             b0 = sB + s * p.bslot_stride;
           } else {
@@ -156,14 +193,15 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_patch_kernel(const __grid_
             b0 = sB + slot * p.bslot_stride;
           }
           const uint32_t b_lo = ((b0 >> 4) & 0x3FFF) | (1u << 16);
+          const uint32_t a_tap = a_lo + static_cast<uint32_t>(p.tap_off[t]) * rb16;
 #pragma unroll
           for (int j = 0; j < R; ++j) {
             if (j < rows) {
-              const uint32_t arow = a_lo + static_cast<uint32_t>((j + ti) * PW + tj) * rb16;
+              const uint32_t arow = a_tap + static_cast<uint32_t>(j * PW) * rb16;
               for (int kk = 0; kk < KK; ++kk) {
                 const uint64_t ad = (static_cast<uint64_t>(desc_hi) << 32) | (arow + kk * 2);
                 const uint64_t bd = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + kk * 2);
-                if (leader && !(p.dbg & 2)) mma_bf16(d0 + j * p.N, ad, bd, idesc, (cb | tap | kk) != 0);
+                if (leader) mma_bf16(d0 + j * p.N, ad, bd, idesc, (cb | t | kk) != 0);
               }
             }
           }
@@ -182,41 +220,27 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_patch_kernel(const __grid_
     // ===================== epilogue =====================
     const int q = warp & 3;
     const int m = q * 32 + lane;
-    int it = 0;
-    const uint32_t items32 = static_cast<uint32_t>(p.items);
-    for (uint32_t item = blockIdx.x; item < items32; item += gridDim.x, ++it) {
-      const int wt = static_cast<int>(item % static_cast<uint32_t>(p.WT));
-      const uint32_t r1 = item / static_cast<uint32_t>(p.WT);
-      const int hp = static_cast<int>(r1 % static_cast<uint32_t>(p.HP)), b = static_cast<int>(r1 / static_cast<uint32_t>(p.HP));
-      const int rows = min(R, p.H - hp * R);
-      const int acc = p.acc_stages == 2 ? (it & 1) : 0;
+    uint32_t it = 0;
+    for (uint32_t item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      const int wt = static_cast<int>(item % WT);
+      const uint32_t r1 = item / WT;
+      const int hp = static_cast<int>(r1 % HP), b = static_cast<int>(r1 / HP);
+      const int rows = min(R, p.GH - hp * R);
+      const uint32_t acc = p.acc_stages == 2 ? (it & 1) : 0;
       const uint32_t acc_phase = p.acc_stages == 2 ? ((it >> 1) & 1) : (it & 1);
+      const int g = wt * TW + m;
+      const int ow = g * p.osw + p.opw;
+      const bool col_ok = g < p.GW && ow < p.OW;
       mbar_wait(&tfull[acc], acc_phase);
       fence_after_sync();
-      const int w = wt * TW + m;
-      for (int j = 0; j < ((p.dbg & 16) ? 0 : rows); ++j) {
-        const long long pixel = (static_cast<long long>(b) * p.H + hp * R + j) * p.W + w;
+      for (int j = 0; j < rows; ++j) {
+        const int oh = (hp * R + j) * p.osh + p.oph;
+        const bool valid = col_ok && oh < p.OH;
+        const long long pixel = (static_cast<long long>(b) * p.OH + oh) * p.OW + ow;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (acc * R + j) * p.N;
-        for (int c0 = 0; c0 < p.N; c0 += 16) {
-          float v[16];
-          if (!(p.dbg & 8)) tmem_ld16(taddr + c0, v);
-          if (w < p.W && !(p.dbg & 1)) {
-            if (p.res) {
-              const bf16x8* rp = reinterpret_cast<const bf16x8*>(p.res + pixel * p.res_ld + c0);
-              float rf[16];
-              unpack8(rp[0], rf); unpack8(rp[1], rf + 8);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] += rf[i];
-            }
-            if (p.relu) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-            }
-            bf16x8* op = reinterpret_cast<bf16x8*>(p.out + pixel * p.out_ld + c0);
-            op[0] = pack8(v);
-            op[1] = pack8(v + 8);
-          }
-        }
+        int c0 = 0;
+        for (; c0 + 32 <= p.N; c0 += 32) epilogue_chunk<32>(p, taddr, pixel, c0, valid);
+        if (c0 < p.N) epilogue_chunk<16>(p, taddr, pixel, c0, valid);
       }
       fence_before_sync();
       mbar_arrive(&tempty[acc]);
@@ -231,23 +255,23 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_patch_kernel(const __grid_
 // Weight packing for the patch kernel: one pre-swizzled [N rows][CB channels] K-major image per (cb, tap), exactly
 // the bytes a TMA load with the matching swizzle would have produced, so one bulk copy per slice suffices:
 //   element (n, k) of slice (cb, tap) at byte  swizzle(n * CB*2 + (k / 8) * 16) + (k % 8) * 2
-//   mode 0 (fprop): w is [N = Cout][9][C = Cin];   value = w[n][tap][ch]
-//   mode 1 (dgrad): w is [C = Cout][9][N = Cin];   value = w[ch][8 - tap][n]   (flipped taps, swapped channels)
-__global__ void pack3x3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int C, int N, int CB, int mode) {
-  const long long total = 9LL * C * N;
+//   mode 0 (fprop): w is [N = Cout][taps][C = Cin];   value = w[n][tap][ch]
+//   mode 1 (dgrad): w is [C = Cout][taps][N = Cin];   value = w[ch][taps - 1 - tap][n]   (flipped taps, swapped channels)
+__global__ void pack_patch_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int C, int N, int CB, int taps, int mode) {
+  const long long total = static_cast<long long>(taps) * C * N;
   const uint32_t mask = CB == 64 ? 7u : (CB == 32 ? 3u : 1u);
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int k = static_cast<int>(i % CB);
     long long t = i / CB;
     const int n = static_cast<int>(t % N); t /= N;
-    const int tap = static_cast<int>(t % 9);
-    const int cb = static_cast<int>(t / 9);
+    const int tap = static_cast<int>(t % taps);
+    const int cb = static_cast<int>(t / taps);
     const int ch = cb * CB + k;
-    const float v = mode == 0 ? w[(static_cast<long long>(n) * 9 + tap) * C + ch]
-                              : w[(static_cast<long long>(ch) * 9 + (8 - tap)) * N + n];
+    const float v = mode == 0 ? w[(static_cast<long long>(n) * taps + tap) * C + ch]
+                              : w[(static_cast<long long>(ch) * taps + (taps - 1 - tap)) * N + n];
     const uint32_t off = swizzle_offset(static_cast<uint32_t>(n) * CB * 2 + (k >> 3) * 16, mask) + (k & 7) * 2;
-    dst[(static_cast<long long>(cb) * 9 + tap) * N * CB + (off >> 1)] = f2bf(v);
+    dst[(static_cast<long long>(cb) * taps + tap) * N * CB + (off >> 1)] = f2bf(v);
   }
 }
 
@@ -257,7 +281,7 @@ using namespace air_patch;
 
 static int patch_cb(int C) { return C <= 64 ? C : 64; }
 
-// 1 when (C, N, W) can run on the patch kernel
+// 1 when (C, N) can run on the patch kernel
 extern "C" int air_conv3x3_patch_supported(int C, int N, int H, int W) {
   if (!(C == 16 || C == 32 || (C >= 64 && C % 64 == 0))) return 0;
   if (N % 16 != 0 || N > 256 || N < 16) return 0;
@@ -266,54 +290,122 @@ extern "C" int air_conv3x3_patch_supported(int C, int N, int H, int W) {
   return 1;
 }
 
-extern "C" int air_conv3x3_pack_weights(const float* w, void* dst, int C, int N, int mode, cudaStream_t stream) {
-  if (!w || !dst || !air_conv3x3_patch_supported(C, N, 1, 1) || (mode != 0 && mode != 1)) return AIR_ERR_ARG;
-  const long long total = 9LL * C * N;
-  pack3x3_kernel<<<static_cast<int>(std::min<long long>((total + 255) / 256, 2048)), 256, 0, stream>>>(
-      w, reinterpret_cast<__nv_bfloat16*>(dst), C, N, patch_cb(C), mode);
+// taps = 9 (3x3) or 1 (1x1); dst holds taps*C*N bf16
+extern "C" int air_conv_patch_pack_weights(const float* w, void* dst, int C, int N, int taps, int mode, cudaStream_t stream) {
+  if (!w || !dst || !air_conv3x3_patch_supported(C, N, 1, 1) || (mode != 0 && mode != 1) || taps < 1 || taps > MAX_TAPS) return AIR_ERR_ARG;
+  const long long total = static_cast<long long>(taps) * C * N;
+  pack_patch_kernel<<<static_cast<int>(std::min<long long>((total + 255) / 256, 2048)), 256, 0, stream>>>(
+      w, reinterpret_cast<__nv_bfloat16*>(dst), C, N, patch_cb(C), taps, mode);
   return air_launch_status();
 }
 
-extern "C" int air_conv3x3_patch_bf16(const void* a, long long a_ld, int B, int H, int W, int C,
-                                      const void* wpk, int N, void* out, long long out_ld,
-                                      const void* res, long long res_ld, int relu, int num_sms, cudaStream_t stream) {
-  if (!a || !wpk || !out || B <= 0) return AIR_ERR_ARG;
-  if (!air_conv3x3_patch_supported(C, N, H, W)) return AIR_ERR_UNSUPPORTED;
+extern "C" int air_conv3x3_pack_weights(const float* w, void* dst, int C, int N, int mode, cudaStream_t stream) {
+  return air_conv_patch_pack_weights(w, dst, C, N, 9, mode, stream);
+}
+
+// The general entry point: explicit tap table and output pixel mapping (see the formula at the top of this file).
+//   a: (B, Hin, Win, C) channels-last bf16;  out / res: (B, OH, OW, N);  item grid GH x GW;
+//   tap t reads the window that starts at patch pixel (tap_dr[t], tap_dc[t]) (0 <= dr, dc <= 2) and uses weight slice
+//   tap_slice[t] (< wtaps) of every channel block.
+extern "C" int air_conv_patch_taps_bf16(const void* a, long long a_ld, int B, int Hin, int Win, int C,
+                                        const void* wpk, int wtaps, int N, void* out, long long out_ld, int OH, int OW,
+                                        const void* res, long long res_ld, int relu,
+                                        int GH, int GW, int org_h, int org_w, int osh, int osw, int oph, int opw,
+                                        int ntaps, const int* tap_dr, const int* tap_dc, const int* tap_slice,
+                                        int num_sms, cudaStream_t stream) {
+  if (!a || !wpk || !out || B <= 0 || !tap_dr || !tap_dc || !tap_slice) return AIR_ERR_ARG;
+  if (ntaps < 1 || ntaps > MAX_TAPS || wtaps < 1 || GH < 1 || GW < 1 || osh < 1 || osw < 1 || oph < 0 || opw < 0) return AIR_ERR_ARG;
+  if (!air_conv3x3_patch_supported(C, N, Hin, Win)) return AIR_ERR_UNSUPPORTED;
   if (a_ld % 8 != 0 || out_ld % 8 != 0 || (res && res_ld % 8 != 0)) return AIR_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(wpk) |
        reinterpret_cast<uintptr_t>(res)) & 15) return AIR_ERR_UNSUPPORTED;
   PatchParams p;
-  p.B = B; p.H = H; p.W = W; p.C = C;
-  p.wpk = reinterpret_cast<const __nv_bfloat16*>(wpk); p.N = N;
+  p.B = B; p.GH = GH; p.GW = GW; p.OH = OH; p.OW = OW; p.osh = osh; p.osw = osw; p.oph = oph; p.opw = opw;
+  p.org_h = org_h; p.org_w = org_w; p.C = C; p.N = N;
+  p.wpk = reinterpret_cast<const __nv_bfloat16*>(wpk); p.wtaps = wtaps;
   p.out = reinterpret_cast<__nv_bfloat16*>(out); p.out_ld = out_ld;
   p.res = reinterpret_cast<const __nv_bfloat16*>(res); p.res_ld = res_ld; p.relu = relu;
-  p.CB = patch_cb(C); p.NCB = C / p.CB; p.WT = (W + TW - 1) / TW; p.HP = (H + R - 1) / R;
+  p.ntaps = ntaps;
+  for (int t = 0; t < MAX_TAPS; ++t) { p.tap_off[t] = 0; p.tap_slice[t] = 0; }
+  for (int t = 0; t < ntaps; ++t) {
+    if (tap_dr[t] < 0 || tap_dr[t] > PR - R || tap_dc[t] < 0 || tap_dc[t] > PW - TW || tap_slice[t] < 0 || tap_slice[t] >= wtaps)
+      return AIR_ERR_ARG;
+    p.tap_off[t] = tap_dr[t] * PW + tap_dc[t];
+    p.tap_slice[t] = tap_slice[t];
+  }
+  p.CB = patch_cb(C); p.NCB = C / p.CB; p.WT = (GW + TW - 1) / TW; p.HP = (GH + R - 1) / R;
   p.row_bytes = p.CB * 2; p.layout = p.CB == 64 ? 2 : (p.CB == 32 ? 4 : 6);
-  p.items = static_cast<long long>(B) * p.HP * p.WT;
+  const long long items = static_cast<long long>(B) * p.HP * p.WT;
+  if (items > 0x7fffffffLL) return AIR_ERR_UNSUPPORTED;
+  p.items = static_cast<uint32_t>(items);
   p.acc_stages = (2 * R * N <= 512) ? 2 : 1;
-  { const char* e = getenv("AIR_PATCH_DBG"); p.dbg = e ? atoi(e) : 0; }
   p.pstage_bytes = static_cast<uint32_t>((PPIX * p.row_bytes + 1023) / 1024 * 1024);
   p.bslot_bytes = static_cast<uint32_t>(N * p.row_bytes);
   p.bslot_stride = (p.bslot_bytes + 1023u) / 1024u * 1024u;
   const int budget = 225 * 1024 - PSTAGES * static_cast<int>(p.pstage_bytes) - 2048;
   int slots = budget / static_cast<int>(p.bslot_stride);
-  const int nslices = p.NCB * 9;
+  const int nslices = p.NCB * ntaps;
   if (slots >= nslices) { slots = nslices; p.resident = 1; } else { p.resident = 0; if (slots > 12) slots = 12; }
-  if (slots < 2) return AIR_ERR_UNSUPPORTED;
+  if (slots < 2 && nslices > 1) return AIR_ERR_UNSUPPORTED;
   p.nb_slots = slots;
   const size_t smem = 1024 + static_cast<size_t>(PSTAGES) * p.pstage_bytes + static_cast<size_t>(slots) * p.bslot_stride +
                       (2 * PSTAGES + 2 * slots + 4) * 8 + 16;
   CUtensorMap tm;
-  const int tr = air_tmap::make_act_tmap(&tm, a, a_ld, B, H, W, C, p.CB, PW, PR, p.row_bytes);
+  const int tr = air_tmap::make_act_tmap(&tm, a, a_ld, B, Hin, Win, C, p.CB, PW, PR, p.row_bytes);
   if (tr != 0) return tr < 0 ? AIR_ERR_UNSUPPORTED : 10000 + tr;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_done = true;
   }
   if (num_sms <= 0) num_sms = 148;
-  const int grid = static_cast<int>(std::min<long long>(p.items, num_sms));
-  conv3x3_patch_kernel<<<grid, THREADS, smem, stream>>>(tm, p);
+  const int grid = static_cast<int>(std::min<long long>(items, num_sms));
+  conv_patch_kernel<<<grid, THREADS, smem, stream>>>(tm, p);
   return air_launch_status();
+}
+
+// 3x3 / stride 1 / pad 1 (forward with mode-0 weights, data gradient with mode-1 weights)
+extern "C" int air_conv3x3_patch_bf16(const void* a, long long a_ld, int B, int H, int W, int C,
+                                      const void* wpk, int N, void* out, long long out_ld,
+                                      const void* res, long long res_ld, int relu, int num_sms, cudaStream_t stream) {
+  int dr[9], dc[9], sl[9];
+  for (int t = 0; t < 9; ++t) { dr[t] = t / 3; dc[t] = t % 3; sl[t] = t; }
+  return air_conv_patch_taps_bf16(a, a_ld, B, H, W, C, wpk, 9, N, out, out_ld, H, W, res, res_ld, relu,
+                                  H, W, -1, -1, 1, 1, 0, 0, 9, dr, dc, sl, num_sms, stream);
+}
+
+// Data gradient of a k x k (k = 3, pad 1 or k = 1, pad 0) / STRIDE-2 convolution: dy (B, Ho, Wo, Cout) -> dx (B, H, W, Cin),
+// one launch per output parity class with only its structurally non-zero taps.  wpk: mode-1 packed weights (k*k taps).
+// k = 3: every pixel of dx is written (+ res).  k = 1: only the even-even pixels are written (dx = res + contribution there);
+// the other pixels of dx are left untouched, so pass res = dx to accumulate into an existing gradient.
+extern "C" int air_conv_s2_dgrad_patch_bf16(const void* dy, long long dy_ld, int B, int Ho, int Wo, int Cout,
+                                            const void* wpk, int k, int Cin, void* dx, long long dx_ld, int H, int W,
+                                            const void* res, long long res_ld, int num_sms, cudaStream_t stream) {
+  if (k != 3 && k != 1) return AIR_ERR_UNSUPPORTED;
+  for (int ph = 0; ph < 2; ++ph) {
+    for (int pw = 0; pw < 2; ++pw) {
+      if (k == 1 && (ph | pw)) continue;
+      const int GH = (H - ph + 1) / 2, GW = (W - pw + 1) / 2;
+      if (GH < 1 || GW < 1) continue;
+      int dr[9], dc[9], sl[9], nt = 0;
+      if (k == 1) { dr[0] = 0; dc[0] = 0; sl[0] = 0; nt = 1; }
+      else {
+        // forward: y[ho][wo] += x[2ho + i - 1][2wo + j - 1] * W[i][j]  =>  dx[h][w] += dy[(h+1-i)/2][(w+1-j)/2] * W[i][j]
+        for (int i = 0; i < 3; ++i) {
+          if ((ph + 1 - i) & 1) continue;
+          for (int j = 0; j < 3; ++j) {
+            if ((pw + 1 - j) & 1) continue;
+            dr[nt] = (ph + 1 - i) / 2; dc[nt] = (pw + 1 - j) / 2;
+            sl[nt] = 8 - (3 * i + j);                       // mode-1 packing stores original tap t at slice 8 - t
+            ++nt;
+          }
+        }
+      }
+      const int st = air_conv_patch_taps_bf16(dy, dy_ld, B, Ho, Wo, Cout, wpk, k * k, Cin, dx, dx_ld, H, W, res, res_ld, 0,
+                                              GH, GW, 0, 0, 2, 2, ph, pw, nt, dr, dc, sl, num_sms, stream);
+      if (st != 0) return st;
+    }
+  }
+  return AIR_OK;
 }

@@ -94,13 +94,23 @@ class ConvLayer:
         self.wpk_d = torch.empty(ops.packed_elems(self.cin_g, self.taps * cout), device=dev, dtype=BF16) if need_dgrad else None
         self._wtmp = torch.zeros(cout, self.taps, self.cin_g, device=dev) if self.cin_g != cin else None
         # 3x3 / stride 1 / pad 1 layers may run on the patch-resident kernel (chosen per call from the image size)
-        self.patch_ok = ((kh, kw, sh, sw, ph, pw, dh, dw) == (3, 3, 1, 1, 1, 1, 1, 1) and not bias and self._wtmp is None
+        geom = (kh, kw, sh, sw, ph, pw, dh, dw)
+        plain = not bias and self._wtmp is None
+        self.patch_ok = (geom == (3, 3, 1, 1, 1, 1, 1, 1) and plain
                          and ops.patch_supported(cin, cout, 1, 1) and ops.patch_supported(cout, cin, 1, 1)
                          and cin <= 256 and cout <= 256)
-        self.wpatch_ok = ((kh, kw, sh, sw, ph, pw, dh, dw) == (3, 3, 1, 1, 1, 1, 1, 1) and self._wtmp is None
+        self.wpatch_ok = (geom == (3, 3, 1, 1, 1, 1, 1, 1) and self._wtmp is None
                           and ops.wgrad_patch_supported(cin, cout))
-        self.wpk3 = torch.empty(9 * cin * cout, device=dev, dtype=BF16) if self.patch_ok else None
-        self.wpk3_d = torch.empty(9 * cin * cout, device=dev, dtype=BF16) if (self.patch_ok and need_dgrad) else None
+        # stride-2 layers: data gradient by output parity classes on the patch kernel (3x3 pad 1, or the 1x1 shortcut)
+        self.s2_dgrad_ok = (need_dgrad and plain and geom in ((3, 3, 2, 2, 1, 1, 1, 1), (1, 1, 2, 2, 0, 0, 1, 1))
+                            and ops.patch_supported(cout, cin, 1, 1))
+        # 1x1 / stride-1 layers: a GEMM over pixels through the same TMA kernel (single tap)
+        self.p1x1_ok = (geom == (1, 1, 1, 1, 0, 0, 1, 1) and plain and ops.patch_supported(cin, cout, 1, 1)
+                        and (not need_dgrad or ops.patch_supported(cout, cin, 1, 1)))
+        n = self.taps * cin * cout
+        self.wpk3 = torch.empty(n, device=dev, dtype=BF16) if (self.patch_ok or self.p1x1_ok) else None
+        self.wpk3_d = torch.empty(n, device=dev, dtype=BF16) if (need_dgrad and (self.patch_ok or self.s2_dgrad_ok
+                                                                                 or self.p1x1_ok)) else None
 
     @staticmethod
     def _patch_efficiency(H, W):
@@ -125,15 +135,18 @@ class ConvLayer:
         ops.pack_weights(w, 0, self.cin_g, self.cout, self.taps, self.wpk)
         if self.need_dgrad:
             ops.pack_weights(w, 1, self.cin_g, self.cout, self.taps, self.wpk_d)
-        if self.patch_ok:
-            ops.pack3x3(w, self.cin, self.cout, 0, self.wpk3)
-            if self.need_dgrad:
-                ops.pack3x3(w, self.cout, self.cin, 1, self.wpk3_d)
+        if self.wpk3 is not None:
+            ops.pack_patch(w, self.cin, self.cout, self.taps, 0, self.wpk3)
+        if self.wpk3_d is not None:
+            ops.pack_patch(w, self.cout, self.cin, self.taps, 1, self.wpk3_d)
 
     def fprop(self, x, x_ld, B, H, W, out, out_ld, res=None, res_ld=0, relu=False):
         Ho, Wo = self.out_hw(H, W)
         if self.use_patch(H, W):
             ops.conv3x3_patch(x, x_ld, B, H, W, self.cin, self.wpk3, self.cout, out, out_ld, res, res_ld, relu, 0)
+            return Ho, Wo
+        if self.p1x1_ok:
+            ops.conv1x1_patch(x, x_ld, B, H, W, self.cin, self.wpk3, self.cout, out, out_ld, res, res_ld, relu, 0)
             return Ho, Wo
         bias = self.store.view(self.name + ".bias") if self.bias else None
         ops.conv_gemm(x, x_ld, B, H, W, self.cin_g, Ho, Wo, self.kh, self.kw, self.sh, self.sw, self.ph, self.pw,
@@ -148,6 +161,13 @@ class ConvLayer:
             res, res_ld = dx, dx_ld
         if out2 is None and self.use_patch(H, W):
             ops.conv3x3_patch(dy, dy_ld, B, H, W, self.cout, self.wpk3_d, self.cin, dx, dx_ld, res, res_ld, False, 1)
+            return
+        if out2 is None and self.p1x1_ok:
+            ops.conv1x1_patch(dy, dy_ld, B, H, W, self.cout, self.wpk3_d, self.cin, dx, dx_ld, res, res_ld, False, 1)
+            return
+        if out2 is None and self.s2_dgrad_ok and (self.kh == 3 or accumulate):
+            ops.conv_s2_dgrad_patch(dy, dy_ld, B, Ho, Wo, self.cout, self.wpk3_d, self.kh, self.cin, dx, dx_ld, H, W,
+                                    res, res_ld)
             return
         ops.conv_gemm_ex(dy, dy_ld, B, Ho, Wo, self.cout, H, W, self.kh, self.kw, self.sh, self.sw, self.ph, self.pw,
                          self.dh, self.dw, 1, self.wpk_d, self.cin_g, self.taps * self.cout, dx, dx_ld, None,

@@ -75,6 +75,33 @@ def conv3x3_patch(a, a_ld, B, H, W, C, wpk, N, out, out_ld, res=None, res_ld=0, 
     return out
 
 
+def pack_patch(w, C, N, taps, mode, out):
+    """w: fp32 [Cout][taps][Cin]; mode 0: (C, N) = (Cin, Cout); mode 1: (C, N) = (Cout, Cin), taps flipped."""
+    _lib.check(_lib.lib().air_conv_patch_pack_weights(_lib.ptr(w), _lib.ptr(out), C, N, taps, mode, _lib.stream_ptr()),
+               "air_conv_patch_pack_weights")
+    return out
+
+
+_ONE_TAP = (ctypes.c_int * 1)(0)
+
+
+def conv1x1_patch(a, a_ld, B, H, W, C, wpk, N, out, out_ld, res=None, res_ld=0, relu=False, mode=0):
+    """1x1 / stride-1 convolution (a plain GEMM over pixels) through the TMA patch kernel; mode labels the profile."""
+    _lib.check(_lib.lib().air_conv_patch_taps_bf16(
+        _lib.ptr(a), _lib.LL(a_ld), B, H, W, C, _lib.ptr(wpk), 1, N, _lib.ptr(out), _lib.LL(out_ld), H, W,
+        _lib.ptr(res), _lib.LL(res_ld), int(relu), H, W, 0, 0, 1, 1, 0, 0, 1, _ONE_TAP, _ONE_TAP, _ONE_TAP,
+        num_sms(), _lib.stream_ptr()), "air_conv_patch_taps_bf16")
+    return out
+
+
+def conv_s2_dgrad_patch(dy, dy_ld, B, Ho, Wo, Cout, wpk, k, Cin, dx, dx_ld, H, W, res=None, res_ld=0):
+    """Data gradient of a stride-2 k x k (k = 3 pad 1 / k = 1 pad 0) convolution by output parity classes."""
+    _lib.check(_lib.lib().air_conv_s2_dgrad_patch_bf16(
+        _lib.ptr(dy), _lib.LL(dy_ld), B, Ho, Wo, Cout, _lib.ptr(wpk), k, Cin, _lib.ptr(dx), _lib.LL(dx_ld), H, W,
+        _lib.ptr(res), _lib.LL(res_ld), num_sms(), _lib.stream_ptr()), "air_conv_s2_dgrad_patch_bf16", 4 if k == 3 else 1)
+    return dx
+
+
 def wgrad_patch_supported(C, N):
     return bool(_lib.lib().air_conv3x3_wgrad_patch_supported(int(C), int(N)))
 
@@ -401,3 +428,7 @@ pack3x3 = _timed(pack3x3, "pack_weights")
 conv3x3_patch = _timed(conv3x3_patch, lambda a: "conv_dgrad" if (len(a) > 13 and a[13] == 1) else "conv_fprop",
                        lambda a: 2.0 * a[2] * a[3] * a[4] * a[5] * a[7] * 9)
 conv3x3_wgrad_patch = _timed(conv3x3_wgrad_patch, "conv_wgrad", lambda a: 2.0 * a[2] * a[3] * a[4] * a[5] * a[8] * 9)
+pack_patch = _timed(pack_patch, "pack_weights")
+conv1x1_patch = _timed(conv1x1_patch, lambda a: "conv_dgrad" if (len(a) > 13 and a[13] == 1) else "conv_fprop",
+                       lambda a: 2.0 * a[2] * a[3] * a[4] * a[5] * a[7])
+conv_s2_dgrad_patch = _timed(conv_s2_dgrad_patch, "conv_dgrad", lambda a: 2.0 * a[2] * a[3] * a[4] * a[5] * a[8] * a[7] * a[7])

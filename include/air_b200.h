@@ -108,6 +108,25 @@ int air_conv3x3_patch_bf16(const void* a, long long a_ld, int B, int H, int W, i
                            const void* wpk, int N, void* out, long long out_ld,
                            const void* res, long long res_ld, int relu, int num_sms, air_stream_t stream);
 
+/* General form of the patch kernel: explicit tap table and output pixel mapping
+ *   out[b, g*osh+oph, g'*osw+opw, n] = sum_t sum_c a[b, g+org_h+tap_dr[t], g'+org_w+tap_dc[t], c] * Wp[tap_slice[t]][n][c] (+res)(ReLU)
+ * over the item grid g < GH, g' < GW (0 <= tap_dr, tap_dc <= 2; out-of-range reads are zero).  wpk holds wtaps slices
+ * per channel block (air_conv_patch_pack_weights, taps = 9 or 1). */
+int air_conv_patch_pack_weights(const float* w, void* dst, int C, int N, int taps, int mode, air_stream_t stream);
+int air_conv_patch_taps_bf16(const void* a, long long a_ld, int B, int Hin, int Win, int C,
+                             const void* wpk, int wtaps, int N, void* out, long long out_ld, int OH, int OW,
+                             const void* res, long long res_ld, int relu,
+                             int GH, int GW, int org_h, int org_w, int osh, int osw, int oph, int opw,
+                             int ntaps, const int* tap_dr, const int* tap_dc, const int* tap_slice,
+                             int num_sms, air_stream_t stream);
+/* Data gradient of a stride-2 layer (k = 3 / pad 1: resnet.py:56 conv1 of layer2-4.0; k = 1 / pad 0: the shortcut,
+ * resnet.py:60-61) decomposed by output parity so that only structurally non-zero taps are multiplied.
+ * dy (B,Ho,Wo,Cout) -> dx (B,H,W,Cin); wpk = mode-1 packed weights with k*k taps.  k = 1 writes only the even-even
+ * pixels (pass res = dx to accumulate into an existing gradient). */
+int air_conv_s2_dgrad_patch_bf16(const void* dy, long long dy_ld, int B, int Ho, int Wo, int Cout,
+                                 const void* wpk, int k, int Cin, void* dx, long long dx_ld, int H, int W,
+                                 const void* res, long long res_ld, int num_sms, air_stream_t stream);
+
 /* Weight gradient of the same 3x3 / stride 1 / pad 1 layers from shared-memory resident patches
  * (csrc/conv_wgrad_patch.cu): dW[co][i][j][ci] += sum_{b,h,w} x[b,h+i-1,w+j-1,ci] * dy[b,h,w,co], accumulated with fp32
  * atomics into the caller-zeroed dw_out ([Cout][dw_ld >= 9*Cin] fp32, GEMM layout).  C % 64 == 0, N % 64 == 0. */

@@ -200,3 +200,66 @@ def test_patch_conv3x3_wgrad(name):
     err = (got - ref).norm() / ref.norm()
     worst = (got - ref).abs().max() / ref.abs().max()
     assert err < 1e-3 and worst < 2e-3, "%s: normwise %.3g, worst %.3g" % (name, float(err), float(worst))
+
+
+S2_CASES = {
+    # name: B, H, W, Cin, Cout, k
+    "l2_3x3": (2, 18, 750, 64, 128, 3),
+    "l3_3x3_odd": (2, 9, 375, 128, 256, 3),
+    "l4_3x3_odd_h": (2, 5, 188, 256, 256, 3),
+    "tiny_3x3": (1, 3, 5, 64, 64, 3),
+    "l2_1x1": (2, 18, 750, 64, 128, 1),
+    "l3_1x1_odd": (2, 9, 375, 128, 256, 1),
+}
+
+
+@pytest.mark.parametrize("name", list(S2_CASES))
+def test_patch_stride2_dgrad_by_parity(name):
+    """air_conv_s2_dgrad_patch_bf16: output-parity decomposition of the stride-2 data gradient vs torch fp32."""
+    from asvspoof2021_air_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    B, H, W, Cin, Cout, k = S2_CASES[name]
+    pad = 1 if k == 3 else 0
+    g = torch.Generator(device="cpu").manual_seed(17)
+    Ho, Wo = ops.conv_out_size(H, k, 2, pad, 1), ops.conv_out_size(W, k, 2, pad, 1)
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).cuda()
+    dy = torch.randn(B, Cout, Ho, Wo, generator=g).cuda().to(torch.bfloat16)
+    prev = torch.randn(B, H, W, Cin, generator=g).cuda().to(torch.bfloat16)
+    wq = w.to(torch.bfloat16).float()
+    wpk_d = torch.empty(k * k * Cin * Cout, device="cuda", dtype=torch.bfloat16)
+    ops.pack_patch(w.permute(0, 2, 3, 1).contiguous(), Cout, Cin, k * k, 1, wpk_d)
+    dx = prev.clone()
+    ops.conv_s2_dgrad_patch(dy.permute(0, 2, 3, 1).contiguous(), Cout, B, Ho, Wo, Cout, wpk_d, k, Cin, dx, Cin, H, W, dx, Cin)
+    torch.cuda.synchronize()
+    ref = torch.nn.grad.conv2d_input((B, Cin, H, W), wq, dy.float(), stride=2, padding=pad) + prev.float().permute(0, 3, 1, 2)
+    _check(dx.float().permute(0, 3, 1, 2), ref, name + " s2 dgrad (accumulate)")
+    if k == 3:
+        dx2 = torch.full((B, H, W, Cin), float("nan"), device="cuda", dtype=torch.bfloat16)
+        ops.conv_s2_dgrad_patch(dy.permute(0, 2, 3, 1).contiguous(), Cout, B, Ho, Wo, Cout, wpk_d, k, Cin, dx2, Cin, H, W)
+        torch.cuda.synchronize()
+        _check(dx2.float().permute(0, 3, 1, 2), ref - prev.float().permute(0, 3, 1, 2), name + " s2 dgrad")
+
+
+@pytest.mark.parametrize("shape", [(2, 18, 750, 16, 64), (2, 7, 130, 64, 16), (1, 3, 94, 128, 256)])
+def test_patch_conv1x1(shape):
+    """single-tap use of the patch kernel (1x1 / stride 1 = GEMM over pixels) vs torch fp32."""
+    from asvspoof2021_air_b200 import ops
+    B, H, W, Cin, Cout = shape
+    g = torch.Generator(device="cpu").manual_seed(19)
+    x = torch.randn(B, H, W, Cin, generator=g).cuda().to(torch.bfloat16)
+    w = (torch.randn(Cout, Cin, generator=g) / Cin ** 0.5).cuda()
+    res = torch.randn(B, H, W, Cout, generator=g).cuda().to(torch.bfloat16)
+    wpk = torch.empty(Cin * Cout, device="cuda", dtype=torch.bfloat16)
+    ops.pack_patch(w.contiguous(), Cin, Cout, 1, 0, wpk)
+    out = torch.full((B, H, W, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.conv1x1_patch(x, Cin, B, H, W, Cin, wpk, Cout, out, Cout, res, Cout, False)
+    torch.cuda.synchronize()
+    ref = x.float() @ w.to(torch.bfloat16).float().t() + res.float()
+    _check(out.float(), ref, "1x1 patch fprop")
+    wpk_d = torch.empty(Cin * Cout, device="cuda", dtype=torch.bfloat16)
+    ops.pack_patch(w.contiguous(), Cout, Cin, 1, 1, wpk_d)
+    dy = torch.randn(B, H, W, Cout, generator=g).cuda().to(torch.bfloat16)
+    dx = torch.full((B, H, W, Cin), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.conv1x1_patch(dy, Cout, B, H, W, Cout, wpk_d, Cin, dx, Cin, None, 0, False, 1)
+    torch.cuda.synchronize()
+    _check(dx.float(), dy.float() @ w.to(torch.bfloat16).float(), "1x1 patch dgrad")
