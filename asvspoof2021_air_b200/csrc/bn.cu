@@ -28,8 +28,21 @@ __global__ void __launch_bounds__(THREADS) bn_stats_kernel(const __nv_bfloat16* 
 #pragma unroll
   for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
   if (tr < rows_per_it) {
-    for (long long m = static_cast<long long>(blockIdx.x) * rows_per_it + tr; m < M;
-         m += static_cast<long long>(gridDim.x) * rows_per_it) {
+    const long long step = static_cast<long long>(gridDim.x) * rows_per_it;
+    long long m = static_cast<long long>(blockIdx.x) * rows_per_it + tr;
+    for (; m + 3 * step < M; m += 4 * step) {             // four independent 16-byte loads in flight per thread
+      bf16x8 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const bf16x8*>(x + (m + u * step) * ld + tc * 8);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        unpack8(v[u], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+      }
+    }
+    for (; m < M; m += step) {
       const bf16x8 v = *reinterpret_cast<const bf16x8*>(x + m * ld + tc * 8);
       float f[8];
       unpack8(v, f);
@@ -64,10 +77,15 @@ struct ApplyParams {
 };
 
 __global__ void __launch_bounds__(THREADS) bn_apply_kernel(const ApplyParams p) {
-  extern __shared__ float sh[];                 // scale[C], shift[C]
-  float* scale = sh;
-  float* shift = sh + p.C;
-  for (int c = threadIdx.x; c < p.C; c += THREADS) {
+  // thread -> fixed 8-channel chunk tc (scale / shift live in registers), rows strided over the grid
+  const int cpr = p.C >> 3;
+  const int rows_per_it = THREADS / cpr;
+  const int tc = threadIdx.x % cpr, tr = threadIdx.x / cpr;
+  if (tr >= rows_per_it) return;
+  float scale[8], shift[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = tc * 8 + k;
     float mean, invstd;
     if (p.training) {
       const double mu = p.sums[c] / static_cast<double>(p.M);
@@ -75,7 +93,7 @@ __global__ void __launch_bounds__(THREADS) bn_apply_kernel(const ApplyParams p) 
       if (var < 0.0) var = 0.0;
       mean = static_cast<float>(mu);
       invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.eps)));
-      if (blockIdx.x == 0) {
+      if (blockIdx.x == 0 && tr == 0) {
         if (p.save_mean) { p.save_mean[c] = mean; p.save_invstd[c] = invstd; }
         if (p.running_mean) {
           const double unb = p.M > 1 ? var * static_cast<double>(p.M) / static_cast<double>(p.M - 1) : var;
@@ -87,22 +105,37 @@ __global__ void __launch_bounds__(THREADS) bn_apply_kernel(const ApplyParams p) 
       mean = p.running_mean[c];
       invstd = rsqrtf(p.running_var[c] + p.eps);
     }
-    const float g = p.gamma ? p.gamma[c] : 1.f, b = p.beta ? p.beta[c] : 0.f;
-    scale[c] = g * invstd;
-    shift[c] = b - mean * g * invstd;
+    const float g = p.gamma ? p.gamma[c] : 1.f, be = p.beta ? p.beta[c] : 0.f;
+    scale[k] = g * invstd;
+    shift[k] = be - mean * g * invstd;
   }
-  __syncthreads();
-  const int cpr = p.C >> 3;
-  const long long total = p.M * cpr;
-  for (long long i = static_cast<long long>(blockIdx.x) * THREADS + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * THREADS) {
-    const long long m = i / cpr;
-    const int c0 = static_cast<int>(i - m * cpr) * 8;
+  const long long step = static_cast<long long>(gridDim.x) * rows_per_it;
+  long long m = static_cast<long long>(blockIdx.x) * rows_per_it + tr;
+  const int c0 = tc * 8;
+  if (!p.y2) {
+    for (; m + 3 * step < p.M; m += 4 * step) {            // four independent loads in flight before the first store
+      bf16x8 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const bf16x8*>(p.x + (m + u * step) * p.x_ld + c0);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        unpack8(v[u], f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          f[k] = fmaf(f[k], scale[k], shift[k]);
+          if (p.relu) f[k] = fmaxf(f[k], 0.f);
+        }
+        *reinterpret_cast<bf16x8*>(p.y + (m + u * step) * p.y_ld + c0) = pack8(f);
+      }
+    }
+  }
+  for (; m < p.M; m += step) {
     float f[8];
     unpack8(*reinterpret_cast<const bf16x8*>(p.x + m * p.x_ld + c0), f);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      f[k] = fmaf(f[k], scale[c0 + k], shift[c0 + k]);
+      f[k] = fmaf(f[k], scale[k], shift[k]);
       if (p.relu) f[k] = fmaxf(f[k], 0.f);
     }
     const bf16x8 yv = pack8(f);
@@ -145,18 +178,37 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_reduce_kernel(const BwdParams 
       const int c = tc * 8 + i;
       mu[i] = p.mean[c]; is[i] = p.invstd[c]; ga[i] = p.gamma ? p.gamma[c] : 1.f; be[i] = p.beta ? p.beta[c] : 0.f;
     }
-    for (long long m = static_cast<long long>(blockIdx.x) * rows_per_it + tr; m < p.M;
-         m += static_cast<long long>(gridDim.x) * rows_per_it) {
-      float g[8], xv[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(p.dy + m * p.dy_ld + tc * 8), g);
-      unpack8(*reinterpret_cast<const bf16x8*>(p.x + m * p.x_ld + tc * 8), xv);
+    const long long step = static_cast<long long>(gridDim.x) * rows_per_it;
+    long long m = static_cast<long long>(blockIdx.x) * rows_per_it + tr;
+    constexpr int U = 4;                                   // 2 x U independent 16-byte loads in flight per thread
+    while (m < p.M) {
+      bf16x8 gv[U], xq[U];
+      int n = 0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float xh = (xv[i] - mu[i]) * is[i];
-        float gi = g[i];
-        if (p.order == 0 && !(fmaf(ga[i], xh, be[i]) > 0.f)) gi = 0.f;
-        s[i] += gi; q[i] = fmaf(gi, xh, q[i]);
+      for (int u = 0; u < U; ++u) {
+        const long long mm = m + u * step;
+        if (mm < p.M) {
+          gv[u] = *reinterpret_cast<const bf16x8*>(p.dy + mm * p.dy_ld + tc * 8);
+          xq[u] = *reinterpret_cast<const bf16x8*>(p.x + mm * p.x_ld + tc * 8);
+          n = u + 1;
+        }
       }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (u < n) {
+          float g[8], xv[8];
+          unpack8(gv[u], g);
+          unpack8(xq[u], xv);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float xh = (xv[i] - mu[i]) * is[i];
+            float gi = g[i];
+            if (p.order == 0 && !(fmaf(ga[i], xh, be[i]) > 0.f)) gi = 0.f;
+            s[i] += gi; q[i] = fmaf(gi, xh, q[i]);
+          }
+        }
+      }
+      m += U * step;
     }
   }
   float* ss = sh;
@@ -176,66 +228,77 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_reduce_kernel(const BwdParams 
 // backward, pass 2: dx = gamma*invstd*(g - sum_g/M - xhat*sum_gx/M) [* (x > 0) for order 1] [+ add]
 // block 0 also writes dgamma = sum g*xhat, dbeta = sum g (accumulating into the gradient buffer).
 __global__ void __launch_bounds__(THREADS) bn_bwd_apply_kernel(const BwdParams p) {
-  extern __shared__ float sh[];                 // k1[C] = gamma*invstd, k2[C] = sum_g/M, k3[C] = sum_gx/M, mean, invstd, gamma, beta
-  float* k1 = sh; float* k2 = sh + p.C; float* k3 = sh + 2 * p.C;
-  float* smu = sh + 3 * p.C; float* sis = sh + 4 * p.C; float* sga = sh + 5 * p.C; float* sbe = sh + 6 * p.C;
-  for (int c = threadIdx.x; c < p.C; c += THREADS) {
-    const float ga = p.gamma ? p.gamma[c] : 1.f;
+  // thread -> fixed 8-channel chunk tc; the per-channel constants live in registers:
+  //   xh = x * a + b2 (a = invstd, b2 = -mean * invstd),  dx = gi * k1 - (c2 + xh * c3),  c2 = k1 * sum_g / M, c3 = k1 * sum_gx / M
+  extern __shared__ float sh[];                 // [THREADS][8] (dbias reduction only)
+  const int cpr = p.C >> 3;
+  const int rows_per_it = THREADS / cpr;
+  const int tc = threadIdx.x % cpr, tr = threadIdx.x / cpr;
+  const bool active = tr < rows_per_it;
+  float a[8], b2[8], k1[8], c2[8], c3[8], ga[8], be[8], bs[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = tc * 8 + k;
+    const float gam = p.gamma ? p.gamma[c] : 1.f;
     const double sg = p.rsum[c], sgx = p.rsum[p.C + c];
-    k1[c] = ga * p.invstd[c];
-    k2[c] = static_cast<float>(sg / static_cast<double>(p.M));
-    k3[c] = static_cast<float>(sgx / static_cast<double>(p.M));
-    smu[c] = p.mean[c]; sis[c] = p.invstd[c]; sga[c] = ga; sbe[c] = p.beta ? p.beta[c] : 0.f;
-    if (blockIdx.x == 0) {
+    const float is = p.invstd[c], mu = p.mean[c];
+    a[k] = is; b2[k] = -mu * is; k1[k] = gam * is;
+    c2[k] = k1[k] * static_cast<float>(sg / static_cast<double>(p.M));
+    c3[k] = k1[k] * static_cast<float>(sgx / static_cast<double>(p.M));
+    ga[k] = gam; be[k] = p.beta ? p.beta[c] : 0.f; bs[k] = 0.f;
+    if (blockIdx.x == 0 && tr == 0) {
       if (p.dgamma) p.dgamma[c] += static_cast<float>(sgx);
       if (p.dbeta) p.dbeta[c] += static_cast<float>(sg);
     }
   }
-  __syncthreads();
-  const int cpr = p.C >> 3;
-  const long long total = p.M * cpr;
-  float bs[8];
+  if (active) {
+    const long long step = static_cast<long long>(gridDim.x) * rows_per_it;
+    const int c0 = tc * 8;
+    for (long long m0 = static_cast<long long>(blockIdx.x) * rows_per_it + tr; m0 < p.M; m0 += 2 * step) {
+      // two rows' loads (up to 6 x 16 bytes) are issued before the first store
+      bf16x8 gq[2], xq[2], aq[2];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) bs[k] = 0.f;
-  int my_c0 = -1;
-  for (long long i = static_cast<long long>(blockIdx.x) * THREADS + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * THREADS) {
-    const long long m = i / cpr;
-    const int c0 = static_cast<int>(i - m * cpr) * 8;
-    my_c0 = c0;                       // constant per thread when (gridDim.x * THREADS) % cpr == 0 (launcher guarantees it with dbias)
-    float g[8], xv[8], ad[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(p.dy + m * p.dy_ld + c0), g);
-    unpack8(*reinterpret_cast<const bf16x8*>(p.x + m * p.x_ld + c0), xv);
-    if (p.add) unpack8(*reinterpret_cast<const bf16x8*>(p.add + m * p.add_ld + c0), ad);
+      for (int u = 0; u < 2; ++u) {
+        const long long m = m0 + u * step;
+        if (m < p.M) {
+          gq[u] = *reinterpret_cast<const bf16x8*>(p.dy + m * p.dy_ld + c0);
+          xq[u] = *reinterpret_cast<const bf16x8*>(p.x + m * p.x_ld + c0);
+          if (p.add) aq[u] = *reinterpret_cast<const bf16x8*>(p.add + m * p.add_ld + c0);
+        }
+      }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int c = c0 + k;
-      const float xh = (xv[k] - smu[c]) * sis[c];
-      float gi = g[k];
-      if (p.order == 0 && !(fmaf(sga[c], xh, sbe[c]) > 0.f)) gi = 0.f;
-      float d = k1[c] * (gi - k2[c] - xh * k3[c]);
-      if (p.order == 1 && !(xv[k] > 0.f)) d = 0.f;
-      if (p.add) d += ad[k];
-      g[k] = d;
-      bs[k] += d;
+      for (int u = 0; u < 2; ++u) {
+        const long long m = m0 + u * step;
+        if (m >= p.M) continue;
+        float g[8], xv[8], ad[8];
+        unpack8(gq[u], g);
+        unpack8(xq[u], xv);
+        if (p.add) unpack8(aq[u], ad);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float xh = fmaf(xv[k], a[k], b2[k]);
+          float gi = g[k];
+          if (p.order == 0 && !(fmaf(ga[k], xh, be[k]) > 0.f)) gi = 0.f;
+          float d = fmaf(gi, k1[k], -fmaf(xh, c3[k], c2[k]));
+          if (p.order == 1 && !(xv[k] > 0.f)) d = 0.f;
+          if (p.add) d += ad[k];
+          g[k] = d;
+          bs[k] += d;
+        }
+        *reinterpret_cast<bf16x8*>(p.dx + m * p.dx_ld + c0) = pack8(g);
+      }
     }
-    *reinterpret_cast<bf16x8*>(p.dx + m * p.dx_ld + c0) = pack8(g);
   }
   if (p.dbias) {
-    // block-level reduction first (one atomic per channel per CTA): thread t owns chunk
-    // ((blockIdx.x * THREADS + t) % cpr) for the whole loop (launcher guarantees (gridDim.x * THREADS) % cpr == 0)
-    float* red = sh + 7 * p.C;                  // [THREADS][8]
-    (void)my_c0;
+    // block-level reduction first (one atomic per channel per CTA): thread t owns chunk t % cpr
 #pragma unroll
-    for (int k = 0; k < 8; ++k) red[threadIdx.x * 8 + k] = bs[k];
+    for (int k = 0; k < 8; ++k) sh[threadIdx.x * 8 + k] = active ? bs[k] : 0.f;
     __syncthreads();
-    const int first = static_cast<int>((static_cast<long long>(blockIdx.x) * THREADS) % cpr);
     for (int c = threadIdx.x; c < p.C; c += THREADS) {
       const int chunk = c >> 3, e = c & 7;
-      int t0 = chunk - first; if (t0 < 0) t0 += cpr;
-      float a = 0.f;
-      for (int t = t0; t < THREADS; t += cpr) a += red[t * 8 + e];
-      atomicAdd(&p.dbias[c], a);
+      float acc = 0.f;
+      for (int t = chunk; t < THREADS; t += cpr) acc += sh[t * 8 + e];
+      atomicAdd(&p.dbias[c], acc);
     }
   }
 }
@@ -275,8 +338,10 @@ extern "C" int air_bn_apply_add(const void* x, long long x_ld, void* y, long lon
   ApplyParams p{reinterpret_cast<const __nv_bfloat16*>(x), x_ld, reinterpret_cast<__nv_bfloat16*>(y), y_ld, M, C,
                 sums, gamma, beta, eps, relu, training, save_mean, save_invstd, running_mean, running_var, momentum,
                 reinterpret_cast<const __nv_bfloat16*>(add), add_ld, reinterpret_cast<__nv_bfloat16*>(y2), y2_ld};
-  const int grid = grid_for(M * (C / 8), THREADS * 8, num_sms);
-  bn_apply_kernel<<<grid, THREADS, 2 * C * sizeof(float), stream>>>(p);
+  const int rows_per_it = THREADS / (C / 8);
+  if (rows_per_it < 1) return AIR_ERR_UNSUPPORTED;
+  const int grid = grid_for(M, rows_per_it * 8, num_sms);
+  bn_apply_kernel<<<grid, THREADS, 0, stream>>>(p);
   return air_launch_status();
 }
 
@@ -313,13 +378,7 @@ extern "C" int air_bn_bwd_bias(const void* dy, long long dy_ld, const void* x, l
   const int rows_per_it = THREADS / (C / 8);
   if (rows_per_it < 1) return AIR_ERR_UNSUPPORTED;
   bn_bwd_reduce_kernel<<<grid_for(M, rows_per_it * 16, num_sms), THREADS, 2 * THREADS * 8 * sizeof(float), stream>>>(p);
-  int agrid = grid_for(M * (C / 8), THREADS * 8, num_sms);
-  if (dbias) {                         // every thread must stay on one 8-channel chunk: (grid * THREADS) % (C/8) == 0
-    const int cpr = C / 8;
-    int q = cpr;                       // smallest multiple of cpr / gcd(cpr, THREADS)
-    { int a = cpr, b = THREADS; while (b) { int t = a % b; a = b; b = t; } q = cpr / a; }
-    agrid = std::max(q, agrid / q * q);
-  }
-  bn_bwd_apply_kernel<<<agrid, THREADS, (7 * C + (dbias ? THREADS * 8 : 0)) * sizeof(float), stream>>>(p);
+  const int agrid = grid_for(M, rows_per_it * 8, num_sms);
+  bn_bwd_apply_kernel<<<agrid, THREADS, (dbias ? THREADS * 8 : 0) * sizeof(float), stream>>>(p);
   return air_launch_status();
 }

@@ -18,6 +18,7 @@
 #include <algorithm>
 #include "common.cuh"
 #include "tc05.cuh"
+#include "pack.cuh"
 
 namespace air_gemm {
 using namespace tc05;
@@ -149,35 +150,36 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const ConvParams 
       }
     }
   } else if (warp == 5) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = instr_desc_bf16(BLOCK_M, p.block_n, 0, 0);
-      const uint32_t b_chunk = static_cast<uint32_t>(p.block_n) * 16;
-      uint32_t a_lbo = A_CHUNK_STRIDE, a_sbo = 128, b_lbo = b_chunk, b_sbo = 128;
-      if (p.flags & 1) { a_lbo = 128; a_sbo = A_CHUNK_STRIDE; b_lbo = 128; b_sbo = b_chunk; }   // debug: swapped roles
-      uint32_t stage = 0, phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tempty[acc], acc_phase ^ 1);
+    // ===================== MMA issuer (warp-uniform loop: descriptors in uniform registers, elected lane issues) =====================
+    const bool leader = elect_one();
+    const uint32_t idesc = instr_desc_bf16(BLOCK_M, p.block_n, 0, 0);
+    const uint32_t b_chunk = static_cast<uint32_t>(p.block_n) * 16;
+    uint32_t a_lbo = A_CHUNK_STRIDE, a_sbo = 128, b_lbo = b_chunk, b_sbo = 128;
+    if (p.flags & 1) { a_lbo = 128; a_sbo = A_CHUNK_STRIDE; b_lbo = 128; b_sbo = b_chunk; }   // debug: swapped roles
+    const uint32_t a_hi = (a_sbo >> 4) | (1u << 14), b_hi = (b_sbo >> 4) | (1u << 14);
+    const uint32_t a_lbo16 = (a_lbo >> 4) << 16, b_lbo16 = (b_lbo >> 4) << 16;
+    uint32_t stage = 0, phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      fence_after_sync();
+      const uint32_t d_tmem = tmem_base + acc * p.block_n;
+      for (int kb = 0; kb < p.KB; ++kb) {
+        mbar_wait(&full[stage], phase);
         fence_after_sync();
-        const uint32_t d_tmem = tmem_base + acc * p.block_n;
-        for (int kb = 0; kb < p.KB; ++kb) {
-          mbar_wait(&full[stage], phase);
-          fence_after_sync();
-          const uint32_t a0 = smem_u32(sA) + stage * A_STAGE_BYTES;
-          const uint32_t b0 = smem_u32(sB) + stage * b_stage_bytes;
+        const uint32_t a0 = (((smem_u32(sA) + stage * A_STAGE_BYTES) >> 4) & 0x3FFF) | a_lbo16;
+        const uint32_t b0 = (((smem_u32(sB) + stage * b_stage_bytes) >> 4) & 0x3FFF) | b_lbo16;
 #pragma unroll
-          for (int kk = 0; kk < BLOCK_K / 16; ++kk) {
-            const uint64_t ad = smem_desc(a0 + kk * 2 * A_CHUNK_STRIDE, a_lbo, a_sbo);
-            const uint64_t bd = smem_desc(b0 + kk * 2 * b_chunk, b_lbo, b_sbo);
-            mma_bf16(d_tmem, ad, bd, idesc, (kb | kk) != 0);
-          }
-          mma_commit(&empty[stage]);
-          if (kb == p.KB - 1) mma_commit(&tfull[acc]);
-          if (++stage == static_cast<uint32_t>(S)) { stage = 0; phase ^= 1; }
+        for (int kk = 0; kk < BLOCK_K / 16; ++kk) {
+          const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a0 + kk * ((2 * A_CHUNK_STRIDE) >> 4));
+          const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b0 + kk * ((2 * b_chunk) >> 4));
+          if (leader) mma_bf16(d_tmem, ad, bd, idesc, (kb | kk) != 0);
         }
+        if (leader) mma_commit(&empty[stage]);
+        if (kb == p.KB - 1 && leader) mma_commit(&tfull[acc]);
+        if (++stage == static_cast<uint32_t>(S)) { stage = 0; phase ^= 1; }
       }
     }
     __syncwarp();
@@ -246,20 +248,8 @@ __global__ void pack_weights_kernel(const float* __restrict__ src, __nv_bfloat16
   // (for a column slice of a wider matrix, e.g. attention.0's W_x = W[:, :1536], sn is the full row stride)
   const long long total = static_cast<long long>(N) * KB * BLOCK_K;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    // destination order: [n_tile][kb][chunk][n_local][e]
-    const int e = static_cast<int>(i & 7);
-    long long t = i >> 3;
-    const int n_local = static_cast<int>(t % block_n); t /= block_n;
-    const int c = static_cast<int>(t & 7); t >>= 3;
-    const int kb = static_cast<int>(t % KB);
-    const int n_tile = static_cast<int>(t / KB);
-    const int n = n_tile * block_n + n_local;
-    const int k = kb * BLOCK_K + c * 8 + e;
-    float v = 0.f;
-    if (k < K && n < N) v = src[n * sn + static_cast<long long>(k / inner) * so + static_cast<long long>(k % inner) * si];
-    dst[i] = f2bf(v);
-  }
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    air_pack::gemm_pack_elem(src, dst, i, N, K, KB, block_n, sn, inner, so, si);
 }
 
 static int pick_block_n(int N) {

@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "tc05.cuh"
 #include "tmap.cuh"
+#include "pack.cuh"
 
 namespace air_patch {
 using namespace tc05;
@@ -259,20 +260,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_patch_kernel(const __grid_con
 //   mode 1 (dgrad): w is [C = Cout][taps][N = Cin];   value = w[ch][taps - 1 - tap][n]   (flipped taps, swapped channels)
 __global__ void pack_patch_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int C, int N, int CB, int taps, int mode) {
   const long long total = static_cast<long long>(taps) * C * N;
-  const uint32_t mask = CB == 64 ? 7u : (CB == 32 ? 3u : 1u);
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int k = static_cast<int>(i % CB);
-    long long t = i / CB;
-    const int n = static_cast<int>(t % N); t /= N;
-    const int tap = static_cast<int>(t % taps);
-    const int cb = static_cast<int>(t / taps);
-    const int ch = cb * CB + k;
-    const float v = mode == 0 ? w[(static_cast<long long>(n) * taps + tap) * C + ch]
-                              : w[(static_cast<long long>(ch) * taps + (taps - 1 - tap)) * N + n];
-    const uint32_t off = swizzle_offset(static_cast<uint32_t>(n) * CB * 2 + (k >> 3) * 16, mask) + (k & 7) * 2;
-    dst[(static_cast<long long>(cb) * taps + tap) * N * CB + (off >> 1)] = f2bf(v);
-  }
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    air_pack::patch_pack_elem(w, dst, i, C, N, CB, taps, mode);
 }
 
 }  // namespace air_patch

@@ -138,28 +138,29 @@ __global__ void __launch_bounds__(THREADS, 1) conv_wgrad_kernel(const WgradParam
       fence_before_sync();
       mbar_arrive(tempty);
     } else if (warp == 4) {
-      if (lane == 0) {
-        const uint32_t idesc = instr_desc_bf16(128, p.block_n, 1, 1);
-        uint32_t lbo = 128, sbo = CHUNK_STRIDE;
-        if (p.flags & 1) { lbo = CHUNK_STRIDE; sbo = 128; }
-        mbar_wait(tempty, (it & 1) ^ 1);
+      // warp-uniform issue loop: descriptors in uniform registers, one elected lane issues
+      const bool leader = elect_one();
+      const uint32_t idesc = instr_desc_bf16(128, p.block_n, 1, 1);
+      uint32_t lbo = 128, sbo = CHUNK_STRIDE;
+      if (p.flags & 1) { lbo = CHUNK_STRIDE; sbo = 128; }
+      const uint32_t d_hi = (sbo >> 4) | (1u << 14), lbo16 = (lbo >> 4) << 16;
+      mbar_wait(tempty, (it & 1) ^ 1);
+      fence_after_sync();
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full[stage], phase);
         fence_after_sync();
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full[stage], phase);
-          fence_after_sync();
-          const uint32_t s0 = smem_u32(smem) + stage * stage_bytes;
+        const uint32_t s0 = (((smem_u32(smem) + stage * stage_bytes) >> 4) & 0x3FFF) | lbo16;
 #pragma unroll
-          for (int kk = 0; kk < PIX / 16; ++kk) {
-            const uint64_t bd = smem_desc(s0 + 2 * A_HALF_BYTES + kk * 256, lbo, sbo);
-            for (int h = 0; h < halves; ++h) {
-              const uint64_t ad = smem_desc(s0 + h * A_HALF_BYTES + kk * 256, lbo, sbo);
-              mma_bf16(tmem_base + h * p.block_n, ad, bd, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
-            }
+        for (int kk = 0; kk < PIX / 16; ++kk) {
+          const uint64_t bd = (static_cast<uint64_t>(d_hi) << 32) | (s0 + ((2 * A_HALF_BYTES + kk * 256) >> 4));
+          for (int h = 0; h < halves; ++h) {
+            const uint64_t ad = (static_cast<uint64_t>(d_hi) << 32) | (s0 + ((h * A_HALF_BYTES + kk * 256) >> 4));
+            if (leader) mma_bf16(tmem_base + h * p.block_n, ad, bd, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
           }
-          mma_commit(&empty[stage]);
-          if (kb == kb1 - 1) mma_commit(tfull);
-          if (++stage == static_cast<uint32_t>(S)) { stage = 0; phase ^= 1; }
         }
+        if (leader) mma_commit(&empty[stage]);
+        if (kb == kb1 - 1 && leader) mma_commit(tfull);
+        if (++stage == static_cast<uint32_t>(S)) { stage = 0; phase ^= 1; }
       }
       __syncwarp();
     }

@@ -17,76 +17,95 @@ struct StemParams {
   const float* w; __nv_bfloat16* y; const __nv_bfloat16* dy; float* dw; long long M;
 };
 
+// Forward: a thread computes 4 consecutive output columns x 16 channels; a weight vector (16 channels of one tap,
+// 4 x LDS.128) feeds 64 FMAs, an input row segment of 6 samples is loaded once for the 3 horizontal taps.
+constexpr int FW_PIX = 4;
 __global__ void __launch_bounds__(256) stem_fwd_kernel(const StemParams p) {
-  __shared__ float sw[CO * MAX_TAPS];
+  __shared__ __align__(16) float swt[MAX_TAPS * CO];          // [tap][co]
   const int taps = p.kh * p.kw;
-  for (int i = threadIdx.x; i < CO * taps; i += blockDim.x) sw[i] = p.w[i];
+  for (int i = threadIdx.x; i < CO * taps; i += blockDim.x) { const int c = i / taps, t = i - c * taps; swt[t * CO + c] = p.w[i]; }
   __syncthreads();
-  for (long long m = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; m < p.M;
-       m += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int wo = static_cast<int>(m % p.Wo); const long long t = m / p.Wo;
+  const int WQ = (p.Wo + FW_PIX - 1) / FW_PIX;
+  const long long total = static_cast<long long>(p.B) * p.Ho * WQ;
+  for (long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; q < total;
+       q += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int wq = static_cast<int>(q % WQ); const long long t = q / WQ;
     const int ho = static_cast<int>(t % p.Ho), b = static_cast<int>(t / p.Ho);
-    float acc[CO];
+    const int wo0 = wq * FW_PIX;
+    float acc[FW_PIX][CO];
 #pragma unroll
-    for (int c = 0; c < CO; ++c) acc[c] = 0.f;
+    for (int px = 0; px < FW_PIX; ++px)
+#pragma unroll
+      for (int c = 0; c < CO; ++c) acc[px][c] = 0.f;
     const __nv_bfloat16* img = p.x + static_cast<long long>(b) * p.H * p.W;
     for (int i = 0; i < p.kh; ++i) {
       const int hi = ho * p.sh - p.ph + i;
       if (hi < 0 || hi >= p.H) continue;
-      for (int j = 0; j < p.kw; ++j) {
-        const int wi = wo * p.sw - p.pw + j;
-        if (wi < 0 || wi >= p.W) continue;
-        const float xv = bf2f(img[hi * p.W + wi]);
-        const int tp = i * p.kw + j;
+      const __nv_bfloat16* row = img + static_cast<long long>(hi) * p.W;
+      float xin[FW_PIX + 2];
 #pragma unroll
-        for (int c = 0; c < CO; ++c) acc[c] = fmaf(xv, sw[c * taps + tp], acc[c]);
+      for (int u = 0; u < FW_PIX + 2; ++u) {
+        const int wi = wo0 - p.pw + u;
+        xin[u] = (wi >= 0 && wi < p.W) ? bf2f(row[wi]) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const float4* wv = reinterpret_cast<const float4*>(swt + (i * 3 + j) * CO);
+        const float4 w0 = wv[0], w1 = wv[1], w2 = wv[2], w3 = wv[3];
+        const float wl[CO] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+#pragma unroll
+        for (int px = 0; px < FW_PIX; ++px)
+#pragma unroll
+          for (int c = 0; c < CO; ++c) acc[px][c] = fmaf(xin[px + j], wl[c], acc[px][c]);
       }
     }
-    bf16x8* op = reinterpret_cast<bf16x8*>(p.y + m * CO);
-    op[0] = pack8(acc);
-    op[1] = pack8(acc + 8);
+    const long long m0 = (static_cast<long long>(b) * p.Ho + ho) * p.Wo + wo0;
+#pragma unroll
+    for (int px = 0; px < FW_PIX; ++px) {
+      if (wo0 + px < p.Wo) {
+        bf16x8* op = reinterpret_cast<bf16x8*>(p.y + (m0 + px) * CO);
+        op[0] = pack8(acc[px]);
+        op[1] = pack8(acc[px] + 8);
+      }
+    }
   }
 }
 
-// dw[co][tap] += sum_m dy[m][co] * x[pix(m, tap)]
-constexpr int WG_THREADS = 512;
-constexpr int WG_PIX = 128;
-__global__ void __launch_bounds__(WG_THREADS) stem_wgrad_kernel(const StemParams p) {
-  __shared__ float sdy[WG_PIX][CO];
-  __shared__ float sx[WG_PIX][MAX_TAPS + 1];
-  const int taps = p.kh * p.kw;
-  const int co = threadIdx.x / taps, tp = threadIdx.x - co * taps;
-  const bool active = threadIdx.x < CO * taps;
-  float acc = 0.f;
-  const long long chunks = (p.M + WG_PIX - 1) / WG_PIX;
-  for (long long ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
-    const long long m0 = ch * WG_PIX;
-    for (int i = threadIdx.x; i < WG_PIX * CO; i += WG_THREADS) {
-      const int pp = i / CO, c = i - pp * CO;
-      const long long m = m0 + pp;
-      sdy[pp][c] = m < p.M ? bf2f(p.dy[m * CO + c]) : 0.f;
+// dw[co][tap] += sum_m dy[m][co] * x[pix(m, tap)].  One warp per kernel row i, one lane per pixel: a lane reads the
+// 16 gradients of its pixel (2 x 16 B) and the 3 input samples of row i once for 48 FMAs; partial sums stay in
+// registers over all the pixels of the block and are reduced by warp shuffles at the end.
+__global__ void __launch_bounds__(320) stem_wgrad_kernel(const StemParams p) {
+  const int i = threadIdx.x >> 5, lane = threadIdx.x & 31;      // blockDim.x = 32 * kh
+  float acc[3][CO];
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int c = 0; c < CO; ++c) acc[j][c] = 0.f;
+  for (long long m = static_cast<long long>(blockIdx.x) * 32 + lane; m < p.M; m += static_cast<long long>(gridDim.x) * 32) {
+    const int wo = static_cast<int>(m % p.Wo); const long long t = m / p.Wo;
+    const int ho = static_cast<int>(t % p.Ho), b = static_cast<int>(t / p.Ho);
+    const int hi = ho * p.sh - p.ph + i;
+    if (hi < 0 || hi >= p.H) continue;
+    const bf16x8* gp = reinterpret_cast<const bf16x8*>(p.dy + m * CO);
+    float g[CO];
+    unpack8(gp[0], g); unpack8(gp[1], g + 8);
+    const __nv_bfloat16* row = p.x + (static_cast<long long>(b) * p.H + hi) * p.W;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int wi = wo - p.pw + j;
+      const float xv = (wi >= 0 && wi < p.W) ? bf2f(row[wi]) : 0.f;
+#pragma unroll
+      for (int c = 0; c < CO; ++c) acc[j][c] = fmaf(g[c], xv, acc[j][c]);
     }
-    for (int i = threadIdx.x; i < WG_PIX * taps; i += WG_THREADS) {
-      const int pp = i / taps, t2 = i - pp * taps;
-      const long long m = m0 + pp;
-      float v = 0.f;
-      if (m < p.M) {
-        const int wo = static_cast<int>(m % p.Wo); const long long t = m / p.Wo;
-        const int ho = static_cast<int>(t % p.Ho), b = static_cast<int>(t / p.Ho);
-        const int ki = t2 / p.kw, kj = t2 - ki * p.kw;
-        const int hi = ho * p.sh - p.ph + ki, wi = wo * p.sw - p.pw + kj;
-        if (hi >= 0 && hi < p.H && wi >= 0 && wi < p.W) v = bf2f(p.x[(static_cast<long long>(b) * p.H + hi) * p.W + wi]);
-      }
-      sx[pp][t2] = v;
-    }
-    __syncthreads();
-    if (active) {
-#pragma unroll 8
-      for (int pp = 0; pp < WG_PIX; ++pp) acc = fmaf(sdy[pp][co], sx[pp][tp], acc);
-    }
-    __syncthreads();
   }
-  if (active) atomicAdd(&p.dw[co * taps + tp], acc);
+  const int taps = p.kh * 3;
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int c = 0; c < CO; ++c) {
+      const float v = warp_sum(acc[j][c]);
+      if (lane == 0) atomicAdd(&p.dw[c * taps + i * 3 + j], v);
+    }
 }
 
 }  // namespace air_stem
@@ -106,9 +125,10 @@ extern "C" int air_stem_conv_fwd(const void* x, int B, int H, int W, int kh, int
                                  const float* w, int Cout, void* y, cudaStream_t stream) {
   StemParams p{};
   if (int e = stem_fill(p, x, B, H, W, kh, kw, sh, sw, ph, pw)) return e;
-  if (!w || !y || Cout != CO) return AIR_ERR_UNSUPPORTED;
+  if (!w || !y || Cout != CO || kw != 3 || sw != 1) return AIR_ERR_UNSUPPORTED;
   p.w = w; p.y = reinterpret_cast<__nv_bfloat16*>(y);
-  const int blocks = static_cast<int>(std::min<long long>((p.M + 255) / 256, 148 * 16));
+  const long long quads = static_cast<long long>(B) * p.Ho * ((p.Wo + FW_PIX - 1) / FW_PIX);
+  const int blocks = static_cast<int>(std::min<long long>((quads + 255) / 256, 148 * 16));
   stem_fwd_kernel<<<blocks, 256, 0, stream>>>(p);
   return air_launch_status();
 }
@@ -117,10 +137,10 @@ extern "C" int air_stem_conv_wgrad(const void* x, int B, int H, int W, int kh, i
                                    const void* dy, int Cout, float* dw, cudaStream_t stream) {
   StemParams p{};
   if (int e = stem_fill(p, x, B, H, W, kh, kw, sh, sw, ph, pw)) return e;
-  if (!dy || !dw || Cout != CO || CO * kh * kw > WG_THREADS) return AIR_ERR_UNSUPPORTED;
+  if (!dy || !dw || Cout != CO || kw != 3 || sw != 1 || kh > 10) return AIR_ERR_UNSUPPORTED;
   p.dy = reinterpret_cast<const __nv_bfloat16*>(dy); p.dw = dw;
-  const long long chunks = (p.M + WG_PIX - 1) / WG_PIX;
-  const int blocks = static_cast<int>(std::min<long long>(chunks, 148 * 2));
-  stem_wgrad_kernel<<<blocks, WG_THREADS, 0, stream>>>(p);
+  const long long chunks = (p.M + 31) / 32;
+  const int blocks = static_cast<int>(std::min<long long>(chunks, 148 * 6));
+  stem_wgrad_kernel<<<blocks, 32 * kh, 0, stream>>>(p);
   return air_launch_status();
 }

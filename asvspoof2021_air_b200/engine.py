@@ -126,12 +126,16 @@ class ConvLayer:
     def weight(self):
         return self.store.view(self.name + ".weight")
 
-    def pack(self):
+    def _pack_source(self):
         w = self.weight().reshape(self.cout, self.taps, self.cin)
         if self._wtmp is not None:                  # zero-padded input channels
             self._wtmp[:, :, :self.cin].copy_(w)
             w = self._wtmp
-        w = w.reshape(-1)
+        return w.reshape(-1)
+
+    def pack(self):
+        """Per-tensor launches (used when the layer is not part of a PackPlan)."""
+        w = self._pack_source()
         ops.pack_weights(w, 0, self.cin_g, self.cout, self.taps, self.wpk)
         if self.need_dgrad:
             ops.pack_weights(w, 1, self.cin_g, self.cout, self.taps, self.wpk_d)
@@ -139,6 +143,20 @@ class ConvLayer:
             ops.pack_patch(w, self.cin, self.cout, self.taps, 0, self.wpk3)
         if self.wpk3_d is not None:
             ops.pack_patch(w, self.cout, self.cin, self.taps, 1, self.wpk3_d)
+
+    def add_pack_jobs(self, plan):
+        """Register this layer's packings in a batched PackPlan; returns False when the layer needs its own path."""
+        if self._wtmp is not None:
+            return False
+        w = self.weight().reshape(-1)
+        plan.add_gemm(w, self.taps * self.cin_g, 0, self.cin_g, self.cout, self.taps, self.wpk)
+        if self.need_dgrad:
+            plan.add_gemm(w, self.taps * self.cin_g, 1, self.cin_g, self.cout, self.taps, self.wpk_d)
+        if self.wpk3 is not None:
+            plan.add_patch(w, self.cin, self.cout, self.taps, 0, self.wpk3)
+        if self.wpk3_d is not None:
+            plan.add_patch(w, self.cout, self.cin, self.taps, 1, self.wpk3_d)
+        return True
 
     def fprop(self, x, x_ld, B, H, W, out, out_ld, res=None, res_ld=0, relu=False):
         Ho, Wo = self.out_hw(H, W)
@@ -439,7 +457,11 @@ class ResNetEngine:
         return out + [("bn5", self.bn5)]
 
     def pack_weights(self):
-        for c in self.convs():
+        if getattr(self, "_pack_plan", None) is None:
+            self._pack_plan = ops.PackPlan(self.device)
+            self._pack_rest = [c for c in self.convs() if not c.add_pack_jobs(self._pack_plan)]
+        self._pack_plan.run()
+        for c in self._pack_rest:
             c.pack()
         self._packed_version = self.store.step
 

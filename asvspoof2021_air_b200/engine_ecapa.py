@@ -176,7 +176,11 @@ class EcapaEngine:
         return out
 
     def pack_weights(self):
-        for c in self.convs():
+        if getattr(self, "_pack_plan", None) is None:
+            self._pack_plan = ops.PackPlan(self.device)
+            self._pack_rest = [c for c in self.convs() if not c.add_pack_jobs(self._pack_plan)]
+        self._pack_plan.run()
+        for c in self._pack_rest:
             c.pack()
         w = self.store.view("attention.0.weight")                       # [128][1][4608]
         ops.pack_weights_ld(w, 3 * self.C3, 0, self.C3, 128, 1, self.att0_wpk)

@@ -82,6 +82,43 @@ def pack_patch(w, C, N, taps, mode, out):
     return out
 
 
+class PackPlan:
+    """Batched weight packing: collect the (source view, destination buffer, layout) jobs of a model once, then
+    re-pack all of them with ONE launch per optimiser step (csrc/pack.cu)."""
+
+    def __init__(self, device):
+        self.device, self.records, self.keep, self.table, self.max_total = device, [], [], None, 0
+
+    def _rec(self):
+        return (ctypes.c_longlong * 16)()
+
+    def add_gemm(self, w, w_ld, mode, cin, cout, taps, out):
+        n, k = (cout, taps * cin) if mode == 0 else (cin, taps * cout)
+        r = self._rec()
+        _lib.check(_lib.lib().air_pack_job_gemm(r, _lib.ptr(w), _lib.LL(w_ld), _lib.ptr(out), n, k, mode, cin, cout, taps),
+                   "air_pack_job_gemm", 0)
+        self._push(r, w, out)
+
+    def add_patch(self, w, C, N, taps, mode, out):
+        r = self._rec()
+        _lib.check(_lib.lib().air_pack_job_patch(r, _lib.ptr(w), _lib.ptr(out), C, N, taps, mode), "air_pack_job_patch", 0)
+        self._push(r, w, out)
+
+    def _push(self, r, w, out):
+        self.records.append(list(r))
+        self.keep.append((w, out))          # the table holds raw pointers: keep the tensors alive
+        self.max_total = max(self.max_total, int(r[3]))
+        self.table = None
+
+    def run(self):
+        if not self.records:
+            return
+        if self.table is None:
+            self.table = torch.tensor(self.records, dtype=torch.int64, device=self.device)
+        _lib.check(_lib.lib().air_pack_jobs(_lib.ptr(self.table), len(self.records), _lib.LL(self.max_total),
+                                            _lib.stream_ptr()), "air_pack_jobs")
+
+
 _ONE_TAP = (ctypes.c_int * 1)(0)
 
 
@@ -432,3 +469,4 @@ pack_patch = _timed(pack_patch, "pack_weights")
 conv1x1_patch = _timed(conv1x1_patch, lambda a: "conv_dgrad" if (len(a) > 13 and a[13] == 1) else "conv_fprop",
                        lambda a: 2.0 * a[2] * a[3] * a[4] * a[5] * a[7])
 conv_s2_dgrad_patch = _timed(conv_s2_dgrad_patch, "conv_dgrad", lambda a: 2.0 * a[2] * a[3] * a[4] * a[5] * a[8] * a[7] * a[7])
+PackPlan.run = _timed(PackPlan.run, "pack_weights")

@@ -108,6 +108,15 @@ int air_conv3x3_patch_bf16(const void* a, long long a_ld, int B, int H, int W, i
                            const void* wpk, int N, void* out, long long out_ld,
                            const void* res, long long res_ld, int relu, int num_sms, air_stream_t stream);
 
+/* Batched weight packing (csrc/pack.cu): one launch re-packs every convolution weight of a model from a
+ * device-resident table of 16 x int64 job records.  air_pack_job_* fill ONE host-side record with the same arguments
+ * as air_conv_pack_weights_ld / air_conv_patch_pack_weights; the caller uploads the table once and calls air_pack_jobs
+ * after every optimiser step.  max_total = largest packed element count among the jobs (record field 3). */
+int air_pack_job_gemm(long long* rec, const float* w, long long w_ld, void* dst, int N, int K, int mode,
+                      int Cin, int Cout, int taps);
+int air_pack_job_patch(long long* rec, const float* w, void* dst, int C, int N, int taps, int mode);
+int air_pack_jobs(const long long* jobs, int njobs, long long max_total, air_stream_t stream);
+
 /* General form of the patch kernel: explicit tap table and output pixel mapping
  *   out[b, g*osh+oph, g'*osw+opw, n] = sum_t sum_c a[b, g+org_h+tap_dr[t], g'+org_w+tap_dc[t], c] * Wp[tap_slice[t]][n][c] (+res)(ReLU)
  * over the item grid g < GH, g' < GW (0 <= tap_dr, tap_dc <= 2; out-of-range reads are zero).  wpk holds wtaps slices

@@ -263,3 +263,30 @@ def test_patch_conv1x1(shape):
     ops.conv1x1_patch(dy, Cout, B, H, W, Cout, wpk_d, Cin, dx, Cin, None, 0, False, 1)
     torch.cuda.synchronize()
     _check(dx.float(), dy.float() @ w.to(torch.bfloat16).float(), "1x1 patch dgrad")
+
+
+def test_batched_pack_plan_matches_per_tensor_packing():
+    """csrc/pack.cu: one launch over a job table == the per-tensor packing kernels, bit for bit."""
+    from asvspoof2021_air_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(23)
+    plan = ops.PackPlan(torch.device("cuda"))
+    checks = []
+    for cin, cout, taps in ((64, 64, 9), (16, 64, 9), (128, 256, 9), (64, 128, 1), (512, 256, 9)):
+        w = torch.randn(cout, taps, cin, generator=g).cuda().reshape(-1)
+        for mode in (0, 1):
+            n, k = (cout, taps * cin) if mode == 0 else (cin, taps * cout)
+            ref = ops.pack_weights(w, mode, cin, cout, taps)
+            out = torch.zeros_like(ref)
+            plan.add_gemm(w, taps * cin, mode, cin, cout, taps, out)
+            checks.append((ref, out))
+            C, N = (cin, cout) if mode == 0 else (cout, cin)
+            if ops.patch_supported(C, N, 1, 1):
+                ref3 = torch.zeros(taps * cin * cout, device="cuda", dtype=torch.bfloat16)
+                ops.pack_patch(w, C, N, taps, mode, ref3)
+                out3 = torch.zeros_like(ref3)
+                plan.add_patch(w, C, N, taps, mode, out3)
+                checks.append((ref3, out3))
+    plan.run()
+    torch.cuda.synchronize()
+    for ref, out in checks:
+        assert torch.equal(ref, out)
