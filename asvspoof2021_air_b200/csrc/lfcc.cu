@@ -278,6 +278,19 @@ __global__ void lfcc_fill_kernel(const Params p) {
 
 }  // namespace air_lfcc
 
+// rows that no source frame maps to (zero tail / silence head); shared with the tensor-core path (lfcc_tc.cu)
+extern "C" int air_lfcc_fill(const int* lengths, int B, int L, void* out, long long sb, long long sj, long long sd,
+                             int out_bf16, int Tout, int feat_len, int pad_mode, const float* silence, cudaStream_t stream) {
+  using namespace air_lfcc;
+  if (!out || B <= 0 || feat_len <= 0 || (pad_mode != 1 && pad_mode != 3)) return AIR_ERR_ARG;
+  Params p{};
+  p.lengths = lengths; p.L = L; p.B = B; p.out = out; p.sb = sb; p.sj = sj; p.sd = sd; p.out_bf16 = out_bf16;
+  p.time_minor = (sj == 1); p.Tout = Tout; p.feat_len = feat_len; p.pad_mode = pad_mode; p.silence = silence;
+  dim3 g2(8, B);
+  lfcc_fill_kernel<<<g2, 256, 0, stream>>>(p);
+  return air_launch_status();
+}
+
 extern "C" int air_lfcc_table_floats() { return air_lfcc::TBL_FLOATS; }
 
 extern "C" int air_lfcc_fwd(const float* wave, long long ldw, const int* lengths, int B, int L,

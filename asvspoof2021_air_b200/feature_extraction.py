@@ -8,6 +8,7 @@ for the first conv of ResNet / ECAPA (main_train.py:338,347-348) so raw waves go
 device.  There is no CPU implementation: inputs must live on a CUDA device.
 """
 import ctypes
+import os
 
 import torch
 import torch.nn as nn
@@ -40,6 +41,9 @@ class LFCC(nn.Module):
         self.l_dct = _FrozenDCT(filter_num)
         self._table = None
         self._silence = None
+        self._tc = None
+        # "tc": tensor-core DFT path (csrc/lfcc_tc.cu, default); "fft": radix-FFT path on CUDA cores (csrc/lfcc.cu)
+        self.impl = os.environ.get("AIR_LFCC_IMPL", "tc")
 
     # -- constants -------------------------------------------------------------------------
     def _consts(self, device):
@@ -47,6 +51,15 @@ class LFCC(nn.Module):
             self._table = lfcc_tables.pack_table(self.lfcc_fb, self.l_dct.weight).to(device)
             self._silence = None
         return self._table
+
+    def _tc_consts(self, device):
+        """Tables of the tensor-core path, or None when the filterbank buffer does not have the canonical band structure."""
+        if self._tc is None or self._tc[0].device != device:
+            if not lfcc_tables.tc_filter_structure_ok(self.lfcc_fb):
+                return None
+            self._tc = (lfcc_tables.pack_tc_table(self.lfcc_fb, self.l_dct.weight).to(device),
+                        lfcc_tables.pack_tc_dft().to(device))
+        return self._tc
 
     def num_frames(self, length):
         return 1 + length // self.fs
@@ -88,6 +101,16 @@ class LFCC(nn.Module):
         if start is not None:
             start = start.to(device=dev, dtype=torch.int32).contiguous()
         sil = self.silence_vector(dev) if (feat_len > 0 and pad_mode == 3) else None
+        tc = self._tc_consts(dev) if self.impl == "tc" else None
+        if tc is not None:
+            st = _lib.lib().air_lfcc_tc_fwd(
+                _lib.ptr(x), _lib.LL(x.stride(0)), _lib.ptr(lengths), B, L, _lib.ptr(tc[0]), _lib.ptr(tc[1]),
+                _lib.ptr(out), _lib.LL(sb), _lib.LL(sj), _lib.LL(sd), int(dtype == torch.bfloat16),
+                Tout, feat_len, pad_mode, _lib.ptr(start), _lib.ptr(sil),
+                ctypes.c_float(0.97 if self.with_emphasis else 0.0),
+                torch.cuda.get_device_properties(dev).multi_processor_count, _lib.stream_ptr())
+            _lib.check(st, "air_lfcc_tc_fwd")
+            return out
         table = self._consts(dev)
         st = _lib.lib().air_lfcc_fwd(
             _lib.ptr(x), _lib.LL(x.stride(0)), _lib.ptr(lengths), B, L, _lib.ptr(table),

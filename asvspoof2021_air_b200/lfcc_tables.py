@@ -91,3 +91,63 @@ def pack_table(lfcc_fb: torch.Tensor, dct_weight: torch.Tensor, fl=FL) -> torch.
     for kk in range(NF):
         tbl[OFF_DCT + kk * 21:OFF_DCT + kk * 21 + NF] = d[kk]
     return torch.from_numpy(tbl)
+
+
+# ---------------------------------------------------------------------------------------------
+# tables of the tensor-core path (csrc/lfcc_tc.cu)
+# ---------------------------------------------------------------------------------------------
+TC_OFF_WIN, TC_OFF_FBW, TC_OFF_DCT = 0, 320, 320 + 512
+TC_TBL_FLOATS = TC_OFF_DCT + NF * NF
+TC_KBLK, TC_CHUNK_ELEMS = 5, 128 * 32
+
+
+def tc_filter_structure_ok(lfcc_fb) -> bool:
+    """The kernel hard-codes WHICH filters a bin feeds (floor(21k/256)-1 and floor(21k/256), the support of the
+    reference's trimf bands, feature_extraction.py:77-85) and takes the weights from the module's buffer."""
+    fb = lfcc_fb.detach().cpu().float().numpy()
+    if fb.shape != (FN // 2 + 1, NF) or np.count_nonzero(fb[0]) or np.count_nonzero(fb[256]):
+        return False
+    for k in range(1, 256):
+        fh = (21 * k) >> 8
+        if not set(np.nonzero(fb[k])[0].tolist()) <= {fh - 1, fh}:
+            return False
+    return True
+
+
+def pack_tc_table(lfcc_fb: torch.Tensor, dct_weight: torch.Tensor) -> torch.Tensor:
+    """fp32 table: periodic Hamming window (feature_extraction.py:110), per-bin filter weight pairs, DCT matrix."""
+    assert tc_filter_structure_ok(lfcc_fb)
+    fb = lfcc_fb.detach().cpu().float().numpy()
+    tbl = np.zeros(TC_TBL_FLOATS, dtype=np.float32)
+    tbl[TC_OFF_WIN:TC_OFF_WIN + FL] = torch.hamming_window(FL).numpy()
+    for k in range(1, 256):
+        fh = (21 * k) >> 8
+        if fh - 1 >= 0:
+            tbl[TC_OFF_FBW + 2 * k] = fb[k, fh - 1]
+        if fh < NF:
+            tbl[TC_OFF_FBW + 2 * k + 1] = fb[k, fh]
+    tbl[TC_OFF_DCT:TC_OFF_DCT + NF * NF] = dct_weight.detach().cpu().float().numpy().reshape(-1)
+    return torch.from_numpy(tbl)
+
+
+def pack_tc_dft() -> torch.Tensor:
+    """bf16 hi/lo split of the folded real-DFT matrices cos / sin (2 pi k m / 512), k = 1..256, m = 0..159, as
+    pre-swizzled (SWIZZLE_64B, K-major) [128 bins][32 samples] operand chunks in MMA order [Re/Im][half][kb][hi/lo]."""
+    k = np.arange(1, 257, dtype=np.float64)[:, None]
+    m = np.arange(160, dtype=np.float64)[None, :]
+    ang = 2.0 * math.pi * k * m / 512.0
+    out = torch.zeros(2, 2, TC_KBLK, 2, TC_CHUNK_ELEMS, dtype=torch.bfloat16)
+    n = np.arange(128)[:, None]
+    kk = np.arange(32)[None, :]
+    off = n * 64 + kk * 2
+    idx = torch.from_numpy(((off ^ (((off >> 7) & 3) << 4)) >> 1).reshape(-1).astype(np.int64))
+    for part, mat in enumerate((np.cos(ang), np.sin(ang))):
+        full = torch.from_numpy(mat.astype(np.float32))
+        hi = full.to(torch.bfloat16)
+        lo = (torch.from_numpy(mat) - hi.double()).float().to(torch.bfloat16)
+        for h in range(2):
+            for kb in range(TC_KBLK):
+                for which, src in enumerate((hi, lo)):
+                    blk = src[128 * h:128 * h + 128, 32 * kb:32 * kb + 32].reshape(-1)
+                    out[part, h, kb, which, idx] = blk
+    return out.reshape(-1)

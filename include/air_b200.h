@@ -53,6 +53,21 @@ int air_lfcc_fwd(const float* wave, long long ldw, const int* lengths, int B, in
                  int out_bf16, int Tout, int feat_len, int pad_mode, const int* start,
                  const float* silence, float preemph, int fseg, air_stream_t stream);
 
+/* Tensor-core path of the same front-end (csrc/lfcc_tc.cu): the 512-point spectrum of feature_extraction.py:109-113 as
+ * a folded real DFT on tcgen05 (bf16 hi/lo 3-term split, fp32 accumulation in TMEM; deviation <= 1e-5*(|ref|+1)).
+ * Same arguments as air_lfcc_fwd except the tables: `table` = air_lfcc_tc_table_floats() floats (window, per-bin
+ * filter weight pairs, DCT), `wmat` = air_lfcc_tc_wmat_elems() bf16 (pre-swizzled DFT operand chunks); both are built
+ * by lfcc_tables.pack_tc_table / pack_tc_dft from the module's registered buffers. */
+int air_lfcc_tc_table_floats(void);
+int air_lfcc_tc_wmat_elems(void);
+int air_lfcc_tc_fwd(const float* wave, long long ldw, const int* lengths, int B, int L,
+                    const float* table, const void* wmat, void* out, long long sb, long long sj, long long sd,
+                    int out_bf16, int Tout, int feat_len, int pad_mode, const int* start,
+                    const float* silence, float preemph, int num_sms, air_stream_t stream);
+/* rows of a padded output that no source frame maps to (zero tail / silence head; dataset.py:513-528) */
+int air_lfcc_fill(const int* lengths, int B, int L, void* out, long long sb, long long sj, long long sd,
+                  int out_bf16, int Tout, int feat_len, int pad_mode, const float* silence, air_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution on tcgen05 tensor cores (bf16 in, fp32 accumulate in TMEM).
  * Replaces nn.Conv2d / nn.Conv1d forward and data-gradient (cuDNN in the reference:

@@ -96,3 +96,70 @@ def lfcc_emulated(wave, tbl):
         out[t, 20:40] = c[tp] - c[tm]
         out[t, 40:] = (c[cl(tp + 1)] - c[cl(tp - 1)]) - (c[cl(tm + 1)] - c[cl(tm - 1)])
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# tensor-core path (csrc/lfcc_tc.cu): folded real DFT with a 3-term bf16 hi/lo split, emulated from the PACKED tables
+# ---------------------------------------------------------------------------------------------------
+def _bf16(x):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(torch.bfloat16).float().numpy()
+
+
+def unpack_tc_dft(wmat):
+    """Inverse of lfcc_tables.pack_tc_dft: -> (C_hi, C_lo, S_hi, S_lo), each (256 bins k=1..256, 160 samples) float32."""
+    w = wmat.float().numpy().reshape(2, 2, lt.TC_KBLK, 2, 128, 64 // 2)      # [part][h][kb][which][flat 4096] viewed later
+    w = wmat.float().numpy().reshape(2, 2, lt.TC_KBLK, 2, lt.TC_CHUNK_ELEMS)
+    n = np.arange(128)[:, None]
+    kk = np.arange(32)[None, :]
+    off = n * 64 + kk * 2
+    idx = (off ^ (((off >> 7) & 3) << 4)) >> 1
+    mats = np.zeros((2, 2, 256, 160), dtype=np.float32)                        # [part][which][k][m]
+    for part in range(2):
+        for h in range(2):
+            for kb in range(lt.TC_KBLK):
+                for which in range(2):
+                    mats[part, which, 128 * h:128 * h + 128, 32 * kb:32 * kb + 32] = w[part, h, kb, which][idx]
+    return mats[0, 0], mats[0, 1], mats[1, 0], mats[1, 1]
+
+
+def lfcc_tc_emulate(wave, tbl, wmat, preemph=0.97):
+    """(B, L) float32 -> (B, T, 20) cepstra with the arithmetic of the tensor-core kernel (fp32 accumulation emulated
+    by float64 sums rounded once, which only makes this emulation slightly MORE exact than the device)."""
+    tbl = np.asarray(tbl, dtype=np.float32)
+    win = tbl[lt.TC_OFF_WIN:lt.TC_OFF_WIN + 320]
+    fbw = tbl[lt.TC_OFF_FBW:lt.TC_OFF_FBW + 512].reshape(256, 2)
+    dct = tbl[lt.TC_OFF_DCT:lt.TC_OFF_DCT + 400].reshape(20, 20)
+    Chi, Clo, Shi, Slo = (m.astype(np.float64) for m in unpack_tc_dft(wmat))
+    wave = np.asarray(wave, dtype=np.float32)
+    B, L = wave.shape
+    T = 1 + L // 160
+    y = wave.copy()
+    y[:, 1:] = wave[:, 1:] - np.float32(preemph) * wave[:, :-1]
+    ypad = np.zeros((B, 160 * (T + 2)), np.float32)
+    ypad[:, 160:160 + L] = y
+    kbin = np.arange(1, 257)
+    c160 = np.cos(5 * np.pi * (kbin % 16) / 8).astype(np.float32)
+    s160 = np.sin(5 * np.pi * (kbin % 16) / 8).astype(np.float32)
+    mm = np.arange(1, 160)
+    out = np.zeros((B, T, 20), np.float32)
+    for t in range(T):
+        a = ypad[:, 160 * t:160 * t + 320] * win
+        e = np.zeros((B, 160), np.float32)
+        o = np.zeros((B, 160), np.float32)
+        e[:, 0] = a[:, 160]
+        e[:, 1:] = a[:, 160 + mm] + a[:, 160 - mm]
+        o[:, 1:] = a[:, 160 + mm] - a[:, 160 - mm]
+        ehi, ohi = _bf16(e), _bf16(o)
+        elo, olo = _bf16(e - ehi), _bf16(o - ohi)
+        re = (ehi @ Chi.T + elo @ Chi.T + ehi @ Clo.T).astype(np.float32) + a[:, :1] * c160
+        im = (ohi @ Shi.T + olo @ Shi.T + ohi @ Slo.T).astype(np.float32) - a[:, :1] * s160
+        P = re * re + im * im
+        fb = np.zeros((B, 22), np.float32)
+        for k in range(1, 256):
+            fh = (21 * k) >> 8
+            fb[:, fh] += fbw[k, 0] * P[:, k - 1]
+            fb[:, fh + 1] += fbw[k, 1] * P[:, k - 1]
+        fbe = np.log10(fb[:, 1:21] + np.float32(1.1920929e-07))
+        out[:, t] = fbe @ dct.T
+    return out

@@ -14,10 +14,14 @@ from tolerances import lfcc_close, lfcc_worst
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def mod():
+@pytest.fixture(scope="module", params=["tc", "fft"])
+def mod(request):
+    """Both device implementations: "tc" = tensor-core folded DFT (csrc/lfcc_tc.cu, the default), "fft" = radix FFT on
+    CUDA cores (csrc/lfcc.cu)."""
     from asvspoof2021_air_b200.feature_extraction import LFCC
-    return LFCC(320, 160, 512, 16000, 20).cuda()
+    m = LFCC(320, 160, 512, 16000, 20).cuda()
+    m.impl = request.param
+    return m
 
 
 @pytest.fixture(scope="module")

@@ -158,3 +158,19 @@ def test_state_specs_match_reference_modules():
     e = ec.Res2Net2(ec.Bottle2neck, C=512, model_scale=8, nOut=2, n_mels=60)
     assert [(k, tuple(v.shape)) for k, v in e.state_dict().items()] == [(k, s) for k, s, _ in ss.ecapa_spec()]
     assert len(ss.resnet_spec()) == 117 and len(ss.ecapa_spec()) == 248
+
+
+def test_tensor_core_lfcc_algorithm_and_tables_on_cpu():
+    """The folded real DFT with the 3-term bf16 split of csrc/lfcc_tc.cu, emulated from the PACKED device tables
+    (pre-swizzled DFT chunks, per-bin filter pairs), meets the fp32 LFCC tolerance against the float64 oracle."""
+    import lfcc_emulation as em
+    from asvspoof2021_air_b200 import lfcc_tables as lt
+    from tolerances import lfcc_close, lfcc_worst
+    fb, dct = lt.linear_filterbank(512, 16000, 20), lt.dct_ortho_matrix(20)
+    assert lt.tc_filter_structure_ok(fb)
+    tbl, wmat = lt.pack_tc_table(fb, dct), lt.pack_tc_dft()
+    w = ss.seeded_waves(2, 4000, seed=3, edge_rows=True).numpy()
+    got = em.lfcc_tc_emulate(w, tbl.numpy(), wmat)
+    want = lo.lfcc(w)[:, :, :20]
+    assert lfcc_close(got, want).all(), lfcc_worst(got, want)
+    assert lfcc_worst(got, want) < 2e-5
