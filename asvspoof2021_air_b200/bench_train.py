@@ -108,8 +108,16 @@ def run(args, rank, world, helpers):
     achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
     peak = peaks["bf16_tflops_sustained"]
     breakdown = {k: {"ms_per_step": round(v["ms"] / nprof, 4), "launches_per_step": v["launches"] // nprof,
-                     **({"tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1)} if v["flops"] else {})}
+                     **({"tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1)} if v["flops"] else {}),
+                     **({"gbs": round(v["bytes"] / (v["ms"] / 1e3) / 1e9, 1)} if v["bytes"] else {})}
                  for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
+    lf = fam.get("lfcc")
+    lfcc_roof = None
+    if lf and lf["ms"] > 0:
+        gbs = lf["bytes"] / (lf["ms"] / 1e3) / 1e9
+        lfcc_roof = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                     "kernel": "air_lfcc_tc::lfcc_tc_kernel (fused wave -> padded bf16 model-layout LFCC, inside the step)",
+                     "bytes_per_launch": lf["bytes"] / nprof, "ms_per_step": lf["ms"] / nprof}
     flops_per_utt = (FWD_FLOPS_PER_UTT if scoring else TRAIN_FLOPS_PER_UTT)[arch]
     name = {"resnet": "ResNet-18-OC", "ecapa": "ECAPA-TDNN-512"}[arch]
     line = {
@@ -124,10 +132,13 @@ def run(args, rank, world, helpers):
                    "l2": "per-step activations (> 4 GB) exceed the 126 MB L2; waves rotate over %d buffers" % nbuf},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak if peak else None, "traffic": None, "peak_src": peaks["src"] + " (sustained)",
-                     "kernel": "conv stack: air_gemm::conv_gemm_kernel (fprop+dgrad) + air_wgrad::conv_wgrad_kernel",
+                     "kernel": "conv stack (all tcgen05): air_patch::conv_patch_kernel (3x3 / 1x1 fprop + dgrad, stride-2 dgrad "
+                               "by parity), air_wpatch::conv3x3_wgrad_patch_kernel, air_gemm::conv_gemm_kernel, "
+                               "air_wgrad::conv_wgrad_kernel",
                      "flops_per_step": conv_flops / nprof, "conv_ms_per_step": conv_ms / nprof,
                      "conv_share_of_step": conv_ms / total_ms if total_ms else None,
                      "whole_step_tflops": B * flops_per_utt / (ms / args.steps / 1e3) / 1e12},
+        "roofline_lfcc": lfcc_roof,
         "kernels": breakdown,
         "e2e": {"value": e2e, "unit": "utterances/s", "h2d_bytes_per_step": B * WAVE_LEN * 4,
                 "d2h_bytes_per_step": int(res_host.numel()) * 4, "ms_per_step": ms_e2e / args.steps},

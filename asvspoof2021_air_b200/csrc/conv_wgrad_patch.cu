@@ -26,12 +26,12 @@ namespace air_wpatch {
 using namespace tc05;
 
 constexpr int TW = 128, PW = TW + 2, R = 2, PR = R + 2, PPIX = PR * PW;
+constexpr int NACC = 5;                             // wide 3x3: tap pairs (0,1) (2,3) (4,5) (6,7) (8,-); narrow 3x3: 3 tap rows
 constexpr int THREADS = 256;
 constexpr int STAGES = 2;
 constexpr uint32_t X_BYTES = PPIX * 128;            // 66 560 = 65 * 1024
 constexpr uint32_t DY_BYTES = R * TW * 128;         // 32 768
 constexpr uint32_t STAGE_BYTES = X_BYTES + DY_BYTES;
-constexpr int NACC = 5;                             // tap pairs (0,1) (2,3) (4,5) (6,7) (8,-)
 constexpr int ACC_COLS = 64;
 
 struct WParams {
@@ -40,6 +40,12 @@ struct WParams {
   int NCB, NNB, WT, HP;
   uint32_t items;                                   // B * HP * WT
   int parts;                                        // CTAs per job
+  // operand geometry: "wide" = 64 input channels per pixel row (SWIZZLE_128B, two 64-row groups per M = 128),
+  // "narrow" = 16 input channels (SWIZZLE_32B, eight 16-row groups = eight consecutive pixel shifts per M = 128)
+  int narrow, ktaps, org;                           // ktaps = 9 (3x3 / pad 1, org = -1) or 1 (1x1 / pad 0, org = 0)
+  uint32_t x_bytes, stage_bytes;
+  int nacc; int acc_off[NACC]; int acc_lbo[NACC];   // per accumulator: window offset / group distance, in patch pixels
+  int acc_tap[NACC][8];                             // tap of each M row group (-1: not a real tap)
 };
 
 __global__ void __launch_bounds__(THREADS, 1) conv3x3_wgrad_patch_kernel(const __grid_constant__ CUtensorMap tmx,
@@ -49,7 +55,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_wgrad_patch_kernel(const _
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (sbase - smem_u32(smem_raw));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(gen + STAGES * STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gen + STAGES * p.stage_bytes);
   uint64_t* full = bars;                 // [STAGES] expect_tx
   uint64_t* empty = bars + STAGES;       // [STAGES] tcgen05.commit
   uint64_t* tfull = bars + 2 * STAGES;   // [1]
@@ -83,39 +89,41 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_wgrad_patch_kernel(const _
         const uint32_t wt = item % WT, r1 = item / WT;
         const int w0 = static_cast<int>(wt) * TW, h0 = static_cast<int>(r1 % HP) * R, b = static_cast<int>(r1 / HP);
         mbar_wait(&empty[stage], phase ^ 1);
-        const uint32_t dst = sbase + stage * STAGE_BYTES;
-        mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
-        tma_load_4d(dst, &tmx, cb * 64, w0 - 1, h0 - 1, b, &full[stage]);
-        tma_load_4d(dst + X_BYTES, &tmdy, nb * 64, w0, h0, b, &full[stage]);
+        const uint32_t dst = sbase + stage * p.stage_bytes;
+        mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>(PPIX) * (p.narrow ? 32u : 128u) + DY_BYTES);
+        tma_load_4d(dst, &tmx, p.narrow ? 0 : cb * 64, w0 + p.org, h0 + p.org, b, &full[stage]);
+        tma_load_4d(dst + p.x_bytes, &tmdy, nb * 64, w0, h0, b, &full[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 2) {
     const bool leader = elect_one();
     const uint32_t idesc = instr_desc_bf16(128, ACC_COLS, 1, 1);
-    // descriptor high word: SBO = 1024 B (next 8 pixels), version 1, SWIZZLE_128B
-    const uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    // descriptor high words: SBO = next 8 pixels, version 1, swizzle mode (A: 128 B or 32 B rows; B: always 128 B rows)
+    const uint32_t b_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t a_hi = p.narrow ? ((256u >> 4) | (1u << 14) | (6u << 29)) : b_hi;
+    const uint32_t upp = p.narrow ? 2u : 8u;              // 16-byte units per patch pixel
     uint32_t stage = 0, phase = 0;
     for (uint32_t k = 0; k < my_items; ++k) {
       mbar_wait(&full[stage], phase);
       fence_after_sync();
-      const uint32_t x16 = ((sbase + stage * STAGE_BYTES) >> 4) & 0x3FFF;      // 16-byte units; one pixel row = 8 units
-      const uint32_t d16 = x16 + (X_BYTES >> 4);
+      const uint32_t x16 = ((sbase + stage * p.stage_bytes) >> 4) & 0x3FFF;
+      const uint32_t d16 = x16 + (p.x_bytes >> 4);
 #pragma unroll
       for (int r = 0; r < R; ++r) {
 #pragma unroll 2
         for (int ks = 0; ks < TW / 16; ++ks) {
           const uint32_t b_lo = (d16 + static_cast<uint32_t>(r * TW + ks * 16) * 8) | (1u << 16);
-          const uint64_t bd = (static_cast<uint64_t>(desc_hi) << 32) | b_lo;
-          const uint32_t xrow = x16 + static_cast<uint32_t>(r * PW + ks * 16) * 8;
+          const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | b_lo;
+          const uint32_t xrow = x16 + static_cast<uint32_t>(r * PW + ks * 16) * upp;
 #pragma unroll
           for (int a = 0; a < NACC; ++a) {
-            const int t0 = 2 * a, t1 = (2 * a + 1 < 9) ? 2 * a + 1 : 2 * a;
-            const int o0 = (t0 / 3) * PW + (t0 % 3), o1 = (t1 / 3) * PW + (t1 % 3);
-            // LBO = distance between the windows of the two taps (in 16-byte units, 8 per pixel)
-            const uint32_t a_lo = (xrow + static_cast<uint32_t>(o0) * 8) | (static_cast<uint32_t>((o1 - o0) * 8) << 16);
-            const uint64_t ad = (static_cast<uint64_t>(desc_hi) << 32) | a_lo;
-            if (leader) mma_bf16(tmem_base + a * ACC_COLS, ad, bd, idesc, (k | static_cast<uint32_t>(r) | static_cast<uint32_t>(ks)) != 0);
+            if (a < p.nacc) {
+              // LBO = distance between the windows of consecutive M row groups
+              const uint32_t a_lo = (xrow + static_cast<uint32_t>(p.acc_off[a]) * upp) | ((static_cast<uint32_t>(p.acc_lbo[a]) * upp) << 16);
+              const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | a_lo;
+              if (leader) mma_bf16(tmem_base + a * ACC_COLS, ad, bd, idesc, (k | static_cast<uint32_t>(r) | static_cast<uint32_t>(ks)) != 0);
+            }
           }
         }
       }
@@ -130,14 +138,16 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_wgrad_patch_kernel(const _
       mbar_wait(tfull, 0);
       fence_after_sync();
       const int q = warp & 3;
-      const int ci = cb * 64 + (q & 1) * 32 + lane;
-      for (int a = 0; a < NACC; ++a) {
-        const int tap = 2 * a + (q >> 1);
+      const int m = q * 32 + lane;                       // M row of the accumulator = TMEM lane
+      const int grp = p.narrow ? (m >> 4) : (m >> 6);
+      const int ci = p.narrow ? (m & 15) : (cb * 64 + (m & 63));
+      for (int a = 0; a < p.nacc; ++a) {
+        const int tap = p.acc_tap[a][grp];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * ACC_COLS;
         for (int c0 = 0; c0 < ACC_COLS; c0 += 16) {
           float v[16];
           tmem_ld16(taddr + c0, v);
-          if (tap < 9) {
+          if (tap >= 0) {
             float* dst = p.dw + static_cast<long long>(nb * 64 + c0) * p.dw_ld + static_cast<long long>(tap) * p.C + ci;
 #pragma unroll
             for (int i = 0; i < 16; ++i) atomicAdd(dst + static_cast<long long>(i) * p.dw_ld, v[i]);
@@ -156,21 +166,47 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_wgrad_patch_kernel(const _
 
 using namespace air_wpatch;
 
-extern "C" int air_conv3x3_wgrad_patch_supported(int C, int N) {
-  return (C >= 64 && C % 64 == 0 && N >= 64 && N % 64 == 0 && (C / 64) * (N / 64) <= 148) ? 1 : 0;
+static bool wpatch_ok(int C, int N) {
+  return (C == 16 || (C >= 64 && C % 64 == 0)) && N >= 64 && N % 64 == 0 && (C == 16 ? 1 : C / 64) * (N / 64) <= 148;
 }
 
-// dw_out: fp32 [N][dw_ld >= 9*C] in GEMM layout [Cout][tap][Cin], accumulated in place (caller zeroes).
-extern "C" int air_conv3x3_wgrad_patch_bf16(const void* x, long long x_ld, int B, int H, int W, int C,
-                                            const void* dy, long long dy_ld, int N,
-                                            float* dw_out, long long dw_ld, int num_sms, cudaStream_t stream) {
-  if (!x || !dy || !dw_out || B <= 0 || H < 1 || W < 1) return AIR_ERR_ARG;
-  if (!air_conv3x3_wgrad_patch_supported(C, N)) return AIR_ERR_UNSUPPORTED;
-  if (x_ld % 8 != 0 || dy_ld % 8 != 0 || dw_ld < 9LL * C) return AIR_ERR_ARG;
+extern "C" int air_conv3x3_wgrad_patch_supported(int C, int N) { return wpatch_ok(C, N) ? 1 : 0; }
+
+// dw_out: fp32 [N][dw_ld >= k*k*C] in GEMM layout [Cout][tap][Cin], accumulated in place (caller zeroes).
+// k = 3: 3x3 / stride 1 / pad 1;  k = 1: 1x1 / stride 1 / pad 0.  C = 16 or a multiple of 64; N a multiple of 64.
+extern "C" int air_conv_wgrad_patch_bf16(const void* x, long long x_ld, int B, int H, int W, int C,
+                                         const void* dy, long long dy_ld, int N, int k,
+                                         float* dw_out, long long dw_ld, int num_sms, cudaStream_t stream) {
+  if (!x || !dy || !dw_out || B <= 0 || H < 1 || W < 1 || (k != 3 && k != 1)) return AIR_ERR_ARG;
+  if (!wpatch_ok(C, N)) return AIR_ERR_UNSUPPORTED;
+  if (x_ld % 8 != 0 || dy_ld % 8 != 0 || dw_ld < static_cast<long long>(k) * k * C) return AIR_ERR_ARG;
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) return AIR_ERR_UNSUPPORTED;
   WParams p;
   p.B = B; p.H = H; p.W = W; p.C = C; p.N = N; p.dw = dw_out; p.dw_ld = dw_ld;
-  p.NCB = C / 64; p.NNB = N / 64; p.WT = (W + TW - 1) / TW; p.HP = (H + R - 1) / R;
+  p.narrow = (C == 16) ? 1 : 0; p.ktaps = k * k; p.org = (k == 3) ? -1 : 0;
+  p.NCB = p.narrow ? 1 : C / 64; p.NNB = N / 64; p.WT = (W + TW - 1) / TW; p.HP = (H + R - 1) / R;
+  p.x_bytes = p.narrow ? ((PPIX * 32u + 1023u) / 1024u * 1024u) : X_BYTES;
+  p.stage_bytes = p.x_bytes + DY_BYTES;
+  for (int a = 0; a < NACC; ++a) { p.acc_off[a] = 0; p.acc_lbo[a] = 0; for (int g = 0; g < 8; ++g) p.acc_tap[a][g] = -1; }
+  if (p.narrow) {
+    // eight 16-row groups = eight consecutive pixel shifts: one accumulator per kernel row, taps j = 0..2 are real
+    p.nacc = (k == 3) ? 3 : 1;
+    for (int a = 0; a < p.nacc; ++a) {
+      p.acc_off[a] = a * PW; p.acc_lbo[a] = 1;
+      for (int g = 0; g < (k == 3 ? 3 : 1); ++g) p.acc_tap[a][g] = a * 3 + g;
+    }
+  } else if (k == 3) {
+    // two 64-row groups = two taps: (0,1) (2,3) (4,5) (6,7) (8,-)
+    p.nacc = 5;
+    for (int a = 0; a < 5; ++a) {
+      const int t0 = 2 * a, t1 = (2 * a + 1 < 9) ? 2 * a + 1 : 2 * a;
+      const int o0 = (t0 / 3) * PW + (t0 % 3), o1 = (t1 / 3) * PW + (t1 % 3);
+      p.acc_off[a] = o0; p.acc_lbo[a] = o1 - o0;
+      p.acc_tap[a][0] = t0; p.acc_tap[a][1] = (2 * a + 1 < 9) ? t1 : -1;
+    }
+  } else {
+    p.nacc = 1; p.acc_tap[0][0] = 0;                 // second row group duplicates the first (lbo = 0), ignored
+  }
   const long long items = static_cast<long long>(B) * p.HP * p.WT;
   if (items > 0x7fffffffLL) return AIR_ERR_UNSUPPORTED;
   p.items = static_cast<uint32_t>(items);
@@ -179,10 +215,11 @@ extern "C" int air_conv3x3_wgrad_patch_bf16(const void* x, long long x_ld, int B
   if (jobs > num_sms) return AIR_ERR_UNSUPPORTED;
   p.parts = static_cast<int>(std::min<long long>(num_sms / jobs, items));
   CUtensorMap tmx, tmdy;
-  int tr = air_tmap::make_act_tmap(&tmx, x, x_ld, B, H, W, C, 64, PW, PR, 128);
+  int tr = p.narrow ? air_tmap::make_act_tmap(&tmx, x, x_ld, B, H, W, C, 16, PW, PR, 32)
+                    : air_tmap::make_act_tmap(&tmx, x, x_ld, B, H, W, C, 64, PW, PR, 128);
   if (tr == 0) tr = air_tmap::make_act_tmap(&tmdy, dy, dy_ld, B, H, W, N, 64, TW, R, 128);
   if (tr != 0) return tr < 0 ? AIR_ERR_UNSUPPORTED : 10000 + tr;
-  const size_t smem = 1024 + static_cast<size_t>(STAGES) * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16;
+  const size_t smem = 1024 + static_cast<size_t>(STAGES) * p.stage_bytes + (2 * STAGES + 1) * 8 + 16;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv3x3_wgrad_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -191,4 +228,10 @@ extern "C" int air_conv3x3_wgrad_patch_bf16(const void* x, long long x_ld, int B
   }
   conv3x3_wgrad_patch_kernel<<<jobs * p.parts, THREADS, smem, stream>>>(tmx, tmdy, p);
   return air_launch_status();
+}
+
+extern "C" int air_conv3x3_wgrad_patch_bf16(const void* x, long long x_ld, int B, int H, int W, int C,
+                                            const void* dy, long long dy_ld, int N,
+                                            float* dw_out, long long dw_ld, int num_sms, cudaStream_t stream) {
+  return air_conv_wgrad_patch_bf16(x, x_ld, B, H, W, C, dy, dy_ld, N, 3, dw_out, dw_ld, num_sms, stream);
 }

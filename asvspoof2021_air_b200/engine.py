@@ -99,7 +99,7 @@ class ConvLayer:
         self.patch_ok = (geom == (3, 3, 1, 1, 1, 1, 1, 1) and plain
                          and ops.patch_supported(cin, cout, 1, 1) and ops.patch_supported(cout, cin, 1, 1)
                          and cin <= 256 and cout <= 256)
-        self.wpatch_ok = (geom == (3, 3, 1, 1, 1, 1, 1, 1) and self._wtmp is None
+        self.wpatch_ok = (geom in ((3, 3, 1, 1, 1, 1, 1, 1), (1, 1, 1, 1, 0, 0, 1, 1)) and self._wtmp is None
                           and ops.wgrad_patch_supported(cin, cout))
         # stride-2 layers: data gradient by output parity classes on the patch kernel (3x3 pad 1, or the 1x1 shortcut)
         self.s2_dgrad_ok = (need_dgrad and plain and geom in ((3, 3, 2, 2, 1, 1, 1, 1), (1, 1, 2, 2, 0, 0, 1, 1))
@@ -194,7 +194,8 @@ class ConvLayer:
     def wgrad(self, x, x_ld, B, H, W, dy, dy_ld):
         Ho, Wo = self.out_hw(H, W)
         if self.wpatch_ok and self._patch_efficiency(H, W) >= 0.5:
-            ops.conv3x3_wgrad_patch(x, x_ld, B, H, W, self.cin, dy, dy_ld, self.cout, self.store.grad(self.name + ".weight"))
+            ops.conv_wgrad_patch(x, x_ld, B, H, W, self.cin, dy, dy_ld, self.cout, self.kh,
+                                 self.store.grad(self.name + ".weight"))
             return
         if self._wtmp is not None:
             g = self._gtmp if hasattr(self, "_gtmp") else None

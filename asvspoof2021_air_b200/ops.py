@@ -151,6 +151,14 @@ def conv3x3_wgrad_patch(x, x_ld, B, H, W, C, dy, dy_ld, N, dw_out, dw_ld=None):
     return dw_out
 
 
+def conv_wgrad_patch(x, x_ld, B, H, W, C, dy, dy_ld, N, k, dw_out, dw_ld=None):
+    """k = 3 (3x3 / s1 / p1) or 1 (1x1 / s1 / p0); dw_out fp32 [N][k*k*C] accumulated in place (caller zeroes)."""
+    _lib.check(_lib.lib().air_conv_wgrad_patch_bf16(
+        _lib.ptr(x), _lib.LL(x_ld), B, H, W, C, _lib.ptr(dy), _lib.LL(dy_ld), N, k, _lib.ptr(dw_out),
+        _lib.LL(k * k * C if dw_ld is None else dw_ld), num_sms(), _lib.stream_ptr()), "air_conv_wgrad_patch_bf16")
+    return dw_out
+
+
 def conv_out_size(n, k, s, p, d):
     return (n + 2 * p - d * (k - 1) - 1) // s + 1
 
@@ -393,6 +401,26 @@ class Profile:
 _ACTIVE = None
 
 
+class region:
+    """`with ops.region("family"):` -- CUDA events around a block of launches when a Profile is active."""
+
+    def __init__(self, family, flops=0.0, nbytes=0.0):
+        self.family, self.flops, self.nbytes = family, flops, nbytes
+
+    def __enter__(self):
+        self.prof = _ACTIVE
+        if self.prof is not None:
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.prof is not None:
+            self.e1.record()
+            self.prof.records.append((self.family, self.e0, self.e1, self.flops, self.nbytes))
+            self.prof.details.append(())
+
+
 def _conv_work(args):
     # conv_gemm(a, a_ld, B, H, W, C, Ho, Wo, kh, kw, ..., mode, wpk, N, K, ...)
     # algorithmic FLOPs: a strided dgrad enumerates the input grid, of which 1/(sh*sw) of the
@@ -470,3 +498,4 @@ conv1x1_patch = _timed(conv1x1_patch, lambda a: "conv_dgrad" if (len(a) > 13 and
                        lambda a: 2.0 * a[2] * a[3] * a[4] * a[5] * a[7])
 conv_s2_dgrad_patch = _timed(conv_s2_dgrad_patch, "conv_dgrad", lambda a: 2.0 * a[2] * a[3] * a[4] * a[5] * a[8] * a[7] * a[7])
 PackPlan.run = _timed(PackPlan.run, "pack_weights")
+conv_wgrad_patch = _timed(conv_wgrad_patch, "conv_wgrad", lambda a: 2.0 * a[2] * a[3] * a[4] * a[5] * a[8] * a[9] * a[9])

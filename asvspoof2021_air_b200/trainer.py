@@ -70,8 +70,11 @@ class Trainer:
         shape = (B, 1, 60, self.feat_len) if self.layout == "resnet" else (B, self.feat_len, 64)
         if self.x0 is None or tuple(self.x0.shape) != shape:
             self.x0 = torch.zeros(shape, device=self.device, dtype=BF16)
-        self.lfcc.extract(waves, lengths=lengths, feat_len=self.feat_len, padding=self.padding, start=start,
-                          layout=self.layout, dtype=BF16, out=self.x0)
+        # algorithmic bytes of the fused front-end: read the fp32 wave once, write the padded bf16 model-layout features once
+        nbytes = float(waves.numel() * 4 + self.x0.numel() * 2)
+        with ops.region("lfcc", nbytes=nbytes):
+            self.lfcc.extract(waves, lengths=lengths, feat_len=self.feat_len, padding=self.padding, start=start,
+                              layout=self.layout, dtype=BF16, out=self.x0)
         return self.x0[:, 0] if self.layout == "resnet" else self.x0
 
     def train_step(self, waves, labels, lengths=None, start=None, lr=None):

@@ -195,7 +195,9 @@ def run_lfcc(args, rank, world):
                    "batch_per_gpu": B, "l2": "inputs rotate over %d buffers (360 MB > L2)" % nbuf},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_src": peaks["src"],
-                     "kernel": "air_lfcc::lfcc_kernel", "bytes_per_launch": B * LFCC_BYTES_PER_UTT},
+                     "kernel": ("air_lfcc_tc::lfcc_tc_kernel (tensor-core folded DFT)" if mod.impl == "tc"
+                                else "air_lfcc::lfcc_kernel (radix FFT on CUDA cores)"),
+                     "bytes_per_launch": B * LFCC_BYTES_PER_UTT},
         "e2e": {"value": world * B * args.steps / (ms_e2e / 1e3), "unit": "utterances/s",
                 "h2d_bytes_per_step": B * WAVE_LEN * 4, "d2h_bytes_per_step": B * 60 * 4},
         "gpu_launches": n_timed_launches, "clocks": clocks,

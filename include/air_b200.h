@@ -155,6 +155,11 @@ int air_conv_s2_dgrad_patch_bf16(const void* dy, long long dy_ld, int B, int Ho,
  * (csrc/conv_wgrad_patch.cu): dW[co][i][j][ci] += sum_{b,h,w} x[b,h+i-1,w+j-1,ci] * dy[b,h,w,co], accumulated with fp32
  * atomics into the caller-zeroed dw_out ([Cout][dw_ld >= 9*Cin] fp32, GEMM layout).  C % 64 == 0, N % 64 == 0. */
 int air_conv3x3_wgrad_patch_supported(int C, int N);
+/* general form: k = 3 (3x3 / stride 1 / pad 1) or k = 1 (1x1 / stride 1 / pad 0); C = 16 (SWIZZLE_32B operand, eight
+ * pixel shifts per M = 128 instruction) or a multiple of 64; N a multiple of 64; dw_out [N][dw_ld >= k*k*C]. */
+int air_conv_wgrad_patch_bf16(const void* x, long long x_ld, int B, int H, int W, int C,
+                              const void* dy, long long dy_ld, int N, int k,
+                              float* dw_out, long long dw_ld, int num_sms, air_stream_t stream);
 int air_conv3x3_wgrad_patch_bf16(const void* x, long long x_ld, int B, int H, int W, int C,
                                  const void* dy, long long dy_ld, int N,
                                  float* dw_out, long long dw_ld, int num_sms, air_stream_t stream);

@@ -171,7 +171,11 @@ def test_patch_conv3x3_fprop_and_dgrad(name):
 
 
 WPATCH_CASES = {
-    # name: B, H, W, Cin, Cout
+    # name: B, H, W, Cin, Cout[, k]
+    "l1_16_64_narrow": (2, 18, 750, 16, 64),
+    "narrow_ragged": (3, 5, 131, 16, 128),
+    "l1_shortcut_1x1_narrow": (2, 18, 750, 16, 64, 1),
+    "wide_1x1": (2, 7, 200, 64, 64, 1),
     "l1_64_64": (2, 18, 750, 64, 64),
     "l2_128_128": (2, 9, 375, 128, 128),
     "odd_rows_ragged_width": (3, 5, 131, 64, 128),
@@ -185,18 +189,19 @@ def test_patch_conv3x3_wgrad(name):
     """csrc/conv_wgrad_patch.cu (TMA patches, MN-major shifted windows, tap pairs through LBO) vs torch fp32 wgrad."""
     from asvspoof2021_air_b200 import ops
     torch.backends.cudnn.allow_tf32 = False
-    B, H, W, Cin, Cout = WPATCH_CASES[name]
+    B, H, W, Cin, Cout = WPATCH_CASES[name][:5]
+    k = WPATCH_CASES[name][5] if len(WPATCH_CASES[name]) > 5 else 3
     g = torch.Generator(device="cpu").manual_seed(13)
     x = torch.randn(B, Cin, H, W, generator=g).cuda().to(torch.bfloat16)
     dy = torch.randn(B, Cout, H, W, generator=g).cuda().to(torch.bfloat16)
     assert ops.wgrad_patch_supported(Cin, Cout)
-    dw = torch.zeros(Cout, 9 * Cin, device="cuda")
+    dw = torch.zeros(Cout, k * k * Cin, device="cuda")
     xc, dyc = x.permute(0, 2, 3, 1).contiguous(), dy.permute(0, 2, 3, 1).contiguous()
-    ops.conv3x3_wgrad_patch(xc, Cin, B, H, W, Cin, dyc, Cout, Cout, dw)
-    ops.conv3x3_wgrad_patch(xc, Cin, B, H, W, Cin, dyc, Cout, Cout, dw)          # accumulates
+    ops.conv_wgrad_patch(xc, Cin, B, H, W, Cin, dyc, Cout, Cout, k, dw)
+    ops.conv_wgrad_patch(xc, Cin, B, H, W, Cin, dyc, Cout, Cout, k, dw)          # accumulates
     torch.cuda.synchronize()
-    ref = 2 * torch.nn.grad.conv2d_weight(x.float(), (Cout, Cin, 3, 3), dy.float(), padding=1)
-    got = dw.view(Cout, 3, 3, Cin).permute(0, 3, 1, 2)
+    ref = 2 * torch.nn.grad.conv2d_weight(x.float(), (Cout, Cin, k, k), dy.float(), padding=k // 2)
+    got = dw.view(Cout, k, k, Cin).permute(0, 3, 1, 2)
     err = (got - ref).norm() / ref.norm()
     worst = (got - ref).abs().max() / ref.abs().max()
     assert err < 1e-3 and worst < 2e-3, "%s: normwise %.3g, worst %.3g" % (name, float(err), float(worst))
