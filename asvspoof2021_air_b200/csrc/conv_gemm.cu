@@ -9,9 +9,12 @@
 //   dgrad : dx [m, n]  = sum_k  A'[m, k] * Wd[n, k]     m = (b, h, w),   k = (tap, co), n = ci
 //   wgrad : dW [n, k] += sum_m  dy[m, n] * A[m, k]      (conv_wgrad.cu)
 //
-// A is never materialised: 128 producer threads gather one 128-byte im2col row each per K block
-// with zero-filling 16-byte cp.async, straight into the UMMA "column of rows" layout (tc05.cuh).
-// Pre-packed weight tiles arrive with one bulk copy per K block on the TMA engine.  One elected
+// A is never materialised: 128 producer threads gather the 128 x 64 im2col tile of a K block with zero-filling
+// 16-byte cp.async straight into the SWIZZLE_128B K-major operand image (one 128-byte row per output pixel).
+// Eight consecutive lanes copy the eight 16-byte chunks of ONE row, so a warp instruction reads four contiguous
+// 128-byte segments of global memory and writes four consecutive shared-memory rows (the previous one-row-per-lane
+// mapping cost 64 LSU wavefronts per instruction and made the gather the bottleneck).
+// Pre-packed, pre-swizzled weight tiles arrive with one bulk copy per K block on the TMA engine.  One elected
 // thread issues tcgen05.mma (M = 128, N = block_n <= 256, K = 16 x 4 per stage); accumulators are
 // double-buffered in TMEM so the epilogue warps (TMEM -> registers -> bias/residual/ReLU -> bf16 ->
 // HBM) overlap the next tile's main loop.  The kernel is persistent: grid = #SMs, tiles strided.
@@ -26,7 +29,7 @@ using namespace tc05;
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;      // 16 KB
-constexpr int A_CHUNK_STRIDE = BLOCK_M * 16;              // bytes between 8-element K chunks
+constexpr int ROWS_PER_THREAD = 8;                        // thread t: chunk t & 7 of rows (t >> 3) + 16 i
 constexpr int NUM_A_THREADS = 128;
 constexpr int THREADS = 320;                              // 4 gather warps, TMA warp, MMA warp, 4 epilogue warps
 
@@ -47,7 +50,8 @@ struct ConvParams {
 };
 
 __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const ConvParams p) {
-  extern __shared__ __align__(128) uint8_t smem[];
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // swizzle patterns are anchored at 1024 B
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.stages;
   const uint32_t b_stage_bytes = static_cast<uint32_t>(p.block_n) * BLOCK_K * 2;
@@ -77,56 +81,52 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const ConvParams 
   const int total_tiles = p.m_tiles * p.n_tiles;
 
   if (warp < 4) {
-    // ===================== A gather producers: one im2col row per thread =====================
-    const int r = threadIdx.x;
+    // ===================== A gather producers: 8 lanes per im2col row =====================
+    const int c = threadIdx.x & 7, r0 = threadIdx.x >> 3;            // chunk of the K block, first row
     uint32_t stage = 0, phase = 0;
-    const uint32_t dst_row = smem_u32(sA) + r * 16;
-    const bool fast = (p.C % BLOCK_K) == 0;          // a K block never straddles two taps
+    // destination of row r0 + 16 i, chunk c:  row * 128 + ((c ^ (row & 7)) << 4); (r0 + 16 i) & 7 == r0 & 7
+    const uint32_t dst0 = smem_u32(sA) + r0 * 128 + ((c ^ (r0 & 7)) << 4);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.n_tiles;
-      const long long m = static_cast<long long>(m_tile) * BLOCK_M + r;
-      const bool row_ok = m < p.M;
-      int wo = 0, ho = 0, bb = 0;
-      if (row_ok) { wo = static_cast<int>(m % p.Wo); const long long t = m / p.Wo; ho = static_cast<int>(t % p.Ho); bb = static_cast<int>(t / p.Ho); }
-      const int hbase = p.mode == 0 ? ho * p.sh - p.ph : ho + p.ph;
-      const int wbase = p.mode == 0 ? wo * p.sw - p.pw : wo + p.pw;
-      const __nv_bfloat16* img = p.a + static_cast<long long>(bb) * p.H * p.W * p.a_ld;
-      int tap = 0, ci0 = 0;                          // fast path running position
-      for (int kb = 0; kb < p.KB; ++kb) {
-        mbar_wait(&empty[stage], phase ^ 1);
-        const uint32_t dst = dst_row + stage * A_STAGE_BYTES;
-        if (fast) {
-          const int khi = tap / p.kw, kwi = tap - khi * p.kw;
-          int hi, wi; bool ok = row_ok && (kb * BLOCK_K < p.K);
-          if (p.mode == 0) { hi = hbase + khi * p.dh; wi = wbase + kwi * p.dw; }
-          else {
-            const int hn = hbase - khi * p.dh, wn = wbase - kwi * p.dw;
-            ok = ok && hn >= 0 && wn >= 0 && (hn % p.sh) == 0 && (wn % p.sw) == 0;
-            hi = hn / p.sh; wi = wn / p.sw;
-          }
-          ok = ok && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W;
-          const __nv_bfloat16* src = ok ? img + (static_cast<long long>(hi) * p.W + wi) * p.a_ld + ci0 : p.a;
-          const uint32_t nb = ok ? 16u : 0u;
+      // per-row pixel decode, once per tile: gather base (h, w) and the element offset of that pixel
+      int hb[ROWS_PER_THREAD], wb[ROWS_PER_THREAD]; long long rbase[ROWS_PER_THREAD]; uint32_t okmask = 0;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) cp_async16(dst + c * A_CHUNK_STRIDE, src + (ok ? c * 8 : 0), nb);
-          ci0 += BLOCK_K;
-          if (ci0 >= p.C) { ci0 = 0; ++tap; }
+      for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+        const long long m = static_cast<long long>(m_tile) * BLOCK_M + r0 + 16 * i;
+        int wo = 0, ho = 0, bb = 0;
+        if (m < p.M) { okmask |= 1u << i; wo = static_cast<int>(m % p.Wo); const long long t = m / p.Wo; ho = static_cast<int>(t % p.Ho); bb = static_cast<int>(t / p.Ho); }
+        hb[i] = p.mode == 0 ? ho * p.sh - p.ph : ho + p.ph;
+        wb[i] = p.mode == 0 ? wo * p.sw - p.pw : wo + p.pw;
+        rbase[i] = ((static_cast<long long>(bb) * p.H + hb[i]) * p.W + wb[i]) * p.a_ld;      // may point outside: only used when in range
+      }
+      const bool unit = p.mode == 0 || (p.sh == 1 && p.sw == 1);     // (h, w) = base + signed tap offset, no divisibility test
+      const int sgn = p.mode == 0 ? 1 : -1;
+      for (int kb = 0; kb < p.KB; ++kb) {
+        // this thread's 8 K elements of the block: one tap, 8 consecutive channels
+        const int k = kb * BLOCK_K + c * 8;
+        const int tp = k / p.C, ci = k - tp * p.C;
+        const int khi = tp / p.kw, kwi = tp - khi * p.kw;
+        const bool k_ok = k < p.K;
+        const int dhh = sgn * khi * p.dh, dww = sgn * kwi * p.dw;
+        const long long delta = (static_cast<long long>(dhh) * p.W + dww) * p.a_ld + ci;
+        mbar_wait(&empty[stage], phase ^ 1);
+        const uint32_t dst = dst0 + stage * A_STAGE_BYTES;
+        if (unit) {
+#pragma unroll
+          for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+            const int hi = hb[i] + dhh, wi = wb[i] + dww;
+            const bool ok = k_ok && ((okmask >> i) & 1u) && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W;
+            cp_async16(dst + i * (16 * 128), ok ? p.a + rbase[i] + delta : p.a, ok ? 16u : 0u);
+          }
         } else {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const int k = kb * BLOCK_K + c * 8;
-            const int tp = k / p.C, ci = k - tp * p.C;
-            const int khi = tp / p.kw, kwi = tp - khi * p.kw;
-            int hi, wi; bool ok = row_ok && k < p.K;
-            if (p.mode == 0) { hi = hbase + khi * p.dh; wi = wbase + kwi * p.dw; }
-            else {
-              const int hn = hbase - khi * p.dh, wn = wbase - kwi * p.dw;
-              ok = ok && hn >= 0 && wn >= 0 && (hn % p.sh) == 0 && (wn % p.sw) == 0;
-              hi = hn / p.sh; wi = wn / p.sw;
-            }
-            ok = ok && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W;
-            const __nv_bfloat16* src = ok ? img + (static_cast<long long>(hi) * p.W + wi) * p.a_ld + ci : p.a;
-            cp_async16(dst + c * A_CHUNK_STRIDE, src, ok ? 16u : 0u);
+          for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+            const int hn = hb[i] + dhh, wn = wb[i] + dww;          // strided data gradient: only multiples of the stride hit an output pixel
+            bool ok = k_ok && ((okmask >> i) & 1u) && hn >= 0 && wn >= 0 && (hn % p.sh) == 0 && (wn % p.sw) == 0;
+            const int hi = hn / p.sh, wi = wn / p.sw;
+            ok = ok && hi < p.H && wi < p.W;
+            const long long off = (rbase[i] / p.a_ld - (static_cast<long long>(hb[i]) * p.W + wb[i]) + static_cast<long long>(hi) * p.W + wi) * p.a_ld + ci;
+            cp_async16(dst + i * (16 * 128), ok ? p.a + off : p.a, ok ? 16u : 0u);
           }
         }
         cp_async_arrive_noinc(&full[stage]);
@@ -153,11 +153,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const ConvParams 
     // ===================== MMA issuer (warp-uniform loop: descriptors in uniform registers, elected lane issues) =====================
     const bool leader = elect_one();
     const uint32_t idesc = instr_desc_bf16(BLOCK_M, p.block_n, 0, 0);
-    const uint32_t b_chunk = static_cast<uint32_t>(p.block_n) * 16;
-    uint32_t a_lbo = A_CHUNK_STRIDE, a_sbo = 128, b_lbo = b_chunk, b_sbo = 128;
-    if (p.flags & 1) { a_lbo = 128; a_sbo = A_CHUNK_STRIDE; b_lbo = 128; b_sbo = b_chunk; }   // debug: swapped roles
-    const uint32_t a_hi = (a_sbo >> 4) | (1u << 14), b_hi = (b_sbo >> 4) | (1u << 14);
-    const uint32_t a_lbo16 = (a_lbo >> 4) << 16, b_lbo16 = (b_lbo >> 4) << 16;
+    const uint32_t d_hi = (1024u >> 4) | (1u << 14) | (2u << 29);       // SBO = 8 rows x 128 B, version 1, SWIZZLE_128B
     uint32_t stage = 0, phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -169,12 +165,12 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const ConvParams 
       for (int kb = 0; kb < p.KB; ++kb) {
         mbar_wait(&full[stage], phase);
         fence_after_sync();
-        const uint32_t a0 = (((smem_u32(sA) + stage * A_STAGE_BYTES) >> 4) & 0x3FFF) | a_lbo16;
-        const uint32_t b0 = (((smem_u32(sB) + stage * b_stage_bytes) >> 4) & 0x3FFF) | b_lbo16;
+        const uint32_t a0 = (((smem_u32(sA) + stage * A_STAGE_BYTES) >> 4) & 0x3FFF) | (1u << 16);
+        const uint32_t b0 = (((smem_u32(sB) + stage * b_stage_bytes) >> 4) & 0x3FFF) | (1u << 16);
 #pragma unroll
         for (int kk = 0; kk < BLOCK_K / 16; ++kk) {
-          const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a0 + kk * ((2 * A_CHUNK_STRIDE) >> 4));
-          const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b0 + kk * ((2 * b_chunk) >> 4));
+          const uint64_t ad = (static_cast<uint64_t>(d_hi) << 32) | (a0 + kk * 2);       // +32 B per 16 K elements
+          const uint64_t bd = (static_cast<uint64_t>(d_hi) << 32) | (b0 + kk * 2);
           if (leader) mma_bf16(d_tmem, ad, bd, idesc, (kb | kk) != 0);
         }
         if (leader) mma_commit(&empty[stage]);
@@ -337,11 +333,11 @@ extern "C" int air_conv_gemm_bf16_ex(const void* a, long long a_ld, int B, int H
   p.res = reinterpret_cast<const __nv_bfloat16*>(res); p.res_ld = res_ld; p.relu = relu; p.flags = flags;
   p.bias_rows = bias_rows; p.out2 = reinterpret_cast<__nv_bfloat16*>(out2); p.out2_ld = out2_ld;
   const int stage_bytes = A_STAGE_BYTES + bn * BLOCK_K * 2;
-  int stages = (200 * 1024) / stage_bytes;
+  int stages = (198 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) return AIR_ERR_UNSUPPORTED;
   p.stages = stages;
-  const size_t smem = static_cast<size_t>(stages) * stage_bytes + (2 * stages + 4) * 8 + 16;
+  const size_t smem = 1024 + static_cast<size_t>(stages) * stage_bytes + (2 * stages + 4) * 8 + 16;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);

@@ -6,22 +6,23 @@
 
 namespace air_pack {
 
-// UMMA "column of rows" tiles of the generic implicit-GEMM kernel: destination order [n_tile][kb][chunk][n_local][e]
+// SWIZZLE_128B K-major tiles of the generic implicit-GEMM kernel: destination = [n_tile][kb] tiles of
+// [block_n rows][64 K elements] (128 B per row), 16-byte chunk c of row r stored at chunk position c ^ (r & 7)
 //   value(n, k) = src[n*sn + (k / inner)*so + (k % inner)*si]
 __device__ __forceinline__ void gemm_pack_elem(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long i,
                                                int N, int K, int KB, int block_n, long long sn, int inner, long long so,
                                                long long si) {
-  const int e = static_cast<int>(i & 7);
-  long long t = i >> 3;
+  const int kk = static_cast<int>(i & 63);               // logical element index: [n_tile][kb][n_local][kk]
+  long long t = i >> 6;
   const int n_local = static_cast<int>(t % block_n); t /= block_n;
-  const int c = static_cast<int>(t & 7); t >>= 3;
   const int kb = static_cast<int>(t % KB);
   const int n_tile = static_cast<int>(t / KB);
   const int n = n_tile * block_n + n_local;
-  const int k = kb * 64 + c * 8 + e;
+  const int k = kb * 64 + kk;
   float v = 0.f;
   if (k < K && n < N) v = src[n * sn + static_cast<long long>(k / inner) * so + static_cast<long long>(k % inner) * si];
-  dst[i] = f2bf(v);
+  const long long tile = (static_cast<long long>(n_tile) * KB + kb) * block_n * 64;
+  dst[tile + n_local * 64 + ((((kk >> 3) ^ (n_local & 7)) << 3) | (kk & 7))] = f2bf(v);
 }
 
 // pre-swizzled [N rows][CB channels] K-major slices of the patch kernel, one per (channel block, tap)
