@@ -2,10 +2,11 @@
 //
 //   dW[n, kx] += sum_{pixels m} dy[m, n] * im2col(x)[m, kx]        n = co, kx = (tap, ci)
 //
-// The reduction runs over pixels, so both operands are "MN-major" for the tensor core: rows of the
-// shared-memory image are pixels (the GEMM K dimension), 16-byte chunks are 8 channels.  That is the
-// same "column of rows" image the forward gather builds (tc05.cuh), so the same zero-filling
-// cp.async gather feeds it.  Tile: 256 (kx) x block_n (co) accumulated in TMEM as two M = 128
+// The reduction runs over pixels, so both operands are "MN-major" for the tensor core: a shared-memory row is
+// one pixel (the GEMM K index) holding 64 consecutive kx (or output channels) = 128 B, SWIZZLE_128B; a 128-wide
+// M (or N) extent is two such 8 KB images, chained through the descriptor's leading byte offset.  Eight consecutive
+// lanes copy the eight 16-byte chunks of one pixel row, so a cp.async instruction reads four contiguous 128-byte
+// segments of global memory and writes four consecutive shared-memory rows.  Tile: 256 (kx) x block_n (co) accumulated in TMEM as two M = 128
 // halves; the pixel range is split across CTAs (split-K) and reduced with fp32 red.global.add into
 // the caller-zeroed gradient buffer (GEMM layout [Cout][taps*Cin], fp32).
 #include <algorithm>
@@ -17,8 +18,8 @@ using namespace tc05;
 
 constexpr int TILE_M = 256;              // kx per work item (two UMMA M=128 halves)
 constexpr int PIX = 64;                  // pixels per pipeline stage (GEMM K block)
-constexpr int A_HALF_BYTES = 16 * PIX * 16;      // 16 chunks x 64 rows x 16 B = 16 KB
-constexpr int CHUNK_STRIDE = PIX * 16;           // 1024 B between 8-channel chunks
+constexpr int GROUP_BYTES = PIX * 128;           // one [64 pixels][64 elements] SWIZZLE_128B image = 8 KB
+constexpr int A_HALF_BYTES = 2 * GROUP_BYTES;    // 128 kx = two images = 16 KB
 constexpr int THREADS = 256;             // 4 gather warps, 1 MMA warp, (1 idle), ... see roles below
 
 struct WgradParams {
@@ -35,10 +36,12 @@ struct WgradParams {
 struct ChunkInfo { int hoff, woff, ci, ok; };
 
 __global__ void __launch_bounds__(THREADS, 1) conv_wgrad_kernel(const WgradParams p) {
-  extern __shared__ __align__(128) uint8_t smem[];
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // swizzle patterns are anchored at 1024 B
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.stages;
-  const uint32_t b_bytes = static_cast<uint32_t>(p.block_n / 8) * CHUNK_STRIDE;
+  const int nbg = (p.block_n + 63) / 64;                                        // 64-channel images of dy per stage
+  const uint32_t b_bytes = static_cast<uint32_t>(nbg) * GROUP_BYTES;
   const uint32_t stage_bytes = 2 * A_HALF_BYTES + b_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * stage_bytes);
   uint64_t* full = bars;            // [S] 128 gather arrivals
@@ -88,33 +91,43 @@ __global__ void __launch_bounds__(THREADS, 1) conv_wgrad_kernel(const WgradParam
     __syncthreads();
 
     if (warp < 4) {
-      const int row = threadIdx.x & 63, half = threadIdx.x >> 6;
-      const int nbc = p.block_n / 8;
-      const int bc0 = half * (nbc / 2), bc1 = (half == 0) ? nbc / 2 : nbc;
+      const int c = threadIdx.x & 7, r0 = threadIdx.x >> 3;              // chunk of a 64-element group, first pixel row
+      const uint32_t rowoff = r0 * 128 + ((c ^ (r0 & 7)) << 4);           // (r0 + 16 i) & 7 == r0 & 7
+      const int nag = 2 * halves;                                         // 64-kx images of x to fill
+      // pixel coordinates of this thread's four rows: decoded once per item, then advanced by PIX per stage
+      int rw[PIX / 16], rh[PIX / 16], rb[PIX / 16];
+#pragma unroll
+      for (int i = 0; i < PIX / 16; ++i) {
+        const long long m = static_cast<long long>(kb0) * PIX + r0 + 16 * i;
+        rw[i] = static_cast<int>(m % p.Wo); const long long t = m / p.Wo;
+        rh[i] = static_cast<int>(t % p.Ho); rb[i] = static_cast<int>(t / p.Ho);
+      }
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
-        const long long m = static_cast<long long>(kb) * PIX + row;
-        const bool row_ok = m < p.M;
-        int wo = 0, ho = 0, bb = 0;
-        if (row_ok) { wo = static_cast<int>(m % p.Wo); const long long t = m / p.Wo; ho = static_cast<int>(t % p.Ho); bb = static_cast<int>(t / p.Ho); }
-        const int hs = ho * p.sh, ws = wo * p.sw;
-        const __nv_bfloat16* img = p.x + static_cast<long long>(bb) * p.H * p.W * p.x_ld;
-        const uint32_t sbase = smem_u32(smem) + stage * stage_bytes + row * 16;
-        // x chunks: this thread fills chunks [16*half .. 16*half+16) of the 32-chunk (256 kx) A image
-        if (half < halves) {
-#pragma unroll 4
-          for (int c = 0; c < 16; ++c) {
-            const ChunkInfo ci = cinfo[half * 16 + c];
+        const uint32_t sbase = smem_u32(smem) + stage * stage_bytes + rowoff;
+#pragma unroll
+        for (int i = 0; i < PIX / 16; ++i) {
+          const long long m = static_cast<long long>(kb) * PIX + r0 + 16 * i;
+          const bool row_ok = m < p.M;
+          const int wo = rw[i], ho = rh[i], bb = rb[i];
+          rw[i] += PIX;                                                   // next stage: the same row is PIX pixels further
+          while (rw[i] >= p.Wo) { rw[i] -= p.Wo; if (++rh[i] == p.Ho) { rh[i] = 0; ++rb[i]; } }
+          const int hs = ho * p.sh, ws = wo * p.sw;
+          const __nv_bfloat16* img = p.x + static_cast<long long>(bb) * p.H * p.W * p.x_ld;
+          const uint32_t drow = sbase + i * (16 * 128);
+          for (int g = 0; g < nag; ++g) {                                 // x: chunk c of each 64-kx group
+            const ChunkInfo ci = cinfo[g * 8 + c];
             const int hi = hs + ci.hoff, wi = ws + ci.woff;
             const bool ok = row_ok && ci.ok && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W;
             const __nv_bfloat16* src = ok ? img + (static_cast<long long>(hi) * p.W + wi) * p.x_ld + ci.ci : p.x;
-            cp_async16(sbase + half * A_HALF_BYTES + c * CHUNK_STRIDE, src, ok ? 16u : 0u);
+            cp_async16(drow + g * GROUP_BYTES, src, ok ? 16u : 0u);
+          }
+          const __nv_bfloat16* dsrc = p.dy + m * p.dy_ld + n0 + c * 8;
+          for (int g = 0; g < nbg; ++g) {                                 // dy: chunk c of each 64-channel group
+            const bool ok = row_ok && (g * 64 + c * 8) < p.block_n;
+            cp_async16(drow + 2 * A_HALF_BYTES + g * GROUP_BYTES, ok ? dsrc + g * 64 : p.dy, ok ? 16u : 0u);
           }
         }
-        // dy chunks
-        const __nv_bfloat16* dsrc = p.dy + m * p.dy_ld + n0;
-        for (int c = bc0; c < bc1; ++c)
-          cp_async16(sbase + 2 * A_HALF_BYTES + c * CHUNK_STRIDE, row_ok ? dsrc + c * 8 : p.dy, row_ok ? 16u : 0u);
         cp_async_arrive_noinc(&full[stage]);
         if (++stage == static_cast<uint32_t>(S)) { stage = 0; phase ^= 1; }
       }
@@ -141,9 +154,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_wgrad_kernel(const WgradParam
       // warp-uniform issue loop: descriptors in uniform registers, one elected lane issues
       const bool leader = elect_one();
       const uint32_t idesc = instr_desc_bf16(128, p.block_n, 1, 1);
-      uint32_t lbo = 128, sbo = CHUNK_STRIDE;
-      if (p.flags & 1) { lbo = CHUNK_STRIDE; sbo = 128; }
-      const uint32_t d_hi = (sbo >> 4) | (1u << 14), lbo16 = (lbo >> 4) << 16;
+      // MN-major SWIZZLE_128B: SBO = next 8 pixel rows (1024 B), LBO = next 64-element image (8 KB), version 1
+      const uint32_t d_hi = (1024u >> 4) | (1u << 14) | (2u << 29), lbo16 = (static_cast<uint32_t>(GROUP_BYTES) >> 4) << 16;
       mbar_wait(tempty, (it & 1) ^ 1);
       fence_after_sync();
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -151,10 +163,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_wgrad_kernel(const WgradParam
         fence_after_sync();
         const uint32_t s0 = (((smem_u32(smem) + stage * stage_bytes) >> 4) & 0x3FFF) | lbo16;
 #pragma unroll
-        for (int kk = 0; kk < PIX / 16; ++kk) {
-          const uint64_t bd = (static_cast<uint64_t>(d_hi) << 32) | (s0 + ((2 * A_HALF_BYTES + kk * 256) >> 4));
+        for (int kk = 0; kk < PIX / 16; ++kk) {                            // 16 pixel rows = 2048 B per K step
+          const uint64_t bd = (static_cast<uint64_t>(d_hi) << 32) | (s0 + ((2 * A_HALF_BYTES + kk * 2048) >> 4));
           for (int h = 0; h < halves; ++h) {
-            const uint64_t ad = (static_cast<uint64_t>(d_hi) << 32) | (s0 + ((h * A_HALF_BYTES + kk * 256) >> 4));
+            const uint64_t ad = (static_cast<uint64_t>(d_hi) << 32) | (s0 + ((h * A_HALF_BYTES + kk * 2048) >> 4));
             if (leader) mma_bf16(tmem_base + h * p.block_n, ad, bd, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
           }
         }
@@ -214,12 +226,12 @@ extern "C" int air_conv_wgrad_bf16_ld(const void* x, long long x_ld, int B, int 
   p.kb_per_split = (p.kb_total + splits - 1) / splits;
   p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   p.flags = flags;
-  const int stage_bytes = 2 * A_HALF_BYTES + (bn / 8) * CHUNK_STRIDE;
+  const int stage_bytes = 2 * A_HALF_BYTES + ((bn + 63) / 64) * GROUP_BYTES;
   int stages = (196 * 1024) / stage_bytes;
   if (stages > 6) stages = 6;
   if (stages < 2) return AIR_ERR_UNSUPPORTED;
   p.stages = stages;
-  const size_t smem = static_cast<size_t>(stages) * stage_bytes + (2 * stages + 4) * 8 + 32 * sizeof(ChunkInfo) + 16;
+  const size_t smem = 1024 + static_cast<size_t>(stages) * stage_bytes + (2 * stages + 4) * 8 + 32 * sizeof(ChunkInfo) + 16;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
