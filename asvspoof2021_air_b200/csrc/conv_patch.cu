@@ -56,15 +56,19 @@ struct PatchParams {
   uint32_t items;
 };
 
+// residual of one 32-column (NC = 32) or 16-column chunk of a pixel: 16-byte loads, issued ahead of use
 template <int NC>
-__device__ __forceinline__ void epilogue_chunk(const PatchParams& p, uint32_t taddr, long long pixel, int c0, bool valid) {
-  // NC = 32 or 16 columns: residual loads are issued BEFORE the TMEM load so that their latency overlaps it
-  bf16x8 rv[NC / 8];
+__device__ __forceinline__ void load_res(const PatchParams& p, long long pixel, int c0, bool valid, bf16x8 (&rv)[4]) {
   if (p.res != nullptr && valid) {
     const bf16x8* rp = reinterpret_cast<const bf16x8*>(p.res + pixel * p.res_ld + c0);
 #pragma unroll
     for (int i = 0; i < NC / 8; ++i) rv[i] = rp[i];
   }
+}
+
+template <int NC>
+__device__ __forceinline__ void epilogue_chunk(const PatchParams& p, uint32_t taddr, long long pixel, int c0, bool valid,
+                                               const bf16x8 (&rv)[4]) {
   float v[NC];
   if (NC == 32) tmem_ld32(taddr + c0, v); else tmem_ld16(taddr + c0, v);
   if (valid) {
@@ -232,16 +236,43 @@ __global__ void __launch_bounds__(THREADS, 1) conv_patch_kernel(const __grid_con
       const int g = wt * TW + m;
       const int ow = g * p.osw + p.opw;
       const bool col_ok = g < p.GW && ow < p.OW;
+      // chunk list of the item: (row j, 32-column block); the residual of chunk i+1 is loaded while chunk i is
+      // processed, and the first one before the accumulator is even complete
+      const int cpr = p.N >> 5, tail = p.N & 31;                       // full 32-column chunks per row, 16-column tail
+      const int nch = rows * cpr;
+      static_assert(R == 2, "row select below assumes two rows per item");
+      long long pixr[R]; bool valr[R];
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const int oh = (hp * R + j) * p.osh + p.oph;
+        valr[j] = col_ok && j < rows && oh < p.OH;
+        pixr[j] = (static_cast<long long>(b) * p.OH + oh) * p.OW + ow;
+      }
+      const long long pix0 = pixr[0], pix1 = pixr[1];
+      const bool val0 = valr[0], val1 = valr[1];
+      auto PIX = [&](int j) { return j == 0 ? pix0 : pix1; };
+      auto VAL = [&](int j) { return j == 0 ? val0 : val1; };
+      bf16x8 ra[4], rb[4];
+      if (nch > 0) load_res<32>(p, pix0, 0, val0, ra);
       mbar_wait(&tfull[acc], acc_phase);
       fence_after_sync();
-      for (int j = 0; j < rows; ++j) {
-        const int oh = (hp * R + j) * p.osh + p.oph;
-        const bool valid = col_ok && oh < p.OH;
-        const long long pixel = (static_cast<long long>(b) * p.OH + oh) * p.OW + ow;
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (acc * R + j) * p.N;
-        int c0 = 0;
-        for (; c0 + 32 <= p.N; c0 += 32) epilogue_chunk<32>(p, taddr, pixel, c0, valid);
-        if (c0 < p.N) epilogue_chunk<16>(p, taddr, pixel, c0, valid);
+      const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * R * p.N;
+      for (int i = 0; i < nch; i += 2) {
+        const int j0 = i / cpr, c0 = (i - j0 * cpr) << 5;
+        const int i1 = i + 1, j1 = i1 / cpr, c1 = (i1 - j1 * cpr) << 5;
+        if (i1 < nch) load_res<32>(p, PIX(j1), c1, VAL(j1), rb);
+        epilogue_chunk<32>(p, tacc + j0 * p.N, PIX(j0), c0, VAL(j0), ra);
+        if (i1 < nch) {
+          const int i2 = i + 2, j2 = i2 / cpr, c2 = (i2 - j2 * cpr) << 5;
+          if (i2 < nch) load_res<32>(p, PIX(j2), c2, VAL(j2), ra);
+          epilogue_chunk<32>(p, tacc + j1 * p.N, PIX(j1), c1, VAL(j1), rb);
+        }
+      }
+      if (tail) {
+        for (int j = 0; j < rows; ++j) {
+          load_res<16>(p, PIX(j), cpr << 5, VAL(j), ra);
+          epilogue_chunk<16>(p, tacc + j * p.N, PIX(j), cpr << 5, VAL(j), ra);
+        }
       }
       fence_before_sync();
       mbar_arrive(&tempty[acc]);

@@ -194,7 +194,10 @@ def run_lfcc(args, rank, world):
         "config": {"workload": "lfcc: fused wave->LFCC kernel, B=%d/GPU, 4 s @ 16 kHz, fp32 out (B,401,60)" % B,
                    "batch_per_gpu": B, "l2": "inputs rotate over %d buffers (360 MB > L2)" % nbuf},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_src": peaks["src"],
+                     "frac": achieved / peaks["hbm_gbs"],
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/r01_ncu_full_v6_summary.txt):
+                     # the 65.5 MB of waves are read once; most of the 24.6 MB of output is still L2-resident at kernel end
+                     "traffic": 69.3e6 if (mod.impl == "tc" and B == 256) else None, "peak_src": peaks["src"],
                      "kernel": ("air_lfcc_tc::lfcc_tc_kernel (tensor-core folded DFT)" if mod.impl == "tc"
                                 else "air_lfcc::lfcc_kernel (radix FFT on CUDA cores)"),
                      "bytes_per_launch": B * LFCC_BYTES_PER_UTT},

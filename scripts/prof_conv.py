@@ -23,7 +23,7 @@ elif kind == "wgrad":
     f = lambda: ops.conv_wgrad(x, C, B, H, W, C, dy, N, H, W, N, 3, 3, 1, 1, 1, 1, 1, 1, dw)
 elif kind == "wgrad_patch":
     dw = torch.zeros(N, 9 * C, device="cuda")
-    f = lambda: ops.conv3x3_wgrad_patch(x, C, B, H, W, C, dy, N, N, dw)
+    f = lambda: ops.conv_wgrad_patch(x, C, B, H, W, C, dy, N, N, 3, dw)
 import time
 for _ in range(3):
     f()
