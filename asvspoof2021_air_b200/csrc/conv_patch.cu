@@ -203,10 +203,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv_patch_kernel(const __grid_con
           for (int j = 0; j < R; ++j) {
             if (j < rows) {
               const uint32_t arow = a_tap + static_cast<uint32_t>(j * PW) * rb16;
+              // persistent 64-bit descriptors, advanced in place by 32 B per K step (keeps the issue loop at
+              // ~5 uniform instructions per MMA instead of rebuilding both register pairs)
+              uint64_t ad = (static_cast<uint64_t>(desc_hi) << 32) | arow;
+              uint64_t bd = (static_cast<uint64_t>(desc_hi) << 32) | b_lo;
               for (int kk = 0; kk < KK; ++kk) {
-                const uint64_t ad = (static_cast<uint64_t>(desc_hi) << 32) | (arow + kk * 2);
-                const uint64_t bd = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + kk * 2);
                 if (leader) mma_bf16(d0 + j * p.N, ad, bd, idesc, (cb | t | kk) != 0);
+                ad += 2; bd += 2;
               }
             }
           }

@@ -103,6 +103,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_wgrad_patch_kernel(const _
     const uint32_t b_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
     const uint32_t a_hi = p.narrow ? ((256u >> 4) | (1u << 14) | (6u << 29)) : b_hi;
     const uint32_t upp = p.narrow ? 2u : 8u;              // 16-byte units per patch pixel
+    // per-accumulator A descriptor without the (stage, row, K step) offset: window offset in the low word, LBO above it
+    uint64_t abase[NACC];
+#pragma unroll
+    for (int a = 0; a < NACC; ++a)
+      abase[a] = (static_cast<uint64_t>(a_hi) << 32) |
+                 ((static_cast<uint32_t>(p.acc_off[a]) * upp) | ((static_cast<uint32_t>(p.acc_lbo[a]) * upp) << 16));
+    const uint64_t bbase = (static_cast<uint64_t>(b_hi) << 32) | (1u << 16);
     uint32_t stage = 0, phase = 0;
     for (uint32_t k = 0; k < my_items; ++k) {
       mbar_wait(&full[stage], phase);
@@ -113,15 +120,12 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_wgrad_patch_kernel(const _
       for (int r = 0; r < R; ++r) {
 #pragma unroll 2
         for (int ks = 0; ks < TW / 16; ++ks) {
-          const uint32_t b_lo = (d16 + static_cast<uint32_t>(r * TW + ks * 16) * 8) | (1u << 16);
-          const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | b_lo;
+          const uint64_t bd = bbase + (d16 + static_cast<uint32_t>(r * TW + ks * 16) * 8);
           const uint32_t xrow = x16 + static_cast<uint32_t>(r * PW + ks * 16) * upp;
 #pragma unroll
           for (int a = 0; a < NACC; ++a) {
             if (a < p.nacc) {
-              // LBO = distance between the windows of consecutive M row groups
-              const uint32_t a_lo = (xrow + static_cast<uint32_t>(p.acc_off[a]) * upp) | ((static_cast<uint32_t>(p.acc_lbo[a]) * upp) << 16);
-              const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | a_lo;
+              const uint64_t ad = abase[a] + xrow;             // never carries out of the 14-bit address field
               if (leader) mma_bf16(tmem_base + a * ACC_COLS, ad, bd, idesc, (k | static_cast<uint32_t>(r) | static_cast<uint32_t>(ks)) != 0);
             }
           }
