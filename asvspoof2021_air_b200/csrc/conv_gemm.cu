@@ -46,6 +46,7 @@ struct ConvParams {
   const float* bias; const __nv_bfloat16* res; long long res_ld; int relu;
   int bias_rows;                            // 0: bias[n]; > 0: bias[(m / bias_rows) * N + n] (per-utterance bias)
   __nv_bfloat16* out2; long long out2_ld;   // optional second output: the accumulator (+bias) WITHOUT the residual
+  const float* post_scale; const float* post_shift;   // optional per-channel affine AFTER the ReLU (eval-mode BatchNorm of conv -> ReLU -> BN)
   int stages; int flags;
 };
 
@@ -197,10 +198,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const ConvParams 
         tmem_ld16(taddr + c0, v);
         if (m < p.M) {
           const int n0 = n_tile * p.block_n + c0;
-          if (p.bias) {
-            const float* bp = p.bias + n0 + (p.bias_rows > 0 ? (m / p.bias_rows) * p.N : 0);
+          if (p.bias) {                                  // 16 consecutive floats, 16-byte aligned (checked by the launcher)
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + (p.bias_rows > 0 ? (m / p.bias_rows) * p.N : 0));
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += __ldg(bp + i);
+            for (int i = 0; i < 4; ++i) {
+              const float4 b4 = __ldg(bp + i);
+              v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+            }
           }
           if (p.out2) {
             bf16x8* o2 = reinterpret_cast<bf16x8*>(p.out2 + m * p.out2_ld + n0);
@@ -217,6 +221,16 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const ConvParams 
           if (p.relu) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (p.post_scale) {
+            const float4* sp = reinterpret_cast<const float4*>(p.post_scale + n0);
+            const float4* tp = reinterpret_cast<const float4*>(p.post_shift + n0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 s4 = __ldg(sp + i), t4 = __ldg(tp + i);
+              v[4 * i] = fmaf(v[4 * i], s4.x, t4.x); v[4 * i + 1] = fmaf(v[4 * i + 1], s4.y, t4.y);
+              v[4 * i + 2] = fmaf(v[4 * i + 2], s4.z, t4.z); v[4 * i + 3] = fmaf(v[4 * i + 3], s4.w, t4.w);
+            }
           }
           bf16x8* op = reinterpret_cast<bf16x8*>(p.out + m * p.out_ld + n0);
           op[0] = pack8(v);
@@ -311,14 +325,34 @@ extern "C" int air_conv_gemm_bf16(const void* a, long long a_ld, int B, int H, i
                                bias, 0, res, res_ld, relu, nullptr, 0, num_sms, flags, stream);
 }
 
+extern "C" int air_conv_gemm_bf16_affine(const void* a, long long a_ld, int B, int H, int W, int C, int Ho, int Wo,
+                                         int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw, int mode,
+                                         const void* wpk, int N, int K, void* out, long long out_ld,
+                                         const float* bias, int bias_rows, const void* res, long long res_ld, int relu,
+                                         void* out2, long long out2_ld, const float* post_scale, const float* post_shift,
+                                         int num_sms, int flags, cudaStream_t stream);
+
 extern "C" int air_conv_gemm_bf16_ex(const void* a, long long a_ld, int B, int H, int W, int C, int Ho, int Wo,
                                      int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw, int mode,
                                      const void* wpk, int N, int K, void* out, long long out_ld,
                                      const float* bias, int bias_rows, const void* res, long long res_ld, int relu,
                                      void* out2, long long out2_ld, int num_sms, int flags, cudaStream_t stream) {
-  if (!a || !wpk || !out || B <= 0) return AIR_ERR_ARG;
+  return air_conv_gemm_bf16_affine(a, a_ld, B, H, W, C, Ho, Wo, kh, kw, sh, sw, ph, pw, dh, dw, mode, wpk, N, K, out, out_ld,
+                                   bias, bias_rows, res, res_ld, relu, out2, out2_ld, nullptr, nullptr, num_sms, flags, stream);
+}
+
+// as _ex, plus an optional per-channel affine applied after the ReLU: out = relu(acc + bias) * post_scale[n] + post_shift[n]
+extern "C" int air_conv_gemm_bf16_affine(const void* a, long long a_ld, int B, int H, int W, int C, int Ho, int Wo,
+                                         int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw, int mode,
+                                         const void* wpk, int N, int K, void* out, long long out_ld,
+                                         const float* bias, int bias_rows, const void* res, long long res_ld, int relu,
+                                         void* out2, long long out2_ld, const float* post_scale, const float* post_shift,
+                                         int num_sms, int flags, cudaStream_t stream) {
+  if (!a || !wpk || !out || B <= 0 || ((post_scale == nullptr) != (post_shift == nullptr))) return AIR_ERR_ARG;
   if (C % 8 != 0 || a_ld % 8 != 0 || out_ld % 8 != 0 || (res && res_ld % 8 != 0) || (out2 && out2_ld % 8 != 0)) return AIR_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(out2) & 15) || bias_rows < 0) return AIR_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(post_scale) | reinterpret_cast<uintptr_t>(post_shift)) & 15) return AIR_ERR_UNSUPPORTED;
+  if (bias_rows > 0 && (N % 4) != 0) return AIR_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(wpk) |
        reinterpret_cast<uintptr_t>(res)) & 15) return AIR_ERR_UNSUPPORTED;
   const int bn = air_conv_block_n(N);
@@ -332,6 +366,7 @@ extern "C" int air_conv_gemm_bf16_ex(const void* a, long long a_ld, int B, int H
   p.out = reinterpret_cast<__nv_bfloat16*>(out); p.out_ld = out_ld; p.bias = bias;
   p.res = reinterpret_cast<const __nv_bfloat16*>(res); p.res_ld = res_ld; p.relu = relu; p.flags = flags;
   p.bias_rows = bias_rows; p.out2 = reinterpret_cast<__nv_bfloat16*>(out2); p.out2_ld = out2_ld;
+  p.post_scale = post_scale; p.post_shift = post_shift;
   const int stage_bytes = A_STAGE_BYTES + bn * BLOCK_K * 2;
   int stages = (198 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;

@@ -171,6 +171,14 @@ class ConvLayer:
                       self.dh, self.dw, 0, self.wpk, self.cout, self.K, out, out_ld, bias, res, res_ld, relu)
         return Ho, Wo
 
+    def fprop_affine(self, x, x_ld, B, H, W, out, out_ld, relu, scale, shift):
+        """conv (+bias) -> [ReLU] -> per-channel affine, in one launch (eval-mode conv -> ReLU -> BN)."""
+        Ho, Wo = self.out_hw(H, W)
+        bias = self.store.view(self.name + ".bias") if self.bias else None
+        ops.conv_gemm_affine(x, x_ld, B, H, W, self.cin_g, Ho, Wo, self.kh, self.kw, self.sh, self.sw, self.ph, self.pw,
+                             self.dh, self.dw, 0, self.wpk, self.cout, self.K, out, out_ld, bias, relu, scale, shift)
+        return Ho, Wo
+
     def dgrad(self, dy, dy_ld, B, H, W, dx, dx_ld, accumulate=False, res=None, res_ld=0, out2=None, out2_ld=0):
         """dy on the (Ho,Wo) grid -> dx on the (H,W) input grid.  accumulate adds into dx; `res` adds
         another tensor instead; out2 (optional) receives the gradient without the residual."""

@@ -151,6 +151,7 @@ class EcapaEngine:
 
     def mark_dirty(self):
         self._packed_version = -1
+        self._eval_version = getattr(self, "_eval_version", 0) + 1      # folded eval-mode BN affines are stale
 
     def load_state(self, sd):
         bufs = self.buffers.named_f32()
@@ -236,6 +237,22 @@ class EcapaEngine:
         ops.bn_apply_add(x, x_ld, y, y_ld, M, bn.C, bn.sums, g, b, False, training, bn.save_mean, bn.save_invstd,
                          bn.running_mean, bn.running_var, add, add_ld, y2, y2_ld)
 
+    def _conv_relu_bn(self, conv, bn, x, x_ld, B, T, tmp, y, C, M, training):
+        """conv -> ReLU -> BN (ecapa_tdnn.py:67-69,87-89,156-158).  Training: conv writes `tmp`, batch statistics, apply
+        into `y`.  Eval: the running-statistics affine is folded into the conv epilogue and `y` is written directly."""
+        if training:
+            conv.fprop(x, x_ld, B, 1, T, tmp, C, relu=True)
+            self._bn_fwd(bn, tmp, C, y, C, M, True)
+            return
+        key = (self.store.step, self._eval_version)
+        aff = self._eval_affine.get(bn.name)
+        if aff is None or aff[0] != key:
+            g, b = self.store.view(bn.name + ".weight"), self.store.view(bn.name + ".bias")
+            scale = g * torch.rsqrt(bn.running_var + 1e-5)
+            aff = (key, scale.contiguous(), (b - bn.running_mean * scale).contiguous())
+            self._eval_affine[bn.name] = aff
+        conv.fprop_affine(x, x_ld, B, 1, T, y, C, True, aff[1], aff[2])
+
     def _bn_bwd(self, bn, dy, dy_ld, x, x_ld, dx, dx_ld, M, dbias):
         g, b = self.store.view(bn.name + ".weight"), self.store.view(bn.name + ".bias")
         ops.bn_bwd_bias(dy, dy_ld, x, x_ld, None, 0, dx, dx_ld, M, bn.C, 1, bn.save_mean, bn.save_invstd, g, b, bn.rsum,
@@ -249,18 +266,19 @@ class EcapaEngine:
         self.bind(B, T)
         if self._packed_version != self.store.step:
             self.pack_weights()
+        if not hasattr(self, "_eval_affine"):
+            self._eval_affine, self._eval_version = {}, getattr(self, "_eval_version", 0)
         if training:
             self.buffers.f64.zero_()
+            self._eval_version += 1                                     # running statistics change
         st, C, W, C3, M = self.store, self.C, self.width, self.C3, B * T
         self.x0 = x0
-        self.conv1.fprop(x0, self.mels_g, B, 1, T, self.c1, C, relu=True)                      # :156-158
-        self._bn_fwd(self.bn1, self.c1, C, self.xb1, C, M, training)
+        self._conv_relu_bn(self.conv1, self.bn1, x0, self.mels_g, B, T, self.c1, self.xb1, C, M, training)   # :156-158
         xin, xin_ld = self.xb1, C
         for li, blk in enumerate(self.blocks):
             blk.xin, blk.xin_ld = xin, xin_ld
             out = self.xcat[:, :, li * C:(li + 1) * C]
-            blk.conv1.fprop(xin, xin_ld, B, 1, T, blk.t1, C, relu=True)                        # :67-69
-            self._bn_fwd(blk.bn1, blk.t1, C, blk.o1, C, M, training)
+            self._conv_relu_bn(blk.conv1, blk.bn1, xin, xin_ld, B, T, blk.t1, blk.o1, C, M, training)     # :67-69
             for i in range(self.scale - 1):                                                    # :73-83
                 src = blk.o1[:, :, 0:W] if i == 0 else blk.spin[i]
                 src_ld = C if i == 0 else W
@@ -272,8 +290,7 @@ class EcapaEngine:
                 else:
                     self._bn_fwd(blk.bns[i], blk.tb[i], W, dst, C, M, training)
             ops.copy_channels(blk.o1[:, :, C - W:], C, blk.cat[:, :, C - W:], C, M, W)         # :85
-            blk.conv3.fprop(blk.cat, C, B, 1, T, blk.t3, C, relu=True)                         # :87-89
-            self._bn_fwd(blk.bn3, blk.t3, C, blk.o3, C, M, training)
+            self._conv_relu_bn(blk.conv3, blk.bn3, blk.cat, C, B, T, blk.t3, blk.o3, C, M, training)      # :87-89
             # SE (:15-29): squeeze -> 512->128 -> ReLU -> BN -> 128->512 -> sigmoid -> scale; + residual (:93)
             p = blk.name + ".se.se."
             ops.time_stats(blk.o3, C, B, T, C, blk.s)

@@ -258,6 +258,17 @@ def conv_gemm_ex(a, a_ld, B, H, W, C, Ho, Wo, kh, kw, sh, sw, ph, pw, dh, dw, mo
     return out
 
 
+def conv_gemm_affine(a, a_ld, B, H, W, C, Ho, Wo, kh, kw, sh, sw, ph, pw, dh, dw, mode, wpk, N, K,
+                     out, out_ld, bias, relu, post_scale, post_shift):
+    """fprop with a per-channel affine after the ReLU (eval-mode BatchNorm folded into the conv epilogue)."""
+    st = _lib.lib().air_conv_gemm_bf16_affine(
+        _lib.ptr(a), _lib.LL(a_ld), B, H, W, C, Ho, Wo, kh, kw, sh, sw, ph, pw, dh, dw, mode,
+        _lib.ptr(wpk), N, K, _lib.ptr(out), _lib.LL(out_ld), _lib.ptr(bias), 0, None, _lib.LL(0), int(relu),
+        None, _lib.LL(0), _lib.ptr(post_scale), _lib.ptr(post_shift), num_sms(), 0, _lib.stream_ptr())
+    _lib.check(st, "air_conv_gemm_bf16_affine")
+    return out
+
+
 def conv_wgrad_ld(x, x_ld, B, H, W, C, dy, dy_ld, Ho, Wo, N, kh, kw, sh, sw, ph, pw, dh, dw, dw_out, dw_ld, flags=0):
     st = _lib.lib().air_conv_wgrad_bf16_ld(
         _lib.ptr(x), _lib.LL(x_ld), B, H, W, C, _lib.ptr(dy), _lib.LL(dy_ld), Ho, Wo, N,
@@ -499,3 +510,4 @@ conv1x1_patch = _timed(conv1x1_patch, lambda a: "conv_dgrad" if (len(a) > 13 and
 conv_s2_dgrad_patch = _timed(conv_s2_dgrad_patch, "conv_dgrad", lambda a: 2.0 * a[2] * a[3] * a[4] * a[5] * a[8] * a[7] * a[7])
 PackPlan.run = _timed(PackPlan.run, "pack_weights")
 conv_wgrad_patch = _timed(conv_wgrad_patch, "conv_wgrad", lambda a: 2.0 * a[2] * a[3] * a[4] * a[5] * a[8] * a[9] * a[9])
+conv_gemm_affine = _timed(conv_gemm_affine, "conv_fprop", _conv_work)

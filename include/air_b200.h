@@ -108,6 +108,14 @@ int air_conv_gemm_bf16_ex(const void* a, long long a_ld, int B, int H, int W, in
                           const void* wpk, int N, int K, void* out, long long out_ld,
                           const float* bias, int bias_rows, const void* res, long long res_ld, int relu,
                           void* out2, long long out2_ld, int num_sms, int flags, air_stream_t stream);
+/* as _ex plus an optional per-channel affine after the ReLU (out = relu(acc + bias) * post_scale[n] + post_shift[n]):
+ * eval-mode BatchNorm of the conv -> ReLU -> BN blocks of ecapa_tdnn.py:67-69,87-89,156-158 folded into the conv epilogue */
+int air_conv_gemm_bf16_affine(const void* a, long long a_ld, int B, int H, int W, int C, int Ho, int Wo,
+                              int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw, int mode,
+                              const void* wpk, int N, int K, void* out, long long out_ld,
+                              const float* bias, int bias_rows, const void* res, long long res_ld, int relu,
+                              void* out2, long long out2_ld, const float* post_scale, const float* post_shift,
+                              int num_sms, int flags, air_stream_t stream);
 
 /* 3x3 / stride 1 / pad 1 convolution with a shared-memory resident input patch (csrc/conv_patch.cu): one TMA box
  * load brings a (2+2) x (128+2) pixel patch (zero padding = TMA out-of-bounds fill) and the nine taps are shifted
