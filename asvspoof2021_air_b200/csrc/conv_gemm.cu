@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include "tc05.cuh"
 #include "pack.cuh"
+#include "tmap.cuh"
 
 namespace air_gemm {
 using namespace tc05;
@@ -48,9 +49,10 @@ struct ConvParams {
   __nv_bfloat16* out2; long long out2_ld;   // optional second output: the accumulator (+bias) WITHOUT the residual
   const float* post_scale; const float* post_shift;   // optional per-channel affine AFTER the ReLU (eval-mode BatchNorm of conv -> ReLU -> BN)
   int stages; int flags;
+  int use_tma;                              // 1x1 / stride 1: the A tile is a plain 2-D box of the activation matrix
 };
 
-__global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const ConvParams p) {
+__global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // swizzle patterns are anchored at 1024 B
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -87,6 +89,23 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const ConvParams 
     uint32_t stage = 0, phase = 0;
     // destination of row r0 + 16 i, chunk c:  row * 128 + ((c ^ (row & 7)) << 4); (r0 + 16 i) & 7 == r0 & 7
     const uint32_t dst0 = smem_u32(sA) + r0 * 128 + ((c ^ (r0 & 7)) << 4);
+    if (p.use_tma) {
+      // 1x1 / stride-1 layer: one TMA box [128 pixels][64 channels] per K block, no gather.  Thread 0 issues it (its
+      // arrival carries the transaction bytes); the other gather threads only keep the barrier's arrival count.
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_tiles;
+        for (int kb = 0; kb < p.KB; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (threadIdx.x == 0) {
+            mbar_arrive_expect_tx(&full[stage], A_STAGE_BYTES);
+            tma_load_2d(smem_u32(sA) + stage * A_STAGE_BYTES, &tma_a, kb * BLOCK_K, m_tile * BLOCK_M, &full[stage]);
+          } else {
+            mbar_arrive(&full[stage]);
+          }
+          if (++stage == static_cast<uint32_t>(S)) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.n_tiles;
       // per-row pixel decode, once per tile: gather base (h, w) and the element offset of that pixel
@@ -382,6 +401,11 @@ extern "C" int air_conv_gemm_bf16_affine(const void* a, long long a_ld, int B, i
   if (num_sms <= 0) num_sms = 148;
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int grid = total_tiles < num_sms ? total_tiles : num_sms;
-  conv_gemm_kernel<<<grid, THREADS, smem, stream>>>(p);
+  CUtensorMap tm{};
+  p.use_tma = 0;
+  if (kh == 1 && kw == 1 && sh == 1 && sw == 1 && ph == 0 && pw == 0 && Ho == H && Wo == W && p.M < 0x7fffffffLL) {
+    if (air_tmap::make_mat_tmap(&tm, a, a_ld, p.M, C, BLOCK_M) == 0) p.use_tma = 1;     // otherwise: the gather path
+  }
+  conv_gemm_kernel<<<grid, THREADS, smem, stream>>>(tm, p);
   return air_launch_status();
 }

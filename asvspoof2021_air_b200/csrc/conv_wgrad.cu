@@ -12,6 +12,7 @@
 #include <algorithm>
 #include "common.cuh"
 #include "tc05.cuh"
+#include "tmap.cuh"
 
 namespace air_wgrad {
 using namespace tc05;
@@ -31,11 +32,13 @@ struct WgradParams {
   long long M;                            // pixels = B*Ho*Wo
   int m_tiles, n_tiles, splits, kb_total, kb_per_split, block_n;
   int stages, flags;
+  int use_tma;                            // 1x1 / stride 1: x and dy tiles are plain 2-D boxes of [pixels][channels] matrices
 };
 
 struct ChunkInfo { int hoff, woff, ci, ok; };
 
-__global__ void __launch_bounds__(THREADS, 1) conv_wgrad_kernel(const WgradParams p) {
+__global__ void __launch_bounds__(THREADS, 1) conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmx,
+                                                                const __grid_constant__ CUtensorMap tmdy, const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // swizzle patterns are anchored at 1024 B
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -94,6 +97,22 @@ __global__ void __launch_bounds__(THREADS, 1) conv_wgrad_kernel(const WgradParam
       const int c = threadIdx.x & 7, r0 = threadIdx.x >> 3;              // chunk of a 64-element group, first pixel row
       const uint32_t rowoff = r0 * 128 + ((c ^ (r0 & 7)) << 4);           // (r0 + 16 i) & 7 == r0 & 7
       const int nag = 2 * halves;                                         // 64-kx images of x to fill
+      if (p.use_tma) {
+        // 1x1 / stride-1 layer: [64 pixels][64 channels] TMA boxes, no gather.  Thread 0 issues them (its arrival carries
+        // the transaction bytes); the other gather threads only keep the barrier's arrival count.
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (threadIdx.x == 0) {
+            const uint32_t s0 = smem_u32(smem) + stage * stage_bytes;
+            mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>(nag + nbg) * GROUP_BYTES);
+            for (int g = 0; g < nag; ++g) tma_load_2d(s0 + g * GROUP_BYTES, &tmx, m0 + g * 64, kb * PIX, &full[stage]);
+            for (int g = 0; g < nbg; ++g) tma_load_2d(s0 + 2 * A_HALF_BYTES + g * GROUP_BYTES, &tmdy, n0 + g * 64, kb * PIX, &full[stage]);
+          } else {
+            mbar_arrive(&full[stage]);
+          }
+          if (++stage == static_cast<uint32_t>(S)) { stage = 0; phase ^= 1; }
+        }
+      } else {
       // pixel coordinates of this thread's four rows: decoded once per item, then advanced by PIX per stage
       int rw[PIX / 16], rh[PIX / 16], rb[PIX / 16];
 #pragma unroll
@@ -130,6 +149,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_wgrad_kernel(const WgradParam
         }
         cp_async_arrive_noinc(&full[stage]);
         if (++stage == static_cast<uint32_t>(S)) { stage = 0; phase ^= 1; }
+      }
       }
       // ---------------- epilogue (same warps): TMEM -> red.global.add ----------------
       mbar_wait(tfull, it & 1);
@@ -240,6 +260,12 @@ extern "C" int air_conv_wgrad_bf16_ld(const void* x, long long x_ld, int B, int 
   }
   const int total_items = base_items * p.splits;
   const int grid = std::min(total_items, num_sms);
-  conv_wgrad_kernel<<<grid, THREADS, smem, stream>>>(p);
+  CUtensorMap tmx{}, tmdy{};
+  p.use_tma = 0;
+  if (kh == 1 && kw == 1 && sh == 1 && sw == 1 && ph == 0 && pw == 0 && Ho == H && Wo == W && p.M < 0x7fffffffLL) {
+    if (air_tmap::make_mat_tmap(&tmx, x, x_ld, p.M, C, PIX) == 0 && air_tmap::make_mat_tmap(&tmdy, dy, dy_ld, p.M, N, PIX) == 0)
+      p.use_tma = 1;                                         // otherwise: the gather path
+  }
+  conv_wgrad_kernel<<<grid, THREADS, smem, stream>>>(tmx, tmdy, p);
   return air_launch_status();
 }

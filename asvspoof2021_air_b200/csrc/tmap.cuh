@@ -45,4 +45,19 @@ static inline int make_act_tmap(CUtensorMap* tm, const void* base, long long ld,
   return static_cast<int>(r);
 }
 
+// bf16 row-major matrix [rows][ld >= cols] viewed as the 2-D tensor (cols, rows) with a (64, box_rows) SWIZZLE_128B box:
+// the A operand of a 1x1 / stride-1 convolution (rows = pixels, cols = channels) needs no gather at all.
+static inline int make_mat_tmap(CUtensorMap* tm, const void* base, long long ld, long long rows, int cols, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return -1;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return static_cast<int>(r);
+}
+
 }  // namespace air_tmap
