@@ -135,45 +135,70 @@ __global__ void selfattn_pool_bwd_kernel(const __nv_bfloat16* __restrict__ x, co
 // ------------------------------------------------------------------------------------------
 // fp32 linear layer  y = x W^T + b   (x (M,K), W (N,K))
 // ------------------------------------------------------------------------------------------
-__global__ void linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
-                                  float* __restrict__ y, int M, int N, int K, long long ldx, long long ldw, int accumulate) {
-  const int lane = threadIdx.x & 31;
-  const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-  for (long long o = warp; o < static_cast<long long>(M) * N; o += nwarps) {
-    const int m = static_cast<int>(o / N), n = static_cast<int>(o - static_cast<long long>(m) * N);
-    float acc = 0.f;
-    for (int k = lane; k < K; k += 32) acc = fmaf(x[static_cast<long long>(m) * ldx + k], W[static_cast<long long>(n) * ldw + k], acc);
-    acc = warp_sum(acc);
-    if (lane == 0) y[o] = acc + (bias ? bias[n] : 0.f) + (accumulate ? y[o] : 0.f);
-  }
-}
-// dx[m][k] = sum_n dy[m][n] W[n][k]
-__global__ void linear_dx_kernel(const float* __restrict__ dy, const float* __restrict__ W, float* __restrict__ dx,
-                                 int M, int N, int K, long long ldw) {
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < static_cast<long long>(M) * K;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int m = static_cast<int>(i / K), k = static_cast<int>(i - static_cast<long long>(m) * K);
-    float acc = 0.f;
-    for (int n = 0; n < N; ++n) acc = fmaf(dy[static_cast<long long>(m) * N + n], W[static_cast<long long>(n) * ldw + k], acc);
-    dx[i] = acc;
-  }
-}
-// dW[n][k] += sum_m dy[m][n] x[m][k];  db[n] += sum_m dy[m][n]
-__global__ void linear_dw_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dW,
-                                 float* __restrict__ db, int M, int N, int K, long long ldw) {
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < static_cast<long long>(N) * K;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int n = static_cast<int>(i / K), k = static_cast<int>(i - static_cast<long long>(n) * K);
-    float acc = 0.f;
-    for (int m = 0; m < M; ++m) acc = fmaf(dy[static_cast<long long>(m) * N + n], x[static_cast<long long>(m) * K + k], acc);
-    dW[static_cast<long long>(n) * ldw + k] += acc;
-    if (k == 0 && db) {
-      float s = 0.f;
-      for (int m = 0; m < M; ++m) s += dy[static_cast<long long>(m) * N + n];
-      db[n] += s;
+// Small fp32 GEMM with arbitrary element strides (the fully connected layers: fc / fc_mu resnet.py:142-143, fc6 / fc7
+// and the SE bottleneck ecapa_tdnn.py:19-23,148-149):  C[i][j] (+)= sum_l A(i,l) * B(l,j) (+ bias[j]) (+ rowsum)
+//   A(i,l) = A[i*sai + l*sal],  B(l,j) = B[l*sbl + j*sbj],  C[i][j] = C[i*ldc + j]
+// 32 x 32 output tile per 256-thread CTA (each thread 4 rows of one column), 32-deep K tiles through padded shared
+// memory; the tile loaders put the contiguous index of each operand on consecutive lanes.
+__global__ void __launch_bounds__(256) sgemm_strided_kernel(const float* __restrict__ A, long long sai, long long sal,
+                                                            const float* __restrict__ B, long long sbl, long long sbj,
+                                                            float* __restrict__ C, long long ldc, int I, int J, int L,
+                                                            const float* __restrict__ bias, int accumulate,
+                                                            float* __restrict__ colsum_of_a) {
+  __shared__ float sa[32][33], sb[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;            // ty 0..7
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  // fp64 accumulation: these GEMMs are tiny, and the 1-D BatchNorms that follow them (SE, bn5 over B rows) amplify
+  // summation-order noise of an fp32 reduction over K = 3072
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  float csum[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int l0 = 0; l0 < L; l0 += 32) {
+    // A tile: sa[i][l].  lanes follow the contiguous index
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int u = ty + 8 * r;                                       // the slow index of this load
+      int ii, ll;
+      if (sal == 1) { ii = u; ll = tx; } else { ii = tx; ll = u; }
+      const int gi = i0 + ii, gl = l0 + ll;
+      sa[ii][ll] = (gi < I && gl < L) ? A[gi * sai + gl * sal] : 0.f;
     }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int u = ty + 8 * r;
+      int ll, jj;
+      if (sbj == 1) { ll = u; jj = tx; } else { ll = tx; jj = u; }
+      const int gl = l0 + ll, gj = j0 + jj;
+      sb[ll][jj] = (gl < L && gj < J) ? B[gl * sbl + gj * sbj] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int l = 0; l < 32; ++l) {
+      const float bv = sb[l][tx];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) { const float av = sa[ty + 8 * r][l]; acc[r] = fma(static_cast<double>(av), static_cast<double>(bv), acc[r]); csum[r] += av; }
+    }
+    __syncthreads();
   }
+  const int j = j0 + tx;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i = i0 + ty + 8 * r;
+    if (i < I && j < J) {
+      float v = static_cast<float>(acc[r] + (bias ? static_cast<double>(bias[j]) : 0.0));
+      float* cp = C + i * ldc + j;
+      *cp = accumulate ? *cp + v : v;
+    }
+    // row sums of A (the bias gradient when A = dy^T): written once per row by the j-tile 0, column 0 thread
+    if (colsum_of_a && blockIdx.x == 0 && tx == 0 && i < I) colsum_of_a[i] += csum[r];
+  }
+}
+
+static int launch_sgemm(const float* A, long long sai, long long sal, const float* B, long long sbl, long long sbj,
+                        float* C, long long ldc, int I, int J, int L, const float* bias, int accumulate, float* colsum,
+                        cudaStream_t stream) {
+  dim3 grid((J + 31) / 32, (I + 31) / 32);
+  sgemm_strided_kernel<<<grid, 256, 0, stream>>>(A, sai, sal, B, sbl, sbj, C, ldc, I, J, L, bias, accumulate, colsum);
+  return air_launch_status();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -276,10 +301,8 @@ extern "C" int air_selfattn_pool_bwd(const void* x, const float* att, const floa
 extern "C" int air_linear_fwd(const float* x, const float* W, const float* bias, float* y, int M, int N, int K,
                               cudaStream_t stream) {
   if (!x || !W || !y || M <= 0 || N <= 0 || K <= 0) return AIR_ERR_ARG;
-  const long long warps = static_cast<long long>(M) * N;
-  const int blocks = static_cast<int>(std::min<long long>((warps + 7) / 8, 148 * 16));
-  linear_fwd_kernel<<<blocks, 256, 0, stream>>>(x, W, bias, y, M, N, K, K, K, 0);
-  return air_launch_status();
+  // y[m][n] = sum_k x[m][k] W[n][k] + b[n]
+  return launch_sgemm(x, K, 1, W, 1, K, y, N, M, N, K, bias, 0, nullptr, stream);
 }
 
 // y (+)= x W[:, slice]^T + b with a row stride on W (column slice of a wider weight, e.g. the
@@ -287,24 +310,18 @@ extern "C" int air_linear_fwd(const float* x, const float* W, const float* bias,
 extern "C" int air_linear_fwd_ld(const float* x, const float* W, long long ldw, const float* bias, float* y, int M, int N, int K,
                                  int accumulate, cudaStream_t stream) {
   if (!x || !W || !y || M <= 0 || N <= 0 || K <= 0 || ldw < K) return AIR_ERR_ARG;
-  const long long warps = static_cast<long long>(M) * N;
-  const int blocks = static_cast<int>(std::min<long long>((warps + 7) / 8, 148 * 16));
-  linear_fwd_kernel<<<blocks, 256, 0, stream>>>(x, W, bias, y, M, N, K, K, ldw, accumulate);
-  return air_launch_status();
+  return launch_sgemm(x, K, 1, W, 1, ldw, y, N, M, N, K, bias, accumulate, nullptr, stream);
 }
 
 extern "C" int air_linear_bwd_ld(const float* x, const float* W, long long ldw, const float* dy, float* dx, float* dW, float* db,
                                  int M, int N, int K, cudaStream_t stream) {
   if (!x || !W || !dy || M <= 0 || N <= 0 || K <= 0 || ldw < K) return AIR_ERR_ARG;
-  if (dx) {
-    const int blocks = static_cast<int>(std::min<long long>((static_cast<long long>(M) * K + 255) / 256, 148 * 16));
-    linear_dx_kernel<<<blocks, 256, 0, stream>>>(dy, W, dx, M, N, K, ldw);
-  }
-  if (dW) {
-    const int blocks = static_cast<int>(std::min<long long>((static_cast<long long>(N) * K + 255) / 256, 148 * 16));
-    linear_dw_kernel<<<blocks, 256, 0, stream>>>(dy, x, dW, db, M, N, K, ldw);
-  }
-  return air_launch_status();
+  int st = AIR_OK;
+  // dx[m][k] = sum_n dy[m][n] W[n][k]
+  if (dx) st = launch_sgemm(dy, N, 1, W, ldw, 1, dx, K, M, K, N, nullptr, 0, nullptr, stream);
+  // dW[n][k] += sum_m dy[m][n] x[m][k];  db[n] += sum_m dy[m][n]
+  if (dW && st == AIR_OK) st = launch_sgemm(dy, 1, N, x, K, 1, dW, ldw, N, K, M, nullptr, 1, db, stream);
+  return st;
 }
 
 extern "C" int air_linear_bwd(const float* x, const float* W, const float* dy, float* dx, float* dW, float* db,
