@@ -52,6 +52,69 @@ struct ConvParams {
   int use_tma;                              // 1x1 / stride 1: the A tile is a plain 2-D box of the activation matrix
 };
 
+// Epilogue of one warp: TMEM lane quadrant q, columns [c_begin, c_end) of every tile -> bias / residual / ReLU / affine ->
+// bf16 -> HBM.  In TMA mode the four (otherwise idle) gather warps take the upper half of the columns.
+__device__ __forceinline__ void epilogue_role(const ConvParams& p, uint32_t tmem_base, uint64_t* tfull, uint64_t* tempty,
+                                              int q, int lane, int c_begin, int c_end, int total_tiles) {
+  const int row = q * 32 + lane;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    const int m_tile = tile / p.n_tiles, n_tile = tile % p.n_tiles;
+    const int acc = it & 1;
+    const uint32_t acc_phase = (it >> 1) & 1;
+    mbar_wait(&tfull[acc], acc_phase);
+    fence_after_sync();
+    const long long m = static_cast<long long>(m_tile) * BLOCK_M + row;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.block_n;
+    for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+      float v[16];
+      tmem_ld16(taddr + c0, v);
+      if (m < p.M) {
+        const int n0 = n_tile * p.block_n + c0;
+        if (p.bias) {                                  // 16 consecutive floats, 16-byte aligned (checked by the launcher)
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + (p.bias_rows > 0 ? (m / p.bias_rows) * p.N : 0));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 b4 = __ldg(bp + i);
+            v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+          }
+        }
+        if (p.out2) {
+          bf16x8* o2 = reinterpret_cast<bf16x8*>(p.out2 + m * p.out2_ld + n0);
+          o2[0] = pack8(v);
+          o2[1] = pack8(v + 8);
+        }
+        if (p.res) {
+          const bf16x8* rp = reinterpret_cast<const bf16x8*>(p.res + m * p.res_ld + n0);
+          float rf[16];
+          unpack8(rp[0], rf); unpack8(rp[1], rf + 8);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += rf[i];
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (p.post_scale) {
+          const float4* sp = reinterpret_cast<const float4*>(p.post_scale + n0);
+          const float4* tp = reinterpret_cast<const float4*>(p.post_shift + n0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 s4 = __ldg(sp + i), t4 = __ldg(tp + i);
+            v[4 * i] = fmaf(v[4 * i], s4.x, t4.x); v[4 * i + 1] = fmaf(v[4 * i + 1], s4.y, t4.y);
+            v[4 * i + 2] = fmaf(v[4 * i + 2], s4.z, t4.z); v[4 * i + 3] = fmaf(v[4 * i + 3], s4.w, t4.w);
+          }
+        }
+        bf16x8* op = reinterpret_cast<bf16x8*>(p.out + m * p.out_ld + n0);
+        op[0] = pack8(v);
+        op[1] = pack8(v + 8);
+      }
+    }
+    fence_before_sync();
+    mbar_arrive(&tempty[acc]);
+  }
+}
+
 __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // swizzle patterns are anchored at 1024 B
@@ -71,8 +134,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
   while (ncols < 2u * p.block_n) ncols <<= 1;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&full[s], NUM_A_THREADS + 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], p.use_tma ? 1 : NUM_A_THREADS + 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], p.use_tma ? 256 : 128); }
     fence_barrier_init();
   }
   if (warp == 5) tmem_alloc(tmem_slot, ncols);
@@ -90,21 +153,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
     // destination of row r0 + 16 i, chunk c:  row * 128 + ((c ^ (row & 7)) << 4); (r0 + 16 i) & 7 == r0 & 7
     const uint32_t dst0 = smem_u32(sA) + r0 * 128 + ((c ^ (r0 & 7)) << 4);
     if (p.use_tma) {
-      // 1x1 / stride-1 layer: one TMA box [128 pixels][64 channels] per K block, no gather.  Thread 0 issues it (its
-      // arrival carries the transaction bytes); the other gather threads only keep the barrier's arrival count.
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.n_tiles;
-        for (int kb = 0; kb < p.KB; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          if (threadIdx.x == 0) {
-            mbar_arrive_expect_tx(&full[stage], A_STAGE_BYTES);
-            tma_load_2d(smem_u32(sA) + stage * A_STAGE_BYTES, &tma_a, kb * BLOCK_K, m_tile * BLOCK_M, &full[stage]);
-          } else {
-            mbar_arrive(&full[stage]);
-          }
-          if (++stage == static_cast<uint32_t>(S)) { stage = 0; phase ^= 1; }
-        }
-      }
+      // 1x1 / stride-1 layer: no gather (warp 4 issues one TMA box per K block); these four warps own TMEM lane
+      // quadrants 0-3 too, so they drain the upper half of the accumulator columns
+      const int c_begin = ((p.block_n / 16 + 1) / 2) * 16;
+      epilogue_role(p, tmem_base, tfull, tempty, warp & 3, lane, c_begin, p.block_n, total_tiles);
     } else
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.n_tiles;
@@ -162,7 +214,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
         const __nv_bfloat16* wsrc = p.wpk + static_cast<long long>(n_tile) * p.KB * p.block_n * BLOCK_K;
         for (int kb = 0; kb < p.KB; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], b_stage_bytes);
+          mbar_arrive_expect_tx(&full[stage], b_stage_bytes + (p.use_tma ? A_STAGE_BYTES : 0));
+          if (p.use_tma)       // the A tile is a plain [128 pixels][64 channels] box of the activation matrix
+            tma_load_2d(smem_u32(sA) + stage * A_STAGE_BYTES, &tma_a, kb * BLOCK_K, (tile / p.n_tiles) * BLOCK_M, &full[stage]);
           bulk_g2s(smem_u32(sB) + stage * b_stage_bytes, wsrc + static_cast<long long>(kb) * p.block_n * BLOCK_K,
                    b_stage_bytes, &full[stage]);
           if (++stage == static_cast<uint32_t>(S)) { stage = 0; phase ^= 1; }
@@ -201,64 +255,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
     __syncwarp();
   } else {
     // ===================== epilogue: TMEM -> registers -> HBM =====================
-    const int q = warp & 3;                       // TMEM lane quadrant this warp may read
-    const int row = q * 32 + lane;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int m_tile = tile / p.n_tiles, n_tile = tile % p.n_tiles;
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tfull[acc], acc_phase);
-      fence_after_sync();
-      const long long m = static_cast<long long>(m_tile) * BLOCK_M + row;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.block_n;
-      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-        float v[16];
-        tmem_ld16(taddr + c0, v);
-        if (m < p.M) {
-          const int n0 = n_tile * p.block_n + c0;
-          if (p.bias) {                                  // 16 consecutive floats, 16-byte aligned (checked by the launcher)
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + (p.bias_rows > 0 ? (m / p.bias_rows) * p.N : 0));
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 b4 = __ldg(bp + i);
-              v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
-            }
-          }
-          if (p.out2) {
-            bf16x8* o2 = reinterpret_cast<bf16x8*>(p.out2 + m * p.out2_ld + n0);
-            o2[0] = pack8(v);
-            o2[1] = pack8(v + 8);
-          }
-          if (p.res) {
-            const bf16x8* rp = reinterpret_cast<const bf16x8*>(p.res + m * p.res_ld + n0);
-            float rf[16];
-            unpack8(rp[0], rf); unpack8(rp[1], rf + 8);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += rf[i];
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-          }
-          if (p.post_scale) {
-            const float4* sp = reinterpret_cast<const float4*>(p.post_scale + n0);
-            const float4* tp = reinterpret_cast<const float4*>(p.post_shift + n0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 s4 = __ldg(sp + i), t4 = __ldg(tp + i);
-              v[4 * i] = fmaf(v[4 * i], s4.x, t4.x); v[4 * i + 1] = fmaf(v[4 * i + 1], s4.y, t4.y);
-              v[4 * i + 2] = fmaf(v[4 * i + 2], s4.z, t4.z); v[4 * i + 3] = fmaf(v[4 * i + 3], s4.w, t4.w);
-            }
-          }
-          bf16x8* op = reinterpret_cast<bf16x8*>(p.out + m * p.out_ld + n0);
-          op[0] = pack8(v);
-          op[1] = pack8(v + 8);
-        }
-      }
-      fence_before_sync();
-      mbar_arrive(&tempty[acc]);
-    }
+    const int c_end = p.use_tma ? ((p.block_n / 16 + 1) / 2) * 16 : p.block_n;
+    epilogue_role(p, tmem_base, tfull, tempty, warp & 3, lane, 0, c_end, total_tiles);
   }
 
   fence_before_sync();

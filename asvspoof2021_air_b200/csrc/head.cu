@@ -140,6 +140,7 @@ __global__ void selfattn_pool_bwd_kernel(const __nv_bfloat16* __restrict__ x, co
 //   A(i,l) = A[i*sai + l*sal],  B(l,j) = B[l*sbl + j*sbj],  C[i][j] = C[i*ldc + j]
 // 32 x 32 output tile per 256-thread CTA (each thread 4 rows of one column), 32-deep K tiles through padded shared
 // memory; the tile loaders put the contiguous index of each operand on consecutive lanes.
+template <typename AccT>
 __global__ void __launch_bounds__(256) sgemm_strided_kernel(const float* __restrict__ A, long long sai, long long sal,
                                                             const float* __restrict__ B, long long sbl, long long sbj,
                                                             float* __restrict__ C, long long ldc, int I, int J, int L,
@@ -148,9 +149,9 @@ __global__ void __launch_bounds__(256) sgemm_strided_kernel(const float* __restr
   __shared__ float sa[32][33], sb[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;            // ty 0..7
   const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
-  // fp64 accumulation: these GEMMs are tiny, and the 1-D BatchNorms that follow them (SE, bn5 over B rows) amplify
-  // summation-order noise of an fp32 reduction over K = 3072
-  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  // AccT = double for long reductions (fc6: K = 3072): the 1-D BatchNorms that follow (bn5 over B rows) amplify the
+  // summation-order noise of an fp32 reduction; float otherwise
+  AccT acc[4] = {0, 0, 0, 0};
   float csum[4] = {0.f, 0.f, 0.f, 0.f};
   for (int l0 = 0; l0 < L; l0 += 32) {
     // A tile: sa[i][l].  lanes follow the contiguous index
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(256) sgemm_strided_kernel(const float* __restr
     for (int l = 0; l < 32; ++l) {
       const float bv = sb[l][tx];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) { const float av = sa[ty + 8 * r][l]; acc[r] = fma(static_cast<double>(av), static_cast<double>(bv), acc[r]); csum[r] += av; }
+      for (int r = 0; r < 4; ++r) { const float av = sa[ty + 8 * r][l]; acc[r] = fma(static_cast<AccT>(av), static_cast<AccT>(bv), acc[r]); csum[r] += av; }
     }
     __syncthreads();
   }
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(256) sgemm_strided_kernel(const float* __restr
   for (int r = 0; r < 4; ++r) {
     const int i = i0 + ty + 8 * r;
     if (i < I && j < J) {
-      float v = static_cast<float>(acc[r] + (bias ? static_cast<double>(bias[j]) : 0.0));
+      float v = static_cast<float>(acc[r] + (bias ? static_cast<AccT>(bias[j]) : static_cast<AccT>(0)));
       float* cp = C + i * ldc + j;
       *cp = accumulate ? *cp + v : v;
     }
@@ -197,7 +198,8 @@ static int launch_sgemm(const float* A, long long sai, long long sal, const floa
                         float* C, long long ldc, int I, int J, int L, const float* bias, int accumulate, float* colsum,
                         cudaStream_t stream) {
   dim3 grid((J + 31) / 32, (I + 31) / 32);
-  sgemm_strided_kernel<<<grid, 256, 0, stream>>>(A, sai, sal, B, sbl, sbj, C, ldc, I, J, L, bias, accumulate, colsum);
+  if (L >= 2048) sgemm_strided_kernel<double><<<grid, 256, 0, stream>>>(A, sai, sal, B, sbl, sbj, C, ldc, I, J, L, bias, accumulate, colsum);
+  else sgemm_strided_kernel<float><<<grid, 256, 0, stream>>>(A, sai, sal, B, sbl, sbj, C, ldc, I, J, L, bias, accumulate, colsum);
   return air_launch_status();
 }
 
