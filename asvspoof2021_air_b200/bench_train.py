@@ -97,9 +97,12 @@ def run(args, rank, world, helpers):
     # ---- roofline pass: per-family device time over a few profiled steps ----
     peaks = helpers.measured_peaks()
     nprof = 3
+    overlap = tr.engine.overlap_wgrad
+    tr.engine.overlap_wgrad = False          # per-launch times must not include a concurrently running kernel
     with ops.Profile() as prof:
         for i in range(nprof):
             step(i)
+    tr.engine.overlap_wgrad = overlap
     fam = prof.summary()
     conv = {k: v for k, v in fam.items() if k.startswith("conv_")}
     conv_ms = sum(v["ms"] for v in conv.values())
@@ -129,7 +132,9 @@ def run(args, rank, world, helpers):
                    % (args.workload, name, "eval forward" if scoring else "fwd/bwd",
                       "" if scoring else " + Adam(L2)/SGD", B),
                    "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
-                   "l2": "per-step activations (> 4 GB) exceed the 126 MB L2; waves rotate over %d buffers" % nbuf},
+                   "l2": "per-step activations (> 4 GB) exceed the 126 MB L2; waves rotate over %d buffers" % nbuf,
+                   "streams": "weight-gradient kernels on a side stream (overlap the HBM-bound BatchNorm backward); the "
+                              "roofline / per-family pass runs serialised" if overlap else "single stream"},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak if peak else None,
                      # ncu --set full of the largest launches (profiles/r01_ncu_full_v6_summary.txt): layer-1 3x3 fprop moves

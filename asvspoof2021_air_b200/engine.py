@@ -8,6 +8,7 @@ state_dict names as (permuted) views of that buffer, so the optimiser, the NCCL 
 checkpoints all work on the same storage.
 """
 import math
+import os
 
 import torch
 
@@ -295,6 +296,36 @@ def _resolve_lazies(obj):
             setattr(obj, k, v.owner.resolve(v.kind, v.idx))
 
 
+class AsyncWgrad:
+    """Mixin of the engines: weight-gradient launches on a side stream."""
+    # Weight gradients are leaves of the backward graph (they only feed the optimiser), so they run on a side stream:
+    # the tensor-core bound wgrad kernels then overlap the HBM-bound BatchNorm-backward kernels of the main chain.
+    overlap_wgrad = os.environ.get("AIR_OVERLAP_WGRAD", "1") != "0"
+    _side = None
+    _side_pending = False
+
+    def _wgrad_async(self, fn, *args):
+        if not self.overlap_wgrad:
+            fn(*args)
+            return
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        ev = torch.cuda.Event()
+        ev.record()                                   # the output gradient (and zero_grad) precede this point on the main stream
+        self._side.wait_event(ev)
+        with torch.cuda.stream(self._side):
+            fn(*args)
+        self._side_pending = True
+
+    def _join_side(self):
+        if self._side_pending:
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+            torch.cuda.current_stream().wait_event(ev)
+            self._side_pending = False
+
+
+
 # ==========================================================================================
 # ResNet-18 (pre-activation) + SelfAttention pooling      resnet.py:49-69,122-191
 # ==========================================================================================
@@ -302,7 +333,7 @@ class _Block:
     pass
 
 
-class ResNetEngine:
+class ResNetEngine(AsyncWgrad):
     """Forward / backward of ResNet(num_nodes=3, enc_dim, '18', nclasses) for a fixed batch size on
     channels-last bf16 activations.  Input: (B, 60, T) bf16 from the fused LFCC kernel."""
 
@@ -516,9 +547,9 @@ class ResNetEngine:
         self.store.grads.zero_()
 
     grad_hook = None        # optional callable(offset): every gradient at flat index >= offset is final
-
     def _ready(self, name):
         if self.grad_hook is not None:
+            self._join_side()
             self.grad_hook(self.store.offsets[name][0])
 
     def backward(self, dfeat, dmu=None):
@@ -538,20 +569,20 @@ class ResNetEngine:
         M5 = B * self.W5
         self.bn5.backward(self.g_z5, 256, self.c5, 256, self.g_c5, 256, M5, 0)
         last = self.blocks[-1]
-        self.conv5.wgrad(last.y, 512, B, last.Ho, last.Wo, self.g_c5, 256)
+        self._wgrad_async(self.conv5.wgrad, last.y, 512, B, last.Ho, last.Wo, self.g_c5, 256)
         self._ready("conv5.weight")
         self.conv5.dgrad(self.g_c5, 256, B, last.Ho, last.Wo, last.g_y, 512)
         for i in range(len(self.blocks) - 1, -1, -1):
             blk = self.blocks[i]
             Min, Mout = B * blk.H * blk.W, B * blk.Ho * blk.Wo
             g_x = self.blocks[i - 1].g_y if i > 0 else self.g_z1
-            blk.conv2.wgrad(blk.a2, blk.planes, B, blk.Ho, blk.Wo, blk.g_y, blk.planes)
+            self._wgrad_async(blk.conv2.wgrad, blk.a2, blk.planes, B, blk.Ho, blk.Wo, blk.g_y, blk.planes)
             blk.conv2.dgrad(blk.g_y, blk.planes, B, blk.Ho, blk.Wo, blk.g_a2, blk.planes)
             blk.bn2.backward(blk.g_a2, blk.planes, blk.h, blk.planes, blk.g_h, blk.planes, Mout, 0)
-            blk.conv1.wgrad(blk.a1, blk.cin, B, blk.H, blk.W, blk.g_h, blk.planes)
+            self._wgrad_async(blk.conv1.wgrad, blk.a1, blk.cin, B, blk.H, blk.W, blk.g_h, blk.planes)
             blk.conv1.dgrad(blk.g_h, blk.planes, B, blk.H, blk.W, blk.g_a1, blk.cin)
             if blk.sc is not None:
-                blk.sc.wgrad(blk.a1, blk.cin, B, blk.H, blk.W, blk.g_y, blk.planes)
+                self._wgrad_async(blk.sc.wgrad, blk.a1, blk.cin, B, blk.H, blk.W, blk.g_y, blk.planes)
                 blk.sc.dgrad(blk.g_y, blk.planes, B, blk.H, blk.W, blk.g_a1, blk.cin, accumulate=True)
                 blk.bn1.backward(blk.g_a1, blk.cin, blk.x, blk.cin, g_x, blk.cin, Min, 0)
             else:
@@ -559,4 +590,5 @@ class ResNetEngine:
             self._ready(blk.name + ".bn1.weight")
         M1 = B * self.H1 * self.W1
         self.bn1.backward(self.g_z1, 16, self.c1, 16, self.g_c1, 16, M1, 0)
-        ops.stem_wgrad(self.x0, B, self.H0, self.W0, 9, 3, 3, 1, 1, 1, self.g_c1, 16, st.grad("conv1.weight"))
+        self._wgrad_async(ops.stem_wgrad, self.x0, B, self.H0, self.W0, 9, 3, 3, 1, 1, 1, self.g_c1, 16, st.grad("conv1.weight"))
+        self._join_side()

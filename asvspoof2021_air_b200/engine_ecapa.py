@@ -15,7 +15,7 @@ import math
 import torch
 
 from . import ops
-from .engine import BF16, BNLayer, BufferStore, ConvLayer, ParamStore, _conv1d_pt, _ident, _resolve_lazies
+from .engine import AsyncWgrad, BF16, BNLayer, BufferStore, ConvLayer, ParamStore, _conv1d_pt, _ident, _resolve_lazies
 
 CLAMP = 1e-4
 
@@ -47,7 +47,7 @@ class _BN1d:
                      None if frozen else self.store.grad(self.name + ".bias"))
 
 
-class EcapaEngine:
+class EcapaEngine(AsyncWgrad):
     def __init__(self, C=512, scale=8, n_out=2, n_mels=60, bottleneck=128, enc_dim=256, device="cuda", train_head=False):
         assert C % scale == 0 and (C // scale) % 16 == 0
         self.C, self.scale, self.width, self.n_out, self.n_mels = C, scale, C // scale, n_out, n_mels
@@ -324,6 +324,7 @@ class EcapaEngine:
 
     def _ready(self, name):
         if self.grad_hook is not None:
+            self._join_side()
             self.grad_hook(self.store.offsets[name][0])
 
     def backward(self, dfeat, dlogits=None):
@@ -344,7 +345,7 @@ class EcapaEngine:
         ops.asp_bwd(self.e, C3, self.x4, C3, B, T, C3, self.pooled, self.g_pooled, self.smax, self.ssum, self.sq,
                     self.cmean, self.cstd, self.zeros_c3, self.zeros_c3, CLAMP, self.g_e, C3, self.g_x4, C3)
         # attention.3 (128 -> 1536)
-        self.att3.wgrad(self.a2, 128, B, 1, T, self.g_e, C3)
+        self._wgrad_async(self.att3.wgrad, self.a2, 128, B, 1, T, self.g_e, C3)
         ops.colsum(self.g_e, C3, M, C3, st.grad("attention.3.bias"))
         self.att3.dgrad(self.g_e, C3, B, 1, T, self.g_a2, 128)
         # attention.2 BN (+ the ReLU before it) ; dbias = bias gradient of attention.0
@@ -352,7 +353,7 @@ class EcapaEngine:
         # attention.0: x-block through the GEMMs, mean / std blocks through the per-utterance bias
         gw0 = st.grad("attention.0.weight").view(128, 3 * C3)
         w0 = st.view("attention.0.weight").view(128, 3 * C3)
-        ops.conv_wgrad_ld(self.x4, C3, B, 1, T, C3, self.g_a1, 128, 1, T, 128, 1, 1, 1, 1, 0, 0, 1, 1, gw0, 3 * C3)
+        self._wgrad_async(ops.conv_wgrad_ld, self.x4, C3, B, 1, T, C3, self.g_a1, 128, 1, T, 128, 1, 1, 1, 1, 0, 0, 1, 1, gw0, 3 * C3)
         ops.time_stats(self.g_a1, 128, B, T, 128, self.gu, None, -1.0)                          # sum over time
         ops.linear_bwd_ld(self.cmean, w0[:, C3:], 3 * C3, self.gu, self.dcmean, gw0[:, C3:], None, B, 128, C3)
         ops.linear_bwd_ld(self.cstd, w0[:, 2 * C3:], 3 * C3, self.gu, self.dcstd, gw0[:, 2 * C3:], None, B, 128, C3)
@@ -360,7 +361,7 @@ class EcapaEngine:
                          self.g_x4, C3, None, self.g_x4, C3, False)
         ops.ctx_bwd_mask(self.x4, C3, B, T, C3, self.cmean, self.cstd, self.dcmean, self.dcstd, CLAMP, self.g_x4, C3)
         # layer4 (1536 -> 1536)
-        self.layer4.wgrad(self.xcat, C3, B, 1, T, self.g_x4, C3)
+        self._wgrad_async(self.layer4.wgrad, self.xcat, C3, B, 1, T, self.g_x4, C3)
         ops.colsum(self.g_x4, C3, M, C3, st.grad("layer4.bias"))
         self.layer4.dgrad(self.g_x4, C3, B, 1, T, self.g_xcat, C3)
         self._ready("layer4.weight")
@@ -382,7 +383,7 @@ class EcapaEngine:
             ops.se_apply_bwd(dout, C3, blk.g, blk.ds, blk.g_o3, C, B, T, C)
             # bn3 / conv3
             self._bn_bwd(blk.bn3, blk.g_o3, C, blk.t3, C, blk.g_t3, C, M, st.grad(blk.name + ".conv3.bias"))
-            blk.conv3.wgrad(blk.cat, C, B, 1, T, blk.g_t3, C)
+            self._wgrad_async(blk.conv3.wgrad, blk.cat, C, B, 1, T, blk.g_t3, C)
             blk.conv3.dgrad(blk.g_t3, C, B, 1, T, blk.g_cat, C)
             # Res2 branches, last to first
             for i in range(self.scale - 2, -1, -1):
@@ -401,7 +402,7 @@ class EcapaEngine:
             ops.copy_channels(blk.g_cat[:, :, C - W:], C, blk.g_o1[:, :, C - W:], C, M, W)
             # bn1 / conv1
             self._bn_bwd(blk.bn1, blk.g_o1, C, blk.t1, C, blk.g_t1, C, M, st.grad(blk.name + ".conv1.bias"))
-            blk.conv1.wgrad(blk.xin, blk.xin_ld, B, 1, T, blk.g_t1, C)
+            self._wgrad_async(blk.conv1.wgrad, blk.xin, blk.xin_ld, B, 1, T, blk.g_t1, C)
             if li > 0:
                 prev = self.g_xcat[:, :, (li - 1) * C:li * C]
                 blk.conv1.dgrad(blk.g_t1, C, B, 1, T, prev, C3, accumulate=True)
@@ -410,4 +411,5 @@ class EcapaEngine:
             self._ready(blk.name + ".conv1.weight")
         # stem: bn1 / conv1 (no data gradient: the LFCC input needs none)
         self._bn_bwd(self.bn1, self.g_xb1, C, self.c1, C, self.g_c1, C, M, st.grad("conv1.bias"))
-        self.conv1.wgrad(self.x0, self.mels_g, B, 1, T, self.g_c1, C)
+        self._wgrad_async(self.conv1.wgrad, self.x0, self.mels_g, B, 1, T, self.g_c1, C)
+        self._join_side()
