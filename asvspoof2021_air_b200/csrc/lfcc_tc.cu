@@ -19,7 +19,6 @@
 //   epilogue warps(4): TMEM -> |X|^2 -> sparse triangular filterbank (2 filters per bin, compile-time structure,
 //                      run-time weights) -> log10 -> 20x20 DCT -> cepstra in smem -> deltas, pad/crop map, layout, dtype
 #include <algorithm>
-#include <cstdlib>
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -57,7 +56,6 @@ struct Params {
   int T;                    // frames per utterance (flat mode)
   int segs;                 // tiles per utterance (per-utterance mode)
   int tiles;
-  int dbg;                  // AIR_LFCC_DBG timing experiments: 1 no prep, 2 no MMA, 4 no DFT-matrix loads, 8 no epilogue math, 16 no output stage
 };
 
 // cos / sin (5 pi j / 8), j = k mod 16: the a[0] sample (window position 0, distance 160 from the fold centre)
@@ -170,7 +168,7 @@ __global__ void __launch_bounds__(THREADS, 1) lfcc_tc_kernel(const Params p) {
         mbar_wait(&a_empty[part], (it & 1) ^ 1);
         uint8_t* img_hi = gen + SM_A + (part * 2 + 0) * KBLK * CHUNK;
         uint8_t* img_lo = gen + SM_A + (part * 2 + 1) * KBLK * CHUNK;
-        for (int fr = pw; fr < ((p.dbg & 1) ? 0 : TM); fr += PREP_WARPS) {
+        for (int fr = pw; fr < TM; fr += PREP_WARPS) {
           int b = 0, t = 0;
           const bool valid = row_bt(p, tile, fr, b, t);
           const int len = valid ? (p.lengths ? max(0, min(p.lengths[b], p.L)) : p.L) : 0;
@@ -228,7 +226,6 @@ __global__ void __launch_bounds__(THREADS, 1) lfcc_tc_kernel(const Params p) {
       for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
         for (int s = 0; s < 2 * 2 * KBLK * 2; ++s) {
           mbar_wait(&b_empty[slot], phase ^ 1);
-          if (p.dbg & 4) { mbar_arrive(&b_full[slot]); if (++slot == NSLOT) { slot = 0; phase ^= 1; } continue; }
           mbar_arrive_expect_tx(&b_full[slot], CHUNK);
           bulk_g2s(sbase + SM_B + slot * CHUNK, p.wmat + static_cast<long long>(s) * (CHUNK / 2), CHUNK, &b_full[slot]);
           if (++slot == NSLOT) { slot = 0; phase ^= 1; }
@@ -237,8 +234,8 @@ __global__ void __launch_bounds__(THREADS, 1) lfcc_tc_kernel(const Params p) {
     }
   } else if (warp == 4) {
     // ===================== MMA issuer (warp-uniform loop, elected lane issues) =====================
-    const bool leader = elect_one() && !(p.dbg & 2);
-    const bool committer = elect_one();
+    const bool leader = elect_one();
+    const bool committer = leader;
     const uint32_t idesc = instr_desc_bf16(128, 128, 0, 0);
     const uint32_t desc_hi = (512u >> 4) | (1u << 14) | (4u << 29);      // SBO = 8 rows x 64 B, version 1, SWIZZLE_64B
     const uint32_t a16 = ((sbase + SM_A) >> 4) & 0x3FFF, b16 = ((sbase + SM_B) >> 4) & 0x3FFF;
@@ -308,12 +305,12 @@ __global__ void __launch_bounds__(THREADS, 1) lfcc_tc_kernel(const Params p) {
       // a0 was written (double-buffered by tile parity) before the prep warps released a_full[0], which the MMA warp
       // acquired before issuing the MMAs whose completion tfull[0] tracks
       const float a0 = s_a0[(it & 1) * TM + row];
-      if (!(p.dbg & 8)) epilogue_half<0>(tcol, a0, s_fbw, fbv);
+      epilogue_half<0>(tcol, a0, s_fbw, fbv);
       fence_before_sync();
       mbar_arrive(&tempty[0]);
       mbar_wait(&tfull[1], it & 1);
       fence_after_sync();
-      if (!(p.dbg & 8)) epilogue_half<1>(tcol, a0, s_fbw, fbv);
+      epilogue_half<1>(tcol, a0, s_fbw, fbv);
       fence_before_sync();
       mbar_arrive(&tempty[1]);
       // log10 + DCT-II ortho (feature_extraction.py:116-120)
@@ -334,7 +331,7 @@ __global__ void __launch_bounds__(THREADS, 1) lfcc_tc_kernel(const Params p) {
       // the utterance of each output row is recomputed (tiles may straddle two utterances).
       int ub = -1; UttInfo u{};
       const int total = TOUT * NF;
-      for (int i = row; i < ((p.dbg & 16) ? 0 : total); i += 128) {
+      for (int i = row; i < total; i += 128) {
         int fo, k;
         if (p.time_minor) { k = i / TOUT; fo = i - k * TOUT; } else { fo = i / NF; k = i - fo * NF; }
         const int r = HALO + fo;
@@ -396,7 +393,6 @@ extern "C" int air_lfcc_tc_fwd(const float* wave, long long ldw, const int* leng
   p.out = out; p.sb = sb; p.sj = sj; p.sd = sd; p.out_bf16 = out_bf16; p.time_minor = (sj == 1);
   p.Tout = Tout; p.feat_len = feat_len > 0 ? feat_len : 0; p.pad_mode = feat_len > 0 ? pad_mode : 0;
   p.start = start; p.preemph = preemph;
-  { const char* e = getenv("AIR_LFCC_DBG"); p.dbg = e ? atoi(e) : 0; }
   // flat tiling needs identical frame counts and no crop
   p.flat = (lengths == nullptr && !(p.feat_len > 0 && Tmax > p.feat_len)) ? 1 : 0;
   p.T = Tmax;
