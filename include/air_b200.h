@@ -83,7 +83,9 @@ int air_lfcc_fill(const int* lengths, int B, int L, void* out, long long sb, lon
  *                   dy at ((h + ph - i*dh)/sh, (w + pw - j*dw)/sw) of the (H, W, C) = dy grid
  *                   when divisible and in range.
  *   a_ld / out_ld / res_ld: elements between consecutive pixels (channel slices are allowed).
- *   Constraints: C, a_ld, out_ld, res_ld multiples of 8; N multiple of 16; 16-byte aligned bases.
+ *   Constraints: C, a_ld, out_ld, res_ld multiples of 8; N multiple of 16; 16-byte aligned bases (bias included).
+ *   1x1 / stride-1 layers take a TMA path (the A tile is a plain 2-D box of the [pixels][channels] matrix).
+ *   `flags` is reserved and must be 0.
  * --------------------------------------------------------------------------------------------- */
 int air_conv_block_n(int N);
 long long air_conv_packed_elems(int N, int K);
