@@ -34,7 +34,7 @@ constexpr int TW = 128;                 // output columns per row segment (UMMA 
 constexpr int PW = TW + 2;              // patch width
 constexpr int R = 2;                    // output rows per work item
 constexpr int PR = R + 2;               // patch rows
-constexpr int PPIX = PR * PW;           // 520 patch pixels
+constexpr int PW_MAX = TW + 8;          // widest patch (dilated 1-D convolutions)
 constexpr int THREADS = 256;
 constexpr int PSTAGES = 2;
 constexpr int MAX_TAPS = 9;
@@ -43,10 +43,13 @@ struct PatchParams {
   int B, GH, GW;                        // images, output pixel grid enumerated by the items
   int OH, OW, osh, osw, oph, opw;       // output tensor geometry: grid (g, g') -> pixel (g*osh + oph, g'*osw + opw)
   int org_h, org_w;                     // patch origin relative to (first grid row, first grid column) of the item
+  int pw;                               // patch width in pixels: TW + 2 (3x3) or TW + 8 (dilated 1-D taps up to +8)
   int C, N;
   const __nv_bfloat16* wpk; int wtaps;  // packed weights: [C/CB][wtaps] slices of [N][CB]
   __nv_bfloat16* out; long long out_ld;
   const __nv_bfloat16* res; long long res_ld; int relu;
+  const float* bias;                    // optional per-channel bias (ECAPA convs, ecapa_tdnn.py:39,50)
+  __nv_bfloat16* out2; long long out2_ld;   // optional second output: accumulator (+bias) WITHOUT the residual
   int CB, NCB, WT, HP;                  // channels per block (16 / 32 / 64), #blocks, column tiles, row pairs
   int row_bytes, layout;                // CB * 2; UMMA layout type (6 / 4 / 2)
   uint32_t pstage_bytes, bslot_bytes, bslot_stride;
@@ -72,6 +75,19 @@ __device__ __forceinline__ void epilogue_chunk(const PatchParams& p, uint32_t ta
   float v[NC];
   if (NC == 32) tmem_ld32(taddr + c0, v); else tmem_ld16(taddr + c0, v);
   if (valid) {
+    if (p.bias != nullptr) {
+      const float4* bp = reinterpret_cast<const float4*>(p.bias + c0);
+#pragma unroll
+      for (int i = 0; i < NC / 4; ++i) {
+        const float4 b4 = __ldg(bp + i);
+        v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+      }
+    }
+    if (p.out2 != nullptr) {
+      bf16x8* o2 = reinterpret_cast<bf16x8*>(p.out2 + pixel * p.out2_ld + c0);
+#pragma unroll
+      for (int i = 0; i < NC / 8; ++i) o2[i] = pack8(v + i * 8);
+    }
     if (p.res != nullptr) {
 #pragma unroll
       for (int i = 0; i < NC / 8; ++i) {
@@ -135,7 +151,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_patch_kernel(const __grid_con
         const int c3 = static_cast<int>(r1 / HP);
         for (int cb = 0; cb < p.NCB; ++cb) {
           mbar_wait(&empty_p[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_p[stage], static_cast<uint32_t>(PPIX) * p.row_bytes);
+          mbar_arrive_expect_tx(&full_p[stage], static_cast<uint32_t>(PR * p.pw) * p.row_bytes);
           tma_load_4d(sP + stage * p.pstage_bytes, &tmap, cb * p.CB, c1, c2, c3, &full_p[stage]);
           if (++stage == PSTAGES) { stage = 0; phase ^= 1; }
         }
@@ -202,7 +218,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_patch_kernel(const __grid_con
 #pragma unroll
           for (int j = 0; j < R; ++j) {
             if (j < rows) {
-              const uint32_t arow = a_tap + static_cast<uint32_t>(j * PW) * rb16;
+              const uint32_t arow = a_tap + static_cast<uint32_t>(j * p.pw) * rb16;
               // persistent 64-bit descriptors, advanced in place by 32 B per K step (keeps the issue loop at
               // ~5 uniform instructions per MMA instead of rebuilding both register pairs)
               uint64_t ad = (static_cast<uint64_t>(desc_hi) << 32) | arow;
@@ -331,13 +347,37 @@ extern "C" int air_conv3x3_pack_weights(const float* w, void* dst, int C, int N,
 //   a: (B, Hin, Win, C) channels-last bf16;  out / res: (B, OH, OW, N);  item grid GH x GW;
 //   tap t reads the window that starts at patch pixel (tap_dr[t], tap_dc[t]) (0 <= dr, dc <= 2) and uses weight slice
 //   tap_slice[t] (< wtaps) of every channel block.
+extern "C" int air_conv_patch_taps_ex_bf16(const void* a, long long a_ld, int B, int Hin, int Win, int C,
+                                           const void* wpk, int wtaps, int N, void* out, long long out_ld, int OH, int OW,
+                                           const void* res, long long res_ld, int relu, const float* bias,
+                                           void* out2, long long out2_ld,
+                                           int GH, int GW, int org_h, int org_w, int osh, int osw, int oph, int opw,
+                                           int ntaps, const int* tap_dr, const int* tap_dc, const int* tap_slice,
+                                           int num_sms, cudaStream_t stream);
+
 extern "C" int air_conv_patch_taps_bf16(const void* a, long long a_ld, int B, int Hin, int Win, int C,
                                         const void* wpk, int wtaps, int N, void* out, long long out_ld, int OH, int OW,
                                         const void* res, long long res_ld, int relu,
                                         int GH, int GW, int org_h, int org_w, int osh, int osw, int oph, int opw,
                                         int ntaps, const int* tap_dr, const int* tap_dc, const int* tap_slice,
                                         int num_sms, cudaStream_t stream) {
+  return air_conv_patch_taps_ex_bf16(a, a_ld, B, Hin, Win, C, wpk, wtaps, N, out, out_ld, OH, OW, res, res_ld, relu, nullptr,
+                                     nullptr, 0, GH, GW, org_h, org_w, osh, osw, oph, opw, ntaps, tap_dr, tap_dc, tap_slice,
+                                     num_sms, stream);
+}
+
+// as air_conv_patch_taps_bf16 plus a per-channel fp32 bias, a second output without the residual, and column offsets
+// tap_dc up to 8 (the patch is then 136 pixels wide): the dilated k = 3 1-D convolutions of ecapa_tdnn.py:50
+extern "C" int air_conv_patch_taps_ex_bf16(const void* a, long long a_ld, int B, int Hin, int Win, int C,
+                                           const void* wpk, int wtaps, int N, void* out, long long out_ld, int OH, int OW,
+                                           const void* res, long long res_ld, int relu, const float* bias,
+                                           void* out2, long long out2_ld,
+                                           int GH, int GW, int org_h, int org_w, int osh, int osw, int oph, int opw,
+                                           int ntaps, const int* tap_dr, const int* tap_dc, const int* tap_slice,
+                                           int num_sms, cudaStream_t stream) {
   if (!a || !wpk || !out || B <= 0 || !tap_dr || !tap_dc || !tap_slice) return AIR_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(out2)) & 15) return AIR_ERR_UNSUPPORTED;
+  if (out2 && out2_ld % 8 != 0) return AIR_ERR_UNSUPPORTED;
   if (ntaps < 1 || ntaps > MAX_TAPS || wtaps < 1 || GH < 1 || GW < 1 || osh < 1 || osw < 1 || oph < 0 || opw < 0) return AIR_ERR_ARG;
   if (!air_conv3x3_patch_supported(C, N, Hin, Win)) return AIR_ERR_UNSUPPORTED;
   if (a_ld % 8 != 0 || out_ld % 8 != 0 || (res && res_ld % 8 != 0)) return AIR_ERR_UNSUPPORTED;
@@ -351,10 +391,14 @@ extern "C" int air_conv_patch_taps_bf16(const void* a, long long a_ld, int B, in
   p.res = reinterpret_cast<const __nv_bfloat16*>(res); p.res_ld = res_ld; p.relu = relu;
   p.ntaps = ntaps;
   for (int t = 0; t < MAX_TAPS; ++t) { p.tap_off[t] = 0; p.tap_slice[t] = 0; }
+  int max_dc = 0;
+  for (int t = 0; t < ntaps; ++t) max_dc = std::max(max_dc, tap_dc[t]);
+  p.pw = max_dc <= PW - TW ? PW : PW_MAX;
+  p.bias = bias; p.out2 = reinterpret_cast<__nv_bfloat16*>(out2); p.out2_ld = out2_ld;
   for (int t = 0; t < ntaps; ++t) {
-    if (tap_dr[t] < 0 || tap_dr[t] > PR - R || tap_dc[t] < 0 || tap_dc[t] > PW - TW || tap_slice[t] < 0 || tap_slice[t] >= wtaps)
+    if (tap_dr[t] < 0 || tap_dr[t] > PR - R || tap_dc[t] < 0 || tap_dc[t] > p.pw - TW || tap_slice[t] < 0 || tap_slice[t] >= wtaps)
       return AIR_ERR_ARG;
-    p.tap_off[t] = tap_dr[t] * PW + tap_dc[t];
+    p.tap_off[t] = tap_dr[t] * p.pw + tap_dc[t];
     p.tap_slice[t] = tap_slice[t];
   }
   p.CB = patch_cb(C); p.NCB = C / p.CB; p.WT = (GW + TW - 1) / TW; p.HP = (GH + R - 1) / R;
@@ -363,7 +407,7 @@ extern "C" int air_conv_patch_taps_bf16(const void* a, long long a_ld, int B, in
   if (items > 0x7fffffffLL) return AIR_ERR_UNSUPPORTED;
   p.items = static_cast<uint32_t>(items);
   p.acc_stages = (2 * R * N <= 512) ? 2 : 1;
-  p.pstage_bytes = static_cast<uint32_t>((PPIX * p.row_bytes + 1023) / 1024 * 1024);
+  p.pstage_bytes = static_cast<uint32_t>((PR * p.pw * p.row_bytes + 1023) / 1024 * 1024);
   p.bslot_bytes = static_cast<uint32_t>(N * p.row_bytes);
   p.bslot_stride = (p.bslot_bytes + 1023u) / 1024u * 1024u;
   const int budget = 225 * 1024 - PSTAGES * static_cast<int>(p.pstage_bytes) - 2048;
@@ -375,7 +419,7 @@ extern "C" int air_conv_patch_taps_bf16(const void* a, long long a_ld, int B, in
   const size_t smem = 1024 + static_cast<size_t>(PSTAGES) * p.pstage_bytes + static_cast<size_t>(slots) * p.bslot_stride +
                       (2 * PSTAGES + 2 * slots + 4) * 8 + 16;
   CUtensorMap tm;
-  const int tr = air_tmap::make_act_tmap(&tm, a, a_ld, B, Hin, Win, C, p.CB, PW, PR, p.row_bytes);
+  const int tr = air_tmap::make_act_tmap(&tm, a, a_ld, B, Hin, Win, C, p.CB, p.pw, PR, p.row_bytes);
   if (tr != 0) return tr < 0 ? AIR_ERR_UNSUPPORTED : 10000 + tr;
   static bool attr_done = false;
   if (!attr_done) {

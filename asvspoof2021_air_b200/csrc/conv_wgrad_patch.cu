@@ -42,7 +42,8 @@ struct WParams {
   int parts;                                        // CTAs per job
   // operand geometry: "wide" = 64 input channels per pixel row (SWIZZLE_128B, two 64-row groups per M = 128),
   // "narrow" = 16 input channels (SWIZZLE_32B, eight 16-row groups = eight consecutive pixel shifts per M = 128)
-  int narrow, ktaps, org;                           // ktaps = 9 (3x3 / pad 1, org = -1) or 1 (1x1 / pad 0, org = 0)
+  int narrow, ktaps, org_h, org_w;                  // taps of the layer; patch origin relative to the item's first pixel
+  int pw;                                           // patch width in pixels (TW + 2, or TW + 8 for dilated 1-D taps)
   uint32_t x_bytes, stage_bytes;
   int nacc; int acc_off[NACC]; int acc_lbo[NACC];   // per accumulator: window offset / group distance, in patch pixels
   int acc_tap[NACC][8];                             // tap of each M row group (-1: not a real tap)
@@ -90,8 +91,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_wgrad_patch_kernel(const _
         const int w0 = static_cast<int>(wt) * TW, h0 = static_cast<int>(r1 % HP) * R, b = static_cast<int>(r1 / HP);
         mbar_wait(&empty[stage], phase ^ 1);
         const uint32_t dst = sbase + stage * p.stage_bytes;
-        mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>(PPIX) * (p.narrow ? 32u : 128u) + DY_BYTES);
-        tma_load_4d(dst, &tmx, p.narrow ? 0 : cb * 64, w0 + p.org, h0 + p.org, b, &full[stage]);
+        mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>(PR * p.pw) * (p.narrow ? 32u : 128u) + DY_BYTES);
+        tma_load_4d(dst, &tmx, p.narrow ? 0 : cb * 64, w0 + p.org_w, h0 + p.org_h, b, &full[stage]);
         tma_load_4d(dst + p.x_bytes, &tmdy, nb * 64, w0, h0, b, &full[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_wgrad_patch_kernel(const _
 #pragma unroll 2
         for (int ks = 0; ks < TW / 16; ++ks) {
           const uint64_t bd = bbase + (d16 + static_cast<uint32_t>(r * TW + ks * 16) * 8);
-          const uint32_t xrow = x16 + static_cast<uint32_t>(r * PW + ks * 16) * upp;
+          const uint32_t xrow = x16 + static_cast<uint32_t>(r * p.pw + ks * 16) * upp;
 #pragma unroll
           for (int a = 0; a < NACC; ++a) {
             if (a < p.nacc) {
@@ -176,40 +177,54 @@ static bool wpatch_ok(int C, int N) {
 
 extern "C" int air_conv3x3_wgrad_patch_supported(int C, int N) { return wpatch_ok(C, N) ? 1 : 0; }
 
-// dw_out: fp32 [N][dw_ld >= k*k*C] in GEMM layout [Cout][tap][Cin], accumulated in place (caller zeroes).
-// k = 3: 3x3 / stride 1 / pad 1;  k = 1: 1x1 / stride 1 / pad 0.  C = 16 or a multiple of 64; N a multiple of 64.
-extern "C" int air_conv_wgrad_patch_bf16(const void* x, long long x_ld, int B, int H, int W, int C,
-                                         const void* dy, long long dy_ld, int N, int k,
-                                         float* dw_out, long long dw_ld, int num_sms, cudaStream_t stream) {
-  if (!x || !dy || !dw_out || B <= 0 || H < 1 || W < 1 || (k != 3 && k != 1)) return AIR_ERR_ARG;
+// General launcher: explicit tap list.  Tap t reads the x window that starts at patch pixel (tap_dr[t], tap_dc[t]) and
+// accumulates into dw_out[co][t][ci] (GEMM layout [Cout][ntaps][Cin], fp32, caller zeroes).  Wide mode (C % 64 == 0) pairs
+// consecutive taps in one M = 128 instruction; narrow mode (C == 16) needs runs of taps that are consecutive in dc.
+static int launch_wgrad_patch(const void* x, long long x_ld, int B, int H, int W, int C, const void* dy, long long dy_ld, int N,
+                              int ntaps, const int* tap_dr, const int* tap_dc, int org_h, int org_w,
+                              float* dw_out, long long dw_ld, int num_sms, cudaStream_t stream) {
+  if (!x || !dy || !dw_out || B <= 0 || H < 1 || W < 1 || ntaps < 1 || ntaps > 9) return AIR_ERR_ARG;
   if (!wpatch_ok(C, N)) return AIR_ERR_UNSUPPORTED;
-  if (x_ld % 8 != 0 || dy_ld % 8 != 0 || dw_ld < static_cast<long long>(k) * k * C) return AIR_ERR_ARG;
+  if (x_ld % 8 != 0 || dy_ld % 8 != 0 || dw_ld < static_cast<long long>(ntaps) * C) return AIR_ERR_ARG;
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) return AIR_ERR_UNSUPPORTED;
   WParams p;
   p.B = B; p.H = H; p.W = W; p.C = C; p.N = N; p.dw = dw_out; p.dw_ld = dw_ld;
-  p.narrow = (C == 16) ? 1 : 0; p.ktaps = k * k; p.org = (k == 3) ? -1 : 0;
+  p.narrow = (C == 16) ? 1 : 0; p.ktaps = ntaps; p.org_h = org_h; p.org_w = org_w;
+  int max_dc = 0;
+  for (int t = 0; t < ntaps; ++t) {
+    if (tap_dr[t] < 0 || tap_dr[t] > PR - R || tap_dc[t] < 0 || tap_dc[t] > 8) return AIR_ERR_ARG;
+    max_dc = std::max(max_dc, tap_dc[t]);
+  }
+  p.pw = max_dc <= 2 ? PW : TW + 8;
   p.NCB = p.narrow ? 1 : C / 64; p.NNB = N / 64; p.WT = (W + TW - 1) / TW; p.HP = (H + R - 1) / R;
-  p.x_bytes = p.narrow ? ((PPIX * 32u + 1023u) / 1024u * 1024u) : X_BYTES;
+  p.x_bytes = (static_cast<uint32_t>(PR * p.pw) * (p.narrow ? 32u : 128u) + 1023u) / 1024u * 1024u;
   p.stage_bytes = p.x_bytes + DY_BYTES;
   for (int a = 0; a < NACC; ++a) { p.acc_off[a] = 0; p.acc_lbo[a] = 0; for (int g = 0; g < 8; ++g) p.acc_tap[a][g] = -1; }
+  int off[9];
+  for (int t = 0; t < ntaps; ++t) off[t] = tap_dr[t] * p.pw + tap_dc[t];
+  p.nacc = 0;
   if (p.narrow) {
-    // eight 16-row groups = eight consecutive pixel shifts: one accumulator per kernel row, taps j = 0..2 are real
-    p.nacc = (k == 3) ? 3 : 1;
-    for (int a = 0; a < p.nacc; ++a) {
-      p.acc_off[a] = a * PW; p.acc_lbo[a] = 1;
-      for (int g = 0; g < (k == 3 ? 3 : 1); ++g) p.acc_tap[a][g] = a * 3 + g;
-    }
-  } else if (k == 3) {
-    // two 64-row groups = two taps: (0,1) (2,3) (4,5) (6,7) (8,-)
-    p.nacc = 5;
-    for (int a = 0; a < 5; ++a) {
-      const int t0 = 2 * a, t1 = (2 * a + 1 < 9) ? 2 * a + 1 : 2 * a;
-      const int o0 = (t0 / 3) * PW + (t0 % 3), o1 = (t1 / 3) * PW + (t1 % 3);
-      p.acc_off[a] = o0; p.acc_lbo[a] = o1 - o0;
-      p.acc_tap[a][0] = t0; p.acc_tap[a][1] = (2 * a + 1 < 9) ? t1 : -1;
+    // eight 16-row groups = eight consecutive pixel shifts: one accumulator per run of taps with consecutive offsets
+    int t = 0;
+    while (t < ntaps) {
+      if (p.nacc == NACC) return AIR_ERR_UNSUPPORTED;
+      const int a = p.nacc++;
+      p.acc_off[a] = off[t]; p.acc_lbo[a] = 1;
+      int g = 0;
+      p.acc_tap[a][g++] = t++;
+      while (t < ntaps && g < 8 && off[t] == off[t - 1] + 1) p.acc_tap[a][g++] = t++;
     }
   } else {
-    p.nacc = 1; p.acc_tap[0][0] = 0;                 // second row group duplicates the first (lbo = 0), ignored
+    // two 64-row groups = two taps per instruction (the second one through the leading byte offset)
+    for (int t = 0; t < ntaps; t += 2) {
+      if (p.nacc == NACC) return AIR_ERR_UNSUPPORTED;
+      const int a = p.nacc++;
+      p.acc_off[a] = off[t]; p.acc_tap[a][0] = t;
+      if (t + 1 < ntaps) {
+        if (off[t + 1] < off[t]) return AIR_ERR_ARG;                 // offsets must ascend (LBO is unsigned)
+        p.acc_lbo[a] = off[t + 1] - off[t]; p.acc_tap[a][1] = t + 1;
+      }                                                              // else: lbo = 0, the second group duplicates the first
+    }
   }
   const long long items = static_cast<long long>(B) * p.HP * p.WT;
   if (items > 0x7fffffffLL) return AIR_ERR_UNSUPPORTED;
@@ -219,8 +234,8 @@ extern "C" int air_conv_wgrad_patch_bf16(const void* x, long long x_ld, int B, i
   if (jobs > num_sms) return AIR_ERR_UNSUPPORTED;
   p.parts = static_cast<int>(std::min<long long>(num_sms / jobs, items));
   CUtensorMap tmx, tmdy;
-  int tr = p.narrow ? air_tmap::make_act_tmap(&tmx, x, x_ld, B, H, W, C, 16, PW, PR, 32)
-                    : air_tmap::make_act_tmap(&tmx, x, x_ld, B, H, W, C, 64, PW, PR, 128);
+  int tr = p.narrow ? air_tmap::make_act_tmap(&tmx, x, x_ld, B, H, W, C, 16, p.pw, PR, 32)
+                    : air_tmap::make_act_tmap(&tmx, x, x_ld, B, H, W, C, 64, p.pw, PR, 128);
   if (tr == 0) tr = air_tmap::make_act_tmap(&tmdy, dy, dy_ld, B, H, W, N, 64, TW, R, 128);
   if (tr != 0) return tr < 0 ? AIR_ERR_UNSUPPORTED : 10000 + tr;
   const size_t smem = 1024 + static_cast<size_t>(STAGES) * p.stage_bytes + (2 * STAGES + 1) * 8 + 16;
@@ -232,6 +247,29 @@ extern "C" int air_conv_wgrad_patch_bf16(const void* x, long long x_ld, int B, i
   }
   conv3x3_wgrad_patch_kernel<<<jobs * p.parts, THREADS, smem, stream>>>(tmx, tmdy, p);
   return air_launch_status();
+}
+
+// dw_out: fp32 [N][dw_ld >= k*k*C] in GEMM layout [Cout][tap][Cin], accumulated in place (caller zeroes).
+// k = 3: 3x3 / stride 1 / pad 1;  k = 1: 1x1 / stride 1 / pad 0.  C = 16 or a multiple of 64; N a multiple of 64.
+extern "C" int air_conv_wgrad_patch_bf16(const void* x, long long x_ld, int B, int H, int W, int C,
+                                         const void* dy, long long dy_ld, int N, int k,
+                                         float* dw_out, long long dw_ld, int num_sms, cudaStream_t stream) {
+  if (k != 3 && k != 1) return AIR_ERR_ARG;
+  int dr[9], dc[9];
+  for (int t = 0; t < k * k; ++t) { dr[t] = t / k; dc[t] = t % k; }
+  return launch_wgrad_patch(x, x_ld, B, H, W, C, dy, dy_ld, N, k * k, dr, dc, k == 3 ? -1 : 0, k == 3 ? -1 : 0,
+                            dw_out, dw_ld, num_sms, stream);
+}
+
+// 1-D convolution over W (H rows are independent sequences), kernel k <= 5, dilation d, "same" padding d*(k-1)/2, with
+// d*(k-1) <= 8: the dilated Conv1d of the Res2 branches (ecapa_tdnn.py:50).  dw_out [N][k][C].
+extern "C" int air_conv1d_wgrad_patch_bf16(const void* x, long long x_ld, int B, int H, int W, int C,
+                                           const void* dy, long long dy_ld, int N, int k, int d,
+                                           float* dw_out, long long dw_ld, int num_sms, cudaStream_t stream) {
+  if (k < 1 || k > 5 || (k & 1) == 0 || d < 1 || d * (k - 1) > 8) return AIR_ERR_UNSUPPORTED;
+  int dr[9], dc[9];
+  for (int t = 0; t < k; ++t) { dr[t] = 0; dc[t] = t * d; }
+  return launch_wgrad_patch(x, x_ld, B, H, W, C, dy, dy_ld, N, k, dr, dc, 0, -d * (k - 1) / 2, dw_out, dw_ld, num_sms, stream);
 }
 
 extern "C" int air_conv3x3_wgrad_patch_bf16(const void* x, long long x_ld, int B, int H, int W, int C,

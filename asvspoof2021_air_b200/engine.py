@@ -108,10 +108,15 @@ class ConvLayer:
         # 1x1 / stride-1 layers: a GEMM over pixels through the same TMA kernel (single tap)
         self.p1x1_ok = (geom == (1, 1, 1, 1, 0, 0, 1, 1) and plain and ops.patch_supported(cin, cout, 1, 1)
                         and (not need_dgrad or ops.patch_supported(cout, cin, 1, 1)))
+        # dilated 1-D layers (k = 3, "same" padding, reach d*(k-1) <= 8): the Res2 branches of ECAPA
+        self.d1_ok = (kh == 1 and kw in (3, 5) and (sh, sw, ph, dh) == (1, 1, 0, 1) and pw == dw * (kw - 1) // 2
+                      and dw * (kw - 1) <= 8 and self._wtmp is None and cin % 64 == 0 and cout % 64 == 0 and cout <= 256
+                      and ops.patch_supported(cin, cout, 1, 1) and ops.patch_supported(cout, cin, 1, 1)
+                      and ops.wgrad_patch_supported(cin, cout))
         n = self.taps * cin * cout
-        self.wpk3 = torch.empty(n, device=dev, dtype=BF16) if (self.patch_ok or self.p1x1_ok) else None
+        self.wpk3 = torch.empty(n, device=dev, dtype=BF16) if (self.patch_ok or self.p1x1_ok or self.d1_ok) else None
         self.wpk3_d = torch.empty(n, device=dev, dtype=BF16) if (need_dgrad and (self.patch_ok or self.s2_dgrad_ok
-                                                                                 or self.p1x1_ok)) else None
+                                                                                 or self.p1x1_ok or self.d1_ok)) else None
 
     @staticmethod
     def _patch_efficiency(H, W):
@@ -168,6 +173,10 @@ class ConvLayer:
             ops.conv1x1_patch(x, x_ld, B, H, W, self.cin, self.wpk3, self.cout, out, out_ld, res, res_ld, relu, 0)
             return Ho, Wo
         bias = self.store.view(self.name + ".bias") if self.bias else None
+        if self.d1_ok:
+            ops.conv1d_patch(x, x_ld, B, H, W, self.cin, self.wpk3, self.kw, self.dw, self.cout, out, out_ld, bias,
+                             res, res_ld, relu, None, 0, 0)
+            return Ho, Wo
         ops.conv_gemm(x, x_ld, B, H, W, self.cin_g, Ho, Wo, self.kh, self.kw, self.sh, self.sw, self.ph, self.pw,
                       self.dh, self.dw, 0, self.wpk, self.cout, self.K, out, out_ld, bias, res, res_ld, relu)
         return Ho, Wo
@@ -192,6 +201,10 @@ class ConvLayer:
         if out2 is None and self.p1x1_ok:
             ops.conv1x1_patch(dy, dy_ld, B, H, W, self.cout, self.wpk3_d, self.cin, dx, dx_ld, res, res_ld, False, 1)
             return
+        if self.d1_ok:
+            ops.conv1d_patch(dy, dy_ld, B, H, W, self.cout, self.wpk3_d, self.kw, self.dw, self.cin, dx, dx_ld, None,
+                             res, res_ld, False, out2, out2_ld, 1)
+            return
         if out2 is None and self.s2_dgrad_ok and (self.kh == 3 or accumulate):
             ops.conv_s2_dgrad_patch(dy, dy_ld, B, Ho, Wo, self.cout, self.wpk3_d, self.kh, self.cin, dx, dx_ld, H, W,
                                     res, res_ld)
@@ -202,6 +215,10 @@ class ConvLayer:
 
     def wgrad(self, x, x_ld, B, H, W, dy, dy_ld):
         Ho, Wo = self.out_hw(H, W)
+        if self.d1_ok:
+            ops.conv1d_wgrad_patch(x, x_ld, B, H, W, self.cin, dy, dy_ld, self.cout, self.kw, self.dw,
+                                   self.store.grad(self.name + ".weight"))
+            return
         if self.wpatch_ok and self._patch_efficiency(H, W) >= 0.5:
             ops.conv_wgrad_patch(x, x_ld, B, H, W, self.cin, dy, dy_ld, self.cout, self.kh,
                                  self.store.grad(self.name + ".weight"))

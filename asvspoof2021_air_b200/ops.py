@@ -131,6 +131,28 @@ def conv1x1_patch(a, a_ld, B, H, W, C, wpk, N, out, out_ld, res=None, res_ld=0, 
     return out
 
 
+def conv1d_patch(a, a_ld, B, H, W, C, wpk, k, d, N, out, out_ld, bias=None, res=None, res_ld=0, relu=False,
+                 out2=None, out2_ld=0, mode=0):
+    """1-D convolution over W (H independent rows), kernel k, dilation d, 'same' padding, through the TMA patch kernel.
+    mode 0: forward (mode-0 packed weights); mode 1: data gradient (mode-1 packed weights)."""
+    zero = (ctypes.c_int * k)(*([0] * k))
+    dc = (ctypes.c_int * k)(*[t * d for t in range(k)])
+    sl = (ctypes.c_int * k)(*range(k))
+    _lib.check(_lib.lib().air_conv_patch_taps_ex_bf16(
+        _lib.ptr(a), _lib.LL(a_ld), B, H, W, C, _lib.ptr(wpk), k, N, _lib.ptr(out), _lib.LL(out_ld), H, W,
+        _lib.ptr(res), _lib.LL(res_ld), int(relu), _lib.ptr(bias), _lib.ptr(out2), _lib.LL(out2_ld),
+        H, W, 0, -d * (k - 1) // 2, 1, 1, 0, 0, k, zero, dc, sl, num_sms(), _lib.stream_ptr()),
+        "air_conv_patch_taps_ex_bf16")
+    return out
+
+
+def conv1d_wgrad_patch(x, x_ld, B, H, W, C, dy, dy_ld, N, k, d, dw_out, dw_ld=None):
+    _lib.check(_lib.lib().air_conv1d_wgrad_patch_bf16(
+        _lib.ptr(x), _lib.LL(x_ld), B, H, W, C, _lib.ptr(dy), _lib.LL(dy_ld), N, k, d, _lib.ptr(dw_out),
+        _lib.LL(k * C if dw_ld is None else dw_ld), num_sms(), _lib.stream_ptr()), "air_conv1d_wgrad_patch_bf16")
+    return dw_out
+
+
 def conv_s2_dgrad_patch(dy, dy_ld, B, Ho, Wo, Cout, wpk, k, Cin, dx, dx_ld, H, W, res=None, res_ld=0):
     """Data gradient of a stride-2 k x k (k = 3 pad 1 / k = 1 pad 0) convolution by output parity classes."""
     _lib.check(_lib.lib().air_conv_s2_dgrad_patch_bf16(
@@ -511,3 +533,6 @@ conv_s2_dgrad_patch = _timed(conv_s2_dgrad_patch, "conv_dgrad", lambda a: 2.0 * 
 PackPlan.run = _timed(PackPlan.run, "pack_weights")
 conv_wgrad_patch = _timed(conv_wgrad_patch, "conv_wgrad", lambda a: 2.0 * a[2] * a[3] * a[4] * a[5] * a[8] * a[9] * a[9])
 conv_gemm_affine = _timed(conv_gemm_affine, "conv_fprop", _conv_work)
+conv1d_patch = _timed(conv1d_patch, lambda a: "conv_dgrad" if (len(a) > 18 and a[18] == 1) else "conv_fprop",
+                      lambda a: 2.0 * a[2] * a[3] * a[4] * a[5] * a[9] * a[7])
+conv1d_wgrad_patch = _timed(conv1d_wgrad_patch, "conv_wgrad", lambda a: 2.0 * a[2] * a[3] * a[4] * a[5] * a[8] * a[9])

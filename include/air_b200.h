@@ -153,6 +153,16 @@ int air_conv_patch_taps_bf16(const void* a, long long a_ld, int B, int Hin, int 
                              int GH, int GW, int org_h, int org_w, int osh, int osw, int oph, int opw,
                              int ntaps, const int* tap_dr, const int* tap_dc, const int* tap_slice,
                              int num_sms, air_stream_t stream);
+/* as above plus a per-channel fp32 bias, a second output WITHOUT the residual (out2), and column offsets tap_dc up to 8
+ * (the patch is then 136 pixels wide): the dilated k = 3 Conv1d of the Res2 branches, ecapa_tdnn.py:50, forward
+ * (bias, ReLU) and data gradient (mode-1 weights, res / out2). */
+int air_conv_patch_taps_ex_bf16(const void* a, long long a_ld, int B, int Hin, int Win, int C,
+                                const void* wpk, int wtaps, int N, void* out, long long out_ld, int OH, int OW,
+                                const void* res, long long res_ld, int relu, const float* bias,
+                                void* out2, long long out2_ld,
+                                int GH, int GW, int org_h, int org_w, int osh, int osw, int oph, int opw,
+                                int ntaps, const int* tap_dr, const int* tap_dc, const int* tap_slice,
+                                int num_sms, air_stream_t stream);
 /* Data gradient of a stride-2 layer (k = 3 / pad 1: resnet.py:56 conv1 of layer2-4.0; k = 1 / pad 0: the shortcut,
  * resnet.py:60-61) decomposed by output parity so that only structurally non-zero taps are multiplied.
  * dy (B,Ho,Wo,Cout) -> dx (B,H,W,Cin); wpk = mode-1 packed weights with k*k taps.  k = 1 writes only the even-even
@@ -170,6 +180,11 @@ int air_conv3x3_wgrad_patch_supported(int C, int N);
 int air_conv_wgrad_patch_bf16(const void* x, long long x_ld, int B, int H, int W, int C,
                               const void* dy, long long dy_ld, int N, int k,
                               float* dw_out, long long dw_ld, int num_sms, air_stream_t stream);
+/* weight gradient of a 1-D convolution over W (kernel k <= 5 odd, dilation d, "same" padding, d*(k-1) <= 8; H rows are
+ * independent sequences): dw_out [N][k][C] fp32, accumulated (ecapa_tdnn.py:50 and its autograd) */
+int air_conv1d_wgrad_patch_bf16(const void* x, long long x_ld, int B, int H, int W, int C,
+                                const void* dy, long long dy_ld, int N, int k, int d,
+                                float* dw_out, long long dw_ld, int num_sms, air_stream_t stream);
 int air_conv3x3_wgrad_patch_bf16(const void* x, long long x_ld, int B, int H, int W, int C,
                                  const void* dy, long long dy_ld, int N,
                                  float* dw_out, long long dw_ld, int num_sms, air_stream_t stream);

@@ -295,3 +295,47 @@ def test_batched_pack_plan_matches_per_tensor_packing():
     torch.cuda.synchronize()
     for ref, out in checks:
         assert torch.equal(ref, out)
+
+
+@pytest.mark.parametrize("d", [2, 3, 4])
+def test_patch_dilated_conv1d_fprop_dgrad_wgrad(d):
+    """The Res2-branch Conv1d(64, 64, k=3, dilation=d, padding=d) of ecapa_tdnn.py:50 on the TMA patch kernels
+    (136-pixel patch, taps at 0 / d / 2d), on 64-channel slices of 512-wide tensors, vs torch fp32."""
+    from asvspoof2021_air_b200 import ops
+    B, T, C, Wd = 3, 750, 512, 64
+    g = torch.Generator(device="cpu").manual_seed(29 + d)
+    big = torch.randn(B, T, C, generator=g).cuda().to(torch.bfloat16)
+    w = (torch.randn(Wd, Wd, 3, generator=g) / (3 * Wd) ** 0.5).cuda()            # (Cout, Cin, k)
+    bias = torch.randn(Wd, generator=g).cuda()
+    wq = w.to(torch.bfloat16).float()
+    wg = w.permute(0, 2, 1).contiguous().reshape(-1)                              # GEMM layout [Cout][k][Cin]
+    wpk = torch.empty(3 * Wd * Wd, device="cuda", dtype=torch.bfloat16)
+    wpk_d = torch.empty_like(wpk)
+    ops.pack_patch(wg, Wd, Wd, 3, 0, wpk)
+    ops.pack_patch(wg, Wd, Wd, 3, 1, wpk_d)
+    src = big[:, :, 128:192]
+    out = torch.full((B, T, Wd), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.conv1d_patch(src, C, B, 1, T, Wd, wpk, 3, d, Wd, out, Wd, bias, None, 0, True)
+    torch.cuda.synchronize()
+    xs = src.float().permute(0, 2, 1)
+    ref = F.relu(F.conv1d(xs, wq, bias, padding=d, dilation=d))
+    _check(out.float().permute(0, 2, 1), ref, "dilated conv1d fprop d=%d" % d)
+    # data gradient with a residual and the un-accumulated second output
+    dy = torch.randn(B, T, Wd, generator=g).cuda().to(torch.bfloat16)
+    res = torch.randn(B, T, C, generator=g).cuda().to(torch.bfloat16)
+    dx = torch.full((B, T, Wd), float("nan"), device="cuda", dtype=torch.bfloat16)
+    dx2 = torch.zeros(B, T, C, device="cuda", dtype=torch.bfloat16)
+    ops.conv1d_patch(dy, Wd, B, 1, T, Wd, wpk_d, 3, d, Wd, dx, Wd, None, res[:, :, 64:128], C, False, dx2[:, :, 192:256], C, 1)
+    torch.cuda.synchronize()
+    refd = torch.nn.grad.conv1d_input((B, Wd, T), wq, dy.float().permute(0, 2, 1), padding=d, dilation=d)
+    _check(dx2[:, :, 192:256].float().permute(0, 2, 1), refd, "dilated conv1d dgrad (out2) d=%d" % d)
+    _check(dx.float().permute(0, 2, 1), refd + res[:, :, 64:128].float().permute(0, 2, 1), "dilated conv1d dgrad (+res) d=%d" % d)
+    assert (dx2[:, :, :192] == 0).all() and (dx2[:, :, 256:] == 0).all()
+    # weight gradient
+    dw = torch.zeros(Wd, 3 * Wd, device="cuda")
+    ops.conv1d_wgrad_patch(src, C, B, 1, T, Wd, dy, Wd, Wd, 3, d, dw)
+    torch.cuda.synchronize()
+    refw = torch.nn.grad.conv1d_weight(xs, (Wd, Wd, 3), dy.float().permute(0, 2, 1), padding=d, dilation=d)
+    got = dw.view(Wd, 3, Wd).permute(0, 2, 1)
+    err = (got - refw).norm() / refw.norm()
+    assert err < 1e-3, "dilated conv1d wgrad d=%d: normwise %.3g" % (d, float(err))
