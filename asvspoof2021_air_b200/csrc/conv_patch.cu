@@ -50,6 +50,8 @@ struct PatchParams {
   const __nv_bfloat16* res; long long res_ld; int relu;
   const float* bias;                    // optional per-channel bias (ECAPA convs, ecapa_tdnn.py:39,50)
   __nv_bfloat16* out2; long long out2_ld;   // optional second output: accumulator (+bias) WITHOUT the residual
+  double* stats;                        // optional: stats[n] += sum of the stored outputs, stats[N + n] += sum of squares
+                                        // (the batch statistics of the BatchNorm that consumes `out`, bn_stats fused)
   int CB, NCB, WT, HP;                  // channels per block (16 / 32 / 64), #blocks, column tiles, row pairs
   int row_bytes, layout;                // CB * 2; UMMA layout type (6 / 4 / 2)
   uint32_t pstage_bytes, bslot_bytes, bslot_stride;
@@ -69,10 +71,27 @@ __device__ __forceinline__ void load_res(const PatchParams& p, long long pixel, 
   }
 }
 
+// Transpose-reduce over the warp: every lane holds 32 values v[0..31] (its pixel's channels); on return lane l holds
+// sum over the 32 lanes of v[l] (31 shuffles: each stage exchanges half of the remaining values).
+__device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = up ? v[i] : v[i + o];
+      const float keep = up ? v[i + o] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
+}
+
+// One chunk of NC = 32 / 16 accumulator columns of a pixel: (+bias) (-> out2) (+res) (ReLU) -> bf16 -> out.  With
+// keep_vals the array v holds, on return, the STORED (bf16-rounded) values as floats, zeros for an invalid pixel.
 template <int NC>
 __device__ __forceinline__ void epilogue_chunk(const PatchParams& p, uint32_t taddr, long long pixel, int c0, bool valid,
-                                               const bf16x8 (&rv)[4]) {
-  float v[NC];
+                                               const bf16x8 (&rv)[4], float (&v)[NC], bool keep_vals) {
   if (NC == 32) tmem_ld32(taddr + c0, v); else tmem_ld16(taddr + c0, v);
   if (valid) {
     if (p.bias != nullptr) {
@@ -103,7 +122,14 @@ __device__ __forceinline__ void epilogue_chunk(const PatchParams& p, uint32_t ta
     }
     bf16x8* op = reinterpret_cast<bf16x8*>(p.out + pixel * p.out_ld + c0);
 #pragma unroll
-    for (int i = 0; i < NC / 8; ++i) op[i] = pack8(v + i * 8);
+    for (int i = 0; i < NC / 8; ++i) {
+      const bf16x8 pk = pack8(v + i * 8);
+      op[i] = pk;
+      if (keep_vals) unpack8(pk, v + i * 8);
+    }
+  } else if (keep_vals) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) v[i] = 0.f;
   }
 }
 
@@ -122,6 +148,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_patch_kernel(const __grid_con
   uint64_t* tfull = empty_b + p.nb_slots;           // [2]
   uint64_t* tempty = tfull + 2;                     // [2] 128 epilogue threads
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* s_stats = p.stats ? reinterpret_cast<float*>(tmem_slot + 4) : nullptr;      // [2][N] per-CTA partial sums
+  if (s_stats) for (int i = threadIdx.x; i < 2 * p.N; i += THREADS) s_stats[i] = 0.f;
 
   uint32_t ncols = 32;
   while (ncols < static_cast<uint32_t>(p.acc_stages * R * p.N)) ncols <<= 1;
@@ -271,26 +299,42 @@ __global__ void __launch_bounds__(THREADS, 1) conv_patch_kernel(const __grid_con
       const bool val0 = valr[0], val1 = valr[1];
       auto PIX = [&](int j) { return j == 0 ? pix0 : pix1; };
       auto VAL = [&](int j) { return j == 0 ? val0 : val1; };
+      // column blocks of 32 channels; both rows of a block are processed together so that the fused BatchNorm
+      // statistics need one warp transpose-reduce per block instead of one per (row, block).  The residual of
+      // the first block is requested before the accumulator is even complete.
       bf16x8 ra[4], rb[4];
-      if (nch > 0) load_res<32>(p, pix0, 0, val0, ra);
+      (void)nch;
+      if (cpr > 0) { load_res<32>(p, pix0, 0, val0, ra); if (rows > 1) load_res<32>(p, pix1, 0, val1, rb); }
       mbar_wait(&tfull[acc], acc_phase);
       fence_after_sync();
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * R * p.N;
-      for (int i = 0; i < nch; i += 2) {
-        const int j0 = i / cpr, c0 = (i - j0 * cpr) << 5;
-        const int i1 = i + 1, j1 = i1 / cpr, c1 = (i1 - j1 * cpr) << 5;
-        if (i1 < nch) load_res<32>(p, PIX(j1), c1, VAL(j1), rb);
-        epilogue_chunk<32>(p, tacc + j0 * p.N, PIX(j0), c0, VAL(j0), ra);
-        if (i1 < nch) {
-          const int i2 = i + 2, j2 = i2 / cpr, c2 = (i2 - j2 * cpr) << 5;
-          if (i2 < nch) load_res<32>(p, PIX(j2), c2, VAL(j2), ra);
-          epilogue_chunk<32>(p, tacc + j1 * p.N, PIX(j1), c1, VAL(j1), rb);
+      const bool st = s_stats != nullptr;
+      for (int cb = 0; cb < cpr; ++cb) {
+        const int c0 = cb << 5;
+        float v0[32], v1[32];
+        epilogue_chunk<32>(p, tacc, pix0, c0, val0, ra, v0, st);
+        if (rows > 1) epilogue_chunk<32>(p, tacc + p.N, pix1, c0, val1, rb, v1, st);
+        if (cb + 1 < cpr) { load_res<32>(p, pix0, c0 + 32, val0, ra); if (rows > 1) load_res<32>(p, pix1, c0 + 32, val1, rb); }
+        if (st) {                                   // warp-uniform: every lane takes part in the shuffles
+          float sq[32];
+          if (rows > 1) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { sq[i] = fmaf(v0[i], v0[i], v1[i] * v1[i]); v0[i] += v1[i]; }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sq[i] = v0[i] * v0[i];
+          }
+          const float cs = warp_column_sums(v0, lane);
+          const float cq = warp_column_sums(sq, lane);
+          atomicAdd(s_stats + c0 + lane, cs);
+          atomicAdd(s_stats + p.N + c0 + lane, cq);
         }
       }
       if (tail) {
         for (int j = 0; j < rows; ++j) {
+          float vt[16];
           load_res<16>(p, PIX(j), cpr << 5, VAL(j), ra);
-          epilogue_chunk<16>(p, tacc + j * p.N, PIX(j), cpr << 5, VAL(j), ra);
+          epilogue_chunk<16>(p, tacc + j * p.N, PIX(j), cpr << 5, VAL(j), ra, vt, false);
         }
       }
       fence_before_sync();
@@ -301,6 +345,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_patch_kernel(const __grid_con
   fence_before_sync();
   __syncthreads();
   if (warp == 2) { fence_after_sync(); tmem_dealloc(tmem_base, ncols); }
+  if (s_stats) for (int i = threadIdx.x; i < 2 * p.N; i += THREADS) atomicAdd(p.stats + i, static_cast<double>(s_stats[i]));
 }
 
 // Weight packing for the patch kernel: one pre-swizzled [N rows][CB channels] K-major image per (cb, tap), exactly
@@ -350,7 +395,7 @@ extern "C" int air_conv3x3_pack_weights(const float* w, void* dst, int C, int N,
 extern "C" int air_conv_patch_taps_ex_bf16(const void* a, long long a_ld, int B, int Hin, int Win, int C,
                                            const void* wpk, int wtaps, int N, void* out, long long out_ld, int OH, int OW,
                                            const void* res, long long res_ld, int relu, const float* bias,
-                                           void* out2, long long out2_ld,
+                                           void* out2, long long out2_ld, double* stats,
                                            int GH, int GW, int org_h, int org_w, int osh, int osw, int oph, int opw,
                                            int ntaps, const int* tap_dr, const int* tap_dc, const int* tap_slice,
                                            int num_sms, cudaStream_t stream);
@@ -362,8 +407,8 @@ extern "C" int air_conv_patch_taps_bf16(const void* a, long long a_ld, int B, in
                                         int ntaps, const int* tap_dr, const int* tap_dc, const int* tap_slice,
                                         int num_sms, cudaStream_t stream) {
   return air_conv_patch_taps_ex_bf16(a, a_ld, B, Hin, Win, C, wpk, wtaps, N, out, out_ld, OH, OW, res, res_ld, relu, nullptr,
-                                     nullptr, 0, GH, GW, org_h, org_w, osh, osw, oph, opw, ntaps, tap_dr, tap_dc, tap_slice,
-                                     num_sms, stream);
+                                     nullptr, 0, nullptr, GH, GW, org_h, org_w, osh, osw, oph, opw, ntaps, tap_dr, tap_dc,
+                                     tap_slice, num_sms, stream);
 }
 
 // as air_conv_patch_taps_bf16 plus a per-channel fp32 bias, a second output without the residual, and column offsets
@@ -371,11 +416,12 @@ extern "C" int air_conv_patch_taps_bf16(const void* a, long long a_ld, int B, in
 extern "C" int air_conv_patch_taps_ex_bf16(const void* a, long long a_ld, int B, int Hin, int Win, int C,
                                            const void* wpk, int wtaps, int N, void* out, long long out_ld, int OH, int OW,
                                            const void* res, long long res_ld, int relu, const float* bias,
-                                           void* out2, long long out2_ld,
+                                           void* out2, long long out2_ld, double* stats,
                                            int GH, int GW, int org_h, int org_w, int osh, int osw, int oph, int opw,
                                            int ntaps, const int* tap_dr, const int* tap_dc, const int* tap_slice,
                                            int num_sms, cudaStream_t stream) {
   if (!a || !wpk || !out || B <= 0 || !tap_dr || !tap_dc || !tap_slice) return AIR_ERR_ARG;
+  if (stats && (N % 32) != 0) return AIR_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(out2)) & 15) return AIR_ERR_UNSUPPORTED;
   if (out2 && out2_ld % 8 != 0) return AIR_ERR_UNSUPPORTED;
   if (ntaps < 1 || ntaps > MAX_TAPS || wtaps < 1 || GH < 1 || GW < 1 || osh < 1 || osw < 1 || oph < 0 || opw < 0) return AIR_ERR_ARG;
@@ -394,7 +440,7 @@ extern "C" int air_conv_patch_taps_ex_bf16(const void* a, long long a_ld, int B,
   int max_dc = 0;
   for (int t = 0; t < ntaps; ++t) max_dc = std::max(max_dc, tap_dc[t]);
   p.pw = max_dc <= PW - TW ? PW : PW_MAX;
-  p.bias = bias; p.out2 = reinterpret_cast<__nv_bfloat16*>(out2); p.out2_ld = out2_ld;
+  p.bias = bias; p.out2 = reinterpret_cast<__nv_bfloat16*>(out2); p.out2_ld = out2_ld; p.stats = stats;
   for (int t = 0; t < ntaps; ++t) {
     if (tap_dr[t] < 0 || tap_dr[t] > PR - R || tap_dc[t] < 0 || tap_dc[t] > p.pw - TW || tap_slice[t] < 0 || tap_slice[t] >= wtaps)
       return AIR_ERR_ARG;
@@ -417,7 +463,7 @@ extern "C" int air_conv_patch_taps_ex_bf16(const void* a, long long a_ld, int B,
   if (slots < 2 && nslices > 1) return AIR_ERR_UNSUPPORTED;
   p.nb_slots = slots;
   const size_t smem = 1024 + static_cast<size_t>(PSTAGES) * p.pstage_bytes + static_cast<size_t>(slots) * p.bslot_stride +
-                      (2 * PSTAGES + 2 * slots + 4) * 8 + 16;
+                      (2 * PSTAGES + 2 * slots + 4) * 8 + 32 + 2 * 256 * sizeof(float);
   CUtensorMap tm;
   const int tr = air_tmap::make_act_tmap(&tm, a, a_ld, B, Hin, Win, C, p.CB, p.pw, PR, p.row_bytes);
   if (tr != 0) return tr < 0 ? AIR_ERR_UNSUPPORTED : 10000 + tr;
@@ -441,6 +487,18 @@ extern "C" int air_conv3x3_patch_bf16(const void* a, long long a_ld, int B, int 
   for (int t = 0; t < 9; ++t) { dr[t] = t / 3; dc[t] = t % 3; sl[t] = t; }
   return air_conv_patch_taps_bf16(a, a_ld, B, H, W, C, wpk, 9, N, out, out_ld, H, W, res, res_ld, relu,
                                   H, W, -1, -1, 1, 1, 0, 0, 9, dr, dc, sl, num_sms, stream);
+}
+
+// 3x3 / stride 1 / pad 1 forward that also accumulates the per-channel sum / sum of squares of its (stored) output into
+// stats[0..N) / stats[N..2N) (fp64, caller zeroes): the batch statistics of the BatchNorm that follows (resnet.py:65-68)
+extern "C" int air_conv3x3_patch_stats_bf16(const void* a, long long a_ld, int B, int H, int W, int C,
+                                            const void* wpk, int N, void* out, long long out_ld,
+                                            const void* res, long long res_ld, int relu, double* stats,
+                                            int num_sms, cudaStream_t stream) {
+  int dr[9], dc[9], sl[9];
+  for (int t = 0; t < 9; ++t) { dr[t] = t / 3; dc[t] = t % 3; sl[t] = t; }
+  return air_conv_patch_taps_ex_bf16(a, a_ld, B, H, W, C, wpk, 9, N, out, out_ld, H, W, res, res_ld, relu, nullptr, nullptr, 0,
+                                     stats, H, W, -1, -1, 1, 1, 0, 0, 9, dr, dc, sl, num_sms, stream);
 }
 
 // Data gradient of a k x k (k = 3, pad 1 or k = 1, pad 0) / STRIDE-2 convolution: dy (B, Ho, Wo, Cout) -> dx (B, H, W, Cin),

@@ -164,10 +164,17 @@ class ConvLayer:
             plan.add_patch(w, self.cout, self.cin, self.taps, 1, self.wpk3_d)
         return True
 
-    def fprop(self, x, x_ld, B, H, W, out, out_ld, res=None, res_ld=0, relu=False):
+    def fprop(self, x, x_ld, B, H, W, out, out_ld, res=None, res_ld=0, relu=False, stats=None):
+        """stats (optional, fp64 [2*cout]): when the layer runs on the patch kernel the per-channel sum / sum of squares of
+        the output are accumulated there by the conv epilogue and `self.stats_fused` is set (bn_stats can be skipped)."""
         Ho, Wo = self.out_hw(H, W)
+        self.stats_fused = False
         if self.use_patch(H, W):
-            ops.conv3x3_patch(x, x_ld, B, H, W, self.cin, self.wpk3, self.cout, out, out_ld, res, res_ld, relu, 0)
+            if stats is not None and self.cout % 32 == 0:
+                ops.conv3x3_patch_stats(x, x_ld, B, H, W, self.cin, self.wpk3, self.cout, out, out_ld, res, res_ld, relu, stats)
+                self.stats_fused = True
+            else:
+                ops.conv3x3_patch(x, x_ld, B, H, W, self.cin, self.wpk3, self.cout, out, out_ld, res, res_ld, relu, 0)
             return Ho, Wo
         if self.p1x1_ok:
             ops.conv1x1_patch(x, x_ld, B, H, W, self.cin, self.wpk3, self.cout, out, out_ld, res, res_ld, relu, 0)
@@ -250,10 +257,12 @@ class BNLayer:
         self.save_mean = torch.empty(C, device=store.device)
         self.save_invstd = torch.empty(C, device=store.device)
 
-    def forward(self, x, x_ld, y, y_ld, M, relu, training):
+    def forward(self, x, x_ld, y, y_ld, M, relu, training, have_stats=False):
+        """have_stats: the producing conv already accumulated sum / sum of squares of x into self.sums."""
         g, b = self.store.view(self.name + ".weight"), self.store.view(self.name + ".bias")
         if training:
-            ops.bn_stats(x, x_ld, M, self.C, self.sums)
+            if not have_stats:
+                ops.bn_stats(x, x_ld, M, self.C, self.sums)
             self.num_batches_tracked += 1
         ops.bn_apply(x, x_ld, y, y_ld, M, self.C, self.sums, g, b, relu, training, self.save_mean, self.save_invstd,
                      self.running_mean, self.running_var)
@@ -538,16 +547,19 @@ class ResNetEngine(AsyncWgrad):
         M1 = B * self.H1 * self.W1
         self.bn1.forward(self.c1, 16, self.z1, 16, M1, True, training)
         x = self.z1
-        for blk in self.blocks:
+        x_stats = False                         # were the statistics of x accumulated by the conv that produced it?
+        for bi, blk in enumerate(self.blocks):
             Min, Mout = B * blk.H * blk.W, B * blk.Ho * blk.Wo
             blk.x = x
-            blk.bn1.forward(x, blk.cin, blk.a1, blk.cin, Min, True, training)
+            blk.bn1.forward(x, blk.cin, blk.a1, blk.cin, Min, True, training, have_stats=x_stats)
             if blk.sc is not None:
                 blk.sc.fprop(blk.a1, blk.cin, B, blk.H, blk.W, blk.y, blk.planes)
-            blk.conv1.fprop(blk.a1, blk.cin, B, blk.H, blk.W, blk.h, blk.planes)
-            blk.bn2.forward(blk.h, blk.planes, blk.a2, blk.planes, Mout, True, training)
+            blk.conv1.fprop(blk.a1, blk.cin, B, blk.H, blk.W, blk.h, blk.planes, stats=blk.bn2.sums if training else None)
+            blk.bn2.forward(blk.h, blk.planes, blk.a2, blk.planes, Mout, True, training, have_stats=blk.conv1.stats_fused)
             res = blk.y if blk.sc is not None else x
-            blk.conv2.fprop(blk.a2, blk.planes, B, blk.Ho, blk.Wo, blk.y, blk.planes, res=res, res_ld=blk.planes)
+            nxt = self.blocks[bi + 1].bn1.sums if (training and bi + 1 < len(self.blocks)) else None
+            blk.conv2.fprop(blk.a2, blk.planes, B, blk.Ho, blk.Wo, blk.y, blk.planes, res=res, res_ld=blk.planes, stats=nxt)
+            x_stats = blk.conv2.stats_fused
             x = blk.y
         last = self.blocks[-1]
         self.conv5.fprop(x, 512, B, last.Ho, last.Wo, self.c5, 256)

@@ -140,7 +140,7 @@ def conv1d_patch(a, a_ld, B, H, W, C, wpk, k, d, N, out, out_ld, bias=None, res=
     sl = (ctypes.c_int * k)(*range(k))
     _lib.check(_lib.lib().air_conv_patch_taps_ex_bf16(
         _lib.ptr(a), _lib.LL(a_ld), B, H, W, C, _lib.ptr(wpk), k, N, _lib.ptr(out), _lib.LL(out_ld), H, W,
-        _lib.ptr(res), _lib.LL(res_ld), int(relu), _lib.ptr(bias), _lib.ptr(out2), _lib.LL(out2_ld),
+        _lib.ptr(res), _lib.LL(res_ld), int(relu), _lib.ptr(bias), _lib.ptr(out2), _lib.LL(out2_ld), None,
         H, W, 0, -d * (k - 1) // 2, 1, 1, 0, 0, k, zero, dc, sl, num_sms(), _lib.stream_ptr()),
         "air_conv_patch_taps_ex_bf16")
     return out
@@ -179,6 +179,14 @@ def conv_wgrad_patch(x, x_ld, B, H, W, C, dy, dy_ld, N, k, dw_out, dw_ld=None):
         _lib.ptr(x), _lib.LL(x_ld), B, H, W, C, _lib.ptr(dy), _lib.LL(dy_ld), N, k, _lib.ptr(dw_out),
         _lib.LL(k * k * C if dw_ld is None else dw_ld), num_sms(), _lib.stream_ptr()), "air_conv_wgrad_patch_bf16")
     return dw_out
+
+
+def conv3x3_patch_stats(a, a_ld, B, H, W, C, wpk, N, out, out_ld, res, res_ld, relu, stats):
+    """3x3 / s1 / p1 forward that also adds the per-channel sum / sum of squares of its output to `stats` (fp64 [2N])."""
+    _lib.check(_lib.lib().air_conv3x3_patch_stats_bf16(
+        _lib.ptr(a), _lib.LL(a_ld), B, H, W, C, _lib.ptr(wpk), N, _lib.ptr(out), _lib.LL(out_ld), _lib.ptr(res),
+        _lib.LL(res_ld), int(relu), _lib.ptr(stats), num_sms(), _lib.stream_ptr()), "air_conv3x3_patch_stats_bf16")
+    return out
 
 
 def conv_out_size(n, k, s, p, d):
@@ -536,3 +544,4 @@ conv_gemm_affine = _timed(conv_gemm_affine, "conv_fprop", _conv_work)
 conv1d_patch = _timed(conv1d_patch, lambda a: "conv_dgrad" if (len(a) > 18 and a[18] == 1) else "conv_fprop",
                       lambda a: 2.0 * a[2] * a[3] * a[4] * a[5] * a[9] * a[7])
 conv1d_wgrad_patch = _timed(conv1d_wgrad_patch, "conv_wgrad", lambda a: 2.0 * a[2] * a[3] * a[4] * a[5] * a[8] * a[9])
+conv3x3_patch_stats = _timed(conv3x3_patch_stats, "conv_fprop", lambda a: 2.0 * a[2] * a[3] * a[4] * a[5] * a[7] * 9)

@@ -132,6 +132,10 @@ int air_conv3x3_pack_weights(const float* w, void* dst, int C, int N, int mode, 
 int air_conv3x3_patch_bf16(const void* a, long long a_ld, int B, int H, int W, int C,
                            const void* wpk, int N, void* out, long long out_ld,
                            const void* res, long long res_ld, int relu, int num_sms, air_stream_t stream);
+int air_conv3x3_patch_stats_bf16(const void* a, long long a_ld, int B, int H, int W, int C,
+                                 const void* wpk, int N, void* out, long long out_ld,
+                                 const void* res, long long res_ld, int relu, double* stats,
+                                 int num_sms, air_stream_t stream);
 
 /* Batched weight packing (csrc/pack.cu): one launch re-packs every convolution weight of a model from a
  * device-resident table of 16 x int64 job records.  air_pack_job_* fill ONE host-side record with the same arguments
@@ -155,11 +159,13 @@ int air_conv_patch_taps_bf16(const void* a, long long a_ld, int B, int Hin, int 
                              int num_sms, air_stream_t stream);
 /* as above plus a per-channel fp32 bias, a second output WITHOUT the residual (out2), and column offsets tap_dc up to 8
  * (the patch is then 136 pixels wide): the dilated k = 3 Conv1d of the Res2 branches, ecapa_tdnn.py:50, forward
- * (bias, ReLU) and data gradient (mode-1 weights, res / out2). */
+ * (bias, ReLU) and data gradient (mode-1 weights, res / out2).  `stats` (optional, N % 32 == 0): fp64 [2N], the
+ * per-channel sum and sum of squares of the stored output are ADDED to it -- the batch statistics of the BatchNorm that
+ * consumes `out` (air_bn_stats fused into the conv epilogue; resnet.py:65-68). */
 int air_conv_patch_taps_ex_bf16(const void* a, long long a_ld, int B, int Hin, int Win, int C,
                                 const void* wpk, int wtaps, int N, void* out, long long out_ld, int OH, int OW,
                                 const void* res, long long res_ld, int relu, const float* bias,
-                                void* out2, long long out2_ld,
+                                void* out2, long long out2_ld, double* stats,
                                 int GH, int GW, int org_h, int org_w, int osh, int osw, int oph, int opw,
                                 int ntaps, const int* tap_dr, const int* tap_dc, const int* tap_slice,
                                 int num_sms, air_stream_t stream);

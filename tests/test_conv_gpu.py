@@ -339,3 +339,28 @@ def test_patch_dilated_conv1d_fprop_dgrad_wgrad(d):
     got = dw.view(Wd, 3, Wd).permute(0, 2, 1)
     err = (got - refw).norm() / refw.norm()
     assert err < 1e-3, "dilated conv1d wgrad d=%d: normwise %.3g" % (d, float(err))
+
+
+@pytest.mark.parametrize("shape", [(2, 18, 750, 64, 64), (3, 5, 131, 64, 128), (2, 9, 375, 128, 128)])
+def test_patch_conv_fused_batchnorm_statistics(shape):
+    """air_conv3x3_patch_stats_bf16: per-channel sum / sum of squares of the stored output, accumulated in the conv
+    epilogue (warp transpose-reduce + shared-memory partials + fp64 atomics) == sums of the output tensor."""
+    from asvspoof2021_air_b200 import ops
+    B, H, W, Cin, Cout = shape
+    g = torch.Generator(device="cpu").manual_seed(31)
+    x = torch.randn(B, H, W, Cin, generator=g).cuda().to(torch.bfloat16)
+    w = (torch.randn(Cout, 3, 3, Cin, generator=g) / (Cin * 9) ** 0.5).cuda()
+    res = torch.randn(B, H, W, Cout, generator=g).cuda().to(torch.bfloat16)
+    wpk = torch.empty(9 * Cin * Cout, device="cuda", dtype=torch.bfloat16)
+    ops.pack3x3(w.contiguous(), Cin, Cout, 0, wpk)
+    out = torch.empty(B, H, W, Cout, device="cuda", dtype=torch.bfloat16)
+    ref = torch.empty_like(out)
+    stats = torch.zeros(2 * Cout, device="cuda", dtype=torch.float64)
+    ops.conv3x3_patch_stats(x, Cin, B, H, W, Cin, wpk, Cout, out, Cout, res, Cout, False, stats)
+    ops.conv3x3_patch(x, Cin, B, H, W, Cin, wpk, Cout, ref, Cout, res, Cout, False)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)                                   # the fused path stores the same tensor
+    o = out.double().reshape(-1, Cout)
+    s, q = o.sum(0), (o * o).sum(0)
+    assert torch.allclose(stats[:Cout], s, rtol=1e-5, atol=1e-3 * float(o.abs().sum(0).max()) * 1e-3)
+    assert torch.allclose(stats[Cout:], q, rtol=1e-5)
