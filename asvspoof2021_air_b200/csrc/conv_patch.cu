@@ -148,8 +148,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_patch_kernel(const __grid_con
   uint64_t* tfull = empty_b + p.nb_slots;           // [2]
   uint64_t* tempty = tfull + 2;                     // [2] 128 epilogue threads
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* s_stats = p.stats ? reinterpret_cast<float*>(tmem_slot + 4) : nullptr;      // [2][N] per-CTA partial sums
-  if (s_stats) for (int i = threadIdx.x; i < 2 * p.N; i += THREADS) s_stats[i] = 0.f;
+  float* s_stats = p.stats ? reinterpret_cast<float*>(tmem_slot + 4) : nullptr;      // [4 epilogue warps][2][N] partial sums
 
   uint32_t ncols = 32;
   while (ncols < static_cast<uint32_t>(p.acc_stages * R * p.N)) ncols <<= 1;
@@ -272,6 +271,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_patch_kernel(const __grid_con
     // ===================== epilogue =====================
     const int q = warp & 3;
     const int m = q * 32 + lane;
+    // fused BatchNorm statistics: lane l accumulates channel (32 cb + l) of its warp's pixels in registers, in a fixed
+    // order (bit-reproducible run to run); combined per CTA in shared memory and across CTAs with fp64 atomics
+    float acc_s[8], acc_q[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { acc_s[u] = 0.f; acc_q[u] = 0.f; }
     uint32_t it = 0;
     for (uint32_t item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
       const int wt = static_cast<int>(item % WT);
@@ -326,8 +330,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_patch_kernel(const __grid_con
           }
           const float cs = warp_column_sums(v0, lane);
           const float cq = warp_column_sums(sq, lane);
-          atomicAdd(s_stats + c0 + lane, cs);
-          atomicAdd(s_stats + p.N + c0 + lane, cq);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) if (u == cb) { acc_s[u] += cs; acc_q[u] += cq; }
         }
       }
       if (tail) {
@@ -340,12 +344,26 @@ __global__ void __launch_bounds__(THREADS, 1) conv_patch_kernel(const __grid_con
       fence_before_sync();
       mbar_arrive(&tempty[acc]);
     }
+    if (s_stats != nullptr) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (u * 32 < p.N) {
+          s_stats[q * 2 * p.N + u * 32 + lane] = acc_s[u];
+          s_stats[q * 2 * p.N + p.N + u * 32 + lane] = acc_q[u];
+        }
+      }
+    }
   }
 
   fence_before_sync();
   __syncthreads();
   if (warp == 2) { fence_after_sync(); tmem_dealloc(tmem_base, ncols); }
-  if (s_stats) for (int i = threadIdx.x; i < 2 * p.N; i += THREADS) atomicAdd(p.stats + i, static_cast<double>(s_stats[i]));
+  if (s_stats) {
+    for (int i = threadIdx.x; i < 2 * p.N; i += THREADS) {
+      const float t = ((s_stats[i] + s_stats[2 * p.N + i]) + s_stats[4 * p.N + i]) + s_stats[6 * p.N + i];
+      atomicAdd(p.stats + i, static_cast<double>(t));
+    }
+  }
 }
 
 // Weight packing for the patch kernel: one pre-swizzled [N rows][CB channels] K-major image per (cb, tap), exactly
@@ -463,7 +481,7 @@ extern "C" int air_conv_patch_taps_ex_bf16(const void* a, long long a_ld, int B,
   if (slots < 2 && nslices > 1) return AIR_ERR_UNSUPPORTED;
   p.nb_slots = slots;
   const size_t smem = 1024 + static_cast<size_t>(PSTAGES) * p.pstage_bytes + static_cast<size_t>(slots) * p.bslot_stride +
-                      (2 * PSTAGES + 2 * slots + 4) * 8 + 32 + 2 * 256 * sizeof(float);
+                      (2 * PSTAGES + 2 * slots + 4) * 8 + 32 + (stats ? 4 * 2 * static_cast<size_t>(N) * sizeof(float) : 0);
   CUtensorMap tm;
   const int tr = air_tmap::make_act_tmap(&tm, a, a_ld, B, Hin, Win, C, p.CB, p.pw, PR, p.row_bytes);
   if (tr != 0) return tr < 0 ? AIR_ERR_UNSUPPORTED : 10000 + tr;

@@ -412,6 +412,9 @@ class ResNetEngine(AsyncWgrad):
         self._packed_version = -1
         self.init_parameters()
 
+    # batch statistics of a BatchNorm accumulated by the epilogue of the patch conv that produces its input
+    fuse_bn_stats = os.environ.get("AIR_FUSE_BN_STATS", "1") != "0"
+
     def bind(self, batch, T):
         """(Re)allocate activation / gradient buffers for a (batch, T) input."""
         if self.B == batch and self.T == T:
@@ -554,10 +557,11 @@ class ResNetEngine(AsyncWgrad):
             blk.bn1.forward(x, blk.cin, blk.a1, blk.cin, Min, True, training, have_stats=x_stats)
             if blk.sc is not None:
                 blk.sc.fprop(blk.a1, blk.cin, B, blk.H, blk.W, blk.y, blk.planes)
-            blk.conv1.fprop(blk.a1, blk.cin, B, blk.H, blk.W, blk.h, blk.planes, stats=blk.bn2.sums if training else None)
+            fuse = training and self.fuse_bn_stats
+            blk.conv1.fprop(blk.a1, blk.cin, B, blk.H, blk.W, blk.h, blk.planes, stats=blk.bn2.sums if fuse else None)
             blk.bn2.forward(blk.h, blk.planes, blk.a2, blk.planes, Mout, True, training, have_stats=blk.conv1.stats_fused)
             res = blk.y if blk.sc is not None else x
-            nxt = self.blocks[bi + 1].bn1.sums if (training and bi + 1 < len(self.blocks)) else None
+            nxt = self.blocks[bi + 1].bn1.sums if (fuse and bi + 1 < len(self.blocks)) else None
             blk.conv2.fprop(blk.a2, blk.planes, B, blk.Ho, blk.Wo, blk.y, blk.planes, res=res, res_ld=blk.planes, stats=nxt)
             x_stats = blk.conv2.stats_fused
             x = blk.y

@@ -211,3 +211,32 @@ def test_trainer_step_from_raw_waves_matches_module_path():
     assert abs(l1 - losses[0]) <= 1e-3 * abs(losses[0]), (l1, losses[0])
     assert abs(l2 - losses[1]) <= 2e-2 * abs(losses[1]), (l2, losses[1])
     assert l2 != l1
+
+
+def test_train_step_is_reproducible_run_to_run():
+    """Two identical forward/backward passes: the forward is bit-identical (no floating-point atomics with a free
+    order on the forward path -- the fused BatchNorm statistics accumulate in registers in a fixed order) and the
+    gradients agree to fp32 atomic-order noise.  The data-parallel check (scripts/ddp_check.py) relies on it."""
+    from asvspoof2021_air_b200 import ops
+    from asvspoof2021_air_b200.trainer import Trainer
+    B = 8
+    tr = Trainer(arch="resnet", seed=100)
+    st = tr.engine.store
+    w, lab = ss.seeded_waves(B, 64000, seed=50).cuda(), ss.seeded_labels(B, 0).cuda()
+    runs = []
+    for _ in range(2):
+        x0 = tr.features(w)
+        feat, logits = tr.engine.forward(x0, training=True)
+        dfeat, score = torch.empty(B, feat.shape[1], device="cuda"), torch.empty(B, device="cuda")
+        tr.engine.zero_grad(); tr.center_grad.zero_()
+        ops.ocsoftmax(feat, lab, tr.center, B, feat.shape[1], tr.r_real, tr.r_fake, tr.alpha, 1.0, tr.loss, score, dfeat,
+                      tr.center_grad, logits, logits.shape[1], tr.ce)
+        tr.engine.backward(dfeat)
+        torch.cuda.synchronize()
+        runs.append((feat.clone(), st.grads[:st.n_train].clone()))
+    assert torch.equal(runs[0][0], runs[1][0])
+    for name, (off, n, _) in st.offsets.items():
+        if off >= st.n_train:
+            continue
+        a, b = runs[0][1][off:off + n].double(), runs[1][1][off:off + n].double()
+        assert float((a - b).norm()) <= 1e-5 * float(a.norm()) + 1e-12, name
