@@ -545,3 +545,35 @@ conv1d_patch = _timed(conv1d_patch, lambda a: "conv_dgrad" if (len(a) > 18 and a
                       lambda a: 2.0 * a[2] * a[3] * a[4] * a[5] * a[9] * a[7])
 conv1d_wgrad_patch = _timed(conv1d_wgrad_patch, "conv_wgrad", lambda a: 2.0 * a[2] * a[3] * a[4] * a[5] * a[8] * a[9])
 conv3x3_patch_stats = _timed(conv3x3_patch_stats, "conv_fprop", lambda a: 2.0 * a[2] * a[3] * a[4] * a[5] * a[7] * 9)
+
+
+# ------------------------------------------------------------------------------------------
+# detection-error curve / EER / t-DCF (csrc/det.cu)
+# ------------------------------------------------------------------------------------------
+def det_workspace_bytes(n):
+    out = ctypes.c_longlong(0)
+    st = _lib.lib().air_det_workspace_bytes(_lib.LL(n), ctypes.byref(out))
+    if st != 0:
+        raise _lib.AirError("air_det_workspace_bytes failed: argument error %d" % st)
+    return int(out.value)
+
+
+def det_curve(target, nontarget, negate, c1, c2, want_tdcf, workspace, frr, far, thresholds, tdcf, out):
+    """target / nontarget: contiguous CUDA score vectors of one dtype (float32 or float64)."""
+    f64 = target.dtype == torch.float64
+    fn = _lib.lib().air_det_curve_f64 if f64 else _lib.lib().air_det_curve_f32
+    n = target.numel() + nontarget.numel()
+    _lib.check(fn(_lib.ptr(target), _lib.LL(target.numel()), _lib.ptr(nontarget), _lib.LL(nontarget.numel()),
+                  int(bool(negate)), _lib.D(c1), _lib.D(c2), int(bool(want_tdcf)), _lib.ptr(workspace),
+                  _lib.LL(workspace.numel() * workspace.element_size()), _lib.ptr(frr), _lib.ptr(far),
+                  _lib.ptr(thresholds), _lib.ptr(tdcf), _lib.ptr(out), _lib.stream_ptr()),
+               "air_det_curve", n=_lib.lib().air_det_launches(_lib.LL(n), int(f64)))
+
+
+def det_threshold_counts(scores, threshold, counts):
+    fn = _lib.lib().air_det_threshold_counts_f64 if scores.dtype == torch.float64 else _lib.lib().air_det_threshold_counts_f32
+    _lib.check(fn(_lib.ptr(scores), _lib.LL(scores.numel()), _lib.D(threshold), _lib.ptr(counts), _lib.stream_ptr()),
+               "air_det_threshold_counts")
+
+
+det_curve = _timed(det_curve, "det_curve")

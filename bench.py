@@ -210,6 +210,107 @@ def run_lfcc(args, rank, world):
     return line
 
 
+# ----------------------------------------------------------------------------------------------
+DET_TRIALS = (7355, 63882)          # ASVspoof 2019 LA eval: bona fide, spoof trials
+
+
+def _det_scores(n_tar, n_non, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(n_tar, generator=g) + 1.0, torch.randn(n_non, generator=g) - 1.0
+
+
+def cpu_det_baseline(n_tar, n_non, seconds=10.0):
+    """numpy restatement of eval_metrics.compute_eer (both orientations, main_train.py:662-664), one host thread."""
+    from oracle import metrics_oracle as mo
+    t, n = (x.numpy() for x in _det_scores(n_tar, n_non, 0))
+    mo.eer(t, n)
+    t0, it = time.perf_counter(), 0
+    while time.perf_counter() - t0 < seconds and it < 500:
+        mo.eer(t, n)
+        mo.eer(t, n, negate=True)
+        it += 1
+    dt = time.perf_counter() - t0
+    return {"value": (n_tar + n_non) * it / dt, "unit": "trials/s", "cores": 1, "kind": "port",
+            "sample": "%d x (EER + EER of negated scores) of %d + %d synthetic scores (numpy)" % (it, n_tar, n_non)}
+
+
+def run_det(args, rank, world):
+    """EER of one evaluation set, both score orientations, sorted / reduced on the GPU."""
+    from asvspoof2021_air_b200 import eval_metrics as em, ops
+    n_tar, n_non = DET_TRIALS if not args.batch else (args.batch // 8, args.batch - args.batch // 8)
+    n = n_tar + n_non
+    tar, non = (x.cuda() for x in _det_scores(n_tar, n_non, rank))
+    ws = torch.empty(ops.det_workspace_bytes(n), dtype=torch.uint8, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    lib_launches = _lib_launches()
+
+    def step(i):
+        a = em.det(tar, non, workspace=ws)
+        b = em.det(tar, non, negate=True, workspace=ws)
+        return a, b
+
+    def timed_flushed(fn, sync_result):
+        for i in range(args.warmup):
+            fn(i)
+        barrier(world)
+        total = 0.0
+        for i in range(args.steps):
+            flush.zero_()                                  # 256 MB > 126 MB L2: every step starts cold
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(i)
+            if sync_result:
+                r = min(r[0].host()["eer"], r[1].host()["eer"])
+            e1.record()
+            e1.synchronize()
+            total += e0.elapsed_time(e1)
+        barrier(world)
+        return max_over_ranks(total, world)
+
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.start()
+    l0 = lib_launches()
+    ms = timed_flushed(step, False)
+    per_step_launches = (lib_launches() - l0) // (args.steps + args.warmup)
+    clocks = sampler.stop()
+    host = [x.cpu().pin_memory() for x in (tar, non)]
+
+    def step_e2e(i):
+        t, m = host[0].cuda(non_blocking=True), host[1].cuda(non_blocking=True)
+        return em.det(t, m, workspace=ws), em.det(t, m, negate=True, workspace=ws)
+
+    ms_e2e = timed_flushed(step_e2e, True)
+    peaks = measured_peaks()
+    passes = 5
+    algo = 2 * (n * 4 + 80)                                # per step: the scores read once per orientation + 10 doubles out
+    sort_bytes = 2 * n * (4 + 9 + passes * (9 + 9 + 9) + 9 + 9)   # what the kernels move: keys+class per radix pass etc.
+    per_step_s = ms / 1e3 / args.steps
+    line = {
+        "metric": "detection trials/sec (EER, both orientations)", "value": world * n * args.steps / (ms / 1e3),
+        "unit": "trials/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 keys / u32 counts", "data": "synthetic",
+        "config": {"workload": "det: EER of %d bona fide + %d spoof scores, both orientations (main_train.py:662-664)" % (n_tar, n_non),
+                   "l2": "a 256 MB buffer is rewritten before every timed step (per-step CUDA events, summed)"},
+        "roofline": {"bound": "hbm", "achieved": algo / per_step_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": algo / per_step_s / 1e9 / peaks["hbm_gbs"], "traffic": None, "peak_src": peaks["src"],
+                     "kernel": "air_det:: radix sort (hist / scan / scatter x %d) + curve kernels" % passes,
+                     "bytes_per_launch": algo, "moved_bytes_per_step": sort_bytes,
+                     "moved_gbs": sort_bytes / per_step_s / 1e9,
+                     "note": "launch-latency bound at this size: %d dependent launches per step" % per_step_launches},
+        "e2e": {"value": world * n * args.steps / (ms_e2e / 1e3), "unit": "trials/s", "h2d_bytes_per_step": n * 4,
+                "d2h_bytes_per_step": 160},
+        "gpu_launches": per_step_launches * args.steps, "clocks": clocks,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_det_baseline(n_tar, n_non)
+    return line
+
+
+def _lib_launches():
+    from asvspoof2021_air_b200 import _lib
+    return lambda: _lib.LAUNCHES[0]
+
+
 def run_reference(args, rank, world):
     """The reference's own CPU implementation of the path (oracle port; /root/reference is not on
     the GPU box), all host threads, bounded sample per step."""
@@ -236,6 +337,26 @@ def run_reference(args, rank, world):
                 "cpu_baseline": {"value": v, "unit": "utterances/s", "cores": n, "kind": "port",
                                  "sample": "%d waves x %d steps" % (B, args.steps)},
                 "e2e": {"value": v, "unit": "utterances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if args.workload == "det":
+        from oracle import metrics_oracle as mo
+        n_tar, n_non = DET_TRIALS
+        t, n = (x.numpy() for x in _det_scores(n_tar, n_non, 0))
+        for _ in range(args.warmup):
+            mo.eer(t, n)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            mo.eer(t, n)
+            mo.eer(t, n, negate=True)
+        dt = time.perf_counter() - t0
+        v = (n_tar + n_non) * args.steps / dt
+        return {"impl": "reference", "metric": "detection trials/sec (EER, both orientations)", "value": v,
+                "unit": "trials/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "det: reference CPU path (numpy restatement of eval_metrics.compute_eer)"},
+                "cpu_baseline": {"value": v, "unit": "trials/s", "cores": 1, "kind": "port",
+                                 "sample": "%d + %d scores x %d steps" % (n_tar, n_non, args.steps)},
+                "e2e": {"value": v, "unit": "trials/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     from asvspoof2021_air_b200 import bench_train
     return bench_train.run_reference(args, rank, world)
 
@@ -253,7 +374,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default=None, choices=[None, "lfcc", "resnet_train", "ecapa_train", "ecapa_score"])
+    ap.add_argument("--workload", default=None, choices=[None, "lfcc", "resnet_train", "ecapa_train", "ecapa_score", "det"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--fseg", type=int, default=0)
@@ -277,6 +398,8 @@ def main():
     rank, world, _ = dist_setup(args.gpus)
     if args.workload == "lfcc":
         line = run_lfcc(args, rank, world)
+    elif args.workload == "det":
+        line = run_det(args, rank, world)
     else:
         from asvspoof2021_air_b200 import bench_train
         line = bench_train.run(args, rank, world, helpers=sys.modules[__name__])

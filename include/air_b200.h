@@ -335,6 +335,35 @@ int air_adam_l2_step(float* p, const float* g, float* m, float* v, long long n, 
                      air_stream_t stream);
 int air_sgd_step(float* p, const float* g, long long n, float lr, float grad_scale, air_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Detection-error curve, EER and min t-DCF of countermeasure scores (csrc/det.cu).  Replaces
+ * eval_metrics.py:19-46 (compute_det_curve, compute_eer) and :141-172 (the t-DCF curve of compute_tDCF);
+ * reference call sites main_train.py:662-663, score_fusion.py:117-118, evaluate_tDCF_asvspoof19.py:45-62.
+ * target / nontarget: fp32 (_f32) or fp64 (_f64) device arrays (bona fide / spoof scores; the reference
+ * feeds fp32 model scores and fp64 values parsed from score files).  negate != 0 scores -s instead
+ * (the reference's `other_eer`).  c1, c2: the t-DCF weights C1, C2 (eval_metrics.py:160-162), used when
+ * want_tdcf != 0.  Optional curve outputs, each n_tar + n_non + 1 doubles or NULL: frr, far, thresholds,
+ * tdcf (normalised).  out: 10 doubles = EER, EER threshold, frr and far at that point, min normalised
+ * t-DCF, its threshold, n_tar, n_non, argmin index of |frr - far|, argmin index of the t-DCF.
+ * Results are bit-identical to numpy's on the fp64 values of the scores.  workspace: caller-owned,
+ * air_det_workspace_bytes(n_tar + n_non) bytes.  air_det_launches: kernels launched per call.
+ * air_det_threshold_counts_*: counts_ge_lt[0] = #(s >= threshold), [1] = #(s < threshold), the sums of
+ * obtain_asv_error_rates (eval_metrics.py:4-16). */
+int air_det_workspace_bytes(long long n, long long* bytes);
+int air_det_launches(long long n, int is_f64);
+int air_det_curve_f32(const float* target, long long n_tar, const float* nontarget, long long n_non,
+                      int negate, double c1, double c2, int want_tdcf, void* workspace,
+                      long long workspace_bytes, double* frr, double* far, double* thresholds,
+                      double* tdcf, double* out, air_stream_t stream);
+int air_det_curve_f64(const double* target, long long n_tar, const double* nontarget, long long n_non,
+                      int negate, double c1, double c2, int want_tdcf, void* workspace,
+                      long long workspace_bytes, double* frr, double* far, double* thresholds,
+                      double* tdcf, double* out, air_stream_t stream);
+int air_det_threshold_counts_f32(const float* scores, long long n, double threshold,
+                                 unsigned long long* counts_ge_lt, air_stream_t stream);
+int air_det_threshold_counts_f64(const double* scores, long long n, double threshold,
+                                 unsigned long long* counts_ge_lt, air_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

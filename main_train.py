@@ -126,6 +126,32 @@ def _reject_out_of_scope(args):
         raise SystemExit("only --feat LFCC is implemented (computed on device from raw waves)")
 
 
+def dev_eer(score_chunks, label_chunks, world):
+    """EER of the validation scores as the reference computes it (main_train.py:660-664: label 0 = bona fide is the
+    target class; the better of the two score orientations), sorted and reduced on the GPU (csrc/det.cu).  Under
+    data parallelism every rank contributes its shard of the dev set (one padded all-gather)."""
+    from asvspoof2021_air_b200 import eval_metrics as em
+    if not score_chunks:
+        scores, labels = torch.empty(0, device="cuda"), torch.empty(0, dtype=torch.long, device="cuda")
+    else:
+        scores, labels = torch.cat(score_chunks).float(), torch.cat(label_chunks).long()
+    if world > 1:
+        n = torch.tensor([scores.numel()], device="cuda")
+        sizes = [torch.zeros_like(n) for _ in range(world)]
+        torch.distributed.all_gather(sizes, n)
+        m = max(int(x) for x in sizes)
+        pad = torch.zeros(2, m, device="cuda")
+        pad[0, :scores.numel()], pad[1, :scores.numel()] = scores, labels.float()
+        bufs = [torch.empty_like(pad) for _ in range(world)]
+        torch.distributed.all_gather(bufs, pad)
+        scores = torch.cat([b[0, :int(x)] for b, x in zip(bufs, sizes)])
+        labels = torch.cat([b[1, :int(x)] for b, x in zip(bufs, sizes)]).long()
+    tar, non = scores[labels == 0], scores[labels == 1]
+    if tar.numel() == 0 or non.numel() == 0:
+        return float("nan")
+    return min(em.det(tar, non).host()["eer"], em.det(tar, non, negate=True).host()["eer"])
+
+
 def _source(args, dev=False):
     from asvspoof2021_air_b200 import data
     n = args.dev_synthetic if dev else args.synthetic
@@ -181,19 +207,23 @@ def train(args):
                 pending = []
         val = float("nan")
         if dev_src is not None:
-            tot, cnt = 0.0, 0
+            tot, cnt, dev_scores, dev_labels = 0.0, 0, [], []
             for lo in range(rank * per_rank, len(dev_src), per_rank * world):
                 idx = list(range(lo, min(lo + per_rank, len(dev_src))))
                 waves, lengths, labels, _, start = dev_src.batch(idx)
-                l, _ = tr.eval_loss(waves.cuda(), labels.cuda(), None if int(lengths.min()) == waves.shape[1] else lengths, start)
+                labels = labels.cuda()
+                l, sc = tr.eval_loss(waves.cuda(), labels, None if int(lengths.min()) == waves.shape[1] else lengths, start)
                 tot, cnt = tot + float(l) * len(idx), cnt + len(idx)
+                dev_scores.append(sc.clone())
+                dev_labels.append(labels)
             t = torch.tensor([tot, cnt], device="cuda", dtype=torch.float64)
             if world > 1:
                 torch.distributed.all_reduce(t)
             val = float(t[0] / t[1].clamp(min=1))
-            if rank == 0:
+            eer = dev_eer(dev_scores, dev_labels, world)
+            if rank == 0:                                                 # main_train.py:598-601 / :666-667
                 with open(os.path.join(args.out_fold, "dev_loss.log"), "a") as log:
-                    log.write("%d\t%s\n" % (epoch, val))
+                    log.write("%d\t%s\t%s\n" % (epoch, val, eer))
         if rank == 0:                                                     # main_train.py:674-706
             feat_model, loss_model = tr.modules()
             ck = os.path.join(args.out_fold, "checkpoint")

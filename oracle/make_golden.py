@@ -165,9 +165,75 @@ def golden_nets(batch=4, seed=3):
     np.savez_compressed(os.path.join(GOLD, "nets_golden.npz"), **out)
 
 
+DET_COST = {"Pspoof": 0.05, "Ptar": 0.95 * 0.99, "Pnon": 0.95 * 0.01, "Cmiss_asv": 1, "Cfa_asv": 10,
+            "Cmiss_cm": 1, "Cfa_cm": 10}                      # evaluate_tDCF_asvspoof19.py:10-19
+DET_ASV = (0.02372, 0.02478, 0.61542)                         # Pfa_asv, Pmiss_asv, Pmiss_spoof_asv of a typical ASV
+
+
+def det_cases():
+    """Seeded score sets for the detection metrics: name -> (target, nontarget) in the dtype the case is about."""
+    rng = np.random.RandomState(2021)
+    cases = {}
+    ref_file = os.path.join(ref_shim.REFERENCE_ROOT, "scores", "lfcc_ecapa512ctst_ocs_19dev_score.txt")
+    rows = np.genfromtxt(ref_file, dtype=str)[::7]            # every 7th trial of the reference's own dev scores
+    sc, key = rows[:, 1].astype(np.float64), rows[:, 2]
+    cases["devfile_f64"] = (sc[key == "bonafide"], sc[key == "spoof"])
+    cases["devfile_f32"] = (sc[key == "bonafide"].astype(np.float32), sc[key == "spoof"].astype(np.float32))
+    t = np.round(rng.randn(700) * 0.5 + 0.6, 2)
+    n = np.round(rng.randn(3300) * 0.5 - 0.2, 2)
+    cases["ties_f32"] = (t.astype(np.float32), n.astype(np.float32))      # ~150 distinct values, many cross-class ties
+    cases["ties_f64"] = (t, n)
+    cases["normal_f32"] = ((rng.randn(2548) + 1.5).astype(np.float32), (rng.randn(22296) - 1.0).astype(np.float32))
+    cases["f64_dense"] = (rng.randn(1500) * 1e-9 + 1.0, rng.randn(2600) * 1e-9 + 1.0)   # differ only in low mantissa bits
+    cases["one_each"] = (np.array([0.25], np.float32), np.array([-0.5], np.float32))
+    cases["inverted"] = (np.array([-1.0, -2.0, -3.0], np.float32), np.array([0.5], np.float32))
+    cases["all_equal"] = (np.full(5, 0.125, np.float32), np.full(9, 0.125, np.float32))
+    cases["signed_zero"] = (np.array([0.0, -0.0, 1.0, -1.0], np.float32), np.array([-0.0, 0.0, -1.0, 2.0], np.float32))
+    cases["tile_edge"] = ((rng.rand(1000) * 2 - 1).astype(np.float32), (rng.rand(1049) * 2 - 1.2).astype(np.float32))
+    cases["subnormal"] = ((rng.randn(40) * 1e-41).astype(np.float32), (rng.randn(60) * 1e-41).astype(np.float32))
+    return cases
+
+
+def golden_det():
+    """Outputs of the reference's own eval_metrics functions (imported unmodified) on det_cases()."""
+    sys.path.insert(0, ref_shim.REFERENCE_ROOT)
+    import eval_metrics as rem
+    out = {}
+    for name, (tar, non) in det_cases().items():
+        out[name + "__target"], out[name + "__nontarget"] = tar, non
+        for tag, sign in (("", 1.0), ("_neg", -1.0)):
+            t, n = (sign * tar).astype(tar.dtype), (sign * non).astype(non.dtype)
+            frr, far, thr = rem.compute_det_curve(t, n)
+            e, eth = rem.compute_eer(t, n)
+            out[name + tag + "__eer"] = np.array([e, float(eth), float(np.argmin(np.abs(frr - far)))])
+            out[name + tag + "__sums"] = np.array([frr.sum(), far.sum()])
+            if frr.size <= 4200:
+                out[name + tag + "__frr"], out[name + tag + "__far"] = frr, far
+                out[name + tag + "__thr"] = thr[1:].astype(np.float64)
+            if tag == "" and np.unique(np.concatenate((t, n))).size >= 3:
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    curve, cthr = rem.compute_tDCF(t, n, DET_ASV[0], DET_ASV[1], DET_ASV[2], DET_COST, False)
+                i = int(np.argmin(curve))
+                out[name + "__tdcf"] = np.array([curve[i], float(cthr[i]), float(i), curve.sum()])
+                if curve.size <= 4200:
+                    out[name + "__tdcf_curve"] = curve
+    rng = np.random.RandomState(7)
+    tar_asv, non_asv, spoof_asv = rng.randn(900) * 2 + 3, rng.randn(1100) * 2 - 3, rng.randn(1300) * 2 + 1
+    non_asv[:40] = tar_asv[:40]                                # exact cross-array ties around the threshold
+    e, thr = rem.compute_eer(tar_asv, non_asv)
+    rates = rem.obtain_asv_error_rates(tar_asv, non_asv, spoof_asv, thr)
+    out["asv__tar"], out["asv__non"], out["asv__spoof"] = tar_asv, non_asv, spoof_asv
+    out["asv__expected"] = np.array([e, thr] + [float(r) for r in rates])
+    np.savez_compressed(os.path.join(GOLD, "det_golden.npz"), **out)
+    print("det_golden.npz", len(out), "arrays,", os.path.getsize(os.path.join(GOLD, "det_golden.npz")), "bytes")
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
-    golden_lfcc()
-    golden_padcrop()
-    golden_nets()
+    if "--det-only" not in sys.argv:
+        golden_lfcc()
+        golden_padcrop()
+        golden_nets()
+    golden_det()

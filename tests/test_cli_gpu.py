@@ -24,7 +24,11 @@ def test_train_then_score(tmp_path, arch):
     assert lines[0].startswith("Start recording") and len(lines) == 1 + 2 * 4
     e, s, l = lines[1].split("\t")
     assert (e, s) == ("0", "0") and float(l) > 0
-    assert len(open(out / "dev_loss.log").read().strip().splitlines()) == 3
+    dev = open(out / "dev_loss.log").read().strip().splitlines()
+    assert len(dev) == 3
+    for ln in dev[1:]:                                   # epoch \t dev loss \t EER (sorted / reduced on the GPU)
+        ep, dl, eer = ln.split("\t")
+        assert float(dl) == float(dl) and (0.0 <= float(eer) <= 1.0 or float(eer) != float(eer)), ln
     for name in ("args.json", "anti-spoofing_feat_model.pt", "anti-spoofing_loss_model.pt",
                  "checkpoint/anti-spoofing_feat_model_2.pt", "checkpoint/anti-spoofing_loss_model_2.pt"):
         assert os.path.exists(out / name), name

@@ -174,3 +174,58 @@ def test_tensor_core_lfcc_algorithm_and_tables_on_cpu():
     want = lo.lfcc(w)[:, :, :20]
     assert lfcc_close(got, want).all(), lfcc_worst(got, want)
     assert lfcc_worst(got, want) < 2e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# detection metrics (eval_metrics.py): the numpy restatement against the reference's own outputs
+# ---------------------------------------------------------------------------------------------
+def test_det_oracle_bit_identical_to_reference_golden(golden_dir):
+    import det_cases as dc
+    from oracle import metrics_oracle as mo
+    g = dc.load(golden_dir)
+    names = dc.case_names(g)
+    assert len(names) >= 12
+    for name in names:
+        tar, non = g[name + "__target"], g[name + "__nontarget"]
+        for tag, neg in (("", False), ("_neg", True)):
+            frr, far, thr = mo.det_curve(tar, non, negate=neg)
+            e, eth, idx = mo.eer(tar, non, negate=neg)
+            want = g[name + tag + "__eer"]
+            assert dc.same(e, want[0]) and idx == int(want[2]), (name, tag)
+            if idx > 0 or tar.dtype == np.float64:       # numpy 2 subtracts the 0.001 of point 0 in the input dtype
+                assert dc.same(eth, want[1]), (name, tag)
+            assert dc.same([frr.sum(), far.sum()], g[name + tag + "__sums"]), (name, tag)
+            if name + tag + "__frr" in g.files:
+                assert dc.same(frr, g[name + tag + "__frr"]) and dc.same(far, g[name + tag + "__far"]), (name, tag)
+                assert dc.same(thr[1:], g[name + tag + "__thr"]), (name, tag)
+        if name + "__tdcf" in g.files:
+            c1, c2 = mo.tdcf_weights(*dc.DET_ASV, dc.DET_COST)
+            curve, cthr = mo.tdcf_curve(tar, non, c1, c2)
+            i = int(np.argmin(curve))
+            want = g[name + "__tdcf"]
+            assert dc.same(curve[i], want[0]) and i == int(want[2]) and dc.same(curve.sum(), want[3]), name
+            if name + "__tdcf_curve" in g.files:
+                assert dc.same(curve, g[name + "__tdcf_curve"]), name
+    e, thr, _ = mo.eer(g["asv__tar"], g["asv__non"])
+    rates = mo.asv_error_rates(g["asv__tar"], g["asv__non"], g["asv__spoof"], thr)
+    assert dc.same([e, thr] + list(rates), g["asv__expected"])
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree not mounted")
+def test_det_oracle_vs_reference_on_fresh_random_scores():
+    import sys
+    import det_cases as dc
+    from oracle import metrics_oracle as mo
+    sys.path.insert(0, ref_shim.REFERENCE_ROOT)
+    import eval_metrics as rem
+    rng = np.random.RandomState(99)
+    for trial in range(20):
+        nt, nn = int(rng.randint(1, 400)), int(rng.randint(1, 400))
+        q = [None, 1, 2][trial % 3]
+        tar, non = rng.randn(nt) + 0.5, rng.randn(nn) - 0.5
+        if q:
+            tar, non = np.round(tar, q), np.round(non, q)
+        frr, far, thr = rem.compute_det_curve(tar, non)
+        a, b, c = mo.det_curve(tar, non)
+        assert dc.same(a, frr) and dc.same(b, far) and dc.same(c, thr)
+        assert dc.same(mo.eer(tar, non)[:2], rem.compute_eer(tar, non))
