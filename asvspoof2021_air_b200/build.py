@@ -36,8 +36,11 @@ def _compile(args):
     src, obj, headers, verbose = args
     if not _newer(src, obj, headers):
         return src, "", False
-    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
-    cmd = [_nvcc()] + ARCH + flags + ["-c", src, "-o", obj]
+    if src.endswith(".cpp"):                 # host-only sources (audio ingest): plain C++ through nvcc's host compiler
+        cmd = [_nvcc(), "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-Wall", "-I", CSRC, "-c", src, "-o", obj]
+    else:
+        flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+        cmd = [_nvcc()] + ARCH + flags + ["-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
@@ -46,11 +49,11 @@ def _compile(args):
 
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
-    srcs = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+    srcs = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cpp")))
     headers = tuple(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
     headers += tuple(os.path.join(os.path.dirname(HERE), "include", f)
                      for f in os.listdir(os.path.join(os.path.dirname(HERE), "include")) if f.endswith(".h"))
-    objs = [os.path.join(OBJ, os.path.basename(s)[:-3] + ".o") for s in srcs]
+    objs = [os.path.join(OBJ, os.path.splitext(os.path.basename(s))[0] + ".o") for s in srcs]
     if force:
         for o in objs:
             if os.path.exists(o):
@@ -62,7 +65,7 @@ def build(force=False, verbose=False):
             if did and verbose:
                 print("[build] %s\n%s" % (os.path.basename(src), log))
     if changed or not os.path.exists(LIB):
-        cmd = [_nvcc()] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcuda"]
+        cmd = [_nvcc()] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcuda", "-lpthread"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))

@@ -88,13 +88,14 @@ def test_on_ASVspoof2021(task, feat_model_path, loss_model_path, output_score_pa
         raise SystemExit("no input: pass --wave_dir/--protocol or --synthetic N")
     os.makedirs(output_score_path, exist_ok=True)
     path = score_file_path(output_score_path, model_name, task)
+    order = [list(range(lo, min(lo + args.batch_size, len(src)))) for lo in range(0, len(src), args.batch_size)]
     with open(path, "w") as f:
-        for lo in range(0, len(src), args.batch_size):
-            idx = list(range(lo, min(lo + args.batch_size, len(src))))
-            waves, lengths, labels, names, start = src.batch(idx)
-            s = tr.score_step(waves.cuda(), None if int(lengths.min()) == waves.shape[1] else lengths, start).cpu()
+        # decode + H2D of the next batches overlap the forward pass of this one (data.Prefetcher)
+        for batch in data.Prefetcher(src, order, depth=2, device=torch.device("cuda", torch.cuda.current_device())):
+            waves, lengths, _, names, start = batch
+            s = tr.score_step(waves, lengths, start).cpu()
             for j, name in enumerate(names):
-                f.write(format_line(task, name, float(s[j]), int(labels[j])))
+                f.write(format_line(task, name, float(s[j]), int(batch.labels_host[j])))
     return path
 
 

@@ -364,6 +364,24 @@ int air_det_threshold_counts_f32(const float* scores, long long n, double thresh
 int air_det_threshold_counts_f64(const double* scores, long long n, double threshold,
                                  unsigned long long* counts_ge_lt, air_stream_t stream);
 
+
+/* ---------------------------------------------------------------------------------------------
+ * Host-side audio ingest (csrc/audio_io.cpp, no CUDA): FLAC (decoder written from RFC 9639; CRC-8 /
+ * CRC-16 checked, MD5 of the audio on request) and RIFF/WAVE (PCM 8/16/24/32, float32) -> float32
+ * mono samples, scaled by 2^-(bits-1), channels averaged.  Replaces the reference's per-item
+ * librosa.load / soundfile.read (raw_dataset.py:20-28,61-66).  flags bit 0: verify the FLAC MD5.
+ * Status: 0, -1 argument, -2 unsupported stream, -3 I/O, -4 malformed stream, -5 checksum mismatch.
+ * air_audio_decode_batch_f32: n files -> rows of a caller-owned (pinned) matrix with row stride ld,
+ * zero-padded / truncated to ld, on `threads` host threads (<= 0: all cores); lengths[i] = the file's
+ * own length, status[i] its code; returns the first non-zero status. */
+int air_audio_info(const char* path, int* sample_rate, int* channels, int* bits, long long* frames);
+int air_audio_decode_f32(const char* path, float* out, long long capacity, long long* frames,
+                         int* sample_rate, int flags);
+int air_audio_decode_i32(const char* path, int* out, long long capacity, long long* frames, int* channels,
+                         int* bits, int* sample_rate, int flags);
+int air_audio_decode_batch_f32(const char* const* paths, int n, float* out, long long ld, int* lengths,
+                               int* sample_rates, int* status, int threads, int flags);
+
 #ifdef __cplusplus
 }
 #endif

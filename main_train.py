@@ -182,6 +182,8 @@ def train(args):
         model = torch.load(os.path.join(args.out_fold, "anti-spoofing_feat_model.pt"), weights_only=False)
         lp = os.path.join(args.out_fold, "anti-spoofing_loss_model.pt")
         tr.load_modules(model, torch.load(lp, weights_only=False) if os.path.exists(lp) else None)
+    from asvspoof2021_air_b200 import data
+    device = torch.device("cuda", torch.cuda.current_device())
     src, dev_src = _source(args), _source(args, dev=True)
     per_rank = args.batch_size
     order_rng = np.random.RandomState(args.seed)
@@ -192,12 +194,10 @@ def train(args):
         lr = adjust_learning_rate(args, args.lr, epoch)
         perm = order_rng.permutation(len(src))                            # SubsetRandomSampler, main_train.py:226-242
         pending = []
-        for step in range(steps):
-            base = (step * world + rank) * per_rank
-            idx = [perm[(base + j) % len(src)] for j in range(per_rank)]
-            waves, lengths, labels, _, start = src.batch(idx)
-            loss = tr.train_step(waves.cuda(non_blocking=True), labels.cuda(non_blocking=True),
-                                 lengths=None if int(lengths.min()) == waves.shape[1] else lengths, start=start, lr=lr)
+        order = [[perm[((step * world + rank) * per_rank + j) % len(src)] for j in range(per_rank)] for step in range(steps)]
+        # decode / collate / H2D of the next batches run on a host thread + copy stream while this step computes
+        for step, (waves, lengths, labels, _, start) in enumerate(data.Prefetcher(src, order, depth=2, device=device)):
+            loss = tr.train_step(waves, labels, lengths=lengths, start=start, lr=lr)
             pending.append((step, loss.clone()))
             if len(pending) >= args.log_every or step == steps - 1:
                 if rank == 0:                                             # main_train.py:479-481, batched host reads
@@ -208,12 +208,11 @@ def train(args):
         val = float("nan")
         if dev_src is not None:
             tot, cnt, dev_scores, dev_labels = 0.0, 0, [], []
-            for lo in range(rank * per_rank, len(dev_src), per_rank * world):
-                idx = list(range(lo, min(lo + per_rank, len(dev_src))))
-                waves, lengths, labels, _, start = dev_src.batch(idx)
-                labels = labels.cuda()
-                l, sc = tr.eval_loss(waves.cuda(), labels, None if int(lengths.min()) == waves.shape[1] else lengths, start)
-                tot, cnt = tot + float(l) * len(idx), cnt + len(idx)
+            dev_order = [list(range(lo, min(lo + per_rank, len(dev_src))))
+                         for lo in range(rank * per_rank, len(dev_src), per_rank * world)]
+            for waves, lengths, labels, names, start in data.Prefetcher(dev_src, dev_order, depth=2, device=device):
+                l, sc = tr.eval_loss(waves, labels, lengths, start)
+                tot, cnt = tot + float(l) * len(names), cnt + len(names)
                 dev_scores.append(sc.clone())
                 dev_labels.append(labels)
             t = torch.tensor([tot, cnt], device="cuda", dtype=torch.float64)

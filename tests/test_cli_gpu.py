@@ -61,3 +61,41 @@ def test_train_then_score(tmp_path, arch):
     want = (-score).cpu()
     got = torch.tensor([float(x[1]) for x in rows])
     assert torch.allclose(got, want, atol=5e-3), (got - want).abs().max()
+
+
+def test_train_and_score_from_a_flac_folder(tmp_path):
+    """(f) row 1 end to end: ASVspoof-style FLAC folder -> native batch decoder -> prefetch thread + copy stream ->
+    fused LFCC / ResNet step; ragged lengths (shorter and longer than feat_len frames) in one batch."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import flac_writer as fw
+    rng = np.random.RandomState(0)
+    wav = tmp_path / "flac"
+    wav.mkdir()
+    proto = []
+    for i in range(12):
+        n = 125000 if i == 5 else int(rng.randint(9000, 26000))          # one utterance longer than 750 frames: cropped
+        x = np.round(np.cumsum(rng.randn(n)) * 30).astype(np.int64).clip(-30000, 30000)
+        blocks = [4096] * (n // 4096) + ([n % 4096] if n % 4096 else [])
+        fw.write_flac(str(wav / ("LA_T_%07d.flac" % i)), x, 16, 16000, [fw.FrameSpec(b, [fw.Sub("fixed", 1, rice=9)]) for b in blocks])
+        proto.append("LA_0079 LA_T_%07d - %s %s" % (i, "-" if i % 2 == 0 else "A01", "bonafide" if i % 2 == 0 else "spoof"))
+    (tmp_path / "proto.txt").write_text("\n".join(proto) + "\n")
+    out = tmp_path / "models" / "lfcc_resnet_flac"
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "main_train.py"), "-o", str(out), "-m", "resnet", "--add_loss", "ang_iso",
+                        "--gpu", "0", "--wave_dir", str(wav), "--protocol", str(tmp_path / "proto.txt"), "--dev_wave_dir", str(wav),
+                        "--dev_protocol", str(tmp_path / "proto.txt"), "--batch_size", "4", "--num_epochs", "1", "--log_every", "1"], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    lines = open(out / "train_loss.log").read().strip().splitlines()
+    assert len(lines) == 1 + 3 and all(float(x.split("\t")[2]) == float(x.split("\t")[2]) for x in lines[1:])
+    ep, dl, eer = open(out / "dev_loss.log").read().strip().splitlines()[1].split("\t")
+    assert 0.0 <= float(eer) <= 1.0
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "generate_score.py"), "--model_folder", str(tmp_path / "models"),
+                        "-n", "lfcc_resnet_flac", "-s", str(tmp_path / "scores"), "-t", "19eval", "-l", "ocsoftmax", "--gpu", "0",
+                        "--wave_dir", str(wav), "--protocol", str(tmp_path / "proto.txt"), "--batch_size", "5"],
+                       capture_output=True, text=True, timeout=600, env=env, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    rows = [ln.split() for ln in open(r.stdout.strip().splitlines()[-1]).read().strip().splitlines()]
+    assert [x[0] for x in rows] == ["LA_T_%07d" % i for i in range(12)]
+    assert [x[2] for x in rows] == ["bonafide" if i % 2 == 0 else "spoof" for i in range(12)]
+    assert all(-1.0001 <= float(x[1]) <= 1.0001 for x in rows)

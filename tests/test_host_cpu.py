@@ -129,6 +129,43 @@ def test_data_sources(tmp_path):
     assert 0 <= int(start[0]) < (1 + 200000 // 160) - 750 and int(start[1]) == 0      # dataset.py:66-69
 
 
+def test_flac_folder_and_prefetcher_on_cpu(tmp_path):
+    """ASVspoof-style folder of FLAC files through the native batch decoder, iterated by the prefetch thread."""
+    import flac_writer as fw
+    from asvspoof2021_air_b200 import data
+    rng = np.random.RandomState(4)
+    proto, waves = [], {}
+    for i in range(9):
+        n = int(rng.randint(1000, 5000))
+        x = np.round(np.cumsum(rng.randn(n)) * 20).astype(np.int64).clip(-30000, 30000)
+        blocks = [1152] * (n // 1152) + ([n % 1152] if n % 1152 else [])
+        fw.write_flac(str(tmp_path / ("LA_T_%07d.flac" % i)), x, 16, 16000,
+                      [fw.FrameSpec(b, [fw.Sub("fixed", 1, porder=0)]) for b in blocks])
+        waves["LA_T_%07d" % i] = (x / 32768.0).astype(np.float32)
+        proto.append("LA_0079 LA_T_%07d - %s %s" % (i, "-" if i % 2 == 0 else "A01", "bonafide" if i % 2 == 0 else "spoof"))
+    (tmp_path / "proto.txt").write_text("\n".join(proto) + "\n")
+    src = data.WaveFolder(str(tmp_path), str(tmp_path / "proto.txt"), feat_len=750, seed=0, threads=3, verify=True)
+    order = [[0, 1, 2, 3], [4, 5, 6, 7], [8]]
+    seen = []
+    for w, lens, lab, names, start in data.Prefetcher(src, order, depth=2, device=None):
+        lens = lens if lens is not None else torch.full((len(names),), w.shape[1], dtype=torch.int32)
+        assert w.shape == (len(names), int(lens.max())) and lab.tolist() == [int(n[-1]) % 2 for n in names]
+        for j, n in enumerate(names):
+            assert int(lens[j]) == len(waves[n]) and np.array_equal(w[j, :lens[j]].numpy(), waves[n]) and not w[j, lens[j]:].any()
+        seen += names
+    assert seen == ["LA_T_%07d" % i for i in range(9)]
+    # a missing file is an error at construction, a damaged one surfaces in the consumer
+    (tmp_path / "p2.txt").write_text("x LA_T_9999999 - - bonafide\n")
+    with pytest.raises(FileNotFoundError):
+        data.WaveFolder(str(tmp_path), str(tmp_path / "p2.txt"))
+    raw = bytearray((tmp_path / "LA_T_0000003.flac").read_bytes())
+    raw[-9] ^= 4
+    (tmp_path / "LA_T_0000003.flac").write_bytes(bytes(raw))
+    from asvspoof2021_air_b200.audio_io import AudioError
+    with pytest.raises(AudioError, match="LA_T_0000003"):
+        list(data.Prefetcher(src, order, device=None))
+
+
 def test_parallel_helpers_single_process():
     from asvspoof2021_air_b200 import parallel
     assert [parallel.shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
