@@ -95,7 +95,9 @@ def test_train_and_score_from_a_flac_folder(tmp_path):
                         "--wave_dir", str(wav), "--protocol", str(tmp_path / "proto.txt"), "--batch_size", "5"],
                        capture_output=True, text=True, timeout=600, env=env, cwd=str(tmp_path))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
-    rows = [ln.split() for ln in open(r.stdout.strip().splitlines()[-1]).read().strip().splitlines()]
+    # '19' tasks write under ./scores relative to the working directory (generate_score.py:29-30 of the reference)
+    path = os.path.join(str(tmp_path), r.stdout.strip().splitlines()[-1])
+    rows = [ln.split() for ln in open(path).read().strip().splitlines()]
     assert [x[0] for x in rows] == ["LA_T_%07d" % i for i in range(12)]
     assert [x[2] for x in rows] == ["bonafide" if i % 2 == 0 else "spoof" for i in range(12)]
     assert all(-1.0001 <= float(x[1]) <= 1.0001 for x in rows)
