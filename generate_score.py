@@ -74,8 +74,9 @@ def test_on_ASVspoof2021(task, feat_model_path, loss_model_path, output_score_pa
         raise SystemExit("only -l ocsoftmax is implemented on the fused path (SURVEY.md section 2.1)")
     if not torch.cuda.is_available():
         raise SystemExit("generate_score.py needs a CUDA device: the fused path has no CPU fallback")
-    model = torch.load(feat_model_path, weights_only=False)
-    loss_model = torch.load(loss_model_path, weights_only=False)
+    from asvspoof2021_air_b200 import compat
+    model = compat.load_module(feat_model_path)              # this package's pickles and the reference's own
+    loss_model = compat.load_module(loss_model_path)
     arch = "ecapa" if type(model).__name__ == "Res2Net2" else "resnet"
     tr = Trainer(arch=arch, enc_dim=loss_model.center.shape[1], feat_len=args.feat_len, padding=args.padding,
                  r_real=loss_model.r_real, r_fake=loss_model.r_fake, alpha=loss_model.alpha, device="cuda")

@@ -179,9 +179,10 @@ def train(args):
                  r_fake=args.r_fake, alpha=args.alpha, weight_loss=args.weight_loss, device="cuda", process_group=pg,
                  seed=args.seed)
     if args.continue_training:                                            # main_train.py:172-173
-        model = torch.load(os.path.join(args.out_fold, "anti-spoofing_feat_model.pt"), weights_only=False)
+        from asvspoof2021_air_b200 import compat
+        model = compat.load_module(os.path.join(args.out_fold, "anti-spoofing_feat_model.pt"))
         lp = os.path.join(args.out_fold, "anti-spoofing_loss_model.pt")
-        tr.load_modules(model, torch.load(lp, weights_only=False) if os.path.exists(lp) else None)
+        tr.load_modules(model, compat.load_module(lp) if os.path.exists(lp) else None)
     from asvspoof2021_air_b200 import data
     device = torch.device("cuda", torch.cuda.current_device())
     src, dev_src = _source(args), _source(args, dev=True)

@@ -216,3 +216,128 @@ def test_gradient_reducer_gloo_world_size_2(tmp_path):
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count(" ok") == 2 and "rank 0" in r.stdout and "rank 1" in r.stdout, r.stdout
+
+
+# ---------------------------------------------------------------------------------------------
+# checkpoint compatibility with the reference's whole-module pickles (compat.py)
+# ---------------------------------------------------------------------------------------------
+_STANDIN = '''
+import sys, torch, torch.nn as nn
+sys.path.insert(0, %(root)r)
+class PreActBlock(nn.Module): pass
+class SelfAttention(nn.Module): pass
+class ResNet(nn.Module): pass
+class SEModule(nn.Module): pass
+class Bottle2neck(nn.Module): pass
+class Res2Net2(nn.Module): pass
+class AngularIsoLoss(nn.Module): pass
+'''
+
+_STANDIN_MAIN = '''
+import sys, torch, torch.nn as nn
+sys.path.insert(0, %(tmp)r)
+import model, ECAPA_TDNN, loss
+LEAF = {"resnet": {"attention": model.SelfAttention}, "ecapa": {"se": ECAPA_TDNN.SEModule}}
+def tree(root, sd, kinds, block_cls, depth_cls):
+    """Hang the tensors of a flat state_dict on a module tree whose classes carry the reference's names."""
+    for key, t in sd.items():
+        parts, node = key.split("."), root
+        for i, p in enumerate(parts[:-1]):
+            if p not in node._modules:
+                if p in depth_cls: cls = depth_cls[p]
+                elif p.isdigit() and i == 1 and parts[0].startswith("layer"): cls = block_cls
+                elif parts[0].startswith("layer") and i == 0 and block_cls is ECAPA_TDNN.Bottle2neck: cls = block_cls
+                else: cls = nn.Sequential if not (parts[i + 1:] and parts[i + 1] in ("weight", "bias", "running_mean")) else nn.Module
+                node.add_module(p, cls())
+            node = node._modules[p]
+        if kinds[key] == "param": node.register_parameter(parts[-1], nn.Parameter(t.clone()))
+        else: node.register_buffer(parts[-1], t.clone())
+    return root
+blob = torch.load(%(blob)r)
+m = tree(model.ResNet(), blob["resnet"], blob["resnet_kinds"], model.PreActBlock, LEAF["resnet"]); m.eval()
+torch.save(m, %(tmp)r + "/ref_resnet.pt")
+e = tree(ECAPA_TDNN.Res2Net2(), blob["ecapa"], blob["ecapa_kinds"], ECAPA_TDNN.Bottle2neck, LEAF["ecapa"]); e.train()
+torch.save(e, %(tmp)r + "/ref_ecapa.pt")
+l = loss.AngularIsoLoss(); l.center = nn.Parameter(blob["center"]); l.r_real, l.r_fake, l.alpha, l.feat_dim = 0.9, 0.2, 20.0, 256
+l.softplus = nn.Softplus()
+torch.save(l, %(tmp)r + "/ref_loss.pt")
+'''
+
+
+def test_reference_style_pickles_load_without_the_reference(tmp_path):
+    """Pickles whose classes live in modules named `model`, `ECAPA_TDNN`, `loss` (as the reference's do) are written
+    by a subprocess that has such modules, then loaded here, where they do not exist."""
+    import subprocess
+    from asvspoof2021_air_b200 import compat
+    from asvspoof2021_air_b200.ecapa_tdnn import Bottle2neck, Res2Net2
+    from asvspoof2021_air_b200.resnet import ResNet
+    torch.manual_seed(5)
+    r = ResNet(3, 256, '18', nclasses=2, device="cpu")
+    e = Res2Net2(Bottle2neck, C=512, model_scale=8, nOut=2, n_mels=60, device="cpu")
+    for m in (r, e):
+        for k, v in m.state_dict().items():
+            if v.dtype.is_floating_point:
+                v.copy_(torch.randn_like(v) * 0.1 + (1.0 if k.endswith("running_var") else 0.0))
+    kinds = lambda m: {k: ("param" if k in dict(m.named_parameters()) else "buffer") for k in m.state_dict()}
+    center = torch.randn(1, 256)
+    torch.save({"resnet": r.state_dict(), "resnet_kinds": kinds(r), "ecapa": e.state_dict(), "ecapa_kinds": kinds(e),
+                "center": center}, tmp_path / "blob.pt")
+    for name in ("model", "ECAPA_TDNN", "loss"):
+        (tmp_path / (name + ".py")).write_text(_STANDIN % {"root": ROOT})
+    (tmp_path / "make.py").write_text(_STANDIN_MAIN % {"tmp": str(tmp_path), "blob": str(tmp_path / "blob.pt")})
+    p = subprocess.run([sys.executable, str(tmp_path / "make.py")], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    for name in ("model", "ECAPA_TDNN", "loss"):
+        assert name not in sys.modules
+    with pytest.raises(Exception):
+        torch.load(tmp_path / "ref_resnet.pt", weights_only=False)          # plain torch.load cannot resolve `model.ResNet`
+    r2 = compat.load_module(str(tmp_path / "ref_resnet.pt"), device="cpu")
+    e2 = compat.load_module(str(tmp_path / "ref_ecapa.pt"), device="cpu")
+    l2 = compat.load_module(str(tmp_path / "ref_loss.pt"))
+    assert type(r2) is ResNet and not r2.training and type(e2) is Res2Net2 and e2.training
+    for a, b in ((r, r2), (e, e2)):
+        sa, sb = a.state_dict(), b.state_dict()
+        assert list(sa) == list(sb) and all(torch.equal(sa[k], sb[k]) for k in sa)
+    assert type(l2).__name__ == "AngularIsoLoss" and torch.equal(l2.center.detach(), center)
+    assert (l2.r_real, l2.r_fake, l2.alpha) == (0.9, 0.2, 20.0)
+    for name in ("model", "ECAPA_TDNN", "loss"):
+        assert name not in sys.modules                                       # the shims do not outlive the load
+    # this package's own pickles pass straight through
+    buf = tmp_path / "own.pt"
+    torch.save(r, buf)
+    r3 = compat.load_module(str(buf), device="cpu")
+    assert type(r3) is ResNet and all(torch.equal(v, r3.state_dict()[k]) for k, v in r.state_dict().items())
+    with pytest.raises(NotImplementedError):
+        compat.adopt(torch.nn.Linear(2, 2))
+
+
+def test_real_reference_pickles_load_through_compat(tmp_path):
+    """The same with the reference's own classes (authoring container only: needs /root/reference)."""
+    from oracle import ref_shim
+    if not ref_shim.reference_available():
+        pytest.skip("reference tree not mounted")
+    import subprocess
+    code = '''
+import sys, torch
+sys.path.insert(0, %r)
+from oracle import ref_shim
+rn, ec, ls = ref_shim.load("resnet"), ref_shim.load("ecapa_tdnn"), ref_shim.load("loss")
+torch.manual_seed(688)
+torch.save(rn.ResNet(3, 256, "18", nclasses=2), %r)
+torch.save(ec.Res2Net2(ec.Bottle2neck, C=512, model_scale=8, nOut=2, n_mels=60), %r)
+torch.save(ls.AngularIsoLoss(256, r_real=0.9, r_fake=0.2, alpha=20.0), %r)
+torch.save({"resnet": rn.ResNet(3, 256, "18", nclasses=2).state_dict()}, %r)
+''' % (ROOT, str(tmp_path / "r.pt"), str(tmp_path / "e.pt"), str(tmp_path / "l.pt"), str(tmp_path / "sd.pt"))
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    from asvspoof2021_air_b200 import compat
+    with compat.reference_modules():
+        raw = torch.load(tmp_path / "r.pt", map_location="cpu", weights_only=False)
+    want = compat.named_state(raw)
+    m = compat.load_module(str(tmp_path / "r.pt"), device="cpu")
+    sd = m.state_dict()
+    assert len(sd) == 117 and set(sd) == set(want) and all(torch.equal(sd[k], want[k]) for k in sd)
+    e = compat.load_module(str(tmp_path / "e.pt"), device="cpu")
+    assert len(e.state_dict()) == 248 and e.C == 512 and e.scale == 8
+    l = compat.load_module(str(tmp_path / "l.pt"))
+    assert (l.r_real, l.r_fake, l.alpha) == (0.9, 0.2, 20.0) and l.center.shape == (1, 256)
