@@ -176,6 +176,34 @@ def test_tensor_core_lfcc_algorithm_and_tables_on_cpu():
     assert lfcc_worst(got, want) < 2e-5
 
 
+def test_tensor_core_lfcc_dynamic_range_limit_and_kernel_choice_on_cpu():
+    """Known limit of the 3-term bf16 split: on a frame whose weak bands lie ~60 dB under its strongest harmonics the
+    tensor-core arithmetic leaves the 1e-4 bar (the fp32 arithmetic of the reference does not), which is why
+    LFCC.impl_for() serves fp32 output from the fp32 FFT kernel and only bf16 output from the tensor-core kernel."""
+    import lfcc_emulation as em
+    from asvspoof2021_air_b200 import lfcc_tables as lt
+    from asvspoof2021_air_b200.feature_extraction import LFCC
+    from oracle import lfcc_torch
+    from tolerances import lfcc_worst
+    n = np.arange(8000)
+    rng = np.random.RandomState(0)
+    speech = sum(0.3 / h * np.sin(2 * np.pi * 140 * h * n / 16000) for h in range(1, 9)) + 3e-4 * rng.randn(8000)
+    w = speech[None].astype(np.float32)
+    want = lo.lfcc(w)[:, :, :20]
+    fb, dct = lt.linear_filterbank(512, 16000, 20), lt.dct_ortho_matrix(20)
+    tc = em.lfcc_tc_emulate(w, lt.pack_tc_table(fb, dct).numpy(), lt.pack_tc_dft())
+    fp32 = lfcc_torch.TorchLFCC()(torch.from_numpy(w)).numpy()[:, :, :20]
+    assert 5e-5 < lfcc_worst(tc, want) < 5e-4            # measured 1.4e-4: over the bar, far under bf16's 2^-9
+    assert lfcc_worst(fp32, want) < 3e-5                 # measured 8.6e-6
+    m = LFCC(320, 160, 512, 16000, 20)
+    if m.impl == "auto":
+        assert m.impl_for(torch.float32) == "fft" and m.impl_for(torch.bfloat16) == "tc"
+    m.impl = "tc"
+    assert m.impl_for(torch.float32) == "tc"
+    m.impl = "fft"
+    assert m.impl_for(torch.bfloat16) == "fft"
+
+
 # ---------------------------------------------------------------------------------------------
 # detection metrics (eval_metrics.py): the numpy restatement against the reference's own outputs
 # ---------------------------------------------------------------------------------------------
