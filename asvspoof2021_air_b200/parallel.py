@@ -115,3 +115,23 @@ def broadcast_state(tensors, src=0, group=None):
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         for t in tensors:
             dist.broadcast(t, src=src, group=group)
+
+
+def gather_ragged(columns, group=None):
+    """All-gather per-rank 1-D tensors of different lengths (validation scores + labels of each rank's shard of the
+    dev set): `columns` is a list of equally long 1-D tensors; returns the list of their concatenations over ranks,
+    in rank order.  One size exchange + one padded all-gather; identity when not distributed."""
+    if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+        return list(columns)
+    world = dist.get_world_size(group)
+    dev = columns[0].device
+    n = torch.tensor([columns[0].numel()], device=dev, dtype=torch.int64)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(x) for x in sizes]
+    pad = torch.zeros(len(columns), max(max(sizes), 1), device=dev, dtype=torch.float64)
+    for i, c in enumerate(columns):
+        pad[i, :c.numel()] = c.to(torch.float64)
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    return [torch.cat([b[i, :k] for b, k in zip(bufs, sizes)]).to(c.dtype) for i, c in enumerate(columns)]

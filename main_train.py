@@ -136,16 +136,8 @@ def dev_eer(score_chunks, label_chunks, world):
     else:
         scores, labels = torch.cat(score_chunks).float(), torch.cat(label_chunks).long()
     if world > 1:
-        n = torch.tensor([scores.numel()], device="cuda")
-        sizes = [torch.zeros_like(n) for _ in range(world)]
-        torch.distributed.all_gather(sizes, n)
-        m = max(int(x) for x in sizes)
-        pad = torch.zeros(2, m, device="cuda")
-        pad[0, :scores.numel()], pad[1, :scores.numel()] = scores, labels.float()
-        bufs = [torch.empty_like(pad) for _ in range(world)]
-        torch.distributed.all_gather(bufs, pad)
-        scores = torch.cat([b[0, :int(x)] for b, x in zip(bufs, sizes)])
-        labels = torch.cat([b[1, :int(x)] for b, x in zip(bufs, sizes)]).long()
+        from asvspoof2021_air_b200 import parallel
+        scores, labels = parallel.gather_ragged([scores, labels])
     tar, non = scores[labels == 0], scores[labels == 1]
     if tar.numel() == 0 or non.numel() == 0:
         return float("nan")

@@ -202,6 +202,15 @@ _WORKER = textwrap.dedent('''
     assert torch.equal(p, torch.zeros(5))
     lo, hi = parallel.shard_range(7, rank, world)
     t = torch.tensor([hi - lo], dtype=torch.float32); dist.all_reduce(t); assert int(t) == 7
+    # validation scores / labels of unequal shards (main_train.dev_eer): rank 0 holds 3 trials, rank 1 holds 5
+    k = 3 + 2 * rank
+    sc = torch.arange(k, dtype=torch.float32) + 10 * rank
+    lab = (torch.arange(k) %% 2).long()
+    g_sc, g_lab = parallel.gather_ragged([sc, lab])
+    assert g_sc.tolist() == [0.0, 1.0, 2.0, 10.0, 11.0, 12.0, 13.0, 14.0] and g_sc.dtype == torch.float32
+    assert g_lab.tolist() == [0, 1, 0, 0, 1, 0, 1, 0] and g_lab.dtype == torch.int64
+    e_sc, e_lab = parallel.gather_ragged([sc[:0] if rank == 0 else sc, lab[:0] if rank == 0 else lab])
+    assert e_sc.tolist() == [10.0, 11.0, 12.0, 13.0, 14.0] and e_lab.numel() == 5
     dist.destroy_process_group()
     sys.stdout.write("rank %%d ok\\n" %% rank); sys.stdout.flush()
 ''')
