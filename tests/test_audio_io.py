@@ -2,7 +2,6 @@
 specification (RFC 9639 appendix D.1 and D.3 -- streams produced by the reference libFLAC encoder, each carrying the
 MD5 of its audio, which the decoder verifies) and (b) streams from tests/flac_writer.py that exercise every subframe
 type, predictor order, Rice layout, channel decorrelation and header code; the WAV reader against scipy."""
-import os
 import struct
 
 import numpy as np
