@@ -14,7 +14,7 @@ import torch
 from . import _lib
 
 ERRORS = {-1: "bad argument", -2: "unsupported stream (sample size / channel count changes, exotic WAV coding)",
-          -3: "cannot read the file", -4: "not a valid FLAC / WAV stream", -5: "checksum mismatch (CRC-8 / CRC-16 / MD5)"}
+          -3: "cannot read the file", -4: "not a valid FLAC / WAV stream", -5: "checksum mismatch (CRC-8 / CRC-16 / MD5)", -6: "out of memory while decoding"}
 VERIFY_MD5 = 1
 
 

@@ -17,6 +17,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -27,6 +28,7 @@
 #define AIR_ERR_IO (-3)
 #define AIR_ERR_FORMAT (-4)
 #define AIR_ERR_CHECKSUM (-5)
+#define AIR_ERR_NOMEM (-6)
 
 namespace air_audio {
 
@@ -277,12 +279,15 @@ static int read_subframe(BitReader& br, int block, int bps, int64_t* out, std::v
     res.resize((size_t)block);
     const int st = read_residual(br, block, order, res.data());
     if (st != AIR_OK) return st;
+    // Sums wrap in uint64: a valid stream stays far inside 64 bits, a damaged one (caught by the CRC-16 afterwards)
+    // must not run into signed-overflow UB on the way.
+    uint64_t* u = reinterpret_cast<uint64_t*>(out);
     switch (order) {
       case 0: for (int i = 0; i < block; ++i) out[i] = res[i]; break;
-      case 1: for (int i = 1; i < block; ++i) out[i] = res[i] + out[i - 1]; break;
-      case 2: for (int i = 2; i < block; ++i) out[i] = res[i] + 2 * out[i - 1] - out[i - 2]; break;
-      case 3: for (int i = 3; i < block; ++i) out[i] = res[i] + 3 * out[i - 1] - 3 * out[i - 2] + out[i - 3]; break;
-      default: for (int i = 4; i < block; ++i) out[i] = res[i] + 4 * out[i - 1] - 6 * out[i - 2] + 4 * out[i - 3] - out[i - 4];
+      case 1: for (int i = 1; i < block; ++i) u[i] = (uint64_t)(int64_t)res[i] + u[i - 1]; break;
+      case 2: for (int i = 2; i < block; ++i) u[i] = (uint64_t)(int64_t)res[i] + 2 * u[i - 1] - u[i - 2]; break;
+      case 3: for (int i = 3; i < block; ++i) u[i] = (uint64_t)(int64_t)res[i] + 3 * u[i - 1] - 3 * u[i - 2] + u[i - 3]; break;
+      default: for (int i = 4; i < block; ++i) u[i] = (uint64_t)(int64_t)res[i] + 4 * u[i - 1] - 6 * u[i - 2] + 4 * u[i - 3] - u[i - 4];
     }
   } else if (type >= 32) {                                              // LPC, order 1..32
     const int order = type - 31;
@@ -298,15 +303,15 @@ static int read_subframe(BitReader& br, int block, int bps, int64_t* out, std::v
     const int st = read_residual(br, block, order, res.data());
     if (st != AIR_OK) return st;
     for (int i = order; i < block; ++i) {
-      int64_t acc = 0;
-      for (int j = 0; j < order; ++j) acc += (int64_t)coef[j] * out[i - 1 - j];
-      out[i] = res[i] + (acc >> shift);
+      uint64_t acc = 0;                                                 // wraps, see the FIXED predictor above
+      for (int j = 0; j < order; ++j) acc += (uint64_t)(int64_t)coef[j] * (uint64_t)out[i - 1 - j];
+      out[i] = (int64_t)((uint64_t)(int64_t)res[i] + (uint64_t)((int64_t)acc >> shift));
     }
   } else {
     return AIR_ERR_FORMAT;                                              // reserved subframe type
   }
   if (br.bad) return AIR_ERR_FORMAT;
-  if (wasted) for (int i = 0; i < block; ++i) out[i] *= (int64_t)1 << wasted;
+  if (wasted) for (int i = 0; i < block; ++i) out[i] = (int64_t)((uint64_t)out[i] << wasted);
   return AIR_OK;
 }
 
@@ -326,7 +331,13 @@ static int decode_flac(const std::vector<uint8_t>& buf, Pcm& pcm, bool verify_md
   if (st != AIR_OK) return st;
   pcm.sample_rate = si.sample_rate; pcm.channels = si.channels; pcm.bits = si.bits;
   pcm.data.clear();
-  if (si.total > 0) pcm.data.reserve((size_t)si.total * si.channels);
+  // Reserve what the header announces only as far as the file could plausibly hold it (a damaged 36-bit total must
+  // not become a 100 GB allocation); beyond that the vector grows as frames arrive.
+  {
+    const unsigned long long announced = (unsigned long long)si.total * (unsigned)si.channels;
+    const unsigned long long plausible = (unsigned long long)buf.size() * 16ull + 65536ull;
+    if (si.total > 0) pcm.data.reserve((size_t)(announced < plausible ? announced : plausible));
+  }
   std::vector<int64_t>* ch = sc.ch;
   std::vector<int32_t>& res = sc.res;
   long long frames = 0;
@@ -389,19 +400,20 @@ static int decode_flac(const std::vector<uint8_t>& buf, Pcm& pcm, bool verify_md
     const size_t body_len = br.byte_pos();
     const uint32_t want16 = br.bits(16);
     if (br.bad || crc16(base + o, body_len) != want16) return AIR_ERR_CHECKSUM;
-    if (ch_code == 8) for (int i = 0; i < block; ++i) ch[1][i] = ch[0][i] - ch[1][i];
-    else if (ch_code == 9) for (int i = 0; i < block; ++i) ch[0][i] = ch[1][i] + ch[0][i];
+    if (ch_code == 8) for (int i = 0; i < block; ++i) ch[1][i] = (int64_t)((uint64_t)ch[0][i] - (uint64_t)ch[1][i]);
+    else if (ch_code == 9) for (int i = 0; i < block; ++i) ch[0][i] = (int64_t)((uint64_t)ch[1][i] + (uint64_t)ch[0][i]);
     else if (ch_code == 10)
       for (int i = 0; i < block; ++i) {
-        const int64_t side = ch[1][i], mid = (ch[0][i] << 1) | (side & 1);
-        ch[0][i] = (mid + side) >> 1;
-        ch[1][i] = (mid - side) >> 1;
+        const uint64_t side = (uint64_t)ch[1][i], mid = ((uint64_t)ch[0][i] << 1) | (side & 1);
+        ch[0][i] = (int64_t)(mid + side) >> 1;
+        ch[1][i] = (int64_t)(mid - side) >> 1;
       }
     const size_t at = pcm.data.size();
     pcm.data.resize(at + (size_t)block * nch);
     for (int i = 0; i < block; ++i)
       for (int c = 0; c < nch; ++c) pcm.data[at + (size_t)i * nch + c] = (int32_t)ch[c][i];
     frames += block;
+    if ((si.total > 0 && frames > si.total) || frames > 0x7fffffffll) return AIR_ERR_FORMAT;
     o += body_len + 2;
   }
   if (si.total > 0 && frames != si.total) return AIR_ERR_FORMAT;
@@ -486,13 +498,19 @@ struct Decoded {
 };
 
 static int decode_any(const char* path, Decoded& d, int flags, Scratch& sc) {
-  std::vector<uint8_t>& buf = sc.file;
-  d.fdata.clear();
-  d.pcm.data.clear();
-  int st = read_file(path, buf);
-  if (st != AIR_OK) return st;
-  if (buf.size() >= 4 && memcmp(buf.data(), "RIFF", 4) == 0) return decode_wav(buf, d.pcm, d.fdata);
-  return decode_flac(buf, d.pcm, (flags & 1) != 0, sc);
+  try {                                                                 // no exception crosses the C boundary
+    std::vector<uint8_t>& buf = sc.file;
+    d.fdata.clear();
+    d.pcm.data.clear();
+    int st = read_file(path, buf);
+    if (st != AIR_OK) return st;
+    if (buf.size() >= 4 && memcmp(buf.data(), "RIFF", 4) == 0) return decode_wav(buf, d.pcm, d.fdata);
+    return decode_flac(buf, d.pcm, (flags & 1) != 0, sc);
+  } catch (const std::bad_alloc&) {
+    return AIR_ERR_NOMEM;
+  } catch (...) {
+    return AIR_ERR_FORMAT;
+  }
 }
 static int decode_any(const char* path, Decoded& d, int flags) {
   Scratch sc;
@@ -536,6 +554,8 @@ extern "C" int air_audio_info(const char* path, int* sample_rate, int* channels,
     if (!f) return AIR_ERR_IO;
     std::vector<uint8_t> head(1 << 16);
     head.resize(fread(head.data(), 1, head.size(), f));
+    long long file_size = 0;
+    if (fseek(f, 0, SEEK_END) == 0) file_size = ftell(f);
     fclose(f);
     bool done = false;
     if (head.size() >= 12 && memcmp(head.data(), "RIFF", 4) == 0) {
@@ -548,8 +568,9 @@ extern "C" int air_audio_info(const char* path, int* sample_rate, int* channels,
           pcm.sample_rate = (int)le32(head.data() + o + 12);
           block_align = le16(head.data() + o + 20);
           pcm.bits = le16(head.data() + o + 22);
-        } else if (memcmp(head.data() + o, "data", 4) == 0 && block_align > 0 && len != 0xffffffffu) {
-          pcm.frames = len / block_align;
+        } else if (memcmp(head.data() + o, "data", 4) == 0 && block_align > 0) {
+          const long long avail = file_size - (long long)(o + 8);      // what the file really holds (as the decoder does)
+          pcm.frames = ((long long)len < avail ? (long long)len : (avail > 0 ? avail : 0)) / block_align;
           done = true;
         }
         o += 8 + (size_t)len + (len & 1);
@@ -558,7 +579,9 @@ extern "C" int air_audio_info(const char* path, int* sample_rate, int* channels,
       StreamInfo si;
       size_t start = 0;
       // the metadata may be longer than the 64 KB read here (cover art): then fall through to the full decode
-      if (parse_flac_header(head, si, start) == AIR_OK && si.total > 0) {
+      // ... and so does a total no file of this size can hold (a 65 535-sample frame takes >= 14 bytes), which a
+      // caller would otherwise turn into an allocation: only the decoder's own count is trusted then
+      if (parse_flac_header(head, si, start) == AIR_OK && si.total > 0 && si.total <= file_size * 4700 + 65536) {
         pcm.sample_rate = si.sample_rate; pcm.channels = si.channels; pcm.bits = si.bits; pcm.frames = si.total;
         done = true;
       }

@@ -1,6 +1,5 @@
 """Glue that exposes an engine's flat buffers as an nn.Module tree with the reference's
 state_dict names (parameters/buffers are VIEWS of the flat storage, not copies)."""
-import torch
 import torch.nn as nn
 
 

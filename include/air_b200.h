@@ -370,7 +370,9 @@ int air_det_threshold_counts_f64(const double* scores, long long n, double thres
  * CRC-16 checked, MD5 of the audio on request) and RIFF/WAVE (PCM 8/16/24/32, float32) -> float32
  * mono samples, scaled by 2^-(bits-1), channels averaged.  Replaces the reference's per-item
  * librosa.load / soundfile.read (raw_dataset.py:20-28,61-66).  flags bit 0: verify the FLAC MD5.
- * Status: 0, -1 argument, -2 unsupported stream, -3 I/O, -4 malformed stream, -5 checksum mismatch.
+ * Status: 0, -1 argument, -2 unsupported stream, -3 I/O, -4 malformed stream, -5 checksum mismatch,
+ * -6 out of memory.  No exception crosses the boundary; damaged input never crashes the process
+ * (fuzzed under ASan / UBSan, scripts/fuzz_audio.py).
  * air_audio_decode_batch_f32: n files -> rows of a caller-owned (pinned) matrix with row stride ld,
  * zero-padded / truncated to ld, on `threads` host threads (<= 0: all cores); lengths[i] = the file's
  * own length, status[i] its code; returns the first non-zero status. */

@@ -2,6 +2,7 @@
 specification (RFC 9639 appendix D.1 and D.3 -- streams produced by the reference libFLAC encoder, each carrying the
 MD5 of its audio, which the decoder verifies) and (b) streams from tests/flac_writer.py that exercise every subframe
 type, predictor order, Rice layout, channel decorrelation and header code; the WAV reader against scipy."""
+import os
 import struct
 
 import numpy as np
@@ -12,6 +13,7 @@ import torch
 import flac_writer as fw
 from asvspoof2021_air_b200 import audio_io
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 RFC_D1 = ("664c614380000022100010000000 0f00000f0ac442f0000000013e84b41807dc690307586a3dad1a2e0f"
           "fff869180000bf0358fd03128baa9a")
 RFC_D3 = ("664c6143800000221000100000001f00001f07d0007000000018f8f9e396f5cbcfc6dc807f9977906b32"
@@ -211,3 +213,31 @@ def test_batch_decode_into_padded_rows_on_threads(tmp_path):
     scipy.io.wavfile.write(p8, 8000, np.zeros(100, np.int16))
     with pytest.raises(audio_io.AudioError, match="8000 Hz"):
         audio_io.decode_batch([paths[0], p8], 2048)
+
+
+def test_mutated_streams_never_crash_the_decoder(tmp_path):
+    """400 damaged variants of valid streams: every one returns a status (scripts/fuzz_audio.py runs the same
+    campaign, larger, under AddressSanitizer + UBSan)."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, os, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r); sys.path.insert(0, %r)
+import fuzz_audio as fz
+from asvspoof2021_air_b200 import audio_io
+rng = np.random.RandomState(3)
+ok = bad = 0
+for si, s in enumerate(fz.seeds(rng)):
+    for t in range(80):
+        p = os.path.join(%r, "m.bin")
+        open(p, "wb").write(fz.mutate(s, t, rng))
+        try:
+            audio_io.decode(p, verify=True); ok += 1
+        except audio_io.AudioError:
+            bad += 1
+print("done", ok, bad)
+''' % (os.path.join(ROOT, "scripts"), os.path.join(ROOT, "tests"), ROOT, str(tmp_path))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.startswith("done"), r.stdout[-500:] + r.stderr[-2000:]
+    ok, bad = (int(v) for v in r.stdout.split()[1:3])
+    assert ok + bad == 400 and bad > 200
