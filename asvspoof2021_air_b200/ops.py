@@ -577,3 +577,23 @@ def det_threshold_counts(scores, threshold, counts):
 
 
 det_curve = _timed(det_curve, "det_curve")
+
+
+# ------------------------------------------------------------------------------------------
+# adversarial channel-classifier head (csrc/adv.cu)
+# ------------------------------------------------------------------------------------------
+def dropout_relu_fwd(x, keep, y, p, generate, seed=0):
+    _lib.check(_lib.lib().air_dropout_relu_fwd(_lib.ptr(x), _lib.ptr(keep), _lib.ptr(y), _lib.LL(x.numel()), _lib.F(p),
+                                               int(bool(generate)), ctypes.c_ulonglong(int(seed)), _lib.stream_ptr()),
+               "air_dropout_relu_fwd")
+
+
+def dropout_relu_bwd(dy, x, keep, dx, p):
+    _lib.check(_lib.lib().air_dropout_relu_bwd(_lib.ptr(dy), _lib.ptr(x), _lib.ptr(keep), _lib.ptr(dx), _lib.LL(x.numel()),
+                                               _lib.F(p), _lib.stream_ptr()), "air_dropout_relu_bwd")
+
+
+def relu_ce_fwd_bwd(z, labels, B, C, grad_scale, loss_sum, correct, dz):
+    _lib.check(_lib.lib().air_relu_ce_fwd_bwd(_lib.ptr(z), _lib.ptr(labels), int(B), int(C), _lib.F(grad_scale),
+                                              _lib.ptr(loss_sum), _lib.ptr(correct), _lib.ptr(dz), _lib.stream_ptr()),
+               "air_relu_ce_fwd_bwd")

@@ -50,6 +50,7 @@ class Trainer:
         self.dfeat = None
         self.score = None
         self.launches = 0
+        self.adv, self.lr_d, self.adv_stats = [], 1e-4, []              # --ADV_AUG heads (attach_adversaries)
         self.reducer = None
         if self.world > 1:
             st = self.engine.store
@@ -77,8 +78,21 @@ class Trainer:
                               layout=self.layout, dtype=BF16, out=self.x0)
         return self.x0[:, 0] if self.layout == "resnet" else self.x0
 
-    def train_step(self, waves, labels, lengths=None, start=None, lr=None):
-        """One optimiser step on a (B, L) fp32 wave batch; returns the device loss tensor (no sync)."""
+    def attach_adversaries(self, class_counts, lambda_=0.05, lr_d=1e-4, seed=None):
+        """The channel classifier(s) of --ADV_AUG (main_train.py:211-224): one head per entry of `class_counts`
+        (LA_aug / DF_aug: [n_codecs]; LAPA / DFPA: [n_codecs, n_devices]), Adam(lr_d, L2 5e-4) each."""
+        from .adv import ChannelClassifier
+        if seed is not None:
+            torch.manual_seed(seed)
+        self.adv = [ChannelClassifier(self.center.shape[1], c, lambda_, device=self.device) for c in class_counts]
+        self.lr_d = lr_d
+        return self.adv
+
+    def train_step(self, waves, labels, lengths=None, start=None, lr=None, channels=None, step_seed=0):
+        """One optimiser step on a (B, L) fp32 wave batch; returns the device loss tensor (no sync).
+        channels: (B,) or (B, n_heads) int labels -- when given and adversaries are attached, the step follows
+        main_train.py:377-453: the gradient-reversed channel loss joins the feature loss, then the encoder runs a
+        second time and each classifier takes its own Adam step on the detached features."""
         eng = self.engine
         B = waves.shape[0]
         x0 = self.features(waves, lengths, start)
@@ -90,6 +104,11 @@ class Trainer:
         self.center_grad.zero_()
         ops.ocsoftmax(feat, labels, self.center, B, feat.shape[1], self.r_real, self.r_fake, self.alpha,
                       self.weight_loss, self.loss, self.score, self.dfeat, self.center_grad, logits, logits.shape[1], self.ce)
+        adv_on = channels is not None and len(self.adv) > 0
+        if adv_on:
+            ch = channels.view(B, -1)
+            self.adv_stats = [clf.head_loss_and_feat_grad(feat, ch[:, i], self.dfeat, seed=2 * step_seed * len(self.adv) + i)
+                              for i, clf in enumerate(self.adv)]
         if self.reducer is not None:
             self.reducer.begin()
         eng.backward(self.dfeat)
@@ -97,6 +116,11 @@ class Trainer:
         lr = self.lr if lr is None else lr
         eng.store.adam_step(lr, self.betas[0], self.betas[1], self.eps, self.wd, grad_scale=scale)
         ops.sgd_step(self.center, self.center_grad, self.center.numel(), lr, scale)
+        if adv_on:                                                       # main_train.py:420-453
+            feat2, _ = eng.forward(x0, training=True)
+            for i, clf in enumerate(self.adv):
+                clf.classifier_step(feat2, ch[:, i], self.lr_d, self.betas[0], self.betas[1], self.eps, 0.0005,
+                                    seed=(2 * step_seed + 1) * len(self.adv) + i, group=self.pg)
         return self.loss
 
     @torch.no_grad()

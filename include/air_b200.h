@@ -384,6 +384,22 @@ int air_audio_decode_i32(const char* path, int* out, long long capacity, long lo
 int air_audio_decode_batch_f32(const char* const* paths, int n, float* out, long long ld, int* lengths,
                                int* sample_rates, int* status, int threads, int flags);
 
+
+/* ---------------------------------------------------------------------------------------------
+ * Adversarial channel-classifier head (csrc/adv.cu): the stages between / after the two nn.Linear of
+ * ChannelClassifier (model.py:1002-1023) and its CrossEntropyLoss (main_train.py:251,377-403,420-453).
+ *   air_dropout_relu_fwd : y = relu(x * keep / (1 - p)); keep (bytes) is read, or drawn and written when generate != 0
+ *   air_dropout_relu_bwd : dx = dy * [x * keep > 0] * keep / (1 - p)
+ *   air_relu_ce_fwd_bwd  : logits = relu(z) (B, C); *loss_sum += mean CE; *correct += #(argmax == label) (first maximum);
+ *                          dz = grad_scale * dCE/dz (optional).  loss_sum / correct accumulate: zero them first.
+ * Not yet validated on hardware (round 1 ended without GPU time for tests/test_adv_gpu.py). */
+int air_dropout_relu_fwd(const float* x, unsigned char* keep, float* y, long long n, float p, int generate,
+                         unsigned long long seed, air_stream_t stream);
+int air_dropout_relu_bwd(const float* dy, const float* x, const unsigned char* keep, float* dx, long long n,
+                         float p, air_stream_t stream);
+int air_relu_ce_fwd_bwd(const float* z, const long long* labels, int B, int C, float grad_scale,
+                        double* loss_sum, int* correct, float* dz, air_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -229,11 +229,54 @@ def golden_det():
     print("det_golden.npz", len(out), "arrays,", os.path.getsize(os.path.join(GOLD, "det_golden.npz")), "bytes")
 
 
+def golden_adv(batch=16, enc=256, classes=(60, 13), lambda_=0.05, seed=11):
+    """The reference ChannelClassifier (model.py:1002-1023) + CrossEntropyLoss with a FIXED dropout keep-mask injected
+    into torch.nn.functional.dropout, for the two head sizes of the LAPA / DFPA branch (60 codecs, 13 devices)."""
+    md = ref_shim.load("model")
+    import torch.nn.functional as F
+    out = {"lambda": np.array(lambda_)}
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(batch, enc, generator=g)
+    out["x"] = x.numpy()
+    real_dropout = F.dropout
+    for C in classes:
+        torch.manual_seed(seed + C)
+        clf = md.ChannelClassifier(enc, C, lambda_)
+        clf.train()
+        labels = torch.randint(0, C, (batch,), generator=g)
+        keep = (torch.rand(batch, enc // 2, generator=g) >= 0.3).float()
+        F.dropout = lambda inp, p=0.5, training=True, inplace=False: inp * keep / (1.0 - p)
+        try:
+            xr = x.clone().requires_grad_(True)
+            logits = clf(xr)
+            loss = torch.nn.CrossEntropyLoss()(logits, labels)
+            loss.backward()
+        finally:
+            F.dropout = real_dropout
+        sd = clf.state_dict()
+        pre = "c%d_" % C
+        out[pre + "labels"], out[pre + "keep"] = labels.numpy(), keep.numpy()
+        for k, name in (("classifier.0.weight", "w1"), ("classifier.0.bias", "b1"), ("classifier.3.weight", "w2"), ("classifier.3.bias", "b2")):
+            out[pre + name] = sd[k].numpy()
+        out[pre + "logits"], out[pre + "loss"] = logits.detach().numpy(), np.array(float(loss))
+        out[pre + "pred"] = torch.max(logits.data, 1)[1].numpy()
+        out[pre + "dfeat"] = xr.grad.numpy()
+        ps = dict(clf.named_parameters())
+        for k, name in (("classifier.0.weight", "dw1"), ("classifier.0.bias", "db1"), ("classifier.3.weight", "dw2"), ("classifier.3.bias", "db2")):
+            out[pre + name] = ps[k].grad.numpy()
+    np.savez_compressed(os.path.join(GOLD, "adv_golden.npz"), **out)
+    print("adv_golden.npz", os.path.getsize(os.path.join(GOLD, "adv_golden.npz")), "bytes")
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
-    if "--det-only" not in sys.argv:
+    only = [a[2:-5] for a in sys.argv[1:] if a.startswith("--") and a.endswith("-only")]
+    if not only:
         golden_lfcc()
         golden_padcrop()
         golden_nets()
-    golden_det()
+    if not only or "det" in only:
+        golden_det()
+    if not only or "adv" in only:
+        golden_adv()

@@ -350,3 +350,79 @@ torch.save({"resnet": rn.ResNet(3, 256, "18", nclasses=2).state_dict()}, %r)
     assert len(e.state_dict()) == 248 and e.C == 512 and e.scale == 8
     l = compat.load_module(str(tmp_path / "l.pt"))
     assert (l.r_real, l.r_fake, l.alpha) == (0.9, 0.2, 20.0) and l.center.shape == (1, 256)
+
+
+def test_adv_head_orchestration_with_emulated_kernels(monkeypatch, golden_dir):
+    """The call sequence of adv.ChannelClassifier (argument order, shapes, accumulate semantics of the C entry points it
+    strings together) checked on the CPU: every `ops.*` it uses is replaced by a torch emulation of that entry point's
+    documented contract (include/air_b200.h), the result compared with the reference golden.  The CUDA kernels
+    themselves are covered by tests/test_adv_gpu.py."""
+    from asvspoof2021_air_b200 import adv
+
+    class FakeOps:
+        @staticmethod
+        def linear_fwd(x, W, bias, y, M, N, K):
+            y.copy_(x[:M, :K] @ W.t() + bias)
+
+        @staticmethod
+        def linear_bwd(x, W, dy, dx, dW, db, M, N, K):
+            if dx is not None:
+                dx.copy_(dy @ W)
+            if dW is not None:
+                dW.add_(dy.t() @ x)
+                if db is not None:
+                    db.add_(dy.sum(0))
+
+        @staticmethod
+        def dropout_relu_fwd(x, keep, y, p, generate, seed=0):
+            assert not generate
+            y.copy_(torch.relu(x * keep.float() / (1.0 - p)))
+
+        @staticmethod
+        def dropout_relu_bwd(dy, x, keep, dx, p):
+            dx.copy_(dy * ((keep > 0) & (x > 0)).float() / (1.0 - p))
+
+        @staticmethod
+        def relu_ce_fwd_bwd(z, labels, B, C, grad_scale, loss_sum, correct, dz):
+            logits = torch.relu(z.double())
+            sm = torch.softmax(logits, 1)
+            loss_sum.add_(-torch.log(sm[torch.arange(B), labels]).mean())
+            correct.add_((logits.argmax(1) == labels).sum().int())
+            if dz is not None:
+                d = sm.clone()
+                d[torch.arange(B), labels] -= 1
+                dz.copy_((grad_scale * d / B * (z > 0)).float())
+
+        @staticmethod
+        def sgd_step(p, g, n, lr, grad_scale=1.0):
+            p.sub_(lr * grad_scale * g)
+
+        @staticmethod
+        def adam_l2_step(p, g, m, v, n, lr, b1, b2, eps, wd, step, grad_scale=1.0):
+            gg = g * grad_scale + wd * p
+            m.mul_(b1).add_((1 - b1) * gg)
+            v.mul_(b2).add_((1 - b2) * gg * gg)
+            p.sub_(lr * (m / (1 - b1 ** step)) / ((v / (1 - b2 ** step)).sqrt() + eps))
+
+    monkeypatch.setattr(adv, "ops", FakeOps)
+    monkeypatch.setattr(adv, "_require_cuda", lambda t: None)
+    g = np.load(os.path.join(golden_dir, "adv_golden.npz"))
+    x = torch.from_numpy(g["x"])
+    for C in (60, 13):
+        p = "c%d_" % C
+        clf = adv.ChannelClassifier(256, C, float(g["lambda"]), device="cpu")
+        clf.load_state_dict({"classifier.0.weight": torch.from_numpy(g[p + "w1"]), "classifier.0.bias": torch.from_numpy(g[p + "b1"]),
+                             "classifier.3.weight": torch.from_numpy(g[p + "w2"]), "classifier.3.bias": torch.from_numpy(g[p + "b2"])})
+        labels, keep = torch.from_numpy(g[p + "labels"]), torch.from_numpy(g[p + "keep"])
+        dfeat = torch.zeros(16, 256)
+        loss, correct = clf.head_loss_and_feat_grad(x, labels, dfeat, keep_mask=keep)
+        assert abs(float(loss) - float(g[p + "loss"])) < 1e-5 and int(correct) == int((g[p + "pred"] == g[p + "labels"]).sum())
+        assert np.abs(dfeat.numpy() - g[p + "dfeat"]).max() <= 1e-7 + 1e-4 * np.abs(g[p + "dfeat"]).max()
+        before = clf.flat.clone()
+        clf.classifier_step(x, labels, lr=1e-4, keep_mask=keep)
+        for k, name in (("classifier.0.weight", "dw1"), ("classifier.0.bias", "db1"), ("classifier.3.weight", "dw2"), ("classifier.3.bias", "db2")):
+            ref = g[p + name]
+            assert np.abs(clf._gviews[k].numpy() - ref).max() <= 1e-7 + 1e-4 * np.abs(ref).max(), k
+        step = (clf.flat - before).abs()
+        assert 0.5e-4 < float(step.max()) <= 1.0001e-4                  # first Adam step: |delta| ~ lr
+        assert clf.step_count == 1 and clf(x).shape == (16, C) and float(clf(x).min()) >= 0.0

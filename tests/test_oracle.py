@@ -257,3 +257,19 @@ def test_det_oracle_vs_reference_on_fresh_random_scores():
         a, b, c = mo.det_curve(tar, non)
         assert dc.same(a, frr) and dc.same(b, far) and dc.same(c, thr)
         assert dc.same(mo.eer(tar, non)[:2], rem.compute_eer(tar, non))
+
+
+def test_adv_classifier_oracle_vs_reference_golden(golden_dir):
+    """ChannelClassifier + gradient reversal + CE (model.py:976-1023, main_train.py:377-403) for a fixed dropout mask."""
+    from oracle import adv_oracle as ao
+    g = np.load(os.path.join(golden_dir, "adv_golden.npz"))
+    for C in (60, 13):
+        p = "c%d_" % C
+        r = ao.forward_backward(g["x"], g[p + "labels"], g[p + "w1"], g[p + "b1"], g[p + "w2"], g[p + "b2"], g[p + "keep"],
+                                float(g["lambda"]))
+        assert abs(r["loss"] - float(g[p + "loss"])) < 1e-5 and np.array_equal(r["pred"], g[p + "pred"])
+        assert np.abs(r["logits"] - g[p + "logits"]).max() < 1e-5
+        for k in ("dfeat", "dw1", "db1", "dw2", "db2"):
+            ref = g[p + k]
+            assert np.abs(r[k] - ref).max() <= 1e-6 + 1e-4 * np.abs(ref).max(), (C, k)
+        assert np.abs(g[p + "dfeat"]).max() > 0        # the reversed gradient really reaches the features
