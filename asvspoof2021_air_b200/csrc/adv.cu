@@ -80,7 +80,8 @@ __global__ void relu_ce_kernel(const float* __restrict__ z, const long long* __r
     }
   }
   if (lane == 0) {
-    const float ll = fmaxf(zr[lab], 0.f) - mx - logf(se);
+    // a label outside [0, C) is the caller's error (torch raises): no out-of-bounds read, the loss turns NaN
+    const float ll = (lab >= 0 && lab < C) ? fmaxf(zr[lab], 0.f) - mx - logf(se) : NAN;
     if (loss_sum) atomicAdd(loss_sum, -(double)ll * (double)invB);
     if (correct && arg == lab) atomicAdd(correct, 1);
   }
