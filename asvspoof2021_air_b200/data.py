@@ -54,6 +54,7 @@ class SyntheticWaves:
 
 class WaveFolder:
     EXTS = (".flac", ".wav", ".npy")
+    PIN = None                       # None: pin batch buffers when a CUDA device is present
 
     def __init__(self, folder, protocol, feat_len=750, seed=0, threads=0, verify=False):
         self.folder, self.feat_len, self.threads, self.verify = folder, feat_len, threads, verify
@@ -90,7 +91,8 @@ class WaveFolder:
     def batch(self, indices, pinned=None):
         utts = [self.items[i][0] for i in indices]
         lens = np.array([self.frames(u) for u in utts], dtype=np.int32)
-        pinned = torch.cuda.is_available() if pinned is None else pinned
+        if pinned is None:
+            pinned = torch.cuda.is_available() if self.PIN is None else self.PIN
         waves = torch.zeros(len(utts), int(lens.max()), pin_memory=pinned)
         coded = [j for j, u in enumerate(utts) if not self.paths[u].endswith(".npy")]
         if coded:                                                       # one native call, host threads, GIL released
@@ -110,10 +112,78 @@ class WaveFolder:
         return waves, torch.from_numpy(lens), labels, utts, start
 
 
+def channel_tables(kind):
+    """(channel names, device names or None) of an augmented set -- `kind` in LA / DF / LAPA / DFPA; the list position is
+    the class index (dataset.py:122-138,207-228,345-346,407-413; stored in channel_tables.json)."""
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "channel_tables.json")) as f:
+        t = json.load(f)[kind]
+    return t["channel"], t.get("devices")
+
+
+class AugWaveFolder(WaveFolder):
+    """Original + channel-augmented waves of the --ADV_AUG branch (raw_dataset.py:149-300, dataset.py:105-183,190-277).
+
+    `folder` holds the original utterances `<utt>.{flac,wav,npy}` named by the protocol; `aug_folder` holds augmented
+    copies `<utt>_<channel>.<ext>` (LA / DF) or `<utt>_<channel>_<device>.<ext>` (LAPA / DFPA).  Items 0 .. n_ori-1 are
+    the originals (channel `no_channel`, device ``""``), the rest the augmented files in sorted order -- the index
+    layout main_train.py:226-231 samples its two half-batches from.  batch() returns a sixth element: the int64 class
+    indices, (B,) or (B, 2) = [channel, device]."""
+
+    def __init__(self, folder, aug_folder, protocol, kind, feat_len=750, seed=0, threads=0, verify=False):
+        super().__init__(folder, protocol, feat_len, seed, threads, verify)
+        self.kind = kind
+        self.channel_names, self.device_names = channel_tables(kind)
+        cidx = {n: i for i, n in enumerate(self.channel_names)}
+        didx = {n: i for i, n in enumerate(self.device_names)} if self.device_names else None
+        label_of = dict(self.items)
+        self.n_ori = len(self.items)
+        self.classes = [(cidx["no_channel"], didx[""]) if didx else (cidx["no_channel"],) for _ in self.items]
+        for fn in sorted(os.listdir(aug_folder)):
+            stem, ext = os.path.splitext(fn)
+            if ext not in self.EXTS:
+                continue
+            parts = stem.split("_")
+            ntail = 2 if didx else 1
+            utt, tail = "_".join(parts[:-ntail]), parts[-ntail:]
+            if utt not in label_of:
+                raise KeyError("%s: %s is not in the protocol" % (aug_folder, utt))
+            if tail[0] not in cidx or (didx and tail[1] not in didx):
+                raise KeyError("%s: unknown channel / device in %s" % (aug_folder, fn))
+            name = stem
+            self.items.append((name, label_of[utt]))
+            self.paths[name] = os.path.join(aug_folder, fn)
+            self.classes.append((cidx[tail[0]], didx[tail[1]]) if didx else (cidx[tail[0]],))
+
+    def batch(self, indices, pinned=None):
+        out = super().batch(indices, pinned)
+        ch = torch.tensor([self.classes[i] for i in indices], dtype=torch.long)
+        return out + (ch[:, 0] if ch.shape[1] == 1 else ch,)
+
+
+def half_batches(n_ori, n_total, batch_size, ratio, steps, rng):
+    """Index lists of main_train.py:226-233,309-325: every step int(batch_size * ratio) originals and the rest augmented
+    utterances, each drawn without replacement from its own reshuffled-when-exhausted permutation."""
+    k_ori = int(batch_size * ratio)
+    k_aug = batch_size - k_ori
+    pools = [list(rng.permutation(n_ori)), list(n_ori + rng.permutation(n_total - n_ori))]
+
+    def take(which, k):
+        out = []
+        while len(out) < k:
+            if not pools[which]:
+                pools[which] = list(rng.permutation(n_ori)) if which == 0 else list(n_ori + rng.permutation(n_total - n_ori))
+            out.append(int(pools[which].pop()))
+        return out
+    return [take(0, k_ori) + (take(1, k_aug) if n_total > n_ori else []) for _ in range(steps)]
+
+
 class Batch(tuple):
-    """(waves, lengths, labels, names, start) plus `.labels_host`; `lengths` is None when no row is shorter than the
-    batch matrix (nothing for the kernels to mask)."""
+    """(waves, lengths, labels, names, start) plus `.labels_host` and `.channels` (device tensor, sources that carry
+    channel labels only); `lengths` is None when no row is shorter than the batch matrix (nothing for the kernels to
+    mask)."""
     labels_host = None
+    channels = None
 
 
 class Prefetcher:
@@ -123,6 +193,8 @@ class Prefetcher:
     re-raised in the consumer."""
 
     def __init__(self, source, index_batches, depth=2, device=None):
+        if device is not None and torch.device(device).type != "cuda":
+            device = None                                               # host consumer: no copy stream
         self.source, self.batches, self.device = source, list(index_batches), device
         self.q = queue.Queue(maxsize=max(1, depth))
         self.copy_stream = torch.cuda.Stream(device) if device is not None else None
@@ -132,10 +204,12 @@ class Prefetcher:
     def _work(self):
         try:
             for idx in self.batches:
-                waves, lens, labels, names, start = self.source.batch(idx)
+                item = self.source.batch(idx)
+                waves, lens, labels, names, start = item[:5]
+                channels = item[5] if len(item) > 5 else None
                 if int(lens.min()) == waves.shape[1]:
                     lens = None
-                host = (waves, lens, labels, start)
+                host = (waves, lens, labels, start, channels)
                 ev = None
                 if self.device is not None:
                     with torch.cuda.stream(self.copy_stream):
@@ -145,7 +219,7 @@ class Prefetcher:
                 else:
                     moved = list(host)
                 b = Batch((moved[0], moved[1], moved[2], names, moved[3]))
-                b.labels_host = labels
+                b.labels_host, b.channels = labels, moved[4]
                 self.q.put((b, ev, host))                              # `host` keeps the pinned source alive
             self.q.put(None)
         except BaseException as e:                                      # surfaced by __iter__
@@ -165,7 +239,7 @@ class Prefetcher:
             if ev is not None:
                 cur = torch.cuda.current_stream(self.device)
                 cur.wait_event(ev)
-                for t in (b[0], b[1], b[2], b[4]):
+                for t in (b[0], b[1], b[2], b[4], b.channels):
                     if t is not None:
                         t.record_stream(cur)
             yield b

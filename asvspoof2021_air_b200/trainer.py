@@ -50,7 +50,7 @@ class Trainer:
         self.dfeat = None
         self.score = None
         self.launches = 0
-        self.adv, self.lr_d, self.adv_stats = [], 1e-4, []              # --ADV_AUG heads (attach_adversaries)
+        self.adv, self.lr_d, self.adv_stats, self.adv_stats_c = [], 1e-4, [], []              # --ADV_AUG heads (attach_adversaries)
         self.reducer = None
         if self.world > 1:
             st = self.engine.store
@@ -118,9 +118,9 @@ class Trainer:
         ops.sgd_step(self.center, self.center_grad, self.center.numel(), lr, scale)
         if adv_on:                                                       # main_train.py:420-453
             feat2, _ = eng.forward(x0, training=True)
-            for i, clf in enumerate(self.adv):
-                clf.classifier_step(feat2, ch[:, i], self.lr_d, self.betas[0], self.betas[1], self.eps, 0.0005,
-                                    seed=(2 * step_seed + 1) * len(self.adv) + i, group=self.pg)
+            self.adv_stats_c = [clf.classifier_step(feat2, ch[:, i], self.lr_d, self.betas[0], self.betas[1], self.eps, 0.0005,
+                                                    seed=(2 * step_seed + 1) * len(self.adv) + i, group=self.pg)
+                                for i, clf in enumerate(self.adv)]
         return self.loss
 
     @torch.no_grad()

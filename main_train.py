@@ -82,6 +82,8 @@ def build_parser():
     new.add_argument("--dev_synthetic", type=int, default=0, help="validate on N synthetic utterances")
     new.add_argument("--wave_dir", type=str, default=None, help="folder of .wav / .npy training waves")
     new.add_argument("--protocol", type=str, default=None, help="protocol file for --wave_dir")
+    new.add_argument("--aug_wave_dir", type=str, default=None,
+                     help="--ADV_AUG: folder of <utt>_<channel>[_<device>] augmented copies (raw_dataset.py:149-300)")
     new.add_argument("--dev_wave_dir", type=str, default=None)
     new.add_argument("--dev_protocol", type=str, default=None)
     new.add_argument("--steps_per_epoch", type=int, default=0, help="0: one pass over the source")
@@ -120,10 +122,22 @@ def _reject_out_of_scope(args):
         raise SystemExit("--model %s is outside the B200 hot path (resnet / ecapa only, SURVEY.md section 2.1)" % args.model)
     if args.add_loss != "ang_iso":
         raise SystemExit("only --add_loss ang_iso (OC-Softmax) is implemented on the fused path")
-    if args.ADV_AUG or args.visualize:
-        raise SystemExit("--ADV_AUG / --visualize are outside the B200 hot path")
+    if args.visualize:
+        raise SystemExit("--visualize is outside the B200 hot path")
+    if args.ADV_AUG:
+        if sum(bool(x) for x in (args.LA_aug, args.DF_aug, args.LAPA_aug, args.DFPA_aug)) != 1:
+            raise SystemExit("--ADV_AUG needs exactly one of --LA_aug / --DF_aug / --LAPA_aug / --DFPA_aug (main_train.py:212)")
+        if not (args.wave_dir and args.aug_wave_dir and args.protocol):
+            raise SystemExit("--ADV_AUG trains from raw waves: pass --wave_dir (originals), --aug_wave_dir and --protocol")
+        if os.environ.get("AIR_ADV_UNVALIDATED") != "1":
+            raise SystemExit("--ADV_AUG: the channel-classifier head is built (asvspoof2021_air_b200/adv.py) but its GPU "
+                             "parity test has not run on hardware yet; set AIR_ADV_UNVALIDATED=1 to use it anyway")
     if args.feat != "LFCC":
         raise SystemExit("only --feat LFCC is implemented (computed on device from raw waves)")
+
+
+def _device():
+    return torch.device("cuda", torch.cuda.current_device())
 
 
 def dev_eer(score_chunks, label_chunks, world):
@@ -132,7 +146,7 @@ def dev_eer(score_chunks, label_chunks, world):
     data parallelism every rank contributes its shard of the dev set (one padded all-gather)."""
     from asvspoof2021_air_b200 import eval_metrics as em
     if not score_chunks:
-        scores, labels = torch.empty(0, device="cuda"), torch.empty(0, dtype=torch.long, device="cuda")
+        scores, labels = torch.empty(0, device=_device()), torch.empty(0, dtype=torch.long, device=_device())
     else:
         scores, labels = torch.cat(score_chunks).float(), torch.cat(label_chunks).long()
     if world > 1:
@@ -148,6 +162,9 @@ def _source(args, dev=False):
     from asvspoof2021_air_b200 import data
     n = args.dev_synthetic if dev else args.synthetic
     folder = args.dev_wave_dir if dev else args.wave_dir
+    if folder and args.ADV_AUG and not dev:
+        kind = "LA" if args.LA_aug else "DF" if args.DF_aug else "LAPA" if args.LAPA_aug else "DFPA"
+        return data.AugWaveFolder(folder, args.aug_wave_dir, args.protocol, kind, args.feat_len, args.seed)
     if folder:
         return data.WaveFolder(folder, args.dev_protocol if dev else args.protocol, args.feat_len, args.seed + (1 if dev else 0))
     if n > 0:
@@ -168,7 +185,7 @@ def train(args):
     pg = torch.distributed.group.WORLD if world > 1 else None
     tr = Trainer(arch=args.model, enc_dim=args.enc_dim, feat_len=args.feat_len, padding=args.padding, lr=args.lr,
                  beta_1=args.beta_1, beta_2=args.beta_2, eps=args.eps, weight_decay=0.0005, r_real=args.r_real,
-                 r_fake=args.r_fake, alpha=args.alpha, weight_loss=args.weight_loss, device="cuda", process_group=pg,
+                 r_fake=args.r_fake, alpha=args.alpha, weight_loss=args.weight_loss, device=_device(), process_group=pg,
                  seed=args.seed)
     if args.continue_training:                                            # main_train.py:172-173
         from asvspoof2021_air_b200 import compat
@@ -176,27 +193,53 @@ def train(args):
         lp = os.path.join(args.out_fold, "anti-spoofing_loss_model.pt")
         tr.load_modules(model, compat.load_module(lp) if os.path.exists(lp) else None)
     from asvspoof2021_air_b200 import data
-    device = torch.device("cuda", torch.cuda.current_device())
+    device = _device()
     src, dev_src = _source(args), _source(args, dev=True)
     per_rank = args.batch_size
     order_rng = np.random.RandomState(args.seed)
     steps = args.steps_per_epoch or max(1, len(src) // (per_rank * world))
+    adv = bool(args.ADV_AUG)
+    if adv:                                                               # main_train.py:211-224
+        heads = [len(src.channel_names)] + ([len(src.device_names)] if src.device_names else [])
+        tr.attach_adversaries(heads, lambda_=args.lambda_, lr_d=args.lr_d, seed=args.seed)
+        steps = args.steps_per_epoch or max(1, src.n_ori // max(1, int(per_rank * args.ratio) * world))
+        aug_rng = np.random.RandomState(args.seed + 1000 * rank)
     prev_loss, early_stop_cnt = 1e8, 0
     feat_model = loss_model = None
     for epoch in range(args.num_epochs):
         lr = adjust_learning_rate(args, args.lr, epoch)
-        perm = order_rng.permutation(len(src))                            # SubsetRandomSampler, main_train.py:226-242
         pending = []
-        order = [[perm[((step * world + rank) * per_rank + j) % len(src)] for j in range(per_rank)] for step in range(steps)]
+        if adv:                                                           # two half-batches per step, main_train.py:226-233,309-325
+            tr.lr_d = adjust_learning_rate(args, args.lr_d, epoch)
+            order = data.half_batches(src.n_ori, len(src), per_rank, args.ratio, steps, aug_rng)
+            seen_m = seen_c = 0
+            right_m = torch.zeros(1, dtype=torch.int64, device=device)
+            right_c = torch.zeros(1, dtype=torch.int64, device=device)
+        else:
+            perm = order_rng.permutation(len(src))                        # SubsetRandomSampler, main_train.py:226-242
+            order = [[perm[((step * world + rank) * per_rank + j) % len(src)] for j in range(per_rank)] for step in range(steps)]
         # decode / collate / H2D of the next batches run on a host thread + copy stream while this step computes
-        for step, (waves, lengths, labels, _, start) in enumerate(data.Prefetcher(src, order, depth=2, device=device)):
-            loss = tr.train_step(waves, labels, lengths=lengths, start=start, lr=lr)
-            pending.append((step, loss.clone()))
+        for step, batch in enumerate(data.Prefetcher(src, order, depth=2, device=device)):
+            waves, lengths, labels, _, start = batch
+            adv_now = adv and epoch > 0                                   # main_train.py:377: the adversaries join after epoch 0
+            loss = tr.train_step(waves, labels, lengths=lengths, start=start, lr=lr,
+                                 channels=batch.channels if adv_now else None, step_seed=epoch * steps + step)
+            rec = [step, loss.clone()]
+            if adv_now:                                                   # main_train.py:471-477
+                right_m += tr.adv_stats[0][1]
+                right_c += tr.adv_stats_c[0][1]
+                seen_m, seen_c = seen_m + waves.shape[0], seen_c + waves.shape[0]
+                rec += [sum(s[0] for s in tr.adv_stats).clone(), right_m.clone(), seen_m, right_c.clone(), seen_c]
+            pending.append(rec)
             if len(pending) >= args.log_every or step == steps - 1:
-                if rank == 0:                                             # main_train.py:479-481, batched host reads
+                if rank == 0:                                             # main_train.py:471-481, batched host reads
                     with open(os.path.join(args.out_fold, "train_loss.log"), "a") as log:
-                        for s, l in pending:
-                            log.write("%d\t%d\t%s\n" % (epoch, s, float(l)))
+                        for r in pending:
+                            if len(r) == 2:
+                                log.write("%d\t%d\t%s\n" % (epoch, r[0], float(r[1])))
+                            else:
+                                log.write("%d\t%d\t%s\t%s\t%s\t%s\n" % (epoch, r[0], float(r[2]), 100.0 * int(r[3]) / r[4],
+                                                                         100.0 * int(r[5]) / r[6], float(r[1])))
                 pending = []
         val = float("nan")
         if dev_src is not None:
@@ -208,7 +251,7 @@ def train(args):
                 tot, cnt = tot + float(l) * len(names), cnt + len(names)
                 dev_scores.append(sc.clone())
                 dev_labels.append(labels)
-            t = torch.tensor([tot, cnt], device="cuda", dtype=torch.float64)
+            t = torch.tensor([tot, cnt], device=device, dtype=torch.float64)
             if world > 1:
                 torch.distributed.all_reduce(t)
             val = float(t[0] / t[1].clamp(min=1))

@@ -426,3 +426,149 @@ def test_adv_head_orchestration_with_emulated_kernels(monkeypatch, golden_dir):
         step = (clf.flat - before).abs()
         assert 0.5e-4 < float(step.max()) <= 1.0001e-4                  # first Adam step: |delta| ~ lr
         assert clf.step_count == 1 and clf(x).shape == (16, C) and float(clf(x).min()) >= 0.0
+
+
+def test_augmented_folder_channel_labels_and_half_batches(tmp_path):
+    """--ADV_AUG data side: originals + `<utt>_<channel>[_<device>]` copies, class indices in the reference's order."""
+    import wave
+    from asvspoof2021_air_b200 import data
+    ch, dev = data.channel_tables("LAPA")
+    assert len(ch) == 60 and ch[0] == "no_channel" and len(dev) == 13 and dev[-1] == "" and data.channel_tables("DF")[1] is None
+    assert data.channel_tables("DF")[0] == ['no_channel', 'aac[16k]', 'aac[32k]', 'aac[8k]', 'mp3[16k]', 'mp3[32k]', 'mp3[8k]']
+    ori, aug = tmp_path / "ori", tmp_path / "aug"
+    ori.mkdir(); aug.mkdir()
+
+    def wav(path, n, v):
+        with wave.open(str(path), "wb") as f:
+            f.setnchannels(1); f.setsampwidth(2); f.setframerate(16000)
+            f.writeframes((np.full(n, v, np.int16)).tobytes())
+    proto = []
+    for i in range(4):
+        wav(ori / ("LA_T_%d.wav" % i), 1000 + i, i)
+        proto.append("LA_0001 LA_T_%d - %s %s" % (i, "-" if i % 2 == 0 else "A03", "bonafide" if i % 2 == 0 else "spoof"))
+    (tmp_path / "p.txt").write_text("\n".join(proto) + "\n")
+    wav(aug / ("LA_T_1_%s_%s.wav" % (ch[7], dev[2])), 500, 100)
+    wav(aug / ("LA_T_2_%s_%s.wav" % (ch[59], dev[0])), 700, 101)
+    wav(aug / ("LA_T_0_%s_%s.wav" % (ch[1], dev[11])), 900, 102)
+    src = data.AugWaveFolder(str(ori), str(aug), str(tmp_path / "p.txt"), "LAPA")
+    assert len(src) == 7 and src.n_ori == 4
+    w, lens, lab, names, start, chan = src.batch([0, 3, 4, 5, 6])
+    assert lens.tolist() == [1000, 1003, 900, 500, 700] and lab.tolist() == [0, 1, 0, 1, 0]
+    assert chan.tolist() == [[0, 12], [0, 12], [1, 11], [7, 2], [59, 0]]
+    assert names[2].startswith("LA_T_0_") and abs(float(w[2, 0]) - 102 / 32768) < 1e-7
+    b = next(iter(data.Prefetcher(src, [[4, 0]], device=None)))
+    assert b.channels.tolist() == [[1, 11], [0, 12]] and b.labels_host.tolist() == [0, 0]
+    with pytest.raises(KeyError):
+        wav(aug / "LA_T_3_notacodec_x.wav", 10, 0)
+        data.AugWaveFolder(str(ori), str(aug), str(tmp_path / "p.txt"), "LAPA")
+    # single-label kinds
+    aug2 = tmp_path / "aug2"
+    aug2.mkdir()
+    wav(aug2 / "LA_T_3_mp3[8k].wav", 300, 5)
+    s2 = data.AugWaveFolder(str(ori), str(aug2), str(tmp_path / "p.txt"), "DF")
+    assert s2.batch([4, 1])[5].tolist() == [6, 0]
+    # main_train.py:226-233: int(B * ratio) originals + the rest augmented per step, pools reshuffled when exhausted
+    steps = data.half_batches(4, 7, 4, 0.5, 5, np.random.RandomState(0))
+    assert all(len(s) == 4 and all(i < 4 for i in s[:2]) and all(i >= 4 for i in s[2:]) for s in steps)
+    assert sorted(i for s in steps[:2] for i in s[:2]) == [0, 1, 2, 3]          # the first pass over the originals is a permutation
+
+
+class _FakeTrainer:
+    """Stands in for trainer.Trainer in the CLI dry run: same call surface, no kernels."""
+    instances = []
+
+    def __init__(self, **kw):
+        self.kw, self.calls, self.adv, self.lr_d, self.adv_stats, self.adv_stats_c = kw, [], [], None, [], []
+        _FakeTrainer.instances.append(self)
+
+    def attach_adversaries(self, class_counts, lambda_=0.05, lr_d=1e-4, seed=None):
+        self.adv, self.lr_d, self.lambda_ = list(class_counts), lr_d, lambda_
+
+    def train_step(self, waves, labels, lengths=None, start=None, lr=None, channels=None, step_seed=0):
+        self.calls.append(dict(B=waves.shape[0], lr=lr, lr_d=self.lr_d, channels=None if channels is None else channels.clone(),
+                               ragged=lengths is not None, seed=step_seed))
+        if channels is not None:
+            n = len(self.adv)
+            self.adv_stats = [(torch.tensor([0.5 + i], dtype=torch.float64), torch.tensor([1], dtype=torch.int32)) for i in range(n)]
+            self.adv_stats_c = [(torch.tensor([0.25]), torch.tensor([2], dtype=torch.int32)) for _ in range(n)]
+        return torch.tensor([float(len(self.calls))])
+
+    def eval_loss(self, waves, labels, lengths=None, start=None):
+        return torch.tensor([2.0]), torch.arange(waves.shape[0], dtype=torch.float32)
+
+    def modules(self):
+        return torch.nn.Linear(1, 1), torch.nn.Linear(1, 1)
+
+
+def _cli_dry_run(monkeypatch, argv):
+    sys.path.insert(0, ROOT)
+    import main_train
+    from asvspoof2021_air_b200 import trainer
+    _FakeTrainer.instances = []
+    from asvspoof2021_air_b200 import parallel
+    monkeypatch.setattr(trainer, "Trainer", _FakeTrainer)
+    monkeypatch.setattr(parallel, "init_from_env", lambda backend=None: (0, 1, 0))
+    from asvspoof2021_air_b200 import data
+    monkeypatch.setattr(data.WaveFolder, "PIN", False)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(main_train, "_device", lambda: torch.device("cpu"))
+    monkeypatch.setattr(main_train, "dev_eer", lambda s, l, w: 0.125 if torch.cat(s).numel() == torch.cat(l).numel() else -1)
+    args = main_train.init_params(argv)
+    args.cuda = False
+    main_train.train(args)
+    return _FakeTrainer.instances[-1]
+
+
+def test_training_cli_loop_dry_run_default_path(monkeypatch, tmp_path):
+    """main_train.train() with the Trainer replaced by a recorder: batch order, LR schedule, log formats, checkpoints."""
+    out = tmp_path / "m"
+    tr = _cli_dry_run(monkeypatch, ["-o", str(out), "-m", "resnet", "--add_loss", "ang_iso", "--synthetic", "24", "--dev_synthetic", "10",
+                                    "--batch_size", "8", "--num_epochs", "3", "--interval", "2", "--log_every", "2", "--lr", "0.001"])
+    assert [c["B"] for c in tr.calls] == [8] * 9 and all(c["channels"] is None and not c["ragged"] for c in tr.calls)
+    assert [c["lr"] for c in tr.calls] == [0.001] * 6 + [0.0005] * 3                       # lr * 0.5 ** (epoch // 2)
+    lines = open(out / "train_loss.log").read().strip().splitlines()
+    assert lines[1:] == ["%d\t%d\t%s" % (e, s, float(3 * e + s + 1)) for e in range(3) for s in range(3)]
+    dev = open(out / "dev_loss.log").read().strip().splitlines()
+    assert dev[1:] == ["%d\t2.0\t0.125" % e for e in range(3)]
+    assert os.path.exists(out / "checkpoint" / "anti-spoofing_feat_model_3.pt") and os.path.exists(out / "anti-spoofing_loss_model.pt")
+
+
+def test_training_cli_loop_dry_run_adversarial_path(monkeypatch, tmp_path):
+    """--ADV_AUG bookkeeping (main_train.py:211-233,300-325,377,471-477): gate, heads, half-batches, adversaries from
+    epoch 1, lr_d schedule, six-column log lines."""
+    import wave
+    from asvspoof2021_air_b200 import data
+    ori, aug = tmp_path / "ori", tmp_path / "aug"
+    ori.mkdir(); aug.mkdir()
+    ch, dev = data.channel_tables("LAPA")
+
+    def wav(path):
+        with wave.open(str(path), "wb") as f:
+            f.setnchannels(1); f.setsampwidth(2); f.setframerate(16000); f.writeframes(np.zeros(400, np.int16).tobytes())
+    proto = []
+    for i in range(8):
+        wav(ori / ("LA_T_%d.wav" % i))
+        proto.append("LA_0001 LA_T_%d - - %s" % (i, "bonafide" if i % 2 == 0 else "spoof"))
+        for k in range(2):
+            wav(aug / ("LA_T_%d_%s_%s.wav" % (i, ch[1 + (3 * i + k) % 59], dev[(i + k) % 12])))
+    (tmp_path / "p.txt").write_text("\n".join(proto) + "\n")
+    argv = ["-o", str(tmp_path / "m"), "-m", "ecapa", "--add_loss", "ang_iso", "--ADV_AUG", "--LAPA_aug", "--wave_dir", str(ori),
+            "--aug_wave_dir", str(aug), "--protocol", str(tmp_path / "p.txt"), "--batch_size", "4", "--num_epochs", "2",
+            "--interval", "1", "--lr_d", "0.01", "--lambda_", "0.3", "--log_every", "1"]
+    monkeypatch.delenv("AIR_ADV_UNVALIDATED", raising=False)
+    with pytest.raises(SystemExit, match="has not run on hardware"):
+        _cli_dry_run(monkeypatch, argv)
+    with pytest.raises(SystemExit, match="exactly one of"):
+        _cli_dry_run(monkeypatch, argv + ["--DF_aug"])
+    monkeypatch.setenv("AIR_ADV_UNVALIDATED", "1")
+    tr = _cli_dry_run(monkeypatch, argv)
+    assert tr.adv == [60, 13] and tr.lambda_ == 0.3
+    assert len(tr.calls) == 8 and all(c["B"] == 4 for c in tr.calls)                       # 8 originals / int(4 * 0.5) per epoch
+    assert all(c["channels"] is None for c in tr.calls[:4])                               # epoch 0: no adversaries yet
+    for c in tr.calls[4:]:
+        assert c["channels"].shape == (4, 2) and c["channels"][:2].tolist() == [[0, 12], [0, 12]]      # originals first
+        assert (c["channels"][2:, 0] > 0).all() and (c["channels"][2:, 1] < 12).all() and c["lr_d"] == 0.005
+    lines = open(tmp_path / "m" / "train_loss.log").read().strip().splitlines()
+    assert [len(ln.split("\t")) for ln in lines[1:]] == [3] * 4 + [6] * 4
+    e, s, adv_loss, acc_m, acc_c, loss = lines[5].split("\t")
+    assert (e, s, float(adv_loss), float(acc_m), float(acc_c), float(loss)) == ("1", "0", 2.0, 25.0, 50.0, 5.0)
