@@ -67,6 +67,10 @@ def format_line(task, utt, score, label):
     return "%s %s\n" % (utt, score)
 
 
+def _device():
+    return torch.device("cuda", torch.cuda.current_device())
+
+
 def test_on_ASVspoof2021(task, feat_model_path, loss_model_path, output_score_path, model_name, add_loss, args):
     from asvspoof2021_air_b200 import data
     from asvspoof2021_air_b200.trainer import Trainer
@@ -92,7 +96,7 @@ def test_on_ASVspoof2021(task, feat_model_path, loss_model_path, output_score_pa
     order = [list(range(lo, min(lo + args.batch_size, len(src)))) for lo in range(0, len(src), args.batch_size)]
     with open(path, "w") as f:
         # decode + H2D of the next batches overlap the forward pass of this one (data.Prefetcher)
-        for batch in data.Prefetcher(src, order, depth=2, device=torch.device("cuda", torch.cuda.current_device())):
+        for batch in data.Prefetcher(src, order, depth=2, device=_device()):
             waves, lengths, _, names, start = batch
             s = tr.score_step(waves, lengths, start).cpu()
             for j, name in enumerate(names):

@@ -185,7 +185,7 @@ def train(args):
     pg = torch.distributed.group.WORLD if world > 1 else None
     tr = Trainer(arch=args.model, enc_dim=args.enc_dim, feat_len=args.feat_len, padding=args.padding, lr=args.lr,
                  beta_1=args.beta_1, beta_2=args.beta_2, eps=args.eps, weight_decay=0.0005, r_real=args.r_real,
-                 r_fake=args.r_fake, alpha=args.alpha, weight_loss=args.weight_loss, device=_device(), process_group=pg,
+                 r_fake=args.r_fake, alpha=args.alpha, weight_loss=args.weight_loss, device="cuda", process_group=pg,
                  seed=args.seed)
     if args.continue_training:                                            # main_train.py:172-173
         from asvspoof2021_air_b200 import compat

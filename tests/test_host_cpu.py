@@ -572,3 +572,49 @@ def test_training_cli_loop_dry_run_adversarial_path(monkeypatch, tmp_path):
     assert [len(ln.split("\t")) for ln in lines[1:]] == [3] * 4 + [6] * 4
     e, s, adv_loss, acc_m, acc_c, loss = lines[5].split("\t")
     assert (e, s, float(adv_loss), float(acc_m), float(acc_c), float(loss)) == ("1", "0", 2.0, 25.0, 50.0, 5.0)
+
+
+def test_scoring_cli_loop_dry_run(monkeypatch, tmp_path):
+    """generate_score.test_on_ASVspoof2021 with the Trainer replaced by a recorder: checkpoint loading through compat,
+    architecture detection, batch order, `utt score [label]` lines for a '19' task and a 2021 task."""
+    import types
+    import wave
+    sys.path.insert(0, ROOT)
+    import generate_score as gs
+    from asvspoof2021_air_b200 import compat, data, trainer
+
+    class FakeScorer(_FakeTrainer):
+        def load_modules(self, model, loss_model=None):
+            self.loaded = (type(model).__name__, None if loss_model is None else tuple(loss_model.center.shape))
+
+        def score_step(self, waves, lengths=None, start=None):
+            self.calls.append(dict(B=waves.shape[0], ragged=lengths is not None))
+            return torch.arange(waves.shape[0], dtype=torch.float32) * 0.25 - 0.5
+
+    Res2Net2 = type("Res2Net2", (), {})
+    loss_model = types.SimpleNamespace(center=torch.zeros(1, 256), r_real=0.9, r_fake=0.2, alpha=20.0)
+    monkeypatch.setattr(trainer, "Trainer", FakeScorer)
+    monkeypatch.setattr(compat, "load_module", lambda path, device=None: Res2Net2() if "feat" in path else loss_model)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(gs, "_device", lambda: torch.device("cpu"))
+    monkeypatch.setattr(data.WaveFolder, "PIN", False)
+    proto = []
+    for i in range(5):
+        with wave.open(str(tmp_path / ("LA_E_%d.wav" % i)), "wb") as f:
+            f.setnchannels(1); f.setsampwidth(2); f.setframerate(16000); f.writeframes(np.zeros(300 + 10 * i, np.int16).tobytes())
+        proto.append("LA_0001 LA_E_%d - %s %s" % (i, "-" if i < 2 else "A09", "bonafide" if i < 2 else "spoof"))
+    (tmp_path / "p.txt").write_text("\n".join(proto) + "\n")
+    for task, want_cols in (("19eval", 3), ("LA", 2)):
+        args = gs.build_parser().parse_args(["--model_folder", str(tmp_path), "-n", "m", "-s", str(tmp_path / "scores"), "-t", task,
+                                             "-l", "ocsoftmax", "--wave_dir", str(tmp_path), "--protocol", str(tmp_path / "p.txt"),
+                                             "--batch_size", "2"])
+        _FakeTrainer.instances = []
+        path = gs.test_on_ASVspoof2021(task, str(tmp_path / "feat.pt"), str(tmp_path / "loss.pt"), str(tmp_path / "scores"), "m",
+                                       "ocsoftmax", args)
+        tr = _FakeTrainer.instances[-1]
+        assert tr.kw["arch"] == "ecapa" and tr.loaded == ("Res2Net2", (1, 256)) and [c["B"] for c in tr.calls] == [2, 2, 1]
+        rows = [ln.split() for ln in open(path).read().strip().splitlines()]
+        assert [r[0] for r in rows] == ["LA_E_%d" % i for i in range(5)] and all(len(r) == want_cols for r in rows)
+        assert [float(r[1]) for r in rows] == [-0.5, -0.25, -0.5, -0.25, -0.5]
+        if want_cols == 3:
+            assert [r[2] for r in rows] == ["bonafide"] * 2 + ["spoof"] * 3
