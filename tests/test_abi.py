@@ -38,3 +38,56 @@ def test_det_and_audio_entry_points_validate_arguments_without_a_gpu():
     assert lib.air_audio_info(b"/nonexistent/x.flac", None, None, None, None) == -3
     assert lib.air_audio_decode_f32(b"/nonexistent/x.flac", None, _lib.LL(0), None, None, 0) == -1
     assert lib.air_audio_decode_batch_f32(None, 0, None, _lib.LL(0), None, None, None, 1, 0) == -1
+
+
+def _header_signatures():
+    """name -> list of parameter declarations, from include/air_b200.h."""
+    import re
+    with open(_lib.HEADER) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    sigs = {}
+    for m in re.finditer(r"\b(?:int|long long)\s+(air_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+        params = [p.strip() for p in m.group(2).replace("\n", " ").split(",")]
+        sigs[m.group(1)] = [] if params == ["void"] or params == [""] else params
+    return sigs
+
+
+def test_every_ctypes_call_site_matches_the_header():
+    """Static check of the binding layer: every `<lib>.air_xxx(...)` call in the package passes as many arguments as the
+    header declares, wraps 64-bit integers / floats / doubles in the matching ctypes type (a bare Python number would
+    be passed as a 32-bit int), and passes pointers as c_void_p / byref / None.  Covers wrappers no test can run here."""
+    import ast
+    import os
+    sigs = _header_signatures()
+    assert len(sigs) >= 70 and sigs["air_version"] == []
+    pkg = os.path.dirname(_lib.__file__)
+    wrap_of = {"long long": {"LL", "c_longlong"}, "unsigned long long": {"c_ulonglong"}, "float": {"F", "c_float"},
+               "double": {"D", "c_double"}}
+    checked, problems = 0, []
+    for fn in sorted(os.listdir(pkg)):
+        if not fn.endswith(".py"):
+            continue
+        tree = ast.parse(open(os.path.join(pkg, fn)).read())
+        for node in ast.walk(tree):
+            if not (isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and node.func.attr.startswith("air_")):
+                continue
+            name = node.func.attr
+            if name not in sigs:
+                problems.append("%s:%d calls undeclared %s" % (fn, node.lineno, name))
+                continue
+            if any(isinstance(a, ast.Starred) for a in node.args):
+                continue
+            checked += 1
+            params = sigs[name]
+            if len(node.args) != len(params):
+                problems.append("%s:%d %s passes %d arguments, header declares %d" % (fn, node.lineno, name, len(node.args), len(params)))
+                continue
+            for a, p in zip(node.args, params):
+                base = p.rsplit(" ", 1)[0].replace("const ", "").strip() if "*" not in p else "ptr"
+                if base in wrap_of:
+                    callee = a.func.attr if isinstance(a, ast.Call) and isinstance(a.func, ast.Attribute) else \
+                        a.func.id if isinstance(a, ast.Call) and isinstance(a.func, ast.Name) else None
+                    if callee not in wrap_of[base]:
+                        problems.append("%s:%d %s: `%s` is not wrapped as %s" % (fn, node.lineno, name, p, sorted(wrap_of[base])[0]))
+    assert checked >= 60, checked
+    assert not problems, "\n".join(problems)
