@@ -37,7 +37,8 @@ def _compile(args):
     if not _newer(src, obj, headers):
         return src, "", False
     if src.endswith(".cpp"):                 # host-only sources (audio ingest): plain C++ through nvcc's host compiler
-        cmd = [_nvcc(), "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-Wall", "-I", CSRC, "-c", src, "-o", obj]
+        cmd = [_nvcc(), "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-Wall", "-I", CSRC,
+               "-I", os.path.join(os.path.dirname(HERE), "include"), "-c", src, "-o", obj]
     else:
         flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
         cmd = [_nvcc()] + ARCH + flags + ["-c", src, "-o", obj]

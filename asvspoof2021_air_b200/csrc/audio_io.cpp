@@ -22,13 +22,7 @@
 #include <thread>
 #include <vector>
 
-#define AIR_OK 0
-#define AIR_ERR_ARG (-1)
-#define AIR_ERR_UNSUPPORTED (-2)
-#define AIR_ERR_IO (-3)
-#define AIR_ERR_FORMAT (-4)
-#define AIR_ERR_CHECKSUM (-5)
-#define AIR_ERR_NOMEM (-6)
+#include "air_b200.h"              // status codes + the declarations this file implements
 
 namespace air_audio {
 

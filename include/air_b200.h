@@ -10,6 +10,7 @@
  *   - every call is asynchronous on `stream` (no device synchronisation inside) and re-entrant
  *     across streams;
  *   - return value: 0 on success, < 0 for argument errors (AIR_ERR_*), > 0 = cudaError_t.
+ * The air_audio_* group at the end is host code (file decoding into caller-owned HOST memory, no stream).
  */
 #ifndef AIR_B200_H
 #define AIR_B200_H
@@ -25,6 +26,11 @@ typedef struct CUstream_st* air_stream_t; /* == cudaStream_t */
 #define AIR_OK 0
 #define AIR_ERR_ARG (-1)
 #define AIR_ERR_UNSUPPORTED (-2)
+/* host-side audio ingest only (air_audio_*): */
+#define AIR_ERR_IO (-3)
+#define AIR_ERR_FORMAT (-4)
+#define AIR_ERR_CHECKSUM (-5)
+#define AIR_ERR_NOMEM (-6)
 
 /* Library version (major*10000 + minor*100 + patch). */
 int air_version(void);

@@ -81,7 +81,7 @@ def main():
     with open(os.path.join(work, "main.cpp"), "w") as f:
         f.write(MAIN)
     exe = os.path.join(work, "fuzz_asan")
-    subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-omit-frame-pointer",
+    subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-I", os.path.join(ROOT, "include"),
                     os.path.join(ROOT, "asvspoof2021_air_b200", "csrc", "audio_io.cpp"), os.path.join(work, "main.cpp"),
                     "-o", exe, "-lpthread"], check=True)
     rng = np.random.RandomState(args.seed)
