@@ -4,9 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
-#define AIR_OK 0
-#define AIR_ERR_ARG (-1)
-#define AIR_ERR_UNSUPPORTED (-2)
+#include "air_b200.h"   // status codes; and every extern "C" definition is checked against its public declaration
 
 // Launch-error check used by every entry point: asynchronous, no device sync.
 static inline int air_launch_status() {
