@@ -58,6 +58,8 @@ def cepstra(wave, scheme):
             re, im = re + elo @ Chi.T, im + olo @ Shi.T
         if terms >= 3:
             re, im = re + ehi @ Clo.T, im + ohi @ Slo.T
+        if terms >= 4:
+            re, im = re + elo @ Clo.T, im + olo @ Slo.T
         re = re.astype(np.float32) + a[:, :1] * c160
         im = im.astype(np.float32) - a[:, :1] * s160
         P = (re * re + im * im)[:, :255]
@@ -76,7 +78,7 @@ def signals(L=16000):
 
 
 if __name__ == "__main__":
-    schemes = {"bf16 3 terms (kernel)": ("bf16", 3), "bf16 2 terms (no x_hi*w_lo)": ("bf16", 2),
+    schemes = {"bf16 4 terms (+x_lo*w_lo)": ("bf16", 4), "bf16 3 terms (kernel)": ("bf16", 3), "bf16 2 terms (no x_hi*w_lo)": ("bf16", 2),
                "fp16 2 terms (no x_hi*w_lo)": ("fp16", 2), "fp16 1 term": ("fp16", 1)}
     sig = signals()
     print("%-42s" % "worst |a-b|/(|b|+1) of the 20 cepstra" + "".join("%30s" % s for s in schemes))
