@@ -618,3 +618,54 @@ def test_scoring_cli_loop_dry_run(monkeypatch, tmp_path):
         assert [float(r[1]) for r in rows] == [-0.5, -0.25, -0.5, -0.25, -0.5]
         if want_cols == 3:
             assert [r[2] for r in rows] == ["bonafide"] * 2 + ["spoof"] * 3
+
+
+def _conv_route(layer, H, W):
+    """Which kernel family ConvLayer.fprop / dgrad / wgrad pick for an (H, W) input -- the branch order of engine.py."""
+    f = "patch" if layer.use_patch(H, W) else "patch1x1" if layer.p1x1_ok else "patch1d" if layer.d1_ok else "gemm"
+    if not layer.need_dgrad:
+        d = "-"
+    else:
+        d = ("patch" if layer.use_patch(H, W) else "patch1x1" if layer.p1x1_ok else "patch1d" if layer.d1_ok
+             else "patch_s2" if layer.s2_dgrad_ok else "gemm")
+    w = "patch1d" if layer.d1_ok else "patch" if (layer.wpatch_ok and layer._patch_efficiency(H, W) >= 0.5) else "gemm"
+    return "%s/%s/%s" % (f, d, w)
+
+
+def test_kernel_dispatch_table_at_the_benchmark_geometry():
+    """Performance guard that needs no GPU: which tcgen05 kernel serves fprop / dgrad / wgrad of every conv layer at the
+    BASELINE geometry ((60, 750) features).  The table is the one the measured numbers in profiles/ were taken with; a
+    change that silently drops a layer back to the generic gather kernels shows up here, not only in the next bench."""
+    from asvspoof2021_air_b200.engine import ResNetEngine
+    from asvspoof2021_air_b200.engine_ecapa import EcapaEngine
+    eng = ResNetEngine(enc_dim=256, nclasses=2, device="cpu")
+    H, W = 18, 750                                            # after the 9x3 stem (stride 3 x 1): resnet.py:131
+    got = {}
+    for blk in eng.blocks:
+        Ho, Wo = blk.conv1.out_hw(H, W)
+        got[blk.name] = (H, W, _conv_route(blk.conv1, H, W), _conv_route(blk.conv2, Ho, Wo),
+                         _conv_route(blk.sc, H, W) if blk.sc is not None else None)
+        H, W = Ho, Wo
+    want = {
+        "layer1.0": (18, 750, "patch/patch/patch", "patch/patch/patch", "patch1x1/patch1x1/patch"),
+        "layer1.1": (18, 750, "patch/patch/patch", "patch/patch/patch", None),
+        "layer2.0": (18, 750, "gemm/patch_s2/gemm", "patch/patch/patch", "gemm/patch_s2/gemm"),
+        "layer2.1": (9, 375, "patch/patch/patch", "patch/patch/patch", None),
+        "layer3.0": (9, 375, "gemm/patch_s2/gemm", "patch/patch/patch", "gemm/patch_s2/gemm"),
+        "layer3.1": (5, 188, "patch/patch/patch", "patch/patch/patch", None),
+        "layer4.0": (5, 188, "gemm/patch_s2/gemm", "gemm/gemm/patch", "gemm/patch_s2/gemm"),
+        "layer4.1": (3, 94, "gemm/gemm/patch", "gemm/gemm/patch", None),
+    }
+    assert got == want, got
+    # ECAPA-TDNN-512 at T = 750: 1x1 layers on the TMA GEMM path, the 21 dilated Res2 branches on the 1-D patch kernels
+    ec = EcapaEngine(device="cpu")
+    routes = {}
+    for layer in ec.convs():
+        routes[layer.name] = _conv_route(layer, 1, 750)
+    branch = [v for k, v in routes.items() if ".convs." in k]
+    assert len(branch) == 21 and set(branch) == {"patch1d/patch1d/patch1d"}, routes
+    # the biased 1x1 layers go through the generic entry points, which take their own TMA path for 1x1 / stride 1 in C
+    rest = {k: v for k, v in routes.items() if ".convs." not in k}
+    assert rest.pop("conv1") == "gemm/-/gemm" and set(rest.values()) == {"gemm/gemm/gemm"}, routes
+    assert sorted(rest) == ["attention.3", "layer1.conv1", "layer1.conv3", "layer2.conv1", "layer2.conv3", "layer3.conv1",
+                            "layer3.conv3", "layer4"]
