@@ -669,3 +669,26 @@ def test_kernel_dispatch_table_at_the_benchmark_geometry():
     assert rest.pop("conv1") == "gemm/-/gemm" and set(rest.values()) == {"gemm/gemm/gemm"}, routes
     assert sorted(rest) == ["attention.3", "layer1.conv1", "layer1.conv3", "layer2.conv1", "layer2.conv3", "layer3.conv1",
                             "layer3.conv3", "layer4"]
+
+
+def test_algorithmic_flops_per_utterance_match_the_survey():
+    """The roofline numerator: conv / linear MACs of one forward pass computed from the engines' own layer geometry
+    equal the figures SURVEY.md section 8(d) probed by hooking the reference modules (15.709 and 7.698 GFLOP/utt)."""
+    from asvspoof2021_air_b200.engine import ResNetEngine
+    from asvspoof2021_air_b200.engine_ecapa import EcapaEngine
+    eng = ResNetEngine(enc_dim=256, nclasses=2, device="cpu")
+    H, W = 18, 750
+    total = 2 * H * W * 16 * 27                                    # 9x3 stem, resnet.py:131
+    for b in eng.blocks:
+        Ho, Wo = b.conv1.out_hw(H, W)
+        total += 2 * Ho * Wo * (b.conv1.cout * b.conv1.K + b.conv2.cout * b.conv2.K + (b.sc.cout * b.sc.K if b.sc is not None else 0))
+        H, W = Ho, Wo
+    Ho, Wo = eng.conv5.out_hw(H, W)
+    total += 2 * Ho * Wo * eng.conv5.cout * eng.conv5.K + 2 * (512 * 256 + 256 * 2)
+    assert (Ho, Wo) == (1, 94) and abs(total / 1e9 - 15.709) < 1e-3, total
+    ec = EcapaEngine(device="cpu")
+    T = 750
+    t = sum(2 * T * l.cout * l.taps * l.cin for l in ec.convs())
+    t += 2 * T * 128 * 4608                                        # attention.0 on [x | mean | std] (ecapa_tdnn.py:139-145,174)
+    t += 3 * 2 * (512 * 128 + 128 * 512) + 2 * (3072 * 256 + 256 * 2)    # SE bottlenecks, fc6, fc7
+    assert abs(t / 1e9 - 7.698) < 2e-3, t
