@@ -18,12 +18,33 @@ class AirError(RuntimeError):
     pass
 
 
-def declared_symbols(header=HEADER):
-    """Names of every `int air_*(...)` entry point declared in the public header."""
+def _declarations(header=HEADER):
+    """[(return type, name, [parameter declarations])] of every entry point declared in the public header."""
     with open(header) as f:
         text = f.read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return re.findall(r"\b(?:int|long long)\s+(air_\w+)\s*\(", text)
+    out = []
+    for m in re.finditer(r"\b(int|long long)\s+(air_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+        params = [p.strip() for p in m.group(3).replace("\n", " ").split(",")]
+        out.append((m.group(1), m.group(2), [] if params in (["void"], [""]) else params))
+    return out
+
+
+def declared_symbols(header=HEADER):
+    """Names of every `int air_*(...)` entry point declared in the public header."""
+    return [name for _, name, _ in _declarations(header)]
+
+
+_SCALARS = {"int": ctypes.c_int, "long long": ctypes.c_longlong, "unsigned long long": ctypes.c_ulonglong,
+            "float": ctypes.c_float, "double": ctypes.c_double, "air_stream_t": ctypes.c_void_p}
+
+
+def _ctype_of(param):
+    """ctypes type of one C parameter declaration: every pointer (device or host) travels as c_void_p."""
+    if "*" in param:
+        return ctypes.c_char_p if re.match(r"const char\s*\*\s*\w+$", param) else ctypes.c_void_p
+    base = param.rsplit(" ", 1)[0].replace("const ", "").strip()
+    return _SCALARS[base]
 
 
 def lib():
@@ -33,8 +54,10 @@ def lib():
             raise AirError("libair_b200.so is not built (%s); run `python -m asvspoof2021_air_b200.build`. "
                            "There is no CPU or PyTorch fallback for this path." % LIB_PATH)
         _lib = ctypes.CDLL(LIB_PATH)
-        for name in declared_symbols():
-            getattr(_lib, name).restype = ctypes.c_int
+        for ret, name, params in _declarations():          # restype AND argtypes from the header: a wrong Python
+            fn = getattr(_lib, name)                       # argument raises ctypes.ArgumentError instead of being
+            fn.restype = ctypes.c_longlong if ret == "long long" else ctypes.c_int      # truncated to a 32-bit int
+            fn.argtypes = [_ctype_of(p) for p in params]
     return _lib
 
 

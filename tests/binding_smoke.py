@@ -1,0 +1,88 @@
+"""Binding smoke WITHOUT a GPU: run the real Python orchestration of every product path (train step, validation,
+scoring, both architectures, the adversarial branch, fp32 LFCC, the detection metrics) on CPU tensors with the status
+check softened, so that every ctypes call is made for real -- the header-derived argtypes (asvspoof2021_air_b200/_lib.py)
+must accept every argument -- while the kernel launches themselves simply fail (no driver).  Results are garbage by
+construction; what is checked is that no Python-side error (ctypes.ArgumentError, TypeError, shape / attribute bugs)
+occurs anywhere and which entry points were reached.  Run as a script (it patches torch globally):
+    python tests/binding_smoke.py          -> prints `binding smoke ok <n entry points>`"""
+import ctypes
+import os
+import sys
+
+os.environ["AIR_OVERLAP_WGRAD"] = "0"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from asvspoof2021_air_b200 import _lib, ops  # noqa: E402
+
+if torch.cuda.is_available():
+    print("binding smoke skipped: a CUDA device is present (the GPU tests cover this)")
+    sys.exit(0)
+
+reached = {}
+
+
+def soft_check(status, what, n=1):
+    reached[what] = status
+
+
+class _Props:
+    multi_processor_count = 148
+
+
+_lib.check = soft_check
+_lib.stream_ptr = lambda: ctypes.c_void_p(0)
+ops.num_sms = lambda device=None: 148
+torch.cuda.get_device_properties = lambda d=None: _Props()
+torch.cuda.is_available = lambda: True
+torch.cuda.current_device = lambda: 0
+torch.Tensor.is_cuda = property(lambda self: True)
+
+
+class _NullDeviceContext:
+    def __init__(self, device=None):
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+torch.cuda.device = _NullDeviceContext
+
+from asvspoof2021_air_b200 import data, eval_metrics as em  # noqa: E402
+from asvspoof2021_air_b200.feature_extraction import LFCC  # noqa: E402
+from asvspoof2021_air_b200.trainer import Trainer  # noqa: E402
+
+waves, _, labels, _, _ = data.SyntheticWaves(4, length=64000, seed=2).batch([0, 1, 2, 3])
+ragged = torch.tensor([64000, 40000, 20000, 64000], dtype=torch.int32)
+for arch in ("resnet", "ecapa"):
+    tr = Trainer(arch=arch, device="cpu", seed=1)
+    tr.train_step(waves, labels)
+    tr.train_step(waves, labels, lengths=ragged, start=torch.zeros(4, dtype=torch.int32))
+    tr.eval_loss(waves, labels)
+    tr.score_step(waves)
+    tr.attach_adversaries([5, 3], lambda_=0.5, lr_d=1e-3, seed=4)
+    tr.train_step(waves, labels, channels=torch.tensor([[0, 1], [4, 2], [2, 0], [1, 1]]), step_seed=3)
+    feat_model, loss_model = tr.modules()
+    assert len(feat_model.state_dict()) in (117, 248)
+for impl in ("fft", "tc"):
+    m = LFCC(320, 160, 512, 16000, 20)
+    m.impl = impl
+    assert tuple(m(waves).shape) == (4, 401, 60)
+    for pad in ("zero", "repeat", "silence"):
+        m.extract(waves, lengths=ragged, feat_len=750, padding=pad, layout="ecapa")
+
+# detection metrics
+r = em.det(torch.randn(50), torch.randn(70) - 1, c1=1.0, c2=2.0, curves=True)
+em.det(torch.randn(50).double(), torch.randn(70).double(), negate=True)
+em.obtain_asv_error_rates(torch.randn(9), torch.randn(9), torch.randn(9), 0.1)
+
+bad = {k: v for k, v in reached.items() if v == -1}
+assert not bad, "argument errors: %s" % bad
+assert len(reached) >= 50, sorted(reached)
+print("binding smoke ok %d entry points" % len(reached))

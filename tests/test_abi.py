@@ -63,6 +63,7 @@ def test_every_ctypes_call_site_matches_the_header():
     pkg = os.path.dirname(_lib.__file__)
     wrap_of = {"long long": {"LL", "c_longlong"}, "unsigned long long": {"c_ulonglong"}, "float": {"F", "c_float"},
                "double": {"D", "c_double"}}
+    all_wrappers = {w for ws in wrap_of.values() for w in ws} | {"c_int", "c_void_p", "c_char_p"}
     checked, problems = 0, []
     for fn in sorted(os.listdir(pkg)):
         if not fn.endswith(".py"):
@@ -84,10 +85,13 @@ def test_every_ctypes_call_site_matches_the_header():
                 continue
             for a, p in zip(node.args, params):
                 base = p.rsplit(" ", 1)[0].replace("const ", "").strip() if "*" not in p else "ptr"
+                callee = a.func.attr if isinstance(a, ast.Call) and isinstance(a.func, ast.Attribute) else \
+                    a.func.id if isinstance(a, ast.Call) and isinstance(a.func, ast.Name) else None
                 if base in wrap_of:
-                    callee = a.func.attr if isinstance(a, ast.Call) and isinstance(a.func, ast.Attribute) else \
-                        a.func.id if isinstance(a, ast.Call) and isinstance(a.func, ast.Name) else None
                     if callee not in wrap_of[base]:
                         problems.append("%s:%d %s: `%s` is not wrapped as %s" % (fn, node.lineno, name, p, sorted(wrap_of[base])[0]))
+                elif callee in all_wrappers and not (base == "ptr" and callee in ("c_void_p", "c_char_p")):
+                    # argtypes come from the header (_lib.lib()): a c_longlong handed to an `int` parameter would raise
+                    problems.append("%s:%d %s: `%s` receives a %s" % (fn, node.lineno, name, p, callee))
     assert checked >= 60, checked
     assert not problems, "\n".join(problems)

@@ -692,3 +692,15 @@ def test_algorithmic_flops_per_utterance_match_the_survey():
     t += 2 * T * 128 * 4608                                        # attention.0 on [x | mean | std] (ecapa_tdnn.py:139-145,174)
     t += 3 * 2 * (512 * 128 + 128 * 512) + 2 * (3072 * 256 + 256 * 2)    # SE bottlenecks, fc6, fc7
     assert abs(t / 1e9 - 7.698) < 2e-3, t
+
+
+def test_binding_smoke_every_product_path_on_cpu():
+    """tests/binding_smoke.py: the real orchestration of train step / validation / scoring (both nets, ragged batches,
+    the adversarial branch), fp32 + bf16 LFCC with every pad mode and the detection metrics, run on CPU tensors with
+    kernel launches failing softly -- every ctypes call must be accepted by the header-derived argtypes and no
+    Python-level error may occur anywhere on those paths."""
+    if torch.cuda.is_available():
+        pytest.skip("covered by the GPU tests when a device is present")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "binding_smoke.py")], capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0 and "binding smoke ok" in r.stdout, r.stdout[-1000:] + r.stderr[-3000:]
