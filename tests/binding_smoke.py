@@ -70,6 +70,11 @@ for arch in ("resnet", "ecapa"):
     tr.train_step(waves, labels, channels=torch.tensor([[0, 1], [4, 2], [2, 0], [1, 1]]), step_seed=3)
     feat_model, loss_model = tr.modules()
     assert len(feat_model.state_dict()) in (117, 248)
+    # an off-benchmark geometry: odd batch, short utterances, another feature length
+    tr2 = Trainer(arch=arch, device="cpu", seed=1, feat_len=400)
+    w2, _, l2, _, _ = data.SyntheticWaves(3, length=16000, seed=5).batch([0, 1, 2])
+    tr2.train_step(w2, l2)
+    tr2.score_step(w2[:1])
 for impl in ("fft", "tc"):
     m = LFCC(320, 160, 512, 16000, 20)
     m.impl = impl
