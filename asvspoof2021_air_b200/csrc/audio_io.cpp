@@ -670,3 +670,35 @@ extern "C" int air_audio_decode_batch_f32(const char* const* paths, int n, float
   }
   return first;
 }
+
+// Rows of a (pinned) float matrix from a packed int16 corpus (data.PackedWaves): row i = blob[offsets[i] ..
+// offsets[i] + min(lengths[i], ld)) * 2^-15, zero-padded to ld.  Memory-bound; `threads` host threads (<= 0: all).
+extern "C" int air_audio_gather_i16_f32(const short* blob, const long long* offsets, const int* lengths, int n,
+                                        float* out, long long ld, int threads) {
+  if (!blob || !offsets || !lengths || n < 0 || !out || ld < 1) return AIR_ERR_ARG;
+  for (int i = 0; i < n; ++i) if (offsets[i] < 0 || lengths[i] < 0) return AIR_ERR_ARG;
+  if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+  if (threads < 1) threads = 1;
+  if (threads > n) threads = n;
+  std::atomic<int> next{0};
+  auto work = [&]() {
+    const float scale = 1.0f / 32768.0f;
+    for (;;) {
+      const int i = next.fetch_add(1);
+      if (i >= n) return;
+      const short* src = blob + offsets[i];
+      float* row = out + (long long)i * ld;
+      const long long k = lengths[i] < ld ? lengths[i] : ld;
+      for (long long j = 0; j < k; ++j) row[j] = (float)src[j] * scale;
+      memset(row + k, 0, (size_t)(ld - k) * sizeof(float));
+    }
+  };
+  if (threads <= 1) {
+    work();
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t) pool.emplace_back(work);
+    for (auto& t : pool) t.join();
+  }
+  return AIR_OK;
+}

@@ -8,6 +8,9 @@ and LFCC / crop / pad happen inside the step, so a source only has to deliver
                    `utt_id label` or ASVspoof-style `spk utt_id - attack label` (label: bonafide / spoof);
                    FLAC and WAV are decoded by the native batch decoder (csrc/audio_io.cpp, host threads, straight
                    into pinned rows) -- the ASVspoof corpora ship as 16 kHz FLAC (raw_dataset.py:20-28,61-66)
+  AugWaveFolder  : originals + channel-augmented copies with channel / device class labels (--ADV_AUG)
+  PackedWaves    : a folder decoded once by pack_folder() into one memory-mapped int16 file; batches are gathered and
+                   converted by a native threaded copy (full-speed epochs without re-decoding FLAC)
   Prefetcher     : decodes / collates batch i+1.. on a host thread and copies it to the device on a copy stream while
                    step i runs (the DataLoader(num_workers) + .to(device) of main_train.py:226-242,338-348)
 Crop policy for utterances longer than feat_len frames follows dataset.py:66-69: start ~ np.random.randint.
@@ -110,6 +113,87 @@ class WaveFolder:
         labels = torch.tensor([self.items[i][1] for i in indices], dtype=torch.long)
         start = torch.from_numpy(_crop_starts(lens, self.feat_len, self.rng))
         return waves, torch.from_numpy(lens), labels, utts, start
+
+
+def pack_folder(source, prefix, batch=256):
+    """Decode a WaveFolder ONCE into a packed int16 corpus: `<prefix>.i16` (all utterances back to back) and
+    `<prefix>.json` (names, labels, offsets, lengths, extra per-item classes).  The native decoder delivers about 700
+    four-second FLAC files per second and core while one GPU consumes ~11 000 utterances per second, so every epoch
+    after the first should read this file (PackedWaves) instead of the FLAC folder.  16-bit sources only: the float
+    samples are mapped back to the exact integers they came from."""
+    import json
+    offsets, lengths, pos = [], [], 0
+    with open(prefix + ".i16", "wb") as f:
+        for lo in range(0, len(source), batch):
+            idx = list(range(lo, min(lo + batch, len(source))))
+            item = source.batch(idx, pinned=False)
+            waves, lens = item[0], item[1]
+            q = torch.round(waves * 32768.0)
+            if float((q - waves * 32768.0).abs().max()) > 1e-3 or float(q.abs().max()) > 32768:
+                raise ValueError("pack_folder: the source is not 16-bit PCM (samples are not multiples of 2^-15)")
+            q = q.clamp(-32768, 32767).to(torch.int16).numpy()
+            for j, n in enumerate(lens.tolist()):
+                f.write(q[j, :n].tobytes())
+                offsets.append(pos)
+                lengths.append(n)
+                pos += n
+    meta = {"names": [u for u, _ in source.items], "labels": [int(l) for _, l in source.items], "offsets": offsets,
+            "lengths": lengths, "sample_rate": 16000, "samples": pos,
+            "classes": [list(c) for c in getattr(source, "classes", [])], "kind": getattr(source, "kind", None),
+            "n_ori": getattr(source, "n_ori", len(source))}
+    with open(prefix + ".json", "w") as f:
+        json.dump(meta, f)
+    return meta
+
+
+class PackedWaves:
+    """A corpus written by pack_folder(): memory-mapped int16 samples, rows gathered and converted to float32 by the
+    native threaded gather (csrc/audio_io.cpp air_audio_gather_i16_f32) straight into pinned memory.  Same batch()
+    contract as WaveFolder / AugWaveFolder (a sixth element with the channel classes when the source had them)."""
+    PIN = None
+
+    def __init__(self, prefix, feat_len=750, seed=0, threads=0):
+        import json
+        with open(prefix + ".json") as f:
+            m = json.load(f)
+        self.names, self.labels = m["names"], np.asarray(m["labels"], dtype=np.int64)
+        self.offsets = np.asarray(m["offsets"], dtype=np.int64)
+        self.lengths = np.asarray(m["lengths"], dtype=np.int32)
+        self.classes = np.asarray(m["classes"], dtype=np.int64) if m.get("classes") else None
+        self.kind, self.n_ori = m.get("kind"), m.get("n_ori", len(self.names))
+        if self.kind:
+            self.channel_names, self.device_names = channel_tables(self.kind)
+        self.blob = np.memmap(prefix + ".i16", dtype=np.int16, mode="r")
+        if self.blob.shape[0] != m["samples"]:
+            raise ValueError("%s.i16 holds %d samples, the index announces %d" % (prefix, self.blob.shape[0], m["samples"]))
+        self.items = list(zip(self.names, self.labels.tolist()))
+        self.feat_len, self.threads = feat_len, threads
+        self.rng = np.random.RandomState(seed)
+
+    def __len__(self):
+        return len(self.names)
+
+    def batch(self, indices, pinned=None):
+        import ctypes
+        from . import _lib
+        idx = np.asarray(indices, dtype=np.int64)
+        lens = np.ascontiguousarray(self.lengths[idx])
+        offs = np.ascontiguousarray(self.offsets[idx])
+        if pinned is None:
+            pinned = torch.cuda.is_available() if self.PIN is None else self.PIN
+        waves = torch.empty(len(idx), int(lens.max()), pin_memory=pinned)
+        st = _lib.lib().air_audio_gather_i16_f32(ctypes.c_void_p(self.blob.ctypes.data), offs.ctypes.data_as(ctypes.c_void_p),
+                                                 lens.ctypes.data_as(ctypes.c_void_p), len(idx), ctypes.c_void_p(waves.data_ptr()),
+                                                 _lib.LL(waves.stride(0)), int(self.threads))
+        if st != 0:
+            raise audio_io.AudioError("air_audio_gather_i16_f32 failed: status %d" % st)
+        labels = torch.from_numpy(self.labels[idx])
+        start = torch.from_numpy(_crop_starts(lens, self.feat_len, self.rng))
+        out = (waves, torch.from_numpy(lens), labels, [self.names[i] for i in idx], start)
+        if self.classes is not None and self.classes.size:
+            ch = torch.from_numpy(self.classes[idx])
+            out += (ch[:, 0] if ch.shape[1] == 1 else ch,)
+        return out
 
 
 def channel_tables(kind):
@@ -243,3 +327,28 @@ class Prefetcher:
                     if t is not None:
                         t.record_stream(cur)
             yield b
+
+
+def _main(argv=None):
+    """python -m asvspoof2021_air_b200.data pack --wave_dir DIR --protocol FILE --out PREFIX
+                                            [--aug_wave_dir DIR --kind LA|DF|LAPA|DFPA] [--verify]"""
+    import argparse
+    ap = argparse.ArgumentParser(prog="python -m asvspoof2021_air_b200.data")
+    ap.add_argument("command", choices=["pack"])
+    ap.add_argument("--wave_dir", required=True)
+    ap.add_argument("--protocol", required=True)
+    ap.add_argument("--out", required=True)
+    ap.add_argument("--aug_wave_dir", default=None)
+    ap.add_argument("--kind", default=None, choices=[None, "LA", "DF", "LAPA", "DFPA"])
+    ap.add_argument("--verify", action="store_true", help="check the MD5 signature of every FLAC file")
+    a = ap.parse_args(argv)
+    if a.aug_wave_dir:
+        src = AugWaveFolder(a.wave_dir, a.aug_wave_dir, a.protocol, a.kind or "LA", verify=a.verify)
+    else:
+        src = WaveFolder(a.wave_dir, a.protocol, verify=a.verify)
+    m = pack_folder(src, a.out)
+    print("packed %d utterances, %.1f MB -> %s.i16" % (len(m["names"]), 2e-6 * m["samples"], a.out))
+
+
+if __name__ == "__main__":
+    _main()

@@ -35,6 +35,7 @@ def build_parser():
     new.add_argument("--synthetic", type=int, default=0)
     new.add_argument("--wave_dir", type=str, default=None)
     new.add_argument("--protocol", type=str, default=None)
+    new.add_argument("--packed_waves", type=str, default=None, help="prefix of a corpus written by asvspoof2021_air_b200.data pack")
     new.add_argument("--batch_size", type=int, default=1024)
     new.add_argument("--feat_len", type=int, default=750)
     new.add_argument("--padding", type=str, default="repeat", choices=["zero", "repeat", "silence"])
@@ -85,7 +86,9 @@ def test_on_ASVspoof2021(task, feat_model_path, loss_model_path, output_score_pa
     tr = Trainer(arch=arch, enc_dim=loss_model.center.shape[1], feat_len=args.feat_len, padding=args.padding,
                  r_real=loss_model.r_real, r_fake=loss_model.r_fake, alpha=loss_model.alpha, device="cuda")
     tr.load_modules(model, loss_model)
-    if args.wave_dir:
+    if args.packed_waves:
+        src = data.PackedWaves(args.packed_waves, args.feat_len)
+    elif args.wave_dir:
         src = data.WaveFolder(args.wave_dir, args.protocol, args.feat_len)
     elif args.synthetic > 0:
         src = data.SyntheticWaves(args.synthetic, feat_len=args.feat_len)

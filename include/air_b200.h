@@ -389,6 +389,10 @@ int air_audio_decode_i32(const char* path, int* out, long long capacity, long lo
                          int* bits, int* sample_rate, int flags);
 int air_audio_decode_batch_f32(const char* const* paths, int n, float* out, long long ld, int* lengths,
                                int* sample_rates, int* status, int threads, int flags);
+/* rows of a (pinned) float matrix from a packed int16 corpus: row i = blob[offsets[i] .. + min(lengths[i], ld)) / 32768,
+ * zero-padded to ld (asvspoof2021_air_b200/data.py PackedWaves; decode once, train many epochs) */
+int air_audio_gather_i16_f32(const short* blob, const long long* offsets, const int* lengths, int n,
+                             float* out, long long ld, int threads);
 
 
 /* ---------------------------------------------------------------------------------------------

@@ -84,6 +84,9 @@ def build_parser():
     new.add_argument("--protocol", type=str, default=None, help="protocol file for --wave_dir")
     new.add_argument("--aug_wave_dir", type=str, default=None,
                      help="--ADV_AUG: folder of <utt>_<channel>[_<device>] augmented copies (raw_dataset.py:149-300)")
+    new.add_argument("--packed_waves", type=str, default=None,
+                     help="prefix of a corpus written by `python -m asvspoof2021_air_b200.data pack` (decode FLAC once)")
+    new.add_argument("--dev_packed_waves", type=str, default=None)
     new.add_argument("--dev_wave_dir", type=str, default=None)
     new.add_argument("--dev_protocol", type=str, default=None)
     new.add_argument("--steps_per_epoch", type=int, default=0, help="0: one pass over the source")
@@ -127,8 +130,9 @@ def _reject_out_of_scope(args):
     if args.ADV_AUG:
         if sum(bool(x) for x in (args.LA_aug, args.DF_aug, args.LAPA_aug, args.DFPA_aug)) != 1:
             raise SystemExit("--ADV_AUG needs exactly one of --LA_aug / --DF_aug / --LAPA_aug / --DFPA_aug (main_train.py:212)")
-        if not (args.wave_dir and args.aug_wave_dir and args.protocol):
-            raise SystemExit("--ADV_AUG trains from raw waves: pass --wave_dir (originals), --aug_wave_dir and --protocol")
+        if not ((args.wave_dir and args.aug_wave_dir and args.protocol) or args.packed_waves):
+            raise SystemExit("--ADV_AUG trains from raw waves: pass --wave_dir (originals), --aug_wave_dir and --protocol, "
+                             "or --packed_waves of a corpus packed from them")
         if os.environ.get("AIR_ADV_UNVALIDATED") != "1":
             raise SystemExit("--ADV_AUG: the channel-classifier head is built (asvspoof2021_air_b200/adv.py) but its GPU "
                              "parity test has not run on hardware yet; set AIR_ADV_UNVALIDATED=1 to use it anyway")
@@ -162,6 +166,9 @@ def _source(args, dev=False):
     from asvspoof2021_air_b200 import data
     n = args.dev_synthetic if dev else args.synthetic
     folder = args.dev_wave_dir if dev else args.wave_dir
+    packed = args.dev_packed_waves if dev else args.packed_waves
+    if packed:
+        return data.PackedWaves(packed, args.feat_len, args.seed + (1 if dev else 0))
     if folder and args.ADV_AUG and not dev:
         kind = "LA" if args.LA_aug else "DF" if args.DF_aug else "LAPA" if args.LAPA_aug else "DFPA"
         return data.AugWaveFolder(folder, args.aug_wave_dir, args.protocol, kind, args.feat_len, args.seed)

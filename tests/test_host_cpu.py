@@ -704,3 +704,45 @@ def test_binding_smoke_every_product_path_on_cpu():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "binding_smoke.py")], capture_output=True, text=True,
                        timeout=900)
     assert r.returncode == 0 and "binding smoke ok" in r.stdout, r.stdout[-1000:] + r.stderr[-3000:]
+
+
+def test_packed_corpus_round_trip_and_threaded_gather(tmp_path):
+    """pack_folder() -> PackedWaves: the same batches as the FLAC / WAV folder it was made from, bit for bit."""
+    import flac_writer as fw
+    import wave
+    from asvspoof2021_air_b200 import data
+    rng = np.random.RandomState(8)
+    proto = []
+    for i in range(7):
+        n = int(rng.randint(300, 4000))
+        x = rng.randint(-32768, 32768, n).astype(np.int64)
+        x[:3] = [-32768, 32767, 0]                                         # both ends of the 16-bit range survive
+        if i % 2:
+            with wave.open(str(tmp_path / ("u%d.wav" % i)), "wb") as f:
+                f.setnchannels(1); f.setsampwidth(2); f.setframerate(16000); f.writeframes(x.astype(np.int16).tobytes())
+        else:
+            fw.write_flac(str(tmp_path / ("u%d.flac" % i)), x, 16, 16000, [fw.FrameSpec(n, [fw.Sub("verbatim")])])
+        proto.append("spk u%d - - %s" % (i, "spoof" if i % 3 == 0 else "bonafide"))
+    (tmp_path / "p.txt").write_text("\n".join(proto) + "\n")
+    src = data.WaveFolder(str(tmp_path), str(tmp_path / "p.txt"), seed=3)
+    meta = data.pack_folder(src, str(tmp_path / "corpus"), batch=3)
+    assert meta["samples"] == sum(meta["lengths"]) and os.path.getsize(tmp_path / "corpus.i16") == 2 * meta["samples"]
+    for threads in (1, 3):
+        pk = data.PackedWaves(str(tmp_path / "corpus"), seed=3, threads=threads)
+        ref = data.WaveFolder(str(tmp_path), str(tmp_path / "p.txt"), seed=3)
+        assert len(pk) == 7
+        for idx in ([0, 1, 2, 3], [6, 2], [5]):
+            a, b = pk.batch(idx), ref.batch(idx)
+            assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and a[3] == b[3]
+            assert torch.equal(a[4], b[4]) and len(a) == 5
+    batches = list(data.Prefetcher(data.PackedWaves(str(tmp_path / "corpus")), [[0, 1], [2, 3, 4]], device=None))
+    assert [b[0].shape[0] for b in batches] == [2, 3]
+    # a float source that is not 16-bit PCM is refused rather than silently quantised
+    np.save(tmp_path / "f.npy", (rng.randn(100) * 0.1).astype(np.float32))
+    (tmp_path / "p2.txt").write_text("f bonafide\n")
+    with pytest.raises(ValueError, match="not 16-bit"):
+        data.pack_folder(data.WaveFolder(str(tmp_path), str(tmp_path / "p2.txt")), str(tmp_path / "c2"))
+    with open(tmp_path / "corpus.i16", "ab") as f:
+        f.write(b"\x00\x00")
+    with pytest.raises(ValueError, match="announces"):
+        data.PackedWaves(str(tmp_path / "corpus"))
