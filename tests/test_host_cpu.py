@@ -746,3 +746,35 @@ def test_packed_corpus_round_trip_and_threaded_gather(tmp_path):
         f.write(b"\x00\x00")
     with pytest.raises(ValueError, match="announces"):
         data.PackedWaves(str(tmp_path / "corpus"))
+
+
+def test_training_cli_dry_run_from_packed_corpora(monkeypatch, tmp_path):
+    """--packed_waves / --dev_packed_waves, plain and with the adversarial branch (classes travel inside the corpus)."""
+    import wave
+    from asvspoof2021_air_b200 import data
+    ori, aug = tmp_path / "ori", tmp_path / "aug"
+    ori.mkdir(); aug.mkdir()
+    ch, _ = data.channel_tables("DF")
+    proto = []
+    for i in range(6):
+        for folder, name in ((ori, "u%d" % i), (aug, "u%d_%s" % (i, ch[1 + i % 6]))):
+            with wave.open(str(folder / (name + ".wav")), "wb") as f:
+                f.setnchannels(1); f.setsampwidth(2); f.setframerate(16000); f.writeframes(np.full(200 + i, i, np.int16).tobytes())
+        proto.append("s u%d - - %s" % (i, "bonafide" if i % 2 else "spoof"))
+    (tmp_path / "p.txt").write_text("\n".join(proto) + "\n")
+    data._main(["pack", "--wave_dir", str(ori), "--protocol", str(tmp_path / "p.txt"), "--out", str(tmp_path / "plain")])
+    data._main(["pack", "--wave_dir", str(ori), "--protocol", str(tmp_path / "p.txt"), "--out", str(tmp_path / "adv"),
+                "--aug_wave_dir", str(aug), "--kind", "DF"])
+    monkeypatch.setattr(data.PackedWaves, "PIN", False)
+    tr = _cli_dry_run(monkeypatch, ["-o", str(tmp_path / "m1"), "-m", "resnet", "--add_loss", "ang_iso", "--packed_waves",
+                                    str(tmp_path / "plain"), "--dev_packed_waves", str(tmp_path / "plain"), "--batch_size", "3",
+                                    "--num_epochs", "1"])
+    assert [c["B"] for c in tr.calls] == [3, 3] and all(c["ragged"] for c in tr.calls)
+    assert open(tmp_path / "m1" / "dev_loss.log").read().strip().splitlines()[1] == "0\t2.0\t0.125"
+    monkeypatch.setenv("AIR_ADV_UNVALIDATED", "1")
+    tr = _cli_dry_run(monkeypatch, ["-o", str(tmp_path / "m2"), "-m", "resnet", "--add_loss", "ang_iso", "--ADV_AUG", "--DF_aug",
+                                    "--packed_waves", str(tmp_path / "adv"), "--batch_size", "4", "--num_epochs", "2"])
+    assert tr.adv == [7] and len(tr.calls) == 6
+    assert all(c["channels"] is None for c in tr.calls[:3])
+    for c in tr.calls[3:]:
+        assert c["channels"].shape == (4,) and c["channels"][:2].tolist() == [0, 0] and (c["channels"][2:] > 0).all()
