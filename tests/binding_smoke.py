@@ -82,6 +82,14 @@ for impl in ("fft", "tc"):
     for pad in ("zero", "repeat", "silence"):
         m.extract(waves, lengths=ragged, feat_len=750, padding=pad, layout="ecapa")
 
+# wrappers only the GPU parity tests call directly
+bf = torch.bfloat16
+ops.pack3x3(torch.zeros(64, 3, 3, 64), 64, 64, 0, torch.zeros(9 * 64 * 64, dtype=bf))
+ops.pack_patch(torch.zeros(64, 1, 64), 64, 64, 1, 1, torch.zeros(64 * 64, dtype=bf))
+ops.conv3x3_wgrad_patch(torch.zeros(2, 4, 128, 64, dtype=bf), 64, 2, 4, 128, 64, torch.zeros(2, 4, 128, 64, dtype=bf), 64, 64,
+                        torch.zeros(64, 9 * 64))
+ops.pack_weights(torch.zeros(64, 9, 64), 0, 64, 64, 9)
+
 # detection metrics
 r = em.det(torch.randn(50), torch.randn(70) - 1, c1=1.0, c2=2.0, curves=True)
 em.det(torch.randn(50).double(), torch.randn(70).double(), negate=True)
