@@ -24,7 +24,7 @@ def _declarations(header=HEADER):
         text = f.read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     out = []
-    for m in re.finditer(r"\b(int|long long)\s+(air_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+    for m in re.finditer(r"\b(int|long long|const char\s*\*)\s*(air_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
         params = [p.strip() for p in m.group(3).replace("\n", " ").split(",")]
         out.append((m.group(1), m.group(2), [] if params in (["void"], [""]) else params))
     return out
@@ -56,7 +56,8 @@ def lib():
         _lib = ctypes.CDLL(LIB_PATH)
         for ret, name, params in _declarations():          # restype AND argtypes from the header: a wrong Python
             fn = getattr(_lib, name)                       # argument raises ctypes.ArgumentError instead of being
-            fn.restype = ctypes.c_longlong if ret == "long long" else ctypes.c_int      # truncated to a 32-bit int
+            fn.restype = (ctypes.c_longlong if ret == "long long" else ctypes.c_char_p if "char" in ret
+                          else ctypes.c_int)                                            # truncated to a 32-bit int
             fn.argtypes = [_ctype_of(p) for p in params]
     return _lib
 
@@ -68,7 +69,11 @@ def check(status, what, n=1):
     LAUNCHES[0] += n
     if status != 0:
         kind = "argument error" if status < 0 else "CUDA error"
-        raise AirError("%s failed: %s %d" % (what, kind, status))
+        try:
+            detail = lib().air_last_error_string().decode()
+        except Exception:                                   # never mask the original failure
+            detail = ""
+        raise AirError("%s failed: %s %d (%s)" % (what, kind, status, detail))
 
 
 def ptr(t):

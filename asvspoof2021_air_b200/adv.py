@@ -12,8 +12,8 @@ them: a gradient-reversal layer and a two-layer MLP on the 256-d embedding, trai
 The two nn.Linear run on air_linear_fwd / air_linear_bwd, the rest on csrc/adv.cu; parameters live in one flat fp32
 buffer with Adam moments beside it, exposed under the reference's state_dict keys (classifier.0.*, classifier.3.*).
 
-STATUS: the kernels compile and the arithmetic is pinned on the CPU (oracle/adv_oracle.py against the reference
-module); tests/test_adv_gpu.py has not run on hardware yet, and main_train.py keeps rejecting --ADV_AUG until it has.
+Pinned on the CPU by oracle/adv_oracle.py against the reference module and on a B200 by tests/test_adv_gpu.py
+(golden from the reference, oracle with an injected dropout mask, mask statistics, Adam step, inside a train step).
 """
 import math
 
@@ -128,7 +128,8 @@ class ChannelClassifier(nn.Module):
         gradient-reversed -lambda * dCE/dfeats into `dfeat` (the encoder's feature gradient, (B, enc_dim) fp32)."""
         w = self._forward_backward(feats, labels, keep_mask, seed, want_dx=True, want_param_grads=False)
         ops.sgd_step(dfeat, w["dx"], dfeat.numel(), self.lambda_)         # dfeat -= lambda * dx  (GRL, model.py:990-994)
-        return w["loss"], w["correct"]
+        # copies: the work buffers are overwritten by the classifier pass of the same train step
+        return w["loss"].clone(), w["correct"].clone()
 
     def classifier_step(self, feats, labels, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0005, keep_mask=None, seed=0,
                         group=None):
@@ -144,7 +145,7 @@ class ChannelClassifier(nn.Module):
         self.step_count += 1
         ops.adam_l2_step(self.flat, self.grad, self.m, self.v, self.flat.numel(), lr, beta1, beta2, eps, weight_decay,
                          self.step_count, scale)
-        return w["loss"], w["correct"]
+        return w["loss"].clone(), w["correct"].clone()
 
     def forward(self, x):
         """Eval-style logits (validation, main_train.py:560-566): relu(W2 relu(W1 x + b1) + b2), no dropout, no grad."""

@@ -672,12 +672,15 @@ extern "C" int air_audio_decode_batch_f32(const char* const* paths, int n, float
 }
 
 // Rows of a (pinned) float matrix from a packed int16 corpus (data.PackedWaves): row i = blob[offsets[i] ..
-// offsets[i] + min(lengths[i], ld)) * 2^-15, zero-padded to ld.  Memory-bound; `threads` host threads (<= 0: all).
-extern "C" int air_audio_gather_i16_f32(const short* blob, const long long* offsets, const int* lengths, int n,
-                                        float* out, long long ld, int threads) {
-  if (!blob || !offsets || !lengths || n < 0 || !out || ld < 1) return AIR_ERR_ARG;
-  for (int i = 0; i < n; ++i) if (offsets[i] < 0 || lengths[i] < 0) return AIR_ERR_ARG;
+// offsets[i] + min(lengths[i], ld)) * 2^-15, zero-padded to ld.  `blob_samples` bounds every (offset, length) pair -- a
+// stale index must not read past the mapping.  Memory-bound; `threads` host threads (<= 0: all, capped at 16).
+extern "C" int air_audio_gather_i16_f32(const short* blob, long long blob_samples, const long long* offsets,
+                                        const int* lengths, int n, float* out, long long ld, int threads) {
+  if (!blob || blob_samples < 0 || !offsets || !lengths || n < 0 || !out || ld < 1) return AIR_ERR_ARG;
+  for (int i = 0; i < n; ++i)
+    if (offsets[i] < 0 || lengths[i] < 0 || offsets[i] > blob_samples || lengths[i] > blob_samples - offsets[i]) return AIR_ERR_ARG;
   if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+  if (threads > 16) threads = 16;
   if (threads < 1) threads = 1;
   if (threads > n) threads = n;
   std::atomic<int> next{0};
@@ -693,12 +696,17 @@ extern "C" int air_audio_gather_i16_f32(const short* blob, const long long* offs
       memset(row + k, 0, (size_t)(ld - k) * sizeof(float));
     }
   };
-  if (threads <= 1) {
-    work();
-  } else {
+  if (threads > 1) {
     std::vector<std::thread> pool;
-    for (int t = 0; t < threads; ++t) pool.emplace_back(work);
+    try {
+      for (int t = 1; t < threads; ++t) pool.emplace_back(work);
+    } catch (...) {
+      // thread creation failed (resource limits): the calling thread and the workers that did start drain the queue
+    }
+    work();
     for (auto& t : pool) t.join();
+  } else {
+    work();
   }
   return AIR_OK;
 }

@@ -6,10 +6,18 @@
 
 #include "air_b200.h"   // status codes; and every extern "C" definition is checked against its public declaration
 
+// Every non-zero status leaves a per-thread record (status, source line) behind for air_last_error_string() (capi.cu):
+// inside the kernel sources the two argument-error codes expand to a call that notes where they were returned.
+extern "C" int air_internal_note_status(int status, const char* file, int line);
+#undef AIR_ERR_ARG
+#define AIR_ERR_ARG air_internal_note_status(-1, __FILE__, __LINE__)
+#undef AIR_ERR_UNSUPPORTED
+#define AIR_ERR_UNSUPPORTED air_internal_note_status(-2, __FILE__, __LINE__)
+
 // Launch-error check used by every entry point: asynchronous, no device sync.
 static inline int air_launch_status() {
   cudaError_t e = cudaGetLastError();
-  return e == cudaSuccess ? AIR_OK : (int)e;
+  return e == cudaSuccess ? AIR_OK : air_internal_note_status((int)e, nullptr, 0);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

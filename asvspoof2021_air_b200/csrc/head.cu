@@ -337,7 +337,15 @@ extern "C" int air_ocsoftmax_fwd_bwd(const float* x, const long long* labels, co
                                      const float* logits, int ncls, float* ce, cudaStream_t stream) {
   if (!x || !center || B <= 0 || D <= 0) return AIR_ERR_ARG;
   const size_t smem = (static_cast<size_t>(D) + 3 * static_cast<size_t>(B) + 32) * sizeof(float);
-  if (smem > 48 * 1024) return AIR_ERR_UNSUPPORTED;
+  if (smem > 200 * 1024) return AIR_ERR_UNSUPPORTED;          // B <= ~17 000 at D = 256; callers chunk above that
+  if (smem > 48 * 1024) {
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaError_t e = cudaFuncSetAttribute(ocsoftmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      attr_done = true;
+    }
+  }
   ocsoftmax_kernel<<<1, 256, smem, stream>>>(x, labels, center, B, D, r_real, r_fake, alpha, grad_scale,
                                               loss, score, dfeat, dcenter, logits, ncls, ce);
   return air_launch_status();

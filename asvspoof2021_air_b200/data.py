@@ -166,6 +166,13 @@ class PackedWaves:
         self.blob = np.memmap(prefix + ".i16", dtype=np.int16, mode="r")
         if self.blob.shape[0] != m["samples"]:
             raise ValueError("%s.i16 holds %d samples, the index announces %d" % (prefix, self.blob.shape[0], m["samples"]))
+        if len(self.offsets) != len(self.names) or len(self.lengths) != len(self.names):
+            raise ValueError("%s.json: %d names, %d offsets, %d lengths" % (prefix, len(self.names), len(self.offsets), len(self.lengths)))
+        bad = (self.offsets < 0) | (self.lengths < 0) | (self.offsets + self.lengths > self.blob.shape[0])
+        if bad.any():                                        # a stale / corrupt index must not read outside the mapping
+            raise ValueError("%s.json: item %d (offset %d, length %d) lies outside the %d samples of the corpus"
+                             % (prefix, int(np.argmax(bad)), int(self.offsets[np.argmax(bad)]), int(self.lengths[np.argmax(bad)]),
+                                self.blob.shape[0]))
         self.items = list(zip(self.names, self.labels.tolist()))
         self.feat_len, self.threads = feat_len, threads
         self.rng = np.random.RandomState(seed)
@@ -182,7 +189,8 @@ class PackedWaves:
         if pinned is None:
             pinned = torch.cuda.is_available() if self.PIN is None else self.PIN
         waves = torch.empty(len(idx), int(lens.max()), pin_memory=pinned)
-        st = _lib.lib().air_audio_gather_i16_f32(ctypes.c_void_p(self.blob.ctypes.data), offs.ctypes.data_as(ctypes.c_void_p),
+        st = _lib.lib().air_audio_gather_i16_f32(ctypes.c_void_p(self.blob.ctypes.data), _lib.LL(self.blob.shape[0]),
+                                                 offs.ctypes.data_as(ctypes.c_void_p),
                                                  lens.ctypes.data_as(ctypes.c_void_p), len(idx), ctypes.c_void_p(waves.data_ptr()),
                                                  _lib.LL(waves.stride(0)), int(self.threads))
         if st != 0:

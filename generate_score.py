@@ -39,6 +39,9 @@ def build_parser():
     new.add_argument("--batch_size", type=int, default=1024)
     new.add_argument("--feat_len", type=int, default=750)
     new.add_argument("--padding", type=str, default="repeat", choices=["zero", "repeat", "silence"])
+    new.add_argument("--attention_noise", action="store_true",
+                     help="resnet: add SelfAttention's 1e-5 * randn (resnet.py:38-42) as the reference does even when "
+                          "scoring; off by default so that score files are reproducible")
     return p
 
 
@@ -72,6 +75,9 @@ def _device():
     return torch.device("cuda", torch.cuda.current_device())
 
 
+MAX_BATCH = 16384        # air_ocsoftmax_fwd_bwd: (D + 3B + 32) floats of shared memory, 200 KB limit at D = 256
+
+
 def test_on_ASVspoof2021(task, feat_model_path, loss_model_path, output_score_path, model_name, add_loss, args):
     from asvspoof2021_air_b200 import data
     from asvspoof2021_air_b200.trainer import Trainer
@@ -79,12 +85,15 @@ def test_on_ASVspoof2021(task, feat_model_path, loss_model_path, output_score_pa
         raise SystemExit("only -l ocsoftmax is implemented on the fused path (SURVEY.md section 2.1)")
     if not torch.cuda.is_available():
         raise SystemExit("generate_score.py needs a CUDA device: the fused path has no CPU fallback")
+    if not 1 <= args.batch_size <= MAX_BATCH:
+        raise SystemExit("--batch_size must be in [1, %d] (one OC-Softmax launch holds the whole batch on one SM)" % MAX_BATCH)
     from asvspoof2021_air_b200 import compat
     model = compat.load_module(feat_model_path)              # this package's pickles and the reference's own
     loss_model = compat.load_module(loss_model_path)
     arch = "ecapa" if type(model).__name__ == "Res2Net2" else "resnet"
     tr = Trainer(arch=arch, enc_dim=loss_model.center.shape[1], feat_len=args.feat_len, padding=args.padding,
-                 r_real=loss_model.r_real, r_fake=loss_model.r_fake, alpha=loss_model.alpha, device="cuda")
+                 r_real=loss_model.r_real, r_fake=loss_model.r_fake, alpha=loss_model.alpha, device="cuda",
+                 attention_noise=args.attention_noise)
     tr.load_modules(model, loss_model)
     if args.packed_waves:
         src = data.PackedWaves(args.packed_waves, args.feat_len)

@@ -34,6 +34,14 @@ typedef struct CUstream_st* air_stream_t; /* == cudaStream_t */
 
 /* Library version (major*10000 + minor*100 + patch). */
 int air_version(void);
+/* Static description of a status code returned by any entry point (AIR_ERR_* name and meaning, or the CUDA runtime's
+ * text for a positive cudaError_t).  The reference reports errors as Python exceptions; the
+ * binding raises AirError with this text. */
+const char* air_status_string(int status);
+/* The most recent non-zero status returned to the CALLING THREAD by a device entry point, with the source line of the
+ * check that rejected the call ("status -2 at conv_patch.cu:447: AIR_ERR_UNSUPPORTED ...").  The pointer stays valid
+ * until the next call of this function on the same thread. */
+const char* air_last_error_string(void);
 
 /* ---------------------------------------------------------------------------------------------
  * LFCC front-end.  Replaces LFCC.forward (feature_extraction.py:93-138: pre-emphasis, torch.stft
@@ -390,8 +398,9 @@ int air_audio_decode_i32(const char* path, int* out, long long capacity, long lo
 int air_audio_decode_batch_f32(const char* const* paths, int n, float* out, long long ld, int* lengths,
                                int* sample_rates, int* status, int threads, int flags);
 /* rows of a (pinned) float matrix from a packed int16 corpus: row i = blob[offsets[i] .. + min(lengths[i], ld)) / 32768,
- * zero-padded to ld (asvspoof2021_air_b200/data.py PackedWaves; decode once, train many epochs) */
-int air_audio_gather_i16_f32(const short* blob, const long long* offsets, const int* lengths, int n,
+ * zero-padded to ld (asvspoof2021_air_b200/data.py PackedWaves; decode once, train many epochs).  blob_samples = size of
+ * the mapping in samples: every (offset, length) pair is checked against it (AIR_ERR_ARG). */
+int air_audio_gather_i16_f32(const short* blob, long long blob_samples, const long long* offsets, const int* lengths, int n,
                              float* out, long long ld, int threads);
 
 

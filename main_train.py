@@ -9,8 +9,10 @@ checkpoints `checkpoint/anti-spoofing_{feat,loss}_model_%d.pt`, best-dev copies 
 lr * lr_decay^(epoch // interval), --continue_training (model + loss module only, main_train.py:172-173).
 New flags: --synthetic N (seeded synthetic utterances per epoch), --wave_dir / --protocol (+ --dev_*) for raw
 audio, --steps_per_epoch, --log_every.  Out of the hot-path scope and rejected at run time with a clear
-message: models other than resnet / ecapa, --add_loss other than ang_iso, --ADV_AUG, --visualize
-(SURVEY.md section 2.1).
+message: models other than resnet / ecapa, --add_loss other than ang_iso, --visualize.
+--ADV_AUG (main_train.py:211-224,377-453) runs from raw waves: --wave_dir + --aug_wave_dir + --protocol, or a packed
+corpus of them.  Deviation: validation uses the plain dev source (--dev_*); the reference validates on the augmented
+dev set and logs the channel accuracy there (main_train.py:489-577), which needs the augmented dev audio.
 """
 import argparse
 import json
@@ -91,6 +93,8 @@ def build_parser():
     new.add_argument("--dev_protocol", type=str, default=None)
     new.add_argument("--steps_per_epoch", type=int, default=0, help="0: one pass over the source")
     new.add_argument("--log_every", type=int, default=50, help="steps between host reads of the device losses")
+    new.add_argument("--attention_noise", type=str2bool, nargs="?", const=True, default=True,
+                     help="resnet: the 1e-5 * randn of SelfAttention's pooled std (resnet.py:38-42), drawn on device")
     return parser
 
 
@@ -133,9 +137,6 @@ def _reject_out_of_scope(args):
         if not ((args.wave_dir and args.aug_wave_dir and args.protocol) or args.packed_waves):
             raise SystemExit("--ADV_AUG trains from raw waves: pass --wave_dir (originals), --aug_wave_dir and --protocol, "
                              "or --packed_waves of a corpus packed from them")
-        if os.environ.get("AIR_ADV_UNVALIDATED") != "1":
-            raise SystemExit("--ADV_AUG: the channel-classifier head is built (asvspoof2021_air_b200/adv.py) but its GPU "
-                             "parity test has not run on hardware yet; set AIR_ADV_UNVALIDATED=1 to use it anyway")
     if args.feat != "LFCC":
         raise SystemExit("only --feat LFCC is implemented (computed on device from raw waves)")
 
@@ -193,7 +194,7 @@ def train(args):
     tr = Trainer(arch=args.model, enc_dim=args.enc_dim, feat_len=args.feat_len, padding=args.padding, lr=args.lr,
                  beta_1=args.beta_1, beta_2=args.beta_2, eps=args.eps, weight_decay=0.0005, r_real=args.r_real,
                  r_fake=args.r_fake, alpha=args.alpha, weight_loss=args.weight_loss, device="cuda", process_group=pg,
-                 seed=args.seed)
+                 seed=args.seed, attention_noise=args.attention_noise)
     if args.continue_training:                                            # main_train.py:172-173
         from asvspoof2021_air_b200 import compat
         model = compat.load_module(os.path.join(args.out_fold, "anti-spoofing_feat_model.pt"))
@@ -207,6 +208,9 @@ def train(args):
     steps = args.steps_per_epoch or max(1, len(src) // (per_rank * world))
     adv = bool(args.ADV_AUG)
     if adv:                                                               # main_train.py:211-224
+        if not getattr(src, "channel_names", None):
+            raise SystemExit("--ADV_AUG: the training source carries no channel labels (a corpus packed without "
+                             "--aug_wave_dir?); pack originals + augmented copies together or pass --wave_dir/--aug_wave_dir")
         heads = [len(src.channel_names)] + ([len(src.device_names)] if src.device_names else [])
         tr.attach_adversaries(heads, lambda_=args.lambda_, lr_d=args.lr_d, seed=args.seed)
         steps = args.steps_per_epoch or max(1, src.n_ori // max(1, int(per_rank * args.ratio) * world))
@@ -228,14 +232,18 @@ def train(args):
         # decode / collate / H2D of the next batches run on a host thread + copy stream while this step computes
         for step, batch in enumerate(data.Prefetcher(src, order, depth=2, device=device)):
             waves, lengths, labels, _, start = batch
-            adv_now = adv and epoch > 0                                   # main_train.py:377: the adversaries join after epoch 0
+            # main_train.py:377 / :420: the gradient-reversed term joins after epoch 0; the classifier's own step (second
+            # forward on detached features) runs in every epoch, epoch 0 included
+            adv_now = adv and epoch > 0
             loss = tr.train_step(waves, labels, lengths=lengths, start=start, lr=lr,
-                                 channels=batch.channels if adv_now else None, step_seed=epoch * steps + step)
+                                 channels=batch.channels if adv else None, step_seed=epoch * steps + step, grl=adv_now)
             rec = [step, loss.clone()]
-            if adv_now:                                                   # main_train.py:471-477
-                right_m += tr.adv_stats[0][1]
+            if adv:                                                       # main_train.py:428-429 (every epoch)
                 right_c += tr.adv_stats_c[0][1]
-                seen_m, seen_c = seen_m + waves.shape[0], seen_c + waves.shape[0]
+                seen_c += waves.shape[0]
+            if adv_now:                                                   # main_train.py:383-384,471-477
+                right_m += tr.adv_stats[0][1]
+                seen_m += waves.shape[0]
                 rec += [sum(s[0] for s in tr.adv_stats).clone(), right_m.clone(), seen_m, right_c.clone(), seen_c]
             pending.append(rec)
             if len(pending) >= args.log_every or step == steps - 1:

@@ -22,6 +22,28 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert st == -1
 
 
+def test_last_error_string_names_the_rejecting_check():
+    """air_last_error_string (SURVEY.md section 8b minimum export set): per-thread record of the last non-zero status."""
+    import threading
+    lib = _lib.lib()
+    assert "air_last_error_string" in _lib.declared_symbols() and "air_status_string" in _lib.declared_symbols()
+    assert lib.air_status_string(0) == b"AIR_OK" and lib.air_status_string(-2).startswith(b"AIR_ERR_UNSUPPORTED")
+    seen = {}
+    t = threading.Thread(target=lambda: seen.setdefault("fresh", lib.air_last_error_string()))
+    t.start(); t.join()
+    assert seen["fresh"] == b"no error recorded on this thread"
+    st = lib.air_lfcc_fwd(None, _lib.LL(0), None, 0, 0, None, None, _lib.LL(0), _lib.LL(0), _lib.LL(0),
+                          0, 0, 0, 0, None, None, ctypes.c_float(0.97), 0, None)
+    msg = lib.air_last_error_string().decode()
+    assert st == -1 and msg.startswith("status -1 at lfcc.cu:") and "AIR_ERR_ARG" in msg
+    try:
+        _lib.check(st, "air_lfcc_fwd")
+    except _lib.AirError as e:
+        assert "lfcc.cu:" in str(e)
+    else:
+        raise AssertionError("check() must raise")
+
+
 def test_det_and_audio_entry_points_validate_arguments_without_a_gpu():
     lib = _lib.lib()
     n = ctypes.c_longlong(0)
@@ -46,7 +68,7 @@ def _header_signatures():
     with open(_lib.HEADER) as f:
         text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
     sigs = {}
-    for m in re.finditer(r"\b(?:int|long long)\s+(air_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+    for m in re.finditer(r"\b(?:int|long long|const char\s*\*)\s*(air_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
         params = [p.strip() for p in m.group(2).replace("\n", " ").split(",")]
         sigs[m.group(1)] = [] if params == ["void"] or params == [""] else params
     return sigs

@@ -101,3 +101,38 @@ def test_train_and_score_from_a_flac_folder(tmp_path):
     assert [x[0] for x in rows] == ["LA_T_%07d" % i for i in range(12)]
     assert [x[2] for x in rows] == ["bonafide" if i % 2 == 0 else "spoof" for i in range(12)]
     assert all(-1.0001 <= float(x[1]) <= 1.0001 for x in rows)
+
+
+def test_adversarial_training_cli(tmp_path):
+    """(f) row 4 end to end: `main_train.py --ADV_AUG --LA_aug` on a folder of originals + channel-augmented copies.
+    Epoch 0: three-column log (the classifier trains on detached features, main_train.py:420-453); epoch 1: the
+    gradient-reversed term joins and the log carries adv loss and both accuracies (main_train.py:377,471-477)."""
+    import wave
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    from asvspoof2021_air_b200 import data
+    ch, _ = data.channel_tables("LA")
+    ori, aug = tmp_path / "ori", tmp_path / "aug"
+    ori.mkdir(); aug.mkdir()
+    rng = np.random.RandomState(1)
+    proto = []
+    for i in range(8):
+        x = (rng.randn(20000 + 500 * i) * 3000).astype(np.int16)
+        for folder, name in [(ori, "LA_T_%d" % i)] + [(aug, "LA_T_%d_%s" % (i, ch[1 + (2 * i + k) % (len(ch) - 1)])) for k in range(2)]:
+            with wave.open(str(folder / (name + ".wav")), "wb") as f:
+                f.setnchannels(1); f.setsampwidth(2); f.setframerate(16000); f.writeframes(x.tobytes())
+        proto.append("LA_0001 LA_T_%d - - %s" % (i, "bonafide" if i % 2 == 0 else "spoof"))
+    (tmp_path / "p.txt").write_text("\n".join(proto) + "\n")
+    out = tmp_path / "m"
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "main_train.py"), "-o", str(out), "-m", "resnet", "--add_loss", "ang_iso",
+                        "--gpu", "0", "--ADV_AUG", "--LA_aug", "--wave_dir", str(ori), "--aug_wave_dir", str(aug), "--protocol",
+                        str(tmp_path / "p.txt"), "--batch_size", "4", "--num_epochs", "2", "--log_every", "1", "--lr_d", "0.001"],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    lines = [ln.split("\t") for ln in open(out / "train_loss.log").read().strip().splitlines()[1:]]
+    assert [len(x) for x in lines] == [3] * 4 + [6] * 4, lines
+    for e, s, adv_loss, acc_m, acc_c, loss in lines[4:]:
+        assert e == "1" and 0.0 < float(adv_loss) < 20.0 and 0.0 <= float(acc_m) <= 100.0 and 0.0 <= float(acc_c) <= 100.0
+        assert float(loss) == float(loss)
+    assert os.path.exists(out / "checkpoint" / "anti-spoofing_feat_model_2.pt")

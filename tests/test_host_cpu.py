@@ -484,12 +484,13 @@ class _FakeTrainer:
     def attach_adversaries(self, class_counts, lambda_=0.05, lr_d=1e-4, seed=None):
         self.adv, self.lr_d, self.lambda_ = list(class_counts), lr_d, lambda_
 
-    def train_step(self, waves, labels, lengths=None, start=None, lr=None, channels=None, step_seed=0):
+    def train_step(self, waves, labels, lengths=None, start=None, lr=None, channels=None, step_seed=0, grl=True):
         self.calls.append(dict(B=waves.shape[0], lr=lr, lr_d=self.lr_d, channels=None if channels is None else channels.clone(),
-                               ragged=lengths is not None, seed=step_seed))
+                               ragged=lengths is not None, seed=step_seed, grl=grl))
         if channels is not None:
             n = len(self.adv)
-            self.adv_stats = [(torch.tensor([0.5 + i], dtype=torch.float64), torch.tensor([1], dtype=torch.int32)) for i in range(n)]
+            self.adv_stats = [(torch.tensor([0.5 + i], dtype=torch.float64), torch.tensor([1], dtype=torch.int32))
+                              for i in range(n)] if grl else []
             self.adv_stats_c = [(torch.tensor([0.25]), torch.tensor([2], dtype=torch.int32)) for _ in range(n)]
         return torch.tensor([float(len(self.calls))])
 
@@ -555,23 +556,32 @@ def test_training_cli_loop_dry_run_adversarial_path(monkeypatch, tmp_path):
     argv = ["-o", str(tmp_path / "m"), "-m", "ecapa", "--add_loss", "ang_iso", "--ADV_AUG", "--LAPA_aug", "--wave_dir", str(ori),
             "--aug_wave_dir", str(aug), "--protocol", str(tmp_path / "p.txt"), "--batch_size", "4", "--num_epochs", "2",
             "--interval", "1", "--lr_d", "0.01", "--lambda_", "0.3", "--log_every", "1"]
-    monkeypatch.delenv("AIR_ADV_UNVALIDATED", raising=False)
-    with pytest.raises(SystemExit, match="has not run on hardware"):
-        _cli_dry_run(monkeypatch, argv)
     with pytest.raises(SystemExit, match="exactly one of"):
         _cli_dry_run(monkeypatch, argv + ["--DF_aug"])
-    monkeypatch.setenv("AIR_ADV_UNVALIDATED", "1")
     tr = _cli_dry_run(monkeypatch, argv)
     assert tr.adv == [60, 13] and tr.lambda_ == 0.3
     assert len(tr.calls) == 8 and all(c["B"] == 4 for c in tr.calls)                       # 8 originals / int(4 * 0.5) per epoch
-    assert all(c["channels"] is None for c in tr.calls[:4])                               # epoch 0: no adversaries yet
-    for c in tr.calls[4:]:
+    # epoch 0: the classifiers already train on the detached features (main_train.py:420-453), only the gradient-reversed
+    # term waits for epoch 1 (main_train.py:377)
+    assert [c["grl"] for c in tr.calls] == [False] * 4 + [True] * 4
+    for c in tr.calls:
         assert c["channels"].shape == (4, 2) and c["channels"][:2].tolist() == [[0, 12], [0, 12]]      # originals first
-        assert (c["channels"][2:, 0] > 0).all() and (c["channels"][2:, 1] < 12).all() and c["lr_d"] == 0.005
+        assert (c["channels"][2:, 0] > 0).all() and (c["channels"][2:, 1] < 12).all()
+    assert [c["lr_d"] for c in tr.calls] == [0.01] * 4 + [0.005] * 4
     lines = open(tmp_path / "m" / "train_loss.log").read().strip().splitlines()
     assert [len(ln.split("\t")) for ln in lines[1:]] == [3] * 4 + [6] * 4
     e, s, adv_loss, acc_m, acc_c, loss = lines[5].split("\t")
     assert (e, s, float(adv_loss), float(acc_m), float(acc_c), float(loss)) == ("1", "0", 2.0, 25.0, 50.0, 5.0)
+
+
+def test_adversarial_statistics_do_not_alias_the_work_buffers():
+    """head_loss_and_feat_grad / classifier_step hand out copies: the classifier pass of the same train step re-uses the
+    per-batch work buffers, so an alias would make the logged adversarial loss the classifier's."""
+    import inspect
+    from asvspoof2021_air_b200 import adv
+    for fn in (adv.ChannelClassifier.head_loss_and_feat_grad, adv.ChannelClassifier.classifier_step):
+        src = inspect.getsource(fn)
+        assert 'return w["loss"].clone(), w["correct"].clone()' in src
 
 
 def test_scoring_cli_loop_dry_run(monkeypatch, tmp_path):
@@ -742,6 +752,21 @@ def test_packed_corpus_round_trip_and_threaded_gather(tmp_path):
     (tmp_path / "p2.txt").write_text("f bonafide\n")
     with pytest.raises(ValueError, match="not 16-bit"):
         data.pack_folder(data.WaveFolder(str(tmp_path), str(tmp_path / "p2.txt")), str(tmp_path / "c2"))
+    # a stale index (an item reaching past the blob) is refused at load time and by the native gather itself
+    import json, ctypes
+    from asvspoof2021_air_b200 import _lib
+    good = json.load(open(tmp_path / "corpus.json"))
+    stale = dict(good, lengths=good["lengths"][:-1] + [good["lengths"][-1] + 5])
+    json.dump(stale, open(tmp_path / "corpus.json", "w"))
+    with pytest.raises(ValueError, match="lies outside"):
+        data.PackedWaves(str(tmp_path / "corpus"))
+    json.dump(good, open(tmp_path / "corpus.json", "w"))
+    pk = data.PackedWaves(str(tmp_path / "corpus"))
+    offs, lens = np.array([good["samples"] - 3], dtype=np.int64), np.array([4], dtype=np.int32)
+    row = np.zeros(8, dtype=np.float32)
+    assert _lib.lib().air_audio_gather_i16_f32(ctypes.c_void_p(pk.blob.ctypes.data), _lib.LL(pk.blob.shape[0]),
+                                               offs.ctypes.data_as(ctypes.c_void_p), lens.ctypes.data_as(ctypes.c_void_p), 1,
+                                               row.ctypes.data_as(ctypes.c_void_p), _lib.LL(8), 1) == -1
     with open(tmp_path / "corpus.i16", "ab") as f:
         f.write(b"\x00\x00")
     with pytest.raises(ValueError, match="announces"):
@@ -771,10 +796,9 @@ def test_training_cli_dry_run_from_packed_corpora(monkeypatch, tmp_path):
                                     "--num_epochs", "1"])
     assert [c["B"] for c in tr.calls] == [3, 3] and all(c["ragged"] for c in tr.calls)
     assert open(tmp_path / "m1" / "dev_loss.log").read().strip().splitlines()[1] == "0\t2.0\t0.125"
-    monkeypatch.setenv("AIR_ADV_UNVALIDATED", "1")
     tr = _cli_dry_run(monkeypatch, ["-o", str(tmp_path / "m2"), "-m", "resnet", "--add_loss", "ang_iso", "--ADV_AUG", "--DF_aug",
                                     "--packed_waves", str(tmp_path / "adv"), "--batch_size", "4", "--num_epochs", "2"])
     assert tr.adv == [7] and len(tr.calls) == 6
-    assert all(c["channels"] is None for c in tr.calls[:3])
-    for c in tr.calls[3:]:
+    assert [c["grl"] for c in tr.calls] == [False] * 3 + [True] * 3
+    for c in tr.calls:
         assert c["channels"].shape == (4,) and c["channels"][:2].tolist() == [0, 0] and (c["channels"][2:] > 0).all()
