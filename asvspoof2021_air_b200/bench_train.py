@@ -31,6 +31,26 @@ def _waves(B, seed):
     return 0.1 * torch.randn(B, WAVE_LEN, generator=g)
 
 
+NBUF = 2
+NAMES = {"resnet": "ResNet-18-OC", "ecapa": "ECAPA-TDNN-512"}
+
+
+def workload_config(workload, B, world, overlap=None):
+    """The `config` object of the JSON line -- shared by this arm and `--impl reference` (which times a bounded sample of
+    the SAME workload: the driver compares the two configs)."""
+    arch = "resnet" if workload.startswith("resnet") else "ecapa"
+    scoring = workload.endswith("_score")
+    if overlap is None:
+        overlap = os.environ.get("AIR_OVERLAP_WGRAD", "1") != "0"
+    return {"workload": "%s: wave->LFCC->%s %s + OC-Softmax%s, B=%d/GPU, 4 s @ 16 kHz, feat_len 750 (repeat pad)"
+                        % (workload, NAMES[arch], "eval forward" if scoring else "fwd/bwd",
+                           "" if scoring else " + Adam(L2)/SGD", B),
+            "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
+            "l2": "per-step activations (> 4 GB) exceed the 126 MB L2; waves rotate over %d buffers" % NBUF,
+            "streams": "weight-gradient kernels on a side stream (overlap the HBM-bound BatchNorm backward); the "
+                       "roofline / per-family pass runs serialised" if (overlap and not scoring) else "single stream"}
+
+
 def run(args, rank, world, helpers):
     from . import _lib, ops
     from .trainer import Trainer
@@ -42,7 +62,7 @@ def run(args, rank, world, helpers):
         import torch.distributed as dist
         pg = dist.group.WORLD
     tr = Trainer(arch=arch, device="cuda", process_group=pg, seed=688)
-    nbuf = 2
+    nbuf = NBUF
     waves = [_waves(B, rank * 16 + i).cuda() for i in range(nbuf)]
     labels = _labels(B, rank).cuda()
 
@@ -122,19 +142,12 @@ def run(args, rank, world, helpers):
                      "kernel": "air_lfcc_tc::lfcc_tc_kernel (fused wave -> padded bf16 model-layout LFCC, inside the step)",
                      "bytes_per_launch": lf["bytes"] / nprof, "ms_per_step": lf["ms"] / nprof}
     flops_per_utt = (FWD_FLOPS_PER_UTT if scoring else TRAIN_FLOPS_PER_UTT)[arch]
-    name = {"resnet": "ResNet-18-OC", "ecapa": "ECAPA-TDNN-512"}[arch]
     line = {
         "metric": "utterances/sec (4 s@16 kHz) %s" % ("scoring" if scoring else "train-step"),
         "value": value, "unit": "utterances/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "%s: wave->LFCC->%s %s + OC-Softmax%s, B=%d/GPU, 4 s @ 16 kHz, feat_len 750 (repeat pad)"
-                   % (args.workload, name, "eval forward" if scoring else "fwd/bwd",
-                      "" if scoring else " + Adam(L2)/SGD", B),
-                   "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
-                   "l2": "per-step activations (> 4 GB) exceed the 126 MB L2; waves rotate over %d buffers" % nbuf,
-                   "streams": "weight-gradient kernels on a side stream (overlap the HBM-bound BatchNorm backward); the "
-                              "roofline / per-family pass runs serialised" if overlap else "single stream"},
+        "config": workload_config(args.workload, B, world, overlap),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak if peak else None,
                      # ncu --set full of the largest launches (profiles/r01_ncu_full_v6_summary.txt): layer-1 3x3 fprop moves
@@ -212,19 +225,85 @@ class _CpuStep:
         return loss.detach()
 
 
+class _RefStep:
+    """The reference ITSELF: the unmodified modules of oracle/_ref (copied there by oracle/build_ref.sh; or the mounted
+    tree) imported under oracle/ref_shim and wired as main_train.py:162-175,338-409 wires them -- feature_extraction.LFCC
+    -> repeat pad (dataset.py:519-522) -> transpose (main_train.py:338,347-348) -> resnet.ResNet / ecapa_tdnn.Res2Net2 ->
+    loss.AngularIsoLoss -> torch.optim.Adam(weight_decay 5e-4) + SGD on the centre; scoring as generate_score.py:84-119."""
+    kind = "reference"
+
+    def __init__(self, arch, scoring, B):
+        import warnings
+        from oracle import ref_shim, state_spec as ss
+        if not ref_shim.use_copy_if_needed():
+            raise ImportError("no reference modules (oracle/_ref is built by oracle/build_ref.sh where /root/reference exists)")
+        fe, ls = ref_shim.load("feature_extraction"), ref_shim.load("loss")
+        torch.manual_seed(688)                                             # main_train.py:26
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            self.lfcc = fe.LFCC(320, 160, 512, 16000, 20, with_energy=False)      # dataset.py:13
+            if arch == "resnet":
+                self.model = ref_shim.load("resnet").ResNet(3, 256, resnet_type="18", nclasses=2)
+            else:
+                ec = ref_shim.load("ecapa_tdnn")
+                self.model = ec.Res2Net2(ec.Bottle2neck, C=512, model_scale=8, nOut=2, n_mels=60)
+        self.loss = ls.AngularIsoLoss(256, r_real=0.9, r_fake=0.2, alpha=20.0)
+        self.arch, self.scoring, self.B = arch, scoring, B
+        self.opt = torch.optim.Adam(self.model.parameters(), lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0005)
+        self.opt_c = torch.optim.SGD(self.loss.parameters(), lr=5e-4)
+        self.waves = ss.seeded_waves(B, WAVE_LEN, seed=0)
+        self.labels = ss.seeded_labels(B, 0)
+        self.model.eval() if scoring else self.model.train()
+
+    def __call__(self):
+        with torch.no_grad():
+            y = self.lfcc(self.waves.clone())                              # the reference pre-emphasises in place
+        idx = torch.arange(750) % y.shape[1]
+        x = y[:, idx].unsqueeze(1).transpose(2, 3)
+        if self.arch == "ecapa":
+            x = x.squeeze(1)
+        if self.scoring:
+            with torch.no_grad():
+                feats, _ = self.model(x)
+                return self.loss(feats, torch.zeros(self.B, dtype=torch.long))[1]
+        feats, outputs = self.model(x)
+        torch.nn.functional.cross_entropy(outputs.detach(), self.labels)   # the logged CE, main_train.py:355-357
+        loss, _ = self.loss(feats, self.labels)
+        self.opt.zero_grad()
+        self.opt_c.zero_grad()
+        loss.backward()
+        self.opt.step()
+        self.opt_c.step()
+        return loss.detach()
+
+
+def _cpu_step(arch, scoring, B):
+    """The reference itself when its modules are present (oracle/_ref), else the oracle port."""
+    try:
+        return _RefStep(arch, scoring, B)
+    except ImportError:
+        st = _CpuStep(arch, scoring, B)
+        st.kind = "port"
+        return st
+
+
 def cpu_baseline(arch, scoring, seconds=15.0, B=8):
     n = os.cpu_count() or 1
     torch.set_num_threads(n)
-    st = _CpuStep(arch, scoring, B)
+    st = _cpu_step(arch, scoring, B)
     st()
     t0, it = time.perf_counter(), 0
     while it < 2 or (time.perf_counter() - t0 < seconds and it < 50):
         st()
         it += 1
     dt = time.perf_counter() - t0
-    return {"value": B * it / dt, "unit": "utterances/s", "cores": n, "kind": "port",
-            "sample": "%d %s steps of B=%d synthetic 4 s waves (torch-CPU fp32 port of the reference: LFCC -> %s -> "
-                      "OC-Softmax%s)" % (it, "scoring" if scoring else "train", B, arch, "" if scoring else " -> Adam/SGD")}
+    return {"value": B * it / dt, "unit": "utterances/s", "cores": n, "kind": st.kind,
+            "sample": "%d %s steps of B=%d synthetic 4 s waves (%s, torch-CPU fp32: LFCC -> %s -> OC-Softmax%s)"
+                      % (it, "scoring" if scoring else "train", B, _KIND_TEXT[st.kind], arch, "" if scoring else " -> Adam/SGD")}
+
+
+_KIND_TEXT = {"reference": "the reference's own modules from oracle/_ref under oracle/ref_shim",
+              "port": "oracle port of the reference"}
 
 
 def run_reference(args, rank, world):
@@ -235,7 +314,7 @@ def run_reference(args, rank, world):
     n = os.cpu_count() or 1
     torch.set_num_threads(n)
     B = 8
-    st = _CpuStep(arch, scoring, B)
+    st = _cpu_step(arch, scoring, B)
     for _ in range(min(args.warmup, 2)):
         st()
     t0 = time.perf_counter()
@@ -247,8 +326,8 @@ def run_reference(args, rank, world):
             "value": v, "unit": "utterances/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%s: reference CPU path (torch fp32 port), bounded sample of B=%d per step"
-                       % (args.workload, B)},
-            "cpu_baseline": {"value": v, "unit": "utterances/s", "cores": n, "kind": "port",
-                             "sample": "%d steps x B=%d" % (args.steps, B)},
+            "config": workload_config(args.workload, args.batch or (1024 if scoring else 256), world),
+            "cpu_baseline": {"value": v, "unit": "utterances/s", "cores": n, "kind": st.kind,
+                             "sample": "%d steps x B=%d utterances of the workload per step (%s; fp32, %d host threads)"
+                                       % (args.steps, B, _KIND_TEXT[st.kind], n)},
             "e2e": {"value": v, "unit": "utterances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

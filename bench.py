@@ -133,12 +133,29 @@ def timed(step_fn, steps, warmup, world):
 
 
 # ----------------------------------------------------------------------------------------------
+def _cpu_lfcc():
+    """(callable, kind): the reference's own LFCC module from oracle/_ref when present, else the oracle port."""
+    from oracle import ref_shim
+    if ref_shim.use_copy_if_needed():
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            mod = ref_shim.load("feature_extraction").LFCC(320, 160, 512, 16000, 20, with_energy=False)
+
+        def run(w):
+            with torch.no_grad():
+                return mod(w.clone())                      # the reference pre-emphasises its input in place
+        return run, "reference"
+    from oracle import lfcc_torch
+    return lfcc_torch.TorchLFCC(), "port"
+
+
 def cpu_lfcc_baseline(seconds=10.0, batch=32):
-    """Oracle port of the reference LFCC (torch fp32, all host threads) on a bounded sample."""
-    from oracle import lfcc_torch, state_spec as ss
+    """The reference LFCC (feature_extraction.py:93-138, torch fp32, all host threads) on a bounded sample."""
+    from oracle import state_spec as ss
     n = os.cpu_count() or 1
     torch.set_num_threads(n)
-    m = lfcc_torch.TorchLFCC()
+    m, kind = _cpu_lfcc()
     w = ss.seeded_waves(batch, WAVE_LEN, seed=0)
     m(w)
     t0, it = time.perf_counter(), 0
@@ -146,8 +163,18 @@ def cpu_lfcc_baseline(seconds=10.0, batch=32):
         m(w)
         it += 1
     dt = time.perf_counter() - t0
-    return {"value": batch * it / dt, "unit": "utterances/s", "cores": n, "kind": "port",
-            "sample": "%d x LFCC of %d synthetic 4 s waves (torch fp32 restatement of feature_extraction.py:93-138)" % (it, batch)}
+    return {"value": batch * it / dt, "unit": "utterances/s", "cores": n, "kind": kind,
+            "sample": "%d x LFCC of %d synthetic 4 s waves (feature_extraction.py:93-138, %s)" % (it, batch, kind)}
+
+
+def lfcc_config(B, nbuf=4):
+    return {"workload": "lfcc: fused wave->LFCC kernel, B=%d/GPU, 4 s @ 16 kHz, fp32 out (B,401,60)" % B,
+            "batch_per_gpu": B, "l2": "inputs rotate over %d buffers (360 MB > L2)" % nbuf}
+
+
+def det_config(n_tar, n_non):
+    return {"workload": "det: EER of %d bona fide + %d spoof scores, both orientations (main_train.py:662-664)" % (n_tar, n_non),
+            "l2": "a 256 MB buffer is rewritten before every timed step (per-step CUDA events, summed)"}
 
 
 def run_lfcc(args, rank, world):
@@ -200,8 +227,7 @@ def run_lfcc(args, rank, world):
         "unit": "utterances/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "lfcc: fused wave->LFCC kernel, B=%d/GPU, 4 s @ 16 kHz, fp32 out (B,401,60)" % B,
-                   "batch_per_gpu": B, "l2": "inputs rotate over %d buffers (360 MB > L2)" % nbuf},
+        "config": lfcc_config(B, nbuf),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"],
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/r01_ncu_full_v6_summary.txt):
@@ -302,8 +328,7 @@ def run_det(args, rank, world):
         "metric": "detection trials/sec (EER, both orientations)", "value": world * n * args.steps / (ms / 1e3),
         "unit": "trials/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 keys / u32 counts", "data": "synthetic",
-        "config": {"workload": "det: EER of %d bona fide + %d spoof scores, both orientations (main_train.py:662-664)" % (n_tar, n_non),
-                   "l2": "a 256 MB buffer is rewritten before every timed step (per-step CUDA events, summed)"},
+        "config": det_config(n_tar, n_non),
         "roofline": {"bound": "hbm", "achieved": algo / per_step_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": algo / per_step_s / 1e9 / peaks["hbm_gbs"], "traffic": None, "peak_src": peaks["src"],
                      "kernel": "air_det:: radix sort (hist / scan / scatter x %d) + curve kernels" % passes,
@@ -330,11 +355,11 @@ def run_reference(args, rank, world):
     if rank != 0:
         return None
     if args.workload == "lfcc":
-        from oracle import lfcc_torch, state_spec as ss
+        from oracle import state_spec as ss
         n = os.cpu_count() or 1
         torch.set_num_threads(n)
         B = 32
-        m = lfcc_torch.TorchLFCC()
+        m, kind = _cpu_lfcc()
         w = ss.seeded_waves(B, WAVE_LEN, seed=0)
         for _ in range(args.warmup):
             m(w)
@@ -346,9 +371,10 @@ def run_reference(args, rank, world):
         return {"impl": "reference", "metric": "LFCC utterances/sec (4 s@16 kHz)", "value": v, "unit": "utterances/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "lfcc: reference CPU path (torch fp32 port), %d waves per step" % B},
-                "cpu_baseline": {"value": v, "unit": "utterances/s", "cores": n, "kind": "port",
-                                 "sample": "%d waves x %d steps" % (B, args.steps)},
+                "config": lfcc_config(args.batch or 256),
+                "cpu_baseline": {"value": v, "unit": "utterances/s", "cores": n, "kind": kind,
+                                 "sample": "%d waves of the workload per step x %d steps (feature_extraction.LFCC, %s)"
+                                           % (B, args.steps, kind)},
                 "e2e": {"value": v, "unit": "utterances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     if args.workload == "det":
         from oracle import metrics_oracle as mo
@@ -366,9 +392,10 @@ def run_reference(args, rank, world):
                 "unit": "trials/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "det: reference CPU path (numpy restatement of eval_metrics.compute_eer)"},
+                "config": det_config(n_tar, n_non),
                 "cpu_baseline": {"value": v, "unit": "trials/s", "cores": 1, "kind": "port",
-                                 "sample": "%d + %d scores x %d steps" % (n_tar, n_non, args.steps)},
+                                 "sample": "%d + %d scores x %d steps (numpy restatement of eval_metrics.compute_eer)"
+                                           % (n_tar, n_non, args.steps)},
                 "e2e": {"value": v, "unit": "trials/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     from asvspoof2021_air_b200 import bench_train
     return bench_train.run_reference(args, rank, world)

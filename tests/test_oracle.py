@@ -273,3 +273,22 @@ def test_adv_classifier_oracle_vs_reference_golden(golden_dir):
             ref = g[p + k]
             assert np.abs(r[k] - ref).max() <= 1e-6 + 1e-4 * np.abs(ref).max(), (C, k)
         assert np.abs(g[p + "dfeat"]).max() > 0        # the reversed gradient really reaches the features
+
+
+def test_reference_copy_for_the_cpu_arm_is_byte_identical():
+    """oracle/_ref (built by oracle/build_ref.sh, git-ignored, travels to the GPU box) holds the reference's own hot-path
+    modules unmodified; bench.py --impl reference imports them under the shim (kind "reference")."""
+    import hashlib
+    import subprocess
+    from oracle import ref_shim
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.isfile("/root/reference/feature_extraction.py"):
+        pytest.skip("reference tree not mounted")
+    subprocess.run(["sh", os.path.join(root, "oracle", "build_ref.sh")], check=True, capture_output=True)
+    assert ref_shim.copy_available()
+    for line in open(os.path.join(ref_shim.REF_COPY, "MANIFEST")).read().strip().splitlines():
+        digest, name = line.split()
+        for base in ("/root/reference", ref_shim.REF_COPY):
+            assert hashlib.sha256(open(os.path.join(base, name), "rb").read()).hexdigest() == digest, (base, name)
+    ignored = subprocess.run(["git", "check-ignore", "oracle/_ref/resnet.py"], cwd=root, capture_output=True, text=True)
+    assert ignored.returncode == 0, "oracle/_ref must stay out of the history"
