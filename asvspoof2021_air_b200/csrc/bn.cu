@@ -18,7 +18,8 @@ constexpr int THREADS = 256;
 // ---------------------------------------------------------------------------------------------
 // per-channel sum / sum of squares:  sums[0..C) += sum_m x[m][c], sums[C..2C) += sum_m x^2
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(THREADS) bn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long ld,
+template <typename T>
+__global__ void __launch_bounds__(THREADS) bn_stats_kernel(const T* __restrict__ x, long long ld,
                                                             long long M, int C, double* __restrict__ sums) {
   extern __shared__ float sh[];                 // [2][THREADS][8]
   const int cpr = C >> 3;                       // 16-byte chunks per row
@@ -31,9 +32,9 @@ __global__ void __launch_bounds__(THREADS) bn_stats_kernel(const __nv_bfloat16* 
     const long long step = static_cast<long long>(gridDim.x) * rows_per_it;
     long long m = static_cast<long long>(blockIdx.x) * rows_per_it + tr;
     for (; m + 3 * step < M; m += 4 * step) {             // four independent 16-byte loads in flight per thread
-      bf16x8 v[4];
+      V8<T> v[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const bf16x8*>(x + (m + u * step) * ld + tc * 8);
+      for (int u = 0; u < 4; ++u) v[u] = ldv8(x + (m + u * step) * ld + tc * 8);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         float f[8];
@@ -43,7 +44,7 @@ __global__ void __launch_bounds__(THREADS) bn_stats_kernel(const __nv_bfloat16* 
       }
     }
     for (; m < M; m += step) {
-      const bf16x8 v = *reinterpret_cast<const bf16x8*>(x + m * ld + tc * 8);
+      const V8<T> v = ldv8(x + m * ld + tc * 8);
       float f[8];
       unpack8(v, f);
 #pragma unroll
@@ -69,14 +70,16 @@ __global__ void __launch_bounds__(THREADS) bn_stats_kernel(const __nv_bfloat16* 
 // (biased variance), block 0 saves mean/invstd and updates the running statistics
 // (momentum, unbiased variance).  eval: running statistics.
 // ---------------------------------------------------------------------------------------------
+template <typename T>
 struct ApplyParams {
-  const __nv_bfloat16* x; long long x_ld; __nv_bfloat16* y; long long y_ld; long long M; int C;
+  const T* x; long long x_ld; T* y; long long y_ld; long long M; int C;
   const double* sums; const float* gamma; const float* beta; float eps; int relu; int training;
   float* save_mean; float* save_invstd; float* running_mean; float* running_var; float momentum;
-  const __nv_bfloat16* add; long long add_ld; __nv_bfloat16* y2; long long y2_ld;   // optional: y2 = y + add
+  const T* add; long long add_ld; T* y2; long long y2_ld;   // optional: y2 = y + add
 };
 
-__global__ void __launch_bounds__(THREADS) bn_apply_kernel(const ApplyParams p) {
+template <typename T>
+__global__ void __launch_bounds__(THREADS) bn_apply_kernel(const ApplyParams<T> p) {
   // thread -> fixed 8-channel chunk tc (scale / shift live in registers), rows strided over the grid
   const int cpr = p.C >> 3;
   const int rows_per_it = THREADS / cpr;
@@ -114,9 +117,9 @@ __global__ void __launch_bounds__(THREADS) bn_apply_kernel(const ApplyParams p) 
   const int c0 = tc * 8;
   if (!p.y2) {
     for (; m + 3 * step < p.M; m += 4 * step) {            // four independent loads in flight before the first store
-      bf16x8 v[4];
+      V8<T> v[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const bf16x8*>(p.x + (m + u * step) * p.x_ld + c0);
+      for (int u = 0; u < 4; ++u) v[u] = ldv8(p.x + (m + u * step) * p.x_ld + c0);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         float f[8];
@@ -126,27 +129,28 @@ __global__ void __launch_bounds__(THREADS) bn_apply_kernel(const ApplyParams p) 
           f[k] = fmaf(f[k], scale[k], shift[k]);
           if (p.relu) f[k] = fmaxf(f[k], 0.f);
         }
-        *reinterpret_cast<bf16x8*>(p.y + (m + u * step) * p.y_ld + c0) = pack8(f);
+        st8(p.y + (m + u * step) * p.y_ld + c0, f);
       }
     }
   }
   for (; m < p.M; m += step) {
     float f[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(p.x + m * p.x_ld + c0), f);
+    unpack8(ldv8(p.x + m * p.x_ld + c0), f);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       f[k] = fmaf(f[k], scale[k], shift[k]);
       if (p.relu) f[k] = fmaxf(f[k], 0.f);
     }
-    const bf16x8 yv = pack8(f);
-    *reinterpret_cast<bf16x8*>(p.y + m * p.y_ld + c0) = yv;
+    V8<T> yv;
+    packv(f, yv);
+    stv8(p.y + m * p.y_ld + c0, yv);
     if (p.y2) {                                   // Res2 branch input: sp_{i} + spx[i+1] (ecapa_tdnn.py:77-80)
       float a[8];
       unpack8(yv, f);                             // the consumer adds the ROUNDED branch output
-      unpack8(*reinterpret_cast<const bf16x8*>(p.add + m * p.add_ld + c0), a);
+      unpack8(ldv8(p.add + m * p.add_ld + c0), a);
 #pragma unroll
       for (int k = 0; k < 8; ++k) f[k] += a[k];
-      *reinterpret_cast<bf16x8*>(p.y2 + m * p.y2_ld + c0) = pack8(f);
+      st8(p.y2 + m * p.y2_ld + c0, f);
     }
   }
 }
@@ -155,16 +159,18 @@ __global__ void __launch_bounds__(THREADS) bn_apply_kernel(const ApplyParams p) 
 // backward, pass 1: rsum[0..C) += sum g, rsum[C..2C) += sum g * xhat
 //   order 0: g = dy * (gamma*xhat + beta > 0)        order 1: g = dy
 // ---------------------------------------------------------------------------------------------
+template <typename T>
 struct BwdParams {
-  const __nv_bfloat16* dy; long long dy_ld; const __nv_bfloat16* x; long long x_ld;
-  const __nv_bfloat16* add; long long add_ld;          // optional extra gradient added to dx
-  __nv_bfloat16* dx; long long dx_ld; long long M; int C; int order;
+  const T* dy; long long dy_ld; const T* x; long long x_ld;
+  const T* add; long long add_ld;          // optional extra gradient added to dx
+  T* dx; long long dx_ld; long long M; int C; int order;
   const float* mean; const float* invstd; const float* gamma; const float* beta;
   double* rsum; float* dgamma; float* dbeta;
   float* dbias;                                        // optional: dbias[c] += sum_m dx[m][c] (bias of the producing conv)
 };
 
-__global__ void __launch_bounds__(THREADS) bn_bwd_reduce_kernel(const BwdParams p) {
+template <typename T>
+__global__ void __launch_bounds__(THREADS) bn_bwd_reduce_kernel(const BwdParams<T> p) {
   extern __shared__ float sh[];                 // [2][THREADS][8]
   const int cpr = p.C >> 3;
   const int rows_per_it = THREADS / cpr;
@@ -182,14 +188,14 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_reduce_kernel(const BwdParams 
     long long m = static_cast<long long>(blockIdx.x) * rows_per_it + tr;
     constexpr int U = 4;                                   // 2 x U independent 16-byte loads in flight per thread
     while (m < p.M) {
-      bf16x8 gv[U], xq[U];
+      V8<T> gv[U], xq[U];
       int n = 0;
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const long long mm = m + u * step;
         if (mm < p.M) {
-          gv[u] = *reinterpret_cast<const bf16x8*>(p.dy + mm * p.dy_ld + tc * 8);
-          xq[u] = *reinterpret_cast<const bf16x8*>(p.x + mm * p.x_ld + tc * 8);
+          gv[u] = ldv8(p.dy + mm * p.dy_ld + tc * 8);
+          xq[u] = ldv8(p.x + mm * p.x_ld + tc * 8);
           n = u + 1;
         }
       }
@@ -227,7 +233,8 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_reduce_kernel(const BwdParams 
 
 // backward, pass 2: dx = gamma*invstd*(g - sum_g/M - xhat*sum_gx/M) [* (x > 0) for order 1] [+ add]
 // block 0 also writes dgamma = sum g*xhat, dbeta = sum g (accumulating into the gradient buffer).
-__global__ void __launch_bounds__(THREADS) bn_bwd_apply_kernel(const BwdParams p) {
+template <typename T>
+__global__ void __launch_bounds__(THREADS) bn_bwd_apply_kernel(const BwdParams<T> p) {
   // thread -> fixed 8-channel chunk tc; the per-channel constants live in registers:
   //   xh = x * a + b2 (a = invstd, b2 = -mean * invstd),  dx = gi * k1 - (c2 + xh * c3),  c2 = k1 * sum_g / M, c3 = k1 * sum_gx / M
   extern __shared__ float sh[];                 // [THREADS][8] (dbias reduction only)
@@ -256,14 +263,14 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_apply_kernel(const BwdParams p
     const int c0 = tc * 8;
     for (long long m0 = static_cast<long long>(blockIdx.x) * rows_per_it + tr; m0 < p.M; m0 += 2 * step) {
       // two rows' loads (up to 6 x 16 bytes) are issued before the first store
-      bf16x8 gq[2], xq[2], aq[2];
+      V8<T> gq[2], xq[2], aq[2];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const long long m = m0 + u * step;
         if (m < p.M) {
-          gq[u] = *reinterpret_cast<const bf16x8*>(p.dy + m * p.dy_ld + c0);
-          xq[u] = *reinterpret_cast<const bf16x8*>(p.x + m * p.x_ld + c0);
-          if (p.add) aq[u] = *reinterpret_cast<const bf16x8*>(p.add + m * p.add_ld + c0);
+          gq[u] = ldv8(p.dy + m * p.dy_ld + c0);
+          xq[u] = ldv8(p.x + m * p.x_ld + c0);
+          if (p.add) aq[u] = ldv8(p.add + m * p.add_ld + c0);
         }
       }
 #pragma unroll
@@ -285,7 +292,7 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_apply_kernel(const BwdParams p
           g[k] = d;
           bs[k] += d;
         }
-        *reinterpret_cast<bf16x8*>(p.dx + m * p.dx_ld + c0) = pack8(g);
+        st8(p.dx + m * p.dx_ld + c0, g);
       }
     }
   }
@@ -317,14 +324,58 @@ static bool bn_args_ok(long long M, int C, long long ld) {
   return M > 0 && C >= 8 && C % 8 == 0 && C <= 2048 && ld % 8 == 0 && (THREADS % (C / 8) == 0 || C / 8 > THREADS ? (C / 8 <= THREADS) : true);
 }
 
-extern "C" int air_bn_stats(const void* x, long long x_ld, long long M, int C, double* sums, int num_sms, cudaStream_t stream) {
+template <typename T>
+static int bn_stats_impl(const void* x, long long x_ld, long long M, int C, double* sums, int num_sms, cudaStream_t stream) {
   if (!x || !sums || !bn_args_ok(M, C, x_ld)) return AIR_ERR_ARG;
   const int rows_per_it = THREADS / (C / 8);
   if (rows_per_it < 1) return AIR_ERR_UNSUPPORTED;
   const int grid = grid_for(M, rows_per_it * 16, num_sms);
-  bn_stats_kernel<<<grid, THREADS, 2 * THREADS * 8 * sizeof(float), stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), x_ld, M, C, sums);
+  bn_stats_kernel<T><<<grid, THREADS, 2 * THREADS * 8 * sizeof(float), stream>>>(reinterpret_cast<const T*>(x), x_ld, M, C, sums);
   return air_launch_status();
+}
+
+template <typename T>
+static int bn_apply_impl(const void* x, long long x_ld, void* y, long long y_ld, long long M, int C,
+                         const double* sums, const float* gamma, const float* beta, float eps, int relu,
+                         int training, float* save_mean, float* save_invstd, float* running_mean,
+                         float* running_var, float momentum, const void* add, long long add_ld, void* y2,
+                         long long y2_ld, int num_sms, cudaStream_t stream) {
+  if (!x || !y || !bn_args_ok(M, C, x_ld) || y_ld % 8 != 0) return AIR_ERR_ARG;
+  if (training ? !sums : (!running_mean || !running_var)) return AIR_ERR_ARG;
+  if (y2 && (!add || add_ld % 8 != 0 || y2_ld % 8 != 0)) return AIR_ERR_ARG;
+  ApplyParams<T> p{reinterpret_cast<const T*>(x), x_ld, reinterpret_cast<T*>(y), y_ld, M, C,
+                   sums, gamma, beta, eps, relu, training, save_mean, save_invstd, running_mean, running_var, momentum,
+                   reinterpret_cast<const T*>(add), add_ld, reinterpret_cast<T*>(y2), y2_ld};
+  const int rows_per_it = THREADS / (C / 8);
+  if (rows_per_it < 1) return AIR_ERR_UNSUPPORTED;
+  const int grid = grid_for(M, rows_per_it * 8, num_sms);
+  bn_apply_kernel<T><<<grid, THREADS, 0, stream>>>(p);
+  return air_launch_status();
+}
+
+template <typename T>
+static int bn_bwd_impl(const void* dy, long long dy_ld, const void* x, long long x_ld, const void* add, long long add_ld,
+                       void* dx, long long dx_ld, long long M, int C, int order,
+                       const float* mean, const float* invstd, const float* gamma, const float* beta,
+                       double* rsum, float* dgamma, float* dbeta, float* dbias, int num_sms, cudaStream_t stream) {
+  if (!dy || !x || !dx || !mean || !invstd || !rsum || !bn_args_ok(M, C, x_ld)) return AIR_ERR_ARG;
+  if (dy_ld % 8 != 0 || dx_ld % 8 != 0 || (add && add_ld % 8 != 0)) return AIR_ERR_ARG;
+  BwdParams<T> p{reinterpret_cast<const T*>(dy), dy_ld, reinterpret_cast<const T*>(x), x_ld,
+                 reinterpret_cast<const T*>(add), add_ld, reinterpret_cast<T*>(dx), dx_ld, M, C, order,
+                 mean, invstd, gamma, beta, rsum, dgamma, dbeta, dbias};
+  const int rows_per_it = THREADS / (C / 8);
+  if (rows_per_it < 1) return AIR_ERR_UNSUPPORTED;
+  bn_bwd_reduce_kernel<T><<<grid_for(M, rows_per_it * 16, num_sms), THREADS, 2 * THREADS * 8 * sizeof(float), stream>>>(p);
+  const int agrid = grid_for(M, rows_per_it * 8, num_sms);
+  bn_bwd_apply_kernel<T><<<agrid, THREADS, (dbias ? THREADS * 8 : 0) * sizeof(float), stream>>>(p);
+  return air_launch_status();
+}
+
+extern "C" int air_bn_stats(const void* x, long long x_ld, long long M, int C, double* sums, int num_sms, cudaStream_t stream) {
+  return bn_stats_impl<__nv_bfloat16>(x, x_ld, M, C, sums, num_sms, stream);
+}
+extern "C" int air_bn_stats_f32(const void* x, long long x_ld, long long M, int C, double* sums, int num_sms, cudaStream_t stream) {
+  return bn_stats_impl<float>(x, x_ld, M, C, sums, num_sms, stream);
 }
 
 extern "C" int air_bn_apply_add(const void* x, long long x_ld, void* y, long long y_ld, long long M, int C,
@@ -332,17 +383,16 @@ extern "C" int air_bn_apply_add(const void* x, long long x_ld, void* y, long lon
                                 int training, float* save_mean, float* save_invstd, float* running_mean,
                                 float* running_var, float momentum, const void* add, long long add_ld, void* y2,
                                 long long y2_ld, int num_sms, cudaStream_t stream) {
-  if (!x || !y || !bn_args_ok(M, C, x_ld) || y_ld % 8 != 0) return AIR_ERR_ARG;
-  if (training ? !sums : (!running_mean || !running_var)) return AIR_ERR_ARG;
-  if (y2 && (!add || add_ld % 8 != 0 || y2_ld % 8 != 0)) return AIR_ERR_ARG;
-  ApplyParams p{reinterpret_cast<const __nv_bfloat16*>(x), x_ld, reinterpret_cast<__nv_bfloat16*>(y), y_ld, M, C,
-                sums, gamma, beta, eps, relu, training, save_mean, save_invstd, running_mean, running_var, momentum,
-                reinterpret_cast<const __nv_bfloat16*>(add), add_ld, reinterpret_cast<__nv_bfloat16*>(y2), y2_ld};
-  const int rows_per_it = THREADS / (C / 8);
-  if (rows_per_it < 1) return AIR_ERR_UNSUPPORTED;
-  const int grid = grid_for(M, rows_per_it * 8, num_sms);
-  bn_apply_kernel<<<grid, THREADS, 0, stream>>>(p);
-  return air_launch_status();
+  return bn_apply_impl<__nv_bfloat16>(x, x_ld, y, y_ld, M, C, sums, gamma, beta, eps, relu, training, save_mean, save_invstd,
+                                      running_mean, running_var, momentum, add, add_ld, y2, y2_ld, num_sms, stream);
+}
+extern "C" int air_bn_apply_add_f32(const void* x, long long x_ld, void* y, long long y_ld, long long M, int C,
+                                    const double* sums, const float* gamma, const float* beta, float eps, int relu,
+                                    int training, float* save_mean, float* save_invstd, float* running_mean,
+                                    float* running_var, float momentum, const void* add, long long add_ld, void* y2,
+                                    long long y2_ld, int num_sms, cudaStream_t stream) {
+  return bn_apply_impl<float>(x, x_ld, y, y_ld, M, C, sums, gamma, beta, eps, relu, training, save_mean, save_invstd,
+                              running_mean, running_var, momentum, add, add_ld, y2, y2_ld, num_sms, stream);
 }
 
 extern "C" int air_bn_apply(const void* x, long long x_ld, void* y, long long y_ld, long long M, int C,
@@ -356,7 +406,17 @@ extern "C" int air_bn_apply(const void* x, long long x_ld, void* y, long long y_
 extern "C" int air_bn_bwd_bias(const void* dy, long long dy_ld, const void* x, long long x_ld, const void* add, long long add_ld,
                                void* dx, long long dx_ld, long long M, int C, int order,
                                const float* mean, const float* invstd, const float* gamma, const float* beta,
-                               double* rsum, float* dgamma, float* dbeta, float* dbias, int num_sms, cudaStream_t stream);
+                               double* rsum, float* dgamma, float* dbeta, float* dbias, int num_sms, cudaStream_t stream) {
+  return bn_bwd_impl<__nv_bfloat16>(dy, dy_ld, x, x_ld, add, add_ld, dx, dx_ld, M, C, order, mean, invstd, gamma, beta, rsum,
+                                    dgamma, dbeta, dbias, num_sms, stream);
+}
+extern "C" int air_bn_bwd_bias_f32(const void* dy, long long dy_ld, const void* x, long long x_ld, const void* add, long long add_ld,
+                                   void* dx, long long dx_ld, long long M, int C, int order,
+                                   const float* mean, const float* invstd, const float* gamma, const float* beta,
+                                   double* rsum, float* dgamma, float* dbeta, float* dbias, int num_sms, cudaStream_t stream) {
+  return bn_bwd_impl<float>(dy, dy_ld, x, x_ld, add, add_ld, dx, dx_ld, M, C, order, mean, invstd, gamma, beta, rsum,
+                            dgamma, dbeta, dbias, num_sms, stream);
+}
 
 extern "C" int air_bn_bwd(const void* dy, long long dy_ld, const void* x, long long x_ld, const void* add, long long add_ld,
                           void* dx, long long dx_ld, long long M, int C, int order,
@@ -364,21 +424,4 @@ extern "C" int air_bn_bwd(const void* dy, long long dy_ld, const void* x, long l
                           double* rsum, float* dgamma, float* dbeta, int num_sms, cudaStream_t stream) {
   return air_bn_bwd_bias(dy, dy_ld, x, x_ld, add, add_ld, dx, dx_ld, M, C, order, mean, invstd, gamma, beta, rsum, dgamma,
                          dbeta, nullptr, num_sms, stream);
-}
-
-extern "C" int air_bn_bwd_bias(const void* dy, long long dy_ld, const void* x, long long x_ld, const void* add, long long add_ld,
-                               void* dx, long long dx_ld, long long M, int C, int order,
-                               const float* mean, const float* invstd, const float* gamma, const float* beta,
-                               double* rsum, float* dgamma, float* dbeta, float* dbias, int num_sms, cudaStream_t stream) {
-  if (!dy || !x || !dx || !mean || !invstd || !rsum || !bn_args_ok(M, C, x_ld)) return AIR_ERR_ARG;
-  if (dy_ld % 8 != 0 || dx_ld % 8 != 0 || (add && add_ld % 8 != 0)) return AIR_ERR_ARG;
-  BwdParams p{reinterpret_cast<const __nv_bfloat16*>(dy), dy_ld, reinterpret_cast<const __nv_bfloat16*>(x), x_ld,
-              reinterpret_cast<const __nv_bfloat16*>(add), add_ld, reinterpret_cast<__nv_bfloat16*>(dx), dx_ld, M, C, order,
-              mean, invstd, gamma, beta, rsum, dgamma, dbeta, dbias};
-  const int rows_per_it = THREADS / (C / 8);
-  if (rows_per_it < 1) return AIR_ERR_UNSUPPORTED;
-  bn_bwd_reduce_kernel<<<grid_for(M, rows_per_it * 16, num_sms), THREADS, 2 * THREADS * 8 * sizeof(float), stream>>>(p);
-  const int agrid = grid_for(M, rows_per_it * 8, num_sms);
-  bn_bwd_apply_kernel<<<agrid, THREADS, (dbias ? THREADS * 8 : 0) * sizeof(float), stream>>>(p);
-  return air_launch_status();
 }

@@ -79,3 +79,39 @@ __device__ __forceinline__ bf16x8 pack8(const float* f) {
   p.u.z = f2_to_bf2x(f[4], f[5]); p.u.w = f2_to_bf2x(f[6], f[7]);
   return p;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Activation storage type T = __nv_bfloat16 (the product path) or float (the fp32 parity mode):
+// the HBM-bound kernels are templates over T and move 8 channels per access either way (16 B of bf16, 2 x 16 B of fp32).
+// ---------------------------------------------------------------------------------------------------------------
+struct __align__(16) f32x8 { float4 a, b; };
+template <typename T> struct V8sel;
+template <> struct V8sel<__nv_bfloat16> { using type = bf16x8; };
+template <> struct V8sel<float> { using type = f32x8; };
+template <typename T> using V8 = typename V8sel<T>::type;
+
+__device__ __forceinline__ void unpack8(const f32x8& p, float* f) {
+  f[0] = p.a.x; f[1] = p.a.y; f[2] = p.a.z; f[3] = p.a.w; f[4] = p.b.x; f[5] = p.b.y; f[6] = p.b.z; f[7] = p.b.w;
+}
+__device__ __forceinline__ bf16x8 ldv8(const __nv_bfloat16* p) { return *reinterpret_cast<const bf16x8*>(p); }
+__device__ __forceinline__ f32x8 ldv8(const float* p) {
+  f32x8 v;
+  v.a = reinterpret_cast<const float4*>(p)[0]; v.b = reinterpret_cast<const float4*>(p)[1];
+  return v;
+}
+__device__ __forceinline__ void packv(const float* f, bf16x8& out) { out = pack8(f); }
+__device__ __forceinline__ void packv(const float* f, f32x8& out) {
+  out.a = make_float4(f[0], f[1], f[2], f[3]); out.b = make_float4(f[4], f[5], f[6], f[7]);
+}
+__device__ __forceinline__ void stv8(__nv_bfloat16* p, const bf16x8& v) { *reinterpret_cast<bf16x8*>(p) = v; }
+__device__ __forceinline__ void stv8(float* p, const f32x8& v) {
+  reinterpret_cast<float4*>(p)[0] = v.a; reinterpret_cast<float4*>(p)[1] = v.b;
+}
+// 8 floats -> storage (rounded for bf16)
+template <typename T> __device__ __forceinline__ void st8(T* p, const float* f) { V8<T> v; packv(f, v); stv8(p, v); }
+// 8 stored values -> floats
+template <typename T> __device__ __forceinline__ void ld8(const T* p, float* f) { unpack8(ldv8(p), f); }
+__device__ __forceinline__ float ld1(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ float ld1(const float* p) { return *p; }
+__device__ __forceinline__ void st1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void st1(float* p, float v) { *p = v; }

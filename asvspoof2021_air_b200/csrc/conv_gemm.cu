@@ -43,10 +43,10 @@ struct ConvParams {
   const __nv_bfloat16* wpk;                 // packed weights [n_tile][k_block][8 chunks][block_n][8]
   int N, K, KB, block_n, n_tiles;
   long long M; int m_tiles;
-  __nv_bfloat16* out; long long out_ld;
-  const float* bias; const __nv_bfloat16* res; long long res_ld; int relu;
+  void* out; long long out_ld;              // bf16, or fp32 when flags & AIR_CONV_F32_OUT (out, res, out2 share the type)
+  const float* bias; const void* res; long long res_ld; int relu;
   int bias_rows;                            // 0: bias[n]; > 0: bias[(m / bias_rows) * N + n] (per-utterance bias)
-  __nv_bfloat16* out2; long long out2_ld;   // optional second output: the accumulator (+bias) WITHOUT the residual
+  void* out2; long long out2_ld;            // optional second output: the accumulator (+bias) WITHOUT the residual
   const float* post_scale; const float* post_shift;   // optional per-channel affine AFTER the ReLU (eval-mode BatchNorm of conv -> ReLU -> BN)
   int stages; int flags;
   int use_tma;                              // 1x1 / stride 1: the A tile is a plain 2-D box of the activation matrix
@@ -79,17 +79,33 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& p, uint32_t tmem
             v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
           }
         }
+        const bool f32 = (p.flags & AIR_CONV_F32_OUT) != 0;       // fp32 parity mode: float storage, no rounding point
         if (p.out2) {
-          bf16x8* o2 = reinterpret_cast<bf16x8*>(p.out2 + m * p.out2_ld + n0);
-          o2[0] = pack8(v);
-          o2[1] = pack8(v + 8);
+          if (f32) {
+            float4* o2 = reinterpret_cast<float4*>(static_cast<float*>(p.out2) + m * p.out2_ld + n0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o2[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else {
+            bf16x8* o2 = reinterpret_cast<bf16x8*>(static_cast<__nv_bfloat16*>(p.out2) + m * p.out2_ld + n0);
+            o2[0] = pack8(v);
+            o2[1] = pack8(v + 8);
+          }
         }
         if (p.res) {
-          const bf16x8* rp = reinterpret_cast<const bf16x8*>(p.res + m * p.res_ld + n0);
-          float rf[16];
-          unpack8(rp[0], rf); unpack8(rp[1], rf + 8);
+          if (f32) {
+            const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(p.res) + m * p.res_ld + n0);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += rf[i];
+            for (int i = 0; i < 4; ++i) {
+              const float4 r4 = rp[i];
+              v[4 * i] += r4.x; v[4 * i + 1] += r4.y; v[4 * i + 2] += r4.z; v[4 * i + 3] += r4.w;
+            }
+          } else {
+            const bf16x8* rp = reinterpret_cast<const bf16x8*>(static_cast<const __nv_bfloat16*>(p.res) + m * p.res_ld + n0);
+            float rf[16];
+            unpack8(rp[0], rf); unpack8(rp[1], rf + 8);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += rf[i];
+          }
         }
         if (p.relu) {
 #pragma unroll
@@ -105,9 +121,15 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& p, uint32_t tmem
             v[4 * i + 2] = fmaf(v[4 * i + 2], s4.z, t4.z); v[4 * i + 3] = fmaf(v[4 * i + 3], s4.w, t4.w);
           }
         }
-        bf16x8* op = reinterpret_cast<bf16x8*>(p.out + m * p.out_ld + n0);
-        op[0] = pack8(v);
-        op[1] = pack8(v + 8);
+        if (f32) {
+          float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + m * p.out_ld + n0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else {
+          bf16x8* op = reinterpret_cast<bf16x8*>(static_cast<__nv_bfloat16*>(p.out) + m * p.out_ld + n0);
+          op[0] = pack8(v);
+          op[1] = pack8(v + 8);
+        }
       }
     }
     fence_before_sync();
@@ -380,9 +402,9 @@ extern "C" int air_conv_gemm_bf16_affine(const void* a, long long a_ld, int B, i
   p.wpk = reinterpret_cast<const __nv_bfloat16*>(wpk); p.N = N; p.K = K; p.KB = (K + BLOCK_K - 1) / BLOCK_K;
   p.block_n = bn; p.n_tiles = N / bn;
   p.M = static_cast<long long>(B) * Ho * Wo; p.m_tiles = static_cast<int>((p.M + BLOCK_M - 1) / BLOCK_M);
-  p.out = reinterpret_cast<__nv_bfloat16*>(out); p.out_ld = out_ld; p.bias = bias;
-  p.res = reinterpret_cast<const __nv_bfloat16*>(res); p.res_ld = res_ld; p.relu = relu; p.flags = flags;
-  p.bias_rows = bias_rows; p.out2 = reinterpret_cast<__nv_bfloat16*>(out2); p.out2_ld = out2_ld;
+  p.out = out; p.out_ld = out_ld; p.bias = bias;
+  p.res = res; p.res_ld = res_ld; p.relu = relu; p.flags = flags;
+  p.bias_rows = bias_rows; p.out2 = out2; p.out2_ld = out2_ld;
   p.post_scale = post_scale; p.post_shift = post_shift;
   const int stage_bytes = A_STAGE_BYTES + bn * BLOCK_K * 2;
   int stages = (198 * 1024) / stage_bytes;

@@ -46,10 +46,11 @@ struct PatchParams {
   int pw;                               // patch width in pixels: TW + 2 (3x3) or TW + 8 (dilated 1-D taps up to +8)
   int C, N;
   const __nv_bfloat16* wpk; int wtaps;  // packed weights: [C/CB][wtaps] slices of [N][CB]
-  __nv_bfloat16* out; long long out_ld;
-  const __nv_bfloat16* res; long long res_ld; int relu;
+  void* out; long long out_ld;          // bf16, or fp32 when f32 != 0 (out, res and out2 share the type)
+  const void* res; long long res_ld; int relu;
   const float* bias;                    // optional per-channel bias (ECAPA convs, ecapa_tdnn.py:39,50)
-  __nv_bfloat16* out2; long long out2_ld;   // optional second output: accumulator (+bias) WITHOUT the residual
+  void* out2; long long out2_ld;        // optional second output: accumulator (+bias) WITHOUT the residual
+  int f32;                              // fp32 parity mode: outputs / residual stored as float (operands stay bf16 splits)
   double* stats;                        // optional: stats[n] += sum of the stored outputs, stats[N + n] += sum of squares
                                         // (the batch statistics of the BatchNorm that consumes `out`, bn_stats fused)
   int CB, NCB, WT, HP;                  // channels per block (16 / 32 / 64), #blocks, column tiles, row pairs
@@ -64,8 +65,8 @@ struct PatchParams {
 // residual of one 32-column (NC = 32) or 16-column chunk of a pixel: 16-byte loads, issued ahead of use
 template <int NC>
 __device__ __forceinline__ void load_res(const PatchParams& p, long long pixel, int c0, bool valid, bf16x8 (&rv)[4]) {
-  if (p.res != nullptr && valid) {
-    const bf16x8* rp = reinterpret_cast<const bf16x8*>(p.res + pixel * p.res_ld + c0);
+  if (p.res != nullptr && valid && !p.f32) {
+    const bf16x8* rp = reinterpret_cast<const bf16x8*>(static_cast<const __nv_bfloat16*>(p.res) + pixel * p.res_ld + c0);
 #pragma unroll
     for (int i = 0; i < NC / 8; ++i) rv[i] = rp[i];
   }
@@ -102,8 +103,32 @@ __device__ __forceinline__ void epilogue_chunk(const PatchParams& p, uint32_t ta
         v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
       }
     }
+    if (p.f32) {
+      // fp32 parity mode: the same epilogue with float storage (no rounding point between the layers)
+      if (p.out2 != nullptr) {
+        float4* o2 = reinterpret_cast<float4*>(static_cast<float*>(p.out2) + pixel * p.out2_ld + c0);
+#pragma unroll
+        for (int i = 0; i < NC / 4; ++i) o2[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
+      if (p.res != nullptr) {
+        const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(p.res) + pixel * p.res_ld + c0);
+#pragma unroll
+        for (int i = 0; i < NC / 4; ++i) {
+          const float4 r4 = rp[i];
+          v[4 * i] += r4.x; v[4 * i + 1] += r4.y; v[4 * i + 2] += r4.z; v[4 * i + 3] += r4.w;
+        }
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int i = 0; i < NC; ++i) v[i] = fmaxf(v[i], 0.f);
+      }
+      float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + pixel * p.out_ld + c0);
+#pragma unroll
+      for (int i = 0; i < NC / 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      return;
+    }
     if (p.out2 != nullptr) {
-      bf16x8* o2 = reinterpret_cast<bf16x8*>(p.out2 + pixel * p.out2_ld + c0);
+      bf16x8* o2 = reinterpret_cast<bf16x8*>(static_cast<__nv_bfloat16*>(p.out2) + pixel * p.out2_ld + c0);
 #pragma unroll
       for (int i = 0; i < NC / 8; ++i) o2[i] = pack8(v + i * 8);
     }
@@ -120,7 +145,7 @@ __device__ __forceinline__ void epilogue_chunk(const PatchParams& p, uint32_t ta
 #pragma unroll
       for (int i = 0; i < NC; ++i) v[i] = fmaxf(v[i], 0.f);
     }
-    bf16x8* op = reinterpret_cast<bf16x8*>(p.out + pixel * p.out_ld + c0);
+    bf16x8* op = reinterpret_cast<bf16x8*>(static_cast<__nv_bfloat16*>(p.out) + pixel * p.out_ld + c0);
 #pragma unroll
     for (int i = 0; i < NC / 8; ++i) {
       const bf16x8 pk = pack8(v + i * 8);
@@ -406,6 +431,14 @@ extern "C" int air_conv3x3_pack_weights(const float* w, void* dst, int C, int N,
   return air_conv_patch_pack_weights(w, dst, C, N, 9, mode, stream);
 }
 
+extern "C" int air_conv_patch_taps_ex2_bf16(const void* a, long long a_ld, int B, int Hin, int Win, int C,
+                                            const void* wpk, int wtaps, int N, void* out, long long out_ld, int OH, int OW,
+                                            const void* res, long long res_ld, int relu, const float* bias,
+                                            void* out2, long long out2_ld, double* stats,
+                                            int GH, int GW, int org_h, int org_w, int osh, int osw, int oph, int opw,
+                                            int ntaps, const int* tap_dr, const int* tap_dc, const int* tap_slice,
+                                            int flags, int num_sms, cudaStream_t stream);
+
 // The general entry point: explicit tap table and output pixel mapping (see the formula at the top of this file).
 //   a: (B, Hin, Win, C) channels-last bf16;  out / res: (B, OH, OW, N);  item grid GH x GW;
 //   tap t reads the window that starts at patch pixel (tap_dr[t], tap_dc[t]) (0 <= dr, dc <= 2) and uses weight slice
@@ -438,6 +471,20 @@ extern "C" int air_conv_patch_taps_ex_bf16(const void* a, long long a_ld, int B,
                                            int GH, int GW, int org_h, int org_w, int osh, int osw, int oph, int opw,
                                            int ntaps, const int* tap_dr, const int* tap_dc, const int* tap_slice,
                                            int num_sms, cudaStream_t stream) {
+  return air_conv_patch_taps_ex2_bf16(a, a_ld, B, Hin, Win, C, wpk, wtaps, N, out, out_ld, OH, OW, res, res_ld, relu, bias,
+                                      out2, out2_ld, stats, GH, GW, org_h, org_w, osh, osw, oph, opw, ntaps, tap_dr, tap_dc,
+                                      tap_slice, 0, num_sms, stream);
+}
+
+// as air_conv_patch_taps_ex_bf16 plus `flags`: AIR_CONV_F32_OUT = out / res / out2 are float tensors (fp32 parity mode: the
+// operands are bf16 split terms concatenated along the channels, the accumulator is stored unrounded)
+extern "C" int air_conv_patch_taps_ex2_bf16(const void* a, long long a_ld, int B, int Hin, int Win, int C,
+                                            const void* wpk, int wtaps, int N, void* out, long long out_ld, int OH, int OW,
+                                            const void* res, long long res_ld, int relu, const float* bias,
+                                            void* out2, long long out2_ld, double* stats,
+                                            int GH, int GW, int org_h, int org_w, int osh, int osw, int oph, int opw,
+                                            int ntaps, const int* tap_dr, const int* tap_dc, const int* tap_slice,
+                                            int flags, int num_sms, cudaStream_t stream) {
   if (!a || !wpk || !out || B <= 0 || !tap_dr || !tap_dc || !tap_slice) return AIR_ERR_ARG;
   if (stats && (N % 32) != 0) return AIR_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(out2)) & 15) return AIR_ERR_UNSUPPORTED;
@@ -451,14 +498,14 @@ extern "C" int air_conv_patch_taps_ex_bf16(const void* a, long long a_ld, int B,
   p.B = B; p.GH = GH; p.GW = GW; p.OH = OH; p.OW = OW; p.osh = osh; p.osw = osw; p.oph = oph; p.opw = opw;
   p.org_h = org_h; p.org_w = org_w; p.C = C; p.N = N;
   p.wpk = reinterpret_cast<const __nv_bfloat16*>(wpk); p.wtaps = wtaps;
-  p.out = reinterpret_cast<__nv_bfloat16*>(out); p.out_ld = out_ld;
-  p.res = reinterpret_cast<const __nv_bfloat16*>(res); p.res_ld = res_ld; p.relu = relu;
+  p.out = out; p.out_ld = out_ld; p.f32 = (flags & AIR_CONV_F32_OUT) ? 1 : 0;
+  p.res = res; p.res_ld = res_ld; p.relu = relu;
   p.ntaps = ntaps;
   for (int t = 0; t < MAX_TAPS; ++t) { p.tap_off[t] = 0; p.tap_slice[t] = 0; }
   int max_dc = 0;
   for (int t = 0; t < ntaps; ++t) max_dc = std::max(max_dc, tap_dc[t]);
   p.pw = max_dc <= PW - TW ? PW : PW_MAX;
-  p.bias = bias; p.out2 = reinterpret_cast<__nv_bfloat16*>(out2); p.out2_ld = out2_ld; p.stats = stats;
+  p.bias = bias; p.out2 = out2; p.out2_ld = out2_ld; p.stats = stats;
   for (int t = 0; t < ntaps; ++t) {
     if (tap_dr[t] < 0 || tap_dr[t] > PR - R || tap_dc[t] < 0 || tap_dc[t] > p.pw - TW || tap_slice[t] < 0 || tap_slice[t] >= wtaps)
       return AIR_ERR_ARG;

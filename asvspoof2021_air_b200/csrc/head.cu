@@ -31,17 +31,18 @@ __device__ __forceinline__ float gauss_noise(long long seed, long long idx) {
 //   x (B,T,C) bf16;  att (C);  stats (B,2C) = [sum_t x*p | unbiased std_t(x*p + noise)]
 //   saved: p (B,T) softmax weights, th (B,T) tanh(x . att)
 // ------------------------------------------------------------------------------------------
-__global__ void selfattn_pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ att,
+template <typename AT>
+__global__ void selfattn_pool_fwd_kernel(const AT* __restrict__ x, const float* __restrict__ att,
                                          float* __restrict__ stats, float* __restrict__ p_out, float* __restrict__ th_out,
                                          int T, int C, long long seed) {
   extern __shared__ float sh[];           // sw[T], red[32]
   float* sw = sh;
   float* red = sh + T;
   const int b = blockIdx.x, c = threadIdx.x, warp = c >> 5, lane = c & 31, nw = C >> 5;
-  const __nv_bfloat16* xb = x + static_cast<long long>(b) * T * C;
+  const AT* xb = x + static_cast<long long>(b) * T * C;
   for (int t = warp; t < T; t += nw) {
     float acc = 0.f;
-    for (int k = lane; k < C; k += 32) acc = fmaf(bf2f(xb[t * C + k]), att[k], acc);
+    for (int k = lane; k < C; k += 32) acc = fmaf(ld1(xb + t * C + k), att[k], acc);
     acc = warp_sum(acc);
     if (lane == 0) sw[t] = tanhf(acc);
   }
@@ -63,36 +64,37 @@ __global__ void selfattn_pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, co
   __syncthreads();
   float sum = 0.f, sumn = 0.f;
   for (int t = 0; t < T; ++t) {
-    const float v = bf2f(xb[t * C + c]) * sw[t];
+    const float v = ld1(xb + t * C + c) * sw[t];
     sum += v;
     sumn += v + gauss_noise(seed, (static_cast<long long>(b) * T + t) * C + c);
   }
   const float mean = sumn / T;
   float ss = 0.f;
   for (int t = 0; t < T; ++t) {
-    const float v = bf2f(xb[t * C + c]) * sw[t] + gauss_noise(seed, (static_cast<long long>(b) * T + t) * C + c) - mean;
+    const float v = ld1(xb + t * C + c) * sw[t] + gauss_noise(seed, (static_cast<long long>(b) * T + t) * C + c) - mean;
     ss = fmaf(v, v, ss);
   }
   stats[static_cast<long long>(b) * 2 * C + c] = sum;
   stats[static_cast<long long>(b) * 2 * C + C + c] = sqrtf(ss / (T - 1));
 }
 
-__global__ void selfattn_pool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ att,
+template <typename AT>
+__global__ void selfattn_pool_bwd_kernel(const AT* __restrict__ x, const float* __restrict__ att,
                                          const float* __restrict__ p_in, const float* __restrict__ th_in,
                                          const float* __restrict__ stats, const float* __restrict__ dstats,
-                                         __nv_bfloat16* __restrict__ dx, float* __restrict__ datt,
+                                         AT* __restrict__ dx, float* __restrict__ datt,
                                          int T, int C, long long seed) {
   extern __shared__ float sh[];           // sp[T], sdp[T], sdw[T], dav[C], kk[C], mn[C], red[32]
   float* sp = sh; float* sdp = sh + T; float* sdw = sh + 2 * T;
   float* dav = sh + 3 * T; float* kk = dav + C; float* mn = kk + C; float* red = mn + C;
   const int b = blockIdx.x, c = threadIdx.x, warp = c >> 5, lane = c & 31, nw = C >> 5;
-  const __nv_bfloat16* xb = x + static_cast<long long>(b) * T * C;
+  const AT* xb = x + static_cast<long long>(b) * T * C;
   for (int t = c; t < T; t += C) sp[t] = p_in[b * T + t];
   __syncthreads();
   {
     float sumn = 0.f;
     for (int t = 0; t < T; ++t)
-      sumn += bf2f(xb[t * C + c]) * sp[t] + gauss_noise(seed, (static_cast<long long>(b) * T + t) * C + c);
+      sumn += ld1(xb + t * C + c) * sp[t] + gauss_noise(seed, (static_cast<long long>(b) * T + t) * C + c);
     const float sd = stats[static_cast<long long>(b) * 2 * C + C + c];
     dav[c] = dstats[static_cast<long long>(b) * 2 * C + c];
     // d std / d v_t = (v_t - mean) / ((T-1) std); a dead channel (std == 0) gets zero gradient
@@ -103,7 +105,7 @@ __global__ void selfattn_pool_bwd_kernel(const __nv_bfloat16* __restrict__ x, co
   for (int t = warp; t < T; t += nw) {            // dp[t] = sum_c dweighted[t][c] * x[t][c]
     float acc = 0.f;
     for (int k = lane; k < C; k += 32) {
-      const float xv = bf2f(xb[t * C + k]);
+      const float xv = ld1(xb + t * C + k);
       const float v = xv * sp[t] + gauss_noise(seed, (static_cast<long long>(b) * T + t) * C + k);
       acc = fmaf(dav[k] + kk[k] * (v - mn[k]), xv, acc);
     }
@@ -123,10 +125,10 @@ __global__ void selfattn_pool_bwd_kernel(const __nv_bfloat16* __restrict__ x, co
   const float a = att[c];
   float da = 0.f;
   for (int t = 0; t < T; ++t) {
-    const float xv = bf2f(xb[t * C + c]);
+    const float xv = ld1(xb + t * C + c);
     const float v = xv * sp[t] + gauss_noise(seed, (static_cast<long long>(b) * T + t) * C + c);
     const float dwgt = dav[c] + kk[c] * (v - mn[c]);
-    dx[(static_cast<long long>(b) * T + t) * C + c] = f2bf(dwgt * sp[t] + sdw[t] * a);
+    st1(dx + (static_cast<long long>(b) * T + t) * C + c, dwgt * sp[t] + sdw[t] * a);
     da = fmaf(sdw[t], xv, da);
   }
   atomicAdd(&datt[c], da);
@@ -281,23 +283,43 @@ __global__ void __launch_bounds__(256) ocsoftmax_kernel(const float* __restrict_
 
 using namespace air_head;
 
-extern "C" int air_selfattn_pool_fwd(const void* x, const float* att, float* stats, float* p_out, float* th_out,
-                                     int B, int T, int C, long long noise_seed, cudaStream_t stream) {
+template <typename AT>
+static int pool_fwd_impl(const void* x, const float* att, float* stats, float* p_out, float* th_out,
+                         int B, int T, int C, long long noise_seed, cudaStream_t stream) {
   if (!x || !att || !stats || !p_out || !th_out || B <= 0 || T < 2 || C % 32 != 0 || C > 1024) return AIR_ERR_ARG;
-  selfattn_pool_fwd_kernel<<<B, C, (T + 32) * sizeof(float), stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), att, stats, p_out, th_out, T, C, noise_seed);
+  selfattn_pool_fwd_kernel<AT><<<B, C, (T + 32) * sizeof(float), stream>>>(
+      reinterpret_cast<const AT*>(x), att, stats, p_out, th_out, T, C, noise_seed);
   return air_launch_status();
 }
 
+template <typename AT>
+static int pool_bwd_impl(const void* x, const float* att, const float* p_in, const float* th_in,
+                         const float* stats, const float* dstats, void* dx, float* datt,
+                         int B, int T, int C, long long noise_seed, cudaStream_t stream) {
+  if (!x || !att || !p_in || !th_in || !stats || !dstats || !dx || !datt || B <= 0 || T < 2 || C % 32 != 0 || C > 1024)
+    return AIR_ERR_ARG;
+  selfattn_pool_bwd_kernel<AT><<<B, C, (3 * T + 3 * C + 32) * sizeof(float), stream>>>(
+      reinterpret_cast<const AT*>(x), att, p_in, th_in, stats, dstats, reinterpret_cast<AT*>(dx), datt, T, C, noise_seed);
+  return air_launch_status();
+}
+
+extern "C" int air_selfattn_pool_fwd(const void* x, const float* att, float* stats, float* p_out, float* th_out,
+                                     int B, int T, int C, long long noise_seed, cudaStream_t stream) {
+  return pool_fwd_impl<__nv_bfloat16>(x, att, stats, p_out, th_out, B, T, C, noise_seed, stream);
+}
+extern "C" int air_selfattn_pool_fwd_f32(const void* x, const float* att, float* stats, float* p_out, float* th_out,
+                                         int B, int T, int C, long long noise_seed, cudaStream_t stream) {
+  return pool_fwd_impl<float>(x, att, stats, p_out, th_out, B, T, C, noise_seed, stream);
+}
 extern "C" int air_selfattn_pool_bwd(const void* x, const float* att, const float* p_in, const float* th_in,
                                      const float* stats, const float* dstats, void* dx, float* datt,
                                      int B, int T, int C, long long noise_seed, cudaStream_t stream) {
-  if (!x || !att || !p_in || !th_in || !stats || !dstats || !dx || !datt || B <= 0 || T < 2 || C % 32 != 0 || C > 1024)
-    return AIR_ERR_ARG;
-  selfattn_pool_bwd_kernel<<<B, C, (3 * T + 3 * C + 32) * sizeof(float), stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), att, p_in, th_in, stats, dstats,
-      reinterpret_cast<__nv_bfloat16*>(dx), datt, T, C, noise_seed);
-  return air_launch_status();
+  return pool_bwd_impl<__nv_bfloat16>(x, att, p_in, th_in, stats, dstats, dx, datt, B, T, C, noise_seed, stream);
+}
+extern "C" int air_selfattn_pool_bwd_f32(const void* x, const float* att, const float* p_in, const float* th_in,
+                                         const float* stats, const float* dstats, void* dx, float* datt,
+                                         int B, int T, int C, long long noise_seed, cudaStream_t stream) {
+  return pool_bwd_impl<float>(x, att, p_in, th_in, stats, dstats, dx, datt, B, T, C, noise_seed, stream);
 }
 
 extern "C" int air_linear_fwd(const float* x, const float* W, const float* bias, float* y, int M, int N, int K,

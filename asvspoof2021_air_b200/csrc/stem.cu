@@ -12,15 +12,17 @@ namespace air_stem {
 constexpr int CO = 16;
 constexpr int MAX_TAPS = 32;
 
+template <typename T>
 struct StemParams {
-  const __nv_bfloat16* x; int B, H, W, Ho, Wo, kh, kw, sh, sw, ph, pw;
-  const float* w; __nv_bfloat16* y; const __nv_bfloat16* dy; float* dw; long long M;
+  const T* x; int B, H, W, Ho, Wo, kh, kw, sh, sw, ph, pw;
+  const float* w; T* y; const T* dy; float* dw; long long M;
 };
 
 // Forward: a thread computes 4 consecutive output columns x 16 channels; a weight vector (16 channels of one tap,
 // 4 x LDS.128) feeds 64 FMAs, an input row segment of 6 samples is loaded once for the 3 horizontal taps.
 constexpr int FW_PIX = 4;
-__global__ void __launch_bounds__(256) stem_fwd_kernel(const StemParams p) {
+template <typename T>
+__global__ void __launch_bounds__(256) stem_fwd_kernel(const StemParams<T> p) {
   __shared__ __align__(16) float swt[MAX_TAPS * CO];          // [tap][co]
   const int taps = p.kh * p.kw;
   for (int i = threadIdx.x; i < CO * taps; i += blockDim.x) { const int c = i / taps, t = i - c * taps; swt[t * CO + c] = p.w[i]; }
@@ -37,16 +39,16 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const StemParams p) {
     for (int px = 0; px < FW_PIX; ++px)
 #pragma unroll
       for (int c = 0; c < CO; ++c) acc[px][c] = 0.f;
-    const __nv_bfloat16* img = p.x + static_cast<long long>(b) * p.H * p.W;
+    const T* img = p.x + static_cast<long long>(b) * p.H * p.W;
     for (int i = 0; i < p.kh; ++i) {
       const int hi = ho * p.sh - p.ph + i;
       if (hi < 0 || hi >= p.H) continue;
-      const __nv_bfloat16* row = img + static_cast<long long>(hi) * p.W;
+      const T* row = img + static_cast<long long>(hi) * p.W;
       float xin[FW_PIX + 2];
 #pragma unroll
       for (int u = 0; u < FW_PIX + 2; ++u) {
         const int wi = wo0 - p.pw + u;
-        xin[u] = (wi >= 0 && wi < p.W) ? bf2f(row[wi]) : 0.f;
+        xin[u] = (wi >= 0 && wi < p.W) ? ld1(row + wi) : 0.f;
       }
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
@@ -63,9 +65,8 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const StemParams p) {
 #pragma unroll
     for (int px = 0; px < FW_PIX; ++px) {
       if (wo0 + px < p.Wo) {
-        bf16x8* op = reinterpret_cast<bf16x8*>(p.y + (m0 + px) * CO);
-        op[0] = pack8(acc[px]);
-        op[1] = pack8(acc[px] + 8);
+        st8(p.y + (m0 + px) * CO, acc[px]);
+        st8(p.y + (m0 + px) * CO + 8, acc[px] + 8);
       }
     }
   }
@@ -74,7 +75,8 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const StemParams p) {
 // dw[co][tap] += sum_m dy[m][co] * x[pix(m, tap)].  One warp per kernel row i, one lane per pixel: a lane reads the
 // 16 gradients of its pixel (2 x 16 B) and the 3 input samples of row i once for 48 FMAs; partial sums stay in
 // registers over all the pixels of the block and are reduced by warp shuffles at the end.
-__global__ void __launch_bounds__(320) stem_wgrad_kernel(const StemParams p) {
+template <typename T>
+__global__ void __launch_bounds__(320) stem_wgrad_kernel(const StemParams<T> p) {
   const int i = threadIdx.x >> 5, lane = threadIdx.x & 31;      // blockDim.x = 32 * kh
   float acc[3][CO];
 #pragma unroll
@@ -86,14 +88,13 @@ __global__ void __launch_bounds__(320) stem_wgrad_kernel(const StemParams p) {
     const int ho = static_cast<int>(t % p.Ho), b = static_cast<int>(t / p.Ho);
     const int hi = ho * p.sh - p.ph + i;
     if (hi < 0 || hi >= p.H) continue;
-    const bf16x8* gp = reinterpret_cast<const bf16x8*>(p.dy + m * CO);
     float g[CO];
-    unpack8(gp[0], g); unpack8(gp[1], g + 8);
-    const __nv_bfloat16* row = p.x + (static_cast<long long>(b) * p.H + hi) * p.W;
+    ld8(p.dy + m * CO, g); ld8(p.dy + m * CO + 8, g + 8);
+    const T* row = p.x + (static_cast<long long>(b) * p.H + hi) * p.W;
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const int wi = wo - p.pw + j;
-      const float xv = (wi >= 0 && wi < p.W) ? bf2f(row[wi]) : 0.f;
+      const float xv = (wi >= 0 && wi < p.W) ? ld1(row + wi) : 0.f;
 #pragma unroll
       for (int c = 0; c < CO; ++c) acc[j][c] = fmaf(g[c], xv, acc[j][c]);
     }
@@ -112,35 +113,55 @@ __global__ void __launch_bounds__(320) stem_wgrad_kernel(const StemParams p) {
 
 using namespace air_stem;
 
-static int stem_fill(StemParams& p, const void* x, int B, int H, int W, int kh, int kw, int sh, int sw, int ph, int pw) {
+template <typename T>
+static int stem_fill(StemParams<T>& p, const void* x, int B, int H, int W, int kh, int kw, int sh, int sw, int ph, int pw) {
   if (!x || B <= 0 || kh * kw > MAX_TAPS) return AIR_ERR_ARG;
-  p.x = reinterpret_cast<const __nv_bfloat16*>(x); p.B = B; p.H = H; p.W = W;
+  p.x = reinterpret_cast<const T*>(x); p.B = B; p.H = H; p.W = W;
   p.kh = kh; p.kw = kw; p.sh = sh; p.sw = sw; p.ph = ph; p.pw = pw;
   p.Ho = (H + 2 * ph - kh) / sh + 1; p.Wo = (W + 2 * pw - kw) / sw + 1;
   p.M = static_cast<long long>(B) * p.Ho * p.Wo;
   return AIR_OK;
 }
 
-extern "C" int air_stem_conv_fwd(const void* x, int B, int H, int W, int kh, int kw, int sh, int sw, int ph, int pw,
-                                 const float* w, int Cout, void* y, cudaStream_t stream) {
-  StemParams p{};
+template <typename T>
+static int stem_fwd_impl(const void* x, int B, int H, int W, int kh, int kw, int sh, int sw, int ph, int pw,
+                         const float* w, int Cout, void* y, cudaStream_t stream) {
+  StemParams<T> p{};
   if (int e = stem_fill(p, x, B, H, W, kh, kw, sh, sw, ph, pw)) return e;
   if (!w || !y || Cout != CO || kw != 3 || sw != 1) return AIR_ERR_UNSUPPORTED;
-  p.w = w; p.y = reinterpret_cast<__nv_bfloat16*>(y);
+  p.w = w; p.y = reinterpret_cast<T*>(y);
   const long long quads = static_cast<long long>(B) * p.Ho * ((p.Wo + FW_PIX - 1) / FW_PIX);
   const int blocks = static_cast<int>(std::min<long long>((quads + 255) / 256, 148 * 16));
-  stem_fwd_kernel<<<blocks, 256, 0, stream>>>(p);
+  stem_fwd_kernel<T><<<blocks, 256, 0, stream>>>(p);
   return air_launch_status();
 }
 
-extern "C" int air_stem_conv_wgrad(const void* x, int B, int H, int W, int kh, int kw, int sh, int sw, int ph, int pw,
-                                   const void* dy, int Cout, float* dw, cudaStream_t stream) {
-  StemParams p{};
+template <typename T>
+static int stem_wgrad_impl(const void* x, int B, int H, int W, int kh, int kw, int sh, int sw, int ph, int pw,
+                           const void* dy, int Cout, float* dw, cudaStream_t stream) {
+  StemParams<T> p{};
   if (int e = stem_fill(p, x, B, H, W, kh, kw, sh, sw, ph, pw)) return e;
   if (!dy || !dw || Cout != CO || kw != 3 || sw != 1 || kh > 10) return AIR_ERR_UNSUPPORTED;
-  p.dy = reinterpret_cast<const __nv_bfloat16*>(dy); p.dw = dw;
+  p.dy = reinterpret_cast<const T*>(dy); p.dw = dw;
   const long long chunks = (p.M + 31) / 32;
   const int blocks = static_cast<int>(std::min<long long>(chunks, 148 * 6));
-  stem_wgrad_kernel<<<blocks, 32 * kh, 0, stream>>>(p);
+  stem_wgrad_kernel<T><<<blocks, 32 * kh, 0, stream>>>(p);
   return air_launch_status();
+}
+
+extern "C" int air_stem_conv_fwd(const void* x, int B, int H, int W, int kh, int kw, int sh, int sw, int ph, int pw,
+                                 const float* w, int Cout, void* y, cudaStream_t stream) {
+  return stem_fwd_impl<__nv_bfloat16>(x, B, H, W, kh, kw, sh, sw, ph, pw, w, Cout, y, stream);
+}
+extern "C" int air_stem_conv_fwd_f32(const void* x, int B, int H, int W, int kh, int kw, int sh, int sw, int ph, int pw,
+                                     const float* w, int Cout, void* y, cudaStream_t stream) {
+  return stem_fwd_impl<float>(x, B, H, W, kh, kw, sh, sw, ph, pw, w, Cout, y, stream);
+}
+extern "C" int air_stem_conv_wgrad(const void* x, int B, int H, int W, int kh, int kw, int sh, int sw, int ph, int pw,
+                                   const void* dy, int Cout, float* dw, cudaStream_t stream) {
+  return stem_wgrad_impl<__nv_bfloat16>(x, B, H, W, kh, kw, sh, sw, ph, pw, dy, Cout, dw, stream);
+}
+extern "C" int air_stem_conv_wgrad_f32(const void* x, int B, int H, int W, int kh, int kw, int sh, int sw, int ph, int pw,
+                                       const void* dy, int Cout, float* dw, cudaStream_t stream) {
+  return stem_wgrad_impl<float>(x, B, H, W, kh, kw, sh, sw, ph, pw, dy, Cout, dw, stream);
 }
