@@ -35,7 +35,7 @@ def declared_symbols(header=HEADER):
     return [name for _, name, _ in _declarations(header)]
 
 
-_SCALARS = {"int": ctypes.c_int, "long long": ctypes.c_longlong, "unsigned long long": ctypes.c_ulonglong,
+_SCALARS = {"int": ctypes.c_int, "unsigned": ctypes.c_uint, "long long": ctypes.c_longlong, "unsigned long long": ctypes.c_ulonglong,
             "float": ctypes.c_float, "double": ctypes.c_double, "air_stream_t": ctypes.c_void_p}
 
 

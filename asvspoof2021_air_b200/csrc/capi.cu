@@ -31,6 +31,7 @@ extern "C" const char* air_status_string(int status) {
     case -4: return "AIR_ERR_FORMAT: malformed or unsupported audio stream";
     case -5: return "AIR_ERR_CHECKSUM: CRC / MD5 mismatch in the audio stream";
     case -6: return "AIR_ERR_NOMEM: host allocation failed";
+    case -7: return "AIR_ERR_DRIVER: cuTensorMapEncodeTiled could not be resolved (no CUDA driver loaded)";
     default: break;
   }
   if (status >= 10000) return "cuTensorMapEncodeTiled failed (status - 10000 = CUresult)";

@@ -13,6 +13,8 @@ extern "C" int air_internal_note_status(int status, const char* file, int line);
 #define AIR_ERR_ARG air_internal_note_status(-1, __FILE__, __LINE__)
 #undef AIR_ERR_UNSUPPORTED
 #define AIR_ERR_UNSUPPORTED air_internal_note_status(-2, __FILE__, __LINE__)
+#undef AIR_ERR_DRIVER
+#define AIR_ERR_DRIVER air_internal_note_status(-7, __FILE__, __LINE__)
 
 // Launch-error check used by every entry point: asynchronous, no device sync.
 static inline int air_launch_status() {

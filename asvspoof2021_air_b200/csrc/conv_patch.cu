@@ -531,7 +531,7 @@ extern "C" int air_conv_patch_taps_ex2_bf16(const void* a, long long a_ld, int B
                       (2 * PSTAGES + 2 * slots + 4) * 8 + 32 + (stats ? 4 * 2 * static_cast<size_t>(N) * sizeof(float) : 0);
   CUtensorMap tm;
   const int tr = air_tmap::make_act_tmap(&tm, a, a_ld, B, Hin, Win, C, p.CB, p.pw, PR, p.row_bytes);
-  if (tr != 0) return tr < 0 ? AIR_ERR_UNSUPPORTED : 10000 + tr;
+  if (tr != 0) return tr < 0 ? AIR_ERR_DRIVER : 10000 + tr;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -573,6 +573,13 @@ extern "C" int air_conv3x3_patch_stats_bf16(const void* a, long long a_ld, int B
 extern "C" int air_conv_s2_dgrad_patch_bf16(const void* dy, long long dy_ld, int B, int Ho, int Wo, int Cout,
                                             const void* wpk, int k, int Cin, void* dx, long long dx_ld, int H, int W,
                                             const void* res, long long res_ld, int num_sms, cudaStream_t stream) {
+  return air_conv_s2_dgrad_patch_ex_bf16(dy, dy_ld, B, Ho, Wo, Cout, wpk, k, Cin, dx, dx_ld, H, W, res, res_ld, 0, num_sms, stream);
+}
+
+// as above plus `flags` (AIR_CONV_F32_OUT: dx / res are float tensors, fp32 parity mode)
+extern "C" int air_conv_s2_dgrad_patch_ex_bf16(const void* dy, long long dy_ld, int B, int Ho, int Wo, int Cout,
+                                               const void* wpk, int k, int Cin, void* dx, long long dx_ld, int H, int W,
+                                               const void* res, long long res_ld, int flags, int num_sms, cudaStream_t stream) {
   if (k != 3 && k != 1) return AIR_ERR_UNSUPPORTED;
   for (int ph = 0; ph < 2; ++ph) {
     for (int pw = 0; pw < 2; ++pw) {
@@ -593,8 +600,9 @@ extern "C" int air_conv_s2_dgrad_patch_bf16(const void* dy, long long dy_ld, int
           }
         }
       }
-      const int st = air_conv_patch_taps_bf16(dy, dy_ld, B, Ho, Wo, Cout, wpk, k * k, Cin, dx, dx_ld, H, W, res, res_ld, 0,
-                                              GH, GW, 0, 0, 2, 2, ph, pw, nt, dr, dc, sl, num_sms, stream);
+      const int st = air_conv_patch_taps_ex2_bf16(dy, dy_ld, B, Ho, Wo, Cout, wpk, k * k, Cin, dx, dx_ld, H, W, res, res_ld, 0,
+                                                  nullptr, nullptr, 0, nullptr, GH, GW, 0, 0, 2, 2, ph, pw, nt, dr, dc, sl,
+                                                  flags, num_sms, stream);
       if (st != 0) return st;
     }
   }

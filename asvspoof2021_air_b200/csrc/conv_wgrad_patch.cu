@@ -237,7 +237,7 @@ static int launch_wgrad_patch(const void* x, long long x_ld, int B, int H, int W
   int tr = p.narrow ? air_tmap::make_act_tmap(&tmx, x, x_ld, B, H, W, C, 16, p.pw, PR, 32)
                     : air_tmap::make_act_tmap(&tmx, x, x_ld, B, H, W, C, 64, p.pw, PR, 128);
   if (tr == 0) tr = air_tmap::make_act_tmap(&tmdy, dy, dy_ld, B, H, W, N, 64, TW, R, 128);
-  if (tr != 0) return tr < 0 ? AIR_ERR_UNSUPPORTED : 10000 + tr;
+  if (tr != 0) return tr < 0 ? AIR_ERR_DRIVER : 10000 + tr;
   const size_t smem = 1024 + static_cast<size_t>(STAGES) * p.stage_bytes + (2 * STAGES + 1) * 8 + 16;
   static bool attr_done = false;
   if (!attr_done) {

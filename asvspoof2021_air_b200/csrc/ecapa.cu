@@ -16,7 +16,8 @@ constexpr int THREADS = TG * CT;
 // ---------------------------------------------------------------------------------------------
 // mean_t and (optionally) sqrt(clamp(unbiased var_t, clampv)) over time.   grid (ceil(C/256), B)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(THREADS) time_stats_kernel(const __nv_bfloat16* __restrict__ x, long long ld, int T, int C,
+template <typename AT>
+__global__ void __launch_bounds__(THREADS) time_stats_kernel(const AT* __restrict__ x, long long ld, int T, int C,
                                                               float* __restrict__ mean_out, float* __restrict__ std_out, float clampv) {
   __shared__ float sh[2][TG][CT * 8 + 8];
   const int b = blockIdx.y, ct = threadIdx.x % CT, tg = threadIdx.x / CT;
@@ -25,10 +26,10 @@ __global__ void __launch_bounds__(THREADS) time_stats_kernel(const __nv_bfloat16
 #pragma unroll
   for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
   if (c0 < C) {
-    const __nv_bfloat16* p = x + static_cast<long long>(b) * T * ld + c0;
+    const AT* p = x + static_cast<long long>(b) * T * ld + c0;
     for (int t = tg; t < T; t += TG) {
       float f[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(p + t * ld), f);
+      ld8(p + t * ld, f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
     }
@@ -55,8 +56,9 @@ __global__ void __launch_bounds__(THREADS) time_stats_kernel(const __nv_bfloat16
 //   w = softmax_t(e);  mu = sum_t x w;  sg = sqrt(clamp(sum_t x^2 w - mu^2, 1e-4))
 // e, x: (B, T, C) bf16.  out (B, 2C) = [mu | sg]; saved per (b, c): max_t e, sum_t exp(e - max), q = sum x^2 w.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(THREADS) asp_fwd_kernel(const __nv_bfloat16* __restrict__ e, long long e_ld,
-                                                           const __nv_bfloat16* __restrict__ x, long long x_ld, int T, int C,
+template <typename AT>
+__global__ void __launch_bounds__(THREADS) asp_fwd_kernel(const AT* __restrict__ e, long long e_ld,
+                                                           const AT* __restrict__ x, long long x_ld, int T, int C,
                                                            float* __restrict__ out, float* __restrict__ smax, float* __restrict__ ssum,
                                                            float* __restrict__ sq) {
   __shared__ float sh[4][TG][CT * 8 + 8];
@@ -66,12 +68,12 @@ __global__ void __launch_bounds__(THREADS) asp_fwd_kernel(const __nv_bfloat16* _
 #pragma unroll
   for (int i = 0; i < 8; ++i) { m[i] = -INFINITY; s[i] = 0.f; sx[i] = 0.f; sxx[i] = 0.f; }
   if (c0 < C) {
-    const __nv_bfloat16* pe = e + static_cast<long long>(b) * T * e_ld + c0;
-    const __nv_bfloat16* px = x + static_cast<long long>(b) * T * x_ld + c0;
+    const AT* pe = e + static_cast<long long>(b) * T * e_ld + c0;
+    const AT* px = x + static_cast<long long>(b) * T * x_ld + c0;
     for (int t = tg; t < T; t += TG) {
       float fe[8], fx[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(pe + t * e_ld), fe);
-      unpack8(*reinterpret_cast<const bf16x8*>(px + t * x_ld), fx);
+      ld8(pe + t * e_ld, fe);
+      ld8(px + t * x_ld, fx);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float mn = fmaxf(m[i], fe[i]);
@@ -114,14 +116,16 @@ __global__ void __launch_bounds__(THREADS) asp_fwd_kernel(const __nv_bfloat16* _
 //      + dmean / T + dstd (x - mean) / ((T-1) std) [var > clamp]  (context statistics, :169-172)
 // with dq = dsg / (2 sg) [q - mu^2 > 1e-4], dmu' = dmu - 2 mu dq.
 // ---------------------------------------------------------------------------------------------
+template <typename AT>
 struct AspBwd {
-  const __nv_bfloat16* e; long long e_ld; const __nv_bfloat16* x; long long x_ld;
+  const AT* e; long long e_ld; const AT* x; long long x_ld;
   const float* out; const float* dout; const float* smax; const float* ssum; const float* sq;
   const float* cmean; const float* cstd; const float* dcmean; const float* dcstd; float clampv;
-  __nv_bfloat16* de; long long de_ld; __nv_bfloat16* dx; long long dx_ld; int T, C;
+  AT* de; long long de_ld; AT* dx; long long dx_ld; int T, C;
 };
 
-__global__ void __launch_bounds__(THREADS) asp_bwd_kernel(const AspBwd p) {
+template <typename AT>
+__global__ void __launch_bounds__(THREADS) asp_bwd_kernel(const AspBwd<AT> p) {
   const int b = blockIdx.y, ct = threadIdx.x % CT, tg = threadIdx.x / CT;
   const int c0 = (blockIdx.x * CT + ct) * 8;
   if (c0 >= p.C) return;
@@ -146,8 +150,8 @@ __global__ void __launch_bounds__(THREADS) asp_bwd_kernel(const AspBwd p) {
   const long long base = static_cast<long long>(b) * p.T;
   for (int t = tg; t < p.T; t += TG) {
     float fe[8], fx[8], oe[8], ox[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(p.e + (base + t) * p.e_ld + c0), fe);
-    unpack8(*reinterpret_cast<const bf16x8*>(p.x + (base + t) * p.x_ld + c0), fx);
+    ld8(p.e + (base + t) * p.e_ld + c0, fe);
+    ld8(p.x + (base + t) * p.x_ld + c0, fx);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float pw = __expf(fe[i] - mx[i]) * rs[i];
@@ -155,17 +159,18 @@ __global__ void __launch_bounds__(THREADS) asp_bwd_kernel(const AspBwd p) {
       oe[i] = pw * (dp - dot[i]);
       ox[i] = pw * dmu[i] + 2.f * fx[i] * pw * dq[i] + k0[i] + k1[i] * (fx[i] - cm[i]);
     }
-    *reinterpret_cast<bf16x8*>(p.de + (base + t) * p.de_ld + c0) = pack8(oe);
-    *reinterpret_cast<bf16x8*>(p.dx + (base + t) * p.dx_ld + c0) = pack8(ox);
+    st8(p.de + (base + t) * p.de_ld + c0, oe);
+    st8(p.dx + (base + t) * p.dx_ld + c0, ox);
   }
 }
 
 // dx = (dx + dmean / T + dstd (x - mean) / ((T-1) std) [var > clamp]) * (x > 0):
 // context-statistics backward (ecapa_tdnn.py:169-172) fused with the ReLU mask of layer4 (:166).
-__global__ void __launch_bounds__(THREADS) ctx_bwd_mask_kernel(const __nv_bfloat16* __restrict__ x, long long x_ld,
+template <typename AT>
+__global__ void __launch_bounds__(THREADS) ctx_bwd_mask_kernel(const AT* __restrict__ x, long long x_ld,
                                                                 const float* __restrict__ cmean, const float* __restrict__ cstd,
                                                                 const float* __restrict__ dcmean, const float* __restrict__ dcstd,
-                                                                float clampv, __nv_bfloat16* __restrict__ dx, long long dx_ld,
+                                                                float clampv, AT* __restrict__ dx, long long dx_ld,
                                                                 int T, int C) {
   const int b = blockIdx.y, ct = threadIdx.x % CT, tg = threadIdx.x / CT;
   const int c0 = (blockIdx.x * CT + ct) * 8;
@@ -182,11 +187,11 @@ __global__ void __launch_bounds__(THREADS) ctx_bwd_mask_kernel(const __nv_bfloat
   const long long base = static_cast<long long>(b) * T;
   for (int t = tg; t < T; t += TG) {
     float fx[8], fd[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(x + (base + t) * x_ld + c0), fx);
-    unpack8(*reinterpret_cast<const bf16x8*>(dx + (base + t) * dx_ld + c0), fd);
+    ld8(x + (base + t) * x_ld + c0, fx);
+    ld8(dx + (base + t) * dx_ld + c0, fd);
 #pragma unroll
     for (int i = 0; i < 8; ++i) fd[i] = fx[i] > 0.f ? fd[i] + k0[i] + k1[i] * (fx[i] - cm[i]) : 0.f;
-    *reinterpret_cast<bf16x8*>(dx + (base + t) * dx_ld + c0) = pack8(fd);
+    st8(dx + (base + t) * dx_ld + c0, fd);
   }
 }
 
@@ -194,9 +199,10 @@ __global__ void __launch_bounds__(THREADS) ctx_bwd_mask_kernel(const __nv_bfloat
 // SE gate application + residual:  out = x * g[b, c] + res        (ecapa_tdnn.py:27-28, :93)
 // backward pieces:  dg[b, c] = sum_t dout * x;   dx = dout * g + ds[b, c] / T  [* (mask > 0)]
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) scale_residual_kernel(const __nv_bfloat16* __restrict__ x, long long x_ld,
-                                                              const float* __restrict__ g, const __nv_bfloat16* __restrict__ res,
-                                                              long long res_ld, __nv_bfloat16* __restrict__ out, long long out_ld,
+template <typename AT>
+__global__ void __launch_bounds__(256) scale_residual_kernel(const AT* __restrict__ x, long long x_ld,
+                                                              const float* __restrict__ g, const AT* __restrict__ res,
+                                                              long long res_ld, AT* __restrict__ out, long long out_ld,
                                                               long long M, int T, int C) {
   const int cpr = C >> 3;
   const long long total = M * cpr;
@@ -206,18 +212,19 @@ __global__ void __launch_bounds__(256) scale_residual_kernel(const __nv_bfloat16
     const int c0 = static_cast<int>(i - m * cpr) * 8;
     const long long b = m / T;
     float f[8], r[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(x + m * x_ld + c0), f);
-    if (res) unpack8(*reinterpret_cast<const bf16x8*>(res + m * res_ld + c0), r);
+    ld8(x + m * x_ld + c0, f);
+    if (res) ld8(res + m * res_ld + c0, r);
     const float4 g0 = *reinterpret_cast<const float4*>(g + b * C + c0), g1 = *reinterpret_cast<const float4*>(g + b * C + c0 + 4);
     const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
     for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], gg[k], res ? r[k] : 0.f);
-    *reinterpret_cast<bf16x8*>(out + m * out_ld + c0) = pack8(f);
+    st8(out + m * out_ld + c0, f);
   }
 }
 
-__global__ void __launch_bounds__(THREADS) se_dgate_kernel(const __nv_bfloat16* __restrict__ dout, long long d_ld,
-                                                            const __nv_bfloat16* __restrict__ x, long long x_ld, int T, int C,
+template <typename AT>
+__global__ void __launch_bounds__(THREADS) se_dgate_kernel(const AT* __restrict__ dout, long long d_ld,
+                                                            const AT* __restrict__ x, long long x_ld, int T, int C,
                                                             float* __restrict__ dg) {
   __shared__ float sh[TG][CT * 8 + 8];
   const int b = blockIdx.y, ct = threadIdx.x % CT, tg = threadIdx.x / CT;
@@ -229,8 +236,8 @@ __global__ void __launch_bounds__(THREADS) se_dgate_kernel(const __nv_bfloat16* 
     const long long base = static_cast<long long>(b) * T;
     for (int t = tg; t < T; t += TG) {
       float fd[8], fx[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(dout + (base + t) * d_ld + c0), fd);
-      unpack8(*reinterpret_cast<const bf16x8*>(x + (base + t) * x_ld + c0), fx);
+      ld8(dout + (base + t) * d_ld + c0, fd);
+      ld8(x + (base + t) * x_ld + c0, fx);
 #pragma unroll
       for (int i = 0; i < 8; ++i) s[i] = fmaf(fd[i], fx[i], s[i]);
     }
@@ -247,9 +254,10 @@ __global__ void __launch_bounds__(THREADS) se_dgate_kernel(const __nv_bfloat16* 
   }
 }
 
-__global__ void __launch_bounds__(256) se_apply_bwd_kernel(const __nv_bfloat16* __restrict__ dout, long long d_ld,
+template <typename AT>
+__global__ void __launch_bounds__(256) se_apply_bwd_kernel(const AT* __restrict__ dout, long long d_ld,
                                                             const float* __restrict__ g, const float* __restrict__ ds,
-                                                            __nv_bfloat16* __restrict__ dx, long long dx_ld, long long M, int T, int C) {
+                                                            AT* __restrict__ dx, long long dx_ld, long long M, int T, int C) {
   const int cpr = C >> 3;
   const long long total = M * cpr;
   const float invT = 1.f / T;
@@ -259,10 +267,10 @@ __global__ void __launch_bounds__(256) se_apply_bwd_kernel(const __nv_bfloat16* 
     const int c0 = static_cast<int>(i - m * cpr) * 8;
     const long long b = m / T;
     float f[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(dout + m * d_ld + c0), f);
+    ld8(dout + m * d_ld + c0, f);
 #pragma unroll
     for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], g[b * C + c0 + k], ds[b * C + c0 + k] * invT);
-    *reinterpret_cast<bf16x8*>(dx + m * dx_ld + c0) = pack8(f);
+    st8(dx + m * dx_ld + c0, f);
   }
 }
 
@@ -338,30 +346,32 @@ __global__ void sigmoid_bwd_kernel(const float* __restrict__ dy, const float* __
 }
 
 // channel-slice copy / masked copy: dst[m][c] = src[m][c] * (mask[m][c] > 0 if mask)
-__global__ void __launch_bounds__(256) copy_channels_kernel(const __nv_bfloat16* __restrict__ src, long long s_ld,
-                                                             const __nv_bfloat16* __restrict__ mask, long long m_ld,
-                                                             __nv_bfloat16* __restrict__ dst, long long d_ld, long long M, int C) {
+template <typename AT>
+__global__ void __launch_bounds__(256) copy_channels_kernel(const AT* __restrict__ src, long long s_ld,
+                                                             const AT* __restrict__ mask, long long m_ld,
+                                                             AT* __restrict__ dst, long long d_ld, long long M, int C) {
   const int cpr = C >> 3;
   const long long total = M * cpr;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long m = i / cpr;
     const int c0 = static_cast<int>(i - m * cpr) * 8;
-    bf16x8 v = *reinterpret_cast<const bf16x8*>(src + m * s_ld + c0);
+    V8<AT> v = ldv8(src + m * s_ld + c0);
     if (mask) {
       float f[8], k[8];
       unpack8(v, f);
-      unpack8(*reinterpret_cast<const bf16x8*>(mask + m * m_ld + c0), k);
+      ld8(mask + m * m_ld + c0, k);
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = k[j] > 0.f ? f[j] : 0.f;
-      v = pack8(f);
+      packv(f, v);
     }
-    *reinterpret_cast<bf16x8*>(dst + m * d_ld + c0) = v;
+    stv8(dst + m * d_ld + c0, v);
   }
 }
 
 // out[c] += sum_m x[m][c]   (conv bias gradients)
-__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ld, long long M, int C,
+template <typename AT>
+__global__ void __launch_bounds__(256) colsum_kernel(const AT* __restrict__ x, long long ld, long long M, int C,
                                                       float* __restrict__ out) {
   extern __shared__ float sh[];                 // [256][8]
   const int cpr = C >> 3;
@@ -373,7 +383,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
   if (tr < rows_per_it) {
     for (long long m = static_cast<long long>(blockIdx.x) * rows_per_it + tr; m < M; m += static_cast<long long>(gridDim.x) * rows_per_it) {
       float f[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(x + m * ld + tc * 8), f);
+      ld8(x + m * ld + tc * 8, f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) s[i] += f[i];
     }
@@ -398,25 +408,44 @@ static int ew_grid(long long items, int per_block) {
 
 using namespace air_ecapa;
 
-extern "C" int air_time_stats_fwd(const void* x, long long x_ld, int B, int T, int C, float* mean_out, float* std_out,
+template <typename AT>
+static int time_stats_fwd_impl(const void* x, long long x_ld, int B, int T, int C, float* mean_out, float* std_out,
                                   float clampv, cudaStream_t stream) {
   if (!x || !mean_out || B <= 0 || T < 2 || C % 8 != 0 || x_ld % 8 != 0) return AIR_ERR_ARG;
   dim3 grid((C + CT * 8 - 1) / (CT * 8), B);
-  time_stats_kernel<<<grid, THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), x_ld, T, C, mean_out, std_out, clampv);
+  time_stats_kernel<AT><<<grid, THREADS, 0, stream>>>(reinterpret_cast<const AT*>(x), x_ld, T, C, mean_out, std_out, clampv);
   return air_launch_status();
 }
+extern "C" int air_time_stats_fwd(const void* x, long long x_ld, int B, int T, int C, float* mean_out, float* std_out,
+                                  float clampv, cudaStream_t stream) {
+  return time_stats_fwd_impl<__nv_bfloat16>(x, x_ld, B, T, C, mean_out, std_out, clampv, stream);
+}
+extern "C" int air_time_stats_fwd_f32(const void* x, long long x_ld, int B, int T, int C, float* mean_out, float* std_out,
+                                  float clampv, cudaStream_t stream) {
+  return time_stats_fwd_impl<float>(x, x_ld, B, T, C, mean_out, std_out, clampv, stream);
+}
 
-extern "C" int air_ecapa_asp_fwd(const void* e, long long e_ld, const void* x, long long x_ld, int B, int T, int C,
+template <typename AT>
+static int ecapa_asp_fwd_impl(const void* e, long long e_ld, const void* x, long long x_ld, int B, int T, int C,
                                  float* out, float* save_max, float* save_sum, float* save_q, cudaStream_t stream) {
   if (!e || !x || !out || !save_max || !save_sum || !save_q || B <= 0 || T < 1 || C % 8 != 0 || e_ld % 8 != 0 || x_ld % 8 != 0)
     return AIR_ERR_ARG;
   dim3 grid((C + CT * 8 - 1) / (CT * 8), B);
-  asp_fwd_kernel<<<grid, THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(e), e_ld,
-                                               reinterpret_cast<const __nv_bfloat16*>(x), x_ld, T, C, out, save_max, save_sum, save_q);
+  asp_fwd_kernel<AT><<<grid, THREADS, 0, stream>>>(reinterpret_cast<const AT*>(e), e_ld,
+                                               reinterpret_cast<const AT*>(x), x_ld, T, C, out, save_max, save_sum, save_q);
   return air_launch_status();
 }
+extern "C" int air_ecapa_asp_fwd(const void* e, long long e_ld, const void* x, long long x_ld, int B, int T, int C,
+                                 float* out, float* save_max, float* save_sum, float* save_q, cudaStream_t stream) {
+  return ecapa_asp_fwd_impl<__nv_bfloat16>(e, e_ld, x, x_ld, B, T, C, out, save_max, save_sum, save_q, stream);
+}
+extern "C" int air_ecapa_asp_fwd_f32(const void* e, long long e_ld, const void* x, long long x_ld, int B, int T, int C,
+                                 float* out, float* save_max, float* save_sum, float* save_q, cudaStream_t stream) {
+  return ecapa_asp_fwd_impl<float>(e, e_ld, x, x_ld, B, T, C, out, save_max, save_sum, save_q, stream);
+}
 
-extern "C" int air_ecapa_asp_bwd(const void* e, long long e_ld, const void* x, long long x_ld, int B, int T, int C,
+template <typename AT>
+static int ecapa_asp_bwd_impl(const void* e, long long e_ld, const void* x, long long x_ld, int B, int T, int C,
                                  const float* out, const float* dout, const float* save_max, const float* save_sum,
                                  const float* save_q, const float* ctx_mean, const float* ctx_std, const float* dctx_mean,
                                  const float* dctx_std, float clampv, void* de, long long de_ld, void* dx, long long dx_ld,
@@ -424,51 +453,103 @@ extern "C" int air_ecapa_asp_bwd(const void* e, long long e_ld, const void* x, l
   if (!e || !x || !out || !dout || !save_max || !save_sum || !save_q || !ctx_mean || !ctx_std || !dctx_mean || !dctx_std || !de || !dx)
     return AIR_ERR_ARG;
   if (B <= 0 || T < 2 || C % 8 != 0 || (e_ld | x_ld | de_ld | dx_ld) % 8 != 0) return AIR_ERR_ARG;
-  AspBwd p{reinterpret_cast<const __nv_bfloat16*>(e), e_ld, reinterpret_cast<const __nv_bfloat16*>(x), x_ld, out, dout,
+  AspBwd<AT> p{reinterpret_cast<const AT*>(e), e_ld, reinterpret_cast<const AT*>(x), x_ld, out, dout,
            save_max, save_sum, save_q, ctx_mean, ctx_std, dctx_mean, dctx_std, clampv,
-           reinterpret_cast<__nv_bfloat16*>(de), de_ld, reinterpret_cast<__nv_bfloat16*>(dx), dx_ld, T, C};
+           reinterpret_cast<AT*>(de), de_ld, reinterpret_cast<AT*>(dx), dx_ld, T, C};
   dim3 grid((C + CT * 8 - 1) / (CT * 8), B);
-  asp_bwd_kernel<<<grid, THREADS, 0, stream>>>(p);
+  asp_bwd_kernel<AT><<<grid, THREADS, 0, stream>>>(p);
   return air_launch_status();
 }
+extern "C" int air_ecapa_asp_bwd(const void* e, long long e_ld, const void* x, long long x_ld, int B, int T, int C,
+                                 const float* out, const float* dout, const float* save_max, const float* save_sum,
+                                 const float* save_q, const float* ctx_mean, const float* ctx_std, const float* dctx_mean,
+                                 const float* dctx_std, float clampv, void* de, long long de_ld, void* dx, long long dx_ld,
+                                 cudaStream_t stream) {
+  return ecapa_asp_bwd_impl<__nv_bfloat16>(e, e_ld, x, x_ld, B, T, C, out, dout, save_max, save_sum, save_q, ctx_mean, ctx_std, dctx_mean, dctx_std, clampv, de, de_ld, dx, dx_ld, stream);
+}
+extern "C" int air_ecapa_asp_bwd_f32(const void* e, long long e_ld, const void* x, long long x_ld, int B, int T, int C,
+                                 const float* out, const float* dout, const float* save_max, const float* save_sum,
+                                 const float* save_q, const float* ctx_mean, const float* ctx_std, const float* dctx_mean,
+                                 const float* dctx_std, float clampv, void* de, long long de_ld, void* dx, long long dx_ld,
+                                 cudaStream_t stream) {
+  return ecapa_asp_bwd_impl<float>(e, e_ld, x, x_ld, B, T, C, out, dout, save_max, save_sum, save_q, ctx_mean, ctx_std, dctx_mean, dctx_std, clampv, de, de_ld, dx, dx_ld, stream);
+}
 
-extern "C" int air_ctx_stats_bwd_mask(const void* x, long long x_ld, int B, int T, int C, const float* ctx_mean,
+template <typename AT>
+static int ctx_stats_bwd_mask_impl(const void* x, long long x_ld, int B, int T, int C, const float* ctx_mean,
                                       const float* ctx_std, const float* dctx_mean, const float* dctx_std, float clampv,
                                       void* dx, long long dx_ld, cudaStream_t stream) {
   if (!x || !ctx_mean || !ctx_std || !dctx_mean || !dctx_std || !dx || B <= 0 || T < 2 || C % 8 != 0 || (x_ld | dx_ld) % 8 != 0)
     return AIR_ERR_ARG;
   dim3 grid((C + CT * 8 - 1) / (CT * 8), B);
-  ctx_bwd_mask_kernel<<<grid, THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), x_ld, ctx_mean, ctx_std,
-                                                    dctx_mean, dctx_std, clampv, reinterpret_cast<__nv_bfloat16*>(dx), dx_ld, T, C);
+  ctx_bwd_mask_kernel<AT><<<grid, THREADS, 0, stream>>>(reinterpret_cast<const AT*>(x), x_ld, ctx_mean, ctx_std,
+                                                    dctx_mean, dctx_std, clampv, reinterpret_cast<AT*>(dx), dx_ld, T, C);
   return air_launch_status();
 }
+extern "C" int air_ctx_stats_bwd_mask(const void* x, long long x_ld, int B, int T, int C, const float* ctx_mean,
+                                      const float* ctx_std, const float* dctx_mean, const float* dctx_std, float clampv,
+                                      void* dx, long long dx_ld, cudaStream_t stream) {
+  return ctx_stats_bwd_mask_impl<__nv_bfloat16>(x, x_ld, B, T, C, ctx_mean, ctx_std, dctx_mean, dctx_std, clampv, dx, dx_ld, stream);
+}
+extern "C" int air_ctx_stats_bwd_mask_f32(const void* x, long long x_ld, int B, int T, int C, const float* ctx_mean,
+                                      const float* ctx_std, const float* dctx_mean, const float* dctx_std, float clampv,
+                                      void* dx, long long dx_ld, cudaStream_t stream) {
+  return ctx_stats_bwd_mask_impl<float>(x, x_ld, B, T, C, ctx_mean, ctx_std, dctx_mean, dctx_std, clampv, dx, dx_ld, stream);
+}
 
-extern "C" int air_scale_residual_fwd(const void* x, long long x_ld, const float* gate, const void* res, long long res_ld,
+template <typename AT>
+static int scale_residual_fwd_impl(const void* x, long long x_ld, const float* gate, const void* res, long long res_ld,
                                       void* out, long long out_ld, int B, int T, int C, cudaStream_t stream) {
   if (!x || !gate || !out || B <= 0 || T <= 0 || C % 8 != 0 || (x_ld | out_ld) % 8 != 0 || (res && res_ld % 8 != 0)) return AIR_ERR_ARG;
   const long long M = static_cast<long long>(B) * T;
-  scale_residual_kernel<<<ew_grid(M * (C / 8), 256 * 4), 256, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), x_ld, gate, reinterpret_cast<const __nv_bfloat16*>(res), res_ld,
-      reinterpret_cast<__nv_bfloat16*>(out), out_ld, M, T, C);
+  scale_residual_kernel<AT><<<ew_grid(M * (C / 8), 256 * 4), 256, 0, stream>>>(
+      reinterpret_cast<const AT*>(x), x_ld, gate, reinterpret_cast<const AT*>(res), res_ld,
+      reinterpret_cast<AT*>(out), out_ld, M, T, C);
   return air_launch_status();
 }
+extern "C" int air_scale_residual_fwd(const void* x, long long x_ld, const float* gate, const void* res, long long res_ld,
+                                      void* out, long long out_ld, int B, int T, int C, cudaStream_t stream) {
+  return scale_residual_fwd_impl<__nv_bfloat16>(x, x_ld, gate, res, res_ld, out, out_ld, B, T, C, stream);
+}
+extern "C" int air_scale_residual_fwd_f32(const void* x, long long x_ld, const float* gate, const void* res, long long res_ld,
+                                      void* out, long long out_ld, int B, int T, int C, cudaStream_t stream) {
+  return scale_residual_fwd_impl<float>(x, x_ld, gate, res, res_ld, out, out_ld, B, T, C, stream);
+}
 
-extern "C" int air_se_dgate(const void* dout, long long d_ld, const void* x, long long x_ld, int B, int T, int C, float* dgate,
+template <typename AT>
+static int se_dgate_impl(const void* dout, long long d_ld, const void* x, long long x_ld, int B, int T, int C, float* dgate,
                             cudaStream_t stream) {
   if (!dout || !x || !dgate || B <= 0 || T <= 0 || C % 8 != 0 || (d_ld | x_ld) % 8 != 0) return AIR_ERR_ARG;
   dim3 grid((C + CT * 8 - 1) / (CT * 8), B);
-  se_dgate_kernel<<<grid, THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dout), d_ld,
-                                                reinterpret_cast<const __nv_bfloat16*>(x), x_ld, T, C, dgate);
+  se_dgate_kernel<AT><<<grid, THREADS, 0, stream>>>(reinterpret_cast<const AT*>(dout), d_ld,
+                                                reinterpret_cast<const AT*>(x), x_ld, T, C, dgate);
   return air_launch_status();
 }
+extern "C" int air_se_dgate(const void* dout, long long d_ld, const void* x, long long x_ld, int B, int T, int C, float* dgate,
+                            cudaStream_t stream) {
+  return se_dgate_impl<__nv_bfloat16>(dout, d_ld, x, x_ld, B, T, C, dgate, stream);
+}
+extern "C" int air_se_dgate_f32(const void* dout, long long d_ld, const void* x, long long x_ld, int B, int T, int C, float* dgate,
+                            cudaStream_t stream) {
+  return se_dgate_impl<float>(dout, d_ld, x, x_ld, B, T, C, dgate, stream);
+}
 
-extern "C" int air_se_apply_bwd(const void* dout, long long d_ld, const float* gate, const float* dmean, void* dx, long long dx_ld,
+template <typename AT>
+static int se_apply_bwd_impl(const void* dout, long long d_ld, const float* gate, const float* dmean, void* dx, long long dx_ld,
                                 int B, int T, int C, cudaStream_t stream) {
   if (!dout || !gate || !dmean || !dx || B <= 0 || T <= 0 || C % 8 != 0 || (d_ld | dx_ld) % 8 != 0) return AIR_ERR_ARG;
   const long long M = static_cast<long long>(B) * T;
-  se_apply_bwd_kernel<<<ew_grid(M * (C / 8), 256 * 4), 256, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(dout), d_ld, gate, dmean, reinterpret_cast<__nv_bfloat16*>(dx), dx_ld, M, T, C);
+  se_apply_bwd_kernel<AT><<<ew_grid(M * (C / 8), 256 * 4), 256, 0, stream>>>(
+      reinterpret_cast<const AT*>(dout), d_ld, gate, dmean, reinterpret_cast<AT*>(dx), dx_ld, M, T, C);
   return air_launch_status();
+}
+extern "C" int air_se_apply_bwd(const void* dout, long long d_ld, const float* gate, const float* dmean, void* dx, long long dx_ld,
+                                int B, int T, int C, cudaStream_t stream) {
+  return se_apply_bwd_impl<__nv_bfloat16>(dout, d_ld, gate, dmean, dx, dx_ld, B, T, C, stream);
+}
+extern "C" int air_se_apply_bwd_f32(const void* dout, long long d_ld, const float* gate, const float* dmean, void* dx, long long dx_ld,
+                                int B, int T, int C, cudaStream_t stream) {
+  return se_apply_bwd_impl<float>(dout, d_ld, gate, dmean, dx, dx_ld, B, T, C, stream);
 }
 
 extern "C" int air_bn1d_f32_fwd(const float* x, float* y, int M, int C, int relu_in, const float* gamma, const float* beta,
@@ -500,22 +581,38 @@ extern "C" int air_sigmoid_bwd(const float* dy, const float* y, float* dx, long 
   return air_launch_status();
 }
 
-extern "C" int air_copy_channels(const void* src, long long s_ld, const void* mask, long long m_ld, void* dst, long long d_ld,
+template <typename AT>
+static int copy_channels_impl(const void* src, long long s_ld, const void* mask, long long m_ld, void* dst, long long d_ld,
                                  long long M, int C, cudaStream_t stream) {
   if (!src || !dst || M <= 0 || C % 8 != 0 || (s_ld | d_ld) % 8 != 0 || (mask && m_ld % 8 != 0)) return AIR_ERR_ARG;
-  copy_channels_kernel<<<ew_grid(M * (C / 8), 256 * 4), 256, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(src), s_ld, reinterpret_cast<const __nv_bfloat16*>(mask), m_ld,
-      reinterpret_cast<__nv_bfloat16*>(dst), d_ld, M, C);
+  copy_channels_kernel<AT><<<ew_grid(M * (C / 8), 256 * 4), 256, 0, stream>>>(
+      reinterpret_cast<const AT*>(src), s_ld, reinterpret_cast<const AT*>(mask), m_ld,
+      reinterpret_cast<AT*>(dst), d_ld, M, C);
   return air_launch_status();
 }
+extern "C" int air_copy_channels(const void* src, long long s_ld, const void* mask, long long m_ld, void* dst, long long d_ld,
+                                 long long M, int C, cudaStream_t stream) {
+  return copy_channels_impl<__nv_bfloat16>(src, s_ld, mask, m_ld, dst, d_ld, M, C, stream);
+}
+extern "C" int air_copy_channels_f32(const void* src, long long s_ld, const void* mask, long long m_ld, void* dst, long long d_ld,
+                                 long long M, int C, cudaStream_t stream) {
+  return copy_channels_impl<float>(src, s_ld, mask, m_ld, dst, d_ld, M, C, stream);
+}
 
-extern "C" int air_colsum_bf16(const void* x, long long ld, long long M, int C, float* out, cudaStream_t stream) {
+template <typename AT>
+static int colsum_bf16_impl(const void* x, long long ld, long long M, int C, float* out, cudaStream_t stream) {
   if (!x || !out || M <= 0 || C % 8 != 0 || C > 2048 || ld % 8 != 0) return AIR_ERR_ARG;
   const int rows_per_it = 256 / (C / 8);
   if (rows_per_it < 1) return AIR_ERR_UNSUPPORTED;
   long long blocks = (M + rows_per_it * 16 - 1) / (rows_per_it * 16);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  colsum_kernel<<<static_cast<int>(blocks), 256, 256 * 8 * sizeof(float), stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), ld, M, C, out);
+  colsum_kernel<AT><<<static_cast<int>(blocks), 256, 256 * 8 * sizeof(float), stream>>>(
+      reinterpret_cast<const AT*>(x), ld, M, C, out);
   return air_launch_status();
+}
+extern "C" int air_colsum_bf16(const void* x, long long ld, long long M, int C, float* out, cudaStream_t stream) {
+  return colsum_bf16_impl<__nv_bfloat16>(x, ld, M, C, out, stream);
+}
+extern "C" int air_colsum_f32(const void* x, long long ld, long long M, int C, float* out, cudaStream_t stream) {
+  return colsum_bf16_impl<float>(x, ld, M, C, out, stream);
 }

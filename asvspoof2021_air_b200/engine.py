@@ -81,8 +81,9 @@ class ConvLayer:
     """One convolution: geometry, weight views, packed bf16 operands, fprop / dgrad / wgrad launches."""
 
     def __init__(self, store, name, cin, cout, kh, kw, sh=1, sw=1, ph=0, pw=0, dh=1, dw=1,
-                 bias=False, need_dgrad=True, cin_pad=None):
+                 bias=False, need_dgrad=True, cin_pad=None, need_fprop=True):
         self.store, self.name = store, name
+        self.need_fprop = need_fprop
         self.cin, self.cout = cin, cout
         self.cin_g = cin_pad or cin                 # channels the gather sees (ECAPA conv1: 60 -> 64)
         self.kh, self.kw, self.sh, self.sw, self.ph, self.pw, self.dh, self.dw = kh, kw, sh, sw, ph, pw, dh, dw
@@ -142,10 +143,11 @@ class ConvLayer:
     def pack(self):
         """Per-tensor launches (used when the layer is not part of a PackPlan)."""
         w = self._pack_source()
-        ops.pack_weights(w, 0, self.cin_g, self.cout, self.taps, self.wpk)
+        if self.need_fprop:
+            ops.pack_weights(w, 0, self.cin_g, self.cout, self.taps, self.wpk)
         if self.need_dgrad:
             ops.pack_weights(w, 1, self.cin_g, self.cout, self.taps, self.wpk_d)
-        if self.wpk3 is not None:
+        if self.wpk3 is not None and self.need_fprop:
             ops.pack_patch(w, self.cin, self.cout, self.taps, 0, self.wpk3)
         if self.wpk3_d is not None:
             ops.pack_patch(w, self.cout, self.cin, self.taps, 1, self.wpk3_d)
@@ -242,6 +244,99 @@ class ConvLayer:
         else:
             ops.conv_wgrad(x, x_ld, B, H, W, self.cin_g, dy, dy_ld, Ho, Wo, self.cout, self.kh, self.kw, self.sh,
                            self.sw, self.ph, self.pw, self.dh, self.dw, self.store.grad(self.name + ".weight"))
+
+
+class Scratch:
+    """Grow-only device scratch buffers of an engine (the split operands of the fp32 parity mode)."""
+
+    def __init__(self, device):
+        self.device, self.bufs = device, {}
+
+    def get(self, key, numel, dtype=BF16):
+        b = self.bufs.get(key)
+        if b is None or b.numel() < numel or b.dtype != dtype:
+            b = self.bufs[key] = torch.empty(int(numel), device=self.device, dtype=dtype)
+        return b[:numel]
+
+
+class _DerivedStore:
+    """Stands in for the ParamStore inside the helper layers of a SplitConvLayer: `<name>.weight` resolves to a derived
+    fp32 tensor (split terms of the master weight), every other name to the real store."""
+
+    def __init__(self, real, name, weight):
+        self.real, self.key, self.weight, self.device = real, name + ".weight", weight, real.device
+
+    def view(self, name):
+        return self.weight if name == self.key else self.real.view(name)
+
+
+class SplitConvLayer(ConvLayer):
+    """fp32 parity mode of one convolution: float activations / gradients in and out, the contraction
+    on the SAME bf16 tcgen05 kernels with 3-term split operands concatenated along the contraction axis
+    (csrc/split.cu):
+
+        fprop : [hi_x | lo_x | hi_x] (3 Cin)  *  [hi_w | hi_w | lo_w]           one launch, fp32 epilogue
+        dgrad : [hi_dy | lo_dy | hi_dy] (3 Cout) * [hi_w ; hi_w ; lo_w]         one launch, fp32 epilogue
+        wgrad : (hi_x, hi_dy) + (lo_x, hi_dy) + (hi_x, lo_dy)                   three launches into the fp32 gradient
+
+    Each product is exact in the fp32 accumulator; the dropped lo*lo term and the 16 significant bits of a hi + lo pair
+    leave a relative error of ~2^-16 per layer instead of the 2^-9 of a bf16 operand."""
+    X_MASK, W_MASK = 0b010, 0b100          # lo positions in [hi, lo, hi] and [hi, hi, lo]
+
+    def __init__(self, store, name, cin, cout, kh, kw, sh=1, sw=1, ph=0, pw=0, dh=1, dw=1,
+                 bias=False, need_dgrad=True, cin_pad=None, scratch=None):
+        super().__init__(store, name, cin, cout, kh, kw, sh, sw, ph, pw, dh, dw, bias, need_dgrad, cin_pad, need_fprop=False)
+        self.scratch = scratch
+        dev, cg = store.device, self.cin_g
+        self.wf = torch.zeros(cout, kh, kw, 3 * cg, device=dev)
+        self.f = ConvLayer(_DerivedStore(store, name, self.wf), name, 3 * cg, cout, kh, kw, sh, sw, ph, pw, dh, dw,
+                           bias=bias, need_dgrad=False)
+        self.d = None
+        if need_dgrad:
+            self.wd = torch.zeros(3 * cout, kh, kw, cg, device=dev)
+            self.d = ConvLayer(_DerivedStore(store, name, self.wd), name, cg, 3 * cout, kh, kw, sh, sw, ph, pw, dh, dw,
+                               bias=False, need_dgrad=True, need_fprop=False)
+        self.wpk = self.wpk_d = self.wpk3 = self.wpk3_d = None        # the plain operands are never used in this mode
+
+    def add_pack_jobs(self, plan):
+        return False                                  # packed per layer by pack(): derived weights first
+
+    def pack(self):
+        w = self._pack_source()                       # fp32 [cout][taps][cin_g]
+        rows, cg = self.cout * self.taps, self.cin_g
+        ops.split_terms(w, cg, rows, cg, self.wf, 3 * cg, 3, self.W_MASK)
+        self.f.pack()
+        if self.d is not None:
+            n = w.numel()
+            ops.split_terms(w, n, 1, n, self.wd, 3 * n, 3, self.W_MASK)       # three whole-tensor copies: [hi ; hi ; lo]
+            self.d.pack()
+
+    def _split(self, key, t, ld, M, C, nterms, mask):
+        buf = self.scratch.get(key, M * nterms * C).view(M, nterms * C)
+        return ops.split_terms(t, ld, M, C, buf, nterms * C, nterms, mask)
+
+    def fprop(self, x, x_ld, B, H, W, out, out_ld, res=None, res_ld=0, relu=False, stats=None):
+        xs = self._split("a", x, x_ld, B * H * W, self.cin_g, 3, self.X_MASK)
+        r = self.f.fprop(xs, 3 * self.cin_g, B, H, W, out, out_ld, res, res_ld, relu, stats)
+        self.stats_fused = self.f.stats_fused
+        return r
+
+    def fprop_affine(self, x, x_ld, B, H, W, out, out_ld, relu, scale, shift):
+        xs = self._split("a", x, x_ld, B * H * W, self.cin_g, 3, self.X_MASK)
+        return self.f.fprop_affine(xs, 3 * self.cin_g, B, H, W, out, out_ld, relu, scale, shift)
+
+    def dgrad(self, dy, dy_ld, B, H, W, dx, dx_ld, accumulate=False, res=None, res_ld=0, out2=None, out2_ld=0):
+        Ho, Wo = self.out_hw(H, W)
+        dys = self._split("a", dy, dy_ld, B * Ho * Wo, self.cout, 3, self.X_MASK)
+        self.d.dgrad(dys, 3 * self.cout, B, H, W, dx, dx_ld, accumulate, res, res_ld, out2, out2_ld)
+
+    def wgrad(self, x, x_ld, B, H, W, dy, dy_ld):
+        Ho, Wo = self.out_hw(H, W)
+        cg, co = self.cin_g, self.cout
+        xs = self._split("a", x, x_ld, B * H * W, cg, 2, 0b10)                  # [hi | lo]
+        dys = self._split("b", dy, dy_ld, B * Ho * Wo, co, 2, 0b10)
+        for xi, di in ((0, 0), (1, 0), (0, 1)):
+            super().wgrad(xs[:, xi * cg:], 2 * cg, B, H, W, dys[:, di * co:], 2 * co)
 
 
 class BNLayer:
@@ -363,7 +458,13 @@ class ResNetEngine(AsyncWgrad):
     """Forward / backward of ResNet(num_nodes=3, enc_dim, '18', nclasses) for a fixed batch size on
     channels-last bf16 activations.  Input: (B, 60, T) bf16 from the fused LFCC kernel."""
 
-    def __init__(self, enc_dim=256, nclasses=2, device="cuda", train_head_mu=False, F=60, num_nodes=3):
+    def __init__(self, enc_dim=256, nclasses=2, device="cuda", train_head_mu=False, F=60, num_nodes=3, precision="bf16"):
+        """precision: "bf16" (the product path: bf16 activations, bf16 tensor-core operands) or "fp32" (parity mode:
+        float activations, 3-term split operands on the same kernels; several times slower, used to show the residual
+        against the reference's fp32 arithmetic is rounding)."""
+        assert precision in ("bf16", "fp32")
+        self.precision = precision
+        self.act_dtype = BF16 if precision == "bf16" else torch.float32
         self.B, self.T, self.F = None, None, F
         self.enc_dim, self.nclasses, self.num_nodes = enc_dim, nclasses, num_nodes
         dev = torch.device(device)
@@ -392,6 +493,14 @@ class ResNetEngine(AsyncWgrad):
         st, bufs = self.store, self.buffers
 
         # ---- layers ----
+        if precision == "fp32":
+            self.scratch = Scratch(dev)
+            self.overlap_wgrad = False              # the split operands of fprop / dgrad / wgrad share scratch buffers
+
+            def ConvLayer(*a, **k):                 # noqa: N802 (shadows the module-level class inside this constructor)
+                return SplitConvLayer(*a, scratch=self.scratch, **k)
+        else:
+            ConvLayer = globals()["ConvLayer"]
         self.bn1 = BNLayer(st, bufs, "bn1", 16)
         self.blocks = []
         for p, cin, planes, stride, has_sc in cfg:
@@ -432,7 +541,7 @@ class ResNetEngine(AsyncWgrad):
         assert self.H5 == 1, "conv5 must collapse the frequency axis (num_nodes == 3 for 60-dim LFCC)"
 
         def act(*shape):
-            return torch.empty(shape, device=dev, dtype=BF16)
+            return torch.empty(shape, device=dev, dtype=self.act_dtype)
         self.c1 = act(B, self.H1, self.W1, 16)
         self.z1 = act(B, self.H1, self.W1, 16)
         self.g_z1 = act(B, self.H1, self.W1, 16)
@@ -537,7 +646,7 @@ class ResNetEngine(AsyncWgrad):
     # ---- forward --------------------------------------------------------------------------
     def forward(self, x0, training=True):
         """x0: (B, 60, T) bf16 (the fused LFCC output, layout 'resnet').  Returns (feat, mu) fp32."""
-        assert x0.dtype == BF16 and x0.is_contiguous() and x0.dim() == 3 and x0.shape[1] == self.F
+        assert x0.dtype == self.act_dtype and x0.is_contiguous() and x0.dim() == 3 and x0.shape[1] == self.F
         self.bind(x0.shape[0], x0.shape[2])
         B = self.B
         if self._packed_version != self.store.step:

@@ -15,7 +15,8 @@ import math
 import torch
 
 from . import ops
-from .engine import AsyncWgrad, BF16, BNLayer, BufferStore, ConvLayer, ParamStore, _conv1d_pt, _ident, _resolve_lazies
+from .engine import (AsyncWgrad, BF16, BNLayer, BufferStore, ConvLayer, ParamStore, Scratch, SplitConvLayer, _conv1d_pt,
+                     _ident, _resolve_lazies)
 
 CLAMP = 1e-4
 
@@ -48,8 +49,13 @@ class _BN1d:
 
 
 class EcapaEngine(AsyncWgrad):
-    def __init__(self, C=512, scale=8, n_out=2, n_mels=60, bottleneck=128, enc_dim=256, device="cuda", train_head=False):
+    def __init__(self, C=512, scale=8, n_out=2, n_mels=60, bottleneck=128, enc_dim=256, device="cuda", train_head=False,
+                 precision="bf16"):
+        """precision: "bf16" (product path) or "fp32" (parity mode, see ResNetEngine / DESIGN.md section 5)."""
         assert C % scale == 0 and (C // scale) % 16 == 0
+        assert precision in ("bf16", "fp32")
+        self.precision = precision
+        self.act_dtype = BF16 if precision == "bf16" else torch.float32
         self.C, self.scale, self.width, self.n_out, self.n_mels = C, scale, C // scale, n_out, n_mels
         self.bott, self.enc_dim = bottleneck, enc_dim
         self.mels_g = (n_mels + 7) // 8 * 8
@@ -85,6 +91,14 @@ class EcapaEngine(AsyncWgrad):
         self.buffers = BufferStore(dev)
         st, bufs = self.store, self.buffers
 
+        if precision == "fp32":
+            self.scratch = Scratch(dev)
+            self.overlap_wgrad = False              # the split operands of fprop / dgrad / wgrad share scratch buffers
+
+            def ConvLayer(*a, **k):                 # noqa: N802 (shadows the imported class inside this constructor)
+                return SplitConvLayer(*a, scratch=self.scratch, **k)
+        else:
+            ConvLayer = globals()["ConvLayer"]
         self.conv1 = ConvLayer(st, "conv1", n_mels, C, 1, 5, pw=2, bias=True, need_dgrad=False, cin_pad=self.mels_g)
         self.bn1 = BNLayer(st, bufs, "bn1", C)
         self.blocks = []
@@ -104,6 +118,11 @@ class EcapaEngine(AsyncWgrad):
         # attention.0: only the x-block of the (128, 4608) weight goes through the GEMM
         self.att0_wpk = torch.empty(ops.packed_elems(128, self.C3), device=dev, dtype=BF16)
         self.att0_wpk_d = torch.empty(ops.packed_elems(self.C3, 128), device=dev, dtype=BF16)
+        if precision == "fp32":                     # split operands of that x-block (3-term, see SplitConvLayer)
+            self.att0_wf = torch.zeros(128, 3 * self.C3, device=dev)
+            self.att0_wd = torch.zeros(3 * 128, self.C3, device=dev)
+            self.att0_wpk = torch.empty(ops.packed_elems(128, 3 * self.C3), device=dev, dtype=BF16)
+            self.att0_wpk_d = torch.empty(ops.packed_elems(self.C3, 3 * 128), device=dev, dtype=BF16)
         self.att_bn = BNLayer(st, bufs, "attention.2", 128)
         self.att3 = ConvLayer(st, "attention.3", 128, self.C3, 1, 1, bias=True)
         self.bn5 = _BN1d(st, bufs, "bn5", 2 * self.C3)
@@ -184,8 +203,16 @@ class EcapaEngine(AsyncWgrad):
         for c in self._pack_rest:
             c.pack()
         w = self.store.view("attention.0.weight")                       # [128][1][4608]
-        ops.pack_weights_ld(w, 3 * self.C3, 0, self.C3, 128, 1, self.att0_wpk)
-        ops.pack_weights_ld(w, 3 * self.C3, 1, self.C3, 128, 1, self.att0_wpk_d)
+        if self.precision == "fp32":
+            C3 = self.C3
+            ops.split_terms(w, 3 * C3, 128, C3, self.att0_wf, 3 * C3, 3, SplitConvLayer.W_MASK)      # [hi | hi | lo] per row
+            for t, lo in enumerate((0, 0, 1)):                                                  # [hi ; hi ; lo] row blocks
+                ops.split_terms(w, 3 * C3, 128, C3, self.att0_wd[t * 128:(t + 1) * 128], C3, 1, lo)
+            ops.pack_weights(self.att0_wf.view(-1), 0, 3 * C3, 128, 1, self.att0_wpk)
+            ops.pack_weights(self.att0_wd.view(-1), 1, C3, 3 * 128, 1, self.att0_wpk_d)
+        else:
+            ops.pack_weights_ld(w, 3 * self.C3, 0, self.C3, 128, 1, self.att0_wpk)
+            ops.pack_weights_ld(w, 3 * self.C3, 1, self.C3, 128, 1, self.att0_wpk_d)
         self._packed_version = self.store.step
 
     # ---- buffers ----------------------------------------------------------------------------
@@ -196,7 +223,7 @@ class EcapaEngine(AsyncWgrad):
         dev, C, W, C3 = self.device, self.C, self.width, self.C3
 
         def act(*shape):
-            return torch.empty(shape, device=dev, dtype=BF16)
+            return torch.empty(shape, device=dev, dtype=self.act_dtype)
 
         def f32(*shape):
             return torch.empty(shape, device=dev, dtype=torch.float32)
@@ -261,7 +288,7 @@ class EcapaEngine(AsyncWgrad):
     # ---- forward ----------------------------------------------------------------------------
     def forward(self, x0, training=True):
         """x0: (B, T, mels_g) bf16 channels-last LFCC (channels >= n_mels zero).  Returns (feat, logits) fp32."""
-        assert x0.dtype == BF16 and x0.dim() == 3 and x0.shape[2] == self.mels_g and x0.is_contiguous()
+        assert x0.dtype == self.act_dtype and x0.dim() == 3 and x0.shape[2] == self.mels_g and x0.is_contiguous()
         B, T = x0.shape[0], x0.shape[1]
         self.bind(B, T)
         if self._packed_version != self.store.step:
@@ -305,8 +332,14 @@ class EcapaEngine(AsyncWgrad):
         w0 = st.view("attention.0.weight").view(128, 3 * C3)
         ops.linear_fwd_ld(self.cmean, w0[:, C3:], 3 * C3, st.view("attention.0.bias"), self.u, B, 128, C3)
         ops.linear_fwd_ld(self.cstd, w0[:, 2 * C3:], 3 * C3, None, self.u, B, 128, C3, accumulate=True)
-        ops.conv_gemm_ex(self.x4, C3, B, 1, T, C3, 1, T, 1, 1, 1, 1, 0, 0, 1, 1, 0, self.att0_wpk, 128, C3,
-                         self.a1, 128, self.u, None, 0, True, 0, T)                             # :139-140 (+ReLU)
+        if self.precision == "fp32":
+            xs = ops.split_terms(self.x4, C3, M, C3, self.scratch.get("a", M * 3 * C3).view(M, 3 * C3), 3 * C3, 3,
+                                 SplitConvLayer.X_MASK)
+            ops.conv_gemm_ex(xs, 3 * C3, B, 1, T, 3 * C3, 1, T, 1, 1, 1, 1, 0, 0, 1, 1, 0, self.att0_wpk, 128, 3 * C3,
+                             self.a1, 128, self.u, None, 0, True, 0, T)
+        else:
+            ops.conv_gemm_ex(self.x4, C3, B, 1, T, C3, 1, T, 1, 1, 1, 1, 0, 0, 1, 1, 0, self.att0_wpk, 128, C3,
+                             self.a1, 128, self.u, None, 0, True, 0, T)                         # :139-140 (+ReLU)
         self._bn_fwd(self.att_bn, self.a1, 128, self.a2, 128, M, training)
         self.att3.fprop(self.a2, 128, B, 1, T, self.e, C3)                                      # :143
         ops.asp_fwd(self.e, C3, self.x4, C3, B, T, C3, self.pooled, self.smax, self.ssum, self.sq)   # :144,182-186
@@ -353,12 +386,25 @@ class EcapaEngine(AsyncWgrad):
         # attention.0: x-block through the GEMMs, mean / std blocks through the per-utterance bias
         gw0 = st.grad("attention.0.weight").view(128, 3 * C3)
         w0 = st.view("attention.0.weight").view(128, 3 * C3)
-        self._wgrad_async(ops.conv_wgrad_ld, self.x4, C3, B, 1, T, C3, self.g_a1, 128, 1, T, 128, 1, 1, 1, 1, 0, 0, 1, 1, gw0, 3 * C3)
+        if self.precision == "fp32":
+            xs = ops.split_terms(self.x4, C3, M, C3, self.scratch.get("a", M * 2 * C3).view(M, 2 * C3), 2 * C3, 2, 0b10)
+            gs = ops.split_terms(self.g_a1, 128, M, 128, self.scratch.get("b", M * 256).view(M, 256), 256, 2, 0b10)
+            for xi, gi in ((0, 0), (1, 0), (0, 1)):
+                ops.conv_wgrad_ld(xs[:, xi * C3:], 2 * C3, B, 1, T, C3, gs[:, gi * 128:], 256, 1, T, 128, 1, 1, 1, 1, 0, 0, 1, 1,
+                                  gw0, 3 * C3)
+        else:
+            self._wgrad_async(ops.conv_wgrad_ld, self.x4, C3, B, 1, T, C3, self.g_a1, 128, 1, T, 128, 1, 1, 1, 1, 0, 0, 1, 1, gw0, 3 * C3)
         ops.time_stats(self.g_a1, 128, B, T, 128, self.gu, None, -1.0)                          # sum over time
         ops.linear_bwd_ld(self.cmean, w0[:, C3:], 3 * C3, self.gu, self.dcmean, gw0[:, C3:], None, B, 128, C3)
         ops.linear_bwd_ld(self.cstd, w0[:, 2 * C3:], 3 * C3, self.gu, self.dcstd, gw0[:, 2 * C3:], None, B, 128, C3)
-        ops.conv_gemm_ex(self.g_a1, 128, B, 1, T, 128, 1, T, 1, 1, 1, 1, 0, 0, 1, 1, 1, self.att0_wpk_d, C3, 128,
-                         self.g_x4, C3, None, self.g_x4, C3, False)
+        if self.precision == "fp32":
+            gs = ops.split_terms(self.g_a1, 128, M, 128, self.scratch.get("a", M * 384).view(M, 384), 384, 3,
+                                 SplitConvLayer.X_MASK)
+            ops.conv_gemm_ex(gs, 384, B, 1, T, 384, 1, T, 1, 1, 1, 1, 0, 0, 1, 1, 1, self.att0_wpk_d, C3, 384,
+                             self.g_x4, C3, None, self.g_x4, C3, False)
+        else:
+            ops.conv_gemm_ex(self.g_a1, 128, B, 1, T, 128, 1, T, 1, 1, 1, 1, 0, 0, 1, 1, 1, self.att0_wpk_d, C3, 128,
+                             self.g_x4, C3, None, self.g_x4, C3, False)
         ops.ctx_bwd_mask(self.x4, C3, B, T, C3, self.cmean, self.cstd, self.dcmean, self.dcstd, CLAMP, self.g_x4, C3)
         # layer4 (1536 -> 1536)
         self._wgrad_async(self.layer4.wgrad, self.xcat, C3, B, 1, T, self.g_x4, C3)

@@ -16,6 +16,31 @@ def num_sms(device=None):
     return _SMS[d]
 
 
+F32 = torch.float32
+F32_OUT = 1                     # AIR_CONV_F32_OUT (include/air_b200.h): out / res / out2 of a conv are float tensors
+
+
+def _is_f32(t):
+    return t is not None and t.dtype == F32
+
+
+def _conv_flags(out, *others):
+    """flags of a conv launch from the dtype of its output; residual / second output must share it (fp32 parity mode)."""
+    f32 = _is_f32(out)
+    for t in others:
+        if t is not None and _is_f32(t) != f32:
+            raise TypeError("conv output, residual and second output must share one dtype")
+    return F32_OUT if f32 else 0
+
+
+def split_terms(x, x_ld, M, C, out, out_ld, nterms, lo_mask):
+    """fp32 rows -> bf16 (or bf16-exact fp32) split terms concatenated along the channels (csrc/split.cu)."""
+    assert x.dtype == F32
+    _lib.check(_lib.lib().air_split_terms(_lib.ptr(x), _lib.LL(x_ld), _lib.LL(M), int(C), _lib.ptr(out), _lib.LL(out_ld),
+                                          int(out.dtype == F32), int(nterms), int(lo_mask), _lib.stream_ptr()), "air_split_terms")
+    return out
+
+
 def conv_block_n(n):
     return _lib.lib().air_conv_block_n(int(n))
 
@@ -42,7 +67,7 @@ def conv_gemm(a, a_ld, B, H, W, C, Ho, Wo, kh, kw, sh, sw, ph, pw, dh, dw, mode,
     st = _lib.lib().air_conv_gemm_bf16(
         _lib.ptr(a), _lib.LL(a_ld), B, H, W, C, Ho, Wo, kh, kw, sh, sw, ph, pw, dh, dw, mode,
         _lib.ptr(wpk), N, K, _lib.ptr(out), _lib.LL(out_ld), _lib.ptr(bias), _lib.ptr(res), _lib.LL(res_ld),
-        int(relu), num_sms(), flags, _lib.stream_ptr())
+        int(relu), num_sms(), flags | _conv_flags(out, res), _lib.stream_ptr())
     _lib.check(st, "air_conv_gemm_bf16")
     return out
 
@@ -69,6 +94,9 @@ def pack3x3(w, C, N, mode, out):
 
 def conv3x3_patch(a, a_ld, B, H, W, C, wpk, N, out, out_ld, res=None, res_ld=0, relu=False, mode=0):
     """mode is only a label for the profiler (0 fprop, 1 dgrad): the arithmetic is identical."""
+    if _is_f32(out):
+        return _patch_taps_ex2(a, a_ld, B, H, W, C, wpk, 9, N, out, out_ld, H, W, res, res_ld, relu, None, None, 0, None,
+                               H, W, -1, -1, 1, 1, 0, 0, 9, _DR3, _DC3, _SL3)
     _lib.check(_lib.lib().air_conv3x3_patch_bf16(_lib.ptr(a), _lib.LL(a_ld), B, H, W, C, _lib.ptr(wpk), N, _lib.ptr(out),
                                                  _lib.LL(out_ld), _lib.ptr(res), _lib.LL(res_ld), int(relu), num_sms(),
                                                  _lib.stream_ptr()), "air_conv3x3_patch_bf16")
@@ -120,10 +148,27 @@ class PackPlan:
 
 
 _ONE_TAP = (ctypes.c_int * 1)(0)
+_DR3 = (ctypes.c_int * 9)(*[t // 3 for t in range(9)])
+_DC3 = (ctypes.c_int * 9)(*[t % 3 for t in range(9)])
+_SL3 = (ctypes.c_int * 9)(*range(9))
+
+
+def _patch_taps_ex2(a, a_ld, B, Hin, Win, C, wpk, wtaps, N, out, out_ld, OH, OW, res, res_ld, relu, bias, out2, out2_ld, stats,
+                    GH, GW, org_h, org_w, osh, osw, oph, opw, ntaps, dr, dc, sl):
+    """The general patch-kernel entry point; the storage type of out / res / out2 (bf16 or float) travels in `flags`."""
+    _lib.check(_lib.lib().air_conv_patch_taps_ex2_bf16(
+        _lib.ptr(a), _lib.LL(a_ld), B, Hin, Win, C, _lib.ptr(wpk), wtaps, N, _lib.ptr(out), _lib.LL(out_ld), OH, OW,
+        _lib.ptr(res), _lib.LL(res_ld), int(relu), _lib.ptr(bias), _lib.ptr(out2), _lib.LL(out2_ld), _lib.ptr(stats),
+        GH, GW, org_h, org_w, osh, osw, oph, opw, ntaps, dr, dc, sl, _conv_flags(out, res, out2), num_sms(),
+        _lib.stream_ptr()), "air_conv_patch_taps_ex2_bf16")
+    return out
 
 
 def conv1x1_patch(a, a_ld, B, H, W, C, wpk, N, out, out_ld, res=None, res_ld=0, relu=False, mode=0):
     """1x1 / stride-1 convolution (a plain GEMM over pixels) through the TMA patch kernel; mode labels the profile."""
+    if _is_f32(out):
+        return _patch_taps_ex2(a, a_ld, B, H, W, C, wpk, 1, N, out, out_ld, H, W, res, res_ld, relu, None, None, 0, None,
+                               H, W, 0, 0, 1, 1, 0, 0, 1, _ONE_TAP, _ONE_TAP, _ONE_TAP)
     _lib.check(_lib.lib().air_conv_patch_taps_bf16(
         _lib.ptr(a), _lib.LL(a_ld), B, H, W, C, _lib.ptr(wpk), 1, N, _lib.ptr(out), _lib.LL(out_ld), H, W,
         _lib.ptr(res), _lib.LL(res_ld), int(relu), H, W, 0, 0, 1, 1, 0, 0, 1, _ONE_TAP, _ONE_TAP, _ONE_TAP,
@@ -138,12 +183,8 @@ def conv1d_patch(a, a_ld, B, H, W, C, wpk, k, d, N, out, out_ld, bias=None, res=
     zero = (ctypes.c_int * k)(*([0] * k))
     dc = (ctypes.c_int * k)(*[t * d for t in range(k)])
     sl = (ctypes.c_int * k)(*range(k))
-    _lib.check(_lib.lib().air_conv_patch_taps_ex_bf16(
-        _lib.ptr(a), _lib.LL(a_ld), B, H, W, C, _lib.ptr(wpk), k, N, _lib.ptr(out), _lib.LL(out_ld), H, W,
-        _lib.ptr(res), _lib.LL(res_ld), int(relu), _lib.ptr(bias), _lib.ptr(out2), _lib.LL(out2_ld), None,
-        H, W, 0, -d * (k - 1) // 2, 1, 1, 0, 0, k, zero, dc, sl, num_sms(), _lib.stream_ptr()),
-        "air_conv_patch_taps_ex_bf16")
-    return out
+    return _patch_taps_ex2(a, a_ld, B, H, W, C, wpk, k, N, out, out_ld, H, W, res, res_ld, relu, bias, out2, out2_ld, None,
+                           H, W, 0, -d * (k - 1) // 2, 1, 1, 0, 0, k, zero, dc, sl)
 
 
 def conv1d_wgrad_patch(x, x_ld, B, H, W, C, dy, dy_ld, N, k, d, dw_out, dw_ld=None):
@@ -155,9 +196,10 @@ def conv1d_wgrad_patch(x, x_ld, B, H, W, C, dy, dy_ld, N, k, d, dw_out, dw_ld=No
 
 def conv_s2_dgrad_patch(dy, dy_ld, B, Ho, Wo, Cout, wpk, k, Cin, dx, dx_ld, H, W, res=None, res_ld=0):
     """Data gradient of a stride-2 k x k (k = 3 pad 1 / k = 1 pad 0) convolution by output parity classes."""
-    _lib.check(_lib.lib().air_conv_s2_dgrad_patch_bf16(
+    _lib.check(_lib.lib().air_conv_s2_dgrad_patch_ex_bf16(
         _lib.ptr(dy), _lib.LL(dy_ld), B, Ho, Wo, Cout, _lib.ptr(wpk), k, Cin, _lib.ptr(dx), _lib.LL(dx_ld), H, W,
-        _lib.ptr(res), _lib.LL(res_ld), num_sms(), _lib.stream_ptr()), "air_conv_s2_dgrad_patch_bf16", 4 if k == 3 else 1)
+        _lib.ptr(res), _lib.LL(res_ld), _conv_flags(dx, res), num_sms(), _lib.stream_ptr()),
+        "air_conv_s2_dgrad_patch_ex_bf16", 4 if k == 3 else 1)
     return dx
 
 
@@ -183,6 +225,9 @@ def conv_wgrad_patch(x, x_ld, B, H, W, C, dy, dy_ld, N, k, dw_out, dw_ld=None):
 
 def conv3x3_patch_stats(a, a_ld, B, H, W, C, wpk, N, out, out_ld, res, res_ld, relu, stats):
     """3x3 / s1 / p1 forward that also adds the per-channel sum / sum of squares of its output to `stats` (fp64 [2N])."""
+    if _is_f32(out):
+        return _patch_taps_ex2(a, a_ld, B, H, W, C, wpk, 9, N, out, out_ld, H, W, res, res_ld, relu, None, None, 0, stats,
+                               H, W, -1, -1, 1, 1, 0, 0, 9, _DR3, _DC3, _SL3)
     _lib.check(_lib.lib().air_conv3x3_patch_stats_bf16(
         _lib.ptr(a), _lib.LL(a_ld), B, H, W, C, _lib.ptr(wpk), N, _lib.ptr(out), _lib.LL(out_ld), _lib.ptr(res),
         _lib.LL(res_ld), int(relu), _lib.ptr(stats), num_sms(), _lib.stream_ptr()), "air_conv3x3_patch_stats_bf16")
@@ -197,12 +242,15 @@ def conv_out_size(n, k, s, p, d):
 # BatchNorm / stem / head / loss / optimiser wrappers
 # ------------------------------------------------------------------------------------------
 def bn_stats(x, x_ld, M, C, sums):
-    _lib.check(_lib.lib().air_bn_stats(_lib.ptr(x), _lib.LL(x_ld), _lib.LL(M), C, _lib.ptr(sums), num_sms(),
-                                       _lib.stream_ptr()), "air_bn_stats")
+    fn = _lib.lib().air_bn_stats_f32 if _is_f32(x) else _lib.lib().air_bn_stats
+    _lib.check(fn(_lib.ptr(x), _lib.LL(x_ld), _lib.LL(M), C, _lib.ptr(sums), num_sms(), _lib.stream_ptr()), "air_bn_stats")
 
 
 def bn_apply(x, x_ld, y, y_ld, M, C, sums, gamma, beta, relu, training, save_mean, save_invstd,
              running_mean, running_var, eps=1e-5, momentum=0.1):
+    if _is_f32(x):
+        return bn_apply_add.__wrapped__(x, x_ld, y, y_ld, M, C, sums, gamma, beta, relu, training, save_mean, save_invstd,
+                                        running_mean, running_var, None, 0, None, 0, eps, momentum)
     _lib.check(_lib.lib().air_bn_apply(
         _lib.ptr(x), _lib.LL(x_ld), _lib.ptr(y), _lib.LL(y_ld), _lib.LL(M), C, _lib.ptr(sums), _lib.ptr(gamma),
         _lib.ptr(beta), _lib.F(eps), int(relu), int(training), _lib.ptr(save_mean), _lib.ptr(save_invstd),
@@ -210,6 +258,9 @@ def bn_apply(x, x_ld, y, y_ld, M, C, sums, gamma, beta, relu, training, save_mea
 
 
 def bn_bwd(dy, dy_ld, x, x_ld, add, add_ld, dx, dx_ld, M, C, order, mean, invstd, gamma, beta, rsum, dgamma, dbeta):
+    if _is_f32(x):
+        return bn_bwd_bias.__wrapped__(dy, dy_ld, x, x_ld, add, add_ld, dx, dx_ld, M, C, order, mean, invstd, gamma, beta, rsum,
+                                       dgamma, dbeta, None)
     _lib.check(_lib.lib().air_bn_bwd(
         _lib.ptr(dy), _lib.LL(dy_ld), _lib.ptr(x), _lib.LL(x_ld), _lib.ptr(add), _lib.LL(add_ld), _lib.ptr(dx),
         _lib.LL(dx_ld), _lib.LL(M), C, order, _lib.ptr(mean), _lib.ptr(invstd), _lib.ptr(gamma), _lib.ptr(beta),
@@ -217,24 +268,27 @@ def bn_bwd(dy, dy_ld, x, x_ld, add, add_ld, dx, dx_ld, M, C, order, mean, invstd
 
 
 def stem_fwd(x, B, H, W, kh, kw, sh, sw, ph, pw, w, cout, y):
-    _lib.check(_lib.lib().air_stem_conv_fwd(_lib.ptr(x), B, H, W, kh, kw, sh, sw, ph, pw, _lib.ptr(w), cout,
-                                            _lib.ptr(y), _lib.stream_ptr()), "air_stem_conv_fwd")
+    fn = _lib.lib().air_stem_conv_fwd_f32 if _is_f32(x) else _lib.lib().air_stem_conv_fwd
+    _lib.check(fn(_lib.ptr(x), B, H, W, kh, kw, sh, sw, ph, pw, _lib.ptr(w), cout, _lib.ptr(y), _lib.stream_ptr()),
+               "air_stem_conv_fwd")
 
 
 def stem_wgrad(x, B, H, W, kh, kw, sh, sw, ph, pw, dy, cout, dw):
-    _lib.check(_lib.lib().air_stem_conv_wgrad(_lib.ptr(x), B, H, W, kh, kw, sh, sw, ph, pw, _lib.ptr(dy), cout,
-                                              _lib.ptr(dw), _lib.stream_ptr()), "air_stem_conv_wgrad")
+    fn = _lib.lib().air_stem_conv_wgrad_f32 if _is_f32(x) else _lib.lib().air_stem_conv_wgrad
+    _lib.check(fn(_lib.ptr(x), B, H, W, kh, kw, sh, sw, ph, pw, _lib.ptr(dy), cout, _lib.ptr(dw), _lib.stream_ptr()),
+               "air_stem_conv_wgrad")
 
 
 def selfattn_pool_fwd(x, att, stats, p, th, B, T, C, seed=-1):
-    _lib.check(_lib.lib().air_selfattn_pool_fwd(_lib.ptr(x), _lib.ptr(att), _lib.ptr(stats), _lib.ptr(p), _lib.ptr(th),
-                                                B, T, C, _lib.LL(seed), _lib.stream_ptr()), "air_selfattn_pool_fwd")
+    fn = _lib.lib().air_selfattn_pool_fwd_f32 if _is_f32(x) else _lib.lib().air_selfattn_pool_fwd
+    _lib.check(fn(_lib.ptr(x), _lib.ptr(att), _lib.ptr(stats), _lib.ptr(p), _lib.ptr(th), B, T, C, _lib.LL(seed),
+                  _lib.stream_ptr()), "air_selfattn_pool_fwd")
 
 
 def selfattn_pool_bwd(x, att, p, th, stats, dstats, dx, datt, B, T, C, seed=-1):
-    _lib.check(_lib.lib().air_selfattn_pool_bwd(_lib.ptr(x), _lib.ptr(att), _lib.ptr(p), _lib.ptr(th), _lib.ptr(stats),
-                                                _lib.ptr(dstats), _lib.ptr(dx), _lib.ptr(datt), B, T, C, _lib.LL(seed),
-                                                _lib.stream_ptr()), "air_selfattn_pool_bwd")
+    fn = _lib.lib().air_selfattn_pool_bwd_f32 if _is_f32(x) else _lib.lib().air_selfattn_pool_bwd
+    _lib.check(fn(_lib.ptr(x), _lib.ptr(att), _lib.ptr(p), _lib.ptr(th), _lib.ptr(stats), _lib.ptr(dstats), _lib.ptr(dx),
+                  _lib.ptr(datt), B, T, C, _lib.LL(seed), _lib.stream_ptr()), "air_selfattn_pool_bwd")
 
 
 def linear_fwd(x, W, bias, y, M, N, K):
@@ -283,7 +337,7 @@ def conv_gemm_ex(a, a_ld, B, H, W, C, Ho, Wo, kh, kw, sh, sw, ph, pw, dh, dw, mo
     st = _lib.lib().air_conv_gemm_bf16_ex(
         _lib.ptr(a), _lib.LL(a_ld), B, H, W, C, Ho, Wo, kh, kw, sh, sw, ph, pw, dh, dw, mode,
         _lib.ptr(wpk), N, K, _lib.ptr(out), _lib.LL(out_ld), _lib.ptr(bias), int(bias_rows), _lib.ptr(res), _lib.LL(res_ld),
-        int(relu), _lib.ptr(out2), _lib.LL(out2_ld), num_sms(), flags, _lib.stream_ptr())
+        int(relu), _lib.ptr(out2), _lib.LL(out2_ld), num_sms(), flags | _conv_flags(out, res, out2), _lib.stream_ptr())
     _lib.check(st, "air_conv_gemm_bf16_ex")
     return out
 
@@ -294,7 +348,7 @@ def conv_gemm_affine(a, a_ld, B, H, W, C, Ho, Wo, kh, kw, sh, sw, ph, pw, dh, dw
     st = _lib.lib().air_conv_gemm_bf16_affine(
         _lib.ptr(a), _lib.LL(a_ld), B, H, W, C, Ho, Wo, kh, kw, sh, sw, ph, pw, dh, dw, mode,
         _lib.ptr(wpk), N, K, _lib.ptr(out), _lib.LL(out_ld), _lib.ptr(bias), 0, None, _lib.LL(0), int(relu),
-        None, _lib.LL(0), _lib.ptr(post_scale), _lib.ptr(post_shift), num_sms(), 0, _lib.stream_ptr())
+        None, _lib.LL(0), _lib.ptr(post_scale), _lib.ptr(post_shift), num_sms(), _conv_flags(out), _lib.stream_ptr())
     _lib.check(st, "air_conv_gemm_bf16_affine")
     return out
 
@@ -309,7 +363,8 @@ def conv_wgrad_ld(x, x_ld, B, H, W, C, dy, dy_ld, Ho, Wo, N, kh, kw, sh, sw, ph,
 
 def bn_apply_add(x, x_ld, y, y_ld, M, C, sums, gamma, beta, relu, training, save_mean, save_invstd,
                  running_mean, running_var, add, add_ld, y2, y2_ld, eps=1e-5, momentum=0.1):
-    _lib.check(_lib.lib().air_bn_apply_add(
+    fn = _lib.lib().air_bn_apply_add_f32 if _is_f32(x) else _lib.lib().air_bn_apply_add
+    _lib.check(fn(
         _lib.ptr(x), _lib.LL(x_ld), _lib.ptr(y), _lib.LL(y_ld), _lib.LL(M), C, _lib.ptr(sums), _lib.ptr(gamma),
         _lib.ptr(beta), _lib.F(eps), int(relu), int(training), _lib.ptr(save_mean), _lib.ptr(save_invstd),
         _lib.ptr(running_mean), _lib.ptr(running_var), _lib.F(momentum), _lib.ptr(add), _lib.LL(add_ld), _lib.ptr(y2),
@@ -318,7 +373,8 @@ def bn_apply_add(x, x_ld, y, y_ld, M, C, sums, gamma, beta, relu, training, save
 
 def bn_bwd_bias(dy, dy_ld, x, x_ld, add, add_ld, dx, dx_ld, M, C, order, mean, invstd, gamma, beta, rsum, dgamma, dbeta,
                 dbias):
-    _lib.check(_lib.lib().air_bn_bwd_bias(
+    fn = _lib.lib().air_bn_bwd_bias_f32 if _is_f32(x) else _lib.lib().air_bn_bwd_bias
+    _lib.check(fn(
         _lib.ptr(dy), _lib.LL(dy_ld), _lib.ptr(x), _lib.LL(x_ld), _lib.ptr(add), _lib.LL(add_ld), _lib.ptr(dx),
         _lib.LL(dx_ld), _lib.LL(M), C, order, _lib.ptr(mean), _lib.ptr(invstd), _lib.ptr(gamma), _lib.ptr(beta),
         _lib.ptr(rsum), _lib.ptr(dgamma), _lib.ptr(dbeta), _lib.ptr(dbias), num_sms(), _lib.stream_ptr()), "air_bn_bwd_bias", 2)
@@ -335,41 +391,41 @@ def linear_bwd_ld(x, W, ldw, dy, dx, dW, db, M, N, K):
 
 
 def time_stats(x, x_ld, B, T, C, mean_out, std_out=None, clampv=0.0):
-    _lib.check(_lib.lib().air_time_stats_fwd(_lib.ptr(x), _lib.LL(x_ld), B, T, C, _lib.ptr(mean_out), _lib.ptr(std_out),
+    _lib.check((_lib.lib().air_time_stats_fwd_f32 if _is_f32(x) else _lib.lib().air_time_stats_fwd)(_lib.ptr(x), _lib.LL(x_ld), B, T, C, _lib.ptr(mean_out), _lib.ptr(std_out),
                                              _lib.F(clampv), _lib.stream_ptr()), "air_time_stats_fwd")
 
 
 def asp_fwd(e, e_ld, x, x_ld, B, T, C, out, smax, ssum, sq):
-    _lib.check(_lib.lib().air_ecapa_asp_fwd(_lib.ptr(e), _lib.LL(e_ld), _lib.ptr(x), _lib.LL(x_ld), B, T, C, _lib.ptr(out),
+    _lib.check((_lib.lib().air_ecapa_asp_fwd_f32 if _is_f32(x) else _lib.lib().air_ecapa_asp_fwd)(_lib.ptr(e), _lib.LL(e_ld), _lib.ptr(x), _lib.LL(x_ld), B, T, C, _lib.ptr(out),
                                             _lib.ptr(smax), _lib.ptr(ssum), _lib.ptr(sq), _lib.stream_ptr()), "air_ecapa_asp_fwd")
 
 
 def asp_bwd(e, e_ld, x, x_ld, B, T, C, out, dout, smax, ssum, sq, cmean, cstd, dcmean, dcstd, clampv, de, de_ld, dx, dx_ld):
-    _lib.check(_lib.lib().air_ecapa_asp_bwd(
+    _lib.check((_lib.lib().air_ecapa_asp_bwd_f32 if _is_f32(x) else _lib.lib().air_ecapa_asp_bwd)(
         _lib.ptr(e), _lib.LL(e_ld), _lib.ptr(x), _lib.LL(x_ld), B, T, C, _lib.ptr(out), _lib.ptr(dout), _lib.ptr(smax),
         _lib.ptr(ssum), _lib.ptr(sq), _lib.ptr(cmean), _lib.ptr(cstd), _lib.ptr(dcmean), _lib.ptr(dcstd), _lib.F(clampv),
         _lib.ptr(de), _lib.LL(de_ld), _lib.ptr(dx), _lib.LL(dx_ld), _lib.stream_ptr()), "air_ecapa_asp_bwd")
 
 
 def ctx_bwd_mask(x, x_ld, B, T, C, cmean, cstd, dcmean, dcstd, clampv, dx, dx_ld):
-    _lib.check(_lib.lib().air_ctx_stats_bwd_mask(_lib.ptr(x), _lib.LL(x_ld), B, T, C, _lib.ptr(cmean), _lib.ptr(cstd),
+    _lib.check((_lib.lib().air_ctx_stats_bwd_mask_f32 if _is_f32(x) else _lib.lib().air_ctx_stats_bwd_mask)(_lib.ptr(x), _lib.LL(x_ld), B, T, C, _lib.ptr(cmean), _lib.ptr(cstd),
                                                  _lib.ptr(dcmean), _lib.ptr(dcstd), _lib.F(clampv), _lib.ptr(dx), _lib.LL(dx_ld),
                                                  _lib.stream_ptr()), "air_ctx_stats_bwd_mask")
 
 
 def scale_residual(x, x_ld, gate, res, res_ld, out, out_ld, B, T, C):
-    _lib.check(_lib.lib().air_scale_residual_fwd(_lib.ptr(x), _lib.LL(x_ld), _lib.ptr(gate), _lib.ptr(res), _lib.LL(res_ld),
+    _lib.check((_lib.lib().air_scale_residual_fwd_f32 if _is_f32(x) else _lib.lib().air_scale_residual_fwd)(_lib.ptr(x), _lib.LL(x_ld), _lib.ptr(gate), _lib.ptr(res), _lib.LL(res_ld),
                                                  _lib.ptr(out), _lib.LL(out_ld), B, T, C, _lib.stream_ptr()),
                "air_scale_residual_fwd")
 
 
 def se_dgate(dout, d_ld, x, x_ld, B, T, C, dgate):
-    _lib.check(_lib.lib().air_se_dgate(_lib.ptr(dout), _lib.LL(d_ld), _lib.ptr(x), _lib.LL(x_ld), B, T, C, _lib.ptr(dgate),
+    _lib.check((_lib.lib().air_se_dgate_f32 if _is_f32(x) else _lib.lib().air_se_dgate)(_lib.ptr(dout), _lib.LL(d_ld), _lib.ptr(x), _lib.LL(x_ld), B, T, C, _lib.ptr(dgate),
                                        _lib.stream_ptr()), "air_se_dgate")
 
 
 def se_apply_bwd(dout, d_ld, gate, dmean, dx, dx_ld, B, T, C):
-    _lib.check(_lib.lib().air_se_apply_bwd(_lib.ptr(dout), _lib.LL(d_ld), _lib.ptr(gate), _lib.ptr(dmean), _lib.ptr(dx),
+    _lib.check((_lib.lib().air_se_apply_bwd_f32 if _is_f32(dout) else _lib.lib().air_se_apply_bwd)(_lib.ptr(dout), _lib.LL(d_ld), _lib.ptr(gate), _lib.ptr(dmean), _lib.ptr(dx),
                                            _lib.LL(dx_ld), B, T, C, _lib.stream_ptr()), "air_se_apply_bwd")
 
 
@@ -396,12 +452,12 @@ def sigmoid_bwd(dy, y, dx, n):
 
 
 def copy_channels(src, s_ld, dst, d_ld, M, C, mask=None, m_ld=0):
-    _lib.check(_lib.lib().air_copy_channels(_lib.ptr(src), _lib.LL(s_ld), _lib.ptr(mask), _lib.LL(m_ld), _lib.ptr(dst),
+    _lib.check((_lib.lib().air_copy_channels_f32 if _is_f32(src) else _lib.lib().air_copy_channels)(_lib.ptr(src), _lib.LL(s_ld), _lib.ptr(mask), _lib.LL(m_ld), _lib.ptr(dst),
                                             _lib.LL(d_ld), _lib.LL(M), C, _lib.stream_ptr()), "air_copy_channels")
 
 
 def colsum(x, ld, M, C, out):
-    _lib.check(_lib.lib().air_colsum_bf16(_lib.ptr(x), _lib.LL(ld), _lib.LL(M), C, _lib.ptr(out), _lib.stream_ptr()),
+    _lib.check((_lib.lib().air_colsum_f32 if _is_f32(x) else _lib.lib().air_colsum_bf16)(_lib.ptr(x), _lib.LL(ld), _lib.LL(M), C, _lib.ptr(out), _lib.stream_ptr()),
                "air_colsum_bf16")
 
 
@@ -492,9 +548,11 @@ def _timed(fn, family, work=None):
         return r
     wrapper.__name__ = fn.__name__
     wrapper.__doc__ = fn.__doc__
+    wrapper.__wrapped__ = fn
     return wrapper
 
 
+split_terms = _timed(split_terms, "split")
 conv_gemm = _timed(conv_gemm, lambda a: "conv_dgrad" if a[16] == 1 else "conv_fprop", _conv_work)
 conv_wgrad = _timed(conv_wgrad, "conv_wgrad", _wgrad_work)
 bn_stats = _timed(bn_stats, "bn_stats")

@@ -31,6 +31,8 @@ typedef struct CUstream_st* air_stream_t; /* == cudaStream_t */
 #define AIR_ERR_FORMAT (-4)
 #define AIR_ERR_CHECKSUM (-5)
 #define AIR_ERR_NOMEM (-6)
+/* the CUDA driver entry point needed to encode a TMA tensor map could not be resolved (no driver loaded) */
+#define AIR_ERR_DRIVER (-7)
 
 /* Library version (major*10000 + minor*100 + patch). */
 int air_version(void);
@@ -418,6 +420,70 @@ int air_dropout_relu_bwd(const float* dy, const float* x, const unsigned char* k
                          float p, air_stream_t stream);
 int air_relu_ce_fwd_bwd(const float* z, const long long* labels, int B, int C, float grad_scale,
                         double* loss_sum, int* correct, float* dz, air_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * fp32 parity mode.  BASELINE.json asks for logits / scores within 1e-3 of the reference's fp32
+ * CPU path; a network with bf16 storage between its layers cannot get there (the fp32 and bf16-storage ORACLES differ by
+ * 1e-2).  In this mode activations and gradients are stored as float, and every convolution still runs on the same
+ * tcgen05 kernels: its fp32 operands are written as bf16 split terms concatenated along the contraction axis
+ * (air_split_terms: x = hi + lo, x*w ~= hi*hi + lo*hi + hi*lo with one fp32 accumulator in TMEM), and the epilogue
+ * stores the accumulator unrounded (AIR_CONV_F32_OUT).  The *_f32 entry points are the float-storage instances of the
+ * HBM-bound kernels above: same arguments, activation pointers are float*.
+ * --------------------------------------------------------------------------------------------- */
+#define AIR_CONV_F32_OUT 1 /* `flags` bit of the conv entry points: out / res / out2 are float tensors */
+int air_split_terms(const float* x, long long x_ld, long long M, int C, void* out, long long out_ld, int out_f32,
+                    int nterms, unsigned lo_mask, air_stream_t stream);
+int air_conv_patch_taps_ex2_bf16(const void* a, long long a_ld, int B, int Hin, int Win, int C,
+                                 const void* wpk, int wtaps, int N, void* out, long long out_ld, int OH, int OW,
+                                 const void* res, long long res_ld, int relu, const float* bias,
+                                 void* out2, long long out2_ld, double* stats,
+                                 int GH, int GW, int org_h, int org_w, int osh, int osw, int oph, int opw,
+                                 int ntaps, const int* tap_dr, const int* tap_dc, const int* tap_slice,
+                                 int flags, int num_sms, air_stream_t stream);
+int air_conv_s2_dgrad_patch_ex_bf16(const void* dy, long long dy_ld, int B, int Ho, int Wo, int Cout,
+                                    const void* wpk, int k, int Cin, void* dx, long long dx_ld, int H, int W,
+                                    const void* res, long long res_ld, int flags, int num_sms, air_stream_t stream);
+int air_bn_stats_f32(const void* x, long long x_ld, long long M, int C, double* sums, int num_sms, air_stream_t stream);
+int air_bn_apply_add_f32(const void* x, long long x_ld, void* y, long long y_ld, long long M, int C,
+                         const double* sums, const float* gamma, const float* beta, float eps, int relu,
+                         int training, float* save_mean, float* save_invstd, float* running_mean,
+                         float* running_var, float momentum, const void* add, long long add_ld, void* y2,
+                         long long y2_ld, int num_sms, air_stream_t stream);
+int air_bn_bwd_bias_f32(const void* dy, long long dy_ld, const void* x, long long x_ld, const void* add, long long add_ld,
+                        void* dx, long long dx_ld, long long M, int C, int order,
+                        const float* mean, const float* invstd, const float* gamma, const float* beta,
+                        double* rsum, float* dgamma, float* dbeta, float* dbias, int num_sms, air_stream_t stream);
+int air_stem_conv_fwd_f32(const void* x, int B, int H, int W, int kh, int kw, int sh, int sw, int ph, int pw,
+                          const float* w, int Cout, void* y, air_stream_t stream);
+int air_stem_conv_wgrad_f32(const void* x, int B, int H, int W, int kh, int kw, int sh, int sw, int ph, int pw,
+                            const void* dy, int Cout, float* dw, air_stream_t stream);
+int air_selfattn_pool_fwd_f32(const void* x, const float* att, float* stats, float* p_out, float* th_out,
+                              int B, int T, int C, long long noise_seed, air_stream_t stream);
+int air_selfattn_pool_bwd_f32(const void* x, const float* att, const float* p_in, const float* th_in,
+                              const float* stats, const float* dstats, void* dx, float* datt,
+                              int B, int T, int C, long long noise_seed, air_stream_t stream);
+
+/* float-storage instances of the ECAPA non-GEMM stages (same arguments as the bf16 entry points above) */
+int air_time_stats_fwd_f32(const void* x, long long x_ld, int B, int T, int C, float* mean_out, float* std_out, float
+    clampv, air_stream_t stream);
+int air_ecapa_asp_fwd_f32(const void* e, long long e_ld, const void* x, long long x_ld, int B, int T, int C, float*
+    out, float* save_max, float* save_sum, float* save_q, air_stream_t stream);
+int air_ecapa_asp_bwd_f32(const void* e, long long e_ld, const void* x, long long x_ld, int B, int T, int C, const
+    float* out, const float* dout, const float* save_max, const float* save_sum, const float* save_q, const float*
+    ctx_mean, const float* ctx_std, const float* dctx_mean, const float* dctx_std, float clampv, void* de, long long
+    de_ld, void* dx, long long dx_ld, air_stream_t stream);
+int air_ctx_stats_bwd_mask_f32(const void* x, long long x_ld, int B, int T, int C, const float* ctx_mean, const float*
+    ctx_std, const float* dctx_mean, const float* dctx_std, float clampv, void* dx, long long dx_ld, air_stream_t
+    stream);
+int air_scale_residual_fwd_f32(const void* x, long long x_ld, const float* gate, const void* res, long long res_ld,
+    void* out, long long out_ld, int B, int T, int C, air_stream_t stream);
+int air_se_dgate_f32(const void* dout, long long d_ld, const void* x, long long x_ld, int B, int T, int C, float*
+    dgate, air_stream_t stream);
+int air_se_apply_bwd_f32(const void* dout, long long d_ld, const float* gate, const float* dmean, void* dx, long long
+    dx_ld, int B, int T, int C, air_stream_t stream);
+int air_copy_channels_f32(const void* src, long long s_ld, const void* mask, long long m_ld, void* dst, long long
+    d_ld, long long M, int C, air_stream_t stream);
+int air_colsum_f32(const void* x, long long ld, long long M, int C, float* out, air_stream_t stream);
 
 #ifdef __cplusplus
 }
