@@ -91,10 +91,38 @@ def test_every_ctypes_call_site_matches_the_header():
         if not fn.endswith(".py"):
             continue
         tree = ast.parse(open(os.path.join(pkg, fn)).read())
-        for node in ast.walk(tree):
-            if not (isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and node.func.attr.startswith("air_")):
+
+        def entry_points(expr):
+            """air_* names an expression can evaluate to: `lib.air_x`, or `lib.air_x_f32 if cond else lib.air_x` (the
+            bf16 / float-storage twins share one argument list)."""
+            if isinstance(expr, ast.Attribute) and expr.attr.startswith("air_"):
+                return [expr.attr]
+            if isinstance(expr, ast.IfExp):
+                a, b = entry_points(expr.body), entry_points(expr.orelse)
+                return a + b if a and b else []
+            return []
+
+        calls = []                                   # (call node, [entry point names])
+        for scope in ast.walk(tree):
+            if not isinstance(scope, (ast.FunctionDef, ast.Module)):
                 continue
-            name = node.func.attr
+            env = {}
+            for node in (ast.walk(scope) if isinstance(scope, ast.FunctionDef) else ()):   # `fn = <entry point expr>` ... `fn(...)`
+                if isinstance(node, ast.Assign) and len(node.targets) == 1 and isinstance(node.targets[0], ast.Name):
+                    names = entry_points(node.value)
+                    if names:
+                        env[node.targets[0].id] = names
+            for node in ast.walk(scope):
+                if not isinstance(node, ast.Call):
+                    continue
+                names = env.get(node.func.id, []) if isinstance(node.func, ast.Name) else entry_points(node.func)
+                if names:
+                    calls.append((node, names))
+        seen = set()
+        for node, name in ((n, nm) for n, nms in calls for nm in nms):
+            if (id(node), name) in seen:
+                continue
+            seen.add((id(node), name))
             if name not in sigs:
                 problems.append("%s:%d calls undeclared %s" % (fn, node.lineno, name))
                 continue
