@@ -40,6 +40,13 @@ def workload_config(workload, B, world, overlap=None):
     the SAME workload: the driver compares the two configs)."""
     arch = "resnet" if workload.startswith("resnet") else "ecapa"
     scoring = workload.endswith("_score")
+    if workload == "resnet_adv":
+        return {"workload": "resnet_adv: wave->LFCC->ResNet-18-OC fwd/bwd + OC-Softmax + gradient-reversed channel classifier "
+                            "(--ADV_AUG --LA_aug, 60 classes) + Adam(L2)/SGD, then a SECOND encoder forward and the classifier's "
+                            "own Adam step (main_train.py:377-453), B=%d/GPU, 4 s @ 16 kHz, feat_len 750" % B,
+                "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
+                "l2": "per-step activations (> 4 GB) exceed the 126 MB L2; waves rotate over %d buffers" % NBUF,
+                "streams": "weight-gradient kernels on a side stream"}
     if overlap is None:
         overlap = os.environ.get("AIR_OVERLAP_WGRAD", "1") != "0"
     return {"workload": "%s: wave->LFCC->%s %s + OC-Softmax%s, B=%d/GPU, 4 s @ 16 kHz, feat_len 750 (repeat pad)"
@@ -65,12 +72,19 @@ def run(args, rank, world, helpers):
     nbuf = NBUF
     waves = [_waves(B, rank * 16 + i).cuda() for i in range(nbuf)]
     labels = _labels(B, rank).cuda()
+    adv = args.workload == "resnet_adv"
+    channels = None
+    if adv:                                   # --ADV_AUG --LA_aug: one 60-class codec head (main_train.py:211-224)
+        tr.attach_adversaries([60], lambda_=0.05, lr_d=1e-4, seed=688)
+        channels = torch.randint(0, 60, (B,), generator=torch.Generator().manual_seed(rank + 3)).cuda()
+
+    def run_step(w, i):
+        if scoring:
+            return tr.score_step(w)
+        return tr.train_step(w, labels, channels=channels, step_seed=i)
 
     def step(i):
-        if scoring:
-            tr.score_step(waves[i % nbuf])
-        else:
-            tr.train_step(waves[i % nbuf], labels)
+        run_step(waves[i % nbuf], i)
 
     step(0)                                   # allocate activations / pack weights outside the timing
     torch.cuda.synchronize()
@@ -106,7 +120,7 @@ def run(args, rank, world, helpers):
             issue_copy(state["next"])
             state["next"] += 1
         main.wait_event(ready[i % 2])
-        out = tr.score_step(dev[i % 2]) if scoring else tr.train_step(dev[i % 2], labels)
+        out = run_step(dev[i % 2], i)
         consumed[i % 2].record(main)
         res_host.copy_(out.reshape(-1), non_blocking=True)
         main.synchronize()                     # the user reads the loss / scores every step
@@ -141,7 +155,7 @@ def run(args, rank, world, helpers):
         lfcc_roof = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
                      "kernel": "air_lfcc_tc::lfcc_tc_kernel (fused wave -> padded bf16 model-layout LFCC, inside the step)",
                      "bytes_per_launch": lf["bytes"] / nprof, "ms_per_step": lf["ms"] / nprof}
-    flops_per_utt = (FWD_FLOPS_PER_UTT if scoring else TRAIN_FLOPS_PER_UTT)[arch]
+    flops_per_utt = (FWD_FLOPS_PER_UTT if scoring else TRAIN_FLOPS_PER_UTT)[arch] + (FWD_FLOPS_PER_UTT[arch] if adv else 0.0)
     line = {
         "metric": "utterances/sec (4 s@16 kHz) %s" % ("scoring" if scoring else "train-step"),
         "value": value, "unit": "utterances/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

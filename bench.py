@@ -9,6 +9,9 @@ Workloads
   ecapa_train   same with ECAPA-TDNN-512
   ecapa_score   generate_score.py inference, B=1024
   lfcc          the fused LFCC kernel alone, B=256 (HBM roofline of the LFCC kernel)
+  resnet_adv    resnet_train with the --ADV_AUG channel classifier (second encoder forward per step)
+The default invocation (no --workload) also attaches short runs of lfcc / ecapa_train / ecapa_score / resnet_adv as
+`also` (value, ms, roofline fraction, clocks each).
 
 One JSON line is printed by rank 0 (contract in the task statement): value = whole-job
 utterances/s with inputs resident in HBM; e2e = same metric through the public Python API with
@@ -401,6 +404,40 @@ def run_reference(args, rank, world):
     return bench_train.run_reference(args, rank, world)
 
 
+ALSO = ("lfcc", "ecapa_train", "ecapa_score", "resnet_adv")
+
+
+def also_results(args, rank, world):
+    """Short runs of the other workloads of the path, attached to the default line as `also` so that they land in the
+    driver's BENCH record (value, ms, roofline fraction, clocks of each; no CPU arm)."""
+    import copy
+    import gc
+    out = {}
+    for w in ALSO:
+        a = copy.copy(args)
+        a.workload, a.steps, a.warmup, a.no_cpu_baseline, a.batch = w, min(args.steps, 10), 3, True, 0
+        try:
+            if w == "lfcc":
+                ln = run_lfcc(a, rank, world)
+            else:
+                from asvspoof2021_air_b200 import bench_train
+                ln = bench_train.run(a, rank, world, helpers=sys.modules[__name__])
+            r = ln["roofline"]
+            out[w] = {"value": ln["value"], "unit": ln["unit"], "ms_per_step": ln["ms_per_step"], "steps": a.steps,
+                      "e2e": ln["e2e"]["value"], "gpu_launches": ln["gpu_launches"],
+                      "roofline": {k: r.get(k) for k in ("bound", "achieved", "peak", "unit", "frac", "kernel",
+                                                         "whole_step_tflops", "conv_ms_per_step", "fp32_exact_kernel")
+                                   if r.get(k) is not None},
+                      "clocks": ln["clocks"], "workload": ln["config"]["workload"]}
+            if ln.get("kernels"):
+                out[w]["kernels_ms"] = {k: v["ms_per_step"] for k, v in ln["kernels"].items()}
+        except Exception as e:                       # a failing side workload must not take the headline line with it
+            out[w] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+        gc.collect()
+        torch.cuda.empty_cache()
+    return out
+
+
 def default_workload():
     try:
         from asvspoof2021_air_b200 import bench_train  # noqa: F401
@@ -414,7 +451,10 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default=None, choices=[None, "lfcc", "resnet_train", "ecapa_train", "ecapa_score", "det"])
+    ap.add_argument("--workload", default=None,
+                    choices=[None, "lfcc", "resnet_train", "ecapa_train", "ecapa_score", "resnet_adv", "det"])
+    ap.add_argument("--no-also", dest="no_also", action="store_true",
+                    help="default invocation only: skip the short runs of the other workloads (`also` in the JSON line)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--fseg", type=int, default=0)
@@ -422,6 +462,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    default_invocation = args.workload is None
     if args.workload is None:
         args.workload = default_workload()
 
@@ -443,6 +484,11 @@ def main():
     else:
         from asvspoof2021_air_b200 import bench_train
         line = bench_train.run(args, rank, world, helpers=sys.modules[__name__])
+    if default_invocation and world == 1 and not args.no_also:
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        line["also"] = also_results(args, rank, world)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

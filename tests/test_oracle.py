@@ -292,3 +292,31 @@ def test_reference_copy_for_the_cpu_arm_is_byte_identical():
             assert hashlib.sha256(open(os.path.join(base, name), "rb").read()).hexdigest() == digest, (base, name)
     ignored = subprocess.run(["git", "check-ignore", "oracle/_ref/resnet.py"], cwd=root, capture_output=True, text=True)
     assert ignored.returncode == 0, "oracle/_ref must stay out of the history"
+
+
+def test_gradient_noise_floor_of_the_reference_fp32_arithmetic():
+    """Why end-to-end gradient comparisons cannot be held to the forward tolerance: the oracle (= the reference's torch
+    ops) in fp32 against the SAME code in fp64.  The forward agrees to ~1e-6, the parameter gradients only to ~1e-3: an
+    activation within the forward deviation of zero flips its ReLU mask, so gradients agree to ~sqrt(forward deviation).
+    tests/test_parity_fp32_gpu.py quotes these numbers for the bar of its golden gradient-norm check."""
+    B = 2
+    spec = ss.resnet_spec()
+    x = torch.from_numpy(lo.apply_frame_map(lo.lfcc(ss.seeded_waves(B, 64000, seed=3).numpy()),
+                                            lo.frame_index_map(401, 750, "repeat"))).float().unsqueeze(1).transpose(2, 3)
+    labels = ss.seeded_labels(B, 3)
+    out = {}
+    for dt in (torch.float32, torch.float64):
+        sd = {k: (v.to(dt) if v.is_floating_point() else v) for k, v in ss.seeded_state(spec, 11).items()}
+        keys = ss.trainable_keys(spec)
+        for k in keys:
+            sd[k].requires_grad_(True)
+        feat, _ = no.resnet_forward(sd, x.to(dt), True)
+        loss, _ = no.ocsoftmax(ss.seeded_center(256, 11).to(dt), feat, labels, 0.9, 0.2, 20.0)
+        loss.backward()
+        out[dt] = (feat.detach().double(), {k: sd[k].grad.double() for k in keys if sd[k].grad is not None})
+    rel = lambda a, b: float((a - b).norm() / b.norm())                   # noqa: E731
+    fwd = rel(out[torch.float32][0], out[torch.float64][0])
+    grads = sorted(rel(out[torch.float32][1][k], g) for k, g in out[torch.float64][1].items())
+    median = grads[len(grads) // 2]
+    print("fp32 vs fp64 reference arithmetic: feat %.1e, gradients median %.1e max %.1e" % (fwd, median, grads[-1]))
+    assert fwd < 1e-5 and 10 * fwd < median < 1e-2
