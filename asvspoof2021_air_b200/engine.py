@@ -438,6 +438,13 @@ class AsyncWgrad:
             fn(*args)
         self._side_pending = True
 
+    def _side_events(self):
+        if not self._side_pending:
+            return ()
+        ev = torch.cuda.Event()
+        ev.record(self._side)
+        return (ev,)
+
     def _join_side(self):
         if self._side_pending:
             ev = torch.cuda.Event()
@@ -688,11 +695,17 @@ class ResNetEngine(AsyncWgrad):
     def zero_grad(self):
         self.store.grads.zero_()
 
-    grad_hook = None        # optional callable(offset): every gradient at flat index >= offset is final
+    grad_hook = None        # optional callable(offset, events): every gradient at flat index >= offset is final
+
+    def ready_names(self):
+        """Parameters at which backward() reports progress to the gradient reducer (bucket boundaries)."""
+        return ["conv5.weight"] + [blk.name + ".bn1.weight" for blk in self.blocks]
+
     def _ready(self, name):
+        """Every gradient at or above `name` in the flat buffer has been LAUNCHED: hand the reducer the offset and an
+        event of the weight-gradient side stream -- the exchange stream waits for it, the compute stream does not."""
         if self.grad_hook is not None:
-            self._join_side()
-            self.grad_hook(self.store.offsets[name][0])
+            self.grad_hook(self.store.offsets[name][0], self._side_events())
 
     def backward(self, dfeat, dmu=None):
         """Accumulates parameter gradients into store.grads (call zero_grad() first).

@@ -355,10 +355,15 @@ class EcapaEngine(AsyncWgrad):
 
     grad_hook = None        # optional callable(offset): every gradient at flat index >= offset is final
 
+    def ready_names(self):
+        """Parameters at which backward() reports progress to the gradient reducer (bucket boundaries)."""
+        return ["layer4.weight"] + [blk.name + ".conv1.weight" for blk in self.blocks]
+
     def _ready(self, name):
+        """Every gradient at or above `name` in the flat buffer has been LAUNCHED: hand the reducer the offset and an
+        event of the weight-gradient side stream -- the exchange stream waits for it, the compute stream does not."""
         if self.grad_hook is not None:
-            self._join_side()
-            self.grad_hook(self.store.offsets[name][0])
+            self.grad_hook(self.store.offsets[name][0], self._side_events())
 
     def backward(self, dfeat, dlogits=None):
         """Accumulates parameter gradients into store.grads (call zero_grad() first)."""

@@ -28,6 +28,9 @@ def init_from_env(backend=None):
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
+            # the ring / NVLS kernels of the gradient exchange run BESIDE persistent 148-CTA conv grids: a handful of
+            # CTAs moves 50 MB per step well inside the backward pass, more only evicts compute (override via the env)
+            os.environ.setdefault("NCCL_MAX_CTAS", "8")
             torch.cuda.set_device(local)
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         else:
@@ -44,12 +47,18 @@ def shard_range(n, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def bucket_bounds(n, bucket_elems):
+def bucket_bounds(n, bucket_elems, cuts=()):
     """Bucket boundaries of a flat buffer of n elements, walked from the END (backward order):
-    [(lo, hi), ...] with hi descending."""
+    [(lo, hi), ...] with hi descending.  `cuts`: offsets that must be bucket boundaries (the offsets at which the
+    backward pass reports "everything above is final": a bucket straddling one would wait for the next report)."""
     out, hi = [], n
+    cuts = sorted({int(c) for c in cuts if 0 < c < n}, reverse=True)
     while hi > 0:
         lo = max(0, hi - bucket_elems)
+        for c in cuts:
+            if lo < c < hi:
+                lo = c
+                break
         out.append((lo, hi))
         hi = lo
     return out
@@ -58,10 +67,10 @@ def bucket_bounds(n, bucket_elems):
 class GradReducer:
     """Bucketed sum all-reduce of a flat gradient buffer, overlapped with the backward pass."""
 
-    def __init__(self, flat, n, group=None, bucket_elems=4 << 20, overlap=True):
+    def __init__(self, flat, n, group=None, bucket_elems=4 << 20, overlap=True, cuts=()):
         self.flat, self.n, self.group = flat, n, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.buckets = bucket_bounds(n, bucket_elems)
+        self.buckets = bucket_bounds(n, bucket_elems, cuts)
         self.overlap = overlap and flat.is_cuda
         self.stream = torch.cuda.Stream() if self.overlap else None
         self.next = 0
@@ -70,15 +79,17 @@ class GradReducer:
     def begin(self):
         self.next = 0
 
-    def ready(self, offset):
-        """Every gradient at flat index >= offset is final: launch the buckets that lie above it."""
+    def ready(self, offset, wait_events=()):
+        """Every gradient at flat index >= offset is final once the current stream AND `wait_events` (e.g. the
+        weight-gradient side stream of the engine) have reached this point: launch the buckets that lie above it.  The
+        exchange stream waits for those events; the compute stream does not wait for anything."""
         if self.world == 1:
             return
         while self.next < len(self.buckets) and self.buckets[self.next][0] >= offset:
-            self._launch(self.buckets[self.next])
+            self._launch(self.buckets[self.next], wait_events)
             self.next += 1
 
-    def _launch(self, rng):
+    def _launch(self, rng, wait_events=()):
         lo, hi = rng
         view = self.flat[lo:hi]
         if self.overlap:
@@ -86,8 +97,12 @@ class GradReducer:
             ev.record(torch.cuda.current_stream())
             with torch.cuda.stream(self.stream):
                 self.stream.wait_event(ev)
+                for e in wait_events:
+                    self.stream.wait_event(e)
                 dist.all_reduce(view, group=self.group)
         else:
+            for e in wait_events:
+                e.synchronize()
             dist.all_reduce(view, group=self.group)
 
     def finish(self, *extra):

@@ -169,6 +169,9 @@ def test_flac_folder_and_prefetcher_on_cpu(tmp_path):
 def test_parallel_helpers_single_process():
     from asvspoof2021_air_b200 import parallel
     assert [parallel.shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    # cuts: the offsets at which the backward pass reports progress are bucket boundaries (no bucket straddles one)
+    bc = parallel.bucket_bounds(20, 8, cuts=[3, 15])
+    assert bc == [(15, 20), (7, 15), (3, 7), (0, 3)] and all(hi - lo <= 8 for lo, hi in bc)
     b = parallel.bucket_bounds(10, 4)
     assert b == [(6, 10), (2, 6), (0, 2)]
     r = parallel.GradReducer(torch.zeros(10), 10, bucket_elems=4)
