@@ -180,12 +180,18 @@ extern "C" int air_conv3x3_wgrad_patch_supported(int C, int N) { return wpatch_o
 // General launcher: explicit tap list.  Tap t reads the x window that starts at patch pixel (tap_dr[t], tap_dc[t]) and
 // accumulates into dw_out[co][t][ci] (GEMM layout [Cout][ntaps][Cin], fp32, caller zeroes).  Wide mode (C % 64 == 0) pairs
 // consecutive taps in one M = 128 instruction; narrow mode (C == 16) needs runs of taps that are consecutive in dc.
+// x view: by default the (B, H, W) grid of dy with pixel stride x_ld; `xv` describes a strided sub-image instead (stride-2
+// layers: one parity class of the input).  tap_id (optional): index of tap t in the layer's [Cout][taps][Cin] gradient.
+struct XView { const void* base; long long sw, sh, sb; int H, W; };
+
 static int launch_wgrad_patch(const void* x, long long x_ld, int B, int H, int W, int C, const void* dy, long long dy_ld, int N,
                               int ntaps, const int* tap_dr, const int* tap_dc, int org_h, int org_w,
-                              float* dw_out, long long dw_ld, int num_sms, cudaStream_t stream) {
+                              float* dw_out, long long dw_ld, int num_sms, cudaStream_t stream,
+                              const XView* xv = nullptr, const int* tap_id = nullptr, int dw_taps = 0) {
   if (!x || !dy || !dw_out || B <= 0 || H < 1 || W < 1 || ntaps < 1 || ntaps > 9) return AIR_ERR_ARG;
+  if (dw_taps <= 0) dw_taps = ntaps;
   if (!wpatch_ok(C, N)) return AIR_ERR_UNSUPPORTED;
-  if (x_ld % 8 != 0 || dy_ld % 8 != 0 || dw_ld < static_cast<long long>(ntaps) * C) return AIR_ERR_ARG;
+  if (x_ld % 8 != 0 || dy_ld % 8 != 0 || dw_ld < static_cast<long long>(dw_taps) * C) return AIR_ERR_ARG;
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) return AIR_ERR_UNSUPPORTED;
   WParams p;
   p.B = B; p.H = H; p.W = W; p.C = C; p.N = N; p.dw = dw_out; p.dw_ld = dw_ld;
@@ -226,6 +232,15 @@ static int launch_wgrad_patch(const void* x, long long x_ld, int B, int H, int W
       }                                                              // else: lbo = 0, the second group duplicates the first
     }
   }
+  if (tap_id) {                                                        // accumulators write the layer's real tap slots
+    for (int a = 0; a < p.nacc; ++a)
+      for (int g = 0; g < 8; ++g)
+        if (p.acc_tap[a][g] >= 0) {
+          const int id = tap_id[p.acc_tap[a][g]];
+          if (id < 0 || id >= dw_taps) return AIR_ERR_ARG;
+          p.acc_tap[a][g] = id;
+        }
+  }
   const long long items = static_cast<long long>(B) * p.HP * p.WT;
   if (items > 0x7fffffffLL) return AIR_ERR_UNSUPPORTED;
   p.items = static_cast<uint32_t>(items);
@@ -234,8 +249,11 @@ static int launch_wgrad_patch(const void* x, long long x_ld, int B, int H, int W
   if (jobs > num_sms) return AIR_ERR_UNSUPPORTED;
   p.parts = static_cast<int>(std::min<long long>(num_sms / jobs, items));
   CUtensorMap tmx, tmdy;
-  int tr = p.narrow ? air_tmap::make_act_tmap(&tmx, x, x_ld, B, H, W, C, 16, p.pw, PR, 32)
-                    : air_tmap::make_act_tmap(&tmx, x, x_ld, B, H, W, C, 64, p.pw, PR, 128);
+  int tr;
+  if (xv) tr = air_tmap::make_act_tmap_strided(&tmx, xv->base, xv->sw, xv->sh, xv->sb, B, xv->H, xv->W, C, p.narrow ? 16 : 64,
+                                               p.pw, PR, p.narrow ? 32 : 128);
+  else tr = p.narrow ? air_tmap::make_act_tmap(&tmx, x, x_ld, B, H, W, C, 16, p.pw, PR, 32)
+                     : air_tmap::make_act_tmap(&tmx, x, x_ld, B, H, W, C, 64, p.pw, PR, 128);
   if (tr == 0) tr = air_tmap::make_act_tmap(&tmdy, dy, dy_ld, B, H, W, N, 64, TW, R, 128);
   if (tr != 0) return tr < 0 ? AIR_ERR_DRIVER : 10000 + tr;
   const size_t smem = 1024 + static_cast<size_t>(STAGES) * p.stage_bytes + (2 * STAGES + 1) * 8 + 16;
@@ -276,4 +294,48 @@ extern "C" int air_conv3x3_wgrad_patch_bf16(const void* x, long long x_ld, int B
                                             const void* dy, long long dy_ld, int N,
                                             float* dw_out, long long dw_ld, int num_sms, cudaStream_t stream) {
   return air_conv_wgrad_patch_bf16(x, x_ld, B, H, W, C, dy, dy_ld, N, 3, dw_out, dw_ld, num_sms, stream);
+}
+
+// Weight gradient of a k x k (k = 3 / pad 1, or k = 1 / pad 0) STRIDE-2 convolution (the first convolution and the
+// shortcut of a down-sampling block, resnet.py:56-60):
+//     dW[co][i][j][ci] += sum_{b,ho,wo} x[b, 2 ho + i - p, 2 wo + j - p, ci] * dy[b, ho, wo, co]
+// The input pixels a tap touches all share the tap's row / column parity, so the layer splits into one stride-1 problem per
+// parity class of x (a strided sub-image = an ordinary TMA tensor map) with only that class's taps: 4 / 2 / 2 / 1 taps for
+// 3x3, the single tap for 1x1.  No zero-stuffed gather, no im2col: x is read once, dy once per class.
+//   x (B, H, W, C) with pixel stride x_ld;  dy (B, Ho, Wo, N) with pixel stride dy_ld;  dw_out fp32 [N][dw_ld >= k*k*C].
+extern "C" int air_conv_s2_wgrad_patch_bf16(const void* x, long long x_ld, int B, int H, int W, int C,
+                                            const void* dy, long long dy_ld, int Ho, int Wo, int N, int k,
+                                            float* dw_out, long long dw_ld, int num_sms, cudaStream_t stream) {
+  if (k != 3 && k != 1) return AIR_ERR_UNSUPPORTED;
+  if (!x || !dy || !dw_out || B <= 0 || H < 1 || W < 1) return AIR_ERR_ARG;
+  const int pad = k == 3 ? 1 : 0;
+  if (Ho != (H + 2 * pad - k) / 2 + 1 || Wo != (W + 2 * pad - k) / 2 + 1) return AIR_ERR_ARG;
+  if (C == 16) return AIR_ERR_UNSUPPORTED;                             // narrow mode needs runs of adjacent taps
+  const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
+  for (int pr = 0; pr < 2; ++pr) {
+    for (int pc = 0; pc < 2; ++pc) {
+      // taps (i, j) whose input row 2 ho + i - pad has parity pr (columns likewise); sub-image row of tap i for output
+      // row ho: (2 ho + i - pad - pr) / 2 = ho + (i - pad - pr) / 2  ->  patch origin -1 when some tap reaches back
+      int dr[9], dc[9], id[9], nt = 0, org_h = 0, org_w = 0;
+      for (int i = 0; i < k; ++i) if (((i - pad - pr) & 1) == 0 && (i - pad - pr) / 2 < 0) org_h = -1;
+      for (int j = 0; j < k; ++j) if (((j - pad - pc) & 1) == 0 && (j - pad - pc) / 2 < 0) org_w = -1;
+      for (int i = 0; i < k; ++i) {
+        if ((i - pad - pr) & 1) continue;
+        for (int j = 0; j < k; ++j) {
+          if ((j - pad - pc) & 1) continue;
+          dr[nt] = (i - pad - pr) / 2 - org_h; dc[nt] = (j - pad - pc) / 2 - org_w; id[nt] = i * k + j;
+          ++nt;
+        }
+      }
+      if (nt == 0) continue;
+      const int Hs = (H - pr + 1) / 2, Ws = (W - pc + 1) / 2;             // rows / columns of this parity class
+      if (Hs < 1 || Ws < 1) continue;
+      XView xv{xb + (static_cast<long long>(pr) * W + pc) * x_ld, 2 * x_ld, 2 * static_cast<long long>(W) * x_ld,
+               static_cast<long long>(H) * W * x_ld, Hs, Ws};
+      const int st = launch_wgrad_patch(x, x_ld, B, Ho, Wo, C, dy, dy_ld, N, nt, dr, dc, org_h, org_w, dw_out, dw_ld, num_sms,
+                                        stream, &xv, id, k * k);
+      if (st != 0) return st;
+    }
+  }
+  return AIR_OK;
 }

@@ -45,6 +45,25 @@ static inline int make_act_tmap(CUtensorMap* tm, const void* base, long long ld,
   return static_cast<int>(r);
 }
 
+// The same 4-D view with explicit element strides between W neighbours / H neighbours / images: a strided sub-image of
+// a channels-last tensor (e.g. every second pixel of every second row, starting at `base`) is an ordinary tensor map.
+static inline int make_act_tmap_strided(CUtensorMap* tm, const void* base, long long sw, long long sh, long long sb,
+                                        int B, int H, int W, int C, int box_c, int box_w, int box_h, int swizzle_bytes) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return -1;
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                        static_cast<cuuint64_t>(B)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(sw) * 2, static_cast<cuuint64_t>(sh) * 2, static_cast<cuuint64_t>(sb) * 2};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUtensorMapSwizzle swz = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                         : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                         : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return static_cast<int>(r);
+}
+
 // bf16 row-major matrix [rows][ld >= cols] viewed as the 2-D tensor (cols, rows) with a (64, box_rows) SWIZZLE_128B box:
 // the A operand of a 1x1 / stride-1 convolution (rows = pixels, cols = channels) needs no gather at all.
 static inline int make_mat_tmap(CUtensorMap* tm, const void* base, long long ld, long long rows, int cols, int box_rows) {

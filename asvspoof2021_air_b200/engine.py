@@ -106,6 +106,9 @@ class ConvLayer:
         # stride-2 layers: data gradient by output parity classes on the patch kernel (3x3 pad 1, or the 1x1 shortcut)
         self.s2_dgrad_ok = (need_dgrad and plain and geom in ((3, 3, 2, 2, 1, 1, 1, 1), (1, 1, 2, 2, 0, 0, 1, 1))
                             and ops.patch_supported(cout, cin, 1, 1))
+        # stride-2 layers: weight gradient as one stride-1 patch problem per input parity class (strided TMA sub-images)
+        self.s2_wgrad_ok = (geom in ((3, 3, 2, 2, 1, 1, 1, 1), (1, 1, 2, 2, 0, 0, 1, 1)) and self._wtmp is None
+                            and cin % 64 == 0 and ops.wgrad_patch_supported(cin, cout))
         # 1x1 / stride-1 layers: a GEMM over pixels through the same TMA kernel (single tap)
         self.p1x1_ok = (geom == (1, 1, 1, 1, 0, 0, 1, 1) and plain and ops.patch_supported(cin, cout, 1, 1)
                         and (not need_dgrad or ops.patch_supported(cout, cin, 1, 1)))
@@ -227,6 +230,10 @@ class ConvLayer:
         if self.d1_ok:
             ops.conv1d_wgrad_patch(x, x_ld, B, H, W, self.cin, dy, dy_ld, self.cout, self.kw, self.dw,
                                    self.store.grad(self.name + ".weight"))
+            return
+        if self.s2_wgrad_ok and self._patch_efficiency(Ho, Wo) >= 0.5:
+            ops.conv_s2_wgrad_patch(x, x_ld, B, H, W, self.cin, dy, dy_ld, Ho, Wo, self.cout, self.kh,
+                                    self.store.grad(self.name + ".weight"))
             return
         if self.wpatch_ok and self._patch_efficiency(H, W) >= 0.5:
             ops.conv_wgrad_patch(x, x_ld, B, H, W, self.cin, dy, dy_ld, self.cout, self.kh,

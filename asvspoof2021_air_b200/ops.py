@@ -223,6 +223,16 @@ def conv_wgrad_patch(x, x_ld, B, H, W, C, dy, dy_ld, N, k, dw_out, dw_ld=None):
     return dw_out
 
 
+def conv_s2_wgrad_patch(x, x_ld, B, H, W, C, dy, dy_ld, Ho, Wo, N, k, dw_out, dw_ld=None):
+    """Weight gradient of a stride-2 k x k (k = 3 pad 1 / k = 1 pad 0) layer: one stride-1 patch problem per input parity
+    class (csrc/conv_wgrad_patch.cu); dw_out fp32 [N][k*k*C] accumulated in place."""
+    _lib.check(_lib.lib().air_conv_s2_wgrad_patch_bf16(
+        _lib.ptr(x), _lib.LL(x_ld), B, H, W, C, _lib.ptr(dy), _lib.LL(dy_ld), Ho, Wo, N, k, _lib.ptr(dw_out),
+        _lib.LL(k * k * C if dw_ld is None else dw_ld), num_sms(), _lib.stream_ptr()), "air_conv_s2_wgrad_patch_bf16",
+        4 if k == 3 else 1)
+    return dw_out
+
+
 def conv3x3_patch_stats(a, a_ld, B, H, W, C, wpk, N, out, out_ld, res, res_ld, relu, stats):
     """3x3 / s1 / p1 forward that also adds the per-channel sum / sum of squares of its output to `stats` (fp64 [2N])."""
     if _is_f32(out):
@@ -603,6 +613,7 @@ conv1d_patch = _timed(conv1d_patch, lambda a: "conv_dgrad" if (len(a) > 18 and a
                       lambda a: 2.0 * a[2] * a[3] * a[4] * a[5] * a[9] * a[7])
 conv1d_wgrad_patch = _timed(conv1d_wgrad_patch, "conv_wgrad", lambda a: 2.0 * a[2] * a[3] * a[4] * a[5] * a[8] * a[9])
 conv3x3_patch_stats = _timed(conv3x3_patch_stats, "conv_fprop", lambda a: 2.0 * a[2] * a[3] * a[4] * a[5] * a[7] * 9)
+conv_s2_wgrad_patch = _timed(conv_s2_wgrad_patch, "conv_wgrad", lambda a: 2.0 * a[2] * a[8] * a[9] * a[5] * a[10] * a[11] * a[11])
 
 
 # ------------------------------------------------------------------------------------------

@@ -204,6 +204,11 @@ int air_conv_wgrad_patch_bf16(const void* x, long long x_ld, int B, int H, int W
                               float* dw_out, long long dw_ld, int num_sms, air_stream_t stream);
 /* weight gradient of a 1-D convolution over W (kernel k <= 5 odd, dilation d, "same" padding, d*(k-1) <= 8; H rows are
  * independent sequences): dw_out [N][k][C] fp32, accumulated (ecapa_tdnn.py:50 and its autograd) */
+/* stride-2 k x k (k = 3 pad 1 / k = 1 pad 0) weight gradient as one stride-1 patch problem per input parity class
+ * (strided TMA sub-images, only the class's taps): x (B,H,W,C), dy (B,Ho,Wo,N), dw_out fp32 [N][dw_ld >= k*k*C] */
+int air_conv_s2_wgrad_patch_bf16(const void* x, long long x_ld, int B, int H, int W, int C,
+                                 const void* dy, long long dy_ld, int Ho, int Wo, int N, int k,
+                                 float* dw_out, long long dw_ld, int num_sms, air_stream_t stream);
 int air_conv1d_wgrad_patch_bf16(const void* x, long long x_ld, int B, int H, int W, int C,
                                 const void* dy, long long dy_ld, int N, int k, int d,
                                 float* dw_out, long long dw_ld, int num_sms, air_stream_t stream);

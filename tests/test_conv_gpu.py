@@ -364,3 +364,35 @@ def test_patch_conv_fused_batchnorm_statistics(shape):
     s, q = o.sum(0), (o * o).sum(0)
     assert torch.allclose(stats[:Cout], s, rtol=1e-5, atol=1e-3 * float(o.abs().sum(0).max()) * 1e-3)
     assert torch.allclose(stats[Cout:], q, rtol=1e-5)
+
+
+S2_WGRAD_CASES = {
+    # name: B, H, W, Cin, Cout, k        (stride 2; k = 3 pad 1 or k = 1 pad 0)
+    "l2_3x3_even": (2, 18, 150, 64, 128, 3),
+    "l3_3x3_odd": (2, 9, 375, 128, 256, 3),             # odd H and W: the last row / column has no partner in one parity class
+    "l4_3x3_odd_h": (2, 5, 188, 256, 512, 3),
+    "l2_sc_1x1": (2, 18, 150, 64, 128, 1),
+    "l3_sc_1x1_odd": (3, 9, 375, 128, 256, 1),
+}
+
+
+@pytest.mark.parametrize("name", list(S2_WGRAD_CASES))
+def test_stride2_wgrad_by_parity_classes(name):
+    """air_conv_s2_wgrad_patch_bf16 (strided TMA sub-images, one stride-1 patch problem per input parity class) against
+    torch's conv2d_weight on the same bf16 operands; x is a channel slice of a wider tensor (pixel stride != C)."""
+    from asvspoof2021_air_b200 import ops
+    B, H, W, Cin, Cout, k = S2_WGRAD_CASES[name]
+    pad = 1 if k == 3 else 0
+    g = torch.Generator(device="cpu").manual_seed(3)
+    Ho, Wo = ops.conv_out_size(H, k, 2, pad, 1), ops.conv_out_size(W, k, 2, pad, 1)
+    xw = torch.randn(B, H, W, Cin + 64, generator=g).cuda().to(torch.bfloat16)
+    xn = xw[..., 64:]                                                     # view: pixel stride Cin + 64
+    dyn = torch.randn(B, Ho, Wo, Cout, generator=g).cuda().to(torch.bfloat16)
+    ref = torch.nn.grad.conv2d_weight(xn.float().permute(0, 3, 1, 2), (Cout, Cin, k, k), dyn.float().permute(0, 3, 1, 2),
+                                      stride=2, padding=pad)
+    dwb = torch.zeros(Cout, k * k * Cin, device="cuda")
+    ops.conv_s2_wgrad_patch(xn, Cin + 64, B, H, W, Cin, dyn, Cout, Ho, Wo, Cout, k, dwb)
+    torch.cuda.synchronize()
+    got = dwb.view(Cout, k, k, Cin).permute(0, 3, 1, 2)
+    err = (got - ref).abs()
+    assert float(err.max()) <= 1e-3 * float(ref.abs().max()) + 1e-3, (name, float(err.max()), float(ref.abs().max()))
