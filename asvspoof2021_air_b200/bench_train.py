@@ -164,10 +164,12 @@ def run(args, rank, world, helpers):
         "config": workload_config(args.workload, B, world, overlap),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak if peak else None,
-                     # ncu --set full of the largest launches (profiles/r01_ncu_full_v6_summary.txt): layer-1 3x3 fprop moves
-                     # 834 MB of DRAM traffic for 885 MB algorithmic, layer-1 wgrad 889 MB for 885 MB -- no re-reads
-                     "traffic": 834.4e6 if (arch == "resnet" and B == 256 and not scoring) else None,
-                     "traffic_kernel": "air_patch::conv_patch_kernel, layer-1 3x3 fprop" if arch == "resnet" else None,
+                     # ncu --set full of the current kernels (profiles/r02_ncu_metrics.json): the layer-1 3x3 fprop in its
+                     # in-step form (residual + fused BatchNorm statistics) moves 1 295 MB of DRAM traffic for 1 327 MB
+                     # algorithmic (x + residual + out), the layer-1 wgrad 890 MB for 885 MB -- no re-reads
+                     "traffic": helpers.ncu_traffic("patch_l1_stats") if (arch == "resnet" and B == 256 and not scoring) else None,
+                     "traffic_kernel": "air_patch::conv_patch_kernel, layer-1 3x3 fprop (+ residual, fused BN statistics)"
+                                       if arch == "resnet" else None,
                      "peak_src": peaks["src"] + " (sustained)",
                      "kernel": "conv stack (all tcgen05): air_patch::conv_patch_kernel (3x3 / 1x1 fprop + dgrad, stride-2 dgrad "
                                "by parity), air_wpatch::conv3x3_wgrad_patch_kernel, air_gemm::conv_gemm_kernel, "

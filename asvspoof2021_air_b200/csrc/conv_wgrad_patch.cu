@@ -43,7 +43,9 @@ struct WParams {
   // operand geometry: "wide" = 64 input channels per pixel row (SWIZZLE_128B, two 64-row groups per M = 128),
   // "narrow" = 16 input channels (SWIZZLE_32B, eight 16-row groups = eight consecutive pixel shifts per M = 128)
   int narrow, ktaps, org_h, org_w;                  // taps of the layer; patch origin relative to the item's first pixel
-  int pw;                                           // patch width in pixels (TW + 2, or TW + 8 for dilated 1-D taps)
+  int tw;                                           // pixels per row segment of an item (K of the MMAs): 128, or 96 when
+                                                    // that covers W with less padding (W = 94 / 188: 73 % -> 98 % useful)
+  int pw;                                           // patch width in pixels (tw + 2, or tw + 8 for dilated 1-D taps)
   uint32_t x_bytes, stage_bytes;
   int nacc; int acc_off[NACC]; int acc_lbo[NACC];   // per accumulator: window offset / group distance, in patch pixels
   int acc_tap[NACC][8];                             // tap of each M row group (-1: not a real tap)
@@ -88,10 +90,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_wgrad_patch_kernel(const _
       for (uint32_t k = 0; k < my_items; ++k) {
         const uint32_t item = part + k * p.parts;
         const uint32_t wt = item % WT, r1 = item / WT;
-        const int w0 = static_cast<int>(wt) * TW, h0 = static_cast<int>(r1 % HP) * R, b = static_cast<int>(r1 / HP);
+        const int w0 = static_cast<int>(wt) * p.tw, h0 = static_cast<int>(r1 % HP) * R, b = static_cast<int>(r1 / HP);
         mbar_wait(&empty[stage], phase ^ 1);
         const uint32_t dst = sbase + stage * p.stage_bytes;
-        mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>(PR * p.pw) * (p.narrow ? 32u : 128u) + DY_BYTES);
+        mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>(PR * p.pw) * (p.narrow ? 32u : 128u) + static_cast<uint32_t>(R * p.tw) * 128u);
         tma_load_4d(dst, &tmx, p.narrow ? 0 : cb * 64, w0 + p.org_w, h0 + p.org_h, b, &full[stage]);
         tma_load_4d(dst + p.x_bytes, &tmdy, nb * 64, w0, h0, b, &full[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -120,8 +122,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_wgrad_patch_kernel(const _
 #pragma unroll
       for (int r = 0; r < R; ++r) {
 #pragma unroll 2
-        for (int ks = 0; ks < TW / 16; ++ks) {
-          const uint64_t bd = bbase + (d16 + static_cast<uint32_t>(r * TW + ks * 16) * 8);
+        for (int ks = 0; ks < p.tw / 16; ++ks) {
+          const uint64_t bd = bbase + (d16 + static_cast<uint32_t>(r * p.tw + ks * 16) * 8);
           const uint32_t xrow = x16 + static_cast<uint32_t>(r * p.pw + ks * 16) * upp;
 #pragma unroll
           for (int a = 0; a < NACC; ++a) {
@@ -201,10 +203,11 @@ static int launch_wgrad_patch(const void* x, long long x_ld, int B, int H, int W
     if (tap_dr[t] < 0 || tap_dr[t] > PR - R || tap_dc[t] < 0 || tap_dc[t] > 8) return AIR_ERR_ARG;
     max_dc = std::max(max_dc, tap_dc[t]);
   }
-  p.pw = max_dc <= 2 ? PW : TW + 8;
-  p.NCB = p.narrow ? 1 : C / 64; p.NNB = N / 64; p.WT = (W + TW - 1) / TW; p.HP = (H + R - 1) / R;
+  p.tw = ((W + 95) / 96) * 96 < ((W + TW - 1) / TW) * TW ? 96 : TW;
+  p.pw = p.tw + (max_dc <= 2 ? 2 : 8);
+  p.NCB = p.narrow ? 1 : C / 64; p.NNB = N / 64; p.WT = (W + p.tw - 1) / p.tw; p.HP = (H + R - 1) / R;
   p.x_bytes = (static_cast<uint32_t>(PR * p.pw) * (p.narrow ? 32u : 128u) + 1023u) / 1024u * 1024u;
-  p.stage_bytes = p.x_bytes + DY_BYTES;
+  p.stage_bytes = p.x_bytes + DY_BYTES;             // dy slot sized for the widest tile
   for (int a = 0; a < NACC; ++a) { p.acc_off[a] = 0; p.acc_lbo[a] = 0; for (int g = 0; g < 8; ++g) p.acc_tap[a][g] = -1; }
   int off[9];
   for (int t = 0; t < ntaps; ++t) off[t] = tap_dr[t] * p.pw + tap_dc[t];
@@ -254,7 +257,7 @@ static int launch_wgrad_patch(const void* x, long long x_ld, int B, int H, int W
                                                p.pw, PR, p.narrow ? 32 : 128);
   else tr = p.narrow ? air_tmap::make_act_tmap(&tmx, x, x_ld, B, H, W, C, 16, p.pw, PR, 32)
                      : air_tmap::make_act_tmap(&tmx, x, x_ld, B, H, W, C, 64, p.pw, PR, 128);
-  if (tr == 0) tr = air_tmap::make_act_tmap(&tmdy, dy, dy_ld, B, H, W, N, 64, TW, R, 128);
+  if (tr == 0) tr = air_tmap::make_act_tmap(&tmdy, dy, dy_ld, B, H, W, N, 64, p.tw, R, 128);
   if (tr != 0) return tr < 0 ? AIR_ERR_DRIVER : 10000 + tr;
   const size_t smem = 1024 + static_cast<size_t>(STAGES) * p.stage_bytes + (2 * STAGES + 1) * 8 + 16;
   static bool attr_done = false;

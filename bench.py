@@ -48,6 +48,18 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
 
 
+def ncu_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of a kernel, from the tracked summary of the round's
+    `ncu --set full` captures (profiles/r02_ncu_metrics.json, written by scripts/gpu_ncu_r02.sh); None when absent."""
+    path = os.path.join(ROOT, "profiles", "r02_ncu_metrics.json")
+    try:
+        with open(path) as f:
+            d = json.load(f).get(key) or {}
+        return d.get("traffic_bytes")
+    except (OSError, ValueError):
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -234,9 +246,9 @@ def run_lfcc(args, rank, world):
         "config": lfcc_config(B, nbuf),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"],
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/r01_ncu_full_v6_summary.txt):
-                     # the 65.5 MB of waves are read once; most of the 24.6 MB of output is still L2-resident at kernel end
-                     "traffic": 69.3e6 if (mod.impl == "tc" and B == 256) else None, "peak_src": peaks["src"],
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/r02_ncu_metrics.json): the 65.5 MB
+                     # of waves are read once; most of the 24.6 MB of output is still L2-resident at kernel end
+                     "traffic": ncu_traffic("lfcc_tc") if (mod.impl == "tc" and B == 256) else None, "peak_src": peaks["src"],
                      "kernel": ("air_lfcc_tc::lfcc_tc_kernel (tensor-core folded DFT)" if mod.impl == "tc"
                                 else "air_lfcc::lfcc_kernel (radix FFT on CUDA cores)"),
                      "bytes_per_launch": B * LFCC_BYTES_PER_UTT,

@@ -15,6 +15,26 @@ if kind == "patch":
     wpk = torch.empty(9 * C * N, device="cuda", dtype=torch.bfloat16)
     ops.pack3x3(w, C, N, 0, wpk)
     f = lambda: ops.conv3x3_patch(x, C, B, H, W, C, wpk, N, out, N)
+elif kind == "patch_stats":          # the in-step form of a layer-1 3x3: residual add + fused BatchNorm statistics epilogue
+    wpk = torch.empty(9 * C * N, device="cuda", dtype=torch.bfloat16)
+    ops.pack3x3(w, C, N, 0, wpk)
+    res = torch.randn(B, H, W, N, device="cuda").to(torch.bfloat16)
+    stats = torch.zeros(2 * N, device="cuda", dtype=torch.float64)
+    f = lambda: ops.conv3x3_patch_stats(x, C, B, H, W, C, wpk, N, out, N, res, N, False, stats)
+elif kind == "s2_wgrad":             # stride-2 3x3 weight gradient by parity classes: x (B,H,W,C), dy (B,H/2,W/2,N)
+    Ho, Wo = (H + 1) // 2, (W + 1) // 2
+    dy = torch.randn(B, Ho, Wo, N, device="cuda").to(torch.bfloat16)
+    dw = torch.zeros(N, 9 * C, device="cuda")
+    f = lambda: ops.conv_s2_wgrad_patch(x, C, B, H, W, C, dy, N, Ho, Wo, N, 3, dw)
+elif kind == "bn_bwd":               # BatchNorm backward (reduce + apply) on a (B*H*W, C) tensor: the HBM-bound reference point
+    M = B * H * W
+    mean, invstd = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    gamma, beta = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
+    rsum = torch.zeros(2 * C, device="cuda", dtype=torch.float64)
+    dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dxo = torch.empty_like(x)
+    xin, dyin = x, torch.randn(B, H, W, C, device="cuda").to(torch.bfloat16)
+    f = lambda: ops.bn_bwd(dyin, C, xin, C, None, 0, dxo, C, M, C, 0, mean, invstd, gamma, beta, rsum, dg, db)
 elif kind == "gemm":
     wpk = ops.pack_weights(w.reshape(N, 9, C).contiguous(), 0, C, N, 9)
     f = lambda: ops.conv_gemm(x, C, B, H, W, C, H, W, 3, 3, 1, 1, 1, 1, 1, 1, 0, wpk, N, 9 * C, out, N)
