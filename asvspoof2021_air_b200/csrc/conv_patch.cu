@@ -19,8 +19,11 @@
 // Roles (256 threads): warp 0 issues the patch TMA loads, warp 1 streams pre-swizzled weight slices (one
 // bulk copy per (channel block, tap); all slices stay resident when they fit), warp 2 issues tcgen05.mma
 // (M = 128 pixels, N = output channels, K = 16 per instruction; the whole warp runs the warp-uniform loop so
-// descriptors live in uniform registers, one elected lane issues), warps 4-7 drain the double-buffered TMEM
-// accumulators.  Persistent grid.
+// descriptors live in uniform registers, one elected lane issues), warps 4-11 drain the double-buffered TMEM
+// accumulators: warp w owns TMEM lanes 32 (w % 4) .. +31 (one pixel per lane) and the 32-channel blocks of parity
+// (w - 4) / 4, so every scheduler holds two epilogue warps whose global-load / TMEM / shuffle latencies overlap
+// (ncu of the four-warp version: the epilogue warps issued 21 % of the time and bounded the N = 64 layers).
+// Persistent grid.
 #include <algorithm>
 #include "common.cuh"
 #include "tc05.cuh"
@@ -35,8 +38,8 @@ constexpr int PW = TW + 2;              // patch width
 constexpr int R = 2;                    // output rows per work item
 constexpr int PR = R + 2;               // patch rows
 constexpr int PW_MAX = TW + 8;          // widest patch (dilated 1-D convolutions)
-constexpr int THREADS = 256;
-constexpr int PSTAGES = 2;
+constexpr int THREADS = 384;            // 4 role warps + 2 x 4 epilogue warps
+constexpr int MAX_PSTAGES = 4;           // patch ring: 2 stages of a 64-channel block or 4 of a 32-channel block
 constexpr int MAX_TAPS = 9;
 
 struct PatchParams {
@@ -56,6 +59,7 @@ struct PatchParams {
   int CB, NCB, WT, HP;                  // channels per block (16 / 32 / 64), #blocks, column tiles, row pairs
   int row_bytes, layout;                // CB * 2; UMMA layout type (6 / 4 / 2)
   uint32_t pstage_bytes, bslot_bytes, bslot_stride;
+  int pstages;                          // patch ring depth
   int nb_slots, resident;               // weight ring
   int acc_stages;                       // 1 or 2
   int ntaps; int tap_off[MAX_TAPS]; int tap_slice[MAX_TAPS];     // window offset in patch pixels, weight slice
@@ -158,11 +162,92 @@ __device__ __forceinline__ void epilogue_chunk(const PatchParams& p, uint32_t ta
   }
 }
 
+struct MmaCtx {
+  const PatchParams& p;
+  uint32_t sP, sB, tmem_base;
+  uint64_t *full_p, *empty_p, *full_b, *empty_b, *tfull, *tempty;
+};
+
+// The MMA warp.  NT = taps (0: run-time p.ntaps), KKT = K = 16 steps per channel block (0: run-time), RES = all weight slices
+// resident (waited for once) or streamed through the slot ring.
+template <int NT, int KKT, bool RES>
+__device__ __forceinline__ void mma_role(const MmaCtx& c) {
+  const PatchParams& p = c.p;
+  const bool leader = elect_one();
+  const int ntaps = NT > 0 ? NT : p.ntaps;
+  const int KK = KKT > 0 ? KKT : (p.CB >> 4);
+  const int NCB = p.NCB, N = p.N, GH = p.GH, acc_stages = p.acc_stages, nb_slots = p.nb_slots;
+  const uint32_t WT = p.WT, HP = p.HP, items = p.items, PSTAGES = static_cast<uint32_t>(p.pstages);
+  const uint32_t pstage16 = p.pstage_bytes >> 4, bslot16 = p.bslot_stride >> 4;
+  const uint32_t idesc = instr_desc_bf16(TW, N, 0, 0);
+  const uint32_t rb16 = static_cast<uint32_t>(p.row_bytes) >> 4;                  // row stride in 16-byte units
+  // descriptor high word: SBO = 8 rows, version 1, swizzle mode
+  const uint64_t desc_hi = static_cast<uint64_t>(((8u * p.row_bytes) >> 4) | (1u << 14) | (static_cast<uint32_t>(p.layout) << 29)) << 32;
+  const uint32_t row16 = static_cast<uint32_t>(p.pw) * rb16;                      // one patch row
+  uint32_t tap16[NT > 0 ? NT : MAX_TAPS];                                         // window offsets in 16-byte units
+#pragma unroll
+  for (int t = 0; t < (NT > 0 ? NT : MAX_TAPS); ++t) tap16[t] = static_cast<uint32_t>(p.tap_off[t]) * rb16;
+  const uint32_t sP16 = ((c.sP >> 4) & 0x3FFF) | (1u << 16), sB16 = ((c.sB >> 4) & 0x3FFF) | (1u << 16);
+  if (RES) {                                      // every slice is loaded exactly once: wait for all of them up front
+    for (int s = 0; s < NCB * ntaps; ++s) mbar_wait(&c.full_b[s], 0);
+    fence_after_sync();
+  }
+  uint32_t pstage = 0, pphase = 0, slot = 0, bphase = 0, it = 0;
+  for (uint32_t item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+    const uint32_t hp = (item / WT) % HP;
+    const bool two = GH - static_cast<int>(hp) * R >= 2;
+    const uint32_t acc = acc_stages == 2 ? (it & 1) : 0;
+    const uint32_t acc_phase = acc_stages == 2 ? ((it >> 1) & 1) : (it & 1);
+    mbar_wait(&c.tempty[acc], acc_phase ^ 1);
+    fence_after_sync();
+    const uint32_t d0 = c.tmem_base + acc * R * N, d1 = d0 + N;
+    for (int cb = 0; cb < NCB; ++cb) {
+      mbar_wait(&c.full_p[pstage], pphase);
+      fence_after_sync();
+      const uint32_t a_lo = sP16 + pstage * pstage16;
+      const uint32_t b_cb = sB16 + static_cast<uint32_t>(cb * ntaps) * bslot16;
+#pragma unroll
+      for (int t = 0; t < (NT > 0 ? NT : MAX_TAPS); ++t) {
+        if (NT == 0 && t >= ntaps) break;
+        uint32_t b_lo;
+        if (RES) {
+          b_lo = b_cb + static_cast<uint32_t>(t) * bslot16;
+        } else {
+          mbar_wait(&c.full_b[slot], bphase);
+          fence_after_sync();
+          b_lo = sB16 + slot * bslot16;
+        }
+        const uint64_t ad0 = desc_hi | (a_lo + tap16[t]), ad1 = ad0 + row16, bd = desc_hi | b_lo;
+        if (leader) {
+          if (KKT > 0) {
+#pragma unroll
+            for (int kk = 0; kk < KKT; ++kk) mma_bf16(d0, ad0 + 2 * kk, bd + 2 * kk, idesc, (t | kk) != 0 ? 1u : static_cast<uint32_t>(cb != 0));
+            if (two) {
+#pragma unroll
+              for (int kk = 0; kk < KKT; ++kk) mma_bf16(d1, ad1 + 2 * kk, bd + 2 * kk, idesc, (t | kk) != 0 ? 1u : static_cast<uint32_t>(cb != 0));
+            }
+          } else {
+            for (int kk = 0; kk < KK; ++kk) mma_bf16(d0, ad0 + 2 * kk, bd + 2 * kk, idesc, (cb | t | kk) != 0);
+            if (two)
+              for (int kk = 0; kk < KK; ++kk) mma_bf16(d1, ad1 + 2 * kk, bd + 2 * kk, idesc, (cb | t | kk) != 0);
+          }
+          if (!RES) mma_commit(&c.empty_b[slot]);
+        }
+        if (!RES) { if (++slot == static_cast<uint32_t>(nb_slots)) { slot = 0; bphase ^= 1; } }
+      }
+      if (leader) mma_commit(&c.empty_p[pstage]);
+      if (++pstage == PSTAGES) { pstage = 0; pphase ^= 1; }
+    }
+    if (leader) mma_commit(&c.tfull[acc]);
+  }
+}
+
 __global__ void __launch_bounds__(THREADS, 1) conv_patch_kernel(const __grid_constant__ CUtensorMap tmap, const PatchParams p) {
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;      // swizzle patterns are anchored at 1024 B
   const uint32_t sP = sbase;
+  const uint32_t PSTAGES = static_cast<uint32_t>(p.pstages);
   const uint32_t sB = sbase + PSTAGES * p.pstage_bytes;
   uint8_t* gen = smem_raw + (sbase - smem_u32(smem_raw));
   uint64_t* bars = reinterpret_cast<uint64_t*>(gen + PSTAGES * p.pstage_bytes + static_cast<size_t>(p.nb_slots) * p.bslot_stride);
@@ -171,7 +256,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_patch_kernel(const __grid_con
   uint64_t* full_b = bars + 2 * PSTAGES;            // [nb_slots] expect_tx
   uint64_t* empty_b = full_b + p.nb_slots;          // [nb_slots] tcgen05.commit
   uint64_t* tfull = empty_b + p.nb_slots;           // [2]
-  uint64_t* tempty = tfull + 2;                     // [2] 128 epilogue threads
+  uint64_t* tempty = tfull + 2;                     // [2] 256 epilogue threads
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* s_stats = p.stats ? reinterpret_cast<float*>(tmem_slot + 4) : nullptr;      // [4 epilogue warps][2][N] partial sums
 
@@ -179,9 +264,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_patch_kernel(const __grid_con
   while (ncols < static_cast<uint32_t>(p.acc_stages * R * p.N)) ncols <<= 1;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < PSTAGES; ++s) { mbar_init(&full_p[s], 1); mbar_init(&empty_p[s], 1); }
+    for (uint32_t s = 0; s < PSTAGES; ++s) { mbar_init(&full_p[s], 1); mbar_init(&empty_p[s], 1); }
     for (int s = 0; s < p.nb_slots; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 256); }
     fence_barrier_init();
     tma_prefetch_desc(&tmap);
   }
@@ -234,73 +319,33 @@ __global__ void __launch_bounds__(THREADS, 1) conv_patch_kernel(const __grid_con
     }
   } else if (warp == 2) {
     // ===================== MMA issuer (warp-uniform loop, elected lane issues) =====================
-    const bool leader = elect_one();
-    const uint32_t idesc = instr_desc_bf16(TW, p.N, 0, 0);
-    const uint32_t rb16 = static_cast<uint32_t>(p.row_bytes) >> 4;                  // row stride in 16-byte units
-    // descriptor high word: SBO = 8 rows, version 1, swizzle mode
-    const uint32_t desc_hi = ((8u * p.row_bytes) >> 4) | (1u << 14) | (static_cast<uint32_t>(p.layout) << 29);
+    // Specialised on (taps, K steps per channel block, resident weights) so that the tap / row / K loops are straight-line
+    // code with immediate offsets: the generic loop costs ~18 instructions per MMA (ncu: 81-110 cycles between MMAs of
+    // 32-64 cycles), which bounded every layer with N <= 128.
     const int KK = p.CB >> 4;
-    uint32_t pstage = 0, pphase = 0, slot = 0, bphase = 0;
-    uint32_t it = 0;
-    for (uint32_t item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-      const uint32_t hp = (item / WT) % HP;
-      const int rows = min(R, p.GH - static_cast<int>(hp) * R);
-      const uint32_t acc = p.acc_stages == 2 ? (it & 1) : 0;
-      const uint32_t acc_phase = p.acc_stages == 2 ? ((it >> 1) & 1) : (it & 1);
-      mbar_wait(&tempty[acc], acc_phase ^ 1);
-      fence_after_sync();
-      const uint32_t d0 = tmem_base + acc * R * p.N;
-      for (int cb = 0; cb < p.NCB; ++cb) {
-        mbar_wait(&full_p[pstage], pphase);
-        fence_after_sync();
-        const uint32_t a_lo = (((sP + pstage * p.pstage_bytes) >> 4) & 0x3FFF) | (1u << 16);
-        for (int t = 0; t < p.ntaps; ++t) {
-          uint32_t b0;
-          if (p.resident) {
-            const int s = cb * p.ntaps + t;
-            if (it == 0) { mbar_wait(&full_b[s], 0); fence_after_sync(); }
-            b0 = sB + s * p.bslot_stride;
-          } else {
-            mbar_wait(&full_b[slot], bphase);
-            fence_after_sync();
-            b0 = sB + slot * p.bslot_stride;
-          }
-          const uint32_t b_lo = ((b0 >> 4) & 0x3FFF) | (1u << 16);
-          const uint32_t a_tap = a_lo + static_cast<uint32_t>(p.tap_off[t]) * rb16;
-#pragma unroll
-          for (int j = 0; j < R; ++j) {
-            if (j < rows) {
-              const uint32_t arow = a_tap + static_cast<uint32_t>(j * p.pw) * rb16;
-              // persistent 64-bit descriptors, advanced in place by 32 B per K step (keeps the issue loop at
-              // ~5 uniform instructions per MMA instead of rebuilding both register pairs)
-              uint64_t ad = (static_cast<uint64_t>(desc_hi) << 32) | arow;
-              uint64_t bd = (static_cast<uint64_t>(desc_hi) << 32) | b_lo;
-              for (int kk = 0; kk < KK; ++kk) {
-                if (leader) mma_bf16(d0 + j * p.N, ad, bd, idesc, (cb | t | kk) != 0);
-                ad += 2; bd += 2;
-              }
-            }
-          }
-          if (!p.resident) {
-            if (leader) mma_commit(&empty_b[slot]);
-            if (++slot == static_cast<uint32_t>(p.nb_slots)) { slot = 0; bphase ^= 1; }
-          }
-        }
-        if (leader) mma_commit(&empty_p[pstage]);
-        if (++pstage == PSTAGES) { pstage = 0; pphase ^= 1; }
-      }
-      if (leader) mma_commit(&tfull[acc]);
-    }
+    const MmaCtx c{p, sP, sB, tmem_base, full_p, empty_p, full_b, empty_b, tfull, tempty};
+    if (p.resident && KK == 4 && p.ntaps == 9) mma_role<9, 4, true>(c);
+    else if (p.resident && KK == 4 && p.ntaps == 4) mma_role<4, 4, true>(c);
+    else if (p.resident && KK == 4 && p.ntaps == 3) mma_role<3, 4, true>(c);
+    else if (p.resident && KK == 4 && p.ntaps == 2) mma_role<2, 4, true>(c);
+    else if (p.resident && KK == 4 && p.ntaps == 1) mma_role<1, 4, true>(c);
+    else if (p.resident && KK == 1 && p.ntaps == 9) mma_role<9, 1, true>(c);
+    else if (p.resident && KK == 1 && p.ntaps == 1) mma_role<1, 1, true>(c);
+    else if (!p.resident && KK == 4 && p.ntaps == 9) mma_role<9, 4, false>(c);
+    else if (!p.resident && KK == 4 && p.ntaps == 4) mma_role<4, 4, false>(c);
+    else if (!p.resident && KK == 4 && p.ntaps == 2) mma_role<2, 4, false>(c);
+    else if (p.resident) mma_role<0, 0, true>(c);
+    else mma_role<0, 0, false>(c);
     __syncwarp();
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int q = warp & 3;
+    const int q = warp & 3, set = (warp - 4) >> 2;      // TMEM lane quarter; parity of the 32-channel blocks this warp drains
     const int m = q * 32 + lane;
     // fused BatchNorm statistics: lane l accumulates channel (32 cb + l) of its warp's pixels in registers, in a fixed
     // order (bit-reproducible run to run); combined per CTA in shared memory and across CTAs with fp64 atomics
-    float acc_s[8], acc_q[8];
+    float acc_s[4], acc_q[4];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) { acc_s[u] = 0.f; acc_q[u] = 0.f; }
+    for (int u = 0; u < 4; ++u) { acc_s[u] = 0.f; acc_q[u] = 0.f; }
     uint32_t it = 0;
     for (uint32_t item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
       const int wt = static_cast<int>(item % WT);
@@ -312,10 +357,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_patch_kernel(const __grid_con
       const int g = wt * TW + m;
       const int ow = g * p.osw + p.opw;
       const bool col_ok = g < p.GW && ow < p.OW;
-      // chunk list of the item: (row j, 32-column block); the residual of chunk i+1 is loaded while chunk i is
-      // processed, and the first one before the accumulator is even complete
       const int cpr = p.N >> 5, tail = p.N & 31;                       // full 32-column chunks per row, 16-column tail
-      const int nch = rows * cpr;
       static_assert(R == 2, "row select below assumes two rows per item");
       long long pixr[R]; bool valr[R];
 #pragma unroll
@@ -326,55 +368,53 @@ __global__ void __launch_bounds__(THREADS, 1) conv_patch_kernel(const __grid_con
       }
       const long long pix0 = pixr[0], pix1 = pixr[1];
       const bool val0 = valr[0], val1 = valr[1];
-      auto PIX = [&](int j) { return j == 0 ? pix0 : pix1; };
-      auto VAL = [&](int j) { return j == 0 ? val0 : val1; };
-      // column blocks of 32 channels; both rows of a block are processed together so that the fused BatchNorm
-      // statistics need one warp transpose-reduce per block instead of one per (row, block).  The residual of
-      // the first block is requested before the accumulator is even complete.
+      // column blocks of 32 channels (this warp: blocks set, set + 2, ...); both rows of a block are processed together
+      // so that the fused BatchNorm statistics need one warp transpose-reduce per block instead of one per (row, block).
+      // The residual of the first block is requested before the accumulator is even complete, the one of block i + 2
+      // while block i is processed.
       bf16x8 ra[4], rb[4];
-      (void)nch;
-      if (cpr > 0) { load_res<32>(p, pix0, 0, val0, ra); if (rows > 1) load_res<32>(p, pix1, 0, val1, rb); }
+      if (set < cpr) { load_res<32>(p, pix0, set << 5, val0, ra); if (rows > 1) load_res<32>(p, pix1, set << 5, val1, rb); }
       mbar_wait(&tfull[acc], acc_phase);
       fence_after_sync();
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * R * p.N;
       const bool st = s_stats != nullptr;
-      for (int cb = 0; cb < cpr; ++cb) {
+      for (int cb = set; cb < cpr; cb += 2) {
         const int c0 = cb << 5;
         float v0[32], v1[32];
         epilogue_chunk<32>(p, tacc, pix0, c0, val0, ra, v0, st);
         if (rows > 1) epilogue_chunk<32>(p, tacc + p.N, pix1, c0, val1, rb, v1, st);
-        if (cb + 1 < cpr) { load_res<32>(p, pix0, c0 + 32, val0, ra); if (rows > 1) load_res<32>(p, pix1, c0 + 32, val1, rb); }
+        if (cb + 2 < cpr) { load_res<32>(p, pix0, c0 + 64, val0, ra); if (rows > 1) load_res<32>(p, pix1, c0 + 64, val1, rb); }
         if (st) {                                   // warp-uniform: every lane takes part in the shuffles
-          float sq[32];
           if (rows > 1) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { sq[i] = fmaf(v0[i], v0[i], v1[i] * v1[i]); v0[i] += v1[i]; }
+            for (int i = 0; i < 32; ++i) { const float t = v1[i]; v1[i] = fmaf(v0[i], v0[i], t * t); v0[i] += t; }
           } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) sq[i] = v0[i] * v0[i];
+            for (int i = 0; i < 32; ++i) v1[i] = v0[i] * v0[i];
           }
           const float cs = warp_column_sums(v0, lane);
-          const float cq = warp_column_sums(sq, lane);
+          const float cq = warp_column_sums(v1, lane);
 #pragma unroll
-          for (int u = 0; u < 8; ++u) if (u == cb) { acc_s[u] += cs; acc_q[u] += cq; }
+          for (int u = 0; u < 4; ++u) if (u == (cb >> 1)) { acc_s[u] += cs; acc_q[u] += cq; }
         }
       }
-      if (tail) {
-        for (int j = 0; j < rows; ++j) {
-          float vt[16];
-          load_res<16>(p, PIX(j), cpr << 5, VAL(j), ra);
-          epilogue_chunk<16>(p, tacc + j * p.N, PIX(j), cpr << 5, VAL(j), ra, vt, false);
-        }
+      if (tail && set < rows) {                     // 16-column tail: row `set` of the item
+        float vt[16];
+        const long long pixt = set == 0 ? pix0 : pix1;
+        const bool valt = set == 0 ? val0 : val1;
+        load_res<16>(p, pixt, cpr << 5, valt, ra);
+        epilogue_chunk<16>(p, tacc + set * p.N, pixt, cpr << 5, valt, ra, vt, false);
       }
       fence_before_sync();
       mbar_arrive(&tempty[acc]);
     }
     if (s_stats != nullptr) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        if (u * 32 < p.N) {
-          s_stats[q * 2 * p.N + u * 32 + lane] = acc_s[u];
-          s_stats[q * 2 * p.N + p.N + u * 32 + lane] = acc_q[u];
+      for (int u = 0; u < 4; ++u) {
+        const int cb = 2 * u + set;
+        if (cb * 32 < p.N) {
+          s_stats[q * 2 * p.N + cb * 32 + lane] = acc_s[u];
+          s_stats[q * 2 * p.N + p.N + cb * 32 + lane] = acc_q[u];
         }
       }
     }
@@ -407,7 +447,15 @@ __global__ void pack_patch_kernel(const float* __restrict__ w, __nv_bfloat16* __
 
 using namespace air_patch;
 
-static int patch_cb(int C) { return C <= 64 ? C : 64; }
+// channels per block.  AIR_PATCH_CB32=1 splits 64-channel inputs into two 32-channel blocks (SWIZZLE_64B rows, a patch ring of
+// four half-size stages = three loads in flight per SM instead of one): measured SLOWER on the N = 64 layers (0.52 vs 0.39 ms,
+// profiles/experiments), so it is an experiment switch only.
+static int patch_cb(int C) {
+  static const int split64 = [] { const char* e = getenv("AIR_PATCH_CB32"); return (e && e[0] == '1') ? 1 : 0; }();
+  if (C == 64 && split64) return 32;
+  return C <= 64 ? C : 64;
+}
+extern "C" int air_conv_patch_cb(int C) { return patch_cb(C); }
 
 // 1 when (C, N) can run on the patch kernel
 extern "C" int air_conv3x3_patch_supported(int C, int N, int H, int W) {
@@ -521,6 +569,8 @@ extern "C" int air_conv_patch_taps_ex2_bf16(const void* a, long long a_ld, int B
   p.pstage_bytes = static_cast<uint32_t>((PR * p.pw * p.row_bytes + 1023) / 1024 * 1024);
   p.bslot_bytes = static_cast<uint32_t>(N * p.row_bytes);
   p.bslot_stride = (p.bslot_bytes + 1023u) / 1024u * 1024u;
+  p.pstages = p.pstage_bytes <= 36u * 1024u ? MAX_PSTAGES : 2;
+  const int PSTAGES = p.pstages;
   const int budget = 225 * 1024 - PSTAGES * static_cast<int>(p.pstage_bytes) - 2048;
   int slots = budget / static_cast<int>(p.bslot_stride);
   const int nslices = p.NCB * ntaps;

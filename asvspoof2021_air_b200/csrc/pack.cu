@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(256) pack_jobs_kernel(const long long* __restr
 
 extern "C" int air_conv_block_n(int N);
 extern "C" int air_conv3x3_patch_supported(int C, int N, int H, int W);
+extern "C" int air_conv_patch_cb(int C);
 
 // Fill one host-side job record for the generic implicit-GEMM packing (same arguments as air_conv_pack_weights_ld).
 extern "C" int air_pack_job_gemm(long long* rec, const float* w, long long w_ld, void* dst, int N, int K, int mode,
@@ -61,7 +62,7 @@ extern "C" int air_pack_job_patch(long long* rec, const float* w, void* dst, int
   for (int i = 0; i < air_pack::REC; ++i) rec[i] = 0;
   rec[0] = 1; rec[1] = reinterpret_cast<long long>(w); rec[2] = reinterpret_cast<long long>(dst);
   rec[3] = static_cast<long long>(taps) * C * N;
-  rec[4] = C; rec[5] = N; rec[6] = C <= 64 ? C : 64; rec[7] = taps; rec[8] = mode;
+  rec[4] = C; rec[5] = N; rec[6] = air_conv_patch_cb(C); rec[7] = taps; rec[8] = mode;
   return AIR_OK;
 }
 

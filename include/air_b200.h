@@ -144,6 +144,8 @@ int air_conv_gemm_bf16_affine(const void* a, long long a_ld, int B, int H, int W
  *   w for air_conv3x3_pack_weights: fp32 GEMM layout [Cout][3][3][Cin]; mode 0: (C, N) = (Cin, Cout),
  *   mode 1: (C, N) = (Cout, Cin); dst holds 9*C*N bf16. */
 int air_conv3x3_patch_supported(int C, int N, int H, int W);
+/* channels per block of the packed patch-kernel weight slices for C input channels (16 / 32 / 64) */
+int air_conv_patch_cb(int C);
 int air_conv3x3_pack_weights(const float* w, void* dst, int C, int N, int mode, air_stream_t stream);
 int air_conv3x3_patch_bf16(const void* a, long long a_ld, int B, int H, int W, int C,
                            const void* wpk, int N, void* out, long long out_ld,
