@@ -41,6 +41,7 @@ constexpr int PW_MAX = TW + 8;          // widest patch (dilated 1-D convolution
 constexpr int THREADS = 384;            // 4 role warps + 2 x 4 epilogue warps
 constexpr int MAX_PSTAGES = 4;           // patch ring: 2 stages of a 64-channel block or 4 of a 32-channel block
 constexpr int MAX_TAPS = 9;
+constexpr uint32_t STAGE_TILE = 2048;    // one epilogue warp's output tile: 32 pixels x 32 channels bf16
 
 struct PatchParams {
   int B, GH, GW;                        // images, output pixel grid enumerated by the items
@@ -60,11 +61,16 @@ struct PatchParams {
   int row_bytes, layout;                // CB * 2; UMMA layout type (6 / 4 / 2)
   uint32_t pstage_bytes, bslot_bytes, bslot_stride;
   int pstages;                          // patch ring depth
+  int stage_out;                        // 1: bf16 outputs leave through per-warp shared-memory tiles + TMA stores
   int nb_slots, resident;               // weight ring
   int acc_stages;                       // 1 or 2
   int ntaps; int tap_off[MAX_TAPS]; int tap_slice[MAX_TAPS];     // window offset in patch pixels, weight slice
   uint32_t items;
 };
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const bf16x8& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.u.x), "r"(v.u.y), "r"(v.u.z), "r"(v.u.w) : "memory");
+}
 
 // residual of one 32-column (NC = 32) or 16-column chunk of a pixel: 16-byte loads, issued ahead of use
 template <int NC>
@@ -96,8 +102,61 @@ __device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {
 // keep_vals the array v holds, on return, the STORED (bf16-rounded) values as floats, zeros for an invalid pixel.
 template <int NC>
 __device__ __forceinline__ void epilogue_chunk(const PatchParams& p, uint32_t taddr, long long pixel, int c0, bool valid,
-                                               const bf16x8 (&rv)[4], float (&v)[NC], bool keep_vals) {
+                                               const bf16x8 (&rv)[4], float (&v)[NC], bool keep_vals, uint32_t stage = 0) {
   if (NC == 32) tmem_ld32(taddr + c0, v); else tmem_ld16(taddr + c0, v);
+  if (NC == 32 && stage != 0) {
+    // bf16 output through the warp's shared-memory tile ([32 pixels][32 channels], SWIZZLE_64B): the caller issues one TMA
+    // store per tile.  A direct store is 16 bytes per lane into 32 different 128-byte lines = 32 L1 wavefronts per
+    // instruction, and those wavefronts share the L1 data pipe with the tensor core's operand reads (ncu: LSU 63 % +
+    // tensor 42 % of the pipe on the N = 64 layers); the tile costs 4 conflict-free wavefronts per instruction.
+    if (valid) {
+      if (p.bias != nullptr) {
+        const float4* bp = reinterpret_cast<const float4*>(p.bias + c0);
+#pragma unroll
+        for (int i = 0; i < NC / 4; ++i) {
+          const float4 b4 = __ldg(bp + i);
+          v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+        }
+      }
+      if (p.out2 != nullptr) {
+        bf16x8* o2 = reinterpret_cast<bf16x8*>(static_cast<__nv_bfloat16*>(p.out2) + pixel * p.out2_ld + c0);
+#pragma unroll
+        for (int i = 0; i < NC / 8; ++i) o2[i] = pack8(v + i * 8);
+      }
+      if (p.res != nullptr) {
+#pragma unroll
+        for (int i = 0; i < NC / 8; ++i) {
+          float rf[8];
+          unpack8(rv[i], rf);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[i * 8 + e] += rf[e];
+        }
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int i = 0; i < NC; ++i) v[i] = fmaxf(v[i], 0.f);
+      }
+    }
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) bulk_wait_read_all();          // the previous tile of this warp has left shared memory
+    __syncwarp();
+    const uint32_t row = stage + static_cast<uint32_t>(lane) * 64u, sw = static_cast<uint32_t>((lane >> 1) & 3);
+#pragma unroll
+    for (int i = 0; i < NC / 8; ++i) {
+      const bf16x8 pk = pack8(v + i * 8);
+      st_shared_v4(row + ((static_cast<uint32_t>(i) ^ sw) << 4), pk);
+      if (keep_vals) {
+        if (valid) unpack8(pk, v + i * 8);
+        else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[i * 8 + e] = 0.f;
+        }
+      }
+    }
+    fence_proxy_async();
+    __syncwarp();
+    return;
+  }
   if (valid) {
     if (p.bias != nullptr) {
       const float4* bp = reinterpret_cast<const float4*>(p.bias + c0);
@@ -242,7 +301,8 @@ __device__ __forceinline__ void mma_role(const MmaCtx& c) {
   }
 }
 
-__global__ void __launch_bounds__(THREADS, 1) conv_patch_kernel(const __grid_constant__ CUtensorMap tmap, const PatchParams p) {
+__global__ void __launch_bounds__(THREADS, 1) conv_patch_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmout,
+                                                                const PatchParams p) {
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;      // swizzle patterns are anchored at 1024 B
@@ -250,7 +310,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_patch_kernel(const __grid_con
   const uint32_t PSTAGES = static_cast<uint32_t>(p.pstages);
   const uint32_t sB = sbase + PSTAGES * p.pstage_bytes;
   uint8_t* gen = smem_raw + (sbase - smem_u32(smem_raw));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(gen + PSTAGES * p.pstage_bytes + static_cast<size_t>(p.nb_slots) * p.bslot_stride);
+  const uint32_t sS = sB + static_cast<uint32_t>(p.nb_slots) * p.bslot_stride;       // [8 epilogue warps][2 KB] output tiles
+  const uint32_t stage_total = p.stage_out ? 8u * STAGE_TILE : 0u;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gen + PSTAGES * p.pstage_bytes + static_cast<size_t>(p.nb_slots) * p.bslot_stride + stage_total);
   uint64_t* full_p = bars;                          // [PSTAGES] expect_tx (TMA)
   uint64_t* empty_p = bars + PSTAGES;               // [PSTAGES] tcgen05.commit
   uint64_t* full_b = bars + 2 * PSTAGES;            // [nb_slots] expect_tx
@@ -269,6 +331,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_patch_kernel(const __grid_con
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 256); }
     fence_barrier_init();
     tma_prefetch_desc(&tmap);
+    if (p.stage_out) tma_prefetch_desc(&tmout);
   }
   if (warp == 2) tmem_alloc(tmem_slot, ncols);
   fence_before_sync();
@@ -341,6 +404,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_patch_kernel(const __grid_con
     // ===================== epilogue =====================
     const int q = warp & 3, set = (warp - 4) >> 2;      // TMEM lane quarter; parity of the 32-channel blocks this warp drains
     const int m = q * 32 + lane;
+    const uint32_t my_tile = p.stage_out ? sS + static_cast<uint32_t>(warp - 4) * STAGE_TILE : 0u;
     // fused BatchNorm statistics: lane l accumulates channel (32 cb + l) of its warp's pixels in registers, in a fixed
     // order (bit-reproducible run to run); combined per CTA in shared memory and across CTAs with fp64 atomics
     float acc_s[4], acc_q[4];
@@ -381,8 +445,12 @@ __global__ void __launch_bounds__(THREADS, 1) conv_patch_kernel(const __grid_con
       for (int cb = set; cb < cpr; cb += 2) {
         const int c0 = cb << 5;
         float v0[32], v1[32];
-        epilogue_chunk<32>(p, tacc, pix0, c0, val0, ra, v0, st);
-        if (rows > 1) epilogue_chunk<32>(p, tacc + p.N, pix1, c0, val1, rb, v1, st);
+        epilogue_chunk<32>(p, tacc, pix0, c0, val0, ra, v0, st, my_tile);
+        if (my_tile && lane == 0) { tma_store_4d(&tmout, my_tile, c0, wt * TW + q * 32, hp * R, b); bulk_commit_group(); }
+        if (rows > 1) {
+          epilogue_chunk<32>(p, tacc + p.N, pix1, c0, val1, rb, v1, st, my_tile);
+          if (my_tile && lane == 0) { tma_store_4d(&tmout, my_tile, c0, wt * TW + q * 32, hp * R + 1, b); bulk_commit_group(); }
+        }
         if (cb + 2 < cpr) { load_res<32>(p, pix0, c0 + 64, val0, ra); if (rows > 1) load_res<32>(p, pix1, c0 + 64, val1, rb); }
         if (st) {                                   // warp-uniform: every lane takes part in the shuffles
           if (rows > 1) {
@@ -408,6 +476,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_patch_kernel(const __grid_con
       fence_before_sync();
       mbar_arrive(&tempty[acc]);
     }
+    if (my_tile && lane == 0) bulk_wait_all();          // every output tile of this warp has been written
     if (s_stats != nullptr) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -571,16 +640,40 @@ extern "C" int air_conv_patch_taps_ex2_bf16(const void* a, long long a_ld, int B
   p.bslot_stride = (p.bslot_bytes + 1023u) / 1024u * 1024u;
   p.pstages = p.pstage_bytes <= 36u * 1024u ? MAX_PSTAGES : 2;
   const int PSTAGES = p.pstages;
-  const int budget = 225 * 1024 - PSTAGES * static_cast<int>(p.pstage_bytes) - 2048;
-  int slots = budget / static_cast<int>(p.bslot_stride);
   const int nslices = p.NCB * ntaps;
-  if (slots >= nslices) { slots = nslices; p.resident = 1; } else { p.resident = 0; if (slots > 12) slots = 12; }
+  const int fixed = 3 * 1024 + (stats ? 4 * 2 * N * static_cast<int>(sizeof(float)) : 0);     // alignment, barriers, statistics
+  auto plan = [&](int staging, int& slots, int& resident) {
+    const int budget = 227 * 1024 - PSTAGES * static_cast<int>(p.pstage_bytes) - fixed - staging;
+    slots = budget / static_cast<int>(p.bslot_stride);
+    if (slots >= nslices) { slots = nslices; resident = 1; } else { resident = 0; if (slots > 12) slots = 12; }
+  };
+  int slots, resident, slots_s, resident_s;
+  plan(0, slots, resident);
+  // bf16 outputs leave through shared-memory tiles + TMA stores when the 16 KB fit without giving up resident weights
+  static const int stage_env = [] { const char* e = getenv("AIR_PATCH_STAGE_OUT"); return (e && e[0] == '0') ? 0 : 1; }();
+  p.stage_out = 0;
+  if (stage_env && !p.f32 && N % 32 == 0) {
+    plan(8 * static_cast<int>(STAGE_TILE), slots_s, resident_s);
+    if (resident_s == resident && (slots_s == slots || slots_s >= 3)) { p.stage_out = 1; slots = slots_s; }
+  }
   if (slots < 2 && nslices > 1) return AIR_ERR_UNSUPPORTED;
-  p.nb_slots = slots;
+  p.nb_slots = slots; p.resident = resident;
   const size_t smem = 1024 + static_cast<size_t>(PSTAGES) * p.pstage_bytes + static_cast<size_t>(slots) * p.bslot_stride +
+                      (p.stage_out ? 8 * STAGE_TILE : 0) +
                       (2 * PSTAGES + 2 * slots + 4) * 8 + 32 + (stats ? 4 * 2 * static_cast<size_t>(N) * sizeof(float) : 0);
-  CUtensorMap tm;
-  const int tr = air_tmap::make_act_tmap(&tm, a, a_ld, B, Hin, Win, C, p.CB, p.pw, PR, p.row_bytes);
+  CUtensorMap tm, tmo;
+  int tr = air_tmap::make_act_tmap(&tm, a, a_ld, B, Hin, Win, C, p.CB, p.pw, PR, p.row_bytes);
+  if (tr == 0 && p.stage_out) {
+    // output view of the item grid: grid point (g, g') is pixel (g * osh + oph, g' * osw + opw); grid points whose pixel
+    // lies outside the tensor are outside the view, so the TMA store clips them
+    const int GWv = std::min(GW, (OW - opw + osw - 1) / osw), GHv = std::min(GH, (OH - oph + osh - 1) / osh);
+    if (GWv < 1 || GHv < 1) return AIR_ERR_ARG;
+    const __nv_bfloat16* ob = reinterpret_cast<const __nv_bfloat16*>(out) + (static_cast<long long>(oph) * OW + opw) * out_ld;
+    tr = air_tmap::make_act_tmap_strided(&tmo, ob, static_cast<long long>(osw) * out_ld, static_cast<long long>(osh) * OW * out_ld,
+                                         static_cast<long long>(OH) * OW * out_ld, B, GHv, GWv, N, 32, 32, 1, 64);
+  } else if (tr == 0) {
+    tmo = tm;
+  }
   if (tr != 0) return tr < 0 ? AIR_ERR_DRIVER : 10000 + tr;
   static bool attr_done = false;
   if (!attr_done) {
@@ -590,7 +683,7 @@ extern "C" int air_conv_patch_taps_ex2_bf16(const void* a, long long a_ld, int B
   }
   if (num_sms <= 0) num_sms = 148;
   const int grid = static_cast<int>(std::min<long long>(items, num_sms));
-  conv_patch_kernel<<<grid, THREADS, smem, stream>>>(tm, p);
+  conv_patch_kernel<<<grid, THREADS, smem, stream>>>(tm, tmo, p);
   return air_launch_status();
 }
 
