@@ -25,7 +25,7 @@
 namespace air_wpatch {
 using namespace tc05;
 
-constexpr int TW = 128, PW = TW + 2, R = 2, PR = R + 2, PPIX = PR * PW;
+constexpr int TW = 128, PW = TW + 2, R = 2, PR = R + 2, PPIX = PR * PW;      // R: default rows per item (p.R: 2 or 3)
 constexpr int NACC = 5;                             // wide 3x3: tap pairs (0,1) (2,3) (4,5) (6,7) (8,-); narrow 3x3: 3 tap rows
 constexpr int THREADS = 256;
 constexpr int STAGES = 2;
@@ -46,10 +46,67 @@ struct WParams {
   int tw;                                           // pixels per row segment of an item (K of the MMAs): 128, or 96 when
                                                     // that covers W with less padding (W = 94 / 188: 73 % -> 98 % useful)
   int pw;                                           // patch width in pixels (tw + 2, or tw + 8 for dilated 1-D taps)
+  int R;                                            // rows per item: 2, or 3 when H = 3 and the wider stage fits (tw = 96)
   uint32_t x_bytes, stage_bytes;
   int nacc; int acc_off[NACC]; int acc_lbo[NACC];   // per accumulator: window offset / group distance, in patch pixels
   int acc_tap[NACC][8];                             // tap of each M row group (-1: not a real tap)
 };
+
+struct WCtx {
+  const WParams& p;
+  uint32_t sbase, tmem_base;
+  uint64_t *full, *empty, *tfull;
+  uint32_t my_items;
+};
+
+// NA = accumulators (0: run-time p.nacc), KS = K = 16 steps per row (0: run-time p.tw / 16)
+template <int NA, int KS, bool NARROW>
+__device__ __forceinline__ void wgrad_mma_role(const WCtx& c) {
+  const WParams& p = c.p;
+  const bool leader = elect_one();
+  const int nacc = NA > 0 ? NA : p.nacc, ksteps = KS > 0 ? KS : p.tw / 16, rows = p.R;
+  const uint32_t idesc = instr_desc_bf16(128, ACC_COLS, 1, 1);
+  // descriptor high words: SBO = next 8 pixels, version 1, swizzle mode (A: 128 B or 32 B rows; B: always 128 B rows)
+  const uint32_t b_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+  const uint32_t a_hi = NARROW ? ((256u >> 4) | (1u << 14) | (6u << 29)) : b_hi;
+  constexpr uint32_t upp = NARROW ? 2u : 8u;              // 16-byte units per patch pixel
+  // per-accumulator A descriptor without the (stage, row, K step) offset: window offset in the low word, LBO above it
+  uint64_t abase[NACC];
+#pragma unroll
+  for (int a = 0; a < NACC; ++a)
+    abase[a] = (static_cast<uint64_t>(a_hi) << 32) |
+               ((static_cast<uint32_t>(p.acc_off[a]) * upp) | ((static_cast<uint32_t>(p.acc_lbo[a]) * upp) << 16));
+  const uint64_t bbase = (static_cast<uint64_t>(b_hi) << 32) | (1u << 16);
+  const uint32_t stage16 = p.stage_bytes >> 4, xb16 = p.x_bytes >> 4;
+  const uint32_t xrow16 = static_cast<uint32_t>(p.pw) * upp, drow16 = static_cast<uint32_t>(p.tw) * 8u;
+  const uint32_t s16 = (c.sbase >> 4) & 0x3FFF;
+  uint32_t stage = 0, phase = 0;
+  for (uint32_t k = 0; k < c.my_items; ++k) {
+    mbar_wait(&c.full[stage], phase);
+    fence_after_sync();
+    const uint32_t x16 = s16 + stage * stage16;
+    const uint32_t d16 = x16 + xb16;
+    for (int r = 0; r < rows; ++r) {
+      const uint64_t bd0 = bbase + (d16 + static_cast<uint32_t>(r) * drow16);
+      const uint32_t xr = x16 + static_cast<uint32_t>(r) * xrow16;
+      if (leader) {
+#pragma unroll
+        for (int ks = 0; ks < (KS > 0 ? KS : 8); ++ks) {
+          if (KS == 0 && ks >= ksteps) break;
+#pragma unroll
+          for (int a = 0; a < NACC; ++a) {
+            if (a < nacc)
+              mma_bf16(c.tmem_base + a * ACC_COLS, abase[a] + (xr + static_cast<uint32_t>(ks) * 16u * upp),
+                       bd0 + static_cast<uint32_t>(ks) * 128u, idesc, (k | static_cast<uint32_t>(r) | static_cast<uint32_t>(ks)) != 0);
+          }
+        }
+      }
+    }
+    if (leader) mma_commit(&c.empty[stage]);
+    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+  }
+  if (leader) mma_commit(c.tfull);
+}
 
 __global__ void __launch_bounds__(THREADS, 1) conv3x3_wgrad_patch_kernel(const __grid_constant__ CUtensorMap tmx,
                                                                          const __grid_constant__ CUtensorMap tmdy,
@@ -90,54 +147,27 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_wgrad_patch_kernel(const _
       for (uint32_t k = 0; k < my_items; ++k) {
         const uint32_t item = part + k * p.parts;
         const uint32_t wt = item % WT, r1 = item / WT;
-        const int w0 = static_cast<int>(wt) * p.tw, h0 = static_cast<int>(r1 % HP) * R, b = static_cast<int>(r1 / HP);
+        const int w0 = static_cast<int>(wt) * p.tw, h0 = static_cast<int>(r1 % HP) * p.R, b = static_cast<int>(r1 / HP);
         mbar_wait(&empty[stage], phase ^ 1);
         const uint32_t dst = sbase + stage * p.stage_bytes;
-        mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>(PR * p.pw) * (p.narrow ? 32u : 128u) + static_cast<uint32_t>(R * p.tw) * 128u);
+        mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>((p.R + 2) * p.pw) * (p.narrow ? 32u : 128u) + static_cast<uint32_t>(p.R * p.tw) * 128u);
         tma_load_4d(dst, &tmx, p.narrow ? 0 : cb * 64, w0 + p.org_w, h0 + p.org_h, b, &full[stage]);
         tma_load_4d(dst + p.x_bytes, &tmdy, nb * 64, w0, h0, b, &full[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 2) {
-    const bool leader = elect_one();
-    const uint32_t idesc = instr_desc_bf16(128, ACC_COLS, 1, 1);
-    // descriptor high words: SBO = next 8 pixels, version 1, swizzle mode (A: 128 B or 32 B rows; B: always 128 B rows)
-    const uint32_t b_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
-    const uint32_t a_hi = p.narrow ? ((256u >> 4) | (1u << 14) | (6u << 29)) : b_hi;
-    const uint32_t upp = p.narrow ? 2u : 8u;              // 16-byte units per patch pixel
-    // per-accumulator A descriptor without the (stage, row, K step) offset: window offset in the low word, LBO above it
-    uint64_t abase[NACC];
-#pragma unroll
-    for (int a = 0; a < NACC; ++a)
-      abase[a] = (static_cast<uint64_t>(a_hi) << 32) |
-                 ((static_cast<uint32_t>(p.acc_off[a]) * upp) | ((static_cast<uint32_t>(p.acc_lbo[a]) * upp) << 16));
-    const uint64_t bbase = (static_cast<uint64_t>(b_hi) << 32) | (1u << 16);
-    uint32_t stage = 0, phase = 0;
-    for (uint32_t k = 0; k < my_items; ++k) {
-      mbar_wait(&full[stage], phase);
-      fence_after_sync();
-      const uint32_t x16 = ((sbase + stage * p.stage_bytes) >> 4) & 0x3FFF;
-      const uint32_t d16 = x16 + (p.x_bytes >> 4);
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-#pragma unroll 2
-        for (int ks = 0; ks < p.tw / 16; ++ks) {
-          const uint64_t bd = bbase + (d16 + static_cast<uint32_t>(r * p.tw + ks * 16) * 8);
-          const uint32_t xrow = x16 + static_cast<uint32_t>(r * p.pw + ks * 16) * upp;
-#pragma unroll
-          for (int a = 0; a < NACC; ++a) {
-            if (a < p.nacc) {
-              const uint64_t ad = abase[a] + xrow;             // never carries out of the 14-bit address field
-              if (leader) mma_bf16(tmem_base + a * ACC_COLS, ad, bd, idesc, (k | static_cast<uint32_t>(r) | static_cast<uint32_t>(ks)) != 0);
-            }
-          }
-        }
-      }
-      if (leader) mma_commit(&empty[stage]);
-      if (++stage == STAGES) { stage = 0; phase ^= 1; }
-    }
-    if (leader) mma_commit(tfull);
+    // MMA issuer, specialised on (accumulators, K steps per row, operand geometry): straight-line descriptors
+    const WCtx c{p, sbase, tmem_base, full, empty, tfull, my_items};
+    const int ks = p.tw / 16;
+    if (!p.narrow && p.nacc == 5 && ks == 8) wgrad_mma_role<5, 8, false>(c);
+    else if (!p.narrow && p.nacc == 5 && ks == 6) wgrad_mma_role<5, 6, false>(c);
+    else if (!p.narrow && p.nacc == 2 && ks == 8) wgrad_mma_role<2, 8, false>(c);
+    else if (!p.narrow && p.nacc == 2 && ks == 6) wgrad_mma_role<2, 6, false>(c);
+    else if (!p.narrow && p.nacc == 1 && ks == 8) wgrad_mma_role<1, 8, false>(c);
+    else if (!p.narrow && p.nacc == 1 && ks == 6) wgrad_mma_role<1, 6, false>(c);
+    else if (p.narrow) wgrad_mma_role<0, 0, true>(c);
+    else wgrad_mma_role<0, 0, false>(c);
     __syncwarp();
   } else if (warp >= 4) {
     // ---------------- final reduction: TMEM -> fp32 red.global.add into dW[co][tap][ci] ----------------
@@ -205,9 +235,14 @@ static int launch_wgrad_patch(const void* x, long long x_ld, int B, int H, int W
   }
   p.tw = ((W + 95) / 96) * 96 < ((W + TW - 1) / TW) * TW ? 96 : TW;
   p.pw = p.tw + (max_dc <= 2 ? 2 : 8);
-  p.NCB = p.narrow ? 1 : C / 64; p.NNB = N / 64; p.WT = (W + p.tw - 1) / p.tw; p.HP = (H + R - 1) / R;
-  p.x_bytes = (static_cast<uint32_t>(PR * p.pw) * (p.narrow ? 32u : 128u) + 1023u) / 1024u * 1024u;
-  p.stage_bytes = p.x_bytes + DY_BYTES;             // dy slot sized for the widest tile
+  // three rows per item when that wastes fewer rows (H = 3: 75 % -> 100 % useful) and two such stages fit
+  p.R = R;
+  if ((H + 2) / 3 * 3 < (H + 1) / 2 * 2 && p.tw == 96 && !p.narrow) p.R = 3;
+  for (int t = 0; t < ntaps; ++t) if (tap_dr[t] > 2) return AIR_ERR_ARG;
+  p.NCB = p.narrow ? 1 : C / 64; p.NNB = N / 64; p.WT = (W + p.tw - 1) / p.tw; p.HP = (H + p.R - 1) / p.R;
+  p.x_bytes = (static_cast<uint32_t>((p.R + 2) * p.pw) * (p.narrow ? 32u : 128u) + 1023u) / 1024u * 1024u;
+  p.stage_bytes = p.x_bytes + (p.R == R ? DY_BYTES : (static_cast<uint32_t>(p.R * p.tw) * 128u + 1023u) / 1024u * 1024u);
+  if (1024 + STAGES * static_cast<size_t>(p.stage_bytes) + 64 > 227 * 1024) return AIR_ERR_UNSUPPORTED;
   for (int a = 0; a < NACC; ++a) { p.acc_off[a] = 0; p.acc_lbo[a] = 0; for (int g = 0; g < 8; ++g) p.acc_tap[a][g] = -1; }
   int off[9];
   for (int t = 0; t < ntaps; ++t) off[t] = tap_dr[t] * p.pw + tap_dc[t];
@@ -254,10 +289,10 @@ static int launch_wgrad_patch(const void* x, long long x_ld, int B, int H, int W
   CUtensorMap tmx, tmdy;
   int tr;
   if (xv) tr = air_tmap::make_act_tmap_strided(&tmx, xv->base, xv->sw, xv->sh, xv->sb, B, xv->H, xv->W, C, p.narrow ? 16 : 64,
-                                               p.pw, PR, p.narrow ? 32 : 128);
-  else tr = p.narrow ? air_tmap::make_act_tmap(&tmx, x, x_ld, B, H, W, C, 16, p.pw, PR, 32)
-                     : air_tmap::make_act_tmap(&tmx, x, x_ld, B, H, W, C, 64, p.pw, PR, 128);
-  if (tr == 0) tr = air_tmap::make_act_tmap(&tmdy, dy, dy_ld, B, H, W, N, 64, p.tw, R, 128);
+                                               p.pw, p.R + 2, p.narrow ? 32 : 128);
+  else tr = p.narrow ? air_tmap::make_act_tmap(&tmx, x, x_ld, B, H, W, C, 16, p.pw, p.R + 2, 32)
+                     : air_tmap::make_act_tmap(&tmx, x, x_ld, B, H, W, C, 64, p.pw, p.R + 2, 128);
+  if (tr == 0) tr = air_tmap::make_act_tmap(&tmdy, dy, dy_ld, B, H, W, N, 64, p.tw, p.R, 128);
   if (tr != 0) return tr < 0 ? AIR_ERR_DRIVER : 10000 + tr;
   const size_t smem = 1024 + static_cast<size_t>(STAGES) * p.stage_bytes + (2 * STAGES + 1) * 8 + 16;
   static bool attr_done = false;

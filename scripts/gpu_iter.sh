@@ -19,3 +19,4 @@ for f in ("a", "b"):
     except Exception as e:
         print(f, "ERR", e)
 PY
+AIR_OVERLAP_WGRAD=0 timeout 300 python scripts/prof_step.py 256 ecapa > gpurun_out/it_percall_ecapa.txt 2>&1
