@@ -32,6 +32,7 @@ constexpr int BLOCK_K = 64;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;      // 16 KB
 constexpr int ROWS_PER_THREAD = 8;                        // thread t: chunk t & 7 of rows (t >> 3) + 16 i
 constexpr int NUM_A_THREADS = 128;
+constexpr uint32_t STAGE_TILE = 2048;                     // one epilogue warp's output tile: 32 rows x 32 channels bf16
 constexpr int THREADS = 320;                              // 4 gather warps, TMA warp, MMA warp, 4 epilogue warps
 
 struct ConvParams {
@@ -50,13 +51,77 @@ struct ConvParams {
   const float* post_scale; const float* post_shift;   // optional per-channel affine AFTER the ReLU (eval-mode BatchNorm of conv -> ReLU -> BN)
   int stages; int flags;
   int use_tma;                              // 1x1 / stride 1: the A tile is a plain 2-D box of the activation matrix
+  int stage_out;                            // 1: bf16 outputs leave through per-warp shared-memory tiles + TMA stores
 };
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const bf16x8& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.u.x), "r"(v.u.y), "r"(v.u.z), "r"(v.u.w) : "memory");
+}
+
+// bias / second output / residual / ReLU / affine of 16 accumulator columns of row m (the part of the epilogue before the store)
+__device__ __forceinline__ void epilogue_math16(const ConvParams& p, long long m, int n0, bool f32, float (&v)[16]) {
+  if (p.bias) {                                  // 16 consecutive floats, 16-byte aligned (checked by the launcher)
+    const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + (p.bias_rows > 0 ? (m / p.bias_rows) * p.N : 0));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 b4 = __ldg(bp + i);
+      v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+    }
+  }
+  if (p.out2) {
+    if (f32) {
+      float4* o2 = reinterpret_cast<float4*>(static_cast<float*>(p.out2) + m * p.out2_ld + n0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o2[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+      bf16x8* o2 = reinterpret_cast<bf16x8*>(static_cast<__nv_bfloat16*>(p.out2) + m * p.out2_ld + n0);
+      o2[0] = pack8(v);
+      o2[1] = pack8(v + 8);
+    }
+  }
+  if (p.res) {
+    if (f32) {
+      const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(p.res) + m * p.res_ld + n0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 r4 = rp[i];
+        v[4 * i] += r4.x; v[4 * i + 1] += r4.y; v[4 * i + 2] += r4.z; v[4 * i + 3] += r4.w;
+      }
+    } else {
+      const bf16x8* rp = reinterpret_cast<const bf16x8*>(static_cast<const __nv_bfloat16*>(p.res) + m * p.res_ld + n0);
+      float rf[16];
+      unpack8(rp[0], rf); unpack8(rp[1], rf + 8);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] += rf[i];
+    }
+  }
+  if (p.relu) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
+  if (p.post_scale) {
+    const float4* sp = reinterpret_cast<const float4*>(p.post_scale + n0);
+    const float4* tp = reinterpret_cast<const float4*>(p.post_shift + n0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 s4 = __ldg(sp + i), t4 = __ldg(tp + i);
+      v[4 * i] = fmaf(v[4 * i], s4.x, t4.x); v[4 * i + 1] = fmaf(v[4 * i + 1], s4.y, t4.y);
+      v[4 * i + 2] = fmaf(v[4 * i + 2], s4.z, t4.z); v[4 * i + 3] = fmaf(v[4 * i + 3], s4.w, t4.w);
+    }
+  }
+}
 
 // Epilogue of one warp: TMEM lane quadrant q, columns [c_begin, c_end) of every tile -> bias / residual / ReLU / affine ->
 // bf16 -> HBM.  In TMA mode the four (otherwise idle) gather warps take the upper half of the columns.
+// stage_tile != 0: bf16 outputs leave 32 columns at a time through this warp's shared-memory tile ([32 rows][32 channels],
+// SWIZZLE_64B) and one TMA store -- a direct store is 16 bytes per lane into 32 different 128-byte lines, 32 wavefronts of the
+// L1 data pipe the tensor core reads its operands through (the K <= 512 layers were bound by it, not by the tensor pipe).
 __device__ __forceinline__ void epilogue_role(const ConvParams& p, uint32_t tmem_base, uint64_t* tfull, uint64_t* tempty,
-                                              int q, int lane, int c_begin, int c_end, int total_tiles) {
+                                              int q, int lane, int c_begin, int c_end, int total_tiles,
+                                              uint32_t stage_tile, const CUtensorMap* tmo) {
   const int row = q * 32 + lane;
+  const bool f32 = (p.flags & AIR_CONV_F32_OUT) != 0;       // fp32 parity mode: float storage, no rounding point
+  const uint32_t srow = stage_tile + static_cast<uint32_t>(lane) * 64u, ssw = static_cast<uint32_t>((lane >> 1) & 3);
   int it = 0;
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
     const int m_tile = tile / p.n_tiles, n_tile = tile % p.n_tiles;
@@ -66,61 +131,31 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& p, uint32_t tmem
     fence_after_sync();
     const long long m = static_cast<long long>(m_tile) * BLOCK_M + row;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * p.block_n;
-    for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+    int c0 = c_begin;
+    if (stage_tile != 0) {
+      for (; c0 + 32 <= c_end; c0 += 32) {
+        float va[16], vb[16];
+        tmem_ld16(taddr + c0, va);
+        tmem_ld16(taddr + c0 + 16, vb);
+        const int n0 = n_tile * p.block_n + c0;
+        if (m < p.M) { epilogue_math16(p, m, n0, false, va); epilogue_math16(p, m, n0 + 16, false, vb); }
+        if (lane == 0) bulk_wait_read_all();        // the previous tile of this warp has left shared memory
+        __syncwarp();
+        st_shared_v4(srow + ((0u ^ ssw) << 4), pack8(va));
+        st_shared_v4(srow + ((1u ^ ssw) << 4), pack8(va + 8));
+        st_shared_v4(srow + ((2u ^ ssw) << 4), pack8(vb));
+        st_shared_v4(srow + ((3u ^ ssw) << 4), pack8(vb + 8));
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) { tma_store_2d(tmo, stage_tile, n0, m_tile * BLOCK_M + q * 32); bulk_commit_group(); }
+      }
+    }
+    for (; c0 < c_end; c0 += 16) {
       float v[16];
       tmem_ld16(taddr + c0, v);
       if (m < p.M) {
         const int n0 = n_tile * p.block_n + c0;
-        if (p.bias) {                                  // 16 consecutive floats, 16-byte aligned (checked by the launcher)
-          const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + (p.bias_rows > 0 ? (m / p.bias_rows) * p.N : 0));
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 b4 = __ldg(bp + i);
-            v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
-          }
-        }
-        const bool f32 = (p.flags & AIR_CONV_F32_OUT) != 0;       // fp32 parity mode: float storage, no rounding point
-        if (p.out2) {
-          if (f32) {
-            float4* o2 = reinterpret_cast<float4*>(static_cast<float*>(p.out2) + m * p.out2_ld + n0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) o2[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          } else {
-            bf16x8* o2 = reinterpret_cast<bf16x8*>(static_cast<__nv_bfloat16*>(p.out2) + m * p.out2_ld + n0);
-            o2[0] = pack8(v);
-            o2[1] = pack8(v + 8);
-          }
-        }
-        if (p.res) {
-          if (f32) {
-            const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(p.res) + m * p.res_ld + n0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 r4 = rp[i];
-              v[4 * i] += r4.x; v[4 * i + 1] += r4.y; v[4 * i + 2] += r4.z; v[4 * i + 3] += r4.w;
-            }
-          } else {
-            const bf16x8* rp = reinterpret_cast<const bf16x8*>(static_cast<const __nv_bfloat16*>(p.res) + m * p.res_ld + n0);
-            float rf[16];
-            unpack8(rp[0], rf); unpack8(rp[1], rf + 8);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += rf[i];
-          }
-        }
-        if (p.relu) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-        }
-        if (p.post_scale) {
-          const float4* sp = reinterpret_cast<const float4*>(p.post_scale + n0);
-          const float4* tp = reinterpret_cast<const float4*>(p.post_shift + n0);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 s4 = __ldg(sp + i), t4 = __ldg(tp + i);
-            v[4 * i] = fmaf(v[4 * i], s4.x, t4.x); v[4 * i + 1] = fmaf(v[4 * i + 1], s4.y, t4.y);
-            v[4 * i + 2] = fmaf(v[4 * i + 2], s4.z, t4.z); v[4 * i + 3] = fmaf(v[4 * i + 3], s4.w, t4.w);
-          }
-        }
+        epilogue_math16(p, m, n0, f32, v);
         if (f32) {
           float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + m * p.out_ld + n0);
 #pragma unroll
@@ -135,9 +170,11 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& p, uint32_t tmem
     fence_before_sync();
     mbar_arrive(&tempty[acc]);
   }
+  if (stage_tile != 0 && lane == 0) bulk_wait_all();
 }
 
-__global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const ConvParams p) {
+__global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_o,
+                                                               const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);      // swizzle patterns are anchored at 1024 B
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -145,7 +182,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
   const uint32_t b_stage_bytes = static_cast<uint32_t>(p.block_n) * BLOCK_K * 2;
   uint8_t* sA = smem;
   uint8_t* sB = smem + S * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + S * b_stage_bytes);
+  uint8_t* sS = sB + S * b_stage_bytes;      // [8 epilogue warps][2 KB] output tiles (stage_out)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sS + (p.stage_out ? 8 * STAGE_TILE : 0));
   uint64_t* full = bars;               // [S]  128 gather arrivals + 1 expect_tx arrival
   uint64_t* empty = bars + S;          // [S]  tcgen05.commit
   uint64_t* tfull = bars + 2 * S;      // [2]  accumulator ready
@@ -178,7 +216,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
       // 1x1 / stride-1 layer: no gather (warp 4 issues one TMA box per K block); these four warps own TMEM lane
       // quadrants 0-3 too, so they drain the upper half of the accumulator columns
       const int c_begin = ((p.block_n / 16 + 1) / 2) * 16;
-      epilogue_role(p, tmem_base, tfull, tempty, warp & 3, lane, c_begin, p.block_n, total_tiles);
+      epilogue_role(p, tmem_base, tfull, tempty, warp & 3, lane, c_begin, p.block_n, total_tiles,
+                    p.stage_out ? smem_u32(sS) + static_cast<uint32_t>(4 + (warp & 3)) * STAGE_TILE : 0u, &tma_o);
     } else
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.n_tiles;
@@ -278,7 +317,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
   } else {
     // ===================== epilogue: TMEM -> registers -> HBM =====================
     const int c_end = p.use_tma ? ((p.block_n / 16 + 1) / 2) * 16 : p.block_n;
-    epilogue_role(p, tmem_base, tfull, tempty, warp & 3, lane, 0, c_end, total_tiles);
+    epilogue_role(p, tmem_base, tfull, tempty, warp & 3, lane, 0, c_end, total_tiles,
+                  p.stage_out ? smem_u32(sS) + static_cast<uint32_t>(warp & 3) * STAGE_TILE : 0u, &tma_o);
   }
 
   fence_before_sync();
@@ -411,10 +451,12 @@ extern "C" int air_conv_gemm_bf16_affine(const void* a, long long a_ld, int B, i
   if (stages > 8) stages = 8;
   if (stages < 2) return AIR_ERR_UNSUPPORTED;
   p.stages = stages;
-  const size_t smem = 1024 + static_cast<size_t>(stages) * stage_bytes + (2 * stages + 4) * 8 + 16;
+  static const int stage_env = [] { const char* e = getenv("AIR_GEMM_STAGE_OUT"); return (e && e[0] == '0') ? 0 : 1; }();
+  p.stage_out = (stage_env && !(flags & AIR_CONV_F32_OUT) && bn % 32 == 0 && p.M < 0x7fffffffLL) ? 1 : 0;
+  const size_t smem = 1024 + static_cast<size_t>(stages) * stage_bytes + (p.stage_out ? 8 * STAGE_TILE : 0) + (2 * stages + 4) * 8 + 16;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_done = true;
   }
@@ -426,6 +468,8 @@ extern "C" int air_conv_gemm_bf16_affine(const void* a, long long a_ld, int B, i
   if (kh == 1 && kw == 1 && sh == 1 && sw == 1 && ph == 0 && pw == 0 && Ho == H && Wo == W && p.M < 0x7fffffffLL) {
     if (air_tmap::make_mat_tmap(&tm, a, a_ld, p.M, C, BLOCK_M) == 0) p.use_tma = 1;     // otherwise: the gather path
   }
-  conv_gemm_kernel<<<grid, THREADS, smem, stream>>>(tm, p);
+  CUtensorMap tmo = tm;
+  if (p.stage_out && air_tmap::make_out_tmap(&tmo, out, out_ld, p.M, N) != 0) return AIR_ERR_DRIVER;
+  conv_gemm_kernel<<<grid, THREADS, smem, stream>>>(tm, tmo, p);
   return air_launch_status();
 }

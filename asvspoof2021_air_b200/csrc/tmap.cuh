@@ -79,4 +79,19 @@ static inline int make_mat_tmap(CUtensorMap* tm, const void* base, long long ld,
   return static_cast<int>(r);
 }
 
+// bf16 row-major matrix [rows][ld >= cols] as the 2-D tensor (cols, rows) with a (32 columns, 32 rows) SWIZZLE_64B box: the
+// shared-memory tile one epilogue warp stores (rows / columns outside the matrix are clipped by the TMA unit).
+static inline int make_out_tmap(CUtensorMap* tm, const void* base, long long ld, long long rows, int cols) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return -1;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return static_cast<int>(r);
+}
+
 }  // namespace air_tmap

@@ -20,3 +20,11 @@ for f in ("a", "b"):
         print(f, "ERR", e)
 PY
 AIR_OVERLAP_WGRAD=0 timeout 300 python scripts/prof_step.py 256 ecapa > gpurun_out/it_percall_ecapa.txt 2>&1
+for w in ecapa_train ecapa_score; do
+  timeout 300 python bench.py --workload $w --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/it_bench_$w.json 2> gpurun_out/it_bench_$w.err
+  python -c "
+import json,sys
+d=json.loads(open('gpurun_out/it_bench_$w.json').read().strip().splitlines()[-1])
+print('$w', '%.3f ms' % d['ms_per_step'], '%.0f utt/s' % d['value'], 'roofline %.3f' % d['roofline']['frac'], {k: v['ms_per_step'] for k, v in d.get('kernels', {}).items() if v['ms_per_step'] > 0.3})
+"
+done
