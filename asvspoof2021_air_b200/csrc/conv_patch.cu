@@ -36,7 +36,7 @@ using namespace tc05;
 constexpr int TW = 128;                 // output columns per row segment (UMMA M)
 constexpr int PW = TW + 2;              // patch width
 constexpr int R = 2;                    // output rows per work item
-constexpr int PR = R + 2;               // patch rows
+constexpr int PR = R + 2;               // patch rows of a 3-row kernel (p.pr = R + the largest row offset of the taps)
 constexpr int PW_MAX = TW + 8;          // widest patch (dilated 1-D convolutions)
 constexpr int THREADS = 384;            // 4 role warps + 2 x 4 epilogue warps
 constexpr int MAX_PSTAGES = 4;           // patch ring: 2 stages of a 64-channel block or 4 of a 32-channel block
@@ -54,6 +54,7 @@ struct PatchParams {
   const void* res; long long res_ld; int relu;
   const float* bias;                    // optional per-channel bias (ECAPA convs, ecapa_tdnn.py:39,50)
   void* out2; long long out2_ld;        // optional second output: accumulator (+bias) WITHOUT the residual
+  const float* post_scale; const float* post_shift;   // optional per-channel affine applied after the ReLU, BEFORE out2 / res
   int f32;                              // fp32 parity mode: outputs / residual stored as float (operands stay bf16 splits)
   double* stats;                        // optional: stats[n] += sum of the stored outputs, stats[N + n] += sum of squares
                                         // (the batch statistics of the BatchNorm that consumes `out`, bn_stats fused)
@@ -61,6 +62,7 @@ struct PatchParams {
   int row_bytes, layout;                // CB * 2; UMMA layout type (6 / 4 / 2)
   uint32_t pstage_bytes, bslot_bytes, bslot_stride;
   int pstages;                          // patch ring depth
+  int pr;                               // patch rows actually loaded: R + max tap row offset (2 for 1-D / 1x1 layers)
   int stage_out;                        // 1: bf16 outputs leave through per-warp shared-memory tiles + TMA stores
   int nb_slots, resident;               // weight ring
   int acc_stages;                       // 1 or 2
@@ -98,17 +100,72 @@ __device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {
   return v[0];
 }
 
+// bf16 epilogue arithmetic of NC accumulator columns of one (valid) pixel, in the order the layer needs:
+//   default:       v += bias;  out2 <- v;  v += res;  ReLU
+//   affine_first:  v += bias;  ReLU;  v = v * post_scale + post_shift;  out2 <- v;  v = round_bf16(v) + res
+// (affine_first = conv -> ReLU -> eval-mode BatchNorm folded into the epilogue, ecapa_tdnn.py:73-83: out2 is the branch
+// output, out = branch output + next split is the next branch's input.)
+template <int NC>
+__device__ __forceinline__ void epilogue_math(const PatchParams& p, long long pixel, int c0, const bf16x8 (&rv)[4], float (&v)[NC]) {
+  if (p.bias != nullptr) {
+    const float4* bp = reinterpret_cast<const float4*>(p.bias + c0);
+#pragma unroll
+    for (int i = 0; i < NC / 4; ++i) {
+      const float4 b4 = __ldg(bp + i);
+      v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+    }
+  }
+  if (p.post_scale != nullptr) {
+    const float4* sp = reinterpret_cast<const float4*>(p.post_scale + c0);
+    const float4* tp = reinterpret_cast<const float4*>(p.post_shift + c0);
+#pragma unroll
+    for (int i = 0; i < NC / 4; ++i) {
+      const float4 s4 = __ldg(sp + i), t4 = __ldg(tp + i);
+      const float sc[4] = {s4.x, s4.y, s4.z, s4.w}, sh[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float t = v[4 * i + e];
+        if (p.relu) t = fmaxf(t, 0.f);
+        v[4 * i + e] = fmaf(t, sc[e], sh[e]);
+      }
+    }
+  }
+  if (p.out2 != nullptr) {
+    bf16x8* o2 = reinterpret_cast<bf16x8*>(static_cast<__nv_bfloat16*>(p.out2) + pixel * p.out2_ld + c0);
+#pragma unroll
+    for (int i = 0; i < NC / 8; ++i) {
+      const bf16x8 pk = pack8(v + i * 8);
+      o2[i] = pk;
+      if (p.post_scale != nullptr) unpack8(pk, v + i * 8);       // the consumer adds the ROUNDED branch output
+    }
+  }
+  if (p.res != nullptr) {
+#pragma unroll
+    for (int i = 0; i < NC / 8; ++i) {
+      float rf[8];
+      unpack8(rv[i], rf);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[i * 8 + e] += rf[e];
+    }
+  }
+  if (p.relu && p.post_scale == nullptr) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
+}
+
 // One chunk of NC = 32 / 16 accumulator columns of a pixel: (+bias) (-> out2) (+res) (ReLU) -> bf16 -> out.  With
 // keep_vals the array v holds, on return, the STORED (bf16-rounded) values as floats, zeros for an invalid pixel.
+// stage != 0 (NC = 32, bf16): the values go to the warp's shared-memory tile ([32 pixels][32 channels], SWIZZLE_64B) and the
+// caller issues one TMA store per tile.  A direct store is 16 bytes per lane into 32 different 128-byte lines = 32 L1
+// wavefronts per instruction, and those wavefronts share the L1 data pipe with the tensor core's operand reads (ncu: LSU
+// 63 % + tensor 42 % of the pipe on the N = 64 layers); the tile costs 4 conflict-free wavefronts per instruction.
 template <int NC>
 __device__ __forceinline__ void epilogue_chunk(const PatchParams& p, uint32_t taddr, long long pixel, int c0, bool valid,
                                                const bf16x8 (&rv)[4], float (&v)[NC], bool keep_vals, uint32_t stage = 0) {
   if (NC == 32) tmem_ld32(taddr + c0, v); else tmem_ld16(taddr + c0, v);
-  if (NC == 32 && stage != 0) {
-    // bf16 output through the warp's shared-memory tile ([32 pixels][32 channels], SWIZZLE_64B): the caller issues one TMA
-    // store per tile.  A direct store is 16 bytes per lane into 32 different 128-byte lines = 32 L1 wavefronts per
-    // instruction, and those wavefronts share the L1 data pipe with the tensor core's operand reads (ncu: LSU 63 % +
-    // tensor 42 % of the pipe on the N = 64 layers); the tile costs 4 conflict-free wavefronts per instruction.
+  if (p.f32) {
+    // fp32 parity mode: the same epilogue with float storage (no rounding point between the layers)
     if (valid) {
       if (p.bias != nullptr) {
         const float4* bp = reinterpret_cast<const float4*>(p.bias + c0);
@@ -119,24 +176,33 @@ __device__ __forceinline__ void epilogue_chunk(const PatchParams& p, uint32_t ta
         }
       }
       if (p.out2 != nullptr) {
-        bf16x8* o2 = reinterpret_cast<bf16x8*>(static_cast<__nv_bfloat16*>(p.out2) + pixel * p.out2_ld + c0);
+        float4* o2 = reinterpret_cast<float4*>(static_cast<float*>(p.out2) + pixel * p.out2_ld + c0);
 #pragma unroll
-        for (int i = 0; i < NC / 8; ++i) o2[i] = pack8(v + i * 8);
+        for (int i = 0; i < NC / 4; ++i) o2[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
       }
       if (p.res != nullptr) {
+        const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(p.res) + pixel * p.res_ld + c0);
 #pragma unroll
-        for (int i = 0; i < NC / 8; ++i) {
-          float rf[8];
-          unpack8(rv[i], rf);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[i * 8 + e] += rf[e];
+        for (int i = 0; i < NC / 4; ++i) {
+          const float4 r4 = rp[i];
+          v[4 * i] += r4.x; v[4 * i + 1] += r4.y; v[4 * i + 2] += r4.z; v[4 * i + 3] += r4.w;
         }
       }
       if (p.relu) {
 #pragma unroll
         for (int i = 0; i < NC; ++i) v[i] = fmaxf(v[i], 0.f);
       }
+      float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + pixel * p.out_ld + c0);
+#pragma unroll
+      for (int i = 0; i < NC / 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else if (keep_vals) {
+#pragma unroll
+      for (int i = 0; i < NC; ++i) v[i] = 0.f;
     }
+    return;
+  }
+  if (valid) epilogue_math<NC>(p, pixel, c0, rv, v);
+  if (NC == 32 && stage != 0) {
     const int lane = threadIdx.x & 31;
     if (lane == 0) bulk_wait_read_all();          // the previous tile of this warp has left shared memory
     __syncwarp();
@@ -158,56 +224,6 @@ __device__ __forceinline__ void epilogue_chunk(const PatchParams& p, uint32_t ta
     return;
   }
   if (valid) {
-    if (p.bias != nullptr) {
-      const float4* bp = reinterpret_cast<const float4*>(p.bias + c0);
-#pragma unroll
-      for (int i = 0; i < NC / 4; ++i) {
-        const float4 b4 = __ldg(bp + i);
-        v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
-      }
-    }
-    if (p.f32) {
-      // fp32 parity mode: the same epilogue with float storage (no rounding point between the layers)
-      if (p.out2 != nullptr) {
-        float4* o2 = reinterpret_cast<float4*>(static_cast<float*>(p.out2) + pixel * p.out2_ld + c0);
-#pragma unroll
-        for (int i = 0; i < NC / 4; ++i) o2[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-      }
-      if (p.res != nullptr) {
-        const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(p.res) + pixel * p.res_ld + c0);
-#pragma unroll
-        for (int i = 0; i < NC / 4; ++i) {
-          const float4 r4 = rp[i];
-          v[4 * i] += r4.x; v[4 * i + 1] += r4.y; v[4 * i + 2] += r4.z; v[4 * i + 3] += r4.w;
-        }
-      }
-      if (p.relu) {
-#pragma unroll
-        for (int i = 0; i < NC; ++i) v[i] = fmaxf(v[i], 0.f);
-      }
-      float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + pixel * p.out_ld + c0);
-#pragma unroll
-      for (int i = 0; i < NC / 4; ++i) op[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-      return;
-    }
-    if (p.out2 != nullptr) {
-      bf16x8* o2 = reinterpret_cast<bf16x8*>(static_cast<__nv_bfloat16*>(p.out2) + pixel * p.out2_ld + c0);
-#pragma unroll
-      for (int i = 0; i < NC / 8; ++i) o2[i] = pack8(v + i * 8);
-    }
-    if (p.res != nullptr) {
-#pragma unroll
-      for (int i = 0; i < NC / 8; ++i) {
-        float rf[8];
-        unpack8(rv[i], rf);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[i * 8 + e] += rf[e];
-      }
-    }
-    if (p.relu) {
-#pragma unroll
-      for (int i = 0; i < NC; ++i) v[i] = fmaxf(v[i], 0.f);
-    }
     bf16x8* op = reinterpret_cast<bf16x8*>(static_cast<__nv_bfloat16*>(p.out) + pixel * p.out_ld + c0);
 #pragma unroll
     for (int i = 0; i < NC / 8; ++i) {
@@ -351,7 +367,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_patch_kernel(const __grid_con
         const int c3 = static_cast<int>(r1 / HP);
         for (int cb = 0; cb < p.NCB; ++cb) {
           mbar_wait(&empty_p[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_p[stage], static_cast<uint32_t>(PR * p.pw) * p.row_bytes);
+          mbar_arrive_expect_tx(&full_p[stage], static_cast<uint32_t>(p.pr * p.pw) * p.row_bytes);
           tma_load_4d(sP + stage * p.pstage_bytes, &tmap, cb * p.CB, c1, c2, c3, &full_p[stage]);
           if (++stage == PSTAGES) { stage = 0; phase ^= 1; }
         }
@@ -555,6 +571,14 @@ extern "C" int air_conv_patch_taps_ex2_bf16(const void* a, long long a_ld, int B
                                             int GH, int GW, int org_h, int org_w, int osh, int osw, int oph, int opw,
                                             int ntaps, const int* tap_dr, const int* tap_dc, const int* tap_slice,
                                             int flags, int num_sms, cudaStream_t stream);
+extern "C" int air_conv_patch_taps_ex3_bf16(const void* a, long long a_ld, int B, int Hin, int Win, int C,
+                                            const void* wpk, int wtaps, int N, void* out, long long out_ld, int OH, int OW,
+                                            const void* res, long long res_ld, int relu, const float* bias,
+                                            const float* post_scale, const float* post_shift,
+                                            void* out2, long long out2_ld, double* stats,
+                                            int GH, int GW, int org_h, int org_w, int osh, int osw, int oph, int opw,
+                                            int ntaps, const int* tap_dr, const int* tap_dc, const int* tap_slice,
+                                            int flags, int num_sms, cudaStream_t stream);
 
 // The general entry point: explicit tap table and output pixel mapping (see the formula at the top of this file).
 //   a: (B, Hin, Win, C) channels-last bf16;  out / res: (B, OH, OW, N);  item grid GH x GW;
@@ -602,7 +626,27 @@ extern "C" int air_conv_patch_taps_ex2_bf16(const void* a, long long a_ld, int B
                                             int GH, int GW, int org_h, int org_w, int osh, int osw, int oph, int opw,
                                             int ntaps, const int* tap_dr, const int* tap_dc, const int* tap_slice,
                                             int flags, int num_sms, cudaStream_t stream) {
+  return air_conv_patch_taps_ex3_bf16(a, a_ld, B, Hin, Win, C, wpk, wtaps, N, out, out_ld, OH, OW, res, res_ld, relu, bias,
+                                      nullptr, nullptr, out2, out2_ld, stats, GH, GW, org_h, org_w, osh, osw, oph, opw, ntaps,
+                                      tap_dr, tap_dc, tap_slice, flags, num_sms, stream);
+}
+
+// as air_conv_patch_taps_ex2_bf16 plus an optional per-channel affine applied right after the ReLU (bf16 storage only):
+//   t = relu(acc + bias) * post_scale + post_shift;  out2 <- t;  out <- round_bf16(t) + res
+// = conv -> ReLU -> eval-mode BatchNorm with the running-statistics affine folded in (ecapa_tdnn.py:73-83: out2 is the
+// branch output, out the next branch's input); without out2 / res simply out <- t.
+extern "C" int air_conv_patch_taps_ex3_bf16(const void* a, long long a_ld, int B, int Hin, int Win, int C,
+                                            const void* wpk, int wtaps, int N, void* out, long long out_ld, int OH, int OW,
+                                            const void* res, long long res_ld, int relu, const float* bias,
+                                            const float* post_scale, const float* post_shift,
+                                            void* out2, long long out2_ld, double* stats,
+                                            int GH, int GW, int org_h, int org_w, int osh, int osw, int oph, int opw,
+                                            int ntaps, const int* tap_dr, const int* tap_dc, const int* tap_slice,
+                                            int flags, int num_sms, cudaStream_t stream) {
   if (!a || !wpk || !out || B <= 0 || !tap_dr || !tap_dc || !tap_slice) return AIR_ERR_ARG;
+  if ((post_scale == nullptr) != (post_shift == nullptr)) return AIR_ERR_ARG;
+  if (post_scale && ((flags & AIR_CONV_F32_OUT) || stats || (N % 32) != 0)) return AIR_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(post_scale) | reinterpret_cast<uintptr_t>(post_shift)) & 15) return AIR_ERR_UNSUPPORTED;
   if (stats && (N % 32) != 0) return AIR_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(out2)) & 15) return AIR_ERR_UNSUPPORTED;
   if (out2 && out2_ld % 8 != 0) return AIR_ERR_UNSUPPORTED;
@@ -620,9 +664,13 @@ extern "C" int air_conv_patch_taps_ex2_bf16(const void* a, long long a_ld, int B
   p.ntaps = ntaps;
   for (int t = 0; t < MAX_TAPS; ++t) { p.tap_off[t] = 0; p.tap_slice[t] = 0; }
   int max_dc = 0;
-  for (int t = 0; t < ntaps; ++t) max_dc = std::max(max_dc, tap_dc[t]);
+  int max_dr = 0;
+  for (int t = 0; t < ntaps; ++t) { max_dc = std::max(max_dc, tap_dc[t]); max_dr = std::max(max_dr, tap_dr[t]); }
+  if (max_dr < 0 || max_dr > PR - R) return AIR_ERR_ARG;
+  p.pr = R + max_dr;
   p.pw = max_dc <= PW - TW ? PW : PW_MAX;
   p.bias = bias; p.out2 = out2; p.out2_ld = out2_ld; p.stats = stats;
+  p.post_scale = post_scale; p.post_shift = post_shift;
   for (int t = 0; t < ntaps; ++t) {
     if (tap_dr[t] < 0 || tap_dr[t] > PR - R || tap_dc[t] < 0 || tap_dc[t] > p.pw - TW || tap_slice[t] < 0 || tap_slice[t] >= wtaps)
       return AIR_ERR_ARG;
@@ -635,7 +683,7 @@ extern "C" int air_conv_patch_taps_ex2_bf16(const void* a, long long a_ld, int B
   if (items > 0x7fffffffLL) return AIR_ERR_UNSUPPORTED;
   p.items = static_cast<uint32_t>(items);
   p.acc_stages = (2 * R * N <= 512) ? 2 : 1;
-  p.pstage_bytes = static_cast<uint32_t>((PR * p.pw * p.row_bytes + 1023) / 1024 * 1024);
+  p.pstage_bytes = static_cast<uint32_t>((p.pr * p.pw * p.row_bytes + 1023) / 1024 * 1024);
   p.bslot_bytes = static_cast<uint32_t>(N * p.row_bytes);
   p.bslot_stride = (p.bslot_bytes + 1023u) / 1024u * 1024u;
   p.pstages = p.pstage_bytes <= 36u * 1024u ? MAX_PSTAGES : 2;
@@ -662,7 +710,7 @@ extern "C" int air_conv_patch_taps_ex2_bf16(const void* a, long long a_ld, int B
                       (p.stage_out ? 8 * STAGE_TILE : 0) +
                       (2 * PSTAGES + 2 * slots + 4) * 8 + 32 + (stats ? 4 * 2 * static_cast<size_t>(N) * sizeof(float) : 0);
   CUtensorMap tm, tmo;
-  int tr = air_tmap::make_act_tmap(&tm, a, a_ld, B, Hin, Win, C, p.CB, p.pw, PR, p.row_bytes);
+  int tr = air_tmap::make_act_tmap(&tm, a, a_ld, B, Hin, Win, C, p.CB, p.pw, p.pr, p.row_bytes);
   if (tr == 0 && p.stage_out) {
     // output view of the item grid: grid point (g, g') is pixel (g * osh + oph, g' * osw + opw); grid points whose pixel
     // lies outside the tensor are outside the view, so the TMA store clips them

@@ -47,6 +47,7 @@ struct WParams {
                                                     // that covers W with less padding (W = 94 / 188: 73 % -> 98 % useful)
   int pw;                                           // patch width in pixels (tw + 2, or tw + 8 for dilated 1-D taps)
   int R;                                            // rows per item: 2, or 3 when H = 3 and the wider stage fits (tw = 96)
+  int xr;                                           // x patch rows actually loaded: R + largest tap row offset
   uint32_t x_bytes, stage_bytes;
   int nacc; int acc_off[NACC]; int acc_lbo[NACC];   // per accumulator: window offset / group distance, in patch pixels
   int acc_tap[NACC][8];                             // tap of each M row group (-1: not a real tap)
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_wgrad_patch_kernel(const _
         const int w0 = static_cast<int>(wt) * p.tw, h0 = static_cast<int>(r1 % HP) * p.R, b = static_cast<int>(r1 / HP);
         mbar_wait(&empty[stage], phase ^ 1);
         const uint32_t dst = sbase + stage * p.stage_bytes;
-        mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>((p.R + 2) * p.pw) * (p.narrow ? 32u : 128u) + static_cast<uint32_t>(p.R * p.tw) * 128u);
+        mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>(p.xr * p.pw) * (p.narrow ? 32u : 128u) + static_cast<uint32_t>(p.R * p.tw) * 128u);
         tma_load_4d(dst, &tmx, p.narrow ? 0 : cb * 64, w0 + p.org_w, h0 + p.org_h, b, &full[stage]);
         tma_load_4d(dst + p.x_bytes, &tmdy, nb * 64, w0, h0, b, &full[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -238,9 +239,11 @@ static int launch_wgrad_patch(const void* x, long long x_ld, int B, int H, int W
   // three rows per item when that wastes fewer rows (H = 3: 75 % -> 100 % useful) and two such stages fit
   p.R = R;
   if ((H + 2) / 3 * 3 < (H + 1) / 2 * 2 && p.tw == 96 && !p.narrow) p.R = 3;
-  for (int t = 0; t < ntaps; ++t) if (tap_dr[t] > 2) return AIR_ERR_ARG;
+  int max_dr = 0;
+  for (int t = 0; t < ntaps; ++t) { if (tap_dr[t] > 2) return AIR_ERR_ARG; max_dr = std::max(max_dr, tap_dr[t]); }
+  p.xr = p.R + max_dr;
   p.NCB = p.narrow ? 1 : C / 64; p.NNB = N / 64; p.WT = (W + p.tw - 1) / p.tw; p.HP = (H + p.R - 1) / p.R;
-  p.x_bytes = (static_cast<uint32_t>((p.R + 2) * p.pw) * (p.narrow ? 32u : 128u) + 1023u) / 1024u * 1024u;
+  p.x_bytes = (static_cast<uint32_t>(p.xr * p.pw) * (p.narrow ? 32u : 128u) + 1023u) / 1024u * 1024u;
   p.stage_bytes = p.x_bytes + (p.R == R ? DY_BYTES : (static_cast<uint32_t>(p.R * p.tw) * 128u + 1023u) / 1024u * 1024u);
   if (1024 + STAGES * static_cast<size_t>(p.stage_bytes) + 64 > 227 * 1024) return AIR_ERR_UNSUPPORTED;
   for (int a = 0; a < NACC; ++a) { p.acc_off[a] = 0; p.acc_lbo[a] = 0; for (int g = 0; g < 8; ++g) p.acc_tap[a][g] = -1; }
@@ -289,9 +292,9 @@ static int launch_wgrad_patch(const void* x, long long x_ld, int B, int H, int W
   CUtensorMap tmx, tmdy;
   int tr;
   if (xv) tr = air_tmap::make_act_tmap_strided(&tmx, xv->base, xv->sw, xv->sh, xv->sb, B, xv->H, xv->W, C, p.narrow ? 16 : 64,
-                                               p.pw, p.R + 2, p.narrow ? 32 : 128);
-  else tr = p.narrow ? air_tmap::make_act_tmap(&tmx, x, x_ld, B, H, W, C, 16, p.pw, p.R + 2, 32)
-                     : air_tmap::make_act_tmap(&tmx, x, x_ld, B, H, W, C, 64, p.pw, p.R + 2, 128);
+                                               p.pw, p.xr, p.narrow ? 32 : 128);
+  else tr = p.narrow ? air_tmap::make_act_tmap(&tmx, x, x_ld, B, H, W, C, 16, p.pw, p.xr, 32)
+                     : air_tmap::make_act_tmap(&tmx, x, x_ld, B, H, W, C, 64, p.pw, p.xr, 128);
   if (tr == 0) tr = air_tmap::make_act_tmap(&tmdy, dy, dy_ld, B, H, W, N, 64, p.tw, p.R, 128);
   if (tr != 0) return tr < 0 ? AIR_ERR_DRIVER : 10000 + tr;
   const size_t smem = 1024 + static_cast<size_t>(STAGES) * p.stage_bytes + (2 * STAGES + 1) * 8 + 16;

@@ -193,10 +193,21 @@ class ConvLayer:
                       self.dh, self.dw, 0, self.wpk, self.cout, self.K, out, out_ld, bias, res, res_ld, relu)
         return Ho, Wo
 
-    def fprop_affine(self, x, x_ld, B, H, W, out, out_ld, relu, scale, shift):
-        """conv (+bias) -> [ReLU] -> per-channel affine, in one launch (eval-mode conv -> ReLU -> BN)."""
+    def fprop_affine(self, x, x_ld, B, H, W, out, out_ld, relu, scale, shift, add=None, add_ld=0, out_sum=None, out_sum_ld=0):
+        """conv (+bias) -> [ReLU] -> per-channel affine, in one launch (eval-mode conv -> ReLU -> BN).
+        add / out_sum (dilated 1-D layers on the patch kernel only): out_sum = round(out) + add, the next Res2 branch's
+        input (ecapa_tdnn.py:77-80)."""
         Ho, Wo = self.out_hw(H, W)
         bias = self.store.view(self.name + ".bias") if self.bias else None
+        if self.d1_ok and out.dtype == BF16 and self.cout % 32 == 0:
+            if out_sum is not None:          # kernel roles: out2 = the affine output, out = rounded output + residual
+                ops.conv1d_patch(x, x_ld, B, H, W, self.cin, self.wpk3, self.kw, self.dw, self.cout, out_sum, out_sum_ld, bias,
+                                 add, add_ld, relu, out, out_ld, 0, scale, shift)
+            else:
+                ops.conv1d_patch(x, x_ld, B, H, W, self.cin, self.wpk3, self.kw, self.dw, self.cout, out, out_ld, bias,
+                                 None, 0, relu, None, 0, 0, scale, shift)
+            return Ho, Wo
+        assert out_sum is None, "fused next-branch sum needs the patch kernel"
         ops.conv_gemm_affine(x, x_ld, B, H, W, self.cin_g, Ho, Wo, self.kh, self.kw, self.sh, self.sw, self.ph, self.pw,
                              self.dh, self.dw, 0, self.wpk, self.cout, self.K, out, out_ld, bias, relu, scale, shift)
         return Ho, Wo

@@ -11,6 +11,7 @@ kernels (csrc/bn.cu, csrc/ecapa.cu).  The 3072 time-constant input columns of at
 materialising the (B, 4608, T) `global_x`.
 """
 import math
+import os
 
 import torch
 
@@ -49,6 +50,9 @@ class _BN1d:
 
 
 class EcapaEngine(AsyncWgrad):
+    # scoring: eval-mode BatchNorm of the Res2 branches folded into the dilated-conv epilogue (AIR_FOLD_EVAL_BN=0: separate pass)
+    fold_eval_bn = os.environ.get("AIR_FOLD_EVAL_BN", "1") != "0"
+
     def __init__(self, C=512, scale=8, n_out=2, n_mels=60, bottleneck=128, enc_dim=256, device="cuda", train_head=False,
                  precision="bf16"):
         """precision: "bf16" (product path) or "fp32" (parity mode, see ResNetEngine / DESIGN.md section 5)."""
@@ -280,6 +284,17 @@ class EcapaEngine(AsyncWgrad):
             self._eval_affine[bn.name] = aff
         conv.fprop_affine(x, x_ld, B, 1, T, y, C, True, aff[1], aff[2])
 
+    def _eval_affine_of(self, bn):
+        """(scale, shift) of an eval-mode BatchNorm1d, cached per parameter / running-statistics version."""
+        key = (self.store.step, self._eval_version)
+        aff = self._eval_affine.get(bn.name)
+        if aff is None or aff[0] != key:
+            g, b = self.store.view(bn.name + ".weight"), self.store.view(bn.name + ".bias")
+            scale = g * torch.rsqrt(bn.running_var + 1e-5)
+            aff = (key, scale.contiguous(), (b - bn.running_mean * scale).contiguous())
+            self._eval_affine[bn.name] = aff
+        return aff[1], aff[2]
+
     def _bn_bwd(self, bn, dy, dy_ld, x, x_ld, dx, dx_ld, M, dbias):
         g, b = self.store.view(bn.name + ".weight"), self.store.view(bn.name + ".bias")
         ops.bn_bwd_bias(dy, dy_ld, x, x_ld, None, 0, dx, dx_ld, M, bn.C, 1, bn.save_mean, bn.save_invstd, g, b, bn.rsum,
@@ -309,8 +324,18 @@ class EcapaEngine(AsyncWgrad):
             for i in range(self.scale - 1):                                                    # :73-83
                 src = blk.o1[:, :, 0:W] if i == 0 else blk.spin[i]
                 src_ld = C if i == 0 else W
-                blk.convs[i].fprop(src, src_ld, B, 1, T, blk.tb[i], W, relu=True)
                 dst = blk.cat[:, :, i * W:(i + 1) * W]
+                conv = blk.convs[i]
+                if not training and self.fold_eval_bn and getattr(conv, "d1_ok", False) and dst.dtype == torch.bfloat16:
+                    # scoring: conv -> ReLU -> BatchNorm (running statistics) -> (+ next split) in one launch
+                    sc, sh = self._eval_affine_of(blk.bns[i])
+                    if i + 1 < self.scale - 1:
+                        conv.fprop_affine(src, src_ld, B, 1, T, dst, C, True, sc, sh, add=blk.o1[:, :, (i + 1) * W:(i + 2) * W],
+                                          add_ld=C, out_sum=blk.spin[i + 1], out_sum_ld=W)
+                    else:
+                        conv.fprop_affine(src, src_ld, B, 1, T, dst, C, True, sc, sh)
+                    continue
+                conv.fprop(src, src_ld, B, 1, T, blk.tb[i], W, relu=True)
                 if i + 1 < self.scale - 1:       # next branch input = this output + spx[i+1]
                     self._bn_fwd(blk.bns[i], blk.tb[i], W, dst, C, M, training,
                                  add=blk.o1[:, :, (i + 1) * W:(i + 2) * W], add_ld=C, y2=blk.spin[i + 1], y2_ld=W)

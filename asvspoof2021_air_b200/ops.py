@@ -177,17 +177,32 @@ def conv1x1_patch(a, a_ld, B, H, W, C, wpk, N, out, out_ld, res=None, res_ld=0, 
 
 
 def conv1d_patch(a, a_ld, B, H, W, C, wpk, k, d, N, out, out_ld, bias=None, res=None, res_ld=0, relu=False,
-                 out2=None, out2_ld=0, mode=0):
+                 out2=None, out2_ld=0, mode=0, post_scale=None, post_shift=None):
     """1-D convolution over W (H independent rows), kernel k, dilation d, 'same' padding, through the TMA patch kernel.
-    mode 0: forward (mode-0 packed weights); mode 1: data gradient (mode-1 packed weights)."""
+    mode 0: forward (mode-0 packed weights); mode 1: data gradient (mode-1 packed weights).
+    post_scale / post_shift (fp32 [N], optional): t = relu(acc + bias) * scale + shift; out2 <- t; out <- round(t) + res
+    (eval-mode BatchNorm folded into the epilogue)."""
     zero = (ctypes.c_int * k)(*([0] * k))
     dc = (ctypes.c_int * k)(*[t * d for t in range(k)])
     sl = (ctypes.c_int * k)(*range(k))
+    if H == 1:
+        # no tap crosses rows, so the B sequences are the rows of ONE image: a work item (two rows x 128 columns) then
+        # carries two sequences instead of one sequence and an empty row (same addresses: (B, 1, W, C) == (1, B, W, C))
+        B, H = 1, B
+    if post_scale is not None:
+        _lib.check(_lib.lib().air_conv_patch_taps_ex3_bf16(
+            _lib.ptr(a), _lib.LL(a_ld), B, H, W, C, _lib.ptr(wpk), k, N, _lib.ptr(out), _lib.LL(out_ld), H, W,
+            _lib.ptr(res), _lib.LL(res_ld), int(relu), _lib.ptr(bias), _lib.ptr(post_scale), _lib.ptr(post_shift),
+            _lib.ptr(out2), _lib.LL(out2_ld), None, H, W, 0, -d * (k - 1) // 2, 1, 1, 0, 0, k, zero, dc, sl,
+            _conv_flags(out, res, out2), num_sms(), _lib.stream_ptr()), "air_conv_patch_taps_ex3_bf16")
+        return out
     return _patch_taps_ex2(a, a_ld, B, H, W, C, wpk, k, N, out, out_ld, H, W, res, res_ld, relu, bias, out2, out2_ld, None,
                            H, W, 0, -d * (k - 1) // 2, 1, 1, 0, 0, k, zero, dc, sl)
 
 
 def conv1d_wgrad_patch(x, x_ld, B, H, W, C, dy, dy_ld, N, k, d, dw_out, dw_ld=None):
+    if H == 1:
+        B, H = 1, B                          # as conv1d_patch: independent rows, two sequences per work item
     _lib.check(_lib.lib().air_conv1d_wgrad_patch_bf16(
         _lib.ptr(x), _lib.LL(x_ld), B, H, W, C, _lib.ptr(dy), _lib.LL(dy_ld), N, k, d, _lib.ptr(dw_out),
         _lib.LL(k * C if dw_ld is None else dw_ld), num_sms(), _lib.stream_ptr()), "air_conv1d_wgrad_patch_bf16")

@@ -447,6 +447,17 @@ int air_conv_patch_taps_ex2_bf16(const void* a, long long a_ld, int B, int Hin, 
                                  int GH, int GW, int org_h, int org_w, int osh, int osw, int oph, int opw,
                                  int ntaps, const int* tap_dr, const int* tap_dc, const int* tap_slice,
                                  int flags, int num_sms, air_stream_t stream);
+/* as air_conv_patch_taps_ex2_bf16 plus an optional per-channel affine applied right after the ReLU (bf16 storage only):
+ * t = relu(acc + bias) * post_scale + post_shift; out2 <- t; out <- round_bf16(t) + res -- conv -> ReLU -> eval-mode
+ * BatchNorm1d with the running-statistics affine folded in (ecapa_tdnn.py:73-83; generate_score.py's forward pass) */
+int air_conv_patch_taps_ex3_bf16(const void* a, long long a_ld, int B, int Hin, int Win, int C,
+                                 const void* wpk, int wtaps, int N, void* out, long long out_ld, int OH, int OW,
+                                 const void* res, long long res_ld, int relu, const float* bias,
+                                 const float* post_scale, const float* post_shift,
+                                 void* out2, long long out2_ld, double* stats,
+                                 int GH, int GW, int org_h, int org_w, int osh, int osw, int oph, int opw,
+                                 int ntaps, const int* tap_dr, const int* tap_dc, const int* tap_slice,
+                                 int flags, int num_sms, air_stream_t stream);
 int air_conv_s2_dgrad_patch_ex_bf16(const void* dy, long long dy_ld, int B, int Ho, int Wo, int Cout,
                                     const void* wpk, int k, int Cin, void* dx, long long dx_ld, int H, int W,
                                     const void* res, long long res_ld, int flags, int num_sms, air_stream_t stream);

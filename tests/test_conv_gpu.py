@@ -320,6 +320,21 @@ def test_patch_dilated_conv1d_fprop_dgrad_wgrad(d):
     xs = src.float().permute(0, 2, 1)
     ref = F.relu(F.conv1d(xs, wq, bias, padding=d, dilation=d))
     _check(out.float().permute(0, 2, 1), ref, "dilated conv1d fprop d=%d" % d)
+    # scoring form: conv -> ReLU -> eval-mode BatchNorm affine in the epilogue; second launch also emits the next branch's
+    # input = round_bf16(affine output) + next split (ecapa_tdnn.py:73-83)
+    sc, sh = (torch.rand(Wd, generator=g) + 0.5).cuda(), torch.randn(Wd, generator=g).cuda()
+    refa = ref * sc[None, :, None] + sh[None, :, None]
+    oa = torch.full((B, T, Wd), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.conv1d_patch(src, C, B, 1, T, Wd, wpk, 3, d, Wd, oa, Wd, bias, None, 0, True, None, 0, 0, sc, sh)
+    torch.cuda.synchronize()
+    _check(oa.float().permute(0, 2, 1), refa, "dilated conv1d fprop + affine d=%d" % d)
+    cat = torch.zeros(B, T, C, device="cuda", dtype=torch.bfloat16)
+    nxt = torch.full((B, T, Wd), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.conv1d_patch(src, C, B, 1, T, Wd, wpk, 3, d, Wd, nxt, Wd, bias, big[:, :, 192:256], C, True, cat[:, :, 64:128], C, 0, sc, sh)
+    torch.cuda.synchronize()
+    assert torch.equal(cat[:, :, 64:128], oa) and (cat[:, :, :64] == 0).all() and (cat[:, :, 128:] == 0).all()
+    want = (oa.float() + big[:, :, 192:256].float()).to(torch.bfloat16)
+    assert torch.equal(nxt, want)
     # data gradient with a residual and the un-accumulated second output
     dy = torch.randn(B, T, Wd, generator=g).cuda().to(torch.bfloat16)
     res = torch.randn(B, T, C, generator=g).cuda().to(torch.bfloat16)

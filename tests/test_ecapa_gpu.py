@@ -172,3 +172,21 @@ def test_trainer_step_from_raw_waves():
     assert l2 == l2 and l2 != l1
     s = tr.score_step(waves.cuda())
     assert s.shape == (B,) and torch.isfinite(s).all()
+
+
+def test_scoring_with_folded_branch_batchnorm_matches_the_separate_pass():
+    """Eval-mode forward with the Res2-branch BatchNorms folded into the dilated-conv epilogues (engine.fold_eval_bn) against
+    the same forward with conv and bn_apply as separate passes: same arithmetic up to fp32 association (scale * x + shift
+    vs (x - mean) * invstd * gamma + beta), i.e. one bf16 rounding per branch output."""
+    from asvspoof2021_air_b200.trainer import Trainer
+    B = 8
+    tr = Trainer(arch="ecapa", seed=7)
+    w = ss.seeded_waves(B, 64000, seed=21).cuda()
+    lab = ss.seeded_labels(B, 0).cuda()
+    tr.train_step(w, lab)                                   # non-trivial running statistics
+    outs = []
+    for fold in (False, True):
+        tr.engine.fold_eval_bn = fold
+        outs.append(tr.score_step(w).float().cpu())
+    assert float((outs[0] - outs[1]).abs().max()) <= 2e-2, float((outs[0] - outs[1]).abs().max())
+    assert not torch.equal(outs[0], outs[0] * 0)
