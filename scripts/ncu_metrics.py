@@ -13,7 +13,14 @@ WANT = {"gpu__time_duration.sum": "time_us", "dram__bytes_read.sum": "dram_read"
         "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_active_pct",
         "dram__throughput.avg.pct_of_peak_sustained_elapsed": "dram_throughput_pct",
         "l1tex__m_xbar2l1tex_read_bytes.sum": "l2_to_sm_read", "launch__registers_per_thread": "registers",
-        "launch__grid_size": "grid", "launch__block_size": "block", "smsp__inst_executed.sum": "warp_instructions"}
+        "launch__grid_size": "grid", "launch__block_size": "block", "smsp__inst_executed.sum": "warp_instructions",
+        # the L1 / shared-memory data pipe: LSU wavefronts (global + shared accesses of the warps) and the tensor core's
+        # operand reads share it -- the bound of the N <= 128 conv layers found in round 2
+        "l1tex__data_pipe_lsu_wavefronts.sum": "l1_lsu_wavefronts",
+        "l1tex__data_pipe_tc_wavefronts_mem_shared.sum": "l1_tensor_operand_wavefronts",
+        "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed": "l1_lsu_wavefronts_pct",
+        "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed": "l1_tensor_operand_wavefronts_pct",
+        "sm__cycles_elapsed.max": "sm_cycles"}
 SCALE = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1e3, "us": 1.0, "ns": 1e-3, "s": 1e6}
 out = {}
 for arg in sys.argv[1:]:
@@ -34,5 +41,7 @@ for arg in sys.argv[1:]:
             d[WANT[h]] = x * SCALE.get(u, 1.0) if WANT[h] in ("time_us", "dram_read", "dram_write", "l2_to_sm_read") else x
     if "dram_read" in d and "dram_write" in d:
         d["traffic_bytes"] = d["dram_read"] + d["dram_write"]
+    if "l1_lsu_wavefronts_pct" in d and "l1_tensor_operand_wavefronts_pct" in d:
+        d["l1_data_pipe_busy_pct"] = d["l1_lsu_wavefronts_pct"] + d["l1_tensor_operand_wavefronts_pct"]
     out[name] = d
 print(json.dumps(out, indent=1, sort_keys=True))
