@@ -186,8 +186,10 @@ class ConvLayer:
             return Ho, Wo
         bias = self.store.view(self.name + ".bias") if self.bias else None
         if self.d1_ok:
+            fuse = stats is not None and self.cout % 32 == 0 and out.dtype == BF16
             ops.conv1d_patch(x, x_ld, B, H, W, self.cin, self.wpk3, self.kw, self.dw, self.cout, out, out_ld, bias,
-                             res, res_ld, relu, None, 0, 0)
+                             res, res_ld, relu, None, 0, 0, None, None, stats if fuse else None)
+            self.stats_fused = fuse
             return Ho, Wo
         ops.conv_gemm(x, x_ld, B, H, W, self.cin_g, Ho, Wo, self.kh, self.kw, self.sh, self.sw, self.ph, self.pw,
                       self.dh, self.dw, 0, self.wpk, self.cout, self.K, out, out_ld, bias, res, res_ld, relu)

@@ -52,6 +52,11 @@ class _BN1d:
 class EcapaEngine(AsyncWgrad):
     # scoring: eval-mode BatchNorm of the Res2 branches folded into the dilated-conv epilogue (AIR_FOLD_EVAL_BN=0: separate pass)
     fold_eval_bn = os.environ.get("AIR_FOLD_EVAL_BN", "1") != "0"
+    # training: batch statistics of the Res2-branch BatchNorms accumulated by the epilogue of the dilated conv.  Off by default:
+    # it saves 0.1 ms of 16.2 (21 small bn_stats launches), and although the sums agree with bn_stats to 1e-7 the golden-size
+    # net (BatchNorm1d over B = 4 rows in SE / bn5) amplifies that summation-order difference to 1e-2 on the embeddings, which
+    # moves the B = 4 loss across the 1e-3 parity bar of test_ecapa_gpu.py.  AIR_ECAPA_FUSE_BN_STATS=1 turns it on.
+    fuse_bn_stats = os.environ.get("AIR_ECAPA_FUSE_BN_STATS", "0") == "1"
 
     def __init__(self, C=512, scale=8, n_out=2, n_mels=60, bottleneck=128, enc_dim=256, device="cuda", train_head=False,
                  precision="bf16"):
@@ -260,10 +265,12 @@ class EcapaEngine(AsyncWgrad):
         self._w1tmp = None
 
     # ---- BN helpers (conv -> ReLU -> BN order: y = bn(x), x already relu'd) --------------------
-    def _bn_fwd(self, bn, x, x_ld, y, y_ld, M, training, add=None, add_ld=0, y2=None, y2_ld=0):
+    def _bn_fwd(self, bn, x, x_ld, y, y_ld, M, training, add=None, add_ld=0, y2=None, y2_ld=0, have_stats=False):
+        """have_stats: the conv that produced x already accumulated its sum / sum of squares into bn.sums."""
         g, b = self.store.view(bn.name + ".weight"), self.store.view(bn.name + ".bias")
         if training:
-            ops.bn_stats(x, x_ld, M, bn.C, bn.sums)
+            if not have_stats:
+                ops.bn_stats(x, x_ld, M, bn.C, bn.sums)
             bn.num_batches_tracked += 1
         ops.bn_apply_add(x, x_ld, y, y_ld, M, bn.C, bn.sums, g, b, False, training, bn.save_mean, bn.save_invstd,
                          bn.running_mean, bn.running_var, add, add_ld, y2, y2_ld)
@@ -335,12 +342,14 @@ class EcapaEngine(AsyncWgrad):
                     else:
                         conv.fprop_affine(src, src_ld, B, 1, T, dst, C, True, sc, sh)
                     continue
-                conv.fprop(src, src_ld, B, 1, T, blk.tb[i], W, relu=True)
+                fuse = training and self.fuse_bn_stats
+                conv.fprop(src, src_ld, B, 1, T, blk.tb[i], W, relu=True, stats=blk.bns[i].sums if fuse else None)
+                hs = bool(fuse and getattr(conv, "stats_fused", False))
                 if i + 1 < self.scale - 1:       # next branch input = this output + spx[i+1]
                     self._bn_fwd(blk.bns[i], blk.tb[i], W, dst, C, M, training,
-                                 add=blk.o1[:, :, (i + 1) * W:(i + 2) * W], add_ld=C, y2=blk.spin[i + 1], y2_ld=W)
+                                 add=blk.o1[:, :, (i + 1) * W:(i + 2) * W], add_ld=C, y2=blk.spin[i + 1], y2_ld=W, have_stats=hs)
                 else:
-                    self._bn_fwd(blk.bns[i], blk.tb[i], W, dst, C, M, training)
+                    self._bn_fwd(blk.bns[i], blk.tb[i], W, dst, C, M, training, have_stats=hs)
             ops.copy_channels(blk.o1[:, :, C - W:], C, blk.cat[:, :, C - W:], C, M, W)         # :85
             self._conv_relu_bn(blk.conv3, blk.bn3, blk.cat, C, B, T, blk.t3, blk.o3, C, M, training)      # :87-89
             # SE (:15-29): squeeze -> 512->128 -> ReLU -> BN -> 128->512 -> sigmoid -> scale; + residual (:93)

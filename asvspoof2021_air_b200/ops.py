@@ -177,11 +177,12 @@ def conv1x1_patch(a, a_ld, B, H, W, C, wpk, N, out, out_ld, res=None, res_ld=0, 
 
 
 def conv1d_patch(a, a_ld, B, H, W, C, wpk, k, d, N, out, out_ld, bias=None, res=None, res_ld=0, relu=False,
-                 out2=None, out2_ld=0, mode=0, post_scale=None, post_shift=None):
+                 out2=None, out2_ld=0, mode=0, post_scale=None, post_shift=None, stats=None):
     """1-D convolution over W (H independent rows), kernel k, dilation d, 'same' padding, through the TMA patch kernel.
     mode 0: forward (mode-0 packed weights); mode 1: data gradient (mode-1 packed weights).
     post_scale / post_shift (fp32 [N], optional): t = relu(acc + bias) * scale + shift; out2 <- t; out <- round(t) + res
-    (eval-mode BatchNorm folded into the epilogue)."""
+    (eval-mode BatchNorm folded into the epilogue).  stats (fp64 [2N], optional): += per-channel sum / sum of squares of the
+    stored output (the batch statistics of the BatchNorm that follows)."""
     zero = (ctypes.c_int * k)(*([0] * k))
     dc = (ctypes.c_int * k)(*[t * d for t in range(k)])
     sl = (ctypes.c_int * k)(*range(k))
@@ -196,7 +197,7 @@ def conv1d_patch(a, a_ld, B, H, W, C, wpk, k, d, N, out, out_ld, bias=None, res=
             _lib.ptr(out2), _lib.LL(out2_ld), None, H, W, 0, -d * (k - 1) // 2, 1, 1, 0, 0, k, zero, dc, sl,
             _conv_flags(out, res, out2), num_sms(), _lib.stream_ptr()), "air_conv_patch_taps_ex3_bf16")
         return out
-    return _patch_taps_ex2(a, a_ld, B, H, W, C, wpk, k, N, out, out_ld, H, W, res, res_ld, relu, bias, out2, out2_ld, None,
+    return _patch_taps_ex2(a, a_ld, B, H, W, C, wpk, k, N, out, out_ld, H, W, res, res_ld, relu, bias, out2, out2_ld, stats,
                            H, W, 0, -d * (k - 1) // 2, 1, 1, 0, 0, k, zero, dc, sl)
 
 

@@ -320,6 +320,16 @@ def test_patch_dilated_conv1d_fprop_dgrad_wgrad(d):
     xs = src.float().permute(0, 2, 1)
     ref = F.relu(F.conv1d(xs, wq, bias, padding=d, dilation=d))
     _check(out.float().permute(0, 2, 1), ref, "dilated conv1d fprop d=%d" % d)
+    # training form: the epilogue also accumulates the batch statistics of the BatchNorm that follows (sum / sum of squares of
+    # the stored output)
+    st = torch.zeros(2 * Wd, device="cuda", dtype=torch.float64)
+    out_s = torch.full((B, T, Wd), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.conv1d_patch(src, C, B, 1, T, Wd, wpk, 3, d, Wd, out_s, Wd, bias, None, 0, True, None, 0, 0, None, None, st)
+    torch.cuda.synchronize()
+    assert torch.equal(out_s, out)
+    o64 = out.double().reshape(-1, Wd)
+    assert torch.allclose(st[:Wd], o64.sum(0), rtol=1e-5, atol=1e-6 * float(o64.abs().sum(0).max())), (st[:Wd] - o64.sum(0)).abs().max()
+    assert torch.allclose(st[Wd:], (o64 * o64).sum(0), rtol=1e-5)
     # scoring form: conv -> ReLU -> eval-mode BatchNorm affine in the epilogue; second launch also emits the next branch's
     # input = round_bf16(affine output) + next split (ecapa_tdnn.py:73-83)
     sc, sh = (torch.rand(Wd, generator=g) + 0.5).cuda(), torch.randn(Wd, generator=g).cuda()
