@@ -183,6 +183,9 @@ def run(args, rank, world, helpers):
                 "d2h_bytes_per_step": int(res_host.numel()) * 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches, "clocks": clocks,
     }
+    red = getattr(tr, "reducer", None)
+    if red is not None and red.exposed_ms() is not None:
+        line["exchange_exposed_ms_per_step"] = red.exposed_ms()      # AIR_DDP_TRACE=1: compute stream waiting for the all-reduce
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(arch, scoring, seconds=15.0)
     return line

@@ -72,9 +72,11 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const StemParams<T> p) {
   }
 }
 
-// dw[co][tap] += sum_m dy[m][co] * x[pix(m, tap)].  One warp per kernel row i, one lane per pixel: a lane reads the
-// 16 gradients of its pixel (2 x 16 B) and the 3 input samples of row i once for 48 FMAs; partial sums stay in
-// registers over all the pixels of the block and are reduced by warp shuffles at the end.
+// dw[co][tap] += sum_m dy[m][co] * x[pix(m, tap)].  One warp per kernel row i; a block walks whole output rows (b, ho), so
+// the pixel decode is per row, not per pixel (the first version spent most of its instructions on two 64-bit modulo
+// operations per pixel); a lane takes the pixels wo = lane, lane + 32, ... of the row, two per iteration: it reads the 16
+// gradients of each pixel (2 x 16 B) and the 3 input samples of row i once for 48 FMAs.  Partial sums stay in registers
+// over all rows of the block and are reduced by warp shuffles at the end.
 template <typename T>
 __global__ void __launch_bounds__(320) stem_wgrad_kernel(const StemParams<T> p) {
   const int i = threadIdx.x >> 5, lane = threadIdx.x & 31;      // blockDim.x = 32 * kh
@@ -83,20 +85,33 @@ __global__ void __launch_bounds__(320) stem_wgrad_kernel(const StemParams<T> p) 
   for (int j = 0; j < 3; ++j)
 #pragma unroll
     for (int c = 0; c < CO; ++c) acc[j][c] = 0.f;
-  for (long long m = static_cast<long long>(blockIdx.x) * 32 + lane; m < p.M; m += static_cast<long long>(gridDim.x) * 32) {
-    const int wo = static_cast<int>(m % p.Wo); const long long t = m / p.Wo;
-    const int ho = static_cast<int>(t % p.Ho), b = static_cast<int>(t / p.Ho);
+  const int rows = p.B * p.Ho;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    const int b = r / p.Ho, ho = r - b * p.Ho;
     const int hi = ho * p.sh - p.ph + i;
-    if (hi < 0 || hi >= p.H) continue;
-    float g[CO];
-    ld8(p.dy + m * CO, g); ld8(p.dy + m * CO + 8, g + 8);
+    if (hi < 0 || hi >= p.H) continue;                            // warp-uniform
     const T* row = p.x + (static_cast<long long>(b) * p.H + hi) * p.W;
+    const T* dyr = p.dy + static_cast<long long>(r) * p.Wo * CO;
+    for (int wo = lane; wo < p.Wo; wo += 64) {
+      const int wo2 = wo + 32;
+      const bool two = wo2 < p.Wo;
+      float g0[CO], g1[CO], x0[3], x1[3];
+      ld8(dyr + static_cast<long long>(wo) * CO, g0); ld8(dyr + static_cast<long long>(wo) * CO + 8, g0 + 8);
+      if (two) { ld8(dyr + static_cast<long long>(wo2) * CO, g1); ld8(dyr + static_cast<long long>(wo2) * CO + 8, g1 + 8); }
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const int wi = wo - p.pw + j;
-      const float xv = (wi >= 0 && wi < p.W) ? ld1(row + wi) : 0.f;
+      for (int j = 0; j < 3; ++j) {
+        const int wi = wo - p.pw + j, wj = wo2 - p.pw + j;
+        x0[j] = (wi >= 0 && wi < p.W) ? ld1(row + wi) : 0.f;
+        x1[j] = (two && wj >= 0 && wj < p.W) ? ld1(row + wj) : 0.f;
+      }
+      if (!two) {
 #pragma unroll
-      for (int c = 0; c < CO; ++c) acc[j][c] = fmaf(g[c], xv, acc[j][c]);
+        for (int c = 0; c < CO; ++c) g1[c] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int c = 0; c < CO; ++c) acc[j][c] = fmaf(g1[c], x1[j], fmaf(g0[c], x0[j], acc[j][c]));
     }
   }
   const int taps = p.kh * 3;
@@ -143,8 +158,8 @@ static int stem_wgrad_impl(const void* x, int B, int H, int W, int kh, int kw, i
   if (int e = stem_fill(p, x, B, H, W, kh, kw, sh, sw, ph, pw)) return e;
   if (!dy || !dw || Cout != CO || kw != 3 || sw != 1 || kh > 10) return AIR_ERR_UNSUPPORTED;
   p.dy = reinterpret_cast<const T*>(dy); p.dw = dw;
-  const long long chunks = (p.M + 31) / 32;
-  const int blocks = static_cast<int>(std::min<long long>(chunks, 148 * 6));
+  if (static_cast<long long>(B) * p.Ho > 0x7fffffffLL) return AIR_ERR_UNSUPPORTED;
+  const int blocks = static_cast<int>(std::min<long long>(static_cast<long long>(B) * p.Ho, 148 * 2));      // two resident blocks per SM (96 registers x 288 threads)
   stem_wgrad_kernel<T><<<blocks, 32 * kh, 0, stream>>>(p);
   return air_launch_status();
 }

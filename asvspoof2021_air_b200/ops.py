@@ -9,11 +9,21 @@ from . import _lib
 _SMS = {}
 
 
+_RESERVED = [0]
+
+
+def reserve_sms(k):
+    """Leave k SMs out of the persistent grids launched from now on (0 = use them all).  The conv kernels are one CTA per SM
+    with the whole register file: a collective kernel resident on a few SMs would push that many of their CTAs into a second
+    wave (a ~2x longer launch); sized to the collective's CTA cap they run side by side (parallel.GradReducer)."""
+    _RESERVED[0] = max(0, int(k))
+
+
 def num_sms(device=None):
     d = torch.cuda.current_device() if device is None else device
     if d not in _SMS:
         _SMS[d] = torch.cuda.get_device_properties(d).multi_processor_count
-    return _SMS[d]
+    return max(1, _SMS[d] - _RESERVED[0])
 
 
 F32 = torch.float32

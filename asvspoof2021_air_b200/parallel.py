@@ -30,7 +30,8 @@ def init_from_env(backend=None):
         if backend == "nccl":
             # the ring / NVLS kernels of the gradient exchange run BESIDE persistent 148-CTA conv grids: a handful of
             # CTAs moves 50 MB per step well inside the backward pass, more only evicts compute (override via the env)
-            os.environ.setdefault("NCCL_MAX_CTAS", "8")
+            # (Trainer leaves exactly that many SMs out of its persistent grids during the backward pass)
+            os.environ.setdefault("NCCL_MAX_CTAS", "2")
             torch.cuda.set_device(local)
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         else:
@@ -38,6 +39,14 @@ def init_from_env(backend=None):
     elif torch.cuda.is_available():
         torch.cuda.set_device(local if world > 1 else torch.cuda.current_device())
     return rank, world, local
+
+
+def collective_ctas():
+    """CTAs (= SMs) the gradient exchange may occupy while compute kernels are running (the NCCL_MAX_CTAS cap)."""
+    try:
+        return max(0, int(os.environ.get("NCCL_MAX_CTAS", "0")))
+    except ValueError:
+        return 0
 
 
 def shard_range(n, rank, world):
@@ -75,6 +84,7 @@ class GradReducer:
         self.stream = torch.cuda.Stream() if self.overlap else None
         self.next = 0
         self.extra = []
+        self.trace = [] if os.environ.get("AIR_DDP_TRACE") == "1" else None
 
     def begin(self):
         self.next = 0
@@ -121,8 +131,24 @@ class GradReducer:
             else:
                 dist.all_reduce(t, group=self.group)
         if self.overlap:
-            torch.cuda.current_stream().wait_stream(self.stream)
+            if self.trace is not None:                       # AIR_DDP_TRACE=1: how long the compute stream waits for the exchange
+                e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                e0.record(torch.cuda.current_stream())       # backward pass done on the compute stream
+                e1.record(self.stream)                       # exchange done
+                torch.cuda.current_stream().wait_stream(self.stream)
+                e2.record(torch.cuda.current_stream())
+                self.trace.append((e0, e2))
+            else:
+                torch.cuda.current_stream().wait_stream(self.stream)
         return 1.0 / self.world
+
+    def exposed_ms(self):
+        """Mean time per step the compute stream spent waiting for the gradient exchange (AIR_DDP_TRACE=1), else None."""
+        if not self.trace:
+            return None
+        torch.cuda.synchronize()
+        v = [a.elapsed_time(b) for a, b in self.trace[len(self.trace) // 2:]]
+        return sum(v) / len(v)
 
 
 def broadcast_state(tensors, src=0, group=None):

@@ -111,7 +111,7 @@ def dist_setup(n_gpus):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         import torch.distributed as dist
-        os.environ.setdefault("NCCL_MAX_CTAS", "8")          # see asvspoof2021_air_b200/parallel.py:init_from_env
+        os.environ.setdefault("NCCL_MAX_CTAS", "2")          # see asvspoof2021_air_b200/parallel.py:init_from_env
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:
