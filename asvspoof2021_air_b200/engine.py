@@ -458,6 +458,33 @@ class AsyncWgrad:
             fn(*args)
         self._side_pending = True
 
+    # Weight packing (fp32 master weights -> pre-swizzled bf16 operand tiles, once per optimiser step) also runs on the side
+    # stream: launched by the Trainer BEFORE the LFCC kernel, it overlaps the front end and the stem, which need no packed
+    # weights; the compute stream waits for it in front of the first tensor-core layer.
+    _pack_event = None
+
+    def prepack(self):
+        """Start packing the current weights on the side stream (no-op when they are already packed)."""
+        if self._packed_version == self.store.step:
+            return
+        if not self.overlap_wgrad:
+            self.pack_weights()
+            return
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        ev = torch.cuda.Event()
+        ev.record()                                   # the optimiser step and the last users of the old tiles precede this point
+        self._side.wait_event(ev)
+        with torch.cuda.stream(self._side):
+            self.pack_weights()
+            self._pack_event = torch.cuda.Event()
+            self._pack_event.record()
+
+    def _await_pack(self):
+        if self._pack_event is not None:
+            torch.cuda.current_stream().wait_event(self._pack_event)
+            self._pack_event = None
+
     def _side_events(self):
         if not self._side_pending:
             return ()
@@ -676,8 +703,7 @@ class ResNetEngine(AsyncWgrad):
         assert x0.dtype == self.act_dtype and x0.is_contiguous() and x0.dim() == 3 and x0.shape[1] == self.F
         self.bind(x0.shape[0], x0.shape[2])
         B = self.B
-        if self._packed_version != self.store.step:
-            self.pack_weights()
+        self.prepack()                          # (normally started by the Trainer before the LFCC kernel)
         self.x0 = x0
         if training:
             self.buffers.f64.zero_()
@@ -685,6 +711,7 @@ class ResNetEngine(AsyncWgrad):
         ops.stem_fwd(x0, B, self.H0, self.W0, 9, 3, 3, 1, 1, 1, st.view("conv1.weight"), 16, self.c1)
         M1 = B * self.H1 * self.W1
         self.bn1.forward(self.c1, 16, self.z1, 16, M1, True, training)
+        self._await_pack()                      # the first layer that reads packed weights follows
         x = self.z1
         x_stats = False                         # were the statistics of x accumulated by the conv that produced it?
         for bi, blk in enumerate(self.blocks):

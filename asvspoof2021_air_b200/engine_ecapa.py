@@ -313,8 +313,8 @@ class EcapaEngine(AsyncWgrad):
         assert x0.dtype == self.act_dtype and x0.dim() == 3 and x0.shape[2] == self.mels_g and x0.is_contiguous()
         B, T = x0.shape[0], x0.shape[1]
         self.bind(B, T)
-        if self._packed_version != self.store.step:
-            self.pack_weights()
+        self.prepack()                          # (normally started by the Trainer before the LFCC kernel)
+        self._await_pack()
         if not hasattr(self, "_eval_affine"):
             self._eval_affine, self._eval_version = {}, getattr(self, "_eval_version", 0)
         if training:
