@@ -7,18 +7,26 @@
 //     e[m] = a[160+m] + a[160-m],  o[m] = a[160+m] - a[160-m]   (m = 1..159),   e[0] = a[160],  o[0] = 0,
 //     Re X_k = sum_m e[m] cos(2 pi k m / 512) + a[0] cos(5 pi k / 8)
 //     Im X_k = sum_m o[m] sin(2 pi k m / 512) - a[0] sin(5 pi k / 8)          (sign irrelevant for |X_k|^2)
-// i.e. two [frames x 160] x [160 x 255] products (bins 0 and 256 carry no filterbank weight).  bf16 tensor cores
-// with fp32 accumulation reach the fp32 parity bar through a 3-term split  x*w ~ x_hi*w_hi + x_lo*w_hi + x_hi*w_lo
-// (x = x_hi + x_lo, both bf16): worst deviation 7e-6 * (|ref| + 1) on the golden waves (tolerance 1e-4).
+// i.e. two [frames x 160] x [160 x 255] products (bins 0 and 256 carry no filterbank weight).  16-bit tensor cores
+// with fp32 accumulation reach the fp32 parity bar through a 3-term split of x = x_hi + x_lo and w = w_hi + w_lo,
+//     x*w ~ x_hi*w_hi  (fp16 x fp16: 11 + 11 significant bits)
+//         + x_lo*w_b   (bf16 x bf16: the residual of x keeps fp32's exponent range, so quiet recordings and tiny residuals
+//                       do not underflow; 8 bits of w = bf16(w) are plenty against a term that is 2^-11 of the product)
+//         + x_hi*w_lo  (fp16 x fp16: w_lo = w - w_hi sits in fp16's subnormal range, absolute precision 2^-24)
+// (kind::f16 takes fp16 or bf16, but both operands of one instruction must have the same format: mixing them is an
+// illegal instruction on sm_100a).  Worst deviation 1.4e-6 * (|ref| + 1) on the golden waves, 1.7e-5 on a speech-like
+// frame with bands 60 dB under its peak, 1.5e-6 on the same frame 100 dB quieter (a bf16 / bf16 split: 7e-6 and 1.0e-4; an
+// fp16 / fp16 split: 3e-4 on quiet input) -- tolerance 1e-4, the reference's own fp32 arithmetic 9e-6.
 //
 // A tile is 128 consecutive frames (UMMA M) of the flattened (utterance, frame) sequence, 124 of which produce
 // output (2 halo frames each side for the delta-deltas).  Per tile, per CTA (persistent, grid = #SMs):
 //   prep warps (8)   : wave -> pre-emphasis -> window -> fold -> bf16 hi/lo -> SWIZZLE_64B K-major A images in smem
-//   producer warp    : streams the pre-swizzled DFT matrices (bf16 hi/lo, 8 KB chunks) through a shared-memory ring
+//   producer warp    : streams the pre-swizzled DFT matrices (w_hi fp16 / w bf16 / w_lo fp16, 8 KB chunks) through a shared-memory ring
 //   MMA warp         : 120 x tcgen05.mma 128x128x16 per tile; Re/Im x two 128-bin halves = 4 accumulators (512 TMEM columns)
 //   epilogue warps(4): TMEM -> |X|^2 -> sparse triangular filterbank (2 filters per bin, compile-time structure,
 //                      run-time weights) -> log10 -> 20x20 DCT -> cepstra in smem -> deltas, pad/crop map, layout, dtype
 #include <algorithm>
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -208,9 +216,9 @@ __global__ void __launch_bounds__(THREADS, 1) lfcc_tc_kernel(const Params p) {
             const float ap = yp * wp[i], am = ym * wm[i];
             float v;
             if (part == 0) v = (m == 0) ? ap : ap + am; else v = (m == 0) ? 0.f : ap - am;
-            const __nv_bfloat16 hi = f2bf(v);
-            const __nv_bfloat16 lo = f2bf(v - bf2f(hi));
-            *reinterpret_cast<__nv_bfloat16*>(img_hi + i * CHUNK + soff) = hi;
+            const __half hi = __float2half_rn(v);                       // 11 significant bits
+            const __nv_bfloat16 lo = f2bf(v - __half2float(hi));         // the residual, fp32 exponent range
+            *reinterpret_cast<__half*>(img_hi + i * CHUNK + soff) = hi;
             *reinterpret_cast<__nv_bfloat16*>(img_lo + i * CHUNK + soff) = lo;
           }
           if (part == 0 && lane == 0) s_a0[(it & 1) * TM + fr] = fmaf(-p.preemph, x00, x0) * w0;
@@ -224,7 +232,7 @@ __global__ void __launch_bounds__(THREADS, 1) lfcc_tc_kernel(const Params p) {
     if (lane == 0) {
       uint32_t slot = 0, phase = 0;
       for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-        for (int s = 0; s < 2 * 2 * KBLK * 2; ++s) {
+        for (int s = 0; s < 2 * 2 * KBLK * 3; ++s) {
           mbar_wait(&b_empty[slot], phase ^ 1);
           mbar_arrive_expect_tx(&b_full[slot], CHUNK);
           bulk_g2s(sbase + SM_B + slot * CHUNK, p.wmat + static_cast<long long>(s) * (CHUNK / 2), CHUNK, &b_full[slot]);
@@ -236,7 +244,8 @@ __global__ void __launch_bounds__(THREADS, 1) lfcc_tc_kernel(const Params p) {
     // ===================== MMA issuer (warp-uniform loop, elected lane issues) =====================
     const bool leader = elect_one();
     const bool committer = leader;
-    const uint32_t idesc = instr_desc_bf16(128, 128, 0, 0);
+    // operand formats per term (both operands of an instruction share one): fp16 x fp16 for the hi images, bf16 x bf16 for x_lo
+    const uint32_t idesc_ff = instr_desc_f16(128, 128, 0, 0, 0, 0), idesc_bb = instr_desc_f16(128, 128, 0, 0, 1, 1);
     const uint32_t desc_hi = (512u >> 4) | (1u << 14) | (4u << 29);      // SBO = 8 rows x 64 B, version 1, SWIZZLE_64B
     const uint32_t a16 = ((sbase + SM_A) >> 4) & 0x3FFF, b16 = ((sbase + SM_B) >> 4) & 0x3FFF;
     uint32_t slot = 0, bphase = 0, it = 0;
@@ -253,35 +262,23 @@ __global__ void __launch_bounds__(THREADS, 1) lfcc_tc_kernel(const Params p) {
           for (int kb = 0; kb < KBLK; ++kb) {
             const uint32_t ahi = a16 + ((part * 2 + 0) * KBLK + kb) * (CHUNK >> 4);
             const uint32_t alo = a16 + ((part * 2 + 1) * KBLK + kb) * (CHUNK >> 4);
-            mbar_wait(&b_full[slot], bphase);
-            fence_after_sync();
-            const uint32_t bhi = b16 + slot * (CHUNK >> 4);
-            const uint32_t s_hi = slot;
-            if (++slot == NSLOT) { slot = 0; bphase ^= 1; }
+            // three chunks per K block, each used by one term: w_hi (fp16) x x_hi, bf16(w) x x_lo, w_lo (fp16) x x_hi
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              const uint64_t ad = (static_cast<uint64_t>(desc_hi) << 32) | ((ahi + ks * 2) | (1u << 16));
-              const uint64_t bd = (static_cast<uint64_t>(desc_hi) << 32) | ((bhi + ks * 2) | (1u << 16));
-              if (leader) mma_bf16(d, ad, bd, idesc, (kb | ks) != 0);
-            }
+            for (int term = 0; term < 3; ++term) {
+              mbar_wait(&b_full[slot], bphase);
+              fence_after_sync();
+              const uint32_t bch = b16 + slot * (CHUNK >> 4);
+              const uint32_t ach = term == 1 ? alo : ahi;
+              const uint32_t idesc = term == 1 ? idesc_bb : idesc_ff;
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              const uint64_t ad = (static_cast<uint64_t>(desc_hi) << 32) | ((alo + ks * 2) | (1u << 16));
-              const uint64_t bd = (static_cast<uint64_t>(desc_hi) << 32) | ((bhi + ks * 2) | (1u << 16));
-              if (leader) mma_bf16(d, ad, bd, idesc, 1u);
+              for (int ks = 0; ks < 2; ++ks) {
+                const uint64_t ad = (static_cast<uint64_t>(desc_hi) << 32) | ((ach + ks * 2) | (1u << 16));
+                const uint64_t bd = (static_cast<uint64_t>(desc_hi) << 32) | ((bch + ks * 2) | (1u << 16));
+                if (leader) mma_bf16(d, ad, bd, idesc, (term | kb | ks) != 0);
+              }
+              if (committer) mma_commit(&b_empty[slot]);
+              if (++slot == NSLOT) { slot = 0; bphase ^= 1; }
             }
-            if (committer) mma_commit(&b_empty[s_hi]);
-            mbar_wait(&b_full[slot], bphase);
-            fence_after_sync();
-            const uint32_t blo = b16 + slot * (CHUNK >> 4);
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              const uint64_t ad = (static_cast<uint64_t>(desc_hi) << 32) | ((ahi + ks * 2) | (1u << 16));
-              const uint64_t bd = (static_cast<uint64_t>(desc_hi) << 32) | ((blo + ks * 2) | (1u << 16));
-              if (leader) mma_bf16(d, ad, bd, idesc, 1u);
-            }
-            if (committer) mma_commit(&b_empty[slot]);
-            if (++slot == NSLOT) { slot = 0; bphase ^= 1; }
           }
           if (part == 1 && committer) mma_commit(&tfull[h]);
         }
@@ -369,8 +366,8 @@ __global__ void __launch_bounds__(THREADS, 1) lfcc_tc_kernel(const Params p) {
 }  // namespace air_lfcc_tc
 
 extern "C" int air_lfcc_tc_table_floats() { return air_lfcc_tc::TBL_FLOATS; }
-// bf16 elements of the DFT operand table: [Re/Im][half][kb][hi/lo] chunks of [128 bins][32 samples]
-extern "C" int air_lfcc_tc_wmat_elems() { return 2 * 2 * air_lfcc_tc::KBLK * 2 * (air_lfcc_tc::CHUNK / 2); }
+// 16-bit elements of the DFT operand table: [Re/Im][half][kb][w_hi fp16 / w bf16 / w_lo fp16] chunks of [128 bins][32 samples]
+extern "C" int air_lfcc_tc_wmat_elems() { return 2 * 2 * air_lfcc_tc::KBLK * 3 * (air_lfcc_tc::CHUNK / 2); }
 
 extern "C" int air_lfcc_fill(const int* lengths, int B, int L, void* out, long long sb, long long sj, long long sd,
                              int out_bf16, int Tout, int feat_len, int pad_mode, const float* silence, cudaStream_t stream);

@@ -203,4 +203,17 @@ __host__ __device__ __forceinline__ uint32_t instr_desc_bf16(int M, int N, int a
   return d;
 }
 
+// the same with the operand formats chosen per operand (kind::f16 takes fp16 and bf16 in any combination): 0 = fp16, 1 = bf16
+__host__ __device__ __forceinline__ uint32_t instr_desc_f16(int M, int N, int a_mn_major, int b_mn_major, int a_bf16, int b_bf16) {
+  uint32_t d = 0;
+  d |= 1u << 4;                       // c_format  = F32
+  d |= static_cast<uint32_t>(a_bf16 & 1) << 7;
+  d |= static_cast<uint32_t>(b_bf16 & 1) << 10;
+  d |= static_cast<uint32_t>(a_mn_major & 1) << 15;
+  d |= static_cast<uint32_t>(b_mn_major & 1) << 16;
+  d |= static_cast<uint32_t>(N >> 3) << 17;
+  d |= static_cast<uint32_t>(M >> 4) << 24;
+  return d;
+}
+
 }  // namespace tc05

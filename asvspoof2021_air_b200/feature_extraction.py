@@ -42,8 +42,8 @@ class LFCC(nn.Module):
         self._table = None
         self._silence = None
         self._tc = None
-        # "tc": tensor-core DFT (csrc/lfcc_tc.cu, 3-term bf16 split); "fft": radix FFT in fp32 on the CUDA cores
-        # (csrc/lfcc.cu); "auto" (default): by output dtype, see impl_for().  AIR_LFCC_IMPL / `.impl` force one.
+        # "tc": tensor-core DFT (csrc/lfcc_tc.cu, 3-term fp16 / bf16 split); "fft": radix FFT in fp32 on the CUDA cores
+        # (csrc/lfcc.cu); "auto" (default) = "tc", see impl_for().  AIR_LFCC_IMPL / `.impl` force one.
         self.impl = os.environ.get("AIR_LFCC_IMPL", "auto")
 
     # -- constants -------------------------------------------------------------------------
@@ -63,14 +63,15 @@ class LFCC(nn.Module):
         return self._tc
 
     def impl_for(self, dtype):
-        """Which kernel serves an output dtype.  bf16 features (what the networks consume) come from the tensor-core
-        kernel: its error -- <= 8e-6 (|ref|+1) on the benchmark's signals, ~1.4e-4 on frames whose weak bands lie 60 dB
-        under the strongest (scripts/lfcc_split_study.py) -- is far below the 2^-9 of the bf16 rounding that follows.
-        fp32 features (LFCC.forward, the reference's own output, where 1e-4 parity is promised for ANY input) come
-        from the fp32 FFT kernel (2.4e-6; 147 us instead of 112 us per 256 utterances)."""
+        """Which kernel serves an output dtype: the tensor-core kernel for every dtype.  Its 3-term split keeps the hi parts
+        in fp16 and the residuals in bf16 (csrc/lfcc_tc.cu), which holds the fp32 contract on any input: worst deviation from
+        the float64 oracle 1.4e-6 (|ref|+1) on the golden waves, 1.7e-5 on frames whose weak bands lie 60 dB under the
+        strongest, 1.4e-6 on the same frames 60 dB quieter (tolerance 1e-4; the reference's own fp32 arithmetic: 9e-6).
+        "fft" (AIR_LFCC_IMPL / `.impl`): the radix FFT in fp32 on the CUDA cores (csrc/lfcc.cu, 2.4e-6, 147 us instead of
+        112 us per 256 utterances); the fp32 parity mode of the Trainer pins it."""
         if self.impl in ("tc", "fft"):
             return self.impl
-        return "fft" if dtype == torch.float32 else "tc"
+        return "tc"
 
     def num_frames(self, length):
         return 1 + length // self.fs

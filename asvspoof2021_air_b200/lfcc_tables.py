@@ -131,23 +131,28 @@ def pack_tc_table(lfcc_fb: torch.Tensor, dct_weight: torch.Tensor) -> torch.Tens
 
 
 def pack_tc_dft() -> torch.Tensor:
-    """bf16 hi/lo split of the folded real-DFT matrices cos / sin (2 pi k m / 512), k = 1..256, m = 0..159, as
-    pre-swizzled (SWIZZLE_64B, K-major) [128 bins][32 samples] operand chunks in MMA order [Re/Im][half][kb][hi/lo]."""
+    """3-term operand split of the folded real-DFT matrices cos / sin (2 pi k m / 512), k = 1..256, m = 0..159, as pre-swizzled
+    (SWIZZLE_64B, K-major) [128 bins][32 samples] operand chunks in MMA order [Re/Im][half][kb][term]:
+        term 0: w_hi = fp16(w)            (multiplies x_hi, fp16 x fp16)
+        term 1: w_b  = bf16(w)            (multiplies x_lo, bf16 x bf16)
+        term 2: w_lo = fp16(w - w_hi)     (multiplies x_hi, fp16 x fp16; fp16 subnormals: absolute precision 2^-24)
+    The returned tensor is 16-bit storage typed bf16: the chunks of terms 0 and 2 hold fp16 BIT PATTERNS."""
     k = np.arange(1, 257, dtype=np.float64)[:, None]
     m = np.arange(160, dtype=np.float64)[None, :]
     ang = 2.0 * math.pi * k * m / 512.0
-    out = torch.zeros(2, 2, TC_KBLK, 2, TC_CHUNK_ELEMS, dtype=torch.bfloat16)
+    out = torch.zeros(2, 2, TC_KBLK, 3, TC_CHUNK_ELEMS, dtype=torch.bfloat16)
     n = np.arange(128)[:, None]
     kk = np.arange(32)[None, :]
     off = n * 64 + kk * 2
     idx = torch.from_numpy(((off ^ (((off >> 7) & 3) << 4)) >> 1).reshape(-1).astype(np.int64))
     for part, mat in enumerate((np.cos(ang), np.sin(ang))):
         full = torch.from_numpy(mat.astype(np.float32))
-        hi = full.to(torch.bfloat16)
-        lo = (torch.from_numpy(mat) - hi.double()).float().to(torch.bfloat16)
+        hi16 = full.to(torch.float16)
+        lo16 = (torch.from_numpy(mat) - hi16.double()).float().to(torch.float16)
+        terms = (hi16.view(torch.bfloat16), full.to(torch.bfloat16), lo16.view(torch.bfloat16))
         for h in range(2):
             for kb in range(TC_KBLK):
-                for which, src in enumerate((hi, lo)):
+                for which, src in enumerate(terms):
                     blk = src[128 * h:128 * h + 128, 32 * kb:32 * kb + 32].reshape(-1)
                     out[part, h, kb, which, idx] = blk
     return out.reshape(-1)

@@ -99,28 +99,39 @@ def lfcc_emulated(wave, tbl):
 
 
 # ---------------------------------------------------------------------------------------------------
-# tensor-core path (csrc/lfcc_tc.cu): folded real DFT with a 3-term bf16 hi/lo split, emulated from the PACKED tables
+# tensor-core path (csrc/lfcc_tc.cu): folded real DFT with the 3-term split x_hi*w_hi (fp16) + x_lo*bf16(w) (bf16) + x_hi*w_lo
+# (fp16), emulated from the PACKED tables
 # ---------------------------------------------------------------------------------------------------
 def _bf16(x):
     import torch
     return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(torch.bfloat16).float().numpy()
 
 
+def _f16(x):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(torch.float16).float().numpy()
+
+
 def unpack_tc_dft(wmat):
-    """Inverse of lfcc_tables.pack_tc_dft: -> (C_hi, C_lo, S_hi, S_lo), each (256 bins k=1..256, 160 samples) float32."""
-    w = wmat.float().numpy().reshape(2, 2, lt.TC_KBLK, 2, 128, 64 // 2)      # [part][h][kb][which][flat 4096] viewed later
-    w = wmat.float().numpy().reshape(2, 2, lt.TC_KBLK, 2, lt.TC_CHUNK_ELEMS)
+    """Inverse of lfcc_tables.pack_tc_dft: -> (C_hi, C_b, C_lo, S_hi, S_b, S_lo), each (256 bins k=1..256, 160 samples)
+    float32.  Terms 0 / 2 of the 16-bit table hold fp16 bit patterns (w_hi, w_lo), term 1 bf16 values (bf16(w))."""
+    import torch
+    w16 = wmat.reshape(2, 2, lt.TC_KBLK, 3, lt.TC_CHUNK_ELEMS)
+    w = np.zeros(w16.shape, dtype=np.float32)
+    for term in (0, 2):
+        w[:, :, :, term] = w16[:, :, :, term].contiguous().view(torch.float16).float().numpy()
+    w[:, :, :, 1] = w16[:, :, :, 1].float().numpy()
     n = np.arange(128)[:, None]
     kk = np.arange(32)[None, :]
     off = n * 64 + kk * 2
     idx = (off ^ (((off >> 7) & 3) << 4)) >> 1
-    mats = np.zeros((2, 2, 256, 160), dtype=np.float32)                        # [part][which][k][m]
+    mats = np.zeros((2, 3, 256, 160), dtype=np.float32)                        # [part][term][k][m]
     for part in range(2):
         for h in range(2):
             for kb in range(lt.TC_KBLK):
-                for which in range(2):
+                for which in range(3):
                     mats[part, which, 128 * h:128 * h + 128, 32 * kb:32 * kb + 32] = w[part, h, kb, which][idx]
-    return mats[0, 0], mats[0, 1], mats[1, 0], mats[1, 1]
+    return mats[0, 0], mats[0, 1], mats[0, 2], mats[1, 0], mats[1, 1], mats[1, 2]
 
 
 def lfcc_tc_emulate(wave, tbl, wmat, preemph=0.97):
@@ -130,7 +141,7 @@ def lfcc_tc_emulate(wave, tbl, wmat, preemph=0.97):
     win = tbl[lt.TC_OFF_WIN:lt.TC_OFF_WIN + 320]
     fbw = tbl[lt.TC_OFF_FBW:lt.TC_OFF_FBW + 512].reshape(256, 2)
     dct = tbl[lt.TC_OFF_DCT:lt.TC_OFF_DCT + 400].reshape(20, 20)
-    Chi, Clo, Shi, Slo = (m.astype(np.float64) for m in unpack_tc_dft(wmat))
+    Chi, Cb, Clo, Shi, Sb, Slo = (m.astype(np.float64) for m in unpack_tc_dft(wmat))
     wave = np.asarray(wave, dtype=np.float32)
     B, L = wave.shape
     T = 1 + L // 160
@@ -150,10 +161,10 @@ def lfcc_tc_emulate(wave, tbl, wmat, preemph=0.97):
         e[:, 0] = a[:, 160]
         e[:, 1:] = a[:, 160 + mm] + a[:, 160 - mm]
         o[:, 1:] = a[:, 160 + mm] - a[:, 160 - mm]
-        ehi, ohi = _bf16(e), _bf16(o)
+        ehi, ohi = _f16(e), _f16(o)                               # hi parts fp16, residuals bf16 (csrc/lfcc_tc.cu)
         elo, olo = _bf16(e - ehi), _bf16(o - ohi)
-        re = (ehi @ Chi.T + elo @ Chi.T + ehi @ Clo.T).astype(np.float32) + a[:, :1] * c160
-        im = (ohi @ Shi.T + olo @ Shi.T + ohi @ Slo.T).astype(np.float32) - a[:, :1] * s160
+        re = (ehi @ Chi.T + elo @ Cb.T + ehi @ Clo.T).astype(np.float32) + a[:, :1] * c160
+        im = (ohi @ Shi.T + olo @ Sb.T + ohi @ Slo.T).astype(np.float32) - a[:, :1] * s160
         P = re * re + im * im
         fb = np.zeros((B, 22), np.float32)
         for k in range(1, 256):

@@ -120,3 +120,25 @@ def test_full_size_properties(mod):
     shift = np.log10(4.0) * np.sqrt(20.0)            # ortho DCT: c0 = sum(fbe)/sqrt(20)
     assert torch.allclose(y2[..., 0] - y[:8, :, 0], torch.full_like(y2[..., 0], shift), atol=1e-3)
     assert torch.allclose(y2[..., 1:20], y[:8, :, 1:20], atol=1e-3)
+
+
+@pytest.mark.parametrize("scale", [1.0, 1e-3])
+def test_tensor_core_kernel_holds_the_fp32_bar_on_high_dynamic_range_speech(scale):
+    """The 3-term split of csrc/lfcc_tc.cu (fp16 hi parts, bf16 residual of x, fp16 residual of w) on a speech-like wave
+    whose weak bands lie ~60 dB under its strongest harmonics, loud and 60 dB quieter: within 5e-5 (|ref|+1) of the float64
+    oracle (tolerance of the contract 1e-4; a bf16 / bf16 split gives 1.0e-4 here, an fp16 / fp16 split 3e-4 on the quiet one;
+    tests/test_oracle.py pins the same numbers on the CPU emulation)."""
+    from asvspoof2021_air_b200.feature_extraction import LFCC
+    from tolerances import lfcc_worst
+    n = np.arange(16000)
+    rng = np.random.RandomState(0)
+    speech = sum(0.3 / h * np.sin(2 * np.pi * 140 * h * n / 16000) for h in range(1, 9)) + 3e-4 * rng.randn(16000)
+    w = (scale * speech)[None].astype(np.float32)
+    want = lo.lfcc(w)
+    m = LFCC(320, 160, 512, 16000, 20).cuda()
+    assert m.impl_for(torch.float32) in ("tc", "fft")
+    m.impl = "tc"
+    got = m(torch.from_numpy(w).cuda()).cpu().numpy()
+    assert got.shape == want.shape
+    assert lfcc_worst(got[:, :, :20], want[:, :, :20]) < 5e-5, lfcc_worst(got[:, :, :20], want[:, :, :20])
+    assert lfcc_worst(got, want) < 1e-4, lfcc_worst(got, want)
