@@ -805,3 +805,25 @@ def test_training_cli_dry_run_from_packed_corpora(monkeypatch, tmp_path):
     assert [c["grl"] for c in tr.calls] == [False] * 3 + [True] * 3
     for c in tr.calls:
         assert c["channels"].shape == (4,) and c["channels"][:2].tolist() == [0, 0] and (c["channels"][2:] > 0).all()
+
+
+def test_sm_reservation_for_the_gradient_exchange(monkeypatch):
+    """ops.reserve_sms(k) takes k SMs out of every persistent grid launched afterwards (the NCCL kernels of the gradient
+    exchange occupy them during the backward pass, parallel.collective_ctas() = the NCCL_MAX_CTAS cap); 0 restores them."""
+    from asvspoof2021_air_b200 import ops, parallel
+    monkeypatch.setitem(ops._SMS, 0, 148)
+    try:
+        assert ops.num_sms(0) == 148
+        ops.reserve_sms(2)
+        assert ops.num_sms(0) == 146
+        ops.reserve_sms(1000)
+        assert ops.num_sms(0) == 1                      # never an empty grid
+    finally:
+        ops.reserve_sms(0)
+    assert ops.num_sms(0) == 148
+    monkeypatch.setenv("NCCL_MAX_CTAS", "2")
+    assert parallel.collective_ctas() == 2
+    monkeypatch.setenv("NCCL_MAX_CTAS", "x")
+    assert parallel.collective_ctas() == 0
+    monkeypatch.delenv("NCCL_MAX_CTAS")
+    assert parallel.collective_ctas() == 0
