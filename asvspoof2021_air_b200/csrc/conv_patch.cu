@@ -67,6 +67,11 @@ struct PatchParams {
   int nb_slots, resident;               // weight ring
   int acc_stages;                       // 1 or 2
   int ntaps; int tap_off[MAX_TAPS]; int tap_slice[MAX_TAPS];     // window offset in patch pixels, weight slice
+  // flat mode (flat_h > 0): the images of the batch are treated as ONE image of B * flat_h rows, so that a work item may
+  // pair the last row of an image with the first row of the next one (odd heights: 5 rows = 3 pairs per image -> 2.5);
+  // the taps that would cross the image boundary are skipped per row: tap row offset tap_dr[t] is applied to image row h
+  // only when 0 <= h + org_h + tap_dr[t] < flat_h.  (Otherwise every tap applies and the TMA zero fill is the padding.)
+  int flat_h; int tap_dr[MAX_TAPS];
   uint32_t items;
 };
 
@@ -271,11 +276,22 @@ __device__ __forceinline__ void mma_role(const MmaCtx& c) {
   for (uint32_t item = blockIdx.x; item < items; item += gridDim.x, ++it) {
     const uint32_t hp = (item / WT) % HP;
     const bool two = GH - static_cast<int>(hp) * R >= 2;
+    uint32_t m0 = 7u, m1 = 7u;                    // per-row masks of the tap row offsets that apply (flat mode)
+    if (p.flat_h > 0) {
+      const int h0 = static_cast<int>(hp * R) % p.flat_h, h1 = static_cast<int>(hp * R + 1) % p.flat_h;
+      m0 = 0u; m1 = 0u;
+#pragma unroll
+      for (int dr = 0; dr < 3; ++dr) {
+        if (h0 + p.org_h + dr >= 0 && h0 + p.org_h + dr < p.flat_h) m0 |= 1u << dr;
+        if (h1 + p.org_h + dr >= 0 && h1 + p.org_h + dr < p.flat_h) m1 |= 1u << dr;
+      }
+    }
     const uint32_t acc = acc_stages == 2 ? (it & 1) : 0;
     const uint32_t acc_phase = acc_stages == 2 ? ((it >> 1) & 1) : (it & 1);
     mbar_wait(&c.tempty[acc], acc_phase ^ 1);
     fence_after_sync();
     const uint32_t d0 = c.tmem_base + acc * R * N, d1 = d0 + N;
+    uint32_t acc0 = 0u, acc1 = 0u;
     for (int cb = 0; cb < NCB; ++cb) {
       mbar_wait(&c.full_p[pstage], pphase);
       fence_after_sync();
@@ -293,21 +309,30 @@ __device__ __forceinline__ void mma_role(const MmaCtx& c) {
           b_lo = sB16 + slot * bslot16;
         }
         const uint64_t ad0 = desc_hi | (a_lo + tap16[t]), ad1 = ad0 + row16, bd = desc_hi | b_lo;
+        const uint32_t drt = static_cast<uint32_t>(p.tap_dr[t]);
+        const bool do0 = (m0 >> drt) & 1u, do1 = two && ((m1 >> drt) & 1u);
+        // acc0 / acc1: has this accumulator row been written in this item yet?  (A skipped tap contributes the zeros the TMA
+        // fill would have contributed, so flat mode gives bit-identical sums.)
         if (leader) {
           if (KKT > 0) {
+            if (do0) {
 #pragma unroll
-            for (int kk = 0; kk < KKT; ++kk) mma_bf16(d0, ad0 + 2 * kk, bd + 2 * kk, idesc, (t | kk) != 0 ? 1u : static_cast<uint32_t>(cb != 0));
-            if (two) {
+              for (int kk = 0; kk < KKT; ++kk) mma_bf16(d0, ad0 + 2 * kk, bd + 2 * kk, idesc, kk != 0 ? 1u : acc0);
+            }
+            if (do1) {
 #pragma unroll
-              for (int kk = 0; kk < KKT; ++kk) mma_bf16(d1, ad1 + 2 * kk, bd + 2 * kk, idesc, (t | kk) != 0 ? 1u : static_cast<uint32_t>(cb != 0));
+              for (int kk = 0; kk < KKT; ++kk) mma_bf16(d1, ad1 + 2 * kk, bd + 2 * kk, idesc, kk != 0 ? 1u : acc1);
             }
           } else {
-            for (int kk = 0; kk < KK; ++kk) mma_bf16(d0, ad0 + 2 * kk, bd + 2 * kk, idesc, (cb | t | kk) != 0);
-            if (two)
-              for (int kk = 0; kk < KK; ++kk) mma_bf16(d1, ad1 + 2 * kk, bd + 2 * kk, idesc, (cb | t | kk) != 0);
+            if (do0)
+              for (int kk = 0; kk < KK; ++kk) mma_bf16(d0, ad0 + 2 * kk, bd + 2 * kk, idesc, kk != 0 ? 1u : acc0);
+            if (do1)
+              for (int kk = 0; kk < KK; ++kk) mma_bf16(d1, ad1 + 2 * kk, bd + 2 * kk, idesc, kk != 0 ? 1u : acc1);
           }
           if (!RES) mma_commit(&c.empty_b[slot]);
         }
+        if (do0) acc0 = 1u;
+        if (do1) acc1 = 1u;
         if (!RES) { if (++slot == static_cast<uint32_t>(nb_slots)) { slot = 0; bphase ^= 1; } }
       }
       if (leader) mma_commit(&c.empty_p[pstage]);
@@ -671,11 +696,24 @@ extern "C" int air_conv_patch_taps_ex3_bf16(const void* a, long long a_ld, int B
   p.pw = max_dc <= PW - TW ? PW : PW_MAX;
   p.bias = bias; p.out2 = out2; p.out2_ld = out2_ld; p.stats = stats;
   p.post_scale = post_scale; p.post_shift = post_shift;
-  for (int t = 0; t < ntaps; ++t) {
+  // flat mode: a plain stride-1, same-size layer whose taps cross rows, odd image height, more than one image
+  static const int flat_env = [] { const char* e = getenv("AIR_PATCH_FLAT"); return (e && e[0] == '0') ? 0 : 1; }();
+  const bool flat = flat_env && B > 1 && (GH & 1) && max_dr > 0 && osh == 1 && osw == 1 && oph == 0 && opw == 0 && GH == OH &&
+                    GW == OW && Hin == GH && Win == GW && org_h <= 0 && org_h + max_dr >= 0 &&
+                    static_cast<long long>(B) * GH < 0x7fffffffLL;
+  p.flat_h = flat ? GH : 0;
+  for (int t = 0; t < MAX_TAPS; ++t) p.tap_dr[t] = 0;
+  for (int k = 0; k < ntaps; ++k) {
+    const int t = k;
     if (tap_dr[t] < 0 || tap_dr[t] > PR - R || tap_dc[t] < 0 || tap_dc[t] > p.pw - TW || tap_slice[t] < 0 || tap_slice[t] >= wtaps)
       return AIR_ERR_ARG;
-    p.tap_off[t] = tap_dr[t] * p.pw + tap_dc[t];
-    p.tap_slice[t] = tap_slice[t];
+    p.tap_off[k] = tap_dr[t] * p.pw + tap_dc[t];
+    p.tap_slice[k] = tap_slice[t];
+    p.tap_dr[k] = tap_dr[t];
+  }
+  if (flat) {                                         // one image of B * GH rows (same addresses: the images are contiguous)
+    Hin = B * GH; GH = B * GH; OH = GH; B = 1;
+    p.B = 1; p.GH = GH; p.OH = OH;
   }
   p.CB = patch_cb(C); p.NCB = C / p.CB; p.WT = (GW + TW - 1) / TW; p.HP = (GH + R - 1) / R;
   p.row_bytes = p.CB * 2; p.layout = p.CB == 64 ? 2 : (p.CB == 32 ? 4 : 6);

@@ -421,3 +421,35 @@ def test_stride2_wgrad_by_parity_classes(name):
     got = dwb.view(Cout, k, k, Cin).permute(0, 3, 1, 2)
     err = (got - ref).abs()
     assert float(err.max()) <= 1e-3 * float(ref.abs().max()) + 1e-3, (name, float(err.max()), float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("shape", [(3, 5, 188, 64, 128), (4, 9, 131, 128, 64), (5, 3, 94, 64, 64)])
+def test_patch_conv_flat_rows_pair_rows_of_neighbouring_images_bit_identically(shape):
+    """Odd image heights: the patch kernel treats the batch as one image of B * H rows, so that the last row of an image
+    shares a work item with the first row of the next one, and skips the taps that would cross the boundary (they would
+    have multiplied the zero padding).  The result is bit-identical to one launch per image, with and without a residual."""
+    from asvspoof2021_air_b200 import ops
+    B, H, W, Cin, Cout = shape
+    g = torch.Generator(device="cpu").manual_seed(41)
+    x = torch.randn(B, H, W, Cin, generator=g).cuda().to(torch.bfloat16)
+    w = (torch.randn(Cout, 3, 3, Cin, generator=g) / (Cin * 9) ** 0.5).cuda()
+    res = torch.randn(B, H, W, Cout, generator=g).cuda().to(torch.bfloat16)
+    wpk = torch.empty(9 * Cin * Cout, device="cuda", dtype=torch.bfloat16)
+    ops.pack3x3(w.contiguous(), Cin, Cout, 0, wpk)
+    for r in (None, res):
+        out = torch.full((B, H, W, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+        ref = torch.full((B, H, W, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+        ops.conv3x3_patch(x, Cin, B, H, W, Cin, wpk, Cout, out, Cout, r, Cout if r is not None else 0, False)
+        for b in range(B):
+            ops.conv3x3_patch(x[b:b + 1], Cin, 1, H, W, Cin, wpk, Cout, ref[b:b + 1], Cout,
+                              None if r is None else r[b:b + 1], Cout if r is not None else 0, False)
+        torch.cuda.synchronize()
+        assert not torch.isnan(out.float()).any()
+        assert torch.equal(out, ref)
+    st = torch.zeros(2 * Cout, device="cuda", dtype=torch.float64)
+    out_s = torch.empty(B, H, W, Cout, device="cuda", dtype=torch.bfloat16)
+    ops.conv3x3_patch_stats(x, Cin, B, H, W, Cin, wpk, Cout, out_s, Cout, res, Cout, False, st)
+    torch.cuda.synchronize()
+    assert torch.equal(out_s, out)
+    o64 = out.double().reshape(-1, Cout)
+    assert torch.allclose(st[:Cout], o64.sum(0), rtol=1e-5, atol=1e-6 * float(o64.abs().sum(0).max()))
