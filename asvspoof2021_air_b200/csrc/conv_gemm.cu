@@ -51,7 +51,7 @@ struct ConvParams {
   const float* post_scale; const float* post_shift;   // optional per-channel affine AFTER the ReLU (eval-mode BatchNorm of conv -> ReLU -> BN)
   int stages; int flags;
   int use_tma;                              // 1x1 / stride 1: the A tile is a plain 2-D box of the activation matrix
-  int stage_out;                            // 1: bf16 outputs leave through per-warp shared-memory tiles + TMA stores
+  int stage_out;                            // 1 / 2: bf16 outputs leave through 1 / 2 shared-memory tiles per epilogue warp + TMA stores
 };
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, const bf16x8& v) {
@@ -121,7 +121,8 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& p, uint32_t tmem
                                               uint32_t stage_tile, const CUtensorMap* tmo) {
   const int row = q * 32 + lane;
   const bool f32 = (p.flags & AIR_CONV_F32_OUT) != 0;       // fp32 parity mode: float storage, no rounding point
-  const uint32_t srow = stage_tile + static_cast<uint32_t>(lane) * 64u, ssw = static_cast<uint32_t>((lane >> 1) & 3);
+  const uint32_t ssw = static_cast<uint32_t>((lane >> 1) & 3);
+  uint32_t tsel = 0;                               // which of the warp's (1 or 2) tiles the next 32-column group uses
   int it = 0;
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
     const int m_tile = tile / p.n_tiles, n_tile = tile % p.n_tiles;
@@ -139,7 +140,8 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& p, uint32_t tmem
         tmem_ld16(taddr + c0 + 16, vb);
         const int n0 = n_tile * p.block_n + c0;
         if (m < p.M) { epilogue_math16(p, m, n0, false, va); epilogue_math16(p, m, n0 + 16, false, vb); }
-        if (lane == 0) bulk_wait_read_all();        // the previous tile of this warp has left shared memory
+        const uint32_t tile = stage_tile + tsel * STAGE_TILE, srow = tile + static_cast<uint32_t>(lane) * 64u;
+        if (lane == 0) { if (p.stage_out == 2) bulk_wait_read_1(); else bulk_wait_read_all(); }   // this tile's previous store has left shared memory
         __syncwarp();
         st_shared_v4(srow + ((0u ^ ssw) << 4), pack8(va));
         st_shared_v4(srow + ((1u ^ ssw) << 4), pack8(va + 8));
@@ -147,7 +149,8 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& p, uint32_t tmem
         st_shared_v4(srow + ((3u ^ ssw) << 4), pack8(vb + 8));
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) { tma_store_2d(tmo, stage_tile, n0, m_tile * BLOCK_M + q * 32); bulk_commit_group(); }
+        if (lane == 0) { tma_store_2d(tmo, tile, n0, m_tile * BLOCK_M + q * 32); bulk_commit_group(); }
+        if (p.stage_out == 2) tsel ^= 1u;
       }
     }
     for (; c0 < c_end; c0 += 16) {
@@ -183,7 +186,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
   uint8_t* sA = smem;
   uint8_t* sB = smem + S * A_STAGE_BYTES;
   uint8_t* sS = sB + S * b_stage_bytes;      // [8 epilogue warps][2 KB] output tiles (stage_out)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sS + (p.stage_out ? 8 * STAGE_TILE : 0));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sS + static_cast<uint32_t>(p.stage_out) * 8 * STAGE_TILE);
   uint64_t* full = bars;               // [S]  128 gather arrivals + 1 expect_tx arrival
   uint64_t* empty = bars + S;          // [S]  tcgen05.commit
   uint64_t* tfull = bars + 2 * S;      // [2]  accumulator ready
@@ -217,7 +220,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
       // quadrants 0-3 too, so they drain the upper half of the accumulator columns
       const int c_begin = ((p.block_n / 16 + 1) / 2) * 16;
       epilogue_role(p, tmem_base, tfull, tempty, warp & 3, lane, c_begin, p.block_n, total_tiles,
-                    p.stage_out ? smem_u32(sS) + static_cast<uint32_t>(4 + (warp & 3)) * STAGE_TILE : 0u, &tma_o);
+                    p.stage_out ? smem_u32(sS) + static_cast<uint32_t>(4 + (warp & 3)) * static_cast<uint32_t>(p.stage_out) * STAGE_TILE : 0u, &tma_o);
     } else
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.n_tiles;
@@ -318,7 +321,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
     // ===================== epilogue: TMEM -> registers -> HBM =====================
     const int c_end = p.use_tma ? ((p.block_n / 16 + 1) / 2) * 16 : p.block_n;
     epilogue_role(p, tmem_base, tfull, tempty, warp & 3, lane, 0, c_end, total_tiles,
-                  p.stage_out ? smem_u32(sS) + static_cast<uint32_t>(warp & 3) * STAGE_TILE : 0u, &tma_o);
+                  p.stage_out ? smem_u32(sS) + static_cast<uint32_t>(warp & 3) * static_cast<uint32_t>(p.stage_out) * STAGE_TILE : 0u, &tma_o);
   }
 
   fence_before_sync();
@@ -453,7 +456,14 @@ extern "C" int air_conv_gemm_bf16_affine(const void* a, long long a_ld, int B, i
   p.stages = stages;
   static const int stage_env = [] { const char* e = getenv("AIR_GEMM_STAGE_OUT"); return (e && e[0] == '0') ? 0 : 1; }();
   p.stage_out = (stage_env && !(flags & AIR_CONV_F32_OUT) && bn % 32 == 0 && p.M < 0x7fffffffLL) ? 1 : 0;
-  const size_t smem = 1024 + static_cast<size_t>(stages) * stage_bytes + (p.stage_out ? 8 * STAGE_TILE : 0) + (2 * stages + 4) * 8 + 16;
+  if (p.stage_out) {
+    // a second tile per epilogue warp (the store of one drains while the next is filled): for the price of one pipeline stage
+    // when there are at least six, for free when it fits anyway
+    auto total = [&](int st, int tiles) { return 1024 + static_cast<size_t>(st) * stage_bytes + tiles * 8 * STAGE_TILE + (2 * st + 4) * 8 + 16; };
+    if (total(stages, 2) <= 227 * 1024) p.stage_out = 2;
+    else if (stages >= 6 && total(stages - 1, 2) <= 227 * 1024) { p.stage_out = 2; p.stages = --stages; }
+  }
+  const size_t smem = 1024 + static_cast<size_t>(stages) * stage_bytes + static_cast<size_t>(p.stage_out) * 8 * STAGE_TILE + (2 * stages + 4) * 8 + 16;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

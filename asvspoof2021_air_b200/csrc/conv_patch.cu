@@ -63,7 +63,7 @@ struct PatchParams {
   uint32_t pstage_bytes, bslot_bytes, bslot_stride;
   int pstages;                          // patch ring depth
   int pr;                               // patch rows actually loaded: R + max tap row offset (2 for 1-D / 1x1 layers)
-  int stage_out;                        // 1: bf16 outputs leave through per-warp shared-memory tiles + TMA stores
+  int stage_out;                        // 1 / 2: bf16 outputs leave through 1 / 2 shared-memory tiles per epilogue warp + TMA stores
   int nb_slots, resident;               // weight ring
   int acc_stages;                       // 1 or 2
   int ntaps; int tap_off[MAX_TAPS]; int tap_slice[MAX_TAPS];     // window offset in patch pixels, weight slice
@@ -209,7 +209,7 @@ __device__ __forceinline__ void epilogue_chunk(const PatchParams& p, uint32_t ta
   if (valid) epilogue_math<NC>(p, pixel, c0, rv, v);
   if (NC == 32 && stage != 0) {
     const int lane = threadIdx.x & 31;
-    if (lane == 0) bulk_wait_read_all();          // the previous tile of this warp has left shared memory
+    if (lane == 0) { if (p.stage_out == 2) bulk_wait_read_1(); else bulk_wait_read_all(); }   // this tile's previous store has left shared memory
     __syncwarp();
     const uint32_t row = stage + static_cast<uint32_t>(lane) * 64u, sw = static_cast<uint32_t>((lane >> 1) & 3);
 #pragma unroll
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_patch_kernel(const __grid_con
   const uint32_t sB = sbase + PSTAGES * p.pstage_bytes;
   uint8_t* gen = smem_raw + (sbase - smem_u32(smem_raw));
   const uint32_t sS = sB + static_cast<uint32_t>(p.nb_slots) * p.bslot_stride;       // [8 epilogue warps][2 KB] output tiles
-  const uint32_t stage_total = p.stage_out ? 8u * STAGE_TILE : 0u;
+  const uint32_t stage_total = static_cast<uint32_t>(p.stage_out) * 8u * STAGE_TILE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(gen + PSTAGES * p.pstage_bytes + static_cast<size_t>(p.nb_slots) * p.bslot_stride + stage_total);
   uint64_t* full_p = bars;                          // [PSTAGES] expect_tx (TMA)
   uint64_t* empty_p = bars + PSTAGES;               // [PSTAGES] tcgen05.commit
@@ -445,7 +445,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_patch_kernel(const __grid_con
     // ===================== epilogue =====================
     const int q = warp & 3, set = (warp - 4) >> 2;      // TMEM lane quarter; parity of the 32-channel blocks this warp drains
     const int m = q * 32 + lane;
-    const uint32_t my_tile = p.stage_out ? sS + static_cast<uint32_t>(warp - 4) * STAGE_TILE : 0u;
+    const uint32_t tile0 = p.stage_out ? sS + static_cast<uint32_t>(warp - 4) * static_cast<uint32_t>(p.stage_out) * STAGE_TILE : 0u;
+    uint32_t tsel = 0;                             // which of the warp's (1 or 2) tiles the next unit uses
     // fused BatchNorm statistics: lane l accumulates channel (32 cb + l) of its warp's pixels in registers, in a fixed
     // order (bit-reproducible run to run); combined per CTA in shared memory and across CTAs with fp64 atomics
     float acc_s[4], acc_q[4];
@@ -486,11 +487,15 @@ __global__ void __launch_bounds__(THREADS, 1) conv_patch_kernel(const __grid_con
       for (int cb = set; cb < cpr; cb += 2) {
         const int c0 = cb << 5;
         float v0[32], v1[32];
+        uint32_t my_tile = tile0 + tsel * STAGE_TILE;
         epilogue_chunk<32>(p, tacc, pix0, c0, val0, ra, v0, st, my_tile);
         if (my_tile && lane == 0) { tma_store_4d(&tmout, my_tile, c0, wt * TW + q * 32, hp * R, b); bulk_commit_group(); }
+        if (p.stage_out == 2) tsel ^= 1u;
         if (rows > 1) {
+          my_tile = tile0 + tsel * STAGE_TILE;
           epilogue_chunk<32>(p, tacc + p.N, pix1, c0, val1, rb, v1, st, my_tile);
           if (my_tile && lane == 0) { tma_store_4d(&tmout, my_tile, c0, wt * TW + q * 32, hp * R + 1, b); bulk_commit_group(); }
+          if (p.stage_out == 2) tsel ^= 1u;
         }
         if (cb + 2 < cpr) { load_res<32>(p, pix0, c0 + 64, val0, ra); if (rows > 1) load_res<32>(p, pix1, c0 + 64, val1, rb); }
         if (st) {                                   // warp-uniform: every lane takes part in the shuffles
@@ -517,7 +522,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_patch_kernel(const __grid_con
       fence_before_sync();
       mbar_arrive(&tempty[acc]);
     }
-    if (my_tile && lane == 0) bulk_wait_all();          // every output tile of this warp has been written
+    if (tile0 && lane == 0) bulk_wait_all();            // every output tile of this warp has been written
     if (s_stats != nullptr) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -740,12 +745,18 @@ extern "C" int air_conv_patch_taps_ex3_bf16(const void* a, long long a_ld, int B
   p.stage_out = 0;
   if (stage_env && !p.f32 && N % 32 == 0) {
     plan(8 * static_cast<int>(STAGE_TILE), slots_s, resident_s);
-    if (resident_s == resident && (slots_s == slots || slots_s >= 3)) { p.stage_out = 1; slots = slots_s; }
+    if (resident_s == resident && (slots_s == slots || slots_s >= 3)) {
+      p.stage_out = 1; const int slots1 = slots_s;
+      // a second tile per warp (the store of one drains while the next is filled) when it costs no weight slot
+      plan(16 * static_cast<int>(STAGE_TILE), slots_s, resident_s);
+      if (resident_s == resident && slots_s == slots1) p.stage_out = 2;
+      slots = slots1;
+    }
   }
   if (slots < 2 && nslices > 1) return AIR_ERR_UNSUPPORTED;
   p.nb_slots = slots; p.resident = resident;
   const size_t smem = 1024 + static_cast<size_t>(PSTAGES) * p.pstage_bytes + static_cast<size_t>(slots) * p.bslot_stride +
-                      (p.stage_out ? 8 * STAGE_TILE : 0) +
+                      static_cast<size_t>(p.stage_out) * 8 * STAGE_TILE +
                       (2 * PSTAGES + 2 * slots + 4) * 8 + 32 + (stats ? 4 * 2 * static_cast<size_t>(N) * sizeof(float) : 0);
   CUtensorMap tm, tmo;
   int tr = air_tmap::make_act_tmap(&tm, a, a_ld, B, Hin, Win, C, p.CB, p.pw, p.pr, p.row_bytes);
