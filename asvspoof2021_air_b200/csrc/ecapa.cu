@@ -204,13 +204,14 @@ __global__ void __launch_bounds__(256) scale_residual_kernel(const AT* __restric
                                                               const float* __restrict__ g, const AT* __restrict__ res,
                                                               long long res_ld, AT* __restrict__ out, long long out_ld,
                                                               long long M, int T, int C) {
-  const int cpr = C >> 3;
-  const long long total = M * cpr;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long m = i / cpr;
-    const int c0 = static_cast<int>(i - m * cpr) * 8;
-    const long long b = m / T;
+  // 32-bit index arithmetic (the launcher checks M * C / 8 < 2^31): the two 64-bit divisions per 16-byte chunk of the first
+  // version cost more instructions than the load, the FMA and the store together
+  const uint32_t cpr = static_cast<uint32_t>(C) >> 3;
+  const uint32_t total = static_cast<uint32_t>(M) * cpr;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint32_t mi = i / cpr;
+    const int c0 = static_cast<int>(i - mi * cpr) * 8;
+    const long long m = mi, b = mi / static_cast<uint32_t>(T);
     float f[8], r[8];
     ld8(x + m * x_ld + c0, f);
     if (res) ld8(res + m * res_ld + c0, r);
@@ -258,14 +259,13 @@ template <typename AT>
 __global__ void __launch_bounds__(256) se_apply_bwd_kernel(const AT* __restrict__ dout, long long d_ld,
                                                             const float* __restrict__ g, const float* __restrict__ ds,
                                                             AT* __restrict__ dx, long long dx_ld, long long M, int T, int C) {
-  const int cpr = C >> 3;
-  const long long total = M * cpr;
+  const uint32_t cpr = static_cast<uint32_t>(C) >> 3;            // 32-bit index arithmetic, see scale_residual_kernel
+  const uint32_t total = static_cast<uint32_t>(M) * cpr;
   const float invT = 1.f / T;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long m = i / cpr;
-    const int c0 = static_cast<int>(i - m * cpr) * 8;
-    const long long b = m / T;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint32_t mi = i / cpr;
+    const int c0 = static_cast<int>(i - mi * cpr) * 8;
+    const long long m = mi, b = mi / static_cast<uint32_t>(T);
     float f[8];
     ld8(dout + m * d_ld + c0, f);
 #pragma unroll
@@ -350,12 +350,12 @@ template <typename AT>
 __global__ void __launch_bounds__(256) copy_channels_kernel(const AT* __restrict__ src, long long s_ld,
                                                              const AT* __restrict__ mask, long long m_ld,
                                                              AT* __restrict__ dst, long long d_ld, long long M, int C) {
-  const int cpr = C >> 3;
-  const long long total = M * cpr;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long m = i / cpr;
-    const int c0 = static_cast<int>(i - m * cpr) * 8;
+  const uint32_t cpr = static_cast<uint32_t>(C) >> 3;            // 32-bit index arithmetic, see scale_residual_kernel
+  const uint32_t total = static_cast<uint32_t>(M) * cpr;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint32_t mi = i / cpr;
+    const int c0 = static_cast<int>(i - mi * cpr) * 8;
+    const long long m = mi;
     V8<AT> v = ldv8(src + m * s_ld + c0);
     if (mask) {
       float f[8], k[8];
@@ -502,6 +502,7 @@ static int scale_residual_fwd_impl(const void* x, long long x_ld, const float* g
                                       void* out, long long out_ld, int B, int T, int C, cudaStream_t stream) {
   if (!x || !gate || !out || B <= 0 || T <= 0 || C % 8 != 0 || (x_ld | out_ld) % 8 != 0 || (res && res_ld % 8 != 0)) return AIR_ERR_ARG;
   const long long M = static_cast<long long>(B) * T;
+  if (M * (C / 8) >= 0x7fffffffLL) return AIR_ERR_UNSUPPORTED;            // 32-bit chunk index in the kernel
   scale_residual_kernel<AT><<<ew_grid(M * (C / 8), 256 * 4), 256, 0, stream>>>(
       reinterpret_cast<const AT*>(x), x_ld, gate, reinterpret_cast<const AT*>(res), res_ld,
       reinterpret_cast<AT*>(out), out_ld, M, T, C);
@@ -539,6 +540,7 @@ static int se_apply_bwd_impl(const void* dout, long long d_ld, const float* gate
                                 int B, int T, int C, cudaStream_t stream) {
   if (!dout || !gate || !dmean || !dx || B <= 0 || T <= 0 || C % 8 != 0 || (d_ld | dx_ld) % 8 != 0) return AIR_ERR_ARG;
   const long long M = static_cast<long long>(B) * T;
+  if (M * (C / 8) >= 0x7fffffffLL) return AIR_ERR_UNSUPPORTED;            // 32-bit chunk index in the kernel
   se_apply_bwd_kernel<AT><<<ew_grid(M * (C / 8), 256 * 4), 256, 0, stream>>>(
       reinterpret_cast<const AT*>(dout), d_ld, gate, dmean, reinterpret_cast<AT*>(dx), dx_ld, M, T, C);
   return air_launch_status();
@@ -585,6 +587,7 @@ template <typename AT>
 static int copy_channels_impl(const void* src, long long s_ld, const void* mask, long long m_ld, void* dst, long long d_ld,
                                  long long M, int C, cudaStream_t stream) {
   if (!src || !dst || M <= 0 || C % 8 != 0 || (s_ld | d_ld) % 8 != 0 || (mask && m_ld % 8 != 0)) return AIR_ERR_ARG;
+  if (M * (C / 8) >= 0x7fffffffLL) return AIR_ERR_UNSUPPORTED;            // 32-bit chunk index in the kernel
   copy_channels_kernel<AT><<<ew_grid(M * (C / 8), 256 * 4), 256, 0, stream>>>(
       reinterpret_cast<const AT*>(src), s_ld, reinterpret_cast<const AT*>(mask), m_ld,
       reinterpret_cast<AT*>(dst), d_ld, M, C);
