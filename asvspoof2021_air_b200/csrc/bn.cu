@@ -112,14 +112,18 @@ __global__ void __launch_bounds__(THREADS) bn_apply_kernel(const ApplyParams<T> 
     scale[k] = g * invstd;
     shift[k] = be - mean * g * invstd;
   }
+  // Rows are walked from the END of the tensor: the kernel that produced x (a persistent conv grid, items in ascending
+  // order) wrote its tail last, so that part is still in the 126 MB L2; and this kernel's own last writes are then the HEAD
+  // of y, which the consumer (a conv walking its items in ascending order) reads first.
   const long long step = static_cast<long long>(gridDim.x) * rows_per_it;
-  long long m = static_cast<long long>(blockIdx.x) * rows_per_it + tr;
+  long long mi = static_cast<long long>(blockIdx.x) * rows_per_it + tr;      // mirrored row index: row = M - 1 - mi
+  const long long last = p.M - 1;
   const int c0 = tc * 8;
   if (!p.y2) {
-    for (; m + 3 * step < p.M; m += 4 * step) {            // four independent loads in flight before the first store
+    for (; mi + 3 * step < p.M; mi += 4 * step) {          // four independent loads in flight before the first store
       V8<T> v[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = ldv8(p.x + (m + u * step) * p.x_ld + c0);
+      for (int u = 0; u < 4; ++u) v[u] = ldv8(p.x + (last - (mi + u * step)) * p.x_ld + c0);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         float f[8];
@@ -129,11 +133,12 @@ __global__ void __launch_bounds__(THREADS) bn_apply_kernel(const ApplyParams<T> 
           f[k] = fmaf(f[k], scale[k], shift[k]);
           if (p.relu) f[k] = fmaxf(f[k], 0.f);
         }
-        st8(p.y + (m + u * step) * p.y_ld + c0, f);
+        st8(p.y + (last - (mi + u * step)) * p.y_ld + c0, f);
       }
     }
   }
-  for (; m < p.M; m += step) {
+  for (; mi < p.M; mi += step) {
+    const long long m = last - mi;
     float f[8];
     unpack8(ldv8(p.x + m * p.x_ld + c0), f);
 #pragma unroll
@@ -194,8 +199,11 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_reduce_kernel(const BwdParams<
       for (int u = 0; u < U; ++u) {
         const long long mm = m + u * step;
         if (mm < p.M) {
-          gv[u] = ldv8(p.dy + mm * p.dy_ld + tc * 8);
-          xq[u] = ldv8(p.x + mm * p.x_ld + tc * 8);
+          // rows from the END first: dy was just written by a data-gradient kernel whose tail is still in L2, and the
+          // second pass (bn_bwd_apply, ascending) then finds the head of dy / x that this pass read last
+          const long long row = p.M - 1 - mm;
+          gv[u] = ldv8(p.dy + row * p.dy_ld + tc * 8);
+          xq[u] = ldv8(p.x + row * p.x_ld + tc * 8);
           n = u + 1;
         }
       }
