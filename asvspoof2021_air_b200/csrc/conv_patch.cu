@@ -249,8 +249,8 @@ struct MmaCtx {
 };
 
 // The MMA warp.  NT = taps (0: run-time p.ntaps), KKT = K = 16 steps per channel block (0: run-time), RES = all weight slices
-// resident (waited for once) or streamed through the slot ring.
-template <int NT, int KKT, bool RES>
+// resident (waited for once) or streamed through the slot ring, FLAT = flat row mode (per-row tap masks; compiled out otherwise).
+template <int NT, int KKT, bool RES, bool FLAT>
 __device__ __forceinline__ void mma_role(const MmaCtx& c) {
   const PatchParams& p = c.p;
   const bool leader = elect_one();
@@ -277,7 +277,7 @@ __device__ __forceinline__ void mma_role(const MmaCtx& c) {
     const uint32_t hp = (item / WT) % HP;
     const bool two = GH - static_cast<int>(hp) * R >= 2;
     uint32_t m0 = 7u, m1 = 7u;                    // per-row masks of the tap row offsets that apply (flat mode)
-    if (p.flat_h > 0) {
+    if (FLAT) {
       const int h0 = static_cast<int>(hp * R) % p.flat_h, h1 = static_cast<int>(hp * R + 1) % p.flat_h;
       m0 = 0u; m1 = 0u;
 #pragma unroll
@@ -309,19 +309,19 @@ __device__ __forceinline__ void mma_role(const MmaCtx& c) {
           b_lo = sB16 + slot * bslot16;
         }
         const uint64_t ad0 = desc_hi | (a_lo + tap16[t]), ad1 = ad0 + row16, bd = desc_hi | b_lo;
-        const uint32_t drt = static_cast<uint32_t>(p.tap_dr[t]);
-        const bool do0 = (m0 >> drt) & 1u, do1 = two && ((m1 >> drt) & 1u);
+        const uint32_t drt = FLAT ? static_cast<uint32_t>(p.tap_dr[t]) : 0u;
+        const bool do0 = !FLAT || ((m0 >> drt) & 1u), do1 = two && (!FLAT || ((m1 >> drt) & 1u));
         // acc0 / acc1: has this accumulator row been written in this item yet?  (A skipped tap contributes the zeros the TMA
         // fill would have contributed, so flat mode gives bit-identical sums.)
         if (leader) {
           if (KKT > 0) {
             if (do0) {
 #pragma unroll
-              for (int kk = 0; kk < KKT; ++kk) mma_bf16(d0, ad0 + 2 * kk, bd + 2 * kk, idesc, kk != 0 ? 1u : acc0);
+              for (int kk = 0; kk < KKT; ++kk) mma_bf16(d0, ad0 + 2 * kk, bd + 2 * kk, idesc, kk != 0 ? 1u : (FLAT ? acc0 : (t != 0 ? 1u : static_cast<uint32_t>(cb != 0))));
             }
             if (do1) {
 #pragma unroll
-              for (int kk = 0; kk < KKT; ++kk) mma_bf16(d1, ad1 + 2 * kk, bd + 2 * kk, idesc, kk != 0 ? 1u : acc1);
+              for (int kk = 0; kk < KKT; ++kk) mma_bf16(d1, ad1 + 2 * kk, bd + 2 * kk, idesc, kk != 0 ? 1u : (FLAT ? acc1 : (t != 0 ? 1u : static_cast<uint32_t>(cb != 0))));
             }
           } else {
             if (do0)
@@ -428,18 +428,24 @@ __global__ void __launch_bounds__(THREADS, 1) conv_patch_kernel(const __grid_con
     // 32-64 cycles), which bounded every layer with N <= 128.
     const int KK = p.CB >> 4;
     const MmaCtx c{p, sP, sB, tmem_base, full_p, empty_p, full_b, empty_b, tfull, tempty};
-    if (p.resident && KK == 4 && p.ntaps == 9) mma_role<9, 4, true>(c);
-    else if (p.resident && KK == 4 && p.ntaps == 4) mma_role<4, 4, true>(c);
-    else if (p.resident && KK == 4 && p.ntaps == 3) mma_role<3, 4, true>(c);
-    else if (p.resident && KK == 4 && p.ntaps == 2) mma_role<2, 4, true>(c);
-    else if (p.resident && KK == 4 && p.ntaps == 1) mma_role<1, 4, true>(c);
-    else if (p.resident && KK == 1 && p.ntaps == 9) mma_role<9, 1, true>(c);
-    else if (p.resident && KK == 1 && p.ntaps == 1) mma_role<1, 1, true>(c);
-    else if (!p.resident && KK == 4 && p.ntaps == 9) mma_role<9, 4, false>(c);
-    else if (!p.resident && KK == 4 && p.ntaps == 4) mma_role<4, 4, false>(c);
-    else if (!p.resident && KK == 4 && p.ntaps == 2) mma_role<2, 4, false>(c);
-    else if (p.resident) mma_role<0, 0, true>(c);
-    else mma_role<0, 0, false>(c);
+    if (p.flat_h > 0) {                               // odd-height 3x3 layers (layer 2 / layer 3 geometries)
+      if (p.resident && KK == 4 && p.ntaps == 9) mma_role<9, 4, true, true>(c);
+      else if (!p.resident && KK == 4 && p.ntaps == 9) mma_role<9, 4, false, true>(c);
+      else if (p.resident) mma_role<0, 0, true, true>(c);
+      else mma_role<0, 0, false, true>(c);
+    }
+    else if (p.resident && KK == 4 && p.ntaps == 9) mma_role<9, 4, true, false>(c);
+    else if (p.resident && KK == 4 && p.ntaps == 4) mma_role<4, 4, true, false>(c);
+    else if (p.resident && KK == 4 && p.ntaps == 3) mma_role<3, 4, true, false>(c);
+    else if (p.resident && KK == 4 && p.ntaps == 2) mma_role<2, 4, true, false>(c);
+    else if (p.resident && KK == 4 && p.ntaps == 1) mma_role<1, 4, true, false>(c);
+    else if (p.resident && KK == 1 && p.ntaps == 9) mma_role<9, 1, true, false>(c);
+    else if (p.resident && KK == 1 && p.ntaps == 1) mma_role<1, 1, true, false>(c);
+    else if (!p.resident && KK == 4 && p.ntaps == 9) mma_role<9, 4, false, false>(c);
+    else if (!p.resident && KK == 4 && p.ntaps == 4) mma_role<4, 4, false, false>(c);
+    else if (!p.resident && KK == 4 && p.ntaps == 2) mma_role<2, 4, false, false>(c);
+    else if (p.resident) mma_role<0, 0, true, false>(c);
+    else mma_role<0, 0, false, false>(c);
     __syncwarp();
   } else if (warp >= 4) {
     // ===================== epilogue =====================
