@@ -30,10 +30,14 @@ using namespace tc05;
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;      // 16 KB
-constexpr int ROWS_PER_THREAD = 8;                        // thread t: chunk t & 7 of rows (t >> 3) + 16 i
-constexpr int NUM_A_THREADS = 128;
+constexpr int GATHER_WARPS = 8;                           // ncu: with four, each gather warp issued one instruction per ~4.5 cycles
+                                                          // all tile long (a single warp's limit) while the tensor pipe idled at 18 %
+constexpr int NUM_A_THREADS = 32 * GATHER_WARPS;
+constexpr int ROW_STEP = NUM_A_THREADS / 8;               // thread t: chunk t & 7 of rows (t >> 3) + ROW_STEP i
+constexpr int ROWS_PER_THREAD = 128 / ROW_STEP;
 constexpr uint32_t STAGE_TILE = 2048;                     // one epilogue warp's output tile: 32 rows x 32 channels bf16
-constexpr int THREADS = 320;                              // 4 gather warps, TMA warp, MMA warp, 4 epilogue warps
+constexpr int W_LOAD = GATHER_WARPS, W_MMA = GATHER_WARPS + 1;      // warp indices of the weight / TMA loader and the MMA issuer
+constexpr int THREADS = 32 * (GATHER_WARPS + 6);          // gather warps, loader warp, MMA warp, 4 epilogue warps
 
 struct ConvParams {
   const __nv_bfloat16* a; long long a_ld;   // gather source, elements between consecutive pixels
@@ -201,7 +205,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], p.use_tma ? 256 : 128); }
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc(tmem_slot, ncols);
+  if (warp == W_MMA) tmem_alloc(tmem_slot, ncols);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -209,18 +213,20 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
 
   const int total_tiles = p.m_tiles * p.n_tiles;
 
-  if (warp < 4) {
+  if (warp < GATHER_WARPS) {
     // ===================== A gather producers: 8 lanes per im2col row =====================
     const int c = threadIdx.x & 7, r0 = threadIdx.x >> 3;            // chunk of the K block, first row
     uint32_t stage = 0, phase = 0;
-    // destination of row r0 + 16 i, chunk c:  row * 128 + ((c ^ (row & 7)) << 4); (r0 + 16 i) & 7 == r0 & 7
+    // destination of row r0 + ROW_STEP i, chunk c:  row * 128 + ((c ^ (row & 7)) << 4); (r0 + ROW_STEP i) & 7 == r0 & 7
     const uint32_t dst0 = smem_u32(sA) + r0 * 128 + ((c ^ (r0 & 7)) << 4);
     if (p.use_tma) {
-      // 1x1 / stride-1 layer: no gather (warp 4 issues one TMA box per K block); these four warps own TMEM lane
-      // quadrants 0-3 too, so they drain the upper half of the accumulator columns
-      const int c_begin = ((p.block_n / 16 + 1) / 2) * 16;
-      epilogue_role(p, tmem_base, tfull, tempty, warp & 3, lane, c_begin, p.block_n, total_tiles,
-                    p.stage_out ? smem_u32(sS) + static_cast<uint32_t>(4 + (warp & 3)) * static_cast<uint32_t>(p.stage_out) * STAGE_TILE : 0u, &tma_o);
+      // 1x1 / stride-1 layer: no gather (the loader warp issues one TMA box per K block); the first four of these warps own
+      // TMEM lane quadrants 0-3 too, so they drain the upper half of the accumulator columns (the other four stay idle)
+      if (warp < 4) {
+        const int c_begin = ((p.block_n / 16 + 1) / 2) * 16;
+        epilogue_role(p, tmem_base, tfull, tempty, warp & 3, lane, c_begin, p.block_n, total_tiles,
+                      p.stage_out ? smem_u32(sS) + static_cast<uint32_t>(4 + (warp & 3)) * static_cast<uint32_t>(p.stage_out) * STAGE_TILE : 0u, &tma_o);
+      }
     } else
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.n_tiles;
@@ -228,7 +234,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
       int hb[ROWS_PER_THREAD], wb[ROWS_PER_THREAD]; long long rbase[ROWS_PER_THREAD]; uint32_t okmask = 0;
 #pragma unroll
       for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-        const long long m = static_cast<long long>(m_tile) * BLOCK_M + r0 + 16 * i;
+        const long long m = static_cast<long long>(m_tile) * BLOCK_M + r0 + ROW_STEP * i;
         int wo = 0, ho = 0, bb = 0;
         if (m < p.M) { okmask |= 1u << i; wo = static_cast<int>(m % p.Wo); const long long t = m / p.Wo; ho = static_cast<int>(t % p.Ho); bb = static_cast<int>(t / p.Ho); }
         hb[i] = p.mode == 0 ? ho * p.sh - p.ph : ho + p.ph;
@@ -252,7 +258,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
           for (int i = 0; i < ROWS_PER_THREAD; ++i) {
             const int hi = hb[i] + dhh, wi = wb[i] + dww;
             const bool ok = k_ok && ((okmask >> i) & 1u) && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W;
-            cp_async16(dst + i * (16 * 128), ok ? p.a + rbase[i] + delta : p.a, ok ? 16u : 0u);
+            cp_async16(dst + i * (ROW_STEP * 128), ok ? p.a + rbase[i] + delta : p.a, ok ? 16u : 0u);
           }
         } else {
 #pragma unroll
@@ -262,14 +268,14 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
             const int hi = hn / p.sh, wi = wn / p.sw;
             ok = ok && hi < p.H && wi < p.W;
             const long long off = (rbase[i] / p.a_ld - (static_cast<long long>(hb[i]) * p.W + wb[i]) + static_cast<long long>(hi) * p.W + wi) * p.a_ld + ci;
-            cp_async16(dst + i * (16 * 128), ok ? p.a + off : p.a, ok ? 16u : 0u);
+            cp_async16(dst + i * (ROW_STEP * 128), ok ? p.a + off : p.a, ok ? 16u : 0u);
           }
         }
         cp_async_arrive_noinc(&full[stage]);
         if (++stage == static_cast<uint32_t>(S)) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == W_LOAD) {
     // ===================== weight tiles: one bulk copy per K block =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
@@ -287,7 +293,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == W_MMA) {
     // ===================== MMA issuer (warp-uniform loop: descriptors in uniform registers, elected lane issues) =====================
     const bool leader = elect_one();
     const uint32_t idesc = instr_desc_bf16(BLOCK_M, p.block_n, 0, 0);
@@ -326,7 +332,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
 
   fence_before_sync();
   __syncthreads();
-  if (warp == 5) { fence_after_sync(); tmem_dealloc(tmem_base, ncols); }
+  if (warp == W_MMA) { fence_after_sync(); tmem_dealloc(tmem_base, ncols); }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -39,6 +39,11 @@ elif kind == "gemm1x1":             # 1x1 / stride-1 layer of ECAPA (B, 1, T, C)
     w1 = torch.randn(N, 1, C, device="cuda") / C ** 0.5
     wpk = ops.pack_weights(w1.contiguous(), 0, C, N, 1)
     f = lambda: ops.conv_gemm(x, C, B, H, W, C, H, W, 1, 1, 1, 1, 0, 0, 1, 1, 0, wpk, N, C, out, N)
+elif kind == "gemm_s2":              # stride-2 3x3 / pad 1 layer (first conv of a down-sampling block) on the generic gather kernel
+    Ho, Wo = (H + 1) // 2, (W + 1) // 2
+    wpk = ops.pack_weights(w.reshape(N, 9, C).contiguous(), 0, C, N, 9)
+    out = torch.empty(B, Ho, Wo, N, device="cuda", dtype=torch.bfloat16)
+    f = lambda: ops.conv_gemm(x, C, B, H, W, C, Ho, Wo, 3, 3, 2, 2, 1, 1, 1, 1, 0, wpk, N, 9 * C, out, N)
 elif kind == "gemm":
     wpk = ops.pack_weights(w.reshape(N, 9, C).contiguous(), 0, C, N, 9)
     f = lambda: ops.conv_gemm(x, C, B, H, W, C, H, W, 3, 3, 1, 1, 1, 1, 1, 1, 0, wpk, N, 9 * C, out, N)
@@ -63,4 +68,4 @@ e1.record()
 host_us = (time.perf_counter() - t0) / NIT * 1e6
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / NIT
-print("%s B=%d H=%d W=%d C=%d N=%d: %.3f ms  %.1f TFLOP/s  (host %.0f us/launch)" % (kind, B, H, W, C, N, ms, 2.0 * B * H * W * C * N * (1 if kind == 'gemm1x1' else 9) / ms / 1e9, host_us))
+print("%s B=%d H=%d W=%d C=%d N=%d: %.3f ms  %.1f TFLOP/s  (host %.0f us/launch)" % (kind, B, H, W, C, N, ms, 2.0 * B * H * W * C * N * (1 if kind == 'gemm1x1' else 9) / (4 if kind == 'gemm_s2' else 1) / ms / 1e9, host_us))
