@@ -11,7 +11,7 @@
 //
 // A is never materialised: 128 producer threads gather the 128 x 64 im2col tile of a K block with zero-filling
 // 16-byte cp.async straight into the SWIZZLE_128B K-major operand image (one 128-byte row per output pixel).
-// Eight consecutive lanes copy the eight 16-byte chunks of ONE row, so a warp instruction reads four contiguous
+// (eight gather warps, 256 threads).  Eight consecutive lanes copy the eight 16-byte chunks of ONE row, so a warp instruction reads four contiguous
 // 128-byte segments of global memory and writes four consecutive shared-memory rows (the previous one-row-per-lane
 // mapping cost 64 LSU wavefronts per instruction and made the gather the bottleneck).
 // Pre-packed, pre-swizzled weight tiles arrive with one bulk copy per K block on the TMA engine.  One elected
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
   uint64_t* full = bars;               // [S]  128 gather arrivals + 1 expect_tx arrival
   uint64_t* empty = bars + S;          // [S]  tcgen05.commit
   uint64_t* tfull = bars + 2 * S;      // [2]  accumulator ready
-  uint64_t* tempty = bars + 2 * S + 2; // [2]  accumulator drained (128 epilogue threads)
+  uint64_t* tempty = bars + 2 * S + 2; // [2]  accumulator drained (128 epilogue threads; 256 in TMA mode)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
 
   uint32_t ncols = 32;

@@ -16,7 +16,7 @@
 // (oph, opw): each class only sees the 1 / 2 / 2 / 4 taps that are structurally non-zero for it, so no
 // zero-stuffed gather is ever made; a 1x1 layer is the single-tap case.
 //
-// Roles (256 threads): warp 0 issues the patch TMA loads, warp 1 streams pre-swizzled weight slices (one
+// Roles (384 threads): warp 0 issues the patch TMA loads, warp 1 streams pre-swizzled weight slices (one
 // bulk copy per (channel block, tap); all slices stay resident when they fit), warp 2 issues tcgen05.mma
 // (M = 128 pixels, N = output channels, K = 16 per instruction; the whole warp runs the warp-uniform loop so
 // descriptors live in uniform registers, one elected lane issues), warps 4-11 drain the double-buffered TMEM
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_patch_kernel(const __grid_con
   uint64_t* tfull = empty_b + p.nb_slots;           // [2]
   uint64_t* tempty = tfull + 2;                     // [2] 256 epilogue threads
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* s_stats = p.stats ? reinterpret_cast<float*>(tmem_slot + 4) : nullptr;      // [4 epilogue warps][2][N] partial sums
+  float* s_stats = p.stats ? reinterpret_cast<float*>(tmem_slot + 4) : nullptr;      // [4 TMEM lane quarters][2][N] partial sums (each quarter's two warps own disjoint channel blocks)
 
   uint32_t ncols = 32;
   while (ncols < static_cast<uint32_t>(p.acc_stages * R * p.N)) ncols <<= 1;
