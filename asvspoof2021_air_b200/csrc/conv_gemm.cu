@@ -9,10 +9,10 @@
 //   dgrad : dx [m, n]  = sum_k  A'[m, k] * Wd[n, k]     m = (b, h, w),   k = (tap, co), n = ci
 //   wgrad : dW [n, k] += sum_m  dy[m, n] * A[m, k]      (conv_wgrad.cu)
 //
-// A is never materialised: 128 producer threads gather the 128 x 64 im2col tile of a K block with zero-filling
-// 16-byte cp.async straight into the SWIZZLE_128B K-major operand image (one 128-byte row per output pixel).
-// (eight gather warps, 256 threads).  Eight consecutive lanes copy the eight 16-byte chunks of ONE row, so a warp instruction reads four contiguous
-// 128-byte segments of global memory and writes four consecutive shared-memory rows (the previous one-row-per-lane
+// A is never materialised: 256 producer threads (eight gather warps) gather the 128 x 64 im2col tile of a K block with
+// zero-filling 16-byte cp.async straight into the SWIZZLE_128B K-major operand image (one 128-byte row per output pixel).
+// Eight consecutive lanes copy the eight 16-byte chunks of ONE row, so a warp instruction reads four contiguous
+// 128-byte segments of global memory and writes four consecutive shared-memory rows (the first one-row-per-lane
 // mapping cost 64 LSU wavefronts per instruction and made the gather the bottleneck).
 // Pre-packed, pre-swizzled weight tiles arrive with one bulk copy per K block on the TMA engine.  One elected
 // thread issues tcgen05.mma (M = 128, N = block_n <= 256, K = 16 x 4 per stage); accumulators are
