@@ -48,6 +48,8 @@ struct WParams {
   int pw;                                           // patch width in pixels (tw + 2, or tw + 8 for dilated 1-D taps)
   int R;                                            // rows per item: 2, or 3 when H = 3 and the wider stage fits (tw = 96)
   int xr;                                           // x patch rows actually loaded: R + largest tap row offset
+  int nbw;                                          // 64-channel dy images per job (1, or 2 = 128-column accumulators when <= 4 accumulators)
+  uint32_t dy_img_bytes;                            // one dy image [R][tw][64 channels] in shared memory (1024-aligned)
   uint32_t x_bytes, stage_bytes;
   int nacc; int acc_off[NACC]; int acc_lbo[NACC];   // per accumulator: window offset / group distance, in patch pixels
   int acc_tap[NACC][8];                             // tap of each M row group (-1: not a real tap)
@@ -66,7 +68,8 @@ __device__ __forceinline__ void wgrad_mma_role(const WCtx& c) {
   const WParams& p = c.p;
   const bool leader = elect_one();
   const int nacc = NA > 0 ? NA : p.nacc, ksteps = KS > 0 ? KS : p.tw / 16, rows = p.R;
-  const uint32_t idesc = instr_desc_bf16(128, ACC_COLS, 1, 1);
+  const int acc_cols = ACC_COLS * p.nbw;                 // 64, or 128: two dy images chained through the B descriptor's LBO
+  const uint32_t idesc = instr_desc_bf16(128, acc_cols, 1, 1);
   // descriptor high words: SBO = next 8 pixels, version 1, swizzle mode (A: 128 B or 32 B rows; B: always 128 B rows)
   const uint32_t b_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
   const uint32_t a_hi = NARROW ? ((256u >> 4) | (1u << 14) | (6u << 29)) : b_hi;
@@ -77,7 +80,7 @@ __device__ __forceinline__ void wgrad_mma_role(const WCtx& c) {
   for (int a = 0; a < NACC; ++a)
     abase[a] = (static_cast<uint64_t>(a_hi) << 32) |
                ((static_cast<uint32_t>(p.acc_off[a]) * upp) | ((static_cast<uint32_t>(p.acc_lbo[a]) * upp) << 16));
-  const uint64_t bbase = (static_cast<uint64_t>(b_hi) << 32) | (1u << 16);
+  const uint64_t bbase = (static_cast<uint64_t>(b_hi) << 32) | ((p.nbw > 1 ? (p.dy_img_bytes >> 4) : 1u) << 16);
   const uint32_t stage16 = p.stage_bytes >> 4, xb16 = p.x_bytes >> 4;
   const uint32_t xrow16 = static_cast<uint32_t>(p.pw) * upp, drow16 = static_cast<uint32_t>(p.tw) * 8u;
   const uint32_t s16 = (c.sbase >> 4) & 0x3FFF;
@@ -97,7 +100,7 @@ __device__ __forceinline__ void wgrad_mma_role(const WCtx& c) {
 #pragma unroll
           for (int a = 0; a < NACC; ++a) {
             if (a < nacc)
-              mma_bf16(c.tmem_base + a * ACC_COLS, abase[a] + (xr + static_cast<uint32_t>(ks) * 16u * upp),
+              mma_bf16(c.tmem_base + a * acc_cols, abase[a] + (xr + static_cast<uint32_t>(ks) * 16u * upp),
                        bd0 + static_cast<uint32_t>(ks) * 128u, idesc, (k | static_cast<uint32_t>(r) | static_cast<uint32_t>(ks)) != 0);
           }
         }
@@ -151,9 +154,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_wgrad_patch_kernel(const _
         const int w0 = static_cast<int>(wt) * p.tw, h0 = static_cast<int>(r1 % HP) * p.R, b = static_cast<int>(r1 / HP);
         mbar_wait(&empty[stage], phase ^ 1);
         const uint32_t dst = sbase + stage * p.stage_bytes;
-        mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>(p.xr * p.pw) * (p.narrow ? 32u : 128u) + static_cast<uint32_t>(p.R * p.tw) * 128u);
+        mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>(p.xr * p.pw) * (p.narrow ? 32u : 128u) +
+                                                static_cast<uint32_t>(p.nbw) * static_cast<uint32_t>(p.R * p.tw) * 128u);
         tma_load_4d(dst, &tmx, p.narrow ? 0 : cb * 64, w0 + p.org_w, h0 + p.org_h, b, &full[stage]);
-        tma_load_4d(dst + p.x_bytes, &tmdy, nb * 64, w0, h0, b, &full[stage]);
+        for (int j = 0; j < p.nbw; ++j)
+          tma_load_4d(dst + p.x_bytes + j * p.dy_img_bytes, &tmdy, (nb * p.nbw + j) * 64, w0, h0, b, &full[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -181,12 +186,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_wgrad_patch_kernel(const _
       const int ci = p.narrow ? (m & 15) : (cb * 64 + (m & 63));
       for (int a = 0; a < p.nacc; ++a) {
         const int tap = p.acc_tap[a][grp];
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * ACC_COLS;
-        for (int c0 = 0; c0 < ACC_COLS; c0 += 16) {
+        const int acc_cols = ACC_COLS * p.nbw;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * acc_cols;
+        for (int c0 = 0; c0 < acc_cols; c0 += 16) {
           float v[16];
           tmem_ld16(taddr + c0, v);
           if (tap >= 0) {
-            float* dst = p.dw + static_cast<long long>(nb * 64 + c0) * p.dw_ld + static_cast<long long>(tap) * p.C + ci;
+            float* dst = p.dw + static_cast<long long>(nb * acc_cols + c0) * p.dw_ld + static_cast<long long>(tap) * p.C + ci;
 #pragma unroll
             for (int i = 0; i < 16; ++i) atomicAdd(dst + static_cast<long long>(i) * p.dw_ld, v[i]);
           }
@@ -242,9 +248,24 @@ static int launch_wgrad_patch(const void* x, long long x_ld, int B, int H, int W
   int max_dr = 0;
   for (int t = 0; t < ntaps; ++t) { if (tap_dr[t] > 2) return AIR_ERR_ARG; max_dr = std::max(max_dr, tap_dr[t]); }
   p.xr = p.R + max_dr;
-  p.NCB = p.narrow ? 1 : C / 64; p.NNB = N / 64; p.WT = (W + p.tw - 1) / p.tw; p.HP = (H + p.R - 1) / p.R;
+  // 128-column accumulators (two dy images per job, chained through the B descriptor's leading byte offset): an M = 128,
+  // N = 64 instruction reads 4 KB + 2 KB of operands for 32 cycles of tensor work, N = 128 reads 4 KB + 4 KB for 64, and the
+  // x patch is loaded once per 128 output channels instead of once per 64.  Needs <= 4 accumulators (512 TMEM columns: the
+  // 1 / 2 / 4-tap parity classes of the stride-2 layers, 1x1 layers) and two stages in shared memory (96-pixel tiles if needed).
+  static const int wide_env = [] { const char* e = getenv("AIR_WGRAD_WIDE"); return (e && e[0] == '0') ? 0 : 1; }();
+  p.nbw = 1;
+  auto x_bytes_of = [&](int tw) { return (static_cast<uint32_t>(p.xr * (tw + (max_dc <= 2 ? 2 : 8))) * 128u + 1023u) / 1024u * 1024u; };
+  auto dy_img_of = [&](int tw) { return (static_cast<uint32_t>(p.R * tw) * 128u + 1023u) / 1024u * 1024u; };
+  auto fits2 = [&](int tw) { return 1024 + STAGES * static_cast<size_t>(x_bytes_of(tw) + 2 * dy_img_of(tw)) + 64 <= 227 * 1024; };
+  if (wide_env && !p.narrow && (ntaps + 1) / 2 <= 4 && N % 128 == 0 && p.R == R) {
+    if (fits2(p.tw)) p.nbw = 2;
+    else if (fits2(96)) { p.nbw = 2; p.tw = 96; p.pw = p.tw + (max_dc <= 2 ? 2 : 8); }
+  }
+  p.NCB = p.narrow ? 1 : C / 64; p.NNB = N / (64 * p.nbw); p.WT = (W + p.tw - 1) / p.tw; p.HP = (H + p.R - 1) / p.R;
   p.x_bytes = (static_cast<uint32_t>(p.xr * p.pw) * (p.narrow ? 32u : 128u) + 1023u) / 1024u * 1024u;
-  p.stage_bytes = p.x_bytes + (p.R == R ? DY_BYTES : (static_cast<uint32_t>(p.R * p.tw) * 128u + 1023u) / 1024u * 1024u);
+  p.dy_img_bytes = p.nbw > 1 ? dy_img_of(p.tw)
+                             : (p.R == R ? DY_BYTES : (static_cast<uint32_t>(p.R * p.tw) * 128u + 1023u) / 1024u * 1024u);
+  p.stage_bytes = p.x_bytes + static_cast<uint32_t>(p.nbw) * p.dy_img_bytes;
   if (1024 + STAGES * static_cast<size_t>(p.stage_bytes) + 64 > 227 * 1024) return AIR_ERR_UNSUPPORTED;
   for (int a = 0; a < NACC; ++a) { p.acc_off[a] = 0; p.acc_lbo[a] = 0; for (int g = 0; g < 8; ++g) p.acc_tap[a][g] = -1; }
   int off[9];
