@@ -56,10 +56,28 @@ struct ConvParams {
   int stages; int flags;
   int use_tma;                              // 1x1 / stride 1: the A tile is a plain 2-D box of the activation matrix
   int stage_out;                            // 1 / 2: bf16 outputs leave through 1 / 2 shared-memory tiles per epilogue warp + TMA stores
+  double* stats;                            // optional (staged path only): stats[n] += sum of the stored outputs, stats[N + n] += sum of
+                                            // squares -- the batch statistics of the BatchNorm that consumes `out` (bn_stats fused)
 };
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, const bf16x8& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.u.x), "r"(v.u.y), "r"(v.u.z), "r"(v.u.w) : "memory");
+}
+
+// Transpose-reduce over the warp: every lane holds 32 values v[0..31] (its row's columns); on return lane l holds the sum over
+// the 32 lanes of v[l] (31 shuffles: each stage exchanges half of the remaining values).  As in conv_patch.cu.
+__device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = up ? v[i] : v[i + o];
+      const float keep = up ? v[i + o] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
 }
 
 // bias / second output / residual / ReLU / affine of 16 accumulator columns of row m (the part of the epilogue before the store)
@@ -127,6 +145,9 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& p, uint32_t tmem
   const bool f32 = (p.flags & AIR_CONV_F32_OUT) != 0;       // fp32 parity mode: float storage, no rounding point
   const uint32_t ssw = static_cast<uint32_t>((lane >> 1) & 3);
   uint32_t tsel = 0;                               // which of the warp's (1 or 2) tiles the next 32-column group uses
+  float acc_s[8], acc_q[8];                        // fused statistics (n_tiles == 1): lane l <-> column c_begin + 32 g + l
+#pragma unroll
+  for (int u = 0; u < 8; ++u) { acc_s[u] = 0.f; acc_q[u] = 0.f; }
   int it = 0;
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
     const int m_tile = tile / p.n_tiles, n_tile = tile % p.n_tiles;
@@ -147,14 +168,30 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& p, uint32_t tmem
         const uint32_t tile = stage_tile + tsel * STAGE_TILE, srow = tile + static_cast<uint32_t>(lane) * 64u;
         if (lane == 0) { if (p.stage_out == 2) bulk_wait_read_1(); else bulk_wait_read_all(); }   // this tile's previous store has left shared memory
         __syncwarp();
-        st_shared_v4(srow + ((0u ^ ssw) << 4), pack8(va));
-        st_shared_v4(srow + ((1u ^ ssw) << 4), pack8(va + 8));
-        st_shared_v4(srow + ((2u ^ ssw) << 4), pack8(vb));
-        st_shared_v4(srow + ((3u ^ ssw) << 4), pack8(vb + 8));
+        const bf16x8 k0 = pack8(va), k1 = pack8(va + 8), k2 = pack8(vb), k3 = pack8(vb + 8);
+        st_shared_v4(srow + ((0u ^ ssw) << 4), k0);
+        st_shared_v4(srow + ((1u ^ ssw) << 4), k1);
+        st_shared_v4(srow + ((2u ^ ssw) << 4), k2);
+        st_shared_v4(srow + ((3u ^ ssw) << 4), k3);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) { tma_store_2d(tmo, tile, n0, m_tile * BLOCK_M + q * 32); bulk_commit_group(); }
         if (p.stage_out == 2) tsel ^= 1u;
+        if (p.stats != nullptr) {                   // warp-uniform: per-column sums of the STORED values of this warp's 32 rows
+          float sv[32], sq[32];
+          unpack8(k0, sv); unpack8(k1, sv + 8); unpack8(k2, sv + 16); unpack8(k3, sv + 24);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { sv[i] = (m < p.M) ? sv[i] : 0.f; sq[i] = sv[i] * sv[i]; }
+          const float cs = warp_column_sums(sv, lane), cq = warp_column_sums(sq, lane);
+          if (p.n_tiles == 1) {                     // every tile has the same columns: keep the sums in registers until the end
+            const int g = (c0 - c_begin) >> 5;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) if (u == g) { acc_s[u] += cs; acc_q[u] += cq; }
+          } else {
+            atomicAdd(p.stats + n0 + lane, static_cast<double>(cs));
+            atomicAdd(p.stats + p.N + n0 + lane, static_cast<double>(cq));
+          }
+        }
       }
     }
     for (; c0 < c_end; c0 += 16) {
@@ -178,6 +215,16 @@ __device__ __forceinline__ void epilogue_role(const ConvParams& p, uint32_t tmem
     mbar_arrive(&tempty[acc]);
   }
   if (stage_tile != 0 && lane == 0) bulk_wait_all();
+  if (p.stats != nullptr && p.n_tiles == 1 && stage_tile != 0) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int n0 = c_begin + 32 * u;
+      if (n0 + 32 <= c_end) {
+        atomicAdd(p.stats + n0 + lane, static_cast<double>(acc_s[u]));
+        atomicAdd(p.stats + p.N + n0 + lane, static_cast<double>(acc_q[u]));
+      }
+    }
+  }
 }
 
 __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_o,
@@ -430,12 +477,42 @@ extern "C" int air_conv_gemm_bf16_ex(const void* a, long long a_ld, int B, int H
 }
 
 // as _ex, plus an optional per-channel affine applied after the ReLU: out = relu(acc + bias) * post_scale[n] + post_shift[n]
+static int launch_conv_gemm(const void* a, long long a_ld, int B, int H, int W, int C, int Ho, int Wo,
+                            int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw, int mode,
+                            const void* wpk, int N, int K, void* out, long long out_ld,
+                            const float* bias, int bias_rows, const void* res, long long res_ld, int relu,
+                            void* out2, long long out2_ld, const float* post_scale, const float* post_shift,
+                            double* stats, int num_sms, int flags, cudaStream_t stream);
+
 extern "C" int air_conv_gemm_bf16_affine(const void* a, long long a_ld, int B, int H, int W, int C, int Ho, int Wo,
                                          int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw, int mode,
                                          const void* wpk, int N, int K, void* out, long long out_ld,
                                          const float* bias, int bias_rows, const void* res, long long res_ld, int relu,
                                          void* out2, long long out2_ld, const float* post_scale, const float* post_shift,
                                          int num_sms, int flags, cudaStream_t stream) {
+  return launch_conv_gemm(a, a_ld, B, H, W, C, Ho, Wo, kh, kw, sh, sw, ph, pw, dh, dw, mode, wpk, N, K, out, out_ld, bias,
+                          bias_rows, res, res_ld, relu, out2, out2_ld, post_scale, post_shift, nullptr, num_sms, flags, stream);
+}
+
+// air_conv_gemm_bf16 whose epilogue also accumulates the per-channel sum / sum of squares of the stored (bf16) output into
+// stats[0..N) / stats[N..2N) (fp64, caller zeroes): the batch statistics of the BatchNorm that follows (resnet.py:65-68).
+// bf16 storage and N a multiple of 32 (per tile a multiple of 32 columns) only.
+extern "C" int air_conv_gemm_bf16_stats(const void* a, long long a_ld, int B, int H, int W, int C, int Ho, int Wo,
+                                        int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw, int mode,
+                                        const void* wpk, int N, int K, void* out, long long out_ld,
+                                        const float* bias, const void* res, long long res_ld, int relu, double* stats,
+                                        int num_sms, int flags, cudaStream_t stream) {
+  if (!stats) return AIR_ERR_ARG;
+  return launch_conv_gemm(a, a_ld, B, H, W, C, Ho, Wo, kh, kw, sh, sw, ph, pw, dh, dw, mode, wpk, N, K, out, out_ld, bias,
+                          0, res, res_ld, relu, nullptr, 0, nullptr, nullptr, stats, num_sms, flags, stream);
+}
+
+static int launch_conv_gemm(const void* a, long long a_ld, int B, int H, int W, int C, int Ho, int Wo,
+                            int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw, int mode,
+                            const void* wpk, int N, int K, void* out, long long out_ld,
+                            const float* bias, int bias_rows, const void* res, long long res_ld, int relu,
+                            void* out2, long long out2_ld, const float* post_scale, const float* post_shift,
+                            double* stats, int num_sms, int flags, cudaStream_t stream) {
   if (!a || !wpk || !out || B <= 0 || ((post_scale == nullptr) != (post_shift == nullptr))) return AIR_ERR_ARG;
   if (C % 8 != 0 || a_ld % 8 != 0 || out_ld % 8 != 0 || (res && res_ld % 8 != 0) || (out2 && out2_ld % 8 != 0)) return AIR_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(out2) & 15) || bias_rows < 0) return AIR_ERR_UNSUPPORTED;
@@ -454,7 +531,7 @@ extern "C" int air_conv_gemm_bf16_affine(const void* a, long long a_ld, int B, i
   p.out = out; p.out_ld = out_ld; p.bias = bias;
   p.res = res; p.res_ld = res_ld; p.relu = relu; p.flags = flags;
   p.bias_rows = bias_rows; p.out2 = out2; p.out2_ld = out2_ld;
-  p.post_scale = post_scale; p.post_shift = post_shift;
+  p.post_scale = post_scale; p.post_shift = post_shift; p.stats = stats;
   const int stage_bytes = A_STAGE_BYTES + bn * BLOCK_K * 2;
   int stages = (198 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
@@ -469,6 +546,7 @@ extern "C" int air_conv_gemm_bf16_affine(const void* a, long long a_ld, int B, i
     if (total(stages, 2) <= 227 * 1024) p.stage_out = 2;
     else if (stages >= 6 && total(stages - 1, 2) <= 227 * 1024) { p.stage_out = 2; p.stages = --stages; }
   }
+  if (stats && !p.stage_out) return AIR_ERR_UNSUPPORTED;
   const size_t smem = 1024 + static_cast<size_t>(stages) * stage_bytes + static_cast<size_t>(p.stage_out) * 8 * STAGE_TILE + (2 * stages + 4) * 8 + 16;
   static bool attr_done = false;
   if (!attr_done) {
@@ -484,6 +562,7 @@ extern "C" int air_conv_gemm_bf16_affine(const void* a, long long a_ld, int B, i
   if (kh == 1 && kw == 1 && sh == 1 && sw == 1 && ph == 0 && pw == 0 && Ho == H && Wo == W && p.M < 0x7fffffffLL) {
     if (air_tmap::make_mat_tmap(&tm, a, a_ld, p.M, C, BLOCK_M) == 0) p.use_tma = 1;     // otherwise: the gather path
   }
+  if (stats && p.use_tma && (((bn / 16 + 1) / 2) * 16) % 32 != 0) return AIR_ERR_UNSUPPORTED;     // a 16-column remainder would bypass the staged path
   CUtensorMap tmo = tm;
   if (p.stage_out && air_tmap::make_out_tmap(&tmo, out, out_ld, p.M, N) != 0) return AIR_ERR_DRIVER;
   conv_gemm_kernel<<<grid, THREADS, smem, stream>>>(tm, tmo, p);

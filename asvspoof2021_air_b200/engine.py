@@ -79,6 +79,8 @@ def _conv1d_pt(t):          # [Cout][k][Cin] -> (Cout, Cin, k)
 
 class ConvLayer:
     """One convolution: geometry, weight views, packed bf16 operands, fprop / dgrad / wgrad launches."""
+    # BatchNorm statistics in the epilogue of the generic kernel as well (AIR_GEMM_STATS=0: separate bn_stats launches)
+    gemm_stats = os.environ.get("AIR_GEMM_STATS", "1") != "0"
 
     def __init__(self, store, name, cin, cout, kh, kw, sh=1, sw=1, ph=0, pw=0, dh=1, dw=1,
                  bias=False, need_dgrad=True, cin_pad=None, need_fprop=True):
@@ -190,6 +192,13 @@ class ConvLayer:
             ops.conv1d_patch(x, x_ld, B, H, W, self.cin, self.wpk3, self.kw, self.dw, self.cout, out, out_ld, bias,
                              res, res_ld, relu, None, 0, 0, None, None, stats if fuse else None)
             self.stats_fused = fuse
+            return Ho, Wo
+        if (stats is not None and self.gemm_stats and out.dtype == BF16 and self.cout % 32 == 0 and (self.cout <= 256 or self.cout % 256 == 0)
+                and not (self.kh == 1 and self.kw == 1 and self.sh == 1 and self.sw == 1)):
+            # generic kernel (gather mode): the statistics of the BatchNorm that follows ride its epilogue too
+            ops.conv_gemm_stats(x, x_ld, B, H, W, self.cin_g, Ho, Wo, self.kh, self.kw, self.sh, self.sw, self.ph, self.pw,
+                                self.dh, self.dw, 0, self.wpk, self.cout, self.K, out, out_ld, bias, res, res_ld, relu, stats)
+            self.stats_fused = True
             return Ho, Wo
         ops.conv_gemm(x, x_ld, B, H, W, self.cin_g, Ho, Wo, self.kh, self.kw, self.sh, self.sw, self.ph, self.pw,
                       self.dh, self.dw, 0, self.wpk, self.cout, self.K, out, out_ld, bias, res, res_ld, relu)
@@ -729,9 +738,9 @@ class ResNetEngine(AsyncWgrad):
             x_stats = blk.conv2.stats_fused
             x = blk.y
         last = self.blocks[-1]
-        self.conv5.fprop(x, 512, B, last.Ho, last.Wo, self.c5, 256)
+        self.conv5.fprop(x, 512, B, last.Ho, last.Wo, self.c5, 256, stats=self.bn5.sums if (training and self.fuse_bn_stats) else None)
         M5 = B * self.W5
-        self.bn5.forward(self.c5, 256, self.z5, 256, M5, True, training)
+        self.bn5.forward(self.c5, 256, self.z5, 256, M5, True, training, have_stats=self.conv5.stats_fused)
         ops.selfattn_pool_fwd(self.z5, st.view("attention.att_weights"), self.stats, self.pool_p, self.pool_th,
                               B, self.W5, 256, self.noise_seed)
         ops.linear_fwd(self.stats, st.view("fc.weight"), st.view("fc.bias"), self.feat, B, self.enc_dim, 512)

@@ -82,6 +82,17 @@ def conv_gemm(a, a_ld, B, H, W, C, Ho, Wo, kh, kw, sh, sw, ph, pw, dh, dw, mode,
     return out
 
 
+def conv_gemm_stats(a, a_ld, B, H, W, C, Ho, Wo, kh, kw, sh, sw, ph, pw, dh, dw, mode, wpk, N, K,
+                    out, out_ld, bias, res, res_ld, relu, stats):
+    """conv_gemm whose epilogue also accumulates sum / sum of squares of the stored output into stats (fp64 [2N])."""
+    st = _lib.lib().air_conv_gemm_bf16_stats(
+        _lib.ptr(a), _lib.LL(a_ld), B, H, W, C, Ho, Wo, kh, kw, sh, sw, ph, pw, dh, dw, mode,
+        _lib.ptr(wpk), N, K, _lib.ptr(out), _lib.LL(out_ld), _lib.ptr(bias), _lib.ptr(res), _lib.LL(res_ld),
+        int(relu), _lib.ptr(stats), num_sms(), _conv_flags(out, res), _lib.stream_ptr())
+    _lib.check(st, "air_conv_gemm_bf16_stats")
+    return out
+
+
 def conv_wgrad(x, x_ld, B, H, W, C, dy, dy_ld, Ho, Wo, N, kh, kw, sh, sw, ph, pw, dh, dw, dw_out, flags=0):
     """dw_out: fp32 [N][kh*kw*C] accumulated in place (caller zeroes)."""
     st = _lib.lib().air_conv_wgrad_bf16(
@@ -635,6 +646,7 @@ conv_s2_dgrad_patch = _timed(conv_s2_dgrad_patch, "conv_dgrad", lambda a: 2.0 * 
 PackPlan.run = _timed(PackPlan.run, "pack_weights")
 conv_wgrad_patch = _timed(conv_wgrad_patch, "conv_wgrad", lambda a: 2.0 * a[2] * a[3] * a[4] * a[5] * a[8] * a[9] * a[9])
 conv_gemm_affine = _timed(conv_gemm_affine, "conv_fprop", _conv_work)
+conv_gemm_stats = _timed(conv_gemm_stats, "conv_fprop", _conv_work)
 conv1d_patch = _timed(conv1d_patch, lambda a: "conv_dgrad" if (len(a) > 18 and a[18] == 1) else "conv_fprop",
                       lambda a: 2.0 * a[2] * a[3] * a[4] * a[5] * a[9] * a[7])
 conv1d_wgrad_patch = _timed(conv1d_wgrad_patch, "conv_wgrad", lambda a: 2.0 * a[2] * a[3] * a[4] * a[5] * a[8] * a[9])

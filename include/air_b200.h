@@ -113,6 +113,14 @@ int air_conv_gemm_bf16(const void* a, long long a_ld, int B, int H, int W, int C
                        const float* bias, const void* res, long long res_ld, int relu,
                        int num_sms, int flags, air_stream_t stream);
 
+/* air_conv_gemm_bf16 whose epilogue also adds the per-channel sum / sum of squares of the stored bf16 output to
+ * stats[0..N) / stats[N..2N) (fp64, caller-zeroed): the batch statistics of the BatchNorm that follows (resnet.py:65-68) */
+int air_conv_gemm_bf16_stats(const void* a, long long a_ld, int B, int H, int W, int C, int Ho, int Wo,
+                             int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw, int mode,
+                             const void* wpk, int N, int K, void* out, long long out_ld,
+                             const float* bias, const void* res, long long res_ld, int relu, double* stats,
+                             int num_sms, int flags, air_stream_t stream);
+
 /* Extended forms used by the ECAPA path:
  *   air_conv_pack_weights_ld : `w` rows are `w_ld` elements apart (a column slice of a wider weight, e.g. the
  *                              x-block of attention.0.weight (128, 4608), ecapa_tdnn.py:139,173-175)

@@ -453,3 +453,27 @@ def test_patch_conv_flat_rows_pair_rows_of_neighbouring_images_bit_identically(s
     assert torch.equal(out_s, out)
     o64 = out.double().reshape(-1, Cout)
     assert torch.allclose(st[:Cout], o64.sum(0), rtol=1e-5, atol=1e-6 * float(o64.abs().sum(0).max()))
+
+
+@pytest.mark.parametrize("name", ["res_l2_3x3_s2_64_128", "res_l4_3x3_512_512", "res_conv5_512_256"])
+def test_generic_conv_fused_batchnorm_statistics(name):
+    """air_conv_gemm_bf16_stats: the generic (gather) kernel stores the same tensor as air_conv_gemm_bf16 and its epilogue
+    accumulates the per-channel sum / sum of squares of the stored output (rows beyond M excluded)."""
+    ops, x, w, dy, Ho, Wo = _setup(name)
+    B, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, dh, dw = CASES[name]
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    wg = w.permute(0, 2, 3, 1).contiguous().reshape(-1)
+    K = kh * kw * Cin
+    wpk = ops.pack_weights(wg, 0, Cin, Cout, kh * kw)
+    res = torch.randn(B, Ho, Wo, Cout, generator=torch.Generator(device="cpu").manual_seed(5)).cuda().to(torch.bfloat16)
+    out = torch.empty(B, Ho, Wo, Cout, device="cuda", dtype=torch.bfloat16)
+    ref = torch.empty_like(out)
+    st = torch.zeros(2 * Cout, device="cuda", dtype=torch.float64)
+    ops.conv_gemm_stats(xn, Cin, B, H, W, Cin, Ho, Wo, kh, kw, sh, sw, ph, pw, dh, dw, 0, wpk, Cout, K, out, Cout, None, res, Cout,
+                        False, st)
+    ops.conv_gemm(xn, Cin, B, H, W, Cin, Ho, Wo, kh, kw, sh, sw, ph, pw, dh, dw, 0, wpk, Cout, K, ref, Cout, None, res, Cout, False)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+    o64 = out.double().reshape(-1, Cout)
+    assert torch.allclose(st[:Cout], o64.sum(0), rtol=1e-5, atol=1e-6 * float(o64.abs().sum(0).max()))
+    assert torch.allclose(st[Cout:], (o64 * o64).sum(0), rtol=1e-5)
