@@ -19,10 +19,11 @@ cap wgrad_patch_l4 conv3x3_wgrad_patch_kernel 3 python scripts/prof_conv.py wgra
 cap s2_wgrad_l2 conv3x3_wgrad_patch_kernel 12 python scripts/prof_conv.py s2_wgrad 256 18 750 64 128
 cap gemm_l4 conv_gemm_kernel 3 python scripts/prof_conv.py gemm 256 3 94 512 512
 cap gemm_1x1_512 conv_gemm_kernel 3 python scripts/prof_conv.py gemm1x1 256 1 750 512 512
+cap gemm_s2_l2 conv_gemm_kernel 3 python scripts/prof_conv.py gemm_s2 256 18 750 64 128
 cap bn_bwd_apply_l1 bn_bwd_apply_kernel 3 python scripts/prof_conv.py bn_bwd 256 18 750 64 64
 AIR_LFCC_IMPL=tc cap lfcc_tc lfcc_tc_kernel 4 python bench.py --workload lfcc --steps 3 --warmup 3 --no-cpu-baseline
 args=""
-for n in patch_l1_stats patch_l1 patch_l2 patch_l3 wgrad_patch_l1 wgrad_patch_l3 wgrad_patch_l4 s2_wgrad_l2 gemm_l4 gemm_1x1_512 bn_bwd_apply_l1 lfcc_tc; do
+for n in patch_l1_stats patch_l1 patch_l2 patch_l3 wgrad_patch_l1 wgrad_patch_l3 wgrad_patch_l4 s2_wgrad_l2 gemm_l4 gemm_1x1_512 gemm_s2_l2 bn_bwd_apply_l1 lfcc_tc; do
   [ -f gpurun_out/r02_ncu_$n.ncu-rep ] && args="$args $n=gpurun_out/r02_ncu_$n.ncu-rep"
 done
 python scripts/ncu_metrics.py $args > gpurun_out/r02_ncu_metrics.json
