@@ -312,6 +312,21 @@ __global__ void bn1d_fwd_kernel(const float* __restrict__ x, float* __restrict__
   }
 }
 
+// Eval mode: the running-statistics affine has no reduction, so it runs one thread per element (the per-channel kernel above
+// walks the batch serially: 0.09 - 0.2 ms per call at the scoring batch of 1024).  Same expression, same results.
+__global__ void bn1d_eval_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, int C, int relu_in,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                 const float* __restrict__ running_mean, const float* __restrict__ running_var) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const float mean = running_mean[c], invstd = rsqrtf(running_var[c] + eps);
+    const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+    float v = x[i];
+    if (relu_in) v = fmaxf(v, 0.f);
+    y[i] = (v - mean) * invstd * g + b;
+  }
+}
+
 __global__ void bn1d_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dx, int M, int C,
                                 int relu_in, const float* __restrict__ gamma, const float* __restrict__ mean,
                                 const float* __restrict__ invstd, float* __restrict__ dgamma, float* __restrict__ dbeta) {
@@ -559,6 +574,12 @@ extern "C" int air_bn1d_f32_fwd(const float* x, float* y, int M, int C, int relu
                                 float* running_var, float momentum, cudaStream_t stream) {
   if (!x || !y || M <= 0 || C <= 0) return AIR_ERR_ARG;
   if (!training && (!running_mean || !running_var)) return AIR_ERR_ARG;
+  if (!training) {
+    const long long n = static_cast<long long>(M) * C;
+    const int blocks = static_cast<int>(std::min<long long>((n + 255) / 256, 148 * 8));
+    bn1d_eval_kernel<<<blocks, 256, 0, stream>>>(x, y, n, C, relu_in, gamma, beta, eps, running_mean, running_var);
+    return air_launch_status();
+  }
   bn1d_fwd_kernel<<<(C + 63) / 64, 64, 0, stream>>>(x, y, M, C, relu_in, gamma, beta, eps, training, save_mean, save_invstd,
                                                      running_mean, running_var, momentum);
   return air_launch_status();

@@ -140,59 +140,103 @@ __global__ void selfattn_pool_bwd_kernel(const AT* __restrict__ x, const float* 
 // Small fp32 GEMM with arbitrary element strides (the fully connected layers: fc / fc_mu resnet.py:142-143, fc6 / fc7
 // and the SE bottleneck ecapa_tdnn.py:19-23,148-149):  C[i][j] (+)= sum_l A(i,l) * B(l,j) (+ bias[j]) (+ rowsum)
 //   A(i,l) = A[i*sai + l*sal],  B(l,j) = B[l*sbl + j*sbj],  C[i][j] = C[i*ldc + j]
-// 32 x 32 output tile per 256-thread CTA (each thread 4 rows of one column), 32-deep K tiles through padded shared
-// memory; the tile loaders put the contiguous index of each operand on consecutive lanes.
-template <typename AccT>
+// 32 x 32 output tile per 256-thread CTA (each thread 4 consecutive rows of one column), 32-deep K tiles through shared
+// memory held in the accumulator type: the A tile is stored l-major so that a thread's four row values are one 16-byte
+// (two for fp64) broadcast load per l, and the fp32 -> fp64 conversion of the long reductions happens once per loaded
+// element instead of once per multiply.  Every output is still the sequential fma chain over l = 0 .. L-1.
+// The next K tile is fetched into registers while the current one is multiplied (a CTA's chain of K tiles is latency-,
+// not throughput-bound: 64 CTAs x 96 tiles for fc6 at B = 256).  Split-K form (part != nullptr, fp64 only): CTA z takes
+// K tiles [z * l_chunk, (z + 1) * l_chunk) and writes its fp64 partial sums to part[z][i][j]; splitk_reduce_kernel adds
+// them in z order -- deterministic, and the fp64 partials keep the result within an ulp of fp32 of the single chain.
+template <typename AccT, bool COLSUM>
 __global__ void __launch_bounds__(256) sgemm_strided_kernel(const float* __restrict__ A, long long sai, long long sal,
                                                             const float* __restrict__ B, long long sbl, long long sbj,
                                                             float* __restrict__ C, long long ldc, int I, int J, int L,
                                                             const float* __restrict__ bias, int accumulate,
-                                                            float* __restrict__ colsum_of_a) {
-  __shared__ float sa[32][33], sb[32][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;            // ty 0..7
+                                                            float* __restrict__ colsum_of_a, double* __restrict__ part,
+                                                            int l_chunk) {
+  __shared__ __align__(16) AccT sa[32][36];                          // sa[l][i]
+  __shared__ AccT sb[32][33];                                        // sb[l][j]
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;            // ty 0..7: rows 4 ty .. 4 ty + 3
   const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  const int lbeg = part ? blockIdx.z * l_chunk : 0, lend = part ? min(L, lbeg + l_chunk) : L;
   // AccT = double for long reductions (fc6: K = 3072): the 1-D BatchNorms that follow (bn5 over B rows) amplify the
   // summation-order noise of an fp32 reduction; float otherwise
   AccT acc[4] = {0, 0, 0, 0};
   float csum[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int l0 = 0; l0 < L; l0 += 32) {
-    // A tile: sa[i][l].  lanes follow the contiguous index
+  // tile coordinates of this thread's loads: lanes follow the contiguous index of each operand
+  int ai[4], al[4], bl[4], bj[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int u = ty + 8 * r;                                         // the slow index of this load
+    if (sal == 1) { ai[r] = u; al[r] = tx; } else { ai[r] = tx; al[r] = u; }
+    if (sbj == 1) { bl[r] = u; bj[r] = tx; } else { bl[r] = tx; bj[r] = u; }
+  }
+  float ra[4], rb[4];
+  auto fetch = [&](int l0) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      const int u = ty + 8 * r;                                       // the slow index of this load
-      int ii, ll;
-      if (sal == 1) { ii = u; ll = tx; } else { ii = tx; ll = u; }
-      const int gi = i0 + ii, gl = l0 + ll;
-      sa[ii][ll] = (gi < I && gl < L) ? A[gi * sai + gl * sal] : 0.f;
+      const int gi = i0 + ai[r], gl = l0 + al[r];
+      ra[r] = (gi < I && gl < lend) ? A[gi * sai + gl * sal] : 0.f;
+      const int hl = l0 + bl[r], gj = j0 + bj[r];
+      rb[r] = (hl < lend && gj < J) ? B[hl * sbl + gj * sbj] : 0.f;
     }
+  };
+  if (lbeg < lend) fetch(lbeg);
+  for (int l0 = lbeg; l0 < lend; l0 += 32) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      const int u = ty + 8 * r;
-      int ll, jj;
-      if (sbj == 1) { ll = u; jj = tx; } else { ll = tx; jj = u; }
-      const int gl = l0 + ll, gj = j0 + jj;
-      sb[ll][jj] = (gl < L && gj < J) ? B[gl * sbl + gj * sbj] : 0.f;
+      sa[al[r]][ai[r]] = static_cast<AccT>(ra[r]);
+      sb[bl[r]][bj[r]] = static_cast<AccT>(rb[r]);
     }
     __syncthreads();
+    if (l0 + 32 < lend) fetch(l0 + 32);
 #pragma unroll 8
     for (int l = 0; l < 32; ++l) {
-      const float bv = sb[l][tx];
+      const AccT bv = sb[l][tx];
+      AccT av[4];
+      if constexpr (sizeof(AccT) == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(&sa[l][4 * ty]);
+        av[0] = t.x; av[1] = t.y; av[2] = t.z; av[3] = t.w;
+      } else {
+        const double2 t0 = *reinterpret_cast<const double2*>(&sa[l][4 * ty]);
+        const double2 t1 = *reinterpret_cast<const double2*>(&sa[l][4 * ty + 2]);
+        av[0] = t0.x; av[1] = t0.y; av[2] = t1.x; av[3] = t1.y;
+      }
 #pragma unroll
-      for (int r = 0; r < 4; ++r) { const float av = sa[ty + 8 * r][l]; acc[r] = fma(static_cast<AccT>(av), static_cast<AccT>(bv), acc[r]); csum[r] += av; }
+      for (int r = 0; r < 4; ++r) {
+        acc[r] = fma(av[r], bv, acc[r]);
+        if constexpr (COLSUM) csum[r] += static_cast<float>(av[r]);
+      }
     }
     __syncthreads();
   }
   const int j = j0 + tx;
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
-    const int i = i0 + ty + 8 * r;
+    const int i = i0 + 4 * ty + r;
     if (i < I && j < J) {
-      float v = static_cast<float>(acc[r] + (bias ? static_cast<AccT>(bias[j]) : static_cast<AccT>(0)));
-      float* cp = C + i * ldc + j;
-      *cp = accumulate ? *cp + v : v;
+      if (part) {
+        part[(static_cast<long long>(blockIdx.z) * I + i) * J + j] = static_cast<double>(acc[r]);
+      } else {
+        float v = static_cast<float>(acc[r] + (bias ? static_cast<AccT>(bias[j]) : static_cast<AccT>(0)));
+        float* cp = C + i * ldc + j;
+        *cp = accumulate ? *cp + v : v;
+      }
     }
     // row sums of A (the bias gradient when A = dy^T): written once per row by the j-tile 0, column 0 thread
-    if (colsum_of_a && blockIdx.x == 0 && tx == 0 && i < I) colsum_of_a[i] += csum[r];
+    if constexpr (COLSUM) { if (blockIdx.x == 0 && tx == 0 && i < I) colsum_of_a[i] += csum[r]; }
+  }
+}
+
+__global__ void splitk_reduce_kernel(const double* __restrict__ part, int splits, long long n, int J, const float* __restrict__ bias,
+                                     float* __restrict__ C, long long ldc) {
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < n; e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    double s = 0.0;
+    for (int z = 0; z < splits; ++z) s += part[z * n + e];
+    const long long i = e / J;
+    const int j = static_cast<int>(e - i * J);
+    C[i * ldc + j] = static_cast<float>(s + (bias ? static_cast<double>(bias[j]) : 0.0));
   }
 }
 
@@ -200,8 +244,10 @@ static int launch_sgemm(const float* A, long long sai, long long sal, const floa
                         float* C, long long ldc, int I, int J, int L, const float* bias, int accumulate, float* colsum,
                         cudaStream_t stream) {
   dim3 grid((J + 31) / 32, (I + 31) / 32);
-  if (L >= 2048) sgemm_strided_kernel<double><<<grid, 256, 0, stream>>>(A, sai, sal, B, sbl, sbj, C, ldc, I, J, L, bias, accumulate, colsum);
-  else sgemm_strided_kernel<float><<<grid, 256, 0, stream>>>(A, sai, sal, B, sbl, sbj, C, ldc, I, J, L, bias, accumulate, colsum);
+#define AIR_SGEMM(T, CS) sgemm_strided_kernel<T, CS><<<grid, 256, 0, stream>>>(A, sai, sal, B, sbl, sbj, C, ldc, I, J, L, bias, accumulate, colsum, nullptr, 0)
+  if (L >= 2048) { if (colsum) AIR_SGEMM(double, true); else AIR_SGEMM(double, false); }
+  else { if (colsum) AIR_SGEMM(float, true); else AIR_SGEMM(float, false); }
+#undef AIR_SGEMM
   return air_launch_status();
 }
 
@@ -346,6 +392,24 @@ extern "C" int air_linear_fwd(const float* x, const float* W, const float* bias,
   if (!x || !W || !y || M <= 0 || N <= 0 || K <= 0) return AIR_ERR_ARG;
   // y[m][n] = sum_k x[m][k] W[n][k] + b[n]
   return launch_sgemm(x, K, 1, W, 1, K, y, N, M, N, K, bias, 0, nullptr, stream);
+}
+
+// The same product with the K dimension dealt to `splits` CTAs per output tile (fc6 of ECAPA, K = 3072: one CTA chain
+// of 96 K tiles took 0.30 ms whatever the batch).  fp64 accumulation and fp64 partial sums in `scratch`
+// (>= splits * M * N doubles), added in split order: deterministic.
+extern "C" int air_linear_fwd_splitk(const float* x, const float* W, const float* bias, float* y, int M, int N, int K,
+                                     double* scratch, int splits, cudaStream_t stream) {
+  if (!x || !W || !y || !scratch || M <= 0 || N <= 0 || K <= 0 || splits < 1 || splits > 64) return AIR_ERR_ARG;
+  const int tiles = (K + 31) / 32;
+  const int l_chunk = ((tiles + splits - 1) / splits) * 32;
+  const int used = (K + l_chunk - 1) / l_chunk;                      // splits that own at least one K tile
+  dim3 grid((N + 31) / 32, (M + 31) / 32, used);
+  sgemm_strided_kernel<double, false><<<grid, 256, 0, stream>>>(x, K, 1, W, 1, K, y, N, M, N, K, nullptr, 0, nullptr, scratch, l_chunk);
+  int st = air_launch_status();
+  if (st != AIR_OK) return st;
+  const long long n = static_cast<long long>(M) * N;
+  splitk_reduce_kernel<<<static_cast<int>(std::min<long long>((n + 255) / 256, 148 * 8)), 256, 0, stream>>>(scratch, used, n, N, bias, y, N);
+  return air_launch_status();
 }
 
 // y (+)= x W[:, slice]^T + b with a row stride on W (column slice of a wider weight, e.g. the

@@ -52,6 +52,7 @@ class _BN1d:
 class EcapaEngine(AsyncWgrad):
     # scoring: eval-mode BatchNorm of the Res2 branches folded into the dilated-conv epilogue (AIR_FOLD_EVAL_BN=0: separate pass)
     fold_eval_bn = os.environ.get("AIR_FOLD_EVAL_BN", "1") != "0"
+    FC6_SPLITS = 8
     # training: batch statistics of the Res2-branch BatchNorms accumulated by the epilogue of the dilated conv.  Off by default:
     # it saves 0.1 ms of 16.2 (21 small bn_stats launches), and although the sums agree with bn_stats to 1e-7 the golden-size
     # net (BatchNorm1d over B = 4 rows in SE / bn5) amplifies that summation-order difference to 1e-2 on the embeddings, which
@@ -262,6 +263,7 @@ class EcapaEngine(AsyncWgrad):
         self.smax, self.ssum, self.sq = f32(B, C3), f32(B, C3), f32(B, C3)
         self.feat, self.g_feat7 = f32(B, self.enc_dim), f32(B, self.enc_dim)
         self.l7, self.logits, self.g_l7 = f32(B, self.n_out), f32(B, self.n_out), f32(B, self.n_out)
+        self.fc6_part = torch.empty(self.FC6_SPLITS * B * self.enc_dim, device=self.device, dtype=torch.float64)
         self._w1tmp = None
 
     # ---- BN helpers (conv -> ReLU -> BN order: y = bn(x), x already relu'd) --------------------
@@ -378,7 +380,9 @@ class EcapaEngine(AsyncWgrad):
         self.att3.fprop(self.a2, 128, B, 1, T, self.e, C3)                                      # :143
         ops.asp_fwd(self.e, C3, self.x4, C3, B, T, C3, self.pooled, self.smax, self.ssum, self.sq)   # :144,182-186
         self.bn5.forward(self.pooled, self.p5, B, False, training)                              # :188
-        ops.linear_fwd(self.p5, st.view("fc6.weight"), st.view("fc6.bias"), self.feat, B, self.enc_dim, 2 * C3)
+        # fc6 (:148): K = 3072 over few outputs -- the K tiles are dealt to FC6_SPLITS CTAs per output tile (fp64 partials)
+        ops.linear_fwd_splitk(self.p5, st.view("fc6.weight"), st.view("fc6.bias"), self.feat, B, self.enc_dim, 2 * C3,
+                              self.fc6_part, self.FC6_SPLITS)
         ops.linear_fwd(self.feat, st.view("fc7.weight"), st.view("fc7.bias"), self.l7, B, self.n_out, self.enc_dim)
         self.bn7.forward(self.l7, self.logits, B, False, training)                              # :192-195
         return self.feat, self.logits

@@ -343,6 +343,13 @@ def linear_fwd(x, W, bias, y, M, N, K):
                                          _lib.stream_ptr()), "air_linear_fwd")
 
 
+def linear_fwd_splitk(x, W, bias, y, M, N, K, scratch, splits):
+    """linear_fwd with K dealt to `splits` CTAs per output tile; `scratch`: fp64 device tensor of >= splits*M*N elements."""
+    assert scratch.dtype == torch.float64 and scratch.numel() >= splits * M * N, "split-K scratch too small"
+    _lib.check(_lib.lib().air_linear_fwd_splitk(_lib.ptr(x), _lib.ptr(W), _lib.ptr(bias), _lib.ptr(y), M, N, K,
+                                                _lib.ptr(scratch), splits, _lib.stream_ptr()), "air_linear_fwd_splitk", 2)
+
+
 def linear_bwd(x, W, dy, dx, dW, db, M, N, K):
     _lib.check(_lib.lib().air_linear_bwd(_lib.ptr(x), _lib.ptr(W), _lib.ptr(dy), _lib.ptr(dx), _lib.ptr(dW), _lib.ptr(db),
                                          M, N, K, _lib.stream_ptr()), "air_linear_bwd", 2)
@@ -610,6 +617,7 @@ stem_wgrad = _timed(stem_wgrad, "stem_wgrad")
 selfattn_pool_fwd = _timed(selfattn_pool_fwd, "pool_fwd")
 selfattn_pool_bwd = _timed(selfattn_pool_bwd, "pool_bwd")
 linear_fwd = _timed(linear_fwd, "linear")
+linear_fwd_splitk = _timed(linear_fwd_splitk, "linear")
 linear_bwd = _timed(linear_bwd, "linear")
 ocsoftmax = _timed(ocsoftmax, "ocsoftmax")
 adam_l2_step = _timed(adam_l2_step, "optim")

@@ -296,6 +296,12 @@ int air_linear_fwd(const float* x, const float* W, const float* bias, float* y, 
 int air_linear_bwd(const float* x, const float* W, const float* dy, float* dx, float* dW, float* db,
                    int M, int N, int K, air_stream_t stream);
 
+/* air_linear_fwd with the K dimension dealt to `splits` (1..64) CTAs per output tile: fp64 accumulation, fp64 partial sums
+ * in `scratch` (>= splits * M * N doubles, device), added in split order (deterministic).  For long reductions over few
+ * outputs (fc6 of ecapa_tdnn.py:148, K = 3072), where a single CTA's chain of K tiles bounds the call. */
+int air_linear_fwd_splitk(const float* x, const float* W, const float* bias, float* y, int M, int N, int K,
+                          double* scratch, int splits, air_stream_t stream);
+
 /* as above with W rows `ldw` elements apart; accumulate != 0 adds into y */
 int air_linear_fwd_ld(const float* x, const float* W, long long ldw, const float* bias, float* y, int M, int N, int K,
                       int accumulate, air_stream_t stream);

@@ -1,4 +1,5 @@
-"""Per-launch device times of one ResNet-OC train step at B=256 (CUDA events around every C-ABI call)."""
+"""Per-launch device times of one train step (default) or one scoring step (third argument `score`): CUDA events around
+every C-ABI call.   python scripts/prof_step.py [B] [resnet|ecapa] [score]"""
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -9,13 +10,15 @@ from asvspoof2021_air_b200.bench_train import _waves, _labels
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 arch = sys.argv[2] if len(sys.argv) > 2 else "resnet"
+score = len(sys.argv) > 3 and sys.argv[3] == "score"
 tr = Trainer(arch=arch, seed=688)
 w, lab = _waves(B, 0).cuda(), _labels(B, 0).cuda()
+step = (lambda: tr.score_step(w)) if score else (lambda: tr.train_step(w, lab))
 for _ in range(2):
-    tr.train_step(w, lab)
+    step()
 torch.cuda.synchronize()
 with ops.Profile() as prof:
-    tr.train_step(w, lab)
+    step()
 tot = 0.0
 for fam, ms, fl, d in prof.per_call():
     tot += ms

@@ -144,10 +144,12 @@ def test_selfattention_noise_matches_reference_scale():
     assert _rel(s1, s0) < 1e-4
 
 
-def test_linear_forward_backward():
+@pytest.mark.parametrize("M,N,K", [(17, 256, 512), (1024, 256, 3072), (37, 250, 2085), (2100, 40, 33)])
+def test_linear_forward_backward(M, N, K):
+    """Ragged tiles in all three dimensions; K >= 2048 takes the fp64-accumulator form (fc6), M >= 2048 takes it in the
+    weight-gradient product."""
     from asvspoof2021_air_b200 import ops
     g = torch.Generator().manual_seed(9)
-    M, N, K = 17, 256, 512
     x, W, b, dy = (torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5,
                    torch.randn(N, generator=g), torch.randn(M, N, generator=g))
     xr, Wr, br = x.clone().requires_grad_(True), W.clone().requires_grad_(True), b.clone().requires_grad_(True)
@@ -159,6 +161,19 @@ def test_linear_forward_backward():
     torch.cuda.synchronize()
     assert _rel(y, F.linear(x, W, b)) < 1e-5
     assert _rel(dx, xr.grad) < 1e-5 and _rel(dW, Wr.grad) < 1e-5 and _rel(db, br.grad) < 1e-5
+    # split-K form (fc6): fp64 partial sums added in split order -- within an fp32 ulp of the fp64 product for any number of
+    # splits (more splits than K tiles included), and the same bits on a second call
+    ref64 = (x.double() @ W.double().t() + b.double())
+    for splits in (1, 3, 8, 64):
+        part = torch.full((splits * M * N,), float("nan"), device="cuda", dtype=torch.float64)
+        ys, ys2 = torch.empty(M, N, device="cuda"), torch.empty(M, N, device="cuda")
+        ops.linear_fwd_splitk(x.cuda(), W.cuda(), b.cuda(), ys, M, N, K, part, splits)
+        ops.linear_fwd_splitk(x.cuda(), W.cuda(), b.cuda(), ys2, M, N, K, part, splits)
+        torch.cuda.synchronize()
+        assert torch.equal(ys, ys2)
+        assert float((ys.cpu().double() - ref64).abs().max()) <= 1.5e-7 * float(ref64.abs().max())
+        if K >= 2048:
+            assert float((ys - y).abs().max()) <= 1.5e-7 * float(ref64.abs().max())
 
 
 @pytest.mark.parametrize("B", [4, 256, 1024])
